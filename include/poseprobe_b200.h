@@ -1,0 +1,225 @@
+/*
+ * poseprobe_b200 -- C ABI of the B200-native (sm_100a) voxel-grid volume-rendering operators.
+ *
+ * This is the drop-in boundary for PoseProbe's `lib/cuda` extensions.  The reference binds its
+ * kernels through pybind11 + torch::Tensor (render_utils.cpp:170-184, total_variation.cpp:29-32,
+ * adam_upd.cpp:79-86, ub360_utils.cpp:21-23).  Here every entry point takes plain device pointers,
+ * extents and a CUDA stream, so any host (ctypes, pybind, cgo, ...) can bind it; the Python shim in
+ * poseprobe_b200/ re-creates the reference's four modules (same names, same 19 functions, same
+ * argument order and return arity) on top of it.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in `_host`;
+ *   - tensors are contiguous, row-major, in the reference's layouts ([N,3] rays, [M] samples,
+ *     [1,C,X,Y,Z] grids, int64 indices, 1-byte bools);
+ *   - `dtype` selects the storage type of the floating tensors (PP_F32 / PP_F64), mirroring the
+ *     reference's AT_DISPATCH_FLOATING_TYPES; scalars stay `float` exactly as in the reference
+ *     signatures (their fp32 rounding is part of bit-exactness);
+ *   - `stream` is a cudaStream_t (the shim passes torch's current stream; the reference used the
+ *     legacy default stream);
+ *   - every function returns PP_OK (0) or a negative pp_status; nothing is allocated inside, no
+ *     host synchronisation happens inside unless documented;
+ *   - outputs are fully written by the callee (callers need not pre-fill), including the
+ *     semantically relevant fill values of the reference (weight=0, T=1 past early termination;
+ *     alphainv_last=1, i_start=i_end=0 for rays without samples; mask=false out of range);
+ *   - there is NO CPU fallback: a host pointer is an error (PP_ERR_NOT_DEVICE where detectable).
+ */
+#ifndef POSEPROBE_B200_H_
+#define POSEPROBE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PP_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define PP_API __attribute__((visibility("default")))
+#else
+#define PP_API
+#endif
+
+typedef void* pp_stream_t; /* cudaStream_t */
+
+typedef enum pp_dtype { PP_F32 = 0, PP_F64 = 1 } pp_dtype;
+
+typedef enum pp_status {
+  PP_OK = 0,
+  PP_ERR_INVALID_ARG = -1,  /* null pointer, negative extent, unknown enum */
+  PP_ERR_CUDA = -2,         /* a CUDA runtime call / launch failed; see pp_last_error() */
+  PP_ERR_TOO_LARGE = -3,    /* extent exceeds the 32-bit sample index space of the reference */
+  PP_ERR_NOT_DEVICE = -4,   /* pointer is not device memory (no CPU fallback) */
+  PP_ERR_UNSUPPORTED = -5   /* combination not implemented (e.g. channel count) */
+} pp_status;
+
+/* --- library -------------------------------------------------------------------------------- */
+PP_API int pp_abi_version(void);
+PP_API const char* pp_last_error(void);          /* thread-local, human-readable text of the last failure */
+PP_API const char* pp_build_info(void);          /* "sm_100a nvcc x.y ..." */
+PP_API int pp_check_device_ptr(const void* p);   /* PP_OK if p is device/managed memory */
+PP_API uint64_t pp_launch_count(void);           /* kernels launched by this library so far (process-wide) */
+
+/* =============================================================================================
+ * render_utils_cuda  (reference: lib/cuda/render_utils.cpp + render_utils_kernel.cu)
+ * ============================================================================================= */
+
+/* replaces infer_t_minmax (render_utils.cpp:50; kernel :12-35).  out: t_min[n], t_max[n] */
+PP_API int pp_infer_t_minmax(pp_dtype dtype, const void* rays_o, const void* rays_d, const void* xyz_min,
+                      const void* xyz_max, float near, float far, int64_t n_rays, void* t_min,
+                      void* t_max, pp_stream_t stream);
+
+/* replaces infer_n_samples (render_utils.cpp:60; kernel :38-55).  out: n_samples[n] int64 */
+PP_API int pp_infer_n_samples(pp_dtype dtype, const void* rays_d, const void* t_min, const void* t_max,
+                       float stepdist, int64_t n_rays, int64_t* n_samples, pp_stream_t stream);
+
+/* replaces infer_ray_start_dir (render_utils.cpp:67; kernel :58-79).  out: 2 x [n,3] */
+PP_API int pp_infer_ray_start_dir(pp_dtype dtype, const void* rays_o, const void* rays_d,
+                           const void* t_min, int64_t n_rays, void* rays_start, void* rays_dir,
+                           pp_stream_t stream);
+
+/* sample_pts_on_rays (render_utils.cpp:74; host :196-242) is split in two because the number of
+ * samples M is data dependent and the caller owns all memory.
+ *
+ * Phase 1 (one kernel): per-ray t_min, t_max, N_steps, rays_start, rays_dir, the inclusive prefix
+ * sum of N_steps (`n_steps_cumsum`, int64[n], scratch the caller keeps until phase 2) and the total
+ * M written to `total_dev` (int64[1], device) AND, if `total_host_pinned` is non-null, to that
+ * pinned host word.  `scan_scratch` is int64[pp_sample_scan_scratch_elems(n_rays)] device
+ * scratch.  No host sync inside; the caller synchronises the stream and reads the total.
+ */
+PP_API int64_t pp_sample_scan_scratch_elems(int64_t n_rays);
+PP_API int pp_sample_pts_prepare(pp_dtype dtype, const void* rays_o, const void* rays_d,
+                          const void* xyz_min, const void* xyz_max, float near, float far,
+                          float stepdist, int64_t n_rays, void* t_min, void* t_max,
+                          int64_t* n_steps, int64_t* n_steps_cumsum, void* rays_start,
+                          void* rays_dir, int64_t* scan_scratch, int64_t* total_dev,
+                          int64_t* total_host_pinned, pp_stream_t stream);
+/* Phase 2 (one kernel): rays_pts[M,3], mask_outbbox[M] (bool), ray_id[M], step_id[M] (int64).
+ * Any of the four outputs may be null to skip it. */
+PP_API int pp_sample_pts_fill(pp_dtype dtype, const void* rays_start, const void* rays_dir,
+                       const void* xyz_min, const void* xyz_max, const int64_t* n_steps,
+                       const int64_t* n_steps_cumsum, float stepdist, int64_t n_rays,
+                       int64_t total, void* rays_pts, uint8_t* mask_outbbox, int64_t* ray_id,
+                       int64_t* step_id, pp_stream_t stream);
+
+/* replaces sample_ndc_pts_on_rays (render_utils.cpp:87; kernel :245-270) */
+PP_API int pp_sample_ndc_pts_on_rays(pp_dtype dtype, const void* rays_o, const void* rays_d,
+                              const void* xyz_min, const void* xyz_max, int32_t n_samples,
+                              int64_t n_rays, void* rays_pts, uint8_t* mask_outbbox,
+                              pp_stream_t stream);
+
+/* replaces sample_bg_pts_on_rays (render_utils.cpp:100; kernel :301-340) */
+PP_API int pp_sample_bg_pts_on_rays(pp_dtype dtype, const void* rays_o, const void* rays_d,
+                             const void* t_max, float bg_preserve, int32_t n_samples,
+                             int64_t n_rays, void* rays_pts, pp_stream_t stream);
+
+/* replaces maskcache_lookup (render_utils.cpp:109; kernel :374-392).  world: bool[sz_i,sz_j,sz_k] */
+PP_API int pp_maskcache_lookup(pp_dtype dtype, const uint8_t* world, const void* xyz,
+                        const void* xyz2ijk_scale, const void* xyz2ijk_shift, int32_t sz_i,
+                        int32_t sz_j, int32_t sz_k, int64_t n_pts, uint8_t* out,
+                        pp_stream_t stream);
+
+/* replaces raw2alpha / raw2alpha_nonuni (render_utils.cpp:120,:125; kernels :431-458).
+ * `interval_pts` non-null selects the per-point (nonuni) variant and `interval` is ignored. */
+PP_API int pp_raw2alpha(pp_dtype dtype, const void* density, float shift, float interval,
+                 const void* interval_pts, int64_t n_pts, void* exp_d, void* alpha,
+                 pp_stream_t stream);
+
+/* replaces raw2alpha_backward / raw2alpha_nonuni_backward (render_utils.cpp:131,:136; :507-530) */
+PP_API int pp_raw2alpha_backward(pp_dtype dtype, const void* exp_d, const void* grad_back,
+                          float interval, const void* interval_pts, int64_t n_pts, void* grad,
+                          pp_stream_t stream);
+
+/* replaces alpha2weight (render_utils.cpp:142; kernels :577-617, host :619-651).
+ * ray_id must be sorted (all samples of a ray contiguous), as the reference requires. */
+PP_API int pp_alpha2weight(pp_dtype dtype, const void* alpha, const int64_t* ray_id, int64_t n_pts,
+                    int64_t n_rays, void* weight, void* T, void* alphainv_last, int64_t* i_start,
+                    int64_t* i_end, pp_stream_t stream);
+
+/* replaces alpha2weight_backward (render_utils.cpp:151; kernel :654-677) */
+PP_API int pp_alpha2weight_backward(pp_dtype dtype, const void* alpha, const void* weight, const void* T,
+                             const void* alphainv_last, const int64_t* i_start,
+                             const int64_t* i_end, int64_t n_rays, int64_t n_pts,
+                             const void* grad_weights, const void* grad_last, void* grad,
+                             pp_stream_t stream);
+
+/* =============================================================================================
+ * total_variation_cuda  (reference: lib/cuda/total_variation.cpp + total_variation_kernel.cu)
+ * param/grad/mask: [1,C,X,Y,Z] viewed as [n_planes = C, sz_i, sz_j, sz_k]; in place on grad.
+ * `mask` null  -> total_variation_add_grad      (:16; kernel :13-35; k,j,i weights = wz,wy,wz)
+ * `mask` given -> total_variation_add_grad_new  (:22; kernel :38-66; k,j,i weights = wx,wy,wz)
+ * wx,wy,wz are the caller's values; the /6 of the reference host code (:76-78) happens inside.
+ * ============================================================================================= */
+PP_API int pp_total_variation_add_grad(pp_dtype dtype, const void* param, void* grad, const void* mask,
+                                float wx, float wy, float wz, int dense_mode, int64_t n_planes,
+                                int64_t sz_i, int64_t sz_j, int64_t sz_k, pp_stream_t stream);
+
+/* =============================================================================================
+ * adam_upd_cuda  (reference: lib/cuda/adam_upd.cpp + adam_upd_kernel.cu), all in place
+ * mode 0: adam_upd (:36)   mode 1: masked_adam_upd (:50, skip grad==0)
+ * mode 2: adam_upd_with_perlr (:64, needs perlr)
+ * ============================================================================================= */
+PP_API int pp_adam_upd(pp_dtype dtype, int mode, void* param, const void* grad, void* exp_avg,
+                void* exp_avg_sq, const void* perlr, int64_t numel, int32_t step, float beta1,
+                float beta2, float lr, float eps, pp_stream_t stream);
+
+/* =============================================================================================
+ * ub360_utils_cuda  (reference: lib/cuda/ub360_utils.cpp:15 + ub360_utils_kernel.cu:12-47)
+ * ============================================================================================= */
+PP_API int pp_cumdist_thres(pp_dtype dtype, const void* dist, float thres, int64_t n_rays, int64_t n_pts,
+                     uint8_t* mask, pp_stream_t stream);
+
+/* =============================================================================================
+ * Operators the reference runs as Python/ATen/torch_scatter composites on the same path.
+ * ============================================================================================= */
+
+/* Per-ray segmented sums: out[r,:] (+)= sum_{i: ray_id[i]==r} src[i,:]  -- the reference's
+ * torch_scatter.segment_coo(reduce='sum') call sites (voxurf_coarse.py:1034-1056, :1179-1200).
+ * `weight` (optional, [M]) multiplies src rows first (fuses the `weights.unsqueeze(-1)*rgb`
+ * products the reference materialises).  `out` is [n_rays, n_ch], overwritten. fp32 only. */
+PP_API int pp_segment_sum(const float* src, const float* weight, const int64_t* ray_id, int64_t n_pts,
+                   int32_t n_ch, int64_t n_rays, float* out, pp_stream_t stream);
+
+/* Inclusive prefix sum of src within each ray segment (the north star's `segment_cumsum`, which
+ * the reference names but does not ship; defined in SURVEY.md section 8 a12). fp32 only.
+ * `scratch` is pp_segment_cumsum_scratch_bytes(n_pts) bytes of device memory. */
+PP_API int64_t pp_segment_cumsum_scratch_bytes(int64_t n_pts);
+PP_API int pp_segment_cumsum(const float* src, const int64_t* ray_id, int64_t n_pts, float* out,
+                      void* scratch, pp_stream_t stream);
+
+/* Dense-grid trilinear interpolation == F.grid_sample(grid[1,C,X,Y,Z], mode='bilinear',
+ * align_corners=True) on ((xyz-xyz_min)/(xyz_max-xyz_min)).flip(-1)*2-1 as DenseGrid.forward does
+ * (lib/grid.py:47-58).  padding: 0 = zeros (DenseGrid), 1 = border (Voxurf.grid_sampler,
+ * voxurf_coarse.py:540).  out: [n, C] (row per point).  grad_xyz_out (optional, [n,C,3]) receives
+ * d out / d xyz analytically (what the reference obtains with autograd.grad, :972-984). fp32. */
+PP_API int pp_trilinear_forward(const float* grid, int32_t n_ch, int32_t sz_x, int32_t sz_y, int32_t sz_z,
+                         const float* xyz, int64_t n_pts, const float* xyz_min_host,
+                         const float* xyz_max_host, int padding, float* out, float* dout_dxyz,
+                         pp_stream_t stream);
+
+/* Backward of the above: grad_grid[1,C,X,Y,Z] += scatter(grad_out[n,C]) (atomic accumulate, the
+ * caller zeroes grad_grid), and optionally grad_xyz[n,3] = sum_c grad_out[n,c] * d out_c / d xyz.
+ * Either output may be null. */
+PP_API int pp_trilinear_backward(const float* grid, int32_t n_ch, int32_t sz_x, int32_t sz_y,
+                          int32_t sz_z, const float* xyz, int64_t n_pts,
+                          const float* xyz_min_host, const float* xyz_max_host, int padding,
+                          const float* grad_out, float* grad_grid, float* grad_xyz,
+                          pp_stream_t stream);
+
+/* NeuS SDF -> alpha (voxurf_coarse.py:483-519, mid-point variant) and its backward.
+ * alpha = clip((sig(prev*inv_s) - sig(next*inv_s) + 1e-5) / (sig(prev*inv_s) + 1e-5), 0, 1),
+ * prev/next = sdf -/+ iter_cos*dist*0.5, iter_cos = -relu(-(viewdirs[ray_id] . gradient)). */
+PP_API int pp_neus_alpha_forward(const float* sdf, const float* gradient, const float* viewdirs,
+                          const int64_t* ray_id, float dist, float inv_s, int64_t n_pts,
+                          float* alpha, pp_stream_t stream);
+PP_API int pp_neus_alpha_backward(const float* sdf, const float* gradient, const float* viewdirs,
+                           const int64_t* ray_id, float dist, float inv_s, int64_t n_pts,
+                           const float* grad_alpha, float* grad_sdf, float* grad_gradient,
+                           pp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POSEPROBE_B200_H_ */

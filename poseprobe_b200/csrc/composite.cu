@@ -1,0 +1,442 @@
+// Per-ray alpha compositing (alpha2weight forward / backward) and per-ray segmented reductions.
+//
+// Replaces render_utils_kernel.cu:577-707.  The reference walks each ray's segment with ONE thread
+// (`for(i=i_s; i<i_e_max; ++i)`), so a warp touches 32 different rays per step: every load/store is
+// a 32-way uncoalesced access.  The recurrences themselves are strictly sequential *and* their
+// float roundings decide an integer output (the early-termination index written back to i_end), so
+// they cannot be re-associated.  The B200 design keeps one lane per ray for the recurrence only and
+// moves all memory traffic through a shared-memory tile:
+//     stage   : for each of the warp's 32 rays, the 32 lanes load the next 32 samples (one 128 B line)
+//     chain   : lane r walks row r of the tile (padded, conflict free) - same arithmetic, same order
+//     output  : rows are written back with the 32 lanes across samples (coalesced), and everything
+//               that is not part of the recurrence (w = T*alpha, the backward's division) is done
+//               here, in parallel.
+#include "common.cuh"
+
+namespace pp {
+
+constexpr int kTile = 32;
+constexpr int kPad = kTile + 1;
+constexpr int kCompWarps = 2;  // warps per block (each warp owns an independent set of 32 rays)
+
+// ---- segment bounds from a sorted ray_id (reference :607-617 and the host line :635) -------------
+__global__ void segment_bounds_kernel(const int64_t* __restrict__ ray_id, int64_t n_pts,
+                                      int64_t n_rays, int64_t* __restrict__ i_start,
+                                      int64_t* __restrict__ i_end) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n_pts) return;
+  const int64_t cur = ray_id[i];
+  if (i > 0) {
+    const int64_t prev = ray_id[i - 1];
+    if (cur != prev) {
+      if ((uint64_t)cur < (uint64_t)n_rays) i_start[cur] = i;
+      if ((uint64_t)prev < (uint64_t)n_rays) i_end[prev] = i;
+    }
+  }
+  if (i == n_pts - 1 && (uint64_t)cur < (uint64_t)n_rays) i_end[cur] = n_pts;
+}
+
+// ---- forward -------------------------------------------------------------------------------------
+// T_cum *= (1. - alpha): double arithmetic narrowed to float each step (reference :596).
+template <typename scalar_t>
+__device__ __forceinline__ float transmit_step(float T_cum, scalar_t a) {
+  return static_cast<float>(static_cast<double>(T_cum) * (1. - static_cast<double>(a)));
+}
+
+template <typename scalar_t>
+__global__ void __launch_bounds__(kCompWarps* kWarp)
+alpha2weight_fwd_kernel(const scalar_t* __restrict__ alpha, int64_t n_rays,
+                        scalar_t* __restrict__ weight, scalar_t* __restrict__ T_out,
+                        scalar_t* __restrict__ alphainv_last, const int64_t* __restrict__ i_start,
+                        int64_t* __restrict__ i_end) {
+  __shared__ scalar_t s_a[kCompWarps][kTile][kPad];
+  __shared__ float s_T[kCompWarps][kTile][kPad];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t ray = (blockIdx.x * (int64_t)kCompWarps + w) * kTile + lane;
+  const bool live = ray < n_rays;
+  int64_t pos = live ? i_start[ray] : 0;
+  const int64_t end = live ? i_end[ray] : 0;
+  float T_cum = 1.f;
+  int64_t cut = -1;  // early-termination index (exclusive end), -1 while the ray is still marching
+
+  unsigned pending = __ballot_sync(kFull, pos < end);
+  while (pending) {
+    // stage: one coalesced line per pending ray
+    for (unsigned m = pending; m; m &= m - 1) {
+      const int k = __ffs(m) - 1;
+      const int64_t idx = __shfl_sync(kFull, pos, k) + lane;
+      if (idx < __shfl_sync(kFull, end, k)) s_a[w][k][lane] = alpha[idx];
+    }
+    __syncwarp();
+    // chain: lane r walks its own row
+    if (pos < end) {
+      const int cnt = static_cast<int>(min64(kTile, end - pos));
+      for (int j = 0; j < cnt; ++j) {
+        if (cut < 0) {
+          const scalar_t a = s_a[w][lane][j];
+          s_T[w][lane][j] = T_cum;
+          T_cum = transmit_step(T_cum, a);
+          if (T_cum < 1e-3) cut = pos + j + 1;  // float widened, compared with the double literal
+        } else {
+          s_T[w][lane][j] = 1.f;   // untouched samples keep the reference's fill values
+          s_a[w][lane][j] = 0;     //   T = 1, weight = 0
+        }
+      }
+    }
+    __syncwarp();
+    // output: rows go back coalesced; w = T * alpha is computed here
+    for (unsigned m = pending; m; m &= m - 1) {
+      const int k = __ffs(m) - 1;
+      const int64_t idx = __shfl_sync(kFull, pos, k) + lane;
+      if (idx < __shfl_sync(kFull, end, k)) {
+        const float Tv = s_T[w][k][lane];
+        weight[idx] = Tv * s_a[w][k][lane];
+        T_out[idx] = Tv;
+      }
+    }
+    __syncwarp();
+    pos += kTile;
+    pending = __ballot_sync(kFull, pos < end);
+  }
+  if (live) {
+    if (cut >= 0) i_end[ray] = cut;  // otherwise i_end already holds i_e_max (or 0 for an empty ray)
+    alphainv_last[ray] = T_cum;
+  }
+}
+
+// ---- backward ------------------------------------------------------------------------------------
+template <typename scalar_t>
+__global__ void __launch_bounds__(kCompWarps* kWarp)
+alpha2weight_bwd_kernel(const scalar_t* __restrict__ alpha, const scalar_t* __restrict__ weight,
+                        const scalar_t* __restrict__ T, const scalar_t* __restrict__ alphainv_last,
+                        const int64_t* __restrict__ i_start, const int64_t* __restrict__ i_end,
+                        int64_t n_rays, const scalar_t* __restrict__ grad_weights,
+                        const scalar_t* __restrict__ grad_last, scalar_t* __restrict__ grad) {
+  __shared__ scalar_t s_gw[kCompWarps][kTile][kPad];
+  __shared__ scalar_t s_w[kCompWarps][kTile][kPad];
+  __shared__ float s_back[kCompWarps][kTile][kPad];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t ray = (blockIdx.x * (int64_t)kCompWarps + w) * kTile + lane;
+  const bool live = ray < n_rays;
+  const int64_t begin = live ? i_start[ray] : 0;
+  int64_t hi = live ? i_end[ray] : 0;  // exclusive; the tile covers (hi-32, hi], walked downwards
+  // back_cum = grad_last * alphainv_last (reference :671)
+  float back = live ? static_cast<float>(grad_last[ray] * alphainv_last[ray]) : 0.f;
+
+  unsigned pending = __ballot_sync(kFull, begin < hi);
+  while (pending) {
+    for (unsigned m = pending; m; m &= m - 1) {
+      const int k = __ffs(m) - 1;
+      const int64_t idx = __shfl_sync(kFull, hi, k) - 1 - lane;
+      if (idx >= __shfl_sync(kFull, begin, k)) {
+        s_gw[w][k][lane] = grad_weights[idx];
+        s_w[w][k][lane] = weight[idx];
+      }
+    }
+    __syncwarp();
+    if (begin < hi) {
+      const int cnt = static_cast<int>(min64(kTile, hi - begin));
+      for (int j = 0; j < cnt; ++j) {
+        s_back[w][lane][j] = back;
+        // back_cum += grad_weights*weight : FMA in scalar_t, narrowed to float (reference :674)
+        back = static_cast<float>(fma_rn(s_gw[w][lane][j], s_w[w][lane][j], static_cast<scalar_t>(back)));
+      }
+    }
+    __syncwarp();
+    for (unsigned m = pending; m; m &= m - 1) {
+      const int k = __ffs(m) - 1;
+      const int64_t idx = __shfl_sync(kFull, hi, k) - 1 - lane;
+      if (idx >= __shfl_sync(kFull, begin, k)) {
+        // grad = gw*T - back/(1-alpha+1e-10): product in scalar_t, quotient and difference in double
+        const scalar_t gT = mul_rn(s_gw[w][k][lane], T[idx]);
+        const scalar_t one_minus = scalar_t(1) - alpha[idx];
+        const double q = static_cast<double>(s_back[w][k][lane]) / (static_cast<double>(one_minus) + 1e-10);
+        grad[idx] = static_cast<scalar_t>(static_cast<double>(gT) - q);
+      }
+    }
+    __syncwarp();
+    hi -= kTile;
+    pending = __ballot_sync(kFull, begin < hi);
+  }
+}
+
+// ---- per-ray segmented sum (torch_scatter.segment_coo(reduce='sum') call sites) -------------------
+// One thread per sample, warp-level segmented reduction keyed by ray_id, one atomic per (warp, ray).
+__global__ void segment_sum_kernel(const float* __restrict__ src, const float* __restrict__ weight,
+                                   const int64_t* __restrict__ ray_id, int64_t n_pts, int n_ch,
+                                   int64_t n_rays, float* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool valid = i < n_pts;
+  const int64_t rid = valid ? ray_id[i] : -1;
+  const float wv = (valid && weight) ? weight[i] : 1.f;
+  // head of a run of equal ray ids inside this warp
+  const int64_t prev = __shfl_up_sync(kFull, rid, 1);
+  const bool head = (lane == 0) || (prev != rid);
+  const unsigned heads = __ballot_sync(kFull, head);
+  // index of the lane after the end of my run
+  const unsigned after = heads & ~((2u << lane) - 1u);           // heads strictly above my lane
+  const int run_end = after ? (__ffs(after) - 1) : 32;            // exclusive
+  for (int c = 0; c < n_ch; ++c) {
+    float v = valid ? src[i * n_ch + c] * wv : 0.f;
+    // segmented suffix-sum by doubling: lane adds lane+o if it is still inside its run
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float up = __shfl_down_sync(kFull, v, o);
+      if (lane + o < run_end) v += up;
+    }
+    if (head && valid && (uint64_t)rid < (uint64_t)n_rays) atomicAdd(&out[rid * n_ch + c], v);
+  }
+}
+
+// ---- per-ray segmented inclusive prefix sum ("segment_cumsum") -------------------------------------
+// Two passes over blocks of kScanElems samples.  Pass 1 records, per block, the sum of its trailing
+// open segment and whether the block contains a segment head; pass 2 rebuilds each block's carry-in
+// by looking back over those summaries and performs the in-block segmented scan.
+constexpr int kScanThreads = 256;
+constexpr int kScanPerThread = 4;
+constexpr int kScanElems = kScanThreads * kScanPerThread;
+
+__device__ __forceinline__ bool is_head(const int64_t* ray_id, int64_t i) {
+  return i == 0 || ray_id[i] != ray_id[i - 1];
+}
+
+// segmented inclusive scan of (v, f) pairs across a block; returns the inclusive value for each of the
+// thread's kScanPerThread consecutive elements. `carry` is added to elements before the first head.
+__device__ __forceinline__ void block_segscan(float v[kScanPerThread], bool h[kScanPerThread],
+                                              float carry, float& tail_sum, bool& any_head) {
+  __shared__ float s_val[kScanThreads / kWarp];
+  __shared__ int s_flag[kScanThreads / kWarp];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // thread-local
+  float acc = 0.f;
+  bool f = false;
+#pragma unroll
+  for (int e = 0; e < kScanPerThread; ++e) {
+    if (h[e]) { acc = 0.f; f = true; }
+    acc += v[e];
+    v[e] = acc;
+  }
+  // warp-level segmented scan on (acc, f)
+  float x = acc;
+  int fl = f;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float ux = __shfl_up_sync(kFull, x, o);
+    const int uf = __shfl_up_sync(kFull, fl, o);
+    if (lane >= o) {
+      if (!fl) x += ux;
+      fl |= uf;
+    }
+  }
+  if (lane == 31) { s_val[warp] = x; s_flag[warp] = fl; }
+  __syncthreads();
+  // prefix from previous warps
+  float wpre = 0.f;
+  int wflag = 0;
+  for (int q = 0; q < warp; ++q) {
+    if (s_flag[q]) { wpre = s_val[q]; wflag = 1; } else { wpre += s_val[q]; }
+  }
+  // exclusive (previous-thread) prefix inside the warp
+  float px = __shfl_up_sync(kFull, x, 1);
+  int pf = __shfl_up_sync(kFull, fl, 1);
+  if (lane == 0) { px = 0.f; pf = 0; }
+  float pre = pf ? px : (px + wpre);
+  const bool pre_flag = pf || wflag;
+  if (!pre_flag) pre += carry;
+  // apply to the thread's elements that precede its first local head
+#pragma unroll
+  for (int e = 0; e < kScanPerThread; ++e) {
+    if (h[e]) break;
+    v[e] += pre;
+  }
+  // block summary
+  float tot = 0.f;
+  int anyf = 0;
+  for (int q = 0; q < kScanThreads / kWarp; ++q) {
+    if (s_flag[q]) { tot = s_val[q]; anyf = 1; } else { tot += s_val[q]; }
+  }
+  tail_sum = tot;
+  any_head = anyf;
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+segcumsum_summary_kernel(const float* __restrict__ src, const int64_t* __restrict__ ray_id,
+                         int64_t n_pts, float* __restrict__ blk_tail, int* __restrict__ blk_head) {
+  const int64_t base = blockIdx.x * (int64_t)kScanElems + threadIdx.x * kScanPerThread;
+  float v[kScanPerThread];
+  bool h[kScanPerThread];
+#pragma unroll
+  for (int e = 0; e < kScanPerThread; ++e) {
+    const int64_t i = base + e;
+    v[e] = i < n_pts ? src[i] : 0.f;
+    h[e] = i < n_pts ? is_head(ray_id, i) : false;
+  }
+  float tail;
+  bool any;
+  block_segscan(v, h, 0.f, tail, any);
+  if (threadIdx.x == 0) {
+    blk_tail[blockIdx.x] = tail;
+    blk_head[blockIdx.x] = any;
+  }
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+segcumsum_apply_kernel(const float* __restrict__ src, const int64_t* __restrict__ ray_id,
+                       int64_t n_pts, const float* __restrict__ blk_tail,
+                       const int* __restrict__ blk_head, float* __restrict__ out) {
+  __shared__ float s_carry;
+  if (threadIdx.x == 0) {
+    // carry-in = tails of the previous blocks back to (and including) the nearest one with a head,
+    // accumulated in forward order so the result does not depend on the block size
+    int first = (int)blockIdx.x;
+    while (first > 0) {
+      --first;
+      if (blk_head[first]) break;
+    }
+    float c = 0.f;
+    for (int b = first; b < (int)blockIdx.x; ++b) c += blk_tail[b];
+    s_carry = c;
+  }
+  __syncthreads();
+  const int64_t base = blockIdx.x * (int64_t)kScanElems + threadIdx.x * kScanPerThread;
+  float v[kScanPerThread];
+  bool h[kScanPerThread];
+#pragma unroll
+  for (int e = 0; e < kScanPerThread; ++e) {
+    const int64_t i = base + e;
+    v[e] = i < n_pts ? src[i] : 0.f;
+    h[e] = i < n_pts ? is_head(ray_id, i) : false;
+  }
+  float tail;
+  bool any;
+  block_segscan(v, h, s_carry, tail, any);
+#pragma unroll
+  for (int e = 0; e < kScanPerThread; ++e) {
+    const int64_t i = base + e;
+    if (i < n_pts) out[i] = v[e];
+  }
+}
+
+}  // namespace pp
+
+using namespace pp;
+
+#define PP_DISPATCH(dtype, ...)                                 \
+  do {                                                          \
+    if ((dtype) == PP_F32) {                                    \
+      using scalar_t = float;                                   \
+      __VA_ARGS__                                               \
+    } else if ((dtype) == PP_F64) {                             \
+      using scalar_t = double;                                  \
+      __VA_ARGS__                                               \
+    } else {                                                    \
+      set_error("unknown dtype %d", (int)(dtype));              \
+      return PP_ERR_INVALID_ARG;                                \
+    }                                                           \
+  } while (0)
+
+template <typename scalar_t>
+static __global__ void fill_kernel(scalar_t* p, scalar_t v, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+extern "C" int pp_alpha2weight(pp_dtype dtype, const void* alpha, const int64_t* ray_id,
+                               int64_t n_pts, int64_t n_rays, void* weight, void* T,
+                               void* alphainv_last, int64_t* i_start, int64_t* i_end,
+                               pp_stream_t stream) {
+  PP_REQUIRE(n_pts >= 0 && n_rays >= 0, PP_ERR_INVALID_ARG, "alpha2weight: negative extent");
+  PP_REQUIRE(n_pts <= INT32_MAX, PP_ERR_TOO_LARGE, "alpha2weight: n_pts exceeds 32-bit index space");
+  cudaStream_t s = as_stream(stream);
+  if (n_rays == 0) return PP_OK;
+  PP_REQUIRE(alphainv_last && i_start && i_end, PP_ERR_INVALID_ARG, "alpha2weight: null pointer");
+  PP_CHECK_CUDA(cudaMemsetAsync(i_start, 0, sizeof(int64_t) * n_rays, s));
+  PP_CHECK_CUDA(cudaMemsetAsync(i_end, 0, sizeof(int64_t) * n_rays, s));
+  if (n_pts == 0) {
+    // reference early return (:629-631): alphainv_last = 1, i_start = i_end = 0
+    PP_DISPATCH(dtype, {
+      fill_kernel<scalar_t><<<ceil_div(n_rays, 256), 256, 0, s>>>((scalar_t*)alphainv_last,
+                                                                 scalar_t(1), n_rays);
+    });
+    PP_CHECK_LAUNCH("alpha2weight(fill)");
+    return PP_OK;
+  }
+  PP_REQUIRE(alpha && ray_id && weight && T, PP_ERR_INVALID_ARG, "alpha2weight: null pointer");
+  segment_bounds_kernel<<<ceil_div(n_pts, 256), 256, 0, s>>>(ray_id, n_pts, n_rays, i_start, i_end);
+  PP_CHECK_LAUNCH("alpha2weight(bounds)");
+  const int rays_per_block = kCompWarps * kTile;
+  PP_DISPATCH(dtype, {
+    alpha2weight_fwd_kernel<scalar_t><<<ceil_div(n_rays, rays_per_block), kCompWarps * kWarp, 0, s>>>(
+        (const scalar_t*)alpha, n_rays, (scalar_t*)weight, (scalar_t*)T, (scalar_t*)alphainv_last,
+        i_start, i_end);
+  });
+  PP_CHECK_LAUNCH("alpha2weight");
+  return PP_OK;
+}
+
+extern "C" int pp_alpha2weight_backward(pp_dtype dtype, const void* alpha, const void* weight,
+                                        const void* T, const void* alphainv_last,
+                                        const int64_t* i_start, const int64_t* i_end,
+                                        int64_t n_rays, int64_t n_pts, const void* grad_weights,
+                                        const void* grad_last, void* grad, pp_stream_t stream) {
+  PP_REQUIRE(n_pts >= 0 && n_rays >= 0, PP_ERR_INVALID_ARG, "alpha2weight_backward: negative extent");
+  if (n_pts == 0) return PP_OK;
+  PP_REQUIRE(grad, PP_ERR_INVALID_ARG, "alpha2weight_backward: grad is null");
+  cudaStream_t s = as_stream(stream);
+  const size_t esz = dtype == PP_F64 ? 8 : 4;
+  // samples past a ray's early-termination index get zero gradient (reference: zeros_like, :684)
+  PP_CHECK_CUDA(cudaMemsetAsync(grad, 0, esz * n_pts, s));
+  if (n_rays == 0) return PP_OK;
+  PP_REQUIRE(alpha && weight && T && alphainv_last && i_start && i_end && grad_weights && grad_last,
+             PP_ERR_INVALID_ARG, "alpha2weight_backward: null pointer");
+  const int rays_per_block = kCompWarps * kTile;
+  PP_DISPATCH(dtype, {
+    alpha2weight_bwd_kernel<scalar_t><<<ceil_div(n_rays, rays_per_block), kCompWarps * kWarp, 0, s>>>(
+        (const scalar_t*)alpha, (const scalar_t*)weight, (const scalar_t*)T,
+        (const scalar_t*)alphainv_last, i_start, i_end, n_rays, (const scalar_t*)grad_weights,
+        (const scalar_t*)grad_last, (scalar_t*)grad);
+  });
+  PP_CHECK_LAUNCH("alpha2weight_backward");
+  return PP_OK;
+}
+
+extern "C" int pp_segment_sum(const float* src, const float* weight, const int64_t* ray_id,
+                              int64_t n_pts, int32_t n_ch, int64_t n_rays, float* out,
+                              pp_stream_t stream) {
+  PP_REQUIRE(n_pts >= 0 && n_rays >= 0 && n_ch >= 1, PP_ERR_INVALID_ARG, "segment_sum: bad extent");
+  if (n_rays == 0) return PP_OK;
+  PP_REQUIRE(out, PP_ERR_INVALID_ARG, "segment_sum: out is null");
+  cudaStream_t s = as_stream(stream);
+  PP_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * n_rays * n_ch, s));
+  if (n_pts == 0) return PP_OK;
+  PP_REQUIRE(src && ray_id, PP_ERR_INVALID_ARG, "segment_sum: null pointer");
+  segment_sum_kernel<<<ceil_div(n_pts, 256), 256, 0, s>>>(src, weight, ray_id, n_pts, n_ch,
+                                                             n_rays, out);
+  PP_CHECK_LAUNCH("segment_sum");
+  return PP_OK;
+}
+
+extern "C" int64_t pp_segment_cumsum_scratch_bytes(int64_t n_pts) {
+  const int64_t blocks = (n_pts + kScanElems - 1) / kScanElems;
+  return blocks * (int64_t)(sizeof(float) + sizeof(int));
+}
+
+extern "C" int pp_segment_cumsum(const float* src, const int64_t* ray_id, int64_t n_pts,
+                                 float* out, void* scratch, pp_stream_t stream) {
+  PP_REQUIRE(n_pts >= 0, PP_ERR_INVALID_ARG, "segment_cumsum: n_pts < 0");
+  if (n_pts == 0) return PP_OK;
+  PP_REQUIRE(src && ray_id && out && scratch, PP_ERR_INVALID_ARG, "segment_cumsum: null pointer");
+  cudaStream_t s = as_stream(stream);
+  const int64_t blocks = (n_pts + kScanElems - 1) / kScanElems;
+  float* blk_tail = reinterpret_cast<float*>(scratch);
+  int* blk_head = reinterpret_cast<int*>(blk_tail + blocks);
+  segcumsum_summary_kernel<<<(unsigned)blocks, kScanThreads, 0, s>>>(src, ray_id, n_pts, blk_tail,
+                                                                     blk_head);
+  PP_CHECK_LAUNCH("segment_cumsum(summary)");
+  segcumsum_apply_kernel<<<(unsigned)blocks, kScanThreads, 0, s>>>(src, ray_id, n_pts, blk_tail,
+                                                                   blk_head, out);
+  PP_CHECK_LAUNCH("segment_cumsum");
+  return PP_OK;
+}

@@ -1,0 +1,192 @@
+"""Autograd-aware operators on top of the C ABI.
+
+Mirrors the reference's Python-side glue for the hot path:
+  * ``Alphas2Weights``   -- lib/voxurf_coarse.py:1316-1332 (same class name / apply signature)
+  * ``Raw2Alpha``        -- upstream DVGO's autograd wrapper around raw2alpha (the kernels exist in the
+                            reference, render_utils.cpp:120-140, the wrapper was dropped)
+  * ``trilinear``        -- DenseGrid.forward's F.grid_sample (lib/grid.py:47-58) as one gather kernel
+                            forward and one scatter kernel backward
+  * ``segment_sum``      -- torch_scatter.segment_coo(reduce='sum') call sites, voxurf_coarse.py:1034-1056
+  * ``segment_cumsum``   -- per-ray inclusive prefix sum
+  * ``neus_alpha``       -- neus_alpha_from_sdf_scatter, voxurf_coarse.py:483-519
+"""
+import torch
+
+from . import render_utils_cuda
+from ._lib import check, lib, ptr, stream
+
+
+class Alphas2Weights(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, alpha, ray_id, N):
+        weights, T, alphainv_last, i_start, i_end = render_utils_cuda.alpha2weight(alpha, ray_id, N)
+        if alpha.requires_grad:
+            ctx.save_for_backward(alpha, weights, T, alphainv_last, i_start, i_end)
+            ctx.n_rays = N
+        return weights, alphainv_last
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_weights, grad_last):
+        alpha, weights, T, alphainv_last, i_start, i_end = ctx.saved_tensors
+        grad = render_utils_cuda.alpha2weight_backward(
+            alpha, weights, T, alphainv_last, i_start, i_end, ctx.n_rays,
+            grad_weights.contiguous(), grad_last.contiguous())
+        return grad, None, None
+
+
+class Raw2Alpha(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, density, shift, interval):
+        exp_d, alpha = render_utils_cuda.raw2alpha(density, shift, interval)
+        if density.requires_grad:
+            ctx.save_for_backward(exp_d)
+            ctx.interval = interval
+        return alpha
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_back):
+        (exp_d,) = ctx.saved_tensors
+        return render_utils_cuda.raw2alpha_backward(exp_d, grad_back.contiguous(), ctx.interval), None, None
+
+
+def _host3(t):
+    v = t.detach().to("cpu", torch.float32).contiguous()
+    assert v.numel() == 3
+    return v
+
+
+class _Trilinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, grid, xyz, mn_host, mx_host, padding):
+        if not grid.is_cuda or not xyz.is_cuda:
+            raise RuntimeError("trilinear: grid and xyz must be CUDA tensors (no CPU fallback)")
+        if grid.dtype != torch.float32 or xyz.dtype != torch.float32:
+            raise RuntimeError('"trilinear" not implemented for non-float32 tensors')
+        grid_c = grid.contiguous()
+        pts = xyz.reshape(-1, 3).contiguous()
+        _, c, x, y, z = grid_c.shape
+        n = pts.shape[0]
+        out = torch.empty((n, c), dtype=torch.float32, device=grid.device)
+        with torch.cuda.device(grid.device):
+            check(lib.pp_trilinear_forward(ptr(grid_c), c, x, y, z, ptr(pts), n, ptr(mn_host), ptr(mx_host),
+                                           padding, ptr(out), None, stream()), "trilinear_forward")
+        ctx.save_for_backward(grid_c, pts)
+        ctx.geom = (mn_host, mx_host, padding, xyz.shape)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        grid_c, pts = ctx.saved_tensors
+        mn_host, mx_host, padding, xyz_shape = ctx.geom
+        _, c, x, y, z = grid_c.shape
+        n = pts.shape[0]
+        grad_out = grad_out.contiguous()
+        need_grid, need_xyz = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        grad_grid = torch.zeros_like(grid_c) if need_grid else None
+        grad_xyz = torch.empty_like(pts) if need_xyz else None
+        with torch.cuda.device(grid_c.device):
+            check(lib.pp_trilinear_backward(ptr(grid_c), c, x, y, z, ptr(pts), n, ptr(mn_host), ptr(mx_host),
+                                            padding, ptr(grad_out), ptr(grad_grid), ptr(grad_xyz), stream()),
+                  "trilinear_backward")
+        if grad_xyz is not None:
+            grad_xyz = grad_xyz.reshape(xyz_shape)
+        return grad_grid, grad_xyz, None, None, None
+
+
+def trilinear(grid, xyz, xyz_min, xyz_max, padding_mode="zeros"):
+    """grid [1,C,X,Y,Z], xyz [...,3] (world) -> [prod(...), C]; differentiable in grid and xyz."""
+    padding = {"zeros": 0, "border": 1}[padding_mode]
+    return _Trilinear.apply(grid, xyz, _host3(xyz_min), _host3(xyz_max), padding)
+
+
+def trilinear_with_grad(grid, xyz, xyz_min, xyz_max, padding_mode="zeros"):
+    """Value [n,C] and analytic spatial gradient d value / d xyz [n,C,3] in one gather (no autograd)."""
+    padding = {"zeros": 0, "border": 1}[padding_mode]
+    grid_c = grid.detach().contiguous()
+    pts = xyz.detach().reshape(-1, 3).contiguous()
+    _, c, x, y, z = grid_c.shape
+    n = pts.shape[0]
+    out = torch.empty((n, c), dtype=torch.float32, device=grid.device)
+    dxyz = torch.empty((n, c, 3), dtype=torch.float32, device=grid.device)
+    mn, mx = _host3(xyz_min), _host3(xyz_max)
+    with torch.cuda.device(grid.device):
+        check(lib.pp_trilinear_forward(ptr(grid_c), c, x, y, z, ptr(pts), n, ptr(mn), ptr(mx), padding,
+                                       ptr(out), ptr(dxyz), stream()), "trilinear_forward")
+    return out, dxyz
+
+
+class _SegmentSum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, ray_id, n_rays):
+        s2 = src.reshape(src.shape[0], -1).contiguous()
+        out = torch.empty((n_rays, s2.shape[1]), dtype=torch.float32, device=src.device)
+        with torch.cuda.device(src.device):
+            check(lib.pp_segment_sum(ptr(s2), None, ptr(ray_id), s2.shape[0], s2.shape[1], n_rays, ptr(out),
+                                     stream()), "segment_sum")
+        ctx.save_for_backward(ray_id)
+        ctx.src_shape = src.shape
+        return out.reshape((n_rays,) + tuple(src.shape[1:]))
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        (ray_id,) = ctx.saved_tensors
+        return grad_out[ray_id].reshape(ctx.src_shape), None, None
+
+
+def segment_sum(src, ray_id, n_rays):
+    """out[r] = sum of src rows whose ray_id == r  (segment_coo(reduce='sum') with sorted index)."""
+    if not src.is_cuda:
+        raise RuntimeError("segment_sum: src must be a CUDA tensor (no CPU fallback)")
+    return _SegmentSum.apply(src.float(), ray_id, n_rays)
+
+
+def segment_cumsum(src, ray_id):
+    """Inclusive prefix sum of src [M] restarted at every ray boundary."""
+    if not src.is_cuda:
+        raise RuntimeError("segment_cumsum: src must be a CUDA tensor (no CPU fallback)")
+    src = src.float().contiguous()
+    out = torch.empty_like(src)
+    n = src.numel()
+    scratch = torch.empty(max(int(lib.pp_segment_cumsum_scratch_bytes(n)), 8), dtype=torch.uint8,
+                          device=src.device)
+    with torch.cuda.device(src.device):
+        check(lib.pp_segment_cumsum(ptr(src), ptr(ray_id), n, ptr(out), ptr(scratch), stream()),
+              "segment_cumsum")
+    return out
+
+
+class _NeusAlpha(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sdf, gradient, viewdirs, ray_id, dist, inv_s):
+        sdf, gradient, viewdirs = sdf.contiguous(), gradient.contiguous(), viewdirs.contiguous()
+        alpha = torch.empty_like(sdf)
+        with torch.cuda.device(sdf.device):
+            check(lib.pp_neus_alpha_forward(ptr(sdf), ptr(gradient), ptr(viewdirs), ptr(ray_id), dist, inv_s,
+                                            sdf.numel(), ptr(alpha), stream()), "neus_alpha_forward")
+        ctx.save_for_backward(sdf, gradient, viewdirs, ray_id)
+        ctx.consts = (dist, inv_s)
+        return alpha
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_alpha):
+        sdf, gradient, viewdirs, ray_id = ctx.saved_tensors
+        dist, inv_s = ctx.consts
+        g_sdf = torch.empty_like(sdf)
+        g_grad = torch.empty_like(gradient)
+        with torch.cuda.device(sdf.device):
+            check(lib.pp_neus_alpha_backward(ptr(sdf), ptr(gradient), ptr(viewdirs), ptr(ray_id), dist, inv_s,
+                                             sdf.numel(), ptr(grad_alpha.contiguous()), ptr(g_sdf), ptr(g_grad),
+                                             stream()), "neus_alpha_backward")
+        return g_sdf, g_grad, None, None, None, None
+
+
+def neus_alpha(viewdirs, ray_id, dist, sdf, gradients, inv_s):
+    """alpha [M] from SDF values and gradients (NeuS mid-point rule); differentiable in sdf, gradients."""
+    if not sdf.is_cuda:
+        raise RuntimeError("neus_alpha: sdf must be a CUDA tensor (no CPU fallback)")
+    return _NeusAlpha.apply(sdf, gradients, viewdirs, ray_id, float(dist), float(inv_s))
