@@ -1,0 +1,179 @@
+"""CPU tier: known-answer tests that pin the oracle on tiny hand-computable inputs, closed forms the
+reference's Python code states (cumprod compositing, softplus form of raw2alpha, Python Adam), and
+structural properties."""
+import math
+
+import pytest
+import torch
+
+from oracle import oracle
+from tests import cases
+
+
+def test_sampling_known_answers():
+    # one axis-aligned ray through the unit box: enters at z=-1 (t=2), leaves at z=1 (t=4)
+    o = torch.tensor([[0.0, 0.0, -3.0]])
+    d = torch.tensor([[0.0, 0.0, 1.0]])
+    mn, mx = cases.bbox()
+    t_min, t_max = oracle.infer_t_minmax(o, d, mn, mx, 0.2, 1e9)
+    assert t_min.item() == 2.0 and t_max.item() == 4.0
+    # zero components are replaced by 1e-6: the x/y slabs become (-1e6, 1e6)
+    n = oracle.infer_n_samples(d, t_min, t_max, 0.5)
+    assert n.item() == 4
+    pts, mask, ray_id, step_id, n_steps, *_ = oracle.sample_pts_on_rays(o, d, mn, mx, 0.2, 1e9, 0.5)
+    assert pts[:, 2].tolist() == [-1.0, -0.5, 0.0, 0.5]
+    assert mask.tolist() == [False] * 4          # strict comparisons: the face itself is inside
+    assert ray_id.tolist() == [0] * 4 and step_id.tolist() == [0, 1, 2, 3]
+    # a ray that misses still gets one (out-of-box) sample
+    o2 = torch.tensor([[5.0, 5.0, 5.0]])
+    d2 = torch.tensor([[1.0, 0.0, 0.0]])
+    pts, mask, ray_id, step_id, n_steps, t_min, t_max, *_ = oracle.sample_pts_on_rays(o2, d2, mn, mx, 0.2, 1e9, 0.5)
+    assert n_steps.tolist() == [1] and mask.tolist() == [True] and t_max.item() <= t_min.item()
+
+
+def test_sampling_matches_dense_python_sampler():
+    """Points of the enumerating sampler are the in-box prefix of the reference's dense sampler
+    (lib/dvgo_ori.py:263-287, no jitter)."""
+    o, d = cases.rays_with_edge_cases(64, seed=2)
+    d = d / d.norm(dim=-1, keepdim=True)
+    mn, mx = cases.bbox()
+    stepdist = 0.03
+    pts, mask, ray_id, step_id, n_steps, t_min, t_max, start, rdir = oracle.sample_pts_on_rays(
+        o, d, mn, mx, 0.2, 1e9, stepdist)
+    vec = torch.where(d == 0, torch.full_like(d, 1e-6), d)
+    ra, rb = (mx - o) / vec, (mn - o) / vec
+    tmin_py = torch.minimum(ra, rb).amax(-1).clamp(min=0.2, max=1e9)
+    tmax_py = torch.maximum(ra, rb).amin(-1).clamp(min=0.2, max=1e9)
+    assert torch.equal(t_min, tmin_py) and torch.equal(t_max, tmax_py)
+    interp = t_min[ray_id] + stepdist * step_id / d.norm(dim=-1)[ray_id]
+    pts_py = o[ray_id] + d[ray_id] * interp[:, None]
+    torch.testing.assert_close(pts, pts_py, rtol=1e-5, atol=1e-5)
+
+
+def test_raw2alpha_equals_softplus_form():
+    """raw2alpha == 1 - exp(-softplus(d + shift) * interval)  (lib/dvgo_ori.py:242-244)."""
+    d = torch.linspace(-12, 12, 997)
+    shift, interval = -4.595, 0.5
+    exp_d, alpha = oracle.raw2alpha(d, shift, interval)
+    want = 1 - torch.exp(-torch.nn.functional.softplus(d.double() + shift) * interval)
+    torch.testing.assert_close(alpha.double(), want, rtol=1e-4, atol=1e-6)
+    # backward == autograd of the closed form
+    dd = d.double().requires_grad_(True)
+    a = 1 - torch.exp(-torch.nn.functional.softplus(dd + shift) * interval)
+    gb = torch.cos(d)
+    a.backward(gb.double())
+    grad = oracle.raw2alpha_backward(exp_d, gb, interval)
+    torch.testing.assert_close(grad.double(), dd.grad, rtol=1e-4, atol=1e-7)
+
+
+def test_alpha2weight_known_answers():
+    alpha = torch.tensor([0.5, 0.5, 0.5, 0.25])
+    ray_id = torch.tensor([0, 0, 0, 2])
+    w, T, last, i_s, i_e = oracle.alpha2weight(alpha, ray_id, 3)
+    assert w.tolist() == [0.5, 0.25, 0.125, 0.25]
+    assert T.tolist() == [1.0, 0.5, 0.25, 1.0]
+    assert last.tolist() == [0.125, 1.0, 0.75]
+    assert i_s.tolist() == [0, 0, 3] and i_e.tolist() == [3, 0, 4]     # ray 1 has no samples
+    # early termination: T < 1e-3 after the 2nd sample -> i_end rewritten, tail keeps fill values
+    alpha = torch.tensor([0.99, 0.99, 0.5, 0.5])
+    w, T, last, i_s, i_e = oracle.alpha2weight(alpha, torch.zeros(4, dtype=torch.int64), 1)
+    assert i_e.tolist() == [2]
+    assert w[2:].tolist() == [0.0, 0.0] and T[2:].tolist() == [1.0, 1.0]
+    assert last.item() == pytest.approx(1e-4, rel=1e-5)
+
+
+def test_alpha2weight_equals_cumprod_compositing():
+    """Without early termination: weights == alpha * cumprod_exclusive(1-alpha) (dvgo_ori.py:478-485)."""
+    g = torch.Generator().manual_seed(0)
+    alpha = torch.rand(20, 30, generator=g) * 0.03
+    ray_id = torch.arange(20).repeat_interleave(30)
+    w, T, last, _, i_e = oracle.alpha2weight(alpha.reshape(-1), ray_id, 20)
+    wd, cum = oracle.get_ray_marching_ray(alpha)
+    torch.testing.assert_close(w.reshape(20, 30), wd, rtol=1e-5, atol=1e-8)
+    torch.testing.assert_close(last, cum[:, -1], rtol=1e-5, atol=1e-8)
+    assert i_e.tolist() == list(range(30, 601, 30))
+
+
+def test_alpha2weight_backward_equals_autograd():
+    g = torch.Generator().manual_seed(1)
+    alpha = torch.rand(11, 17, generator=g) * 0.05
+    ray_id = torch.arange(11).repeat_interleave(17)
+    fwd = oracle.alpha2weight(alpha.reshape(-1), ray_id, 11)
+    gw = torch.randn(11 * 17, generator=g)
+    gl = torch.randn(11, generator=g)
+    grad = oracle.alpha2weight_backward(alpha.reshape(-1), *fwd, 11, gw, gl)
+    a = alpha.double().requires_grad_(True)
+    wd, cum = oracle.get_ray_marching_ray(a)
+    ((wd.reshape(-1) * gw.double()).sum() + (cum[:, -1] * gl.double()).sum()).backward()
+    torch.testing.assert_close(grad.double(), a.grad.reshape(-1), rtol=1e-4, atol=1e-6)
+
+
+def test_total_variation_axis_quirks():
+    """Old kernel: (k, j, i) weights = (wz, wy, wz); new kernel: (wx, wy, wz) -- SURVEY.md A14."""
+    p = torch.zeros(1, 1, 3, 3, 3)
+    p[0, 0, 1, 1, 1] = 0.6
+    for masked in (False, True):
+        grad = torch.zeros_like(p)
+        mask = torch.ones_like(p) if masked else None
+        oracle.total_variation_add_grad(p, grad, 6 * 1.0, 6 * 10.0, 6 * 100.0, True, mask)
+        wk = 1.0 if masked else 100.0
+        centre = 2 * 0.6 * (wk + 10.0 + 100.0)
+        assert grad[0, 0, 1, 1, 1].item() == pytest.approx(centre, rel=1e-6)
+        assert grad[0, 0, 1, 1, 0].item() == pytest.approx(-0.6 * wk, rel=1e-6)      # k neighbour
+        assert grad[0, 0, 1, 0, 1].item() == pytest.approx(-0.6 * 10.0, rel=1e-6)    # j neighbour
+        assert grad[0, 0, 0, 1, 1].item() == pytest.approx(-0.6 * 100.0, rel=1e-6)   # i neighbour
+    # clamp to [-1, 1] and sparse mode
+    p = torch.zeros(1, 1, 1, 1, 2)
+    p[..., 1] = 5.0
+    grad = torch.tensor([0.0, 1.0]).reshape(1, 1, 1, 1, 2)
+    oracle.total_variation_add_grad(p, grad, 6.0, 6.0, 6.0, False)
+    assert grad.flatten().tolist() == [0.0, 2.0]     # first voxel skipped (grad == 0), second += clamp(5)=1
+
+
+def test_adam_kernel_vs_python_adam():
+    """The kernel's update differs from lib/utils.py:176-198 only in where eps enters; with eps = 0 they
+    agree, and masked mode leaves zero-grad elements untouched."""
+    g = torch.Generator().manual_seed(2)
+    p = torch.randn(100, generator=g)
+    grad = torch.randn(100, generator=g)
+    grad[::3] = 0
+    m = torch.randn(100, generator=g) * 0.1
+    v = torch.rand(100, generator=g) * 0.01 + 1e-4
+    kp, km, kv = p.clone(), m.clone(), v.clone()
+    oracle.adam_upd(0, kp, grad, km, kv, None, 5, 0.9, 0.99, 0.01, 0.0)
+    pp_, pm, pv = p.clone().double(), m.clone().double(), v.clone().double()
+    oracle.python_adam_step(pp_, grad.double(), pm, pv, 5, 0.9, 0.99, 0.01, 0.0)
+    torch.testing.assert_close(kp.double(), pp_, rtol=1e-5, atol=1e-7)
+    kp2, km2, kv2 = p.clone(), m.clone(), v.clone()
+    oracle.adam_upd(1, kp2, grad, km2, kv2, None, 5, 0.9, 0.99, 0.01, 1e-8)
+    assert torch.equal(kp2[::3], p[::3]) and torch.equal(km2[::3], m[::3]) and torch.equal(kv2[::3], v[::3])
+    assert not torch.equal(kp2[1::3], p[1::3])
+
+
+def test_cumdist_known_answer():
+    dist = torch.tensor([[0.2, 0.2, 0.2, 0.2, 0.2, 0.2]])
+    assert oracle.cumdist_thres(dist, 0.5).tolist() == [[False, False, True, False, False, True]]
+
+
+def test_maskcache_known_answer():
+    world = torch.zeros(2, 2, 2, dtype=torch.bool)
+    world[1, 0, 1] = True
+    scale = torch.ones(3)
+    shift = torch.zeros(3)
+    xyz = torch.tensor([[1.0, 0.0, 1.0], [0.6, 0.4, 0.5], [1.6, 0.0, 1.0], [-0.6, 0.0, 1.0]])
+    # round-half-away: 0.5 -> 1; 1.6 -> 2 is out of range; -0.6 -> -1 out of range
+    assert oracle.maskcache_lookup(world, xyz, scale, shift).tolist() == [True, True, False, False]
+
+
+def test_segment_ops_and_neus_alpha_reference_forms():
+    src = torch.arange(6, dtype=torch.float32)
+    rid = torch.tensor([0, 0, 2, 2, 2, 3])
+    assert oracle.segment_sum(src[:, None], rid, 5).flatten().tolist() == [1.0, 0.0, 9.0, 5.0, 0.0]
+    assert oracle.segment_cumsum(src, rid).tolist() == [0.0, 1.0, 2.0, 5.0, 9.0, 5.0]
+    # a surface crossed head-on: alpha rises from ~0 to a peak around sdf = 0
+    sdf = torch.linspace(0.1, -0.1, 9)
+    grads = torch.tensor([[0.0, 0.0, 1.0]]).repeat(9, 1)
+    view = torch.tensor([[0.0, 0.0, -1.0]])
+    a = oracle.neus_alpha(view, torch.zeros(9, dtype=torch.int64), 0.025, sdf, grads, 64.0)
+    assert float(a[0]) < 0.05 and float(a[-1]) > 0.5 and bool((a[1:] >= a[:-1]).all())   # opacity rises through the surface
+    assert bool((a >= 0).all()) and bool((a <= 1).all())

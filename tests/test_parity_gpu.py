@@ -175,12 +175,12 @@ def test_raw2alpha(pp, ref_modules, n):
     exp_d, alpha = ru.raw2alpha(density.cuda(), shift, interval)
     oexp, oalpha = oracle.raw2alpha(density, shift, interval)
     close(exp_d, oexp, rtol=1e-5, atol=0)
-    close(alpha, oalpha, rtol=1e-5, atol=1e-7)
+    close(alpha, oalpha, rtol=1e-5, atol=3e-7)   # 1 - pow(): libm vs libdevice pow differ by <= 2 ulp at 1.0
     grad = ru.raw2alpha_backward(exp_d, gb.cuda(), interval)
     close(grad, oracle.raw2alpha_backward(exp_d.cpu(), gb, interval), rtol=1e-5, atol=1e-30)
     exp_n, alpha_n = ru.raw2alpha_nonuni(density.cuda(), shift, iv.cuda())
     oexp_n, oalpha_n = oracle.raw2alpha_nonuni(density, shift, iv)
-    close(alpha_n, oalpha_n, rtol=1e-5, atol=1e-7)
+    close(alpha_n, oalpha_n, rtol=1e-5, atol=3e-7)
     grad_n = ru.raw2alpha_nonuni_backward(exp_n, gb.cuda(), iv.cuda())
     close(grad_n, oracle.raw2alpha_nonuni_backward(exp_n.cpu(), gb, iv), rtol=1e-5, atol=1e-30)
     ref = ref_modules.get("render_utils_cuda")
