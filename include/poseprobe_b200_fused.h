@@ -1,0 +1,101 @@
+/*
+ * poseprobe_b200 -- fused B200-native entry points for the DVGO render / train step.
+ *
+ * The reference runs this path as a chain of operators with every per-sample tensor materialised in
+ * HBM: sample_pts_on_rays -> DenseGrid(density) -> raw2alpha -> alpha2weight -> DenseGrid(k0) ->
+ * sigmoid -> segment_coo sums -> loss -> autograd of all of it -> (masked) Adam
+ * (lib/dvgo_ori.py:289-379 for the dense pure-PyTorch form, lib/voxurf_coarse.py:661-695 and
+ * :1094-1222 for the CUDA-sampler form, lib/cuda/*.cu for the kernels).  The entry points below
+ * compute the same quantities with ONE kernel per direction: a warp marches a ray, gathers 16-byte
+ * voxel records, composites with a warp scan, and (backward) scatters with 128-bit reductions.  No
+ * per-sample tensor ever reaches HBM.
+ *
+ * Voxel record layout ("vox"): float4 per voxel, [X,Y,Z] row-major (Z contiguous) =
+ *   { density, k0_r, k0_g, k0_b }.  pp_voxels_pack / pp_voxels_unpack convert from / to the
+ * reference's parameter layout (density [1,1,X,Y,Z], k0 [1,3,X,Y,Z]; lib/dvgo_ori.py:50,65) so
+ * checkpoints stay interchangeable.  Gradients and Adam moments use the same record layout.
+ */
+#ifndef POSEPROBE_B200_FUSED_H_
+#define POSEPROBE_B200_FUSED_H_
+
+#include "poseprobe_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pp_dvgo_scene {
+  int32_t sx, sy, sz;       /* grid extents X, Y, Z (world_size) */
+  float xyz_min[3];
+  float xyz_max[3];
+  float near, far;          /* ray clamp passed to the sampler (render_kwargs) */
+  float stepdist;           /* stepsize * voxel_size (voxurf_coarse.py:676) */
+  float act_shift;          /* density bias, log(1/(1-alpha_init) - 1) (dvgo_ori.py:43) */
+  float interval;           /* stepsize * voxel_size_ratio (dvgo_ori.py:297) */
+  float bg;                 /* background colour (render_kwargs['bg']) */
+  float fast_color_thres;   /* colour is evaluated for samples with weight > thres (dvgo_ori.py:328) */
+} pp_dvgo_scene;
+
+typedef struct pp_dvgo_loss {
+  float w_rgb;              /* weight of the photometric MSE (mean over rays x 3) */
+  float w_entropy_last;     /* weight of the background-entropy term on alphainv_last (0 = off) */
+  float w_rgbper;           /* weight of the per-point colour term, weights detached (0 = off) */
+} pp_dvgo_loss;
+
+/* density [V], k0 [3,V] (channels first) -> vox [V] float4 records, and back.  Either plane pointer of
+ * unpack may be null. */
+PP_API int pp_voxels_pack(const float* density, const float* k0, int64_t n_voxels, void* vox,
+                          pp_stream_t stream);
+PP_API int pp_voxels_unpack(const void* vox, int64_t n_voxels, float* density, float* k0,
+                            pp_stream_t stream);
+
+/* Forward render (no gradient state kept).  Outputs, each optional:
+ *   rgb_marched [N,3] = sum_i w_i * sigmoid(k0_i) + alphainv_last * bg      (dvgo_ori.py:363)
+ *   alphainv_last [N]  final transmittance                                   (alpha2weight's 3rd output)
+ *   depth [N]          sum_i w_i * (i * stepdist)                            (voxurf_coarse.py:1198)
+ *   n_marched [N] i32  samples composited before termination (in-box ones only) */
+PP_API int pp_dvgo_render_forward(const pp_dvgo_scene* scene, const void* vox, const float* rays_o,
+                                  const float* rays_d, int64_t n_rays, float* rgb_marched,
+                                  float* alphainv_last, float* depth, int32_t* n_marched,
+                                  pp_stream_t stream);
+
+/* Backward of the render for arbitrary losses on (rgb_marched, alphainv_last): recomputes the march,
+ * then walks the ray in reverse and accumulates d loss / d vox into grad_vox (float4 records, +=).
+ * grad_alphainv_last may be null.  grad_rays (optional, [N,6] = d loss/d rays_o | d loss/d rays_d)
+ * receives the per-ray pose gradient through the sample positions. */
+PP_API int pp_dvgo_render_backward(const pp_dvgo_scene* scene, const void* vox, const float* rays_o,
+                                   const float* rays_d, int64_t n_rays, const float* grad_rgb_marched,
+                                   const float* grad_alphainv_last, void* grad_vox, float* grad_rays,
+                                   pp_stream_t stream);
+
+/* Fused forward + loss + backward for the DVGO training losses against target [N,3]:
+ *   loss = w_rgb * mean((rgb_marched - target)^2) [+ entropy_last + rgbper terms]
+ * Accumulates d loss / d vox into grad_vox (+=), writes rgb_marched [N,3] (optional) and ADDS the
+ * batch loss into loss_out[0] and the photometric MSE into loss_out[1] (device floats the caller
+ * zeroes).  grad_rays as above. */
+PP_API int pp_dvgo_train_step(const pp_dvgo_scene* scene, const pp_dvgo_loss* loss, const void* vox,
+                              const float* rays_o, const float* rays_d, const float* target,
+                              int64_t n_rays, void* grad_vox, float* rgb_marched, float* loss_out,
+                              float* grad_rays, pp_stream_t stream);
+
+/* Masked Adam on voxel records, per element exactly masked_adam_upd (adam_upd_kernel.cu:25-40, step size
+ * :72) with separate learning rates for the density channel and the three k0 channels; gradients are
+ * reset to zero in the same pass (the zero_grad the reference does separately).  In place. */
+PP_API int pp_voxel_adam(void* vox, void* grad_vox, void* exp_avg, void* exp_avg_sq, int64_t n_voxels,
+                         int32_t step, float beta1, float beta2, float lr_density, float lr_k0,
+                         float eps, int zero_grad, pp_stream_t stream);
+
+/* Same, preceded by the total-variation gradient (total_variation_add_grad, old kernel weights
+ * k,j,i = wz,wy,wz; total_variation_kernel.cu:13-35) evaluated on the OLD parameters: reads vox_in,
+ * writes vox_out (ping-pong; vox_in is left untouched so neighbours always see pre-step values).
+ * tv_density / tv_k0 are the caller's wx=wy=wz for the density and k0 channels (0 = off);
+ * dense_mode as in the reference (0: only where the ray gradient is non-zero). */
+PP_API int pp_voxel_tv_adam(const pp_dvgo_scene* scene, const void* vox_in, void* vox_out,
+                            void* grad_vox, void* exp_avg, void* exp_avg_sq, int32_t step, float beta1,
+                            float beta2, float lr_density, float lr_k0, float eps, float tv_density,
+                            float tv_k0, int dense_mode, pp_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POSEPROBE_B200_FUSED_H_ */

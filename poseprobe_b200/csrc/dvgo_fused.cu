@@ -1,0 +1,706 @@
+// Fused DVGO render / train-step kernels (see include/poseprobe_b200_fused.h).
+//
+// One warp marches one ray; the 32 lanes are 32 consecutive steps of the march.
+//
+//   gather    : every in-box sample reads its 8 corner voxel RECORDS (float4 = density + 3 colour
+//               channels) with 8 x LDG.128, so one request returns everything both interpolations need;
+//               consecutive lanes are consecutive steps of the same ray, i.e. neighbouring voxels.
+//   composite : transmittance is an inclusive product scan over the lanes (5 shuffle steps) carried
+//               from chunk to chunk; early termination (T < 1e-3 after a sample, alpha2weight's rule,
+//               render_utils_kernel.cu:597) is a ballot.
+//   backward  : alpha and T of the march are staged in shared memory (8 B per step), then the ray is
+//               walked in reverse with a suffix scan for alpha2weight_backward's recurrence
+//               (render_utils_kernel.cu:671-675); the voxel gradient is scattered with one 128-bit
+//               red.global.add.v4.f32 per corner instead of 4 scalar atomics.
+//   loss      : in train mode the photometric MSE (lib/losses.py:26-29), the background entropy and the
+//               per-point colour term are evaluated in the same kernel, so the forward never leaves
+//               the SM.
+//
+// Sample positions, step counts and the in-box test are computed with exactly the arithmetic of the
+// stand-alone sampler (ray_math.cuh), so the set of samples is identical to sample_pts_on_rays + the
+// `~mask_outbbox` compaction of the reference's Python wrapper (voxurf_coarse.py:686-693).
+#include "../../include/poseprobe_b200_fused.h"
+#include "common.cuh"
+#include "ray_math.cuh"
+
+namespace pp {
+
+enum { kModeForward = 0, kModeBackward = 1, kModeTrain = 2 };
+
+// ---- voxel record helpers -----------------------------------------------------------------------
+struct Cell {
+  int base;           // record index of the (x0,y0,z0) corner
+  int ex, ey, ez;     // record strides towards the +X/+Y/+Z corner (0 on the max face: weight is 0)
+  float fx, fy, fz;   // fractional position inside the cell
+  float gx, gy, gz;   // complements, computed as (floor+1) - i like ATen does
+};
+
+// ATen-order continuous voxel index (see grid.cu voxel_coord) for a point known to be inside the box.
+__device__ __forceinline__ float vcoord(float x, float mn, float mx, int size) {
+  const float t = (x - mn) / (mx - mn);
+  const float c = add_rn(mul_rn(t, 2.f), -1.f);
+  return mul_rn(add_rn(c, 1.f) / 2.f, static_cast<float>(size - 1));
+}
+
+__device__ __forceinline__ Cell make_cell(const pp_dvgo_scene& sc, float px, float py, float pz) {
+  Cell c;
+  float ix = vcoord(px, sc.xyz_min[0], sc.xyz_max[0], sc.sx);
+  float iy = vcoord(py, sc.xyz_min[1], sc.xyz_max[1], sc.sy);
+  float iz = vcoord(pz, sc.xyz_min[2], sc.xyz_max[2], sc.sz);
+  // rounding can push an in-box point a hair outside [0, size-1]; zero padding would give it weight
+  // ~1e-7 less, clamping keeps the record index legal
+  ix = fminf(fmaxf(ix, 0.f), static_cast<float>(sc.sx - 1));
+  iy = fminf(fmaxf(iy, 0.f), static_cast<float>(sc.sy - 1));
+  iz = fminf(fmaxf(iz, 0.f), static_cast<float>(sc.sz - 1));
+  const float x0 = floorf(ix), y0 = floorf(iy), z0 = floorf(iz);
+  c.fx = ix - x0; c.gx = (x0 + 1.f) - ix;
+  c.fy = iy - y0; c.gy = (y0 + 1.f) - iy;
+  c.fz = iz - z0; c.gz = (z0 + 1.f) - iz;
+  const int xi = static_cast<int>(x0), yi = static_cast<int>(y0), zi = static_cast<int>(z0);
+  c.base = (xi * sc.sy + yi) * sc.sz + zi;
+  c.ez = (zi + 1 < sc.sz) ? 1 : 0;
+  c.ey = (yi + 1 < sc.sy) ? sc.sz : 0;
+  c.ex = (xi + 1 < sc.sx) ? sc.sy * sc.sz : 0;
+  return c;
+}
+
+__device__ __forceinline__ int corner_off(const Cell& c, int q) {
+  return c.base + ((q & 1) ? c.ez : 0) + ((q & 2) ? c.ey : 0) + ((q & 4) ? c.ex : 0);
+}
+__device__ __forceinline__ float corner_w(const Cell& c, int q) {
+  // (Z term * Y term) * X term : ATen's tnw..bse product order
+  return mul_rn(mul_rn((q & 1) ? c.fz : c.gz, (q & 2) ? c.fy : c.gy), (q & 4) ? c.fx : c.gx);
+}
+
+__device__ __forceinline__ void gather8(const float4* __restrict__ vox, const Cell& c, float4 (&v)[8]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) v[q] = __ldg(vox + corner_off(c, q));
+}
+
+__device__ __forceinline__ float4 interp8(const Cell& c, const float4 (&v)[8]) {
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float w = corner_w(c, q);
+    a.x = fma_rn(v[q].x, w, a.x);
+    a.y = fma_rn(v[q].y, w, a.y);
+    a.z = fma_rn(v[q].z, w, a.z);
+    a.w = fma_rn(v[q].w, w, a.w);
+  }
+  return a;
+}
+
+__device__ __forceinline__ void red_add_v4(float4* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c),
+               "f"(d)
+               : "memory");
+}
+
+__device__ __forceinline__ float sigmoid_ref(float x) { return 1.f / (1.f + expf(-x)); }
+
+// ---- per-ray state ---------------------------------------------------------------------------------
+struct Ray {
+  float start[3], dir[3];
+  float o[3], d[3];
+  float t_min, rnorm;
+  int n_steps;
+  int enter_axis;   // axis whose slab decided t_min, -1 when t_min was clamped to near/far
+};
+
+__device__ __forceinline__ Ray setup_ray(const pp_dvgo_scene& sc, const float* __restrict__ rays_o,
+                                         const float* __restrict__ rays_d, int64_t r) {
+  Ray ray;
+  load3(rays_o, r, ray.o);
+  load3(rays_d, r, ray.d);
+  float t_max;
+  ray_bbox_range(ray.o, ray.d, sc.xyz_min, sc.xyz_max, sc.near, sc.far, ray.t_min, t_max);
+  ray.rnorm = ray_norm(ray.d);
+  const int64_t n = ray_step_count<float>(ray.t_min, t_max, ray.rnorm, sc.stepdist);
+  ray.n_steps = static_cast<int>(min64(n, 1 << 30));
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    ray.start[c] = fma_rn(ray.d[c], ray.t_min, ray.o[c]);
+    ray.dir[c] = ray.d[c] / ray.rnorm;
+  }
+  ray.enter_axis = -1;
+  return ray;
+}
+
+__device__ __forceinline__ bool sample_point(const pp_dvgo_scene& sc, const Ray& ray, int i, float (&p)[3]) {
+  const float dist = sc.stepdist * static_cast<float>(i);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) p[c] = fma_rn(ray.dir[c], dist, ray.start[c]);
+  const bool out = (sc.xyz_min[0] > p[0]) | (sc.xyz_min[1] > p[1]) | (sc.xyz_min[2] > p[2]) |
+                   (sc.xyz_max[0] < p[0]) | (sc.xyz_max[1] < p[1]) | (sc.xyz_max[2] < p[2]);
+  return !out;
+}
+
+// raw2alpha, bit-identical to the stand-alone kernel (alpha.cu / reference :437-442)
+__device__ __forceinline__ float density_to_alpha(float sigma, float shift, float interval, float& e) {
+  e = expf(sigma + shift);
+  return 1.f - powf(1.f + e, -interval);
+}
+
+// ---- the march ------------------------------------------------------------------------------------
+// dynamic shared memory: per warp, s_alpha[cap] then s_T[cap]
+template <int kMode, bool kPoseGrad>
+__global__ void __launch_bounds__(256)
+dvgo_march_kernel(pp_dvgo_scene sc, pp_dvgo_loss ls, const float4* __restrict__ vox,
+                  const float* __restrict__ rays_o, const float* __restrict__ rays_d, int64_t n_rays,
+                  const float* __restrict__ target, const float* __restrict__ grad_rgb_in,
+                  const float* __restrict__ grad_last_in, float4* __restrict__ grad_vox,
+                  float* __restrict__ rgb_marched, float* __restrict__ alphainv_last,
+                  float* __restrict__ depth, int32_t* __restrict__ n_marched,
+                  float* __restrict__ loss_out, float* __restrict__ grad_rays, int cap) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int warps_per_block = blockDim.x >> 5;
+  float* s_alpha = smem + (size_t)warp * 2 * cap;
+  float* s_T = s_alpha + cap;
+
+  for (int64_t r = blockIdx.x * (int64_t)warps_per_block + warp; r < n_rays;
+       r += (int64_t)gridDim.x * warps_per_block) {
+    const Ray ray = setup_ray(sc, rays_o, rays_d, r);
+    const int n_steps = (kMode == kModeForward) ? ray.n_steps : min(ray.n_steps, cap);
+
+    // ---------------- pass 1: forward march ----------------
+    float T_in = 1.f;
+    float acc_r = 0.f, acc_g = 0.f, acc_b = 0.f, acc_depth = 0.f, acc_per = 0.f;
+    int n_live = 0;
+    int end = n_steps;          // exclusive index of the last composited step (+1)
+    float tgt[3] = {0.f, 0.f, 0.f};
+    if (kMode == kModeTrain) load3(target, r, tgt);
+    for (int base = 0; base < n_steps; base += kWarp) {
+      const int i = base + lane;
+      float p[3];
+      const bool live = (i < n_steps) && sample_point(sc, ray, i, p);
+      float alpha = 0.f;
+      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live) {
+        const Cell c = make_cell(sc, p[0], p[1], p[2]);
+        float4 v[8];
+        gather8(vox, c, v);
+        val = interp8(c, v);
+        float e;
+        alpha = density_to_alpha(val.x, sc.act_shift, sc.interval, e);
+      }
+      // inclusive product scan of (1 - alpha)
+      float P = 1.f - alpha;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float up = __shfl_up_sync(kFull, P, o);
+        if (lane >= o) P *= up;
+      }
+      float Pex = __shfl_up_sync(kFull, P, 1);
+      if (lane == 0) Pex = 1.f;
+      const float T_before = T_in * Pex;
+      const float T_after = T_in * P;
+      const unsigned term = __ballot_sync(kFull, live && (T_after < 1e-3f));
+      bool counted = live;
+      int last_lane = 31;
+      if (term) {
+        last_lane = __ffs(term) - 1;
+        counted = live && (lane <= last_lane);
+      }
+      if (!counted) alpha = 0.f;
+      if (kMode != kModeForward && i < n_steps) {
+        s_alpha[i] = alpha;
+        s_T[i] = T_before;
+      }
+      const float w = T_before * alpha;
+      if (counted && w > sc.fast_color_thres) {
+        const float cr = sigmoid_ref(val.y), cg = sigmoid_ref(val.z), cb = sigmoid_ref(val.w);
+        acc_r = fma_rn(w, cr, acc_r);
+        acc_g = fma_rn(w, cg, acc_g);
+        acc_b = fma_rn(w, cb, acc_b);
+        if (kMode == kModeTrain && ls.w_rgbper != 0.f) {
+          const float dr = cr - tgt[0], dg = cg - tgt[1], db = cb - tgt[2];
+          acc_per += w * (dr * dr + dg * dg + db * db);
+        }
+      }
+      if (counted) {
+        acc_depth = fma_rn(w, sc.stepdist * static_cast<float>(i), acc_depth);
+        n_live += 1;
+      }
+      T_in = __shfl_sync(kFull, T_after, last_lane);
+      if (term) {
+        end = base + last_lane + 1;
+        break;
+      }
+    }
+    const float T_last = T_in;
+    acc_r = warp_sum(acc_r);
+    acc_g = warp_sum(acc_g);
+    acc_b = warp_sum(acc_b);
+    const float rgbm[3] = {fma_rn(T_last, sc.bg, acc_r), fma_rn(T_last, sc.bg, acc_g),
+                           fma_rn(T_last, sc.bg, acc_b)};
+    if (kMode != kModeBackward) {
+      if (depth) acc_depth = warp_sum(acc_depth);
+      if (n_marched) n_live = __reduce_add_sync(kFull, n_live);
+      if (lane == 0) {
+        if (rgb_marched) {
+          rgb_marched[3 * r] = rgbm[0];
+          rgb_marched[3 * r + 1] = rgbm[1];
+          rgb_marched[3 * r + 2] = rgbm[2];
+        }
+        if (alphainv_last) alphainv_last[r] = T_last;
+        if (depth) depth[r] = acc_depth;
+        if (n_marched) n_marched[r] = n_live;
+      }
+    }
+    if (kMode == kModeForward) continue;
+
+    // ---------------- loss / incoming gradients ----------------
+    float g[3];          // d loss / d rgb_marched
+    float g_last;        // d loss / d alphainv_last (total, including the bg term of rgb_marched)
+    float per_scale = 0.f;
+    if (kMode == kModeTrain) {
+      const float inv_n = 1.f / static_cast<float>(n_rays);
+      float mse = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float diff = rgbm[c] - tgt[c];
+        mse += diff * diff;
+        g[c] = ls.w_rgb * 2.f * diff * inv_n * (1.f / 3.f);
+      }
+      g_last = (g[0] + g[1] + g[2]) * sc.bg;
+      float loss = ls.w_rgb * mse * inv_n * (1.f / 3.f);
+      if (ls.w_entropy_last != 0.f) {
+        // -(p log p + (1-p) log(1-p)) on clamp(alphainv_last, 1e-6, 1-1e-6), mean over rays
+        const float pc = fminf(fmaxf(T_last, 1e-6f), 1.f - 1e-6f);
+        loss += ls.w_entropy_last * inv_n * -(pc * logf(pc) + (1.f - pc) * logf(1.f - pc));
+        if (T_last >= 1e-6f && T_last <= 1.f - 1e-6f)
+          g_last += ls.w_entropy_last * inv_n * -(logf(pc) - logf(1.f - pc));
+      }
+      if (ls.w_rgbper != 0.f) {
+        acc_per = warp_sum(acc_per);
+        loss += ls.w_rgbper * inv_n * acc_per;
+        per_scale = ls.w_rgbper * inv_n * 2.f;
+      }
+      if (lane == 0 && loss_out) {
+        atomicAdd(loss_out, loss);
+        atomicAdd(loss_out + 1, mse * inv_n * (1.f / 3.f));
+      }
+    } else {
+      load3(grad_rgb_in, r, g);
+      g_last = (g[0] + g[1] + g[2]) * sc.bg;
+      if (grad_last_in) g_last += grad_last_in[r];
+    }
+    __syncwarp();
+
+    // ---------------- pass 2: reverse walk ----------------
+    float back = g_last * T_last;   // back_cum of alpha2weight_backward (reference :671)
+    float G0[3] = {0.f, 0.f, 0.f}, G1[3] = {0.f, 0.f, 0.f};
+    const int last_base = ((end - 1) / kWarp) * kWarp;
+    for (int base = last_base; base >= 0; base -= kWarp) {
+      const int i = base + lane;
+      float p[3];
+      const bool live = (i < end) && sample_point(sc, ray, i, p);
+      float alpha = 0.f, T = 0.f, w = 0.f, gw = 0.f, e = 0.f;
+      float rgb[3] = {0.f, 0.f, 0.f};
+      bool col = false;
+      Cell c;
+      float4 v[8];
+      if (live) {
+        alpha = s_alpha[i];
+        T = s_T[i];
+        c = make_cell(sc, p[0], p[1], p[2]);
+        gather8(vox, c, v);
+        const float4 val = interp8(c, v);
+        e = expf(val.x + sc.act_shift);
+        w = T * alpha;
+        col = w > sc.fast_color_thres;
+        if (col) {
+          rgb[0] = sigmoid_ref(val.y);
+          rgb[1] = sigmoid_ref(val.z);
+          rgb[2] = sigmoid_ref(val.w);
+          gw = g[0] * rgb[0] + g[1] * rgb[1] + g[2] * rgb[2];
+        }
+      }
+      // exclusive suffix sum of gw*w over the lanes above me
+      const float contrib = gw * w;
+      float S = contrib;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float dn = __shfl_down_sync(kFull, S, o);
+        if (lane + o < 32) S += dn;
+      }
+      const float back_i = back + (S - contrib);
+      back += __shfl_sync(kFull, S, 0);
+      if (live) {
+        const float d_alpha = gw * T - back_i / (1.f - alpha + 1e-10f);
+        // raw2alpha_backward (reference :513-516)
+        const float d_sigma = fminf(e, 1e10f) * powf(1.f + e, -sc.interval - 1.f) * sc.interval * d_alpha;
+        float dk[3] = {0.f, 0.f, 0.f};
+        if (col) {
+#pragma unroll
+          for (int ch = 0; ch < 3; ++ch) {
+            float gc = w * g[ch];
+            if (kMode == kModeTrain) gc += per_scale * w * (rgb[ch] - tgt[ch]);
+            dk[ch] = gc * rgb[ch] * (1.f - rgb[ch]);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float wq = corner_w(c, q);
+          if (wq != 0.f)
+            red_add_v4(grad_vox + corner_off(c, q), wq * d_sigma, wq * dk[0], wq * dk[1], wq * dk[2]);
+        }
+        if (kPoseGrad) {
+          // d loss / d point = sum_ch d_ch * grad_xyz(interp_ch); voxel units -> world units below
+          float gp[3] = {0.f, 0.f, 0.f};
+          const float dch[4] = {d_sigma, dk[0], dk[1], dk[2]};
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            float u[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              u[q] = ch == 0 ? v[q].x : ch == 1 ? v[q].y : ch == 2 ? v[q].z : v[q].w;
+            const float dX = ((u[4] - u[0]) * c.gz + (u[5] - u[1]) * c.fz) * c.gy +
+                             ((u[6] - u[2]) * c.gz + (u[7] - u[3]) * c.fz) * c.fy;
+            const float dY = ((u[2] - u[0]) * c.gz + (u[3] - u[1]) * c.fz) * c.gx +
+                             ((u[6] - u[4]) * c.gz + (u[7] - u[5]) * c.fz) * c.fx;
+            const float dZ = ((u[1] - u[0]) * c.gy + (u[3] - u[2]) * c.fy) * c.gx +
+                             ((u[5] - u[4]) * c.gy + (u[7] - u[6]) * c.fy) * c.fx;
+            gp[0] += dch[ch] * dX;
+            gp[1] += dch[ch] * dY;
+            gp[2] += dch[ch] * dZ;
+          }
+          gp[0] *= (sc.sx - 1) / (sc.xyz_max[0] - sc.xyz_min[0]);
+          gp[1] *= (sc.sy - 1) / (sc.xyz_max[1] - sc.xyz_min[1]);
+          gp[2] *= (sc.sz - 1) / (sc.xyz_max[2] - sc.xyz_min[2]);
+          const float s = sc.stepdist * static_cast<float>(i);
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            G0[k] += gp[k];
+            G1[k] += gp[k] * s;
+          }
+        }
+      }
+    }
+    if (kPoseGrad) {
+      // point_i = o + d*t_min + (d/|d|) * s_i.  t_min is treated as locally constant in (o, d) except
+      // through the entering slab: t_min = (face - o_a)/d_a  =>  dt/do_a = -1/d_a, dt/dd_a = -t_min/d_a.
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        G0[k] = warp_sum(G0[k]);
+        G1[k] = warp_sum(G1[k]);
+      }
+      if (lane == 0) {
+        float go[3] = {G0[0], G0[1], G0[2]};
+        float gd[3] = {G0[0] * ray.t_min, G0[1] * ray.t_min, G0[2] * ray.t_min};
+        // through t_min
+        float a[3], b[3];
+        int axis = -1;
+        float best = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float vv = (ray.d[k] == 0.f) ? 1e-6f : ray.d[k];
+          a[k] = (sc.xyz_max[k] - ray.o[k]) / vv;
+          b[k] = (sc.xyz_min[k] - ray.o[k]) / vv;
+          const float m = fminf(a[k], b[k]);
+          if (m > best) { best = m; axis = k; }
+        }
+        if (best == ray.t_min && ray.d[axis] != 0.f) {   // not clamped by near / far
+          const float gdot = G0[0] * ray.d[0] + G0[1] * ray.d[1] + G0[2] * ray.d[2];
+          go[axis] += gdot * (-1.f / ray.d[axis]);
+          gd[axis] += gdot * (-ray.t_min / ray.d[axis]);
+        }
+        // through dir = d/|d|
+        const float inv = 1.f / ray.rnorm;
+        const float dotg = (G1[0] * ray.d[0] + G1[1] * ray.d[1] + G1[2] * ray.d[2]) * inv * inv * inv;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) gd[k] += G1[k] * inv - ray.d[k] * dotg;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          grad_rays[6 * r + k] = go[k];
+          grad_rays[6 * r + 3 + k] = gd[k];
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---- pack / unpack ---------------------------------------------------------------------------------
+__global__ void voxels_pack_kernel(const float* __restrict__ density, const float* __restrict__ k0,
+                                   int64_t n, float4* __restrict__ vox) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    vox[i] = make_float4(density[i], k0[i], k0[n + i], k0[2 * n + i]);
+}
+
+__global__ void voxels_unpack_kernel(const float4* __restrict__ vox, int64_t n,
+                                     float* __restrict__ density, float* __restrict__ k0) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 v = vox[i];
+    if (density) density[i] = v.x;
+    if (k0) {
+      k0[i] = v.y;
+      k0[n + i] = v.z;
+      k0[2 * n + i] = v.w;
+    }
+  }
+}
+
+// ---- optimiser -------------------------------------------------------------------------------------
+// masked_adam_upd per element (adam_upd_kernel.cu:35-39) with the reference build's contraction
+__device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v, float step_size,
+                                          float b1, float b2, float eps) {
+  if (g == 0.f) return;
+  m = fma_rn(b1, m, mul_rn(1.f - b1, g));
+  v = fma_rn(b2, v, mul_rn(mul_rn(1.f - b2, g), g));
+  p = p - mul_rn(step_size, m) / (sqrtf(v) + eps);
+}
+
+__global__ void __launch_bounds__(256)
+voxel_adam_kernel(float4* __restrict__ vox, float4* __restrict__ grad, float4* __restrict__ m4,
+                  float4* __restrict__ v4, int64_t n, float ss_density, float ss_k0, float b1, float b2,
+                  float eps, int zero_grad) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 g = grad[i];
+    if (g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f) continue;
+    float4 p = vox[i], m = m4[i], v = v4[i];
+    adam_elem(p.x, g.x, m.x, v.x, ss_density, b1, b2, eps);
+    adam_elem(p.y, g.y, m.y, v.y, ss_k0, b1, b2, eps);
+    adam_elem(p.z, g.z, m.z, v.z, ss_k0, b1, b2, eps);
+    adam_elem(p.w, g.w, m.w, v.w, ss_k0, b1, b2, eps);
+    vox[i] = p;
+    m4[i] = m;
+    v4[i] = v;
+    if (zero_grad) grad[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+__device__ __forceinline__ float clamp_pm1(float x) { return fminf(fmaxf(x, -1.f), 1.f); }
+
+// TV (old kernel, weights k,j,i = wz,wy,wz with wx=wy=wz=w here) + masked Adam, ping-pong.
+// blockDim (32, 8): x along Z, y along Y; gridDim.z strides X.
+__global__ void __launch_bounds__(256)
+voxel_tv_adam_kernel(const float4* __restrict__ vin, float4* __restrict__ vout,
+                     float4* __restrict__ grad, float4* __restrict__ m4, float4* __restrict__ v4, int sx,
+                     int sy, int sz, float ss_density, float ss_k0, float b1, float b2, float eps,
+                     float tvw_density, float tvw_k0, int dense_mode) {
+  const int k = blockIdx.x * 32 + threadIdx.x;
+  const int j = blockIdx.y * 8 + threadIdx.y;
+  if (k >= sz || j >= sy) return;
+  for (int i = blockIdx.z; i < sx; i += gridDim.z) {
+    const int64_t idx = ((int64_t)i * sy + j) * sz + k;
+    float4 g = grad[idx];
+    const float4 p = vin[idx];
+    // the reference applies TV per element where that element's gradient is non-zero (sparse mode)
+    const bool tx = dense_mode || g.x != 0.f, ty = dense_mode || g.y != 0.f,
+               tz = dense_mode || g.z != 0.f, tw = dense_mode || g.w != 0.f;
+    if ((tvw_density != 0.f || tvw_k0 != 0.f) && (tx || ty || tz || tw)) {
+      float ax = 0.f, ay = 0.f, az = 0.f, aw = 0.f;
+      auto term = [&](bool edge, int64_t off) {
+        if (edge) return;
+        const float4 q = vin[idx + off];
+        ax = add_rn(ax, mul_rn(tvw_density, clamp_pm1(p.x - q.x)));
+        ay = add_rn(ay, mul_rn(tvw_k0, clamp_pm1(p.y - q.y)));
+        az = add_rn(az, mul_rn(tvw_k0, clamp_pm1(p.z - q.z)));
+        aw = add_rn(aw, mul_rn(tvw_k0, clamp_pm1(p.w - q.w)));
+      };
+      term(k == 0, -1);
+      term(k == sz - 1, 1);
+      term(j == 0, -sz);
+      term(j == sy - 1, sz);
+      term(i == 0, -(int64_t)sz * sy);
+      term(i == sx - 1, (int64_t)sz * sy);
+      if (tx && tvw_density != 0.f) g.x = add_rn(g.x, ax);
+      if (ty && tvw_k0 != 0.f) g.y = add_rn(g.y, ay);
+      if (tz && tvw_k0 != 0.f) g.z = add_rn(g.z, az);
+      if (tw && tvw_k0 != 0.f) g.w = add_rn(g.w, aw);
+    }
+    float4 pn = p;
+    if (g.x != 0.f || g.y != 0.f || g.z != 0.f || g.w != 0.f) {
+      float4 m = m4[idx], v = v4[idx];
+      adam_elem(pn.x, g.x, m.x, v.x, ss_density, b1, b2, eps);
+      adam_elem(pn.y, g.y, m.y, v.y, ss_k0, b1, b2, eps);
+      adam_elem(pn.z, g.z, m.z, v.z, ss_k0, b1, b2, eps);
+      adam_elem(pn.w, g.w, m.w, v.w, ss_k0, b1, b2, eps);
+      m4[idx] = m;
+      v4[idx] = v;
+      grad[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    vout[idx] = pn;
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+static int check_scene(const pp_dvgo_scene* sc, const char* who) {
+  PP_REQUIRE(sc, PP_ERR_INVALID_ARG, "%s: scene is null", who);
+  PP_REQUIRE(sc->sx > 0 && sc->sy > 0 && sc->sz > 0, PP_ERR_INVALID_ARG, "%s: empty grid", who);
+  PP_REQUIRE((int64_t)sc->sx * sc->sy * sc->sz < (1LL << 31), PP_ERR_TOO_LARGE, "%s: grid too large", who);
+  PP_REQUIRE(sc->stepdist > 0.f, PP_ERR_INVALID_ARG, "%s: stepdist must be positive", who);
+  for (int c = 0; c < 3; ++c)
+    PP_REQUIRE(sc->xyz_max[c] > sc->xyz_min[c], PP_ERR_INVALID_ARG, "%s: empty bounding box", who);
+  return PP_OK;
+}
+
+// upper bound of N_steps for any ray: the in-box chord is at most the box diagonal
+static int step_capacity(const pp_dvgo_scene* sc) {
+  double d2 = 0;
+  for (int c = 0; c < 3; ++c) {
+    const double e = (double)sc->xyz_max[c] - (double)sc->xyz_min[c];
+    d2 += e * e;
+  }
+  const int n = (int)ceil(sqrt(d2) / (double)sc->stepdist) + 3;
+  return (n + 31) / 32 * 32;
+}
+
+template <int kMode, bool kPoseGrad>
+static int launch_march(const pp_dvgo_scene* sc, const pp_dvgo_loss* ls, const void* vox,
+                        const float* rays_o, const float* rays_d, int64_t n_rays, const float* target,
+                        const float* grad_rgb, const float* grad_last, void* grad_vox,
+                        float* rgb_marched, float* alphainv_last, float* depth, int32_t* n_marched,
+                        float* loss_out, float* grad_rays, cudaStream_t s, const char* who) {
+  int warps = 8;
+  int cap = 0;
+  size_t smem = 0;
+  if (kMode != kModeForward) {
+    cap = step_capacity(sc);
+    smem = (size_t)warps * 2 * cap * sizeof(float);
+    while (smem > 200 * 1024 && warps > 1) {
+      warps /= 2;
+      smem = (size_t)warps * 2 * cap * sizeof(float);
+    }
+    PP_REQUIRE(smem <= 200 * 1024, PP_ERR_UNSUPPORTED,
+               "%s: %d steps per ray exceed the shared-memory staging capacity", who, cap);
+  }
+  auto kernel = dvgo_march_kernel<kMode, kPoseGrad>;
+  if (smem > 48 * 1024)
+    PP_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t blocks_needed = (n_rays + warps - 1) / warps;
+  const int64_t blocks = min64(blocks_needed, (int64_t)sm_count() * 64);
+  pp_dvgo_loss l = {1.f, 0.f, 0.f};
+  if (ls) l = *ls;
+  kernel<<<(unsigned)blocks, warps * 32, smem, s>>>(
+      *sc, l, (const float4*)vox, rays_o, rays_d, n_rays, target, grad_rgb, grad_last,
+      (float4*)grad_vox, rgb_marched, alphainv_last, depth, n_marched, loss_out, grad_rays, cap);
+  PP_CHECK_LAUNCH(who);
+  return PP_OK;
+}
+
+}  // namespace pp
+
+using namespace pp;
+
+extern "C" int pp_voxels_pack(const float* density, const float* k0, int64_t n_voxels, void* vox,
+                              pp_stream_t stream) {
+  PP_REQUIRE(n_voxels >= 0, PP_ERR_INVALID_ARG, "voxels_pack: n_voxels < 0");
+  if (n_voxels == 0) return PP_OK;
+  PP_REQUIRE(density && k0 && vox, PP_ERR_INVALID_ARG, "voxels_pack: null pointer");
+  const int blocks = (int)min64((n_voxels + 255) / 256, (int64_t)sm_count() * 16);
+  voxels_pack_kernel<<<blocks, 256, 0, as_stream(stream)>>>(density, k0, n_voxels, (float4*)vox);
+  PP_CHECK_LAUNCH("voxels_pack");
+  return PP_OK;
+}
+
+extern "C" int pp_voxels_unpack(const void* vox, int64_t n_voxels, float* density, float* k0,
+                                pp_stream_t stream) {
+  PP_REQUIRE(n_voxels >= 0, PP_ERR_INVALID_ARG, "voxels_unpack: n_voxels < 0");
+  if (n_voxels == 0 || (!density && !k0)) return PP_OK;
+  PP_REQUIRE(vox, PP_ERR_INVALID_ARG, "voxels_unpack: null pointer");
+  const int blocks = (int)min64((n_voxels + 255) / 256, (int64_t)sm_count() * 16);
+  voxels_unpack_kernel<<<blocks, 256, 0, as_stream(stream)>>>((const float4*)vox, n_voxels, density, k0);
+  PP_CHECK_LAUNCH("voxels_unpack");
+  return PP_OK;
+}
+
+extern "C" int pp_dvgo_render_forward(const pp_dvgo_scene* scene, const void* vox, const float* rays_o,
+                                      const float* rays_d, int64_t n_rays, float* rgb_marched,
+                                      float* alphainv_last, float* depth, int32_t* n_marched,
+                                      pp_stream_t stream) {
+  const int rc = check_scene(scene, "dvgo_render_forward");
+  if (rc != PP_OK) return rc;
+  PP_REQUIRE(n_rays >= 0, PP_ERR_INVALID_ARG, "dvgo_render_forward: n_rays < 0");
+  if (n_rays == 0) return PP_OK;
+  PP_REQUIRE(vox && rays_o && rays_d, PP_ERR_INVALID_ARG, "dvgo_render_forward: null pointer");
+  return launch_march<kModeForward, false>(scene, nullptr, vox, rays_o, rays_d, n_rays, nullptr, nullptr,
+                                           nullptr, nullptr, rgb_marched, alphainv_last, depth,
+                                           n_marched, nullptr, nullptr, as_stream(stream),
+                                           "dvgo_render_forward");
+}
+
+extern "C" int pp_dvgo_render_backward(const pp_dvgo_scene* scene, const void* vox, const float* rays_o,
+                                       const float* rays_d, int64_t n_rays,
+                                       const float* grad_rgb_marched, const float* grad_alphainv_last,
+                                       void* grad_vox, float* grad_rays, pp_stream_t stream) {
+  const int rc = check_scene(scene, "dvgo_render_backward");
+  if (rc != PP_OK) return rc;
+  PP_REQUIRE(n_rays >= 0, PP_ERR_INVALID_ARG, "dvgo_render_backward: n_rays < 0");
+  if (n_rays == 0) return PP_OK;
+  PP_REQUIRE(vox && rays_o && rays_d && grad_rgb_marched && grad_vox, PP_ERR_INVALID_ARG,
+             "dvgo_render_backward: null pointer");
+  if (grad_rays)
+    return launch_march<kModeBackward, true>(scene, nullptr, vox, rays_o, rays_d, n_rays, nullptr,
+                                             grad_rgb_marched, grad_alphainv_last, grad_vox, nullptr,
+                                             nullptr, nullptr, nullptr, nullptr, grad_rays,
+                                             as_stream(stream), "dvgo_render_backward");
+  return launch_march<kModeBackward, false>(scene, nullptr, vox, rays_o, rays_d, n_rays, nullptr,
+                                            grad_rgb_marched, grad_alphainv_last, grad_vox, nullptr,
+                                            nullptr, nullptr, nullptr, nullptr, nullptr,
+                                            as_stream(stream), "dvgo_render_backward");
+}
+
+extern "C" int pp_dvgo_train_step(const pp_dvgo_scene* scene, const pp_dvgo_loss* loss, const void* vox,
+                                  const float* rays_o, const float* rays_d, const float* target,
+                                  int64_t n_rays, void* grad_vox, float* rgb_marched, float* loss_out,
+                                  float* grad_rays, pp_stream_t stream) {
+  const int rc = check_scene(scene, "dvgo_train_step");
+  if (rc != PP_OK) return rc;
+  PP_REQUIRE(n_rays >= 0, PP_ERR_INVALID_ARG, "dvgo_train_step: n_rays < 0");
+  if (n_rays == 0) return PP_OK;
+  PP_REQUIRE(vox && rays_o && rays_d && target && grad_vox, PP_ERR_INVALID_ARG,
+             "dvgo_train_step: null pointer");
+  if (grad_rays)
+    return launch_march<kModeTrain, true>(scene, loss, vox, rays_o, rays_d, n_rays, target, nullptr,
+                                          nullptr, grad_vox, rgb_marched, nullptr, nullptr, nullptr,
+                                          loss_out, grad_rays, as_stream(stream), "dvgo_train_step");
+  return launch_march<kModeTrain, false>(scene, loss, vox, rays_o, rays_d, n_rays, target, nullptr,
+                                         nullptr, grad_vox, rgb_marched, nullptr, nullptr, nullptr,
+                                         loss_out, nullptr, as_stream(stream), "dvgo_train_step");
+}
+
+static float adam_step_size(float lr, float beta1, float beta2, int step) {
+  // adam_upd_kernel.cu:72
+  return lr * sqrtf(1.f - powf(beta2, (float)step)) / (1.f - powf(beta1, (float)step));
+}
+
+extern "C" int pp_voxel_adam(void* vox, void* grad_vox, void* exp_avg, void* exp_avg_sq,
+                             int64_t n_voxels, int32_t step, float beta1, float beta2,
+                             float lr_density, float lr_k0, float eps, int zero_grad,
+                             pp_stream_t stream) {
+  PP_REQUIRE(n_voxels >= 0, PP_ERR_INVALID_ARG, "voxel_adam: n_voxels < 0");
+  if (n_voxels == 0) return PP_OK;
+  PP_REQUIRE(vox && grad_vox && exp_avg && exp_avg_sq, PP_ERR_INVALID_ARG, "voxel_adam: null pointer");
+  const int blocks = (int)min64((n_voxels + 255) / 256, (int64_t)sm_count() * 8);
+  voxel_adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(
+      (float4*)vox, (float4*)grad_vox, (float4*)exp_avg, (float4*)exp_avg_sq, n_voxels,
+      adam_step_size(lr_density, beta1, beta2, step), adam_step_size(lr_k0, beta1, beta2, step), beta1,
+      beta2, eps, zero_grad);
+  PP_CHECK_LAUNCH("voxel_adam");
+  return PP_OK;
+}
+
+extern "C" int pp_voxel_tv_adam(const pp_dvgo_scene* scene, const void* vox_in, void* vox_out,
+                                void* grad_vox, void* exp_avg, void* exp_avg_sq, int32_t step,
+                                float beta1, float beta2, float lr_density, float lr_k0, float eps,
+                                float tv_density, float tv_k0, int dense_mode, pp_stream_t stream) {
+  const int rc = check_scene(scene, "voxel_tv_adam");
+  if (rc != PP_OK) return rc;
+  PP_REQUIRE(vox_in && vox_out && grad_vox && exp_avg && exp_avg_sq, PP_ERR_INVALID_ARG,
+             "voxel_tv_adam: null pointer");
+  PP_REQUIRE(vox_in != vox_out, PP_ERR_INVALID_ARG, "voxel_tv_adam: vox_in and vox_out must differ");
+  const dim3 block(32, 8, 1);
+  const dim3 grid((scene->sz + 31) / 32, (scene->sy + 7) / 8, (unsigned)min64(scene->sx, 65535));
+  voxel_tv_adam_kernel<<<grid, block, 0, as_stream(stream)>>>(
+      (const float4*)vox_in, (float4*)vox_out, (float4*)grad_vox, (float4*)exp_avg, (float4*)exp_avg_sq,
+      scene->sx, scene->sy, scene->sz, adam_step_size(lr_density, beta1, beta2, step),
+      adam_step_size(lr_k0, beta1, beta2, step), beta1, beta2, eps, tv_density / 6, tv_k0 / 6, dense_mode);
+  PP_CHECK_LAUNCH("voxel_tv_adam");
+  return PP_OK;
+}

@@ -28,23 +28,31 @@ struct Corner8 {
   float w[8];      // trilinear weights
   bool ok[8];      // corner inside the grid
   float fx, fy, fz, gx, gy, gz;  // fractional parts along X,Y,Z and their complements
+  float mx_, my_, mz_;           // d(clipped coord)/d(coord): 0 where border padding clipped the axis
 };
 
 // Continuous voxel coordinate along one axis, replicating
 //   t = (x - min) / (max - min);  c = t*2 - 1        (lib/grid.py:53, separate torch kernels: no FMA)
 //   i = ((c + 1) / 2) * (size - 1)                   (ATen grid_sampler_unnormalize, align_corners)
-__device__ __forceinline__ float voxel_coord(float x, float mn, float mx, int size, int border) {
+__device__ __forceinline__ float voxel_coord(float x, float mn, float mx, int size, int border,
+                                             float& dclip) {
   const float t = (x - mn) / (mx - mn);
   const float c = add_rn(mul_rn(t, 2.f), -1.f);
   float i = mul_rn(add_rn(c, 1.f) / 2.f, static_cast<float>(size - 1));
-  if (border) i = fminf(static_cast<float>(size - 1), fmaxf(i, 0.f));  // clip_coordinates
+  dclip = 1.f;
+  if (border) {
+    // clip_coordinates_set_grad: the derivative vanishes on and beyond the border
+    const float hi = static_cast<float>(size - 1);
+    if (!(i > 0.f && i < hi)) dclip = 0.f;
+    i = fminf(hi, fmaxf(i, 0.f));
+  }
   return i;
 }
 
 __device__ __forceinline__ void make_corners(const GridGeom& g, float x, float y, float z, Corner8& c) {
-  const float ix = voxel_coord(x, g.mn[0], g.mx[0], g.sx, g.border);
-  const float iy = voxel_coord(y, g.mn[1], g.mx[1], g.sy, g.border);
-  const float iz = voxel_coord(z, g.mn[2], g.mx[2], g.sz, g.border);
+  const float ix = voxel_coord(x, g.mn[0], g.mx[0], g.sx, g.border, c.mx_);
+  const float iy = voxel_coord(y, g.mn[1], g.mx[1], g.sy, g.border, c.my_);
+  const float iz = voxel_coord(z, g.mn[2], g.mx[2], g.sz, g.border, c.mz_);
   const float x0 = floorf(ix), y0 = floorf(iy), z0 = floorf(iz);
   c.fx = ix - x0; c.gx = (x0 + 1.f) - ix;
   c.fy = iy - y0; c.gy = (y0 + 1.f) - iy;
@@ -73,9 +81,9 @@ trilinear_fwd_kernel(const float* __restrict__ grid, int n_ch, GridGeom g,
   make_corners(g, xyz[3 * p], xyz[3 * p + 1], xyz[3 * p + 2], c);
   const int64_t plane = (int64_t)g.sx * g.sy * g.sz;
   // d(voxel coord)/d(world coord) per axis
-  const float kx = (g.sx - 1) / (g.mx[0] - g.mn[0]);
-  const float ky = (g.sy - 1) / (g.mx[1] - g.mn[1]);
-  const float kz = (g.sz - 1) / (g.mx[2] - g.mn[2]);
+  const float kx = c.mx_ * (g.sx - 1) / (g.mx[0] - g.mn[0]);
+  const float ky = c.my_ * (g.sy - 1) / (g.mx[1] - g.mn[1]);
+  const float kz = c.mz_ * (g.sz - 1) / (g.mx[2] - g.mn[2]);
   for (int ch = 0; ch < n_ch; ++ch) {
     const float* gp = grid + ch * plane;
     float v[8];
@@ -138,9 +146,9 @@ trilinear_bwd_kernel(const float* __restrict__ grid, int n_ch, GridGeom g,
     }
   }
   if (grad_xyz) {
-    grad_xyz[3 * p] = gX * ((g.sx - 1) / (g.mx[0] - g.mn[0]));
-    grad_xyz[3 * p + 1] = gY * ((g.sy - 1) / (g.mx[1] - g.mn[1]));
-    grad_xyz[3 * p + 2] = gZ * ((g.sz - 1) / (g.mx[2] - g.mn[2]));
+    grad_xyz[3 * p] = gX * (c.mx_ * (g.sx - 1) / (g.mx[0] - g.mn[0]));
+    grad_xyz[3 * p + 1] = gY * (c.my_ * (g.sy - 1) / (g.mx[1] - g.mn[1]));
+    grad_xyz[3 * p + 2] = gZ * (c.mz_ * (g.sz - 1) / (g.mx[2] - g.mn[2]));
   }
 }
 

@@ -1,0 +1,236 @@
+"""GPU parity of the fused DVGO render / train kernels against the composed-operator CPU oracle
+(oracle/dvgo_cpu.py) and size-independent properties at the BASELINE config-B shape."""
+import pytest
+import torch
+
+from oracle import dvgo_cpu, oracle
+from poseprobe_b200 import synthetic
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pp(cuda):
+    import poseprobe_b200
+    from poseprobe_b200 import dvgo
+    return dvgo
+
+
+def close(a, b, rtol=1e-5, atol=1e-6):
+    torch.testing.assert_close(a.cpu(), b.cpu(), rtol=rtol, atol=atol)
+
+
+def small_scene(G=20, n=300, seed=0, density_scale=3.0):
+    density, k0 = synthetic.make_dvgo_grids(G, seed=seed)
+    density = density * density_scale + 2.0          # dense enough that some rays terminate early
+    o, d = cases.rays_with_edge_cases(n, seed=seed)
+    d = d / d.norm(dim=-1, keepdim=True)
+    mn, mx = [-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]
+    kw = dict(near=0.2, far=1e9, stepdist=0.5 * 2.0 / G, act_shift=synthetic.act_shift(), interval=0.5)
+    return density, k0, o.contiguous(), d.contiguous(), mn, mx, kw
+
+
+@pytest.mark.parametrize("bg,thres", [(0.0, 0.0), (1.0, 0.0), (0.5, 1e-4)])
+def test_render_forward_matches_composed_ops(pp, bg, thres):
+    density, k0, o, d, mn, mx, kw = small_scene()
+    want = dvgo_cpu.render_composed(density, k0, o, d, mn, mx, bg=bg, fast_color_thres=thres, **kw)
+    sc = pp.make_scene(density.shape[2:], mn, mx, kw["near"], kw["far"], kw["stepdist"], kw["act_shift"],
+                       kw["interval"], bg, thres)
+    vox = pp.pack_voxels(density.cuda(), k0.cuda())
+    rgb, last, depth, cnt = pp.render_forward(sc, vox, o.cuda(), d.cuda(), want_count=True)
+    assert int((want["n_marched"] < torch.bincount(want["ray_id"], minlength=o.shape[0])).sum()) > 0, \
+        "scene should exercise early termination"
+    assert torch.equal(cnt.cpu(), want["n_marched"])                  # same samples, same cut index
+    close(last, want["alphainv_last"], rtol=1e-5, atol=1e-7)
+    close(rgb, want["rgb_marched"], rtol=1e-5, atol=1e-6)
+    close(depth, want["depth"], rtol=1e-5, atol=1e-6)
+    # pack / unpack round trip is exact
+    d2, k2 = pp.unpack_voxels(vox, density.shape[2:])
+    assert torch.equal(d2.cpu(), density) and torch.equal(k2.cpu(), k0)
+
+
+@pytest.mark.parametrize("thres", [0.0, 1e-4])
+def test_render_backward_matches_autograd_of_composed_ops(pp, thres):
+    density, k0, o, d, mn, mx, kw = small_scene(seed=1)
+    bg = 0.7
+    dens_t = density.clone().requires_grad_(True)
+    k0_t = k0.clone().requires_grad_(True)
+    out = dvgo_cpu.render_composed(dens_t, k0_t, o, d, mn, mx, bg=bg, fast_color_thres=thres, **kw)
+    g = torch.Generator().manual_seed(3)
+    g_rgb = torch.randn(o.shape[0], 3, generator=g)
+    g_last = torch.randn(o.shape[0], generator=g)
+    ((out["rgb_marched"] * g_rgb).sum() + (out["alphainv_last"] * g_last).sum()).backward()
+    sc = pp.make_scene(density.shape[2:], mn, mx, kw["near"], kw["far"], kw["stepdist"], kw["act_shift"],
+                       kw["interval"], bg, thres)
+    dens_g = density.cuda().requires_grad_(True)
+    k0_g = k0.cuda().requires_grad_(True)
+    rgb, last, depth = pp._RenderFn.apply(dens_g, k0_g, o.cuda(), d.cuda(), sc)
+    ((rgb * g_rgb.cuda()).sum() + (last * g_last.cuda()).sum()).backward()
+    for mine, ref in ((dens_g.grad, dens_t.grad), (k0_g.grad, k0_t.grad)):
+        scale = float(ref.abs().max())
+        close(mine, ref, rtol=1e-4, atol=1e-5 * scale)      # float atomics: summation order differs
+
+
+@pytest.mark.parametrize("loss_w", [(1.0, 0.0, 0.0), (1.0, 0.01, 0.1)])
+def test_train_step_matches_composed_ops_and_masked_adam(pp, loss_w):
+    density, k0, o, d, mn, mx, kw = small_scene(seed=2, n=256)
+    target = torch.rand(o.shape[0], 3, generator=torch.Generator().manual_seed(5))
+    w_rgb, w_ent, w_per = loss_w
+    dens_t = density.clone().requires_grad_(True)
+    k0_t = k0.clone().requires_grad_(True)
+    out = dvgo_cpu.render_composed(dens_t, k0_t, o, d, mn, mx, bg=1.0, **kw)
+    loss, mse = dvgo_cpu.losses(out, target, w_rgb, w_ent, w_per)
+    loss.backward()
+    eng = pp.FusedDVGO(density.cuda(), k0.cuda(), mn, mx, stepsize=0.5, bg=1.0, lr_density=0.1, lr_k0=0.05,
+                       w_rgb=w_rgb, w_entropy_last=w_ent, w_rgbper=w_per)
+    rgb = torch.empty(o.shape[0], 3, device="cuda")
+    eng.backward_only(o.cuda(), d.cuda(), target.cuda(), rgb_out=rgb)
+    close(rgb, out["rgb_marched"].detach(), rtol=1e-5, atol=1e-6)
+    close(eng.loss_buf[0], loss.detach(), rtol=1e-4, atol=1e-7)
+    close(eng.loss_buf[1], mse.detach(), rtol=1e-4, atol=1e-7)
+    gd, gk = eng.export_grad()
+    for mine, ref in ((gd, dens_t.grad), (gk, k0_t.grad)):
+        close(mine, ref, rtol=1e-4, atol=1e-5 * float(ref.abs().max()))
+    # optimiser: masked Adam of the reference kernel on the oracle's gradients
+    pd, pk = density.clone(), k0.clone()
+    for p, gr, lr in ((pd, dens_t.grad, 0.1), (pk, k0_t.grad, 0.05)):
+        dvgo_cpu.masked_adam(p, gr, torch.zeros_like(p), torch.zeros_like(p), 1, 0.9, 0.99, lr, 1e-8)
+    eng.optimizer_step()
+    nd, nk = eng.export_grids()
+    # the first Adam step moves every touched element by ~lr * sign(grad): compare where the gradient is
+    # clearly non-zero (tiny gradients may differ in sign between the two summation orders)
+    for mine, ref, gr in ((nd, pd, dens_t.grad), (nk, pk, k0_t.grad)):
+        solid = gr.abs() > 1e-4 * float(gr.abs().max())
+        close(mine.cpu()[solid], ref[solid], rtol=1e-4, atol=1e-5)
+        untouched = gr == 0
+        assert torch.equal(mine.cpu()[untouched], ref[untouched])
+    assert float(eng.grad.abs().max()) == 0.0            # gradients were reset in the same pass
+
+
+def test_pose_gradient_matches_autograd(pp):
+    """d loss / d rays_o, rays_d through the sample positions == autograd of the dense python sampler
+    (lib/voxurf_coarse.py:697-719 formulas) on a scene without early termination."""
+    G = 16
+    density, k0 = synthetic.make_dvgo_grids(G, seed=4)
+    o, d, _ = synthetic.make_rays(64, seed=9)
+    mn, mx = [-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]
+    stepdist, shift, interval = 0.5 * 2.0 / G, synthetic.act_shift(), 0.5
+    target = torch.rand(64, 3, generator=torch.Generator().manual_seed(6))
+    eng = pp.FusedDVGO(density.cuda(), k0.cuda(), mn, mx, stepsize=0.5, bg=0.3, pose_grad=True)
+    grad_rays = torch.zeros(64, 6, device="cuda")
+    eng.backward_only(o.cuda(), d.cuda(), target.cuda(), grad_rays=grad_rays)
+    # fp64 torch restatement with differentiable sample positions
+    od = o.double().requires_grad_(True)
+    dd = d.double().requires_grad_(True)
+    mn_t, mx_t = torch.tensor(mn).double(), torch.tensor(mx).double()
+    pts_f, mask, ray_id, step_id, *_ = oracle.sample_pts_on_rays(o, d, torch.tensor(mn), torch.tensor(mx), 0.2, 1e9,
+                                                                 stepdist)
+    keep = ~mask
+    ray_id, step_id = ray_id[keep], step_id[keep]
+    vec = torch.where(dd == 0, torch.full_like(dd, 1e-6), dd)
+    t_min = torch.minimum((mx_t - od) / vec, (mn_t - od) / vec).amax(-1).clamp(min=0.2, max=1e9)
+    interpx = t_min[ray_id] + (step_id * stepdist) / dd.norm(dim=-1)[ray_id]
+    pts = od[ray_id] + dd[ray_id] * interpx[:, None]
+    dens = oracle.dense_grid_forward(density.double(), pts, mn_t, mx_t)
+    alpha = 1 - torch.exp(-torch.nn.functional.softplus(dens + shift) * interval)
+    # per-ray exclusive cumprod (no early termination in this scene)
+    logT = torch.log1p(-alpha)
+    excl = torch.cumsum(logT, 0) - logT
+    first = torch.cat([torch.tensor([True]), ray_id[1:] != ray_id[:-1]])
+    idx = torch.arange(len(logT))
+    seg_start = torch.cummax(torch.where(first, idx, torch.zeros_like(idx)), 0).values
+    T = torch.exp(excl - excl[seg_start])
+    w = T * alpha
+    rgb = torch.sigmoid(oracle.dense_grid_forward(k0.double(), pts, mn_t, mx_t))
+    last = torch.ones(64, dtype=torch.float64).index_reduce_(0, ray_id, 1 - alpha, "prod")
+    marched = torch.zeros(64, 3, dtype=torch.float64).index_add_(0, ray_id, w[:, None] * rgb) + last[:, None] * 0.3
+    assert float(last.min()) > 1e-3
+    loss = torch.nn.functional.mse_loss(marched, target.double())
+    loss.backward()
+    want = torch.cat([od.grad, dd.grad], -1)
+    scale = float(want.abs().max())
+    close(grad_rays.double(), want, rtol=2e-3, atol=2e-4 * scale)
+
+
+def test_tv_adam_pingpong_matches_reference_sequence(pp):
+    """fused TV + masked Adam == total_variation_add_grad (old kernel) followed by masked_adam_upd."""
+    G = 12
+    density, k0 = synthetic.make_dvgo_grids(G, seed=7)
+    mn, mx = [-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]
+    o, d, _ = synthetic.make_rays(40, seed=3)
+    target = torch.rand(40, 3, generator=torch.Generator().manual_seed(8))
+    for dense in (False, True):
+        eng = pp.FusedDVGO(density.cuda(), k0.cuda(), mn, mx, stepsize=0.5, tv_density=0.3, tv_k0=0.2, tv_dense=dense,
+                           lr_density=0.1, lr_k0=0.02)
+        eng.backward_only(o.cuda(), d.cuda(), target.cuda())
+        gd, gk = [t.cpu() for t in eng.export_grad()]
+        pd, pk = density.clone(), k0.clone()
+        oracle.total_variation_add_grad(pd, gd, 0.3, 0.3, 0.3, dense)
+        oracle.total_variation_add_grad(pk, gk, 0.2, 0.2, 0.2, dense)
+        for p, gr, lr in ((pd, gd, 0.1), (pk, gk, 0.02)):
+            dvgo_cpu.masked_adam(p, gr, torch.zeros_like(p), torch.zeros_like(p), 1, 0.9, 0.99, lr, 1e-8)
+        eng.optimizer_step()
+        nd, nk = eng.export_grids()
+        assert torch.equal(nd.cpu(), pd) and torch.equal(nk.cpu(), pk)     # same roundings as the reference kernels
+
+
+def test_module_drop_in(pp):
+    """DirectVoxGO keeps the reference's parameter names and result-dict keys."""
+    m = pp.DirectVoxGO([-1, -1, -1], [1, 1, 1], num_voxels=20 ** 3, num_voxels_base=20 ** 3, alpha_init=1e-2).cuda()
+    assert set(m.state_dict().keys()) >= {"density", "k0", "xyz_min", "xyz_max"}
+    assert tuple(m.density.shape) == (1, 1, 20, 20, 20) and tuple(m.k0.shape) == (1, 3, 20, 20, 20)
+    with torch.no_grad():
+        m.density.normal_()
+        m.k0.normal_()
+    o, d, v = synthetic.make_rays(100)
+    out = m(o.cuda(), d.cuda(), v.cuda(), global_step=1, near=0.2, far=1e9, stepsize=0.5, bg=1.0)
+    assert set(out) >= {"rgb_marched", "alphainv_cum", "depth", "disp"}
+    torch.nn.functional.mse_loss(out["rgb_marched"], torch.rand(100, 3, device="cuda")).backward()
+    assert float(m.density.grad.abs().sum()) > 0 and float(m.k0.grad.abs().sum()) > 0
+
+
+def test_config_b_full_size_properties(pp):
+    """160^3 grid, 8192 rays, stepsize 0.5 (BASELINE config B): size-independent invariants."""
+    G, N = 160, 8192
+    density, k0 = synthetic.make_dvgo_grids(G)
+    o, d, _ = synthetic.make_rays(N)
+    mn, mx = [-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]
+    o_, d_ = o.cuda(), d.cuda()
+    # (1) partition of unity: with saturated colour and bg = 1, sum(w) + T_last = 1 on every ray
+    eng = pp.FusedDVGO(density.cuda() + 3.0, torch.full_like(k0, 40.0).cuda(), mn, mx, stepsize=0.5, bg=1.0)
+    rgb, last, depth, cnt = eng.render(o_, d_, want_count=True)
+    close(rgb, torch.ones(N, 3), rtol=0, atol=1e-4)
+    assert bool((last >= 0).all()) and bool((last <= 1).all())
+    assert int(cnt.min()) >= 1 and int(cnt.max()) <= synthetic.dense_n_samples(G, 0.5)
+    assert bool((last[cnt < cnt.max()] < 1.0).all())
+    # (2) the train kernel's forward half is the render kernel
+    eng = pp.FusedDVGO(density.cuda(), k0.cuda(), mn, mx, stepsize=0.5, bg=0.0)
+    target = torch.rand(N, 3, generator=torch.Generator().manual_seed(1)).cuda()
+    rgb_r, *_ = eng.render(o_, d_)
+    rgb_t = torch.empty(N, 3, device="cuda")
+    eng.loss_buf.zero_()
+    eng.backward_only(o_, d_, target, rgb_out=rgb_t)
+    assert torch.equal(rgb_r, rgb_t)
+    close(eng.loss_buf[1], torch.nn.functional.mse_loss(rgb_r, target), rtol=1e-4, atol=1e-7)
+    # (3) directional derivative: <grad, delta> matches a central finite difference of the loss
+    g = torch.Generator().manual_seed(2)
+    delta = torch.randn(eng.vox.shape, generator=g).cuda()
+    lin = float((eng.grad.double() * delta.double()).sum())
+    eps = 1e-2
+    vox0 = eng.vox.clone()
+
+    def loss_at(v):
+        eng.vox = v
+        r, *_ = eng.render(o_, d_)
+        return float(torch.nn.functional.mse_loss(r.double(), target.double()))
+    fd = (loss_at(vox0 + eps * delta) - loss_at(vox0 - eps * delta)) / (2 * eps)
+    eng.vox = vox0
+    assert abs(fd - lin) <= 2e-2 * abs(lin) + 1e-7, (fd, lin)
+    # (4) masked Adam: untouched voxels are bit-identical after the step, gradients are reset
+    touched = (eng.grad != 0)
+    before = eng.vox.clone()
+    eng.optimizer_step()
+    assert torch.equal(eng.vox[~touched], before[~touched])
+    assert bool((eng.vox[touched] != before[touched]).float().mean() > 0.99)
+    assert float(eng.grad.abs().max()) == 0.0

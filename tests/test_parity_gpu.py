@@ -264,7 +264,7 @@ def test_alpha2weight_full_size(pp):
     assert bool((last[terminated] < 1e-3).all()) and bool((last[~terminated] >= 1e-3).all())
     # sum of weights + final transmittance == 1 on every ray (telescoping identity)
     tot = torch.zeros(n_rays, device="cuda").index_add_(0, ray_id, weight) + last
-    close(tot, torch.ones(n_rays), rtol=0, atol=2e-5)
+    close(tot, torch.ones(n_rays), rtol=0, atol=1e-4)    # ~460 float roundings per ray
 
 
 # --------------------------------------------------------------------------------------------
@@ -441,10 +441,15 @@ def test_neus_alpha(pp):
     got = pp.ops.neus_alpha(viewdirs.cuda(), ray_id.cuda(), dist, sdf_g, grad_g, inv_s)
     close(got, want, rtol=1e-5, atol=1e-6)
     go = torch.randn(m, generator=g)
-    want.backward(go)
     got.backward(go.cuda())
-    close(sdf_g.grad, sdf_t.grad, rtol=1e-4, atol=1e-5)
-    close(grad_g.grad, grad_t.grad, rtol=1e-4, atol=1e-6)
+    # the two sigmoid branches nearly cancel in d alpha / d sdf, so fp32 autograd is itself only good to
+    # ~1e-5 of the gradient scale: judge against the same formula evaluated in fp64
+    sdf_d = sdf.double().requires_grad_(True)
+    grad_d = grad.double().requires_grad_(True)
+    oracle.neus_alpha(viewdirs.double(), ray_id, dist, sdf_d, grad_d, inv_s).backward(go.double())
+    for mine, ref64 in ((sdf_g.grad, sdf_d.grad), (grad_g.grad, grad_d.grad)):
+        scale = float(ref64.abs().max())
+        close(mine.double(), ref64, rtol=1e-4, atol=2e-6 * scale)
 
 
 # --------------------------------------------------------------------------------------------
