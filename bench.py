@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- train rays/s (fwd+bwd+optimiser) of the voxel-grid volume-rendering hot path.
+
+Workload (BASELINE.json configs[1], "config B"): DVGO coarse stage, 160^3 density + 3-channel colour
+grid, 8192 rays per batch per GPU, stepsize 0.5, synthetic rays / random-init grids (seed 777,
+SURVEY.md section 8d).  A step = sample -> gather -> alpha -> composite -> colour -> MSE -> backward
+(grid scatter) -> masked Adam on all grids (+ grid-gradient all-reduce when N > 1).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  `value` is device-timed throughput with inputs resident in HBM;
+`e2e` is the same metric through the public Python API with pinned-host inputs copied in and the loss
+copied out every step.  `--impl reference` times the reference formulation on the host CPU.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+GRID = 160
+RAYS = 8192
+STEPSIZE = 0.5
+N_BATCHES = 8          # distinct ray batches cycled through the timed region
+XYZ_MIN, XYZ_MAX = [-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc, self.lines = None, []
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_batches(n_batches, n_rays, rank):
+    from poseprobe_b200 import synthetic
+    out = []
+    for b in range(n_batches):
+        o, d, _ = synthetic.make_rays(n_rays, seed=777 + 1000 * rank + b)
+        tgt = torch.rand(n_rays, 3, generator=torch.Generator().manual_seed(99 + 1000 * rank + b))
+        out.append((o, d, tgt))
+    return out
+
+
+# =================================================================================================
+# reference arm: the reference's own pure-PyTorch CPU formulation (lib/dvgo_ori.py), host cores
+# =================================================================================================
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    from oracle import dvgo_cpu
+    from poseprobe_b200 import synthetic
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    density, k0 = synthetic.make_dvgo_grids(GRID)
+    base = dvgo_cpu.DenseBaseline(density, k0, XYZ_MIN, XYZ_MAX, STEPSIZE)
+    o, d, tgt = make_batches(1, RAYS, 0)[0]
+    n = bounded_sample_rays(base, o, d, tgt, budget_s=4.0)
+    for _ in range(args.warmup):
+        base.train_step(o[:n], d[:n], tgt[:n])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        base.train_step(o[:n], d[:n], tgt[:n])
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port",
+                         "sample": "%d of %d rays per step, lib/dvgo_ori.py dense formulation "
+                                   "(grid_sample + cumprod + Python Adam) restated in oracle/dvgo_cpu.py" % (n, RAYS)},
+        "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def bounded_sample_rays(base, o, d, tgt, budget_s):
+    """Largest ray count (multiple of 256, <= RAYS) whose CPU step fits the time budget: two probe steps
+    give the fixed (dense Adam over the whole grid) and per-ray costs."""
+    times = []
+    for n in (256, 1024):
+        t0 = time.perf_counter()
+        base.train_step(o[:n], d[:n], tgt[:n])
+        times.append(time.perf_counter() - t0)
+    per_ray = max((times[1] - times[0]) / (1024 - 256), 1e-6)
+    fixed = max(times[0] - 256 * per_ray, 0.0)
+    n = int((budget_s - fixed) / per_ray)
+    return max(256, min(RAYS, (n // 256) * 256))
+
+
+def workload_config(n_gpus):
+    return {"workload": "DVGO coarse stage (BASELINE configs[1]): 160^3 density+k0(3) grid, 8192 rays/batch/GPU, "
+                        "stepsize 0.5, fwd+bwd+masked Adam, TV off",
+            "grid": GRID, "rays_per_gpu": RAYS, "global_rays": RAYS * n_gpus, "stepsize": STEPSIZE,
+            "l2": "no flush: per-step working set (vox+grad+2 Adam moments = 262 MB) exceeds the 126 MB L2",
+            "parallelism": "ray-sharded replicas, grid-gradient all-reduce (NCCL)" if n_gpus > 1 else "single GPU"}
+
+
+# =================================================================================================
+# our arm
+# =================================================================================================
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    import poseprobe_b200 as pp
+    from poseprobe_b200 import dvgo, synthetic
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    density, k0 = synthetic.make_dvgo_grids(GRID)
+    eng = dvgo.FusedDVGO(density.to(dev), k0.to(dev), XYZ_MIN, XYZ_MAX, stepsize=STEPSIZE)
+    host = [tuple(t.pin_memory() for t in b) for b in make_batches(N_BATCHES, RAYS, rank)]
+    resident = [tuple(t.to(dev) for t in b) for b in host]
+
+    def step_resident(i):
+        o, d, tgt = resident[i % N_BATCHES]
+        eng.loss_buf.zero_()
+        eng.backward_only(o, d, tgt)
+        if world > 1:
+            dist.all_reduce(eng.grad)
+        eng.optimizer_step()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # samples actually composited per batch (for the algorithmic byte count)
+    counts = []
+    for o, d, _ in resident:
+        _, _, _, cnt = eng.render(o, d, want_depth=False, want_count=True)
+        counts.append(int(cnt.sum()))
+    m_bar = sum(counts) / len(counts)
+
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    barrier()
+
+    # ---- timed region (device timed, max over ranks) ----
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = pp._lib.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+             torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        o, d, tgt = resident[i % N_BATCHES]
+        eng.loss_buf.zero_()
+        k_ev[i][0].record()
+        eng.backward_only(o, d, tgt)
+        k_ev[i][1].record()
+        if world > 1:
+            dist.all_reduce(eng.grad)
+        eng.optimizer_step()
+        k_ev[i][2].record()
+    ev[1].record()
+    barrier()
+    launches = pp._lib.launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    ms = torch.tensor([ev[0].elapsed_time(ev[1])], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms)
+    march_ms = sum(a.elapsed_time(b) for a, b, _ in k_ev) / args.steps
+    tail_ms = sum(b.elapsed_time(c) for _, b, c in k_ev) / args.steps
+
+    # ---- end to end through the public API: pinned host inputs in, loss out, every step ----
+    stream = torch.cuda.current_stream()
+    dbuf = [torch.empty_like(t) for t in resident[0]]
+    loss_host = torch.zeros(2).pin_memory()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        for dst, src in zip(dbuf, host[i % N_BATCHES]):
+            dst.copy_(src, non_blocking=True)
+        eng.loss_buf.zero_()
+        eng.backward_only(*dbuf)
+        if world > 1:
+            dist.all_reduce(eng.grad)
+        eng.optimizer_step()
+        loss_host.copy_(eng.loss_buf, non_blocking=True)
+        stream.synchronize()              # the caller reads the loss of every step
+    e1.record()
+    barrier()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_ms)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk, pk_kind = peaks()
+    V = GRID ** 3
+    C_d, C_f = 1, 3
+    sparse_bytes = 60 * RAYS + 96 * (C_d + C_f) * m_bar            # rays + gathers + scatters
+    dense_bytes = 32 * V * (C_d + C_f)                             # Adam 28 B/elem + grad zeroing 4 B/elem
+    step_bytes = sparse_bytes + dense_bytes
+    march_gbs = sparse_bytes / (march_ms * 1e-3) / 1e9
+    step_gbs = step_bytes / (ms_total / args.steps * 1e-3) / 1e9
+    value = world * RAYS * args.steps / (ms_total * 1e-3)
+    line = {
+        "metric": "train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(world),
+        "samples_per_ray": m_bar / RAYS,
+        "roofline": {"bound": "hbm", "kernel": "dvgo_march_kernel<train> (gather + composite + loss + scatter)",
+                     "achieved": march_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": march_gbs / pk["hbm_gbs"],
+                     "peak_kind": pk_kind, "algorithmic_bytes_per_launch": sparse_bytes,
+                     "ms_per_launch": march_ms, "traffic": None},
+        "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "achieved": step_gbs,
+                          "frac": step_gbs / pk["hbm_gbs"], "march_ms": march_ms,
+                          "allreduce_plus_adam_ms": tail_ms},
+        "e2e": {"value": world * RAYS * args.steps / (e2e_ms * 1e-3), "unit": "rays/s",
+                "h2d_bytes_per_step": sum(t.numel() * 4 for t in host[0]), "d2h_bytes_per_step": 8,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline()
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline():
+    """The reference's pure-PyTorch CPU path on a bounded sample of the same workload (rank 0, N=1)."""
+    from oracle import dvgo_cpu
+    from poseprobe_b200 import synthetic
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    density, k0 = synthetic.make_dvgo_grids(GRID)
+    base = dvgo_cpu.DenseBaseline(density, k0, XYZ_MIN, XYZ_MAX, STEPSIZE)
+    o, d, tgt = make_batches(1, RAYS, 0)[0]
+    n = bounded_sample_rays(base, o, d, tgt, budget_s=3.0)
+    t0 = time.perf_counter()
+    steps = 0
+    while steps < 3 or (time.perf_counter() - t0 < 10 and steps < 20):
+        base.train_step(o[:n], d[:n], tgt[:n])
+        steps += 1
+    dt = time.perf_counter() - t0
+    return {"value": n * steps / dt, "unit": "rays/s", "cores": cores, "kind": "port",
+            "sample": "%d steps of %d of the %d rays (lib/dvgo_ori.py dense formulation, oracle/dvgo_cpu.py)"
+                      % (steps, n, RAYS)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU fallback)")
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()
