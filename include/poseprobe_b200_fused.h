@@ -59,6 +59,12 @@ PP_API int pp_dvgo_render_forward(const pp_dvgo_scene* scene, const void* vox, c
                                   float* alphainv_last, float* depth, int32_t* n_marched,
                                   pp_stream_t stream);
 
+/* Scratch the backward / train entry points need: one float4 per step for every ray in flight (the
+ * per-sample colour and d sigma/d alpha computed by the forward half, re-read by the reverse half; it
+ * is written and read by the same warp within microseconds, so it lives in L2).  Depends only on the
+ * scene (steps per ray) and the device (resident warps). */
+PP_API int64_t pp_dvgo_workspace_bytes(const pp_dvgo_scene* scene);
+
 /* Backward of the render for arbitrary losses on (rgb_marched, alphainv_last): recomputes the march,
  * then walks the ray in reverse and accumulates d loss / d vox into grad_vox (float4 records, +=).
  * grad_alphainv_last may be null.  grad_rays (optional, [N,6] = d loss/d rays_o | d loss/d rays_d)
@@ -66,7 +72,7 @@ PP_API int pp_dvgo_render_forward(const pp_dvgo_scene* scene, const void* vox, c
 PP_API int pp_dvgo_render_backward(const pp_dvgo_scene* scene, const void* vox, const float* rays_o,
                                    const float* rays_d, int64_t n_rays, const float* grad_rgb_marched,
                                    const float* grad_alphainv_last, void* grad_vox, float* grad_rays,
-                                   pp_stream_t stream);
+                                   void* workspace, int64_t workspace_bytes, pp_stream_t stream);
 
 /* Fused forward + loss + backward for the DVGO training losses against target [N,3]:
  *   loss = w_rgb * mean((rgb_marched - target)^2) [+ entropy_last + rgbper terms]
@@ -76,7 +82,8 @@ PP_API int pp_dvgo_render_backward(const pp_dvgo_scene* scene, const void* vox, 
 PP_API int pp_dvgo_train_step(const pp_dvgo_scene* scene, const pp_dvgo_loss* loss, const void* vox,
                               const float* rays_o, const float* rays_d, const float* target,
                               int64_t n_rays, void* grad_vox, float* rgb_marched, float* loss_out,
-                              float* grad_rays, pp_stream_t stream);
+                              float* grad_rays, void* workspace, int64_t workspace_bytes,
+                              pp_stream_t stream);
 
 /* Masked Adam on voxel records, per element exactly masked_adam_upd (adam_upd_kernel.cu:25-40, step size
  * :72) with separate learning rates for the density channel and the three k0 channels; gradients are

@@ -19,6 +19,10 @@
 // Sample positions, step counts and the in-box test are computed with exactly the arithmetic of the
 // stand-alone sampler (ray_math.cuh), so the set of samples is identical to sample_pts_on_rays + the
 // `~mask_outbbox` compaction of the reference's Python wrapper (voxurf_coarse.py:686-693).
+#include <stdlib.h>
+
+#include <atomic>
+
 #include "../../include/poseprobe_b200_fused.h"
 #include "common.cuh"
 #include "ray_math.cuh"
@@ -32,7 +36,10 @@ struct Cell {
   int base;           // record index of the (x0,y0,z0) corner
   int ex, ey, ez;     // record strides towards the +X/+Y/+Z corner (0 on the max face: weight is 0)
   float fx, fy, fz;   // fractional position inside the cell
-  float gx, gy, gz;   // complements, computed as (floor+1) - i like ATen does
+  // complements: ATen computes (floor+1) - i, whose exact value is 1 - f, so 1.f - f rounds identically
+  __device__ __forceinline__ float gx() const { return 1.f - fx; }
+  __device__ __forceinline__ float gy() const { return 1.f - fy; }
+  __device__ __forceinline__ float gz() const { return 1.f - fz; }
 };
 
 // ATen-order continuous voxel index (see grid.cu voxel_coord) for a point known to be inside the box.
@@ -53,9 +60,9 @@ __device__ __forceinline__ Cell make_cell(const pp_dvgo_scene& sc, float px, flo
   iy = fminf(fmaxf(iy, 0.f), static_cast<float>(sc.sy - 1));
   iz = fminf(fmaxf(iz, 0.f), static_cast<float>(sc.sz - 1));
   const float x0 = floorf(ix), y0 = floorf(iy), z0 = floorf(iz);
-  c.fx = ix - x0; c.gx = (x0 + 1.f) - ix;
-  c.fy = iy - y0; c.gy = (y0 + 1.f) - iy;
-  c.fz = iz - z0; c.gz = (z0 + 1.f) - iz;
+  c.fx = ix - x0;
+  c.fy = iy - y0;
+  c.fz = iz - z0;
   const int xi = static_cast<int>(x0), yi = static_cast<int>(y0), zi = static_cast<int>(z0);
   c.base = (xi * sc.sy + yi) * sc.sz + zi;
   c.ez = (zi + 1 < sc.sz) ? 1 : 0;
@@ -69,12 +76,19 @@ __device__ __forceinline__ int corner_off(const Cell& c, int q) {
 }
 __device__ __forceinline__ float corner_w(const Cell& c, int q) {
   // (Z term * Y term) * X term : ATen's tnw..bse product order
-  return mul_rn(mul_rn((q & 1) ? c.fz : c.gz, (q & 2) ? c.fy : c.gy), (q & 4) ? c.fx : c.gx);
+  return mul_rn(mul_rn((q & 1) ? c.fz : c.gz(), (q & 2) ? c.fy : c.gy()), (q & 4) ? c.fx : c.gx());
 }
 
 __device__ __forceinline__ void gather8(const float4* __restrict__ vox, const Cell& c, float4 (&v)[8]) {
 #pragma unroll
   for (int q = 0; q < 8; ++q) v[q] = __ldg(vox + corner_off(c, q));
+}
+
+// pull the 8 corner records of a future sample towards L1 (no registers are tied up)
+__device__ __forceinline__ void prefetch8(const float4* __restrict__ vox, const Cell& c) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(vox + corner_off(c, q)));
 }
 
 __device__ __forceinline__ float4 interp8(const Cell& c, const float4 (&v)[8]) {
@@ -96,7 +110,8 @@ __device__ __forceinline__ void red_add_v4(float4* addr, float a, float b, float
                : "memory");
 }
 
-__device__ __forceinline__ float sigmoid_ref(float x) { return 1.f / (1.f + expf(-x)); }
+// sigmoid with the SFU exponential and reciprocal (<= ~4e-7 relative to torch.sigmoid)
+__device__ __forceinline__ float sigmoid_ref(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 
 // ---- per-ray state ---------------------------------------------------------------------------------
 struct Ray {
@@ -135,31 +150,72 @@ __device__ __forceinline__ bool sample_point(const pp_dvgo_scene& sc, const Ray&
   return !out;
 }
 
-// raw2alpha, bit-identical to the stand-alone kernel (alpha.cu / reference :437-442)
+// raw2alpha (reference :437-442): alpha = 1 - (1+e)^(-interval), e = exp(sigma + shift).  The power is
+// evaluated as exp2(-interval * log2(1+e)) with the accurate log2f/exp2f (a third of powf's
+// instructions); it agrees with powf to ~3e-7 in the power, the same distance libm's powf has.
 __device__ __forceinline__ float density_to_alpha(float sigma, float shift, float interval, float& e) {
   e = expf(sigma + shift);
-  return 1.f - powf(1.f + e, -interval);
+  return 1.f - exp2f(-interval * log2f(1.f + e));
 }
 
 // ---- the march ------------------------------------------------------------------------------------
-// dynamic shared memory: per warp, s_alpha[cap] then s_T[cap]
-template <int kMode, bool kPoseGrad>
-__global__ void __launch_bounds__(256)
+struct LaneSample {
+  bool live;
+  Cell c;
+};
+
+__device__ __forceinline__ LaneSample lane_sample(const pp_dvgo_scene& sc, const Ray& ray, int i, int limit) {
+  LaneSample s;
+  float p[3];
+  s.live = (i >= 0) && (i < limit) && sample_point(sc, ray, i, p);
+  if (s.live) s.c = make_cell(sc, p[0], p[1], p[2]);
+  return s;
+}
+
+// inclusive product scan over the lanes; returns inclusive P and exclusive Pex
+__device__ __forceinline__ void lane_product_scan(float q, int lane, float& P, float& Pex) {
+  P = q;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float up = __shfl_up_sync(kFull, P, o);
+    if (lane >= o) P *= up;
+  }
+  Pex = __shfl_up_sync(kFull, P, 1);
+  if (lane == 0) Pex = 1.f;
+}
+
+// rays are handed out through a device-side queue so that long and short rays balance across warps
+constexpr int kQueueSlots = 64;
+__device__ unsigned int g_ray_queue[kQueueSlots];
+
+// dynamic shared memory: per warp, s_alpha[cap] (alpha of every step, 0 where nothing was composited)
+// followed by s_tin[cap/32] (transmittance entering each 32-step chunk)
+template <int kMode, bool kPoseGrad, int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks)
 dvgo_march_kernel(pp_dvgo_scene sc, pp_dvgo_loss ls, const float4* __restrict__ vox,
                   const float* __restrict__ rays_o, const float* __restrict__ rays_d, int64_t n_rays,
                   const float* __restrict__ target, const float* __restrict__ grad_rgb_in,
                   const float* __restrict__ grad_last_in, float4* __restrict__ grad_vox,
                   float* __restrict__ rgb_marched, float* __restrict__ alphainv_last,
                   float* __restrict__ depth, int32_t* __restrict__ n_marched,
-                  float* __restrict__ loss_out, float* __restrict__ grad_rays, int cap) {
+                  float* __restrict__ loss_out, float* __restrict__ grad_rays, int cap,
+                  unsigned int* __restrict__ queue, float4* __restrict__ stash_base, int flags) {
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int warps_per_block = blockDim.x >> 5;
-  float* s_alpha = smem + (size_t)warp * 2 * cap;
-  float* s_T = s_alpha + cap;
+  const int per_warp = cap + cap / kWarp;
+  float* s_alpha = smem + (size_t)warp * per_warp;
+  float* s_tin = s_alpha + cap;
+  // per-warp slice of the caller's workspace: (d sigma / d alpha, r, g, b) of every step of the ray in
+  // flight, written coalesced in pass 1 and read back coalesced in pass 2 (it stays L2 resident), so the
+  // reverse walk does not gather the 8 corner records again
+  float4* stash = stash_base ? stash_base + ((size_t)blockIdx.x * (blockDim.x >> 5) + warp) * cap : nullptr;
 
-  for (int64_t r = blockIdx.x * (int64_t)warps_per_block + warp; r < n_rays;
-       r += (int64_t)gridDim.x * warps_per_block) {
+  for (;;) {
+    unsigned int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(queue, 1u);
+    const int64_t r = __shfl_sync(kFull, ticket, 0);
+    if (r >= n_rays) break;
+
     const Ray ray = setup_ray(sc, rays_o, rays_d, r);
     const int n_steps = (kMode == kModeForward) ? ray.n_steps : min(ray.n_steps, cap);
 
@@ -170,46 +226,45 @@ dvgo_march_kernel(pp_dvgo_scene sc, pp_dvgo_loss ls, const float4* __restrict__ 
     int end = n_steps;          // exclusive index of the last composited step (+1)
     float tgt[3] = {0.f, 0.f, 0.f};
     if (kMode == kModeTrain) load3(target, r, tgt);
+    LaneSample cur = lane_sample(sc, ray, lane, n_steps);
     for (int base = 0; base < n_steps; base += kWarp) {
       const int i = base + lane;
-      float p[3];
-      const bool live = (i < n_steps) && sample_point(sc, ray, i, p);
-      float alpha = 0.f;
+      // software pipeline: the next chunk's cell is computed now and its records start moving towards L1
+      LaneSample nxt = lane_sample(sc, ray, i + kWarp, n_steps);
+      if ((flags & 1) && nxt.live) prefetch8(vox, nxt.c);
+      float alpha = 0.f, e = 0.f;
       float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (live) {
-        const Cell c = make_cell(sc, p[0], p[1], p[2]);
+      if (cur.live) {
         float4 v[8];
-        gather8(vox, c, v);
-        val = interp8(c, v);
-        float e;
+        gather8(vox, cur.c, v);
+        val = interp8(cur.c, v);
         alpha = density_to_alpha(val.x, sc.act_shift, sc.interval, e);
       }
-      // inclusive product scan of (1 - alpha)
-      float P = 1.f - alpha;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const float up = __shfl_up_sync(kFull, P, o);
-        if (lane >= o) P *= up;
-      }
-      float Pex = __shfl_up_sync(kFull, P, 1);
-      if (lane == 0) Pex = 1.f;
+      float P, Pex;
+      lane_product_scan(1.f - alpha, lane, P, Pex);
       const float T_before = T_in * Pex;
       const float T_after = T_in * P;
-      const unsigned term = __ballot_sync(kFull, live && (T_after < 1e-3f));
-      bool counted = live;
+      const unsigned term = __ballot_sync(kFull, cur.live && (T_after < 1e-3f));
+      bool counted = cur.live;
       int last_lane = 31;
       if (term) {
         last_lane = __ffs(term) - 1;
-        counted = live && (lane <= last_lane);
+        counted = cur.live && (lane <= last_lane);
       }
       if (!counted) alpha = 0.f;
-      if (kMode != kModeForward && i < n_steps) {
-        s_alpha[i] = alpha;
-        s_T[i] = T_before;
+      if (kMode != kModeForward) {
+        if (i < n_steps) s_alpha[i] = alpha;
+        if (lane == 0) s_tin[base / kWarp] = T_in;
       }
       const float w = T_before * alpha;
+      float4 keep = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (counted)   // raw2alpha_backward's factor (reference :513-516), (1+e)^(-iv-1) = (1-alpha)/(1+e)
+        keep.x = fminf(e, 1e10f) * ((1.f - alpha) / (1.f + e)) * sc.interval;
       if (counted && w > sc.fast_color_thres) {
         const float cr = sigmoid_ref(val.y), cg = sigmoid_ref(val.z), cb = sigmoid_ref(val.w);
+        keep.y = cr;
+        keep.z = cg;
+        keep.w = cb;
         acc_r = fma_rn(w, cr, acc_r);
         acc_g = fma_rn(w, cg, acc_g);
         acc_b = fma_rn(w, cb, acc_b);
@@ -222,11 +277,13 @@ dvgo_march_kernel(pp_dvgo_scene sc, pp_dvgo_loss ls, const float4* __restrict__ 
         acc_depth = fma_rn(w, sc.stepdist * static_cast<float>(i), acc_depth);
         n_live += 1;
       }
+      if (kMode != kModeForward && i < n_steps) stash[i] = keep;
       T_in = __shfl_sync(kFull, T_after, last_lane);
       if (term) {
         end = base + last_lane + 1;
         break;
       }
+      cur = nxt;
     }
     const float T_last = T_in;
     acc_r = warp_sum(acc_r);
@@ -292,31 +349,21 @@ dvgo_march_kernel(pp_dvgo_scene sc, pp_dvgo_loss ls, const float4* __restrict__ 
     float back = g_last * T_last;   // back_cum of alpha2weight_backward (reference :671)
     float G0[3] = {0.f, 0.f, 0.f}, G1[3] = {0.f, 0.f, 0.f};
     const int last_base = ((end - 1) / kWarp) * kWarp;
+    cur = lane_sample(sc, ray, last_base + lane, end);
+    float4 kept = (last_base + lane < end) ? stash[last_base + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
     for (int base = last_base; base >= 0; base -= kWarp) {
       const int i = base + lane;
-      float p[3];
-      const bool live = (i < end) && sample_point(sc, ray, i, p);
-      float alpha = 0.f, T = 0.f, w = 0.f, gw = 0.f, e = 0.f;
-      float rgb[3] = {0.f, 0.f, 0.f};
-      bool col = false;
-      Cell c;
-      float4 v[8];
-      if (live) {
-        alpha = s_alpha[i];
-        T = s_T[i];
-        c = make_cell(sc, p[0], p[1], p[2]);
-        gather8(vox, c, v);
-        const float4 val = interp8(c, v);
-        e = expf(val.x + sc.act_shift);
-        w = T * alpha;
-        col = w > sc.fast_color_thres;
-        if (col) {
-          rgb[0] = sigmoid_ref(val.y);
-          rgb[1] = sigmoid_ref(val.z);
-          rgb[2] = sigmoid_ref(val.w);
-          gw = g[0] * rgb[0] + g[1] * rgb[1] + g[2] * rgb[2];
-        }
-      }
+      const LaneSample nxt = lane_sample(sc, ray, i - kWarp, end);
+      const float4 kept_nxt = (i - kWarp >= 0) ? stash[i - kWarp] : make_float4(0.f, 0.f, 0.f, 0.f);
+      // transmittance of this chunk, recomputed exactly as in pass 1 from the staged alphas
+      const float alpha = (i < end) ? s_alpha[i] : 0.f;
+      float P, Pex;
+      lane_product_scan(1.f - alpha, lane, P, Pex);
+      const float T = s_tin[base / kWarp] * Pex;
+      const float w = cur.live ? T * alpha : 0.f;
+      const bool col = w > sc.fast_color_thres;
+      const float rgb[3] = {kept.y, kept.z, kept.w};
+      const float gw = col ? g[0] * rgb[0] + g[1] * rgb[1] + g[2] * rgb[2] : 0.f;
       // exclusive suffix sum of gw*w over the lanes above me
       const float contrib = gw * w;
       float S = contrib;
@@ -327,56 +374,85 @@ dvgo_march_kernel(pp_dvgo_scene sc, pp_dvgo_loss ls, const float4* __restrict__ 
       }
       const float back_i = back + (S - contrib);
       back += __shfl_sync(kFull, S, 0);
-      if (live) {
+      // per-sample gradient wrt the interpolated record (density, k0_r, k0_g, k0_b)
+      float4 d = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (cur.live) {
         const float d_alpha = gw * T - back_i / (1.f - alpha + 1e-10f);
-        // raw2alpha_backward (reference :513-516)
-        const float d_sigma = fminf(e, 1e10f) * powf(1.f + e, -sc.interval - 1.f) * sc.interval * d_alpha;
-        float dk[3] = {0.f, 0.f, 0.f};
+        d.x = kept.x * d_alpha;
         if (col) {
+          float gc[3];
 #pragma unroll
           for (int ch = 0; ch < 3; ++ch) {
-            float gc = w * g[ch];
-            if (kMode == kModeTrain) gc += per_scale * w * (rgb[ch] - tgt[ch]);
-            dk[ch] = gc * rgb[ch] * (1.f - rgb[ch]);
+            gc[ch] = w * g[ch];
+            if (kMode == kModeTrain) gc[ch] += per_scale * w * (rgb[ch] - tgt[ch]);
+            gc[ch] *= rgb[ch] * (1.f - rgb[ch]);
           }
-        }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float wq = corner_w(c, q);
-          if (wq != 0.f)
-            red_add_v4(grad_vox + corner_off(c, q), wq * d_sigma, wq * dk[0], wq * dk[1], wq * dk[2]);
-        }
-        if (kPoseGrad) {
-          // d loss / d point = sum_ch d_ch * grad_xyz(interp_ch); voxel units -> world units below
-          float gp[3] = {0.f, 0.f, 0.f};
-          const float dch[4] = {d_sigma, dk[0], dk[1], dk[2]};
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            float u[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              u[q] = ch == 0 ? v[q].x : ch == 1 ? v[q].y : ch == 2 ? v[q].z : v[q].w;
-            const float dX = ((u[4] - u[0]) * c.gz + (u[5] - u[1]) * c.fz) * c.gy +
-                             ((u[6] - u[2]) * c.gz + (u[7] - u[3]) * c.fz) * c.fy;
-            const float dY = ((u[2] - u[0]) * c.gz + (u[3] - u[1]) * c.fz) * c.gx +
-                             ((u[6] - u[4]) * c.gz + (u[7] - u[5]) * c.fz) * c.fx;
-            const float dZ = ((u[1] - u[0]) * c.gy + (u[3] - u[2]) * c.fy) * c.gx +
-                             ((u[5] - u[4]) * c.gy + (u[7] - u[6]) * c.fy) * c.fx;
-            gp[0] += dch[ch] * dX;
-            gp[1] += dch[ch] * dY;
-            gp[2] += dch[ch] * dZ;
-          }
-          gp[0] *= (sc.sx - 1) / (sc.xyz_max[0] - sc.xyz_min[0]);
-          gp[1] *= (sc.sy - 1) / (sc.xyz_max[1] - sc.xyz_min[1]);
-          gp[2] *= (sc.sz - 1) / (sc.xyz_max[2] - sc.xyz_min[2]);
-          const float s = sc.stepdist * static_cast<float>(i);
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            G0[k] += gp[k];
-            G1[k] += gp[k] * s;
-          }
+          d.y = gc[0];
+          d.z = gc[1];
+          d.w = gc[2];
         }
       }
+      // scatter.  Neighbouring lanes are neighbouring steps (half a voxel apart) and often sit in the
+      // same cell: such pairs are merged with one shuffle so the pair issues 8 reductions instead of 16.
+      const Cell& c = cur.c;
+      const int key = cur.live ? c.base : (-1 - lane);
+      const int key_up = __shfl_down_sync(kFull, key, 1);
+      const int key_dn = __shfl_up_sync(kFull, key, 1);
+      const unsigned heads = __ballot_sync(kFull, lane == 0 || key != key_dn);
+      const int run_start = 31 - __clz(heads & ((2u << lane) - 1u));
+      const bool even_pos = ((lane - run_start) & 1) == 0;
+      const bool absorb = (flags & 4) == 0 && cur.live && lane < 31 && key_up == key && even_pos;
+      const bool absorbed = (flags & 4) == 0 && cur.live && lane > 0 && key_dn == key && !even_pos;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float wq = cur.live ? corner_w(c, q) : 0.f;
+        float a0 = wq * d.x, a1 = wq * d.y, a2 = wq * d.z, a3 = wq * d.w;
+        const float b0 = __shfl_down_sync(kFull, a0, 1), b1 = __shfl_down_sync(kFull, a1, 1),
+                    b2 = __shfl_down_sync(kFull, a2, 1), b3 = __shfl_down_sync(kFull, a3, 1);
+        if (absorb) {
+          a0 += b0;
+          a1 += b1;
+          a2 += b2;
+          a3 += b3;
+        }
+        if (cur.live && !absorbed && !(flags & 2) && (a0 != 0.f || a1 != 0.f || a2 != 0.f || a3 != 0.f))
+          red_add_v4(grad_vox + corner_off(c, q), a0, a1, a2, a3);
+      }
+      if (kPoseGrad && cur.live) {
+        // d loss / d point = sum_ch d_ch * grad_xyz(interp_ch); voxel units -> world units below
+        float4 v[8];
+        gather8(vox, c, v);
+        float gp[3] = {0.f, 0.f, 0.f};
+        const float dch[4] = {d.x, d.y, d.z, d.w};
+        const float fx = c.fx, fy = c.fy, fz = c.fz, gx = c.gx(), gy = c.gy(), gz = c.gz();
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          float u[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            u[q] = ch == 0 ? v[q].x : ch == 1 ? v[q].y : ch == 2 ? v[q].z : v[q].w;
+          const float dX = ((u[4] - u[0]) * gz + (u[5] - u[1]) * fz) * gy +
+                           ((u[6] - u[2]) * gz + (u[7] - u[3]) * fz) * fy;
+          const float dY = ((u[2] - u[0]) * gz + (u[3] - u[1]) * fz) * gx +
+                           ((u[6] - u[4]) * gz + (u[7] - u[5]) * fz) * fx;
+          const float dZ = ((u[1] - u[0]) * gy + (u[3] - u[2]) * fy) * gx +
+                           ((u[5] - u[4]) * gy + (u[7] - u[6]) * fy) * fx;
+          gp[0] += dch[ch] * dX;
+          gp[1] += dch[ch] * dY;
+          gp[2] += dch[ch] * dZ;
+        }
+        gp[0] *= (sc.sx - 1) / (sc.xyz_max[0] - sc.xyz_min[0]);
+        gp[1] *= (sc.sy - 1) / (sc.xyz_max[1] - sc.xyz_min[1]);
+        gp[2] *= (sc.sz - 1) / (sc.xyz_max[2] - sc.xyz_min[2]);
+        const float sdist = sc.stepdist * static_cast<float>(i);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          G0[k] += gp[k];
+          G1[k] += gp[k] * sdist;
+        }
+      }
+      cur = nxt;
+      kept = kept_nxt;
     }
     if (kPoseGrad) {
       // point_i = o + d*t_min + (d/|d|) * s_i.  t_min is treated as locally constant in (o, d) except
@@ -389,16 +465,14 @@ dvgo_march_kernel(pp_dvgo_scene sc, pp_dvgo_loss ls, const float4* __restrict__ 
       if (lane == 0) {
         float go[3] = {G0[0], G0[1], G0[2]};
         float gd[3] = {G0[0] * ray.t_min, G0[1] * ray.t_min, G0[2] * ray.t_min};
-        // through t_min
-        float a[3], b[3];
         int axis = -1;
         float best = -INFINITY;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           const float vv = (ray.d[k] == 0.f) ? 1e-6f : ray.d[k];
-          a[k] = (sc.xyz_max[k] - ray.o[k]) / vv;
-          b[k] = (sc.xyz_min[k] - ray.o[k]) / vv;
-          const float m = fminf(a[k], b[k]);
+          const float a = (sc.xyz_max[k] - ray.o[k]) / vv;
+          const float b = (sc.xyz_min[k] - ray.o[k]) / vv;
+          const float m = fminf(a, b);
           if (m > best) { best = m; axis = k; }
         }
         if (best == ray.t_min && ray.d[axis] != 0.f) {   // not clamped by near / far
@@ -406,7 +480,6 @@ dvgo_march_kernel(pp_dvgo_scene sc, pp_dvgo_loss ls, const float4* __restrict__ 
           go[axis] += gdot * (-1.f / ray.d[axis]);
           gd[axis] += gdot * (-ray.t_min / ray.d[axis]);
         }
-        // through dir = d/|d|
         const float inv = 1.f / ray.rnorm;
         const float dotg = (G1[0] * ray.d[0] + G1[1] * ray.d[1] + G1[2] * ray.d[2]) * inv * inv * inv;
 #pragma unroll
@@ -551,37 +624,77 @@ static int step_capacity(const pp_dvgo_scene* sc) {
   return (n + 31) / 32 * 32;
 }
 
-template <int kMode, bool kPoseGrad>
-static int launch_march(const pp_dvgo_scene* sc, const pp_dvgo_loss* ls, const void* vox,
+static int tune_env(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+template <int kMode, bool kPoseGrad, int kMinBlocks>
+static int launch_march_occ(const pp_dvgo_scene* sc, const pp_dvgo_loss* ls, const void* vox,
                         const float* rays_o, const float* rays_d, int64_t n_rays, const float* target,
                         const float* grad_rgb, const float* grad_last, void* grad_vox,
                         float* rgb_marched, float* alphainv_last, float* depth, int32_t* n_marched,
-                        float* loss_out, float* grad_rays, cudaStream_t s, const char* who) {
+                        float* loss_out, float* grad_rays, void* workspace, int64_t workspace_bytes,
+                        cudaStream_t s, const char* who) {
   int warps = 8;
   int cap = 0;
   size_t smem = 0;
   if (kMode != kModeForward) {
     cap = step_capacity(sc);
-    smem = (size_t)warps * 2 * cap * sizeof(float);
+    const size_t per_warp = (size_t)(cap + cap / kWarp) * sizeof(float);
+    smem = warps * per_warp;
     while (smem > 200 * 1024 && warps > 1) {
       warps /= 2;
-      smem = (size_t)warps * 2 * cap * sizeof(float);
+      smem = warps * per_warp;
     }
     PP_REQUIRE(smem <= 200 * 1024, PP_ERR_UNSUPPORTED,
                "%s: %d steps per ray exceed the shared-memory staging capacity", who, cap);
   }
-  auto kernel = dvgo_march_kernel<kMode, kPoseGrad>;
+  auto kernel = dvgo_march_kernel<kMode, kPoseGrad, kMinBlocks>;
   if (smem > 48 * 1024)
     PP_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // persistent grid: every resident warp pulls rays from a device-side queue
+  static std::atomic<unsigned> next_slot{0};
+  static unsigned int* queue_base = nullptr;
+  if (!queue_base) PP_CHECK_CUDA(cudaGetSymbolAddress((void**)&queue_base, g_ray_queue));
+  unsigned int* queue = queue_base + (next_slot.fetch_add(1) % kQueueSlots);
+  PP_CHECK_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned int), s));
+  int per_sm = 0;
+  PP_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem));
+  if (per_sm < 1) per_sm = 1;
   const int64_t blocks_needed = (n_rays + warps - 1) / warps;
-  const int64_t blocks = min64(blocks_needed, (int64_t)sm_count() * 64);
+  const int64_t blocks = min64(blocks_needed, (int64_t)sm_count() * per_sm);
+  if (kMode != kModeForward) {
+    const int64_t need = blocks * warps * (int64_t)cap * (int64_t)sizeof(float4);
+    PP_REQUIRE(workspace && workspace_bytes >= need, PP_ERR_INVALID_ARG,
+               "%s: workspace of %lld bytes required (pp_dvgo_workspace_bytes), got %lld", who,
+               (long long)need, (long long)workspace_bytes);
+  }
   pp_dvgo_loss l = {1.f, 0.f, 0.f};
   if (ls) l = *ls;
   kernel<<<(unsigned)blocks, warps * 32, smem, s>>>(
       *sc, l, (const float4*)vox, rays_o, rays_d, n_rays, target, grad_rgb, grad_last,
-      (float4*)grad_vox, rgb_marched, alphainv_last, depth, n_marched, loss_out, grad_rays, cap);
+      (float4*)grad_vox, rgb_marched, alphainv_last, depth, n_marched, loss_out, grad_rays, cap, queue,
+      (float4*)workspace, tune_env("PP_MARCH_FLAGS", 0));
   PP_CHECK_LAUNCH(who);
   return PP_OK;
+}
+
+template <int kMode, bool kPoseGrad>
+static int launch_march(const pp_dvgo_scene* sc, const pp_dvgo_loss* ls, const void* vox,
+                        const float* rays_o, const float* rays_d, int64_t n_rays, const float* target,
+                        const float* grad_rgb, const float* grad_last, void* grad_vox,
+                        float* rgb_marched, float* alphainv_last, float* depth, int32_t* n_marched,
+                        float* loss_out, float* grad_rays, void* workspace, int64_t workspace_bytes,
+                        cudaStream_t s, const char* who) {
+  // resident blocks per SM the kernel is compiled for (register budget 64 / 80 regs per thread)
+  const int occ = kPoseGrad ? 2 : tune_env("PP_MARCH_OCC", 3);
+#define PP_MARCH_ARGS sc, ls, vox, rays_o, rays_d, n_rays, target, grad_rgb, grad_last, grad_vox, rgb_marched, \
+                      alphainv_last, depth, n_marched, loss_out, grad_rays, workspace, workspace_bytes, s, who
+  if (kPoseGrad) return launch_march_occ<kMode, kPoseGrad, 2>(PP_MARCH_ARGS);
+  if (occ >= 4) return launch_march_occ<kMode, false, 4>(PP_MARCH_ARGS);
+  return launch_march_occ<kMode, false, 3>(PP_MARCH_ARGS);
+#undef PP_MARCH_ARGS
 }
 
 }  // namespace pp
@@ -621,14 +734,21 @@ extern "C" int pp_dvgo_render_forward(const pp_dvgo_scene* scene, const void* vo
   PP_REQUIRE(vox && rays_o && rays_d, PP_ERR_INVALID_ARG, "dvgo_render_forward: null pointer");
   return launch_march<kModeForward, false>(scene, nullptr, vox, rays_o, rays_d, n_rays, nullptr, nullptr,
                                            nullptr, nullptr, rgb_marched, alphainv_last, depth,
-                                           n_marched, nullptr, nullptr, as_stream(stream),
+                                           n_marched, nullptr, nullptr, nullptr, 0, as_stream(stream),
                                            "dvgo_render_forward");
+}
+
+extern "C" int64_t pp_dvgo_workspace_bytes(const pp_dvgo_scene* scene) {
+  if (!scene || scene->stepdist <= 0.f) return 0;
+  // upper bound over every kernel variant: 8 warps per block, at most 4 resident blocks per SM
+  return (int64_t)sm_count() * 4 * 8 * (int64_t)step_capacity(scene) * (int64_t)sizeof(float4);
 }
 
 extern "C" int pp_dvgo_render_backward(const pp_dvgo_scene* scene, const void* vox, const float* rays_o,
                                        const float* rays_d, int64_t n_rays,
                                        const float* grad_rgb_marched, const float* grad_alphainv_last,
-                                       void* grad_vox, float* grad_rays, pp_stream_t stream) {
+                                       void* grad_vox, float* grad_rays, void* workspace,
+                                       int64_t workspace_bytes, pp_stream_t stream) {
   const int rc = check_scene(scene, "dvgo_render_backward");
   if (rc != PP_OK) return rc;
   PP_REQUIRE(n_rays >= 0, PP_ERR_INVALID_ARG, "dvgo_render_backward: n_rays < 0");
@@ -638,18 +758,19 @@ extern "C" int pp_dvgo_render_backward(const pp_dvgo_scene* scene, const void* v
   if (grad_rays)
     return launch_march<kModeBackward, true>(scene, nullptr, vox, rays_o, rays_d, n_rays, nullptr,
                                              grad_rgb_marched, grad_alphainv_last, grad_vox, nullptr,
-                                             nullptr, nullptr, nullptr, nullptr, grad_rays,
-                                             as_stream(stream), "dvgo_render_backward");
+                                             nullptr, nullptr, nullptr, nullptr, grad_rays, workspace,
+                                             workspace_bytes, as_stream(stream), "dvgo_render_backward");
   return launch_march<kModeBackward, false>(scene, nullptr, vox, rays_o, rays_d, n_rays, nullptr,
                                             grad_rgb_marched, grad_alphainv_last, grad_vox, nullptr,
-                                            nullptr, nullptr, nullptr, nullptr, nullptr,
-                                            as_stream(stream), "dvgo_render_backward");
+                                            nullptr, nullptr, nullptr, nullptr, nullptr, workspace,
+                                            workspace_bytes, as_stream(stream), "dvgo_render_backward");
 }
 
 extern "C" int pp_dvgo_train_step(const pp_dvgo_scene* scene, const pp_dvgo_loss* loss, const void* vox,
                                   const float* rays_o, const float* rays_d, const float* target,
                                   int64_t n_rays, void* grad_vox, float* rgb_marched, float* loss_out,
-                                  float* grad_rays, pp_stream_t stream) {
+                                  float* grad_rays, void* workspace, int64_t workspace_bytes,
+                                  pp_stream_t stream) {
   const int rc = check_scene(scene, "dvgo_train_step");
   if (rc != PP_OK) return rc;
   PP_REQUIRE(n_rays >= 0, PP_ERR_INVALID_ARG, "dvgo_train_step: n_rays < 0");
@@ -659,10 +780,12 @@ extern "C" int pp_dvgo_train_step(const pp_dvgo_scene* scene, const pp_dvgo_loss
   if (grad_rays)
     return launch_march<kModeTrain, true>(scene, loss, vox, rays_o, rays_d, n_rays, target, nullptr,
                                           nullptr, grad_vox, rgb_marched, nullptr, nullptr, nullptr,
-                                          loss_out, grad_rays, as_stream(stream), "dvgo_train_step");
+                                          loss_out, grad_rays, workspace, workspace_bytes, as_stream(stream),
+                                          "dvgo_train_step");
   return launch_march<kModeTrain, false>(scene, loss, vox, rays_o, rays_d, n_rays, target, nullptr,
                                          nullptr, grad_vox, rgb_marched, nullptr, nullptr, nullptr,
-                                         loss_out, nullptr, as_stream(stream), "dvgo_train_step");
+                                         loss_out, nullptr, workspace, workspace_bytes, as_stream(stream),
+                                         "dvgo_train_step");
 }
 
 static float adam_step_size(float lr, float beta1, float beta2, int step) {

@@ -77,6 +77,19 @@ def unpack_voxels(vox, world_size):
     return density, k0
 
 
+_workspaces = {}
+
+
+def workspace(scene, device):
+    """Per-device scratch for the backward / train kernels (grown on demand, reused across calls)."""
+    need = int(lib.pp_dvgo_workspace_bytes(ctypes.byref(scene)))
+    ws = _workspaces.get(device)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=device)
+        _workspaces[device] = ws
+    return ws
+
+
 def render_forward(scene, vox, rays_o, rays_d, want_depth=True, want_count=False):
     """-> rgb_marched [N,3], alphainv_last [N], depth [N] | None, n_marched [N] | None"""
     for t, nme in ((vox, "vox"), (rays_o, "rays_o"), (rays_d, "rays_d")):
@@ -118,9 +131,10 @@ class _RenderFn(torch.autograd.Function):
         g_rgb = g_rgb.contiguous() if g_rgb is not None else torch.zeros((n, 3), device=vox.device)
         g_last = g_last.contiguous() if g_last is not None else None
         with torch.cuda.device(vox.device):
+            ws = workspace(ctx.scene, vox.device)
             check(lib.pp_dvgo_render_backward(ctypes.byref(ctx.scene), ptr(vox), ptr(rays_o), ptr(rays_d), n,
-                                              ptr(g_rgb), ptr(g_last), ptr(grad_vox), ptr(grad_rays), stream()),
-                  "dvgo_render_backward")
+                                              ptr(g_rgb), ptr(g_last), ptr(grad_vox), ptr(grad_rays), ptr(ws),
+                                              ws.numel(), stream()), "dvgo_render_backward")
         g_density, g_k0 = unpack_voxels(grad_vox, ctx.world)
         g_o = grad_rays[:, :3].contiguous() if need_rays else None
         g_d = grad_rays[:, 3:].contiguous() if need_rays else None
@@ -199,6 +213,7 @@ class FusedDVGO:
         self.device = self.vox.device
         self.loss_buf = torch.zeros(2, dtype=torch.float32, device=self.device)
         self.n_voxels = self.vox.shape[0]
+        self.ws = workspace(self.scene, self.device)
 
     # -- reference-layout views (checkpoint interchange) --
     def export_grids(self):
@@ -216,7 +231,8 @@ class FusedDVGO:
         with torch.cuda.device(self.device):
             check(lib.pp_dvgo_train_step(ctypes.byref(self.scene), ctypes.byref(self.loss), ptr(self.vox),
                                          ptr(rays_o), ptr(rays_d), ptr(target), n, ptr(self.grad), ptr(rgb_out),
-                                         ptr(self.loss_buf), ptr(grad_rays), stream()), "dvgo_train_step")
+                                         ptr(self.loss_buf), ptr(grad_rays), ptr(self.ws), self.ws.numel(),
+                                         stream()), "dvgo_train_step")
 
     def optimizer_step(self):
         b1, b2, lr_d, lr_k, eps = self.hp
