@@ -102,6 +102,34 @@ PP_API int pp_voxel_tv_adam(const pp_dvgo_scene* scene, const void* vox_in, void
                             float beta2, float lr_density, float lr_k0, float eps, float tv_density,
                             float tv_k0, int dense_mode, pp_stream_t stream);
 
+/* ---- multi-GPU: ray-sharded replicas, voxel-sharded optimiser --------------------------------------
+ * The reference is single-GPU; rays are independent, so each rank marches its own batch
+ * into its own gradient records and the only exchange per step is the voxel gradient / parameter
+ * traffic.  Instead of all-reduce + a full Adam pass on every rank, ONE kernel per rank owns a 1/world
+ * slice of the voxels: it reads that slice of every rank's gradient over NVLink (peer loads = the
+ * reduce-scatter), applies masked Adam once (moments exist only for the slice), and writes the updated
+ * records into every rank's parameter buffer (peer stores = the all-gather).
+ *
+ * Buffers that peers touch must come from pp_shared_alloc (cudaMalloc + IPC handle); handles are
+ * exchanged by the host framework (torch.distributed) and opened with pp_shared_open. */
+#define PP_IPC_HANDLE_BYTES 64
+PP_API int pp_shared_alloc(int64_t bytes, void** ptr_out, void* handle_out);
+PP_API int pp_shared_open(const void* handle, void** ptr_out);
+PP_API int pp_shared_close(void* ptr);
+PP_API int pp_shared_free(void* ptr);
+
+/* vox_ptrs / grad_ptrs: HOST arrays of `world` device pointers (entry `rank` is the local buffer).
+ * exp_avg / exp_avg_sq: local moments of the slice only, pp_voxel_shard_size(n_voxels, world) records.
+ * Slice of rank r: [r*S, min((r+1)*S, n_voxels)), S = pp_voxel_shard_size.  Gradients are summed over
+ * ranks (scale the per-rank loss by 1/world for a global mean).  The caller brackets the launch with
+ * cross-rank stream barriers (all gradients complete before; all slices written after) and zeroes its own
+ * gradient records afterwards. */
+PP_API int64_t pp_voxel_shard_size(int64_t n_voxels, int32_t world);
+PP_API int pp_voxel_adam_exchange(void* const* vox_ptrs, void* const* grad_ptrs, void* exp_avg,
+                                  void* exp_avg_sq, int64_t n_voxels, int32_t world, int32_t rank,
+                                  int32_t step, float beta1, float beta2, float lr_density,
+                                  float lr_k0, float eps, pp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

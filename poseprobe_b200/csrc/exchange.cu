@@ -1,0 +1,152 @@
+// Multi-GPU voxel exchange fused with the optimiser (see include/poseprobe_b200_fused.h).
+//
+// One kernel per rank = reduce-scatter (peer loads of every rank's gradient slice over NVLink 5) +
+// masked Adam on the slice + all-gather (peer stores of the updated records into every rank's
+// parameters).  Per rank and step the NVLink traffic is (world-1)/world of the gradient records in and
+// the same amount of parameter records out - the two directions of the link are used concurrently -
+// and the dense optimiser tail shrinks by 1/world because every voxel is updated exactly once.
+#include <string.h>
+
+#include "../../include/poseprobe_b200_fused.h"
+#include "common.cuh"
+
+namespace pp {
+
+constexpr int kMaxWorld = 16;
+struct PeerPtrs {
+  float4* vox[kMaxWorld];
+  const float4* grad[kMaxWorld];
+};
+
+__device__ __forceinline__ void adam_elem_x(float& p, float g, float& m, float& v, float step_size,
+                                            float b1, float b2, float eps) {
+  if (g == 0.f) return;   // masked_adam_upd (adam_upd_kernel.cu:35)
+  m = fma_rn(b1, m, mul_rn(1.f - b1, g));
+  v = fma_rn(b2, v, mul_rn(mul_rn(1.f - b2, g), g));
+  p = p - mul_rn(step_size, m) / (sqrtf(v) + eps);
+}
+
+template <int kWorld>
+__global__ void __launch_bounds__(256)
+voxel_adam_exchange_kernel(PeerPtrs pp, float4* __restrict__ m4, float4* __restrict__ v4,
+                           int64_t begin, int64_t end, int rank, float ss_density, float ss_k0,
+                           float b1, float b2, float eps) {
+  for (int64_t i = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < end;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    // reduce: one 16-byte load per rank, all issued before the first use; fixed rank order keeps the
+    // sum bit-identical on every rank count run-to-run
+    float4 gr[kWorld];
+#pragma unroll
+    for (int r = 0; r < kWorld; ++r) gr[r] = pp.grad[r][i];
+    float4 g = gr[0];
+#pragma unroll
+    for (int r = 1; r < kWorld; ++r) {
+      g.x += gr[r].x;
+      g.y += gr[r].y;
+      g.z += gr[r].z;
+      g.w += gr[r].w;
+    }
+    if (g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f) continue;
+    float4 p = pp.vox[rank][i];
+    float4 m = m4[i - begin], v = v4[i - begin];
+    adam_elem_x(p.x, g.x, m.x, v.x, ss_density, b1, b2, eps);
+    adam_elem_x(p.y, g.y, m.y, v.y, ss_k0, b1, b2, eps);
+    adam_elem_x(p.z, g.z, m.z, v.z, ss_k0, b1, b2, eps);
+    adam_elem_x(p.w, g.w, m.w, v.w, ss_k0, b1, b2, eps);
+    m4[i - begin] = m;
+    v4[i - begin] = v;
+    // gather: the updated record goes to every replica
+#pragma unroll
+    for (int r = 0; r < kWorld; ++r) pp.vox[r][i] = p;
+  }
+}
+
+}  // namespace pp
+
+using namespace pp;
+
+extern "C" int pp_shared_alloc(int64_t bytes, void** ptr_out, void* handle_out) {
+  PP_REQUIRE(bytes > 0 && ptr_out && handle_out, PP_ERR_INVALID_ARG, "shared_alloc: bad argument");
+  void* p = nullptr;
+  PP_CHECK_CUDA(cudaMalloc(&p, (size_t)bytes));
+  cudaIpcMemHandle_t h;
+  const cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    set_error("cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    return PP_ERR_CUDA;
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == PP_IPC_HANDLE_BYTES, "IPC handle size");
+  memcpy(handle_out, &h, sizeof(h));
+  *ptr_out = p;
+  return PP_OK;
+}
+
+extern "C" int pp_shared_open(const void* handle, void** ptr_out) {
+  PP_REQUIRE(handle && ptr_out, PP_ERR_INVALID_ARG, "shared_open: null pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  PP_CHECK_CUDA(cudaIpcOpenMemHandle(ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+  return PP_OK;
+}
+
+extern "C" int pp_shared_close(void* ptr) {
+  if (ptr) PP_CHECK_CUDA(cudaIpcCloseMemHandle(ptr));
+  return PP_OK;
+}
+
+extern "C" int pp_shared_free(void* ptr) {
+  if (ptr) PP_CHECK_CUDA(cudaFree(ptr));
+  return PP_OK;
+}
+
+extern "C" int64_t pp_voxel_shard_size(int64_t n_voxels, int32_t world) {
+  if (world <= 0 || n_voxels <= 0) return 0;
+  const int64_t s = (n_voxels + world - 1) / world;
+  return (s + 255) / 256 * 256;   // whole 4 KB pages of records per slice
+}
+
+static float adam_step_size_x(float lr, float beta1, float beta2, int step) {
+  return lr * sqrtf(1.f - powf(beta2, (float)step)) / (1.f - powf(beta1, (float)step));
+}
+
+extern "C" int pp_voxel_adam_exchange(void* const* vox_ptrs, void* const* grad_ptrs, void* exp_avg,
+                                      void* exp_avg_sq, int64_t n_voxels, int32_t world, int32_t rank,
+                                      int32_t step, float beta1, float beta2, float lr_density,
+                                      float lr_k0, float eps, pp_stream_t stream) {
+  PP_REQUIRE(vox_ptrs && grad_ptrs && exp_avg && exp_avg_sq, PP_ERR_INVALID_ARG,
+             "voxel_adam_exchange: null pointer");
+  PP_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, PP_ERR_INVALID_ARG,
+             "voxel_adam_exchange: bad world/rank %d/%d", rank, world);
+  PP_REQUIRE(n_voxels >= 0, PP_ERR_INVALID_ARG, "voxel_adam_exchange: n_voxels < 0");
+  const int64_t shard = pp_voxel_shard_size(n_voxels, world);
+  const int64_t begin = shard * rank < n_voxels ? shard * rank : n_voxels;
+  const int64_t end = begin + shard < n_voxels ? begin + shard : n_voxels;
+  if (end <= begin) return PP_OK;
+  PeerPtrs pp;
+  for (int r = 0; r < kMaxWorld; ++r) {
+    pp.vox[r] = r < world ? (float4*)vox_ptrs[r] : nullptr;
+    pp.grad[r] = r < world ? (const float4*)grad_ptrs[r] : nullptr;
+    PP_REQUIRE(r >= world || (pp.vox[r] && pp.grad[r]), PP_ERR_INVALID_ARG,
+               "voxel_adam_exchange: null peer pointer for rank %d", r);
+  }
+  const float ssd = adam_step_size_x(lr_density, beta1, beta2, step);
+  const float ssk = adam_step_size_x(lr_k0, beta1, beta2, step);
+  const int blocks = (int)min64((end - begin + 255) / 256, (int64_t)sm_count() * 8);
+  cudaStream_t s = as_stream(stream);
+#define PP_LAUNCH_X(W)                                                                         \
+  voxel_adam_exchange_kernel<W><<<blocks, 256, 0, s>>>(pp, (float4*)exp_avg, (float4*)exp_avg_sq, \
+                                                       begin, end, rank, ssd, ssk, beta1, beta2, eps)
+  switch (world) {
+    case 1: PP_LAUNCH_X(1); break;
+    case 2: PP_LAUNCH_X(2); break;
+    case 4: PP_LAUNCH_X(4); break;
+    case 8: PP_LAUNCH_X(8); break;
+    default:
+      set_error("voxel_adam_exchange: world size %d not supported (1, 2, 4, 8)", world);
+      return PP_ERR_UNSUPPORTED;
+  }
+#undef PP_LAUNCH_X
+  PP_CHECK_LAUNCH("voxel_adam_exchange");
+  return PP_OK;
+}

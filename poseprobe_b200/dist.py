@@ -1,0 +1,169 @@
+"""Multi-GPU training of the fused DVGO path: ray-sharded replicas, voxel-sharded optimiser.
+
+One process per GPU (torchrun), ``torch.distributed`` (NCCL) for rendezvous, handle exchange and the
+two tiny cross-rank stream barriers of a step.  The data path is NOT an NCCL collective: every rank's
+parameter and gradient records live in IPC-shared device memory, and ``pp_voxel_adam_exchange`` (one
+kernel per rank) reduces the gradient slices over NVLink with peer loads, applies masked Adam once per
+voxel and writes the result into every replica with peer stores.
+
+Step on every rank:
+    march + loss + scatter into the local gradient records          (no communication)
+    all_reduce(loss, 2 floats)          -> global loss, doubles as "all gradients complete" barrier
+    pp_voxel_adam_exchange              -> reduce-scatter + Adam(1/world of the voxels) + all-gather
+    all_reduce(1 float)                 -> "all slices written, all peers done reading" barrier
+    zero the local gradient records
+
+``mode="nccl"`` keeps the plain formulation (all-reduce of the gradient records, full Adam on every rank)
+as the comparison baseline.  The reference itself is single-GPU; the N-rank result equals
+the 1-rank result on the concatenated batch up to fp32 summation order.
+"""
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import dvgo
+from ._lib import check, lib, ptr, stream
+
+_IPC_BYTES = 64
+
+
+def shard_bounds(n_voxels, world, rank):
+    """[begin, end) of the voxel slice rank owns (mirror of pp_voxel_shard_size)."""
+    s = (n_voxels + world - 1) // world
+    s = (s + 255) // 256 * 256
+    begin = min(s * rank, n_voxels)
+    return begin, min(begin + s, n_voxels)
+
+
+class _DeviceBuffer:
+    """float32 view of raw device memory for torch.as_tensor (CUDA array interface)."""
+
+    def __init__(self, address, n_floats, owner=None):
+        self.owner = owner
+        self.__cuda_array_interface__ = {"shape": (n_floats,), "typestr": "<f4", "data": (address, False),
+                                         "version": 2}
+
+
+class SharedRecords:
+    """[n,4] fp32 records in cudaMalloc'ed memory that peers can map (CUDA IPC)."""
+
+    def __init__(self, n_records, device):
+        self.device = device
+        self.n = n_records
+        p = ctypes.c_void_p()
+        self.handle = (ctypes.c_ubyte * _IPC_BYTES)()
+        with torch.cuda.device(device):
+            check(lib.pp_shared_alloc(n_records * 16, ctypes.byref(p), self.handle), "shared_alloc")
+        self.address = p.value
+        self.tensor = torch.as_tensor(_DeviceBuffer(self.address, n_records * 4, self), device=device).view(n_records, 4)
+        self.peers = []
+
+    def exchange(self, group, world, rank):
+        """all-gather the IPC handles and map every peer's buffer; returns the pointer table."""
+        mine = torch.tensor(list(bytes(self.handle)), dtype=torch.uint8, device=self.device)
+        allh = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine, group=group)
+        table = (ctypes.c_void_p * world)()
+        for r in range(world):
+            if r == rank:
+                table[r] = self.address
+                continue
+            h = (ctypes.c_ubyte * _IPC_BYTES)(*allh[r].cpu().tolist())
+            p = ctypes.c_void_p()
+            with torch.cuda.device(self.device):
+                check(lib.pp_shared_open(h, ctypes.byref(p)), "shared_open")
+            self.peers.append(p.value)
+            table[r] = p.value
+        return table
+
+    def close(self):
+        with torch.cuda.device(self.device):
+            for p in self.peers:
+                lib.pp_shared_close(ctypes.c_void_p(p))
+            self.peers = []
+
+
+class DistributedDVGO:
+    """FusedDVGO replicated over the ranks of a process group."""
+
+    def __init__(self, density, k0, xyz_min, xyz_max, stepsize, group=None, mode="p2p", **kw):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.mode = mode if self.world > 1 else "single"
+        dev = density.device
+        kw = dict(kw)
+        kw["w_rgb"] = kw.get("w_rgb", 1.0) / self.world          # global mean over all ranks' rays
+        for k in ("w_entropy_last", "w_rgbper"):
+            if k in kw:
+                kw[k] = kw[k] / self.world
+        n = density.numel()
+        if self.mode == "p2p":
+            self.vox_mem = SharedRecords(n, dev)
+            self.grad_mem = SharedRecords(n, dev)
+            b, e = shard_bounds(n, self.world, self.rank)
+            self.eng = dvgo.FusedDVGO(density, k0, xyz_min, xyz_max, stepsize, vox_buf=self.vox_mem.tensor,
+                                      grad_buf=self.grad_mem.tensor, moment_records=max(e - b, 1), **kw)
+            torch.cuda.synchronize(dev)
+            self.vox_ptrs = self.vox_mem.exchange(group, self.world, self.rank)
+            self.grad_ptrs = self.grad_mem.exchange(group, self.world, self.rank)
+        else:
+            self.eng = dvgo.FusedDVGO(density, k0, xyz_min, xyz_max, stepsize, **kw)
+        self.token = torch.zeros(1, dtype=torch.float32, device=dev)
+        dist.barrier(group=group)
+
+    def train_step(self, rays_o, rays_d, target, events=None):
+        """One optimisation step on this rank's ray batch; returns [global loss, global mse] (device).
+        `events` (optional): three CUDA events recorded before the march, after it, and at the end."""
+        try:
+            return self._train_step(rays_o, rays_d, target, events)
+        finally:
+            if events is not None:
+                events[2].record()
+
+    def _train_step(self, rays_o, rays_d, target, events):
+        eng = self.eng
+        eng.loss_buf.zero_()
+        if events is not None:
+            events[0].record()
+        eng.backward_only(rays_o, rays_d, target)
+        if events is not None:
+            events[1].record()
+        if self.mode == "single":
+            eng.optimizer_step()
+            return eng.loss_buf
+        if self.mode == "nccl":
+            dist.all_reduce(eng.loss_buf, group=self.group)
+            dist.all_reduce(eng.grad, group=self.group)
+            eng.optimizer_step()
+            return eng.loss_buf
+        dist.all_reduce(eng.loss_buf, group=self.group)          # + barrier: every rank finished scattering
+        b1, b2, lr_d, lr_k, eps = eng.hp
+        eng.step += 1
+        with torch.cuda.device(eng.device):
+            check(lib.pp_voxel_adam_exchange(self.vox_ptrs, self.grad_ptrs, ptr(eng.exp_avg), ptr(eng.exp_avg_sq),
+                                             eng.n_voxels, self.world, self.rank, eng.step, b1, b2, lr_d, lr_k,
+                                             eps, stream()), "voxel_adam_exchange")
+        dist.all_reduce(self.token, group=self.group)            # barrier: all slices written / read
+        eng.grad.zero_()
+        return eng.loss_buf
+
+    def render(self, rays_o, rays_d, **kw):
+        return self.eng.render(rays_o, rays_d, **kw)
+
+    def export_grids(self):
+        return self.eng.export_grids()
+
+    def close(self):
+        if self.mode == "p2p":
+            torch.cuda.synchronize(self.eng.device)
+            dist.barrier(group=self.group)
+            self.vox_mem.close()
+            self.grad_mem.close()
+            dist.barrier(group=self.group)      # nobody maps our buffers any more
+            self.eng.vox = self.eng.grad = None
+            for mem in (self.vox_mem, self.grad_mem):
+                mem.tensor = None
+                with torch.cuda.device(mem.device):
+                    lib.pp_shared_free(ctypes.c_void_p(mem.address))

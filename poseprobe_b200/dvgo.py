@@ -193,7 +193,7 @@ class FusedDVGO:
                  alpha_init=1e-2, near=0.2, far=1e9, bg=0.0, fast_color_thres=0.0,
                  lr_density=0.1, lr_k0=0.1, betas=(0.9, 0.99), eps=1e-8,
                  w_rgb=1.0, w_entropy_last=0.0, w_rgbper=0.0, tv_density=0.0, tv_k0=0.0, tv_dense=False,
-                 pose_grad=False):
+                 pose_grad=False, vox_buf=None, grad_buf=None, moment_records=None):
         self.world_size = tuple(int(v) for v in density.shape[2:])
         if voxel_size is None:
             voxel_size = float((xyz_max[0] - xyz_min[0]) / self.world_size[0])
@@ -202,9 +202,14 @@ class FusedDVGO:
                                 fast_color_thres)
         self.loss = _Loss(float(w_rgb), float(w_entropy_last), float(w_rgbper))
         self.vox = pack_voxels(density.contiguous(), k0.contiguous())
-        self.grad = torch.zeros_like(self.vox)
-        self.exp_avg = torch.zeros_like(self.vox)
-        self.exp_avg_sq = torch.zeros_like(self.vox)
+        if vox_buf is not None:          # caller-owned (e.g. IPC-shared) parameter / gradient records
+            vox_buf.copy_(self.vox)
+            self.vox = vox_buf
+        self.grad = grad_buf if grad_buf is not None else torch.zeros_like(self.vox)
+        self.grad.zero_()
+        n_mom = self.vox.shape[0] if moment_records is None else int(moment_records)
+        self.exp_avg = torch.zeros((n_mom, 4), dtype=torch.float32, device=self.vox.device)
+        self.exp_avg_sq = torch.zeros_like(self.exp_avg)
         self.tv = (float(tv_density), float(tv_k0), bool(tv_dense))
         self.vox_next = torch.empty_like(self.vox) if (tv_density or tv_k0) else None
         self.hp = (float(betas[0]), float(betas[1]), float(lr_density), float(lr_k0), float(eps))
