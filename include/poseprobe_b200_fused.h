@@ -40,6 +40,7 @@ typedef struct pp_dvgo_loss {
   float w_rgb;              /* weight of the photometric MSE (mean over rays x 3) */
   float w_entropy_last;     /* weight of the background-entropy term on alphainv_last (0 = off) */
   float w_rgbper;           /* weight of the per-point colour term, weights detached (0 = off) */
+  float mse_scale;          /* factor on the reported photometric MSE (loss_out[1]); 1/world when ranks sum */
 } pp_dvgo_loss;
 
 /* density [V], k0 [3,V] (channels first) -> vox [V] float4 records, and back.  Either plane pointer of

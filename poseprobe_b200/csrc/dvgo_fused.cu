@@ -336,7 +336,7 @@ dvgo_march_kernel(pp_dvgo_scene sc, pp_dvgo_loss ls, const float4* __restrict__ 
       }
       if (lane == 0 && loss_out) {
         atomicAdd(loss_out, loss);
-        atomicAdd(loss_out + 1, mse * inv_n * (1.f / 3.f));
+        atomicAdd(loss_out + 1, ls.mse_scale * mse * inv_n * (1.f / 3.f));
       }
     } else {
       load3(grad_rgb_in, r, g);
@@ -686,7 +686,7 @@ static int launch_march_occ(const pp_dvgo_scene* sc, const pp_dvgo_loss* ls, con
                "%s: workspace of %lld bytes required (pp_dvgo_workspace_bytes), got %lld", who,
                (long long)need, (long long)workspace_bytes);
   }
-  pp_dvgo_loss l = {1.f, 0.f, 0.f};
+  pp_dvgo_loss l = {1.f, 0.f, 0.f, 1.f};
   if (ls) l = *ls;
   kernel<<<(unsigned)blocks, warps * 32, smem, s>>>(
       *sc, l, (const float4*)vox, rays_o, rays_d, n_rays, target, grad_rgb, grad_last,

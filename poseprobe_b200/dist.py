@@ -98,6 +98,7 @@ class DistributedDVGO:
         for k in ("w_entropy_last", "w_rgbper"):
             if k in kw:
                 kw[k] = kw[k] / self.world
+        kw["mse_scale"] = 1.0 / self.world
         n = density.numel()
         if self.mode == "p2p":
             self.vox_mem = SharedRecords(n, dev)

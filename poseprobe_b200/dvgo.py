@@ -27,7 +27,8 @@ class _Scene(ctypes.Structure):
 
 
 class _Loss(ctypes.Structure):
-    _fields_ = [("w_rgb", ctypes.c_float), ("w_entropy_last", ctypes.c_float), ("w_rgbper", ctypes.c_float)]
+    _fields_ = [("w_rgb", ctypes.c_float), ("w_entropy_last", ctypes.c_float), ("w_rgbper", ctypes.c_float),
+                ("mse_scale", ctypes.c_float)]
 
 
 def make_scene(world_size, xyz_min, xyz_max, near, far, stepdist, act_shift, interval, bg=0.0,
@@ -193,14 +194,14 @@ class FusedDVGO:
                  alpha_init=1e-2, near=0.2, far=1e9, bg=0.0, fast_color_thres=0.0,
                  lr_density=0.1, lr_k0=0.1, betas=(0.9, 0.99), eps=1e-8,
                  w_rgb=1.0, w_entropy_last=0.0, w_rgbper=0.0, tv_density=0.0, tv_k0=0.0, tv_dense=False,
-                 pose_grad=False, vox_buf=None, grad_buf=None, moment_records=None):
+                 pose_grad=False, vox_buf=None, grad_buf=None, moment_records=None, mse_scale=1.0):
         self.world_size = tuple(int(v) for v in density.shape[2:])
         if voxel_size is None:
             voxel_size = float((xyz_max[0] - xyz_min[0]) / self.world_size[0])
         self.scene = make_scene(self.world_size, xyz_min, xyz_max, near, far, stepsize * voxel_size,
                                 math.log(1 / (1 - alpha_init) - 1), stepsize * voxel_size_ratio, bg,
                                 fast_color_thres)
-        self.loss = _Loss(float(w_rgb), float(w_entropy_last), float(w_rgbper))
+        self.loss = _Loss(float(w_rgb), float(w_entropy_last), float(w_rgbper), float(mse_scale))
         self.vox = pack_voxels(density.contiguous(), k0.contiguous())
         if vox_buf is not None:          # caller-owned (e.g. IPC-shared) parameter / gradient records
             vox_buf.copy_(self.vox)

@@ -63,6 +63,8 @@ def main():
             # Adam's first steps move a parameter by ~lr regardless of |grad|; compare where all agree on sign
             diff = (mine - ref).abs()
             frac_bad = float((diff > 1e-3).float().mean())
+            if rank == 0:
+                print("%s vs single: %.5f of the voxels differ by > 1e-3, max %.3g" % (mode, frac_bad, float(diff.max())))
             assert frac_bad < 2e-3, "%s: %.4f of the voxels differ from the single-rank run" % (mode, frac_bad)
     d1, k1, _ = results["p2p"]
     d2, k2, _ = results["nccl"]
@@ -73,4 +75,12 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except Exception:
+        import traceback
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "dist_check_rank%s.log" % os.environ.get("RANK", "0")), "w") as f:
+            traceback.print_exc(file=f)
+        traceback.print_exc()
+        raise
