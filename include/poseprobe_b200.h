@@ -219,6 +219,22 @@ PP_API int pp_neus_alpha_backward(const float* sdf, const float* gradient, const
                            const float* grad_alpha, float* grad_sdf, float* grad_gradient,
                            pp_stream_t stream);
 
+/* Camera rays for selected pixels (get_rays / get_rays_of_a_view, lib/voxurf_coarse.py:1339-1368, :1402-1407,
+ * mode='center' is px = i + 0.5 etc. supplied by the caller; flips are applied to px/py by the caller):
+ *   dirs = ((px-cx)/fx, -(py-cy)/fy, -1)   [inverse_y: (.., +(py-cy)/fy, +1)]
+ *   rays_d = normalize(c2w[:3,:3] . dirs),  rays_o = c2w[:3,3]
+ * Ks [n_img,3,3], c2w [n_img,3,4], img_id [N] int32, px/py [N].  Outputs [N,3]. */
+PP_API int pp_rays_from_pixels(const float* Ks, const float* c2w, const int32_t* img_id, const float* px,
+                               const float* py, int inverse_y, int64_t n_rays, float* rays_o,
+                               float* rays_d, pp_stream_t stream);
+
+/* Fused per-image pose-gradient reduction: grad_rays [N,6] (d loss/d rays_o | d loss/d rays_d, as emitted
+ * by pp_dvgo_train_step / pp_dvgo_render_backward) -> grad_c2w [n_img,3,4] (overwritten), i.e. the backward
+ * of pp_rays_from_pixels summed over the rays of each image (the autograd reduction of SURVEY.md a21). */
+PP_API int pp_pose_grad_reduce(const float* Ks, const float* c2w, const int32_t* img_id, const float* px,
+                               const float* py, int inverse_y, int64_t n_rays, int32_t n_img,
+                               const float* grad_rays, float* grad_c2w, pp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -119,6 +119,15 @@ PP_API int pp_shared_open(const void* handle, void** ptr_out);
 PP_API int pp_shared_close(void* ptr);
 PP_API int pp_shared_free(void* ptr);
 
+/* Cross-rank stream barrier over peer memory (one warp; no collective library on the critical path).
+ * sync_ptrs: HOST array of `world` device pointers to each rank's sync block (pp_peer_sync_bytes() bytes from
+ * pp_shared_alloc, zero-initialised once).  `epoch` must increase by one per call on every rank.  If
+ * payload_in (2 device floats) is given, it is delivered to every rank and the rank-ordered sum of all
+ * ranks' payloads is written to payload_sum_out - used to form the global loss for free. */
+PP_API int64_t pp_peer_sync_bytes(void);
+PP_API int pp_peer_sync(void* const* sync_ptrs, int32_t world, int32_t rank, uint32_t epoch,
+                        const float* payload_in, float* payload_sum_out, pp_stream_t stream);
+
 /* vox_ptrs / grad_ptrs: HOST arrays of `world` device pointers (entry `rank` is the local buffer).
  * exp_avg / exp_avg_sq: local moments of the slice only, pp_voxel_shard_size(n_voxels, world) records.
  * Slice of rank r: [r*S, min((r+1)*S, n_voxels)), S = pp_voxel_shard_size.  Gradients are summed over

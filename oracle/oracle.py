@@ -302,3 +302,52 @@ def python_adam_step(param, grad, exp_avg, exp_avg_sq, step, beta1, beta2, lr, e
         param.addcdiv_(exp_avg * per_lr, denom, value=-step_size)
     else:
         param.addcdiv_(exp_avg, denom, value=-step_size)
+
+
+def get_rays_of_a_view(H, W, K, c2w, inverse_y=False, flip_x=False, flip_y=False, mode="center"):
+    """get_rays + get_rays_of_a_view (no NDC), lib/voxurf_coarse.py:1339-1368, :1402-1407.
+    -> rays_o, rays_d (normalised), viewdirs, each [H,W,3]."""
+    i, j = torch.meshgrid(torch.linspace(0, W - 1, W), torch.linspace(0, H - 1, H), indexing="ij")
+    i, j = i.t().float(), j.t().float()
+    if mode == "center":
+        i, j = i + 0.5, j + 0.5
+    if flip_x:
+        i = i.flip((1,))
+    if flip_y:
+        j = j.flip((0,))
+    if inverse_y:
+        dirs = torch.stack([(i - K[0][2]) / K[0][0], (j - K[1][2]) / K[1][1], torch.ones_like(i)], -1)
+    else:
+        dirs = torch.stack([(i - K[0][2]) / K[0][0], -(j - K[1][2]) / K[1][1], -torch.ones_like(i)], -1)
+    rays_d = torch.sum(dirs[..., None, :] * c2w[:3, :3], -1)
+    rays_o = c2w[:3, 3].expand(rays_d.shape)
+    rays_d = rays_d / rays_d.norm(dim=-1, keepdim=True)
+    return rays_o, rays_d, rays_d
+
+
+def se3_to_SE3(wu, nth=10):
+    """Lie.se3_to_SE3, lib/camera.py:127-142 with taylor_A/B/C :165-188."""
+    w, u = wu.split([3, 3], dim=-1)
+    w0, w1, w2 = w.unbind(dim=-1)
+    O = torch.zeros_like(w0)
+    wx = torch.stack([torch.stack([O, -w2, w1], dim=-1), torch.stack([w2, O, -w0], dim=-1),
+                      torch.stack([-w1, w0, O], dim=-1)], dim=-2)
+    theta = w.norm(dim=-1)[..., None, None]
+    I = torch.eye(3, dtype=torch.float32)
+
+    def taylor(first):
+        ans, denom = torch.zeros_like(theta), 1.
+        for i in range(nth + 1):
+            if first == "A":
+                if i > 0:
+                    denom *= (2 * i) * (2 * i + 1)
+            elif first == "B":
+                denom *= (2 * i + 1) * (2 * i + 2)
+            else:
+                denom *= (2 * i + 2) * (2 * i + 3)
+            ans = ans + (-1) ** i * theta ** (2 * i) / denom
+        return ans
+    A, B, C = taylor("A"), taylor("B"), taylor("C")
+    R = I + A * wx + B * wx @ wx
+    V = I + B * wx + C * wx @ wx
+    return torch.cat([R, (V @ u[..., None])], dim=-1)

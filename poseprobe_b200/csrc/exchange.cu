@@ -31,33 +31,96 @@ __global__ void __launch_bounds__(256)
 voxel_adam_exchange_kernel(PeerPtrs pp, float4* __restrict__ m4, float4* __restrict__ v4,
                            int64_t begin, int64_t end, int rank, float ss_density, float ss_k0,
                            float b1, float b2, float eps) {
-  for (int64_t i = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < end;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    // reduce: one 16-byte load per rank, all issued before the first use; fixed rank order keeps the
-    // sum bit-identical on every rank count run-to-run
-    float4 gr[kWorld];
+  constexpr int kUnroll = (kWorld >= 8) ? 2 : 4;   // keep >= 16 peer loads in flight per thread
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < end;
+       i0 += kUnroll * stride) {
+    // reduce: one 16-byte load per rank and record, all issued before the first use (NVLink latency is
+    // ~2 us, so the bytes in flight per SM decide the bandwidth); fixed rank order keeps the sum
+    // deterministic run to run
+    float4 gr[kUnroll][kWorld];
 #pragma unroll
-    for (int r = 0; r < kWorld; ++r) gr[r] = pp.grad[r][i];
-    float4 g = gr[0];
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t i = i0 + u * stride;
 #pragma unroll
-    for (int r = 1; r < kWorld; ++r) {
-      g.x += gr[r].x;
-      g.y += gr[r].y;
-      g.z += gr[r].z;
-      g.w += gr[r].w;
+      for (int r = 0; r < kWorld; ++r)
+        gr[u][r] = (i < end) ? pp.grad[r][i] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if (g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f) continue;
-    float4 p = pp.vox[rank][i];
-    float4 m = m4[i - begin], v = v4[i - begin];
-    adam_elem_x(p.x, g.x, m.x, v.x, ss_density, b1, b2, eps);
-    adam_elem_x(p.y, g.y, m.y, v.y, ss_k0, b1, b2, eps);
-    adam_elem_x(p.z, g.z, m.z, v.z, ss_k0, b1, b2, eps);
-    adam_elem_x(p.w, g.w, m.w, v.w, ss_k0, b1, b2, eps);
-    m4[i - begin] = m;
-    v4[i - begin] = v;
-    // gather: the updated record goes to every replica
 #pragma unroll
-    for (int r = 0; r < kWorld; ++r) pp.vox[r][i] = p;
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i >= end) continue;
+      float4 g = gr[u][0];
+#pragma unroll
+      for (int r = 1; r < kWorld; ++r) {
+        g.x += gr[u][r].x;
+        g.y += gr[u][r].y;
+        g.z += gr[u][r].z;
+        g.w += gr[u][r].w;
+      }
+      if (g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f) continue;
+      float4 p = pp.vox[rank][i];
+      float4 m = m4[i - begin], v = v4[i - begin];
+      adam_elem_x(p.x, g.x, m.x, v.x, ss_density, b1, b2, eps);
+      adam_elem_x(p.y, g.y, m.y, v.y, ss_k0, b1, b2, eps);
+      adam_elem_x(p.z, g.z, m.z, v.z, ss_k0, b1, b2, eps);
+      adam_elem_x(p.w, g.w, m.w, v.w, ss_k0, b1, b2, eps);
+      m4[i - begin] = m;
+      v4[i - begin] = v;
+      // gather: the updated record goes to every replica
+#pragma unroll
+      for (int r = 0; r < kWorld; ++r) pp.vox[r][i] = p;
+    }
+  }
+}
+
+// ---- cross-rank stream barrier over peer memory -----------------------------------------------------
+// Each rank owns a small IPC-shared sync block.  Rank `me` announces epoch E by storing E into slot `me`
+// of every peer's block (release, system scope) and then waits until all slots of its own block reached E
+// (acquire).  An optional 2-float payload travels with the announcement and is summed in rank order, which
+// is how the global loss is formed without a collective.  One warp; launched in stream order, so it
+// separates "my gradient scatter is complete" from "I start reading everybody's gradients".
+struct SyncBlock {
+  unsigned int flags[kMaxWorld];
+  float payload[kMaxWorld][2];
+  unsigned int timed_out;
+};
+struct SyncPtrs {
+  SyncBlock* blk[kMaxWorld];
+};
+
+__global__ void peer_sync_kernel(SyncPtrs sp, int world, int me, unsigned int epoch,
+                                 const float* __restrict__ payload_in, float* __restrict__ payload_sum) {
+  const int r = threadIdx.x;
+  SyncBlock* mine = sp.blk[me];
+  if (r < world) {
+    SyncBlock* peer = sp.blk[r];
+    if (payload_in) {
+      peer->payload[me][0] = payload_in[0];
+      peer->payload[me][1] = payload_in[1];
+    }
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&peer->flags[me]), "r"(epoch) : "memory");
+    const long long t0 = clock64();
+    for (;;) {
+      unsigned int v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(&mine->flags[r]) : "memory");
+      if ((int)(v - epoch) >= 0) break;
+      if (clock64() - t0 > 20000000000LL) {   // ~10 s: a peer died; do not hang the device
+        mine->timed_out = 1;
+        break;
+      }
+    }
+  }
+  __syncwarp();
+  if (payload_sum && r == 0) {
+    float a = 0.f, b = 0.f;
+    for (int q = 0; q < world; ++q) {
+      a += mine->payload[q][0];
+      b += mine->payload[q][1];
+    }
+    payload_sum[0] = a;
+    payload_sum[1] = b;
   }
 }
 
@@ -97,6 +160,24 @@ extern "C" int pp_shared_close(void* ptr) {
 
 extern "C" int pp_shared_free(void* ptr) {
   if (ptr) PP_CHECK_CUDA(cudaFree(ptr));
+  return PP_OK;
+}
+
+extern "C" int64_t pp_peer_sync_bytes(void) { return 4096; }
+
+extern "C" int pp_peer_sync(void* const* sync_ptrs, int32_t world, int32_t rank, uint32_t epoch,
+                            const float* payload_in, float* payload_sum_out, pp_stream_t stream) {
+  PP_REQUIRE(sync_ptrs, PP_ERR_INVALID_ARG, "peer_sync: null pointer table");
+  PP_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, PP_ERR_INVALID_ARG,
+             "peer_sync: bad world/rank %d/%d", rank, world);
+  static_assert(sizeof(SyncBlock) <= 4096, "sync block size");
+  SyncPtrs sp;
+  for (int r = 0; r < kMaxWorld; ++r) {
+    sp.blk[r] = r < world ? (SyncBlock*)sync_ptrs[r] : nullptr;
+    PP_REQUIRE(r >= world || sp.blk[r], PP_ERR_INVALID_ARG, "peer_sync: null sync block for rank %d", r);
+  }
+  peer_sync_kernel<<<1, 32, 0, as_stream(stream)>>>(sp, world, rank, epoch, payload_in, payload_sum_out);
+  PP_CHECK_LAUNCH("peer_sync");
   return PP_OK;
 }
 

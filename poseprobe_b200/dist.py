@@ -6,11 +6,11 @@ parameter and gradient records live in IPC-shared device memory, and ``pp_voxel_
 kernel per rank) reduces the gradient slices over NVLink with peer loads, applies masked Adam once per
 voxel and writes the result into every replica with peer stores.
 
-Step on every rank:
+Step on every rank (every item is one launch on the rank's stream; no NCCL call on the critical path):
     march + loss + scatter into the local gradient records          (no communication)
-    all_reduce(loss, 2 floats)          -> global loss, doubles as "all gradients complete" barrier
+    pp_peer_sync(loss payload)          -> "all gradients complete" barrier; delivers the global loss
     pp_voxel_adam_exchange              -> reduce-scatter + Adam(1/world of the voxels) + all-gather
-    all_reduce(1 float)                 -> "all slices written, all peers done reading" barrier
+    pp_peer_sync                        -> "all slices written, all peers done reading" barrier
     zero the local gradient records
 
 ``mode="nccl"`` keeps the plain formulation (all-reduce of the gradient records, full Adam on every rank)
@@ -48,7 +48,7 @@ class _DeviceBuffer:
 class SharedRecords:
     """[n,4] fp32 records in cudaMalloc'ed memory that peers can map (CUDA IPC)."""
 
-    def __init__(self, n_records, device):
+    def __init__(self, n_records, device, zero=False):
         self.device = device
         self.n = n_records
         p = ctypes.c_void_p()
@@ -57,6 +57,8 @@ class SharedRecords:
             check(lib.pp_shared_alloc(n_records * 16, ctypes.byref(p), self.handle), "shared_alloc")
         self.address = p.value
         self.tensor = torch.as_tensor(_DeviceBuffer(self.address, n_records * 4, self), device=device).view(n_records, 4)
+        if zero:
+            self.tensor.zero_()
         self.peers = []
 
     def exchange(self, group, world, rank):
@@ -106,9 +108,13 @@ class DistributedDVGO:
             b, e = shard_bounds(n, self.world, self.rank)
             self.eng = dvgo.FusedDVGO(density, k0, xyz_min, xyz_max, stepsize, vox_buf=self.vox_mem.tensor,
                                       grad_buf=self.grad_mem.tensor, moment_records=max(e - b, 1), **kw)
+            self.sync_mem = SharedRecords(int(lib.pp_peer_sync_bytes()) // 16, dev, zero=True)
             torch.cuda.synchronize(dev)
             self.vox_ptrs = self.vox_mem.exchange(group, self.world, self.rank)
             self.grad_ptrs = self.grad_mem.exchange(group, self.world, self.rank)
+            self.sync_ptrs = self.sync_mem.exchange(group, self.world, self.rank)
+            self.epoch = 0
+            self.loss_global = torch.zeros(2, dtype=torch.float32, device=dev)
         else:
             self.eng = dvgo.FusedDVGO(density, k0, xyz_min, xyz_max, stepsize, **kw)
         self.token = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -139,16 +145,22 @@ class DistributedDVGO:
             dist.all_reduce(eng.grad, group=self.group)
             eng.optimizer_step()
             return eng.loss_buf
-        dist.all_reduce(eng.loss_buf, group=self.group)          # + barrier: every rank finished scattering
         b1, b2, lr_d, lr_k, eps = eng.hp
         eng.step += 1
         with torch.cuda.device(eng.device):
+            s = stream()
+            # barrier: every rank finished scattering; the local [loss, mse] rides along and comes back summed
+            self.epoch += 1
+            check(lib.pp_peer_sync(self.sync_ptrs, self.world, self.rank, self.epoch, ptr(eng.loss_buf),
+                                   ptr(self.loss_global), s), "peer_sync")
             check(lib.pp_voxel_adam_exchange(self.vox_ptrs, self.grad_ptrs, ptr(eng.exp_avg), ptr(eng.exp_avg_sq),
                                              eng.n_voxels, self.world, self.rank, eng.step, b1, b2, lr_d, lr_k,
-                                             eps, stream()), "voxel_adam_exchange")
-        dist.all_reduce(self.token, group=self.group)            # barrier: all slices written / read
+                                             eps, s), "voxel_adam_exchange")
+            # barrier: all slices written, all peers done reading my gradient
+            self.epoch += 1
+            check(lib.pp_peer_sync(self.sync_ptrs, self.world, self.rank, self.epoch, None, None, s), "peer_sync")
         eng.grad.zero_()
-        return eng.loss_buf
+        return self.loss_global
 
     def render(self, rays_o, rays_d, **kw):
         return self.eng.render(rays_o, rays_d, **kw)
@@ -162,9 +174,10 @@ class DistributedDVGO:
             dist.barrier(group=self.group)
             self.vox_mem.close()
             self.grad_mem.close()
+            self.sync_mem.close()
             dist.barrier(group=self.group)      # nobody maps our buffers any more
             self.eng.vox = self.eng.grad = None
-            for mem in (self.vox_mem, self.grad_mem):
+            for mem in (self.vox_mem, self.grad_mem, self.sync_mem):
                 mem.tensor = None
                 with torch.cuda.device(mem.device):
                     lib.pp_shared_free(ctypes.c_void_p(mem.address))
