@@ -164,7 +164,7 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(dev)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    dist_mode = os.environ.get("PP_DIST_MODE", "p2p")
+    dist_mode = os.environ.get("PP_DIST_MODE", "auto")
     density, k0 = synthetic.make_dvgo_grids(GRID)
     if world > 1:
         trainer = ppdist.DistributedDVGO(density.to(dev), k0.to(dev), XYZ_MIN, XYZ_MAX, STEPSIZE, mode=dist_mode)
@@ -251,6 +251,17 @@ def run_ours(args, rank, world, local_rank):
     barrier()
     clocks = sampler.stop() if sampler else None
 
+    exchange_breakdown = None
+    if trainer is not None and trainer.mode in ("p2p", "nvls"):
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(10)]
+        for i in range(10):
+            trainer.profile_events = evs[i]
+            step(*resident[i % N_BATCHES])
+        trainer.profile_events = None
+        barrier()
+        names = ["sync_gradients_ms", "exchange_adam_kernel_ms", "sync_params_ms", "zero_grad_ms"]
+        exchange_breakdown = {nm: sum(e[k].elapsed_time(e[k + 1]) for e in evs) / len(evs) for k, nm in enumerate(names)}
+
     if rank != 0:
         if trainer is not None:
             trainer.close()
@@ -269,8 +280,12 @@ def run_ours(args, rank, world, local_rank):
     value = world * RAYS * args.steps / (ms_total * 1e-3)
     cfg = workload_config(world)
     if world > 1:
-        cfg["exchange"] = ("fused peer-memory reduce-scatter + Adam + all-gather kernel (NVLink P2P)"
-                           if dist_mode == "p2p" else "NCCL all-reduce of the gradient records")
+        cfg["exchange"] = {
+            "nvls": "ONE kernel: in-switch gradient reduction (multimem.ld_reduce) + masked Adam on 1/N of the "
+                    "voxels + multicast parameter store (multimem.st); peer-memory flag barriers, no NCCL on the step",
+            "p2p": "ONE kernel: peer-load reduce-scatter + masked Adam on 1/N of the voxels + peer-store all-gather",
+            "nccl": "NCCL all-reduce of the gradient records + full Adam on every rank"}[trainer.mode]
+        cfg["parallelism"] = "ray-sharded replicas (dp%d), voxel-sharded optimiser" % world
     line = {
         "metric": "train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -290,6 +305,8 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    if exchange_breakdown:
+        line["step_roofline"]["exchange_breakdown"] = exchange_breakdown
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
     print(json.dumps(line))

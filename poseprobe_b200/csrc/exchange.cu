@@ -5,6 +5,7 @@
 // parameters).  Per rank and step the NVLink traffic is (world-1)/world of the gradient records in and
 // the same amount of parameter records out - the two directions of the link are used concurrently -
 // and the dense optimiser tail shrinks by 1/world because every voxel is updated exactly once.
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/poseprobe_b200_fused.h"
@@ -30,7 +31,7 @@ template <int kWorld>
 __global__ void __launch_bounds__(256)
 voxel_adam_exchange_kernel(PeerPtrs pp, float4* __restrict__ m4, float4* __restrict__ v4,
                            int64_t begin, int64_t end, int rank, float ss_density, float ss_k0,
-                           float b1, float b2, float eps) {
+                           float b1, float b2, float eps, int dbg) {
   constexpr int kUnroll = (kWorld >= 8) ? 2 : 4;   // keep >= 16 peer loads in flight per thread
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i0 = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < end;
@@ -44,7 +45,7 @@ voxel_adam_exchange_kernel(PeerPtrs pp, float4* __restrict__ m4, float4* __restr
       const int64_t i = i0 + u * stride;
 #pragma unroll
       for (int r = 0; r < kWorld; ++r)
-        gr[u][r] = (i < end) ? pp.grad[r][i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        gr[u][r] = (i < end) ? pp.grad[(dbg & 2) ? rank : r][i] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
@@ -69,7 +70,60 @@ voxel_adam_exchange_kernel(PeerPtrs pp, float4* __restrict__ m4, float4* __restr
       v4[i - begin] = v;
       // gather: the updated record goes to every replica
 #pragma unroll
-      for (int r = 0; r < kWorld; ++r) pp.vox[r][i] = p;
+      for (int r = 0; r < kWorld; ++r)
+        if (!(dbg & 1) || r == rank) pp.vox[r][i] = p;
+    }
+  }
+}
+
+// ---- NVSwitch variant: in-switch reduction and multicast ----------------------------------------------
+// With plain peer loads/stores every link direction carries (w-1)/w of the gradient records AND (w-1)/w of
+// the parameter records.  On an NVSwitch system the same two steps can be expressed on a multicast address:
+// multimem.ld_reduce makes the switch fetch the record from every replica, add them (fp32) and return one
+// 16-byte result; multimem.st makes the switch replicate one 16-byte store into every replica.  Per GPU and
+// direction the traffic drops from 2(w-1)/w to (w+1)/w of the record array.
+__device__ __forceinline__ float4 mc_ld_reduce_add(const float4* mc_addr) {
+  float4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(mc_addr)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ void mc_st(float4* mc_addr, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc_addr), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+voxel_adam_exchange_mc_kernel(const float4* __restrict__ vox_local, float4* vox_mc, const float4* grad_mc,
+                              float4* __restrict__ m4, float4* __restrict__ v4, int64_t begin, int64_t end,
+                              float ss_density, float ss_k0, float b1, float b2, float eps) {
+  constexpr int kUnroll = 4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i0 = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < end;
+       i0 += kUnroll * stride) {
+    float4 g[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t i = i0 + u * stride;
+      g[u] = (i < end) ? mc_ld_reduce_add(grad_mc + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i >= end) continue;
+      if (g[u].x == 0.f && g[u].y == 0.f && g[u].z == 0.f && g[u].w == 0.f) continue;
+      float4 p = vox_local[i];
+      float4 m = m4[i - begin], v = v4[i - begin];
+      adam_elem_x(p.x, g[u].x, m.x, v.x, ss_density, b1, b2, eps);
+      adam_elem_x(p.y, g[u].y, m.y, v.y, ss_k0, b1, b2, eps);
+      adam_elem_x(p.z, g[u].z, m.z, v.z, ss_k0, b1, b2, eps);
+      adam_elem_x(p.w, g[u].w, m.w, v.w, ss_k0, b1, b2, eps);
+      m4[i - begin] = m;
+      v4[i - begin] = v;
+      mc_st(vox_mc + i, p);
     }
   }
 }
@@ -128,6 +182,11 @@ __global__ void peer_sync_kernel(SyncPtrs sp, int world, int me, unsigned int ep
 
 using namespace pp;
 
+static float adam_step_size_x(float lr, float beta1, float beta2, int step) {
+  return lr * sqrtf(1.f - powf(beta2, (float)step)) / (1.f - powf(beta1, (float)step));
+}
+
+
 extern "C" int pp_shared_alloc(int64_t bytes, void** ptr_out, void* handle_out) {
   PP_REQUIRE(bytes > 0 && ptr_out && handle_out, PP_ERR_INVALID_ARG, "shared_alloc: bad argument");
   void* p = nullptr;
@@ -163,6 +222,28 @@ extern "C" int pp_shared_free(void* ptr) {
   return PP_OK;
 }
 
+extern "C" int pp_voxel_adam_exchange_mc(const void* vox_local, void* vox_mc, const void* grad_mc,
+                                         void* exp_avg, void* exp_avg_sq, int64_t n_voxels,
+                                         int32_t world, int32_t rank, int32_t step, float beta1,
+                                         float beta2, float lr_density, float lr_k0, float eps,
+                                         pp_stream_t stream) {
+  PP_REQUIRE(vox_local && vox_mc && grad_mc && exp_avg && exp_avg_sq, PP_ERR_INVALID_ARG,
+             "voxel_adam_exchange_mc: null pointer");
+  PP_REQUIRE(world >= 1 && rank >= 0 && rank < world, PP_ERR_INVALID_ARG,
+             "voxel_adam_exchange_mc: bad world/rank %d/%d", rank, world);
+  const int64_t shard = pp_voxel_shard_size(n_voxels, world);
+  const int64_t begin = shard * rank < n_voxels ? shard * rank : n_voxels;
+  const int64_t end = begin + shard < n_voxels ? begin + shard : n_voxels;
+  if (end <= begin) return PP_OK;
+  const int blocks = (int)min64((end - begin + 255) / 256, (int64_t)sm_count() * 8);
+  voxel_adam_exchange_mc_kernel<<<blocks, 256, 0, as_stream(stream)>>>(
+      (const float4*)vox_local, (float4*)vox_mc, (const float4*)grad_mc, (float4*)exp_avg,
+      (float4*)exp_avg_sq, begin, end, adam_step_size_x(lr_density, beta1, beta2, step),
+      adam_step_size_x(lr_k0, beta1, beta2, step), beta1, beta2, eps);
+  PP_CHECK_LAUNCH("voxel_adam_exchange_mc");
+  return PP_OK;
+}
+
 extern "C" int64_t pp_peer_sync_bytes(void) { return 4096; }
 
 extern "C" int pp_peer_sync(void* const* sync_ptrs, int32_t world, int32_t rank, uint32_t epoch,
@@ -185,10 +266,6 @@ extern "C" int64_t pp_voxel_shard_size(int64_t n_voxels, int32_t world) {
   if (world <= 0 || n_voxels <= 0) return 0;
   const int64_t s = (n_voxels + world - 1) / world;
   return (s + 255) / 256 * 256;   // whole 4 KB pages of records per slice
-}
-
-static float adam_step_size_x(float lr, float beta1, float beta2, int step) {
-  return lr * sqrtf(1.f - powf(beta2, (float)step)) / (1.f - powf(beta1, (float)step));
 }
 
 extern "C" int pp_voxel_adam_exchange(void* const* vox_ptrs, void* const* grad_ptrs, void* exp_avg,
@@ -215,9 +292,11 @@ extern "C" int pp_voxel_adam_exchange(void* const* vox_ptrs, void* const* grad_p
   const float ssk = adam_step_size_x(lr_k0, beta1, beta2, step);
   const int blocks = (int)min64((end - begin + 255) / 256, (int64_t)sm_count() * 8);
   cudaStream_t s = as_stream(stream);
+  const char* dbg_env = getenv("PP_XCHG_FLAGS");   // timing experiments only: 1 = no peer stores, 2 = no peer loads
+  const int dbg = dbg_env ? atoi(dbg_env) : 0;
 #define PP_LAUNCH_X(W)                                                                         \
   voxel_adam_exchange_kernel<W><<<blocks, 256, 0, s>>>(pp, (float4*)exp_avg, (float4*)exp_avg_sq, \
-                                                       begin, end, rank, ssd, ssk, beta1, beta2, eps)
+                                                       begin, end, rank, ssd, ssk, beta1, beta2, eps, dbg)
   switch (world) {
     case 1: PP_LAUNCH_X(1); break;
     case 2: PP_LAUNCH_X(2); break;

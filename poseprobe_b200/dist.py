@@ -86,13 +86,47 @@ class SharedRecords:
             self.peers = []
 
 
+class SymmRecords:
+    """[n,4] fp32 records in torch symmetric memory: peer pointers AND an NVSwitch multicast address.
+    torch.distributed is plumbing here (allocation + handle exchange); the kernels that use the addresses
+    are this library's."""
+
+    def __init__(self, n_records, device, group, world, zero=False):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.device = device
+        self.tensor = symm_mem.empty((n_records, 4), dtype=torch.float32, device=device)
+        if zero:
+            self.tensor.zero_()
+        name = (group or dist.group.WORLD).group_name
+        self.hdl = symm_mem.rendezvous(self.tensor, name)
+        self.address = self.tensor.data_ptr()
+        self.multicast_ptr = int(self.hdl.multicast_ptr)
+        self.table = (ctypes.c_void_p * world)(*[int(p) for p in self.hdl.buffer_ptrs])
+
+    def exchange(self, group, world, rank):
+        return self.table
+
+    def close(self):
+        pass
+
+
+def nvls_available():
+    try:
+        import torch.distributed._symmetric_memory  # noqa: F401
+        return True
+    except Exception:
+        return False
+
+
 class DistributedDVGO:
     """FusedDVGO replicated over the ranks of a process group."""
 
-    def __init__(self, density, k0, xyz_min, xyz_max, stepsize, group=None, mode="p2p", **kw):
+    def __init__(self, density, k0, xyz_min, xyz_max, stepsize, group=None, mode="auto", **kw):
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        if mode == "auto":
+            mode = "nvls" if nvls_available() else "p2p"
         self.mode = mode if self.world > 1 else "single"
         dev = density.device
         kw = dict(kw)
@@ -102,13 +136,21 @@ class DistributedDVGO:
                 kw[k] = kw[k] / self.world
         kw["mse_scale"] = 1.0 / self.world
         n = density.numel()
+        if self.mode == "nvls":
+            self.vox_mem = SymmRecords(n, dev, group, self.world)
+            self.grad_mem = SymmRecords(n, dev, group, self.world)
+            if not (self.vox_mem.multicast_ptr and self.grad_mem.multicast_ptr):
+                raise RuntimeError("DistributedDVGO(mode='nvls'): no multicast address (NVSwitch/NVLS not available)")
         if self.mode == "p2p":
             self.vox_mem = SharedRecords(n, dev)
             self.grad_mem = SharedRecords(n, dev)
+        if self.mode in ("p2p", "nvls"):
             b, e = shard_bounds(n, self.world, self.rank)
             self.eng = dvgo.FusedDVGO(density, k0, xyz_min, xyz_max, stepsize, vox_buf=self.vox_mem.tensor,
                                       grad_buf=self.grad_mem.tensor, moment_records=max(e - b, 1), **kw)
-            self.sync_mem = SharedRecords(int(lib.pp_peer_sync_bytes()) // 16, dev, zero=True)
+            n_sync = int(lib.pp_peer_sync_bytes()) // 16
+            self.sync_mem = (SymmRecords(n_sync, dev, group, self.world, zero=True) if self.mode == "nvls"
+                             else SharedRecords(n_sync, dev, zero=True))
             torch.cuda.synchronize(dev)
             self.vox_ptrs = self.vox_mem.exchange(group, self.world, self.rank)
             self.grad_ptrs = self.grad_mem.exchange(group, self.world, self.rank)
@@ -118,6 +160,7 @@ class DistributedDVGO:
         else:
             self.eng = dvgo.FusedDVGO(density, k0, xyz_min, xyz_max, stepsize, **kw)
         self.token = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.profile_events = None      # optional: 5 CUDA events (sync1 start, exchange start/end, sync2 end, zero end)
         dist.barrier(group=group)
 
     def train_step(self, rays_o, rays_d, target, events=None):
@@ -147,19 +190,36 @@ class DistributedDVGO:
             return eng.loss_buf
         b1, b2, lr_d, lr_k, eps = eng.hp
         eng.step += 1
+        prof = self.profile_events
         with torch.cuda.device(eng.device):
             s = stream()
+            if prof is not None:
+                prof[0].record()
             # barrier: every rank finished scattering; the local [loss, mse] rides along and comes back summed
             self.epoch += 1
             check(lib.pp_peer_sync(self.sync_ptrs, self.world, self.rank, self.epoch, ptr(eng.loss_buf),
                                    ptr(self.loss_global), s), "peer_sync")
-            check(lib.pp_voxel_adam_exchange(self.vox_ptrs, self.grad_ptrs, ptr(eng.exp_avg), ptr(eng.exp_avg_sq),
-                                             eng.n_voxels, self.world, self.rank, eng.step, b1, b2, lr_d, lr_k,
-                                             eps, s), "voxel_adam_exchange")
+            if prof is not None:
+                prof[1].record()
+            if self.mode == "nvls":
+                check(lib.pp_voxel_adam_exchange_mc(ptr(eng.vox), self.vox_mem.multicast_ptr,
+                                                    self.grad_mem.multicast_ptr, ptr(eng.exp_avg),
+                                                    ptr(eng.exp_avg_sq), eng.n_voxels, self.world, self.rank,
+                                                    eng.step, b1, b2, lr_d, lr_k, eps, s), "voxel_adam_exchange_mc")
+            else:
+                check(lib.pp_voxel_adam_exchange(self.vox_ptrs, self.grad_ptrs, ptr(eng.exp_avg),
+                                                 ptr(eng.exp_avg_sq), eng.n_voxels, self.world, self.rank,
+                                                 eng.step, b1, b2, lr_d, lr_k, eps, s), "voxel_adam_exchange")
+            if prof is not None:
+                prof[2].record()
             # barrier: all slices written, all peers done reading my gradient
             self.epoch += 1
             check(lib.pp_peer_sync(self.sync_ptrs, self.world, self.rank, self.epoch, None, None, s), "peer_sync")
+            if prof is not None:
+                prof[3].record()
         eng.grad.zero_()
+        if prof is not None:
+            prof[4].record()
         return self.loss_global
 
     def render(self, rays_o, rays_d, **kw):
@@ -169,6 +229,9 @@ class DistributedDVGO:
         return self.eng.export_grids()
 
     def close(self):
+        if self.mode == "nvls":
+            torch.cuda.synchronize(self.eng.device)
+            dist.barrier(group=self.group)
         if self.mode == "p2p":
             torch.cuda.synchronize(self.eng.device)
             dist.barrier(group=self.group)

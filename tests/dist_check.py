@@ -34,7 +34,8 @@ def main():
         t = torch.rand(N, 3, generator=torch.Generator().manual_seed(200 + r))
         batches.append((o.to(dev), d.to(dev), t.to(dev)))
     results = {}
-    for mode in ("p2p", "nccl"):
+    modes = ("nvls", "p2p", "nccl") if ppdist.nvls_available() else ("p2p", "nccl")
+    for mode in modes:
         tr = ppdist.DistributedDVGO(density.to(dev), k0.to(dev), mn, mx, 0.5, mode=mode, bg=0.5)
         losses = []
         for _ in range(K):
@@ -56,7 +57,7 @@ def main():
         single_losses.append(eng.train_step(*cat).clone())
     torch.cuda.synchronize()
     sd, sk = eng.export_grids()
-    for mode in ("p2p", "nccl"):
+    for mode in modes:
         d_, k_, ls = results[mode]
         torch.testing.assert_close(ls, torch.stack(single_losses), rtol=1e-4, atol=1e-7)
         for mine, ref in ((d_, sd), (k_, sk)):

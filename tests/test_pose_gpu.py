@@ -100,4 +100,5 @@ def test_se3_chain_end_to_end_gradient(cuda):
     eps = 2e-3
     fd = (loss_of((se3 + eps * delta).detach(), False) - loss_of((se3 - eps * delta).detach(), False)) / (2 * eps)
     lin = float((grad.double() * delta.double()).sum())
+    print('pose chain directional derivative: fd %.6g  analytic %.6g' % (fd, lin))
     assert abs(fd - lin) <= 0.1 * abs(lin) + 1e-6, (fd, lin)
