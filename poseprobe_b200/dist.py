@@ -136,24 +136,31 @@ class DistributedDVGO:
                 kw[k] = kw[k] / self.world
         kw["mse_scale"] = 1.0 / self.world
         n = density.numel()
+        # two gradient buffers: while step k+1 marches into one, the other (already consumed by step k's
+        # exchange) is zeroed on a side stream, off the critical path
         if self.mode == "nvls":
             self.vox_mem = SymmRecords(n, dev, group, self.world)
-            self.grad_mem = SymmRecords(n, dev, group, self.world)
-            if not (self.vox_mem.multicast_ptr and self.grad_mem.multicast_ptr):
+            self.grad_mems = [SymmRecords(n, dev, group, self.world) for _ in range(2)]
+            if not (self.vox_mem.multicast_ptr and all(g.multicast_ptr for g in self.grad_mems)):
                 raise RuntimeError("DistributedDVGO(mode='nvls'): no multicast address (NVSwitch/NVLS not available)")
         if self.mode == "p2p":
             self.vox_mem = SharedRecords(n, dev)
-            self.grad_mem = SharedRecords(n, dev)
+            self.grad_mems = [SharedRecords(n, dev) for _ in range(2)]
         if self.mode in ("p2p", "nvls"):
             b, e = shard_bounds(n, self.world, self.rank)
             self.eng = dvgo.FusedDVGO(density, k0, xyz_min, xyz_max, stepsize, vox_buf=self.vox_mem.tensor,
-                                      grad_buf=self.grad_mem.tensor, moment_records=max(e - b, 1), **kw)
+                                      grad_buf=self.grad_mems[0].tensor, moment_records=max(e - b, 1), **kw)
+            self.grad_mems[1].tensor.zero_()
             n_sync = int(lib.pp_peer_sync_bytes()) // 16
             self.sync_mem = (SymmRecords(n_sync, dev, group, self.world, zero=True) if self.mode == "nvls"
                              else SharedRecords(n_sync, dev, zero=True))
             torch.cuda.synchronize(dev)
             self.vox_ptrs = self.vox_mem.exchange(group, self.world, self.rank)
-            self.grad_ptrs = self.grad_mem.exchange(group, self.world, self.rank)
+            self.grad_ptrs = [g.exchange(group, self.world, self.rank) for g in self.grad_mems]
+            self.cur = 0
+            self.side = torch.cuda.Stream(device=dev)
+            self.zeroed = [torch.cuda.Event(), torch.cuda.Event()]
+            self.consumed = torch.cuda.Event()
             self.sync_ptrs = self.sync_mem.exchange(group, self.world, self.rank)
             self.epoch = 0
             self.loss_global = torch.zeros(2, dtype=torch.float32, device=dev)
@@ -175,6 +182,9 @@ class DistributedDVGO:
     def _train_step(self, rays_o, rays_d, target, events):
         eng = self.eng
         eng.loss_buf.zero_()
+        if self.mode in ("p2p", "nvls"):
+            eng.grad = self.grad_mems[self.cur].tensor
+            torch.cuda.current_stream().wait_event(self.zeroed[self.cur])     # no-op until first recorded
         if events is not None:
             events[0].record()
         eng.backward_only(rays_o, rays_d, target)
@@ -203,11 +213,11 @@ class DistributedDVGO:
                 prof[1].record()
             if self.mode == "nvls":
                 check(lib.pp_voxel_adam_exchange_mc(ptr(eng.vox), self.vox_mem.multicast_ptr,
-                                                    self.grad_mem.multicast_ptr, ptr(eng.exp_avg),
+                                                    self.grad_mems[self.cur].multicast_ptr, ptr(eng.exp_avg),
                                                     ptr(eng.exp_avg_sq), eng.n_voxels, self.world, self.rank,
                                                     eng.step, b1, b2, lr_d, lr_k, eps, s), "voxel_adam_exchange_mc")
             else:
-                check(lib.pp_voxel_adam_exchange(self.vox_ptrs, self.grad_ptrs, ptr(eng.exp_avg),
+                check(lib.pp_voxel_adam_exchange(self.vox_ptrs, self.grad_ptrs[self.cur], ptr(eng.exp_avg),
                                                  ptr(eng.exp_avg_sq), eng.n_voxels, self.world, self.rank,
                                                  eng.step, b1, b2, lr_d, lr_k, eps, s), "voxel_adam_exchange")
             if prof is not None:
@@ -217,7 +227,14 @@ class DistributedDVGO:
             check(lib.pp_peer_sync(self.sync_ptrs, self.world, self.rank, self.epoch, None, None, s), "peer_sync")
             if prof is not None:
                 prof[3].record()
-        eng.grad.zero_()
+        # every peer has finished reading this gradient buffer: clear it on the side stream while the next
+        # step marches into the other buffer
+        self.consumed.record()
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self.consumed)
+            self.grad_mems[self.cur].tensor.zero_()
+            self.zeroed[self.cur].record()
+        self.cur ^= 1
         if prof is not None:
             prof[4].record()
         return self.loss_global
@@ -236,11 +253,12 @@ class DistributedDVGO:
             torch.cuda.synchronize(self.eng.device)
             dist.barrier(group=self.group)
             self.vox_mem.close()
-            self.grad_mem.close()
+            for g in self.grad_mems:
+                g.close()
             self.sync_mem.close()
             dist.barrier(group=self.group)      # nobody maps our buffers any more
             self.eng.vox = self.eng.grad = None
-            for mem in (self.vox_mem, self.grad_mem, self.sync_mem):
+            for mem in [self.vox_mem, self.sync_mem] + self.grad_mems:
                 mem.tensor = None
                 with torch.cuda.device(mem.device):
                     lib.pp_shared_free(ctypes.c_void_p(mem.address))
