@@ -126,7 +126,9 @@ class DistributedDVGO:
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         if mode == "auto":
-            mode = "nvls" if nvls_available() else "p2p"
+            # measured on 8xB200 (profiles/r1_results.md): in-switch reduction wins at 8 ranks, plain peer
+            # loads/stores at 2 and 4 (their link traffic 2(w-1)/w is below NVLS's (w+1)/w there)
+            mode = "nvls" if (self.world >= 8 and nvls_available()) else "p2p"
         self.mode = mode if self.world > 1 else "single"
         dev = density.device
         kw = dict(kw)
