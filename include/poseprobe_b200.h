@@ -219,6 +219,16 @@ PP_API int pp_neus_alpha_backward(const float* sdf, const float* gradient, const
                            const float* grad_alpha, float* grad_sdf, float* grad_gradient,
                            pp_stream_t stream);
 
+/* rgbnet / colour MLP forward on tcgen05 tensor cores (lib/voxurf_coarse.py:208-216, :1032-1033;
+ * lib/dvgo_ori.py:82-89): out[n,3] = [sigmoid](W_L relu(... relu(W_1 x + b_1) ...) + b_L).
+ * x [n, d0] fp32 row-major (the concatenated feature rows the reference builds);
+ * weights / biases: HOST arrays of `depth` DEVICE pointers, nn.Linear layout ([out,in] row-major fp32);
+ * hidden width must be 128, the last layer has 3 outputs, 2 <= depth <= 5, d0 <= 128.
+ * Operands are rounded to bf16, accumulation is fp32 in TMEM; activations never leave the SM. */
+PP_API int pp_rgbnet_forward(const float* x, int64_t n_pts, int32_t d0, int32_t depth, int32_t width,
+                             const float* const* weights, const float* const* biases, int apply_sigmoid,
+                             float* out, pp_stream_t stream);
+
 /* Camera rays for selected pixels (get_rays / get_rays_of_a_view, lib/voxurf_coarse.py:1339-1368, :1402-1407,
  * mode='center' is px = i + 0.5 etc. supplied by the caller; flips are applied to px/py by the caller):
  *   dirs = ((px-cx)/fx, -(py-cy)/fy, -1)   [inverse_y: (.., +(py-cy)/fy, +1)]

@@ -190,3 +190,33 @@ def neus_alpha(viewdirs, ray_id, dist, sdf, gradients, inv_s):
     if not sdf.is_cuda:
         raise RuntimeError("neus_alpha: sdf must be a CUDA tensor (no CPU fallback)")
     return _NeusAlpha.apply(sdf, gradients, viewdirs, ray_id, float(dist), float(inv_s))
+
+
+def rgbnet_forward(x, weights, biases, sigmoid=True):
+    """Colour MLP forward on the tcgen05 tensor cores (no autograd; the render / inference path).
+
+    x [n, d0] fp32; weights / biases: lists of nn.Linear parameters ([out,in] / [out]), hidden width 128,
+    3 outputs.  `rgbnet_from_sequential` extracts them from the reference's nn.Sequential."""
+    import ctypes
+    if not x.is_cuda:
+        raise RuntimeError("rgbnet_forward: x must be a CUDA tensor (no CPU fallback)")
+    x = x.detach().float().contiguous()
+    ws = [w.detach().float().contiguous() for w in weights]
+    bs = [b.detach().float().contiguous() for b in biases]
+    depth = len(ws)
+    if ws[-1].shape[0] != 3:
+        raise RuntimeError("rgbnet_forward: the last layer must have 3 outputs")
+    n, d0 = x.shape
+    out = torch.empty((n, 3), dtype=torch.float32, device=x.device)
+    wp = (ctypes.c_void_p * depth)(*[w.data_ptr() for w in ws])
+    bp = (ctypes.c_void_p * depth)(*[b.data_ptr() for b in bs])
+    with torch.cuda.device(x.device):
+        check(lib.pp_rgbnet_forward(ptr(x), n, d0, depth, ws[0].shape[0], wp, bp, int(bool(sigmoid)), ptr(out),
+                                    stream()), "rgbnet_forward")
+    return out
+
+
+def rgbnet_from_sequential(seq):
+    """(weights, biases) of the reference's rgbnet nn.Sequential (voxurf_coarse.py:208-216)."""
+    lin = [m for m in seq.modules() if isinstance(m, torch.nn.Linear)]
+    return [m.weight for m in lin], [m.bias for m in lin]
