@@ -45,6 +45,7 @@ void count_launch(int n = 1);
 inline cudaStream_t as_stream(pp_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 __host__ __device__ inline int64_t min64(int64_t a, int64_t b) { return a < b ? a : b; }
+__host__ __device__ inline int64_t max64(int64_t a, int64_t b) { return a > b ? a : b; }
 
 inline int ceil_div(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
 

@@ -2,22 +2,16 @@
 //
 // Replaces render_utils_kernel.cu:577-707.  The reference walks each ray's segment with ONE thread
 // (`for(i=i_s; i<i_e_max; ++i)`), so a warp touches 32 different rays per step: every load/store is
-// a 32-way uncoalesced access.  The recurrences themselves are strictly sequential *and* their
-// float roundings decide an integer output (the early-termination index written back to i_end), so
-// they cannot be re-associated.  The B200 design keeps one lane per ray for the recurrence only and
-// moves all memory traffic through a shared-memory tile:
-//     stage   : for each of the warp's 32 rays, the 32 lanes load the next 32 samples (one 128 B line)
-//     chain   : lane r walks row r of the tile (padded, conflict free) - same arithmetic, same order
-//     output  : rows are written back with the 32 lanes across samples (coalesced), and everything
-//               that is not part of the recurrence (w = T*alpha, the backward's division) is done
-//               here, in parallel.
+// a 32-way uncoalesced access, and 8192 rays occupy 256 warps.  The recurrences themselves are strictly
+// sequential *and* their float roundings decide an integer output (the early-termination index written
+// back to i_end), so they cannot be re-associated.  The B200 design gives every ray a group of 8 lanes: they
+// load / store 8 consecutive samples as one sector, the recurrence runs in the reference's order on values
+// broadcast by shuffle (one instruction advances 4 rays), and everything that is not part of the recurrence
+// (w = T*alpha, the backward's division) is done by the lanes in parallel.
 #include "common.cuh"
 
 namespace pp {
 
-constexpr int kTile = 32;
-constexpr int kPad = kTile + 1;
-constexpr int kCompWarps = 2;  // warps per block (each warp owns an independent set of 32 rays)
 
 // ---- segment bounds from a sorted ray_id (reference :607-617 and the host line :635) -------------
 __global__ void segment_bounds_kernel(const int64_t* __restrict__ ray_id, int64_t n_pts,
@@ -37,11 +31,17 @@ __global__ void segment_bounds_kernel(const int64_t* __restrict__ ray_id, int64_
 }
 
 // ---- forward -------------------------------------------------------------------------------------
-// T_cum *= (1. - alpha): double arithmetic narrowed to float each step (reference :596).
-template <typename scalar_t>
-__device__ __forceinline__ float transmit_step(float T_cum, scalar_t a) {
-  return static_cast<float>(static_cast<double>(T_cum) * (1. - static_cast<double>(a)));
-}
+// kGroup lanes per ray, 32/kGroup rays per warp.  The recurrence T_cum *= (1. - alpha) is double arithmetic
+// narrowed to float at every step (reference :596) and its roundings decide the early-termination index, so
+// it is evaluated in the reference's order - by all lanes of the ray's group redundantly, on values broadcast
+// with width-kGroup shuffles.  The loads and stores of a kGroup-sample chunk are one 32-byte sector per ray,
+// lane j keeps the transmittance that entered sample j, nothing passes through shared memory, and one
+// instruction of the chain advances 32/kGroup rays.  8192 rays = 2048 warps, against the reference's
+// one-thread-per-ray loop that leaves 256 warps for 148 SMs and touches 32 different lines per step.
+constexpr int kGroup = 8;                     // lanes per ray
+constexpr int kRaysPerWarp = kWarp / kGroup;
+constexpr int kCompWarps = 4;                 // warps per block
+constexpr int kRaysPerBlock = kCompWarps * kRaysPerWarp;
 
 template <typename scalar_t>
 __global__ void __launch_bounds__(kCompWarps* kWarp)
@@ -49,62 +49,65 @@ alpha2weight_fwd_kernel(const scalar_t* __restrict__ alpha, int64_t n_rays,
                         scalar_t* __restrict__ weight, scalar_t* __restrict__ T_out,
                         scalar_t* __restrict__ alphainv_last, const int64_t* __restrict__ i_start,
                         int64_t* __restrict__ i_end) {
-  __shared__ scalar_t s_a[kCompWarps][kTile][kPad];
-  __shared__ float s_T[kCompWarps][kTile][kPad];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int64_t ray = (blockIdx.x * (int64_t)kCompWarps + w) * kTile + lane;
+  const int lane = threadIdx.x & 31, sub = lane / kGroup, sl = lane % kGroup;
+  const int64_t ray = (blockIdx.x * (int64_t)kCompWarps + (threadIdx.x >> 5)) * kRaysPerWarp + sub;
   const bool live = ray < n_rays;
-  int64_t pos = live ? i_start[ray] : 0;
-  const int64_t end = live ? i_end[ray] : 0;
+  const int64_t begin = live ? i_start[ray] : 0, end = live ? i_end[ray] : 0;
   float T_cum = 1.f;
-  int64_t cut = -1;  // early-termination index (exclusive end), -1 while the ray is still marching
-
-  unsigned pending = __ballot_sync(kFull, pos < end);
-  while (pending) {
-    // stage: one coalesced line per pending ray
-    for (unsigned m = pending; m; m &= m - 1) {
-      const int k = __ffs(m) - 1;
-      const int64_t idx = __shfl_sync(kFull, pos, k) + lane;
-      if (idx < __shfl_sync(kFull, end, k)) s_a[w][k][lane] = alpha[idx];
-    }
-    __syncwarp();
-    // chain: lane r walks its own row
-    if (pos < end) {
-      const int cnt = static_cast<int>(min64(kTile, end - pos));
-      for (int j = 0; j < cnt; ++j) {
-        if (cut < 0) {
-          const scalar_t a = s_a[w][lane][j];
-          s_T[w][lane][j] = T_cum;
-          T_cum = transmit_step(T_cum, a);
-          if (T_cum < 1e-3) cut = pos + j + 1;  // float widened, compared with the double literal
-        } else {
-          s_T[w][lane][j] = 1.f;   // untouched samples keep the reference's fill values
-          s_a[w][lane][j] = 0;     //   T = 1, weight = 0
+  int64_t cut = -1;       // early-termination index (exclusive end), -1 while the ray is still marching
+  int64_t pos = begin;
+  bool active = pos < end;
+  scalar_t a_next = (pos + sl < end) ? alpha[pos + sl] : scalar_t(0);
+  while (__any_sync(kFull, active)) {
+    const int64_t idx = pos + sl;
+    const scalar_t a = a_next;
+    if (active && pos + kGroup < end) a_next = (idx + kGroup < end) ? alpha[idx + kGroup] : scalar_t(0);
+    int done = active ? static_cast<int>(min64(kGroup, end - pos)) : 0;   // samples composited in this chunk
+    const double q = 1. - static_cast<double>(a);
+    float T_mine = 1.f;
+#pragma unroll
+    for (int j = 0; j < kGroup; ++j) {
+      const double qj = __shfl_sync(kFull, q, j, kGroup);
+      if (j < done) {
+        if (sl == j) T_mine = T_cum;
+        T_cum = static_cast<float>(static_cast<double>(T_cum) * qj);
+        if (T_cum < 1e-3) {   // float widened, compared with the double literal (reference :597)
+          done = j + 1;
+          cut = pos + j + 1;
         }
       }
     }
-    __syncwarp();
-    // output: rows go back coalesced; w = T * alpha is computed here
-    for (unsigned m = pending; m; m &= m - 1) {
-      const int k = __ffs(m) - 1;
-      const int64_t idx = __shfl_sync(kFull, pos, k) + lane;
-      if (idx < __shfl_sync(kFull, end, k)) {
-        const float Tv = s_T[w][k][lane];
-        weight[idx] = Tv * s_a[w][k][lane];
-        T_out[idx] = Tv;
-      }
+    if (active && idx < end) {
+      // samples past the termination keep the reference's fill values: T = 1, weight = 0
+      const bool in = sl < done;
+      T_out[idx] = in ? static_cast<scalar_t>(T_mine) : scalar_t(1);
+      weight[idx] = in ? T_mine * a : scalar_t(0);
     }
-    __syncwarp();
-    pos += kTile;
-    pending = __ballot_sync(kFull, pos < end);
+    if (active) {
+      pos += kGroup;
+      active = cut < 0 && pos < end;
+    }
   }
-  if (live) {
+  // tails of early-terminated rays: fill values, written by the whole warp one ray at a time
+#pragma unroll
+  for (int s = 0; s < kRaysPerWarp; ++s) {
+    const int64_t from = __shfl_sync(kFull, (cut >= 0) ? pos : end, s * kGroup);
+    const int64_t to = __shfl_sync(kFull, end, s * kGroup);
+    for (int64_t i = from + lane; i < to; i += kWarp) {
+      T_out[i] = scalar_t(1);
+      weight[i] = scalar_t(0);
+    }
+  }
+  if (live && sl == 0) {
     if (cut >= 0) i_end[ray] = cut;  // otherwise i_end already holds i_e_max (or 0 for an empty ray)
     alphainv_last[ray] = T_cum;
   }
 }
 
 // ---- backward ------------------------------------------------------------------------------------
+// Same shape, walking each ray downwards from its (early-terminated) end: lane j of a chunk is sample
+// top-1-j.  back_cum += grad_weights*weight is an FMA in scalar_t narrowed to float (reference :674); the
+// division and the difference are not part of the recurrence and run in parallel over the lanes.
 template <typename scalar_t>
 __global__ void __launch_bounds__(kCompWarps* kWarp)
 alpha2weight_bwd_kernel(const scalar_t* __restrict__ alpha, const scalar_t* __restrict__ weight,
@@ -112,51 +115,39 @@ alpha2weight_bwd_kernel(const scalar_t* __restrict__ alpha, const scalar_t* __re
                         const int64_t* __restrict__ i_start, const int64_t* __restrict__ i_end,
                         int64_t n_rays, const scalar_t* __restrict__ grad_weights,
                         const scalar_t* __restrict__ grad_last, scalar_t* __restrict__ grad) {
-  __shared__ scalar_t s_gw[kCompWarps][kTile][kPad];
-  __shared__ scalar_t s_w[kCompWarps][kTile][kPad];
-  __shared__ float s_back[kCompWarps][kTile][kPad];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int64_t ray = (blockIdx.x * (int64_t)kCompWarps + w) * kTile + lane;
+  const int lane = threadIdx.x & 31, sub = lane / kGroup, sl = lane % kGroup;
+  const int64_t ray = (blockIdx.x * (int64_t)kCompWarps + (threadIdx.x >> 5)) * kRaysPerWarp + sub;
   const bool live = ray < n_rays;
   const int64_t begin = live ? i_start[ray] : 0;
-  int64_t hi = live ? i_end[ray] : 0;  // exclusive; the tile covers (hi-32, hi], walked downwards
+  int64_t top = live ? i_end[ray] : 0;
   // back_cum = grad_last * alphainv_last (reference :671)
   float back = live ? static_cast<float>(grad_last[ray] * alphainv_last[ray]) : 0.f;
-
-  unsigned pending = __ballot_sync(kFull, begin < hi);
-  while (pending) {
-    for (unsigned m = pending; m; m &= m - 1) {
-      const int k = __ffs(m) - 1;
-      const int64_t idx = __shfl_sync(kFull, hi, k) - 1 - lane;
-      if (idx >= __shfl_sync(kFull, begin, k)) {
-        s_gw[w][k][lane] = grad_weights[idx];
-        s_w[w][k][lane] = weight[idx];
+  while (__any_sync(kFull, top > begin)) {
+    const int64_t idx = top - 1 - sl;
+    const bool valid = idx >= begin;
+    const scalar_t gw = valid ? grad_weights[idx] : scalar_t(0);
+    const scalar_t wv = valid ? weight[idx] : scalar_t(0);
+    const scalar_t Tv = valid ? T[idx] : scalar_t(0);
+    const scalar_t av = valid ? alpha[idx] : scalar_t(0);
+    const int cnt = static_cast<int>(min64(kGroup, max64(top - begin, 0)));
+    float back_mine = 0.f;
+#pragma unroll
+    for (int j = 0; j < kGroup; ++j) {
+      const scalar_t gj = __shfl_sync(kFull, gw, j, kGroup);
+      const scalar_t wj = __shfl_sync(kFull, wv, j, kGroup);
+      if (j < cnt) {
+        if (sl == j) back_mine = back;
+        back = static_cast<float>(fma_rn(gj, wj, static_cast<scalar_t>(back)));
       }
     }
-    __syncwarp();
-    if (begin < hi) {
-      const int cnt = static_cast<int>(min64(kTile, hi - begin));
-      for (int j = 0; j < cnt; ++j) {
-        s_back[w][lane][j] = back;
-        // back_cum += grad_weights*weight : FMA in scalar_t, narrowed to float (reference :674)
-        back = static_cast<float>(fma_rn(s_gw[w][lane][j], s_w[w][lane][j], static_cast<scalar_t>(back)));
-      }
+    if (valid) {
+      // grad = gw*T - back/(1-alpha+1e-10): product in scalar_t, quotient and difference in double
+      const scalar_t gT = mul_rn(gw, Tv);
+      const scalar_t one_minus = scalar_t(1) - av;
+      const double qd = static_cast<double>(back_mine) / (static_cast<double>(one_minus) + 1e-10);
+      grad[idx] = static_cast<scalar_t>(static_cast<double>(gT) - qd);
     }
-    __syncwarp();
-    for (unsigned m = pending; m; m &= m - 1) {
-      const int k = __ffs(m) - 1;
-      const int64_t idx = __shfl_sync(kFull, hi, k) - 1 - lane;
-      if (idx >= __shfl_sync(kFull, begin, k)) {
-        // grad = gw*T - back/(1-alpha+1e-10): product in scalar_t, quotient and difference in double
-        const scalar_t gT = mul_rn(s_gw[w][k][lane], T[idx]);
-        const scalar_t one_minus = scalar_t(1) - alpha[idx];
-        const double q = static_cast<double>(s_back[w][k][lane]) / (static_cast<double>(one_minus) + 1e-10);
-        grad[idx] = static_cast<scalar_t>(static_cast<double>(gT) - q);
-      }
-    }
-    __syncwarp();
-    hi -= kTile;
-    pending = __ballot_sync(kFull, begin < hi);
+    top -= kGroup;
   }
 }
 
@@ -366,7 +357,7 @@ extern "C" int pp_alpha2weight(pp_dtype dtype, const void* alpha, const int64_t*
   PP_REQUIRE(alpha && ray_id && weight && T, PP_ERR_INVALID_ARG, "alpha2weight: null pointer");
   segment_bounds_kernel<<<ceil_div(n_pts, 256), 256, 0, s>>>(ray_id, n_pts, n_rays, i_start, i_end);
   PP_CHECK_LAUNCH("alpha2weight(bounds)");
-  const int rays_per_block = kCompWarps * kTile;
+  const int rays_per_block = kRaysPerBlock;
   PP_DISPATCH(dtype, {
     alpha2weight_fwd_kernel<scalar_t><<<ceil_div(n_rays, rays_per_block), kCompWarps * kWarp, 0, s>>>(
         (const scalar_t*)alpha, n_rays, (scalar_t*)weight, (scalar_t*)T, (scalar_t*)alphainv_last,
@@ -391,7 +382,7 @@ extern "C" int pp_alpha2weight_backward(pp_dtype dtype, const void* alpha, const
   if (n_rays == 0) return PP_OK;
   PP_REQUIRE(alpha && weight && T && alphainv_last && i_start && i_end && grad_weights && grad_last,
              PP_ERR_INVALID_ARG, "alpha2weight_backward: null pointer");
-  const int rays_per_block = kCompWarps * kTile;
+  const int rays_per_block = kRaysPerBlock;
   PP_DISPATCH(dtype, {
     alpha2weight_bwd_kernel<scalar_t><<<ceil_div(n_rays, rays_per_block), kCompWarps * kWarp, 0, s>>>(
         (const scalar_t*)alpha, (const scalar_t*)weight, (const scalar_t*)T,

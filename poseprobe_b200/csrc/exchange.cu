@@ -27,52 +27,74 @@ __device__ __forceinline__ void adam_elem_x(float& p, float g, float& m, float& 
   p = p - mul_rn(step_size, m) / (sqrtf(v) + eps);
 }
 
+// Software pipeline.  A slice is only a few MB, so "every thread loads, then every thread stores" (one wave)
+// uses the two directions of the link one after the other: all gradient records come in, then all parameter
+// records go out, ~2x the one-direction time.  Instead a thread walks kRecordsPerThread records with its loads
+// issued kDepth records ahead: while record i is updated and stored to the peers, the loads of records
+// i+1..i+kDepth are in flight, so both directions carry traffic for the whole kernel.
+constexpr int kXchgThreads = 256;
+constexpr int kRecordsPerThread = 8;
+
 template <int kWorld>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kXchgThreads)
 voxel_adam_exchange_kernel(PeerPtrs pp, float4* __restrict__ m4, float4* __restrict__ v4,
                            int64_t begin, int64_t end, int rank, float ss_density, float ss_k0,
                            float b1, float b2, float eps, int dbg) {
-  constexpr int kUnroll = (kWorld >= 8) ? 2 : 4;   // keep >= 16 peer loads in flight per thread
+  constexpr int kDepth = 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i0 = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < end;
-       i0 += kUnroll * stride) {
-    // reduce: one 16-byte load per rank and record, all issued before the first use (NVLink latency is
-    // ~2 us, so the bytes in flight per SM decide the bandwidth); fixed rank order keeps the sum
-    // deterministic run to run
-    float4 gr[kUnroll][kWorld];
+  const int64_t first = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  // one 16-byte load per rank and record (fixed rank order keeps the sum deterministic run to run)
+  float4 gr[kDepth][kWorld], pq[kDepth], mq[kDepth], vq[kDepth];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const int64_t i = i0 + u * stride;
+  for (int d = 0; d < kDepth; ++d) {
+    const int64_t i = first + d * stride;
+    const bool in = i < end;
 #pragma unroll
-      for (int r = 0; r < kWorld; ++r)
-        gr[u][r] = (i < end) ? pp.grad[(dbg & 2) ? rank : r][i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = 0; r < kWorld; ++r) gr[d][r] = in ? pp.grad[(dbg & 2) ? rank : r][i] : zero;
+    pq[d] = in ? pp.vox[rank][i] : zero;
+    mq[d] = in ? m4[i - begin] : zero;
+    vq[d] = in ? v4[i - begin] : zero;
+  }
+  for (int64_t i = first; i < end; i += stride) {
+    float4 g = gr[0][0];
+#pragma unroll
+    for (int r = 1; r < kWorld; ++r) {
+      g.x += gr[0][r].x;
+      g.y += gr[0][r].y;
+      g.z += gr[0][r].z;
+      g.w += gr[0][r].w;
     }
+    float4 p = pq[0], m = mq[0], v = vq[0];
+    // rotate the pipeline and issue the loads of record i + kDepth*stride
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const int64_t i = i0 + u * stride;
-      if (i >= end) continue;
-      float4 g = gr[u][0];
+    for (int d = 0; d + 1 < kDepth; ++d) {
 #pragma unroll
-      for (int r = 1; r < kWorld; ++r) {
-        g.x += gr[u][r].x;
-        g.y += gr[u][r].y;
-        g.z += gr[u][r].z;
-        g.w += gr[u][r].w;
-      }
-      if (g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f) continue;
-      float4 p = pp.vox[rank][i];
-      float4 m = m4[i - begin], v = v4[i - begin];
-      adam_elem_x(p.x, g.x, m.x, v.x, ss_density, b1, b2, eps);
-      adam_elem_x(p.y, g.y, m.y, v.y, ss_k0, b1, b2, eps);
-      adam_elem_x(p.z, g.z, m.z, v.z, ss_k0, b1, b2, eps);
-      adam_elem_x(p.w, g.w, m.w, v.w, ss_k0, b1, b2, eps);
-      m4[i - begin] = m;
-      v4[i - begin] = v;
-      // gather: the updated record goes to every replica
-#pragma unroll
-      for (int r = 0; r < kWorld; ++r)
-        if (!(dbg & 1) || r == rank) pp.vox[r][i] = p;
+      for (int r = 0; r < kWorld; ++r) gr[d][r] = gr[d + 1][r];
+      pq[d] = pq[d + 1];
+      mq[d] = mq[d + 1];
+      vq[d] = vq[d + 1];
     }
+    {
+      const int64_t n = i + kDepth * stride;
+      const bool in = n < end;
+#pragma unroll
+      for (int r = 0; r < kWorld; ++r) gr[kDepth - 1][r] = in ? pp.grad[(dbg & 2) ? rank : r][n] : zero;
+      pq[kDepth - 1] = in ? pp.vox[rank][n] : zero;
+      mq[kDepth - 1] = in ? m4[n - begin] : zero;
+      vq[kDepth - 1] = in ? v4[n - begin] : zero;
+    }
+    if (g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f) continue;
+    adam_elem_x(p.x, g.x, m.x, v.x, ss_density, b1, b2, eps);
+    adam_elem_x(p.y, g.y, m.y, v.y, ss_k0, b1, b2, eps);
+    adam_elem_x(p.z, g.z, m.z, v.z, ss_k0, b1, b2, eps);
+    adam_elem_x(p.w, g.w, m.w, v.w, ss_k0, b1, b2, eps);
+    m4[i - begin] = m;
+    v4[i - begin] = v;
+    // gather: the updated record goes to every replica
+#pragma unroll
+    for (int r = 0; r < kWorld; ++r)
+      if (!(dbg & 1) || r == rank) pp.vox[r][i] = p;
   }
 }
 
@@ -96,35 +118,52 @@ __device__ __forceinline__ void mc_st(float4* mc_addr, const float4& v) {
                : "memory");
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kXchgThreads)
 voxel_adam_exchange_mc_kernel(const float4* __restrict__ vox_local, float4* vox_mc, const float4* grad_mc,
                               float4* __restrict__ m4, float4* __restrict__ v4, int64_t begin, int64_t end,
                               float ss_density, float ss_k0, float b1, float b2, float eps) {
-  constexpr int kUnroll = 4;
+  // same software pipeline as the peer-load variant: the in-switch reductions of the next records are in
+  // flight (up-link: every GPU's contribution) while this record's multicast store goes out (down-link)
+  constexpr int kDepth = 3;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i0 = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < end;
-       i0 += kUnroll * stride) {
-    float4 g[kUnroll];
+  const int64_t first = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 gq[kDepth], pq[kDepth], mq[kDepth], vq[kDepth];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const int64_t i = i0 + u * stride;
-      g[u] = (i < end) ? mc_ld_reduce_add(grad_mc + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+  for (int d = 0; d < kDepth; ++d) {
+    const int64_t i = first + d * stride;
+    const bool in = i < end;
+    gq[d] = in ? mc_ld_reduce_add(grad_mc + i) : zero;
+    pq[d] = in ? vox_local[i] : zero;
+    mq[d] = in ? m4[i - begin] : zero;
+    vq[d] = in ? v4[i - begin] : zero;
+  }
+  for (int64_t i = first; i < end; i += stride) {
+    const float4 g = gq[0];
+    float4 p = pq[0], m = mq[0], v = vq[0];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
-      const int64_t i = i0 + u * stride;
-      if (i >= end) continue;
-      if (g[u].x == 0.f && g[u].y == 0.f && g[u].z == 0.f && g[u].w == 0.f) continue;
-      float4 p = vox_local[i];
-      float4 m = m4[i - begin], v = v4[i - begin];
-      adam_elem_x(p.x, g[u].x, m.x, v.x, ss_density, b1, b2, eps);
-      adam_elem_x(p.y, g[u].y, m.y, v.y, ss_k0, b1, b2, eps);
-      adam_elem_x(p.z, g[u].z, m.z, v.z, ss_k0, b1, b2, eps);
-      adam_elem_x(p.w, g[u].w, m.w, v.w, ss_k0, b1, b2, eps);
-      m4[i - begin] = m;
-      v4[i - begin] = v;
-      mc_st(vox_mc + i, p);
+    for (int d = 0; d + 1 < kDepth; ++d) {
+      gq[d] = gq[d + 1];
+      pq[d] = pq[d + 1];
+      mq[d] = mq[d + 1];
+      vq[d] = vq[d + 1];
     }
+    {
+      const int64_t n = i + kDepth * stride;
+      const bool in = n < end;
+      gq[kDepth - 1] = in ? mc_ld_reduce_add(grad_mc + n) : zero;
+      pq[kDepth - 1] = in ? vox_local[n] : zero;
+      mq[kDepth - 1] = in ? m4[n - begin] : zero;
+      vq[kDepth - 1] = in ? v4[n - begin] : zero;
+    }
+    if (g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f) continue;
+    adam_elem_x(p.x, g.x, m.x, v.x, ss_density, b1, b2, eps);
+    adam_elem_x(p.y, g.y, m.y, v.y, ss_k0, b1, b2, eps);
+    adam_elem_x(p.z, g.z, m.z, v.z, ss_k0, b1, b2, eps);
+    adam_elem_x(p.w, g.w, m.w, v.w, ss_k0, b1, b2, eps);
+    m4[i - begin] = m;
+    v4[i - begin] = v;
+    mc_st(vox_mc + i, p);
   }
 }
 
@@ -182,6 +221,14 @@ __global__ void peer_sync_kernel(SyncPtrs sp, int world, int me, unsigned int ep
 
 using namespace pp;
 
+// threads walk kRecordsPerThread records each (PP_XCHG_RPT overrides, for timing experiments)
+static int exchange_blocks(int64_t records) {
+  const char* e = getenv("PP_XCHG_RPT");
+  const int rpt = (e && atoi(e) > 0) ? atoi(e) : kRecordsPerThread;
+  const int64_t per_block = (int64_t)kXchgThreads * rpt;
+  return (int)min64((records + per_block - 1) / per_block, (int64_t)sm_count() * 8);
+}
+
 static float adam_step_size_x(float lr, float beta1, float beta2, int step) {
   return lr * sqrtf(1.f - powf(beta2, (float)step)) / (1.f - powf(beta1, (float)step));
 }
@@ -235,8 +282,8 @@ extern "C" int pp_voxel_adam_exchange_mc(const void* vox_local, void* vox_mc, co
   const int64_t begin = shard * rank < n_voxels ? shard * rank : n_voxels;
   const int64_t end = begin + shard < n_voxels ? begin + shard : n_voxels;
   if (end <= begin) return PP_OK;
-  const int blocks = (int)min64((end - begin + 255) / 256, (int64_t)sm_count() * 8);
-  voxel_adam_exchange_mc_kernel<<<blocks, 256, 0, as_stream(stream)>>>(
+  const int blocks = exchange_blocks(end - begin);
+  voxel_adam_exchange_mc_kernel<<<blocks, kXchgThreads, 0, as_stream(stream)>>>(
       (const float4*)vox_local, (float4*)vox_mc, (const float4*)grad_mc, (float4*)exp_avg,
       (float4*)exp_avg_sq, begin, end, adam_step_size_x(lr_density, beta1, beta2, step),
       adam_step_size_x(lr_k0, beta1, beta2, step), beta1, beta2, eps);
@@ -290,12 +337,12 @@ extern "C" int pp_voxel_adam_exchange(void* const* vox_ptrs, void* const* grad_p
   }
   const float ssd = adam_step_size_x(lr_density, beta1, beta2, step);
   const float ssk = adam_step_size_x(lr_k0, beta1, beta2, step);
-  const int blocks = (int)min64((end - begin + 255) / 256, (int64_t)sm_count() * 8);
+  const int blocks = exchange_blocks(end - begin);
   cudaStream_t s = as_stream(stream);
   const char* dbg_env = getenv("PP_XCHG_FLAGS");   // timing experiments only: 1 = no peer stores, 2 = no peer loads
   const int dbg = dbg_env ? atoi(dbg_env) : 0;
 #define PP_LAUNCH_X(W)                                                                         \
-  voxel_adam_exchange_kernel<W><<<blocks, 256, 0, s>>>(pp, (float4*)exp_avg, (float4*)exp_avg_sq, \
+  voxel_adam_exchange_kernel<W><<<blocks, kXchgThreads, 0, s>>>(pp, (float4*)exp_avg, (float4*)exp_avg_sq, \
                                                        begin, end, rank, ssd, ssk, beta1, beta2, eps, dbg)
   switch (world) {
     case 1: PP_LAUNCH_X(1); break;
