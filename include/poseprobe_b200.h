@@ -224,10 +224,47 @@ PP_API int pp_neus_alpha_backward(const float* sdf, const float* gradient, const
  * x [n, d0] fp32 row-major (the concatenated feature rows the reference builds);
  * weights / biases: HOST arrays of `depth` DEVICE pointers, nn.Linear layout ([out,in] row-major fp32);
  * hidden width must be 128, the last layer has 3 outputs, 2 <= depth <= 5, d0 <= 128.
+ * workspace: n * pp_rgbnet_padded_width(d0) * 2 bytes (the bf16 copy of x).
  * Operands are rounded to bf16, accumulation is fp32 in TMEM; activations never leave the SM. */
 PP_API int pp_rgbnet_forward(const float* x, int64_t n_pts, int32_t d0, int32_t depth, int32_t width,
                              const float* const* weights, const float* const* biases, int apply_sigmoid,
-                             float* out, pp_stream_t stream);
+                             float* out, void* workspace, int64_t workspace_bytes, pp_stream_t stream);
+/* Same on packed bf16 [n, k0p] rows; `out` may be null when the compositing epilogue is used:
+ * rgb_marched[ray_id[i], :] += sample_weight[i] * out[i, :]  (segment_coo of w * rgb, voxurf_coarse.py:1034). */
+PP_API int pp_rgbnet_forward_packed(const void* x_packed, int64_t n_pts, int32_t d0, int32_t depth,
+                                    int32_t width, const float* const* weights, const float* const* biases,
+                                    int apply_sigmoid, float* out, const float* sample_weight,
+                                    const int32_t* ray_id, float* rgb_marched, pp_stream_t stream);
+
+/* rgbnet training step on tcgen05: forward recompute + backward of the whole network per 128-sample tile
+ * (autograd of lib/voxurf_coarse.py:1032-1033 `torch.sigmoid(self.rgbnet(rgb_feat))`).
+ * grad_out [n,3]: d loss / d out (post-sigmoid when apply_sigmoid, else d loss / d logits).
+ * grad_x [n,d0] (nullable: skip the input gradient) is overwritten; grad_weights / grad_biases (HOST arrays of
+ * `depth` DEVICE pointers, nn.Linear layouts) are ACCUMULATED into (+=), like autograd's .grad;
+ * rgb_out [n,3] (nullable) receives the recomputed forward output.
+ * workspace: pp_rgbnet_workspace_bytes(n, d0) bytes of device memory (the bf16 copy of x and the padded
+ * input gradient); nothing is allocated inside.
+ * Supported: hidden width 128, 3 outputs, d0 <= 64 with depth <= 4 or d0 <= 128 with depth <= 3 (the 512
+ * TMEM columns hold every layer's weight-gradient accumulator).  bf16 operands, fp32 accumulation. */
+PP_API int pp_rgbnet_backward(const float* x, const float* grad_out, int64_t n_pts, int32_t d0,
+                              int32_t depth, int32_t width, const float* const* weights,
+                              const float* const* biases, int apply_sigmoid, float* grad_x,
+                              float* const* grad_weights, float* const* grad_biases, float* rgb_out,
+                              void* workspace, int64_t workspace_bytes, pp_stream_t stream);
+PP_API int64_t pp_rgbnet_workspace_bytes(int64_t n_pts, int32_t d0);
+
+/* The pieces of pp_rgbnet_backward, for callers that keep features in the kernels' own format (the fused
+ * fine-stage path): x_packed = bf16 [n, k0p] rows, grad_x_padded = fp32 [n, k0p] rows,
+ * k0p = pp_rgbnet_padded_width(d0) (64 or 128), padding columns zero. */
+PP_API int32_t pp_rgbnet_padded_width(int32_t d0);
+PP_API int pp_rgbnet_pack_input(const float* x, int64_t n_pts, int32_t d0, void* x_packed, pp_stream_t stream);
+PP_API int pp_rgbnet_unpack_grad(const float* grad_x_padded, int64_t n_pts, int32_t d0, float* grad_x,
+                                 pp_stream_t stream);
+PP_API int pp_rgbnet_backward_packed(const void* x_packed, const float* grad_out, int64_t n_pts, int32_t d0,
+                                     int32_t depth, int32_t width, const float* const* weights,
+                                     const float* const* biases, int apply_sigmoid, float* grad_x_padded,
+                                     float* const* grad_weights, float* const* grad_biases, float* rgb_out,
+                                     pp_stream_t stream);
 
 /* Camera rays for selected pixels (get_rays / get_rays_of_a_view, lib/voxurf_coarse.py:1339-1368, :1402-1407,
  * mode='center' is px = i + 0.5 etc. supplied by the caller; flips are applied to px/py by the caller):

@@ -1,0 +1,538 @@
+// rgbnet (colour MLP) training step on the 5th-generation tensor cores: forward recompute + full backward
+// (input gradient, weight gradients, bias gradients) of one 128-sample tile without leaving the SM.
+//
+// The reference trains the colour network through autograd over nn.Linear / ReLU (cuBLAS sgemm) with the
+// [M,d0] feature matrix, three [M,128] activations and their gradients round-tripping HBM
+// (lib/voxurf_coarse.py:208-216, :1032-1033).  Here one persistent CTA per SM (8 warps) owns tiles of 128
+// samples:
+//   forward   : as mlp.cu, but every hidden activation tile H_l stays in shared memory (bf16, UMMA canonical
+//               layout) - they are the operands of the backward;
+//   dZ_L      : (d loss / d rgb) * rgb (1 - rgb), rounded to bf16 into a [128 x 16] tile;
+//   per layer : dH_{l-1} = dZ_l W_l            A = dZ_l (K-major), B = W_l read MN-major from the SAME
+//                                              shared-memory copy the forward used (no transposed copy)
+//               dW_l    += dZ_l^T H_{l-1}      both operands read MN-major from the activation tiles: the
+//                                              contraction runs over the tile's 128 samples
+//               db_l    += dZ_l^T 1            an N=16 MMA against an indicator tile (column l is ones)
+//               dZ_{l-1} = dH_{l-1} * (H_{l-1} > 0) is written in place of H_{l-1};
+//   the weight / bias gradients of ALL the CTA's tiles accumulate in TMEM (fp32, 336..496 of the 512 columns)
+//   and are added to global memory once per CTA at the end.
+// MMAs that nothing waits for (dW, db) are issued behind the dH MMA of the same layer and run while the
+// epilogue warps turn dH into the next dZ.  Input rows arrive as bf16 [M, k0p] (k0p = 64 or 128; the feature
+// kernel of the fused path writes that format directly, the fp32 [n,d0] entry point converts once) and are
+// moved with 16-byte cp.async straight into the UMMA layout of the NEXT tile's buffer while the current tile
+// computes; the input gradient leaves as fp32 [M, k0p] rows.  HBM traffic per sample: k0p*2 B in, 12 B
+// gradient in, k0p*4 B input gradient out; activations and their gradients never leave the SM.
+#include "mlp_common.cuh"
+
+namespace pp {
+
+constexpr int kBwdThreads = 512;
+constexpr int kBwdMaxDepth = 4;
+constexpr int kTile = 128;
+// TMEM columns (fp32, 128 lanes)
+constexpr int kColAcc = 0;        // [0,128)   working accumulator: layer outputs, dH, dX
+constexpr int kColOut = 0;        // [0,16)    logits: aliases the working accumulator (free at that point)
+constexpr int kColDb = 128;       // [128,176) hidden-layer bias gradients, 16 columns per layer (all equal)
+constexpr int kColDwLast = 176;   // [176,192) dW_last^T  (lane = input feature, column = output)
+constexpr int kColDw0 = 192;      // [192,192+k0p) dW_0; then 128 columns per further hidden layer
+
+struct MlpBwdParams {
+  const float* w[kBwdMaxDepth];
+  const float* b[kBwdMaxDepth];
+  float* gw[kBwdMaxDepth];
+  float* gb[kBwdMaxDepth];
+  int depth;      // number of Linear layers (2..4)
+  int d0;         // input features
+  int k0p;        // d0 padded to 64 or 128
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// request one 128-row tile of bf16 [M, k0p] rows: 16-byte pieces land at their UMMA canonical positions;
+// 8 consecutive threads read one 128-byte row segment, rows past M are zero-filled
+__device__ __forceinline__ void stage_tile(const __nv_bfloat16* __restrict__ x, int64_t M, int64_t tile, int k0p,
+                                           uint8_t* sX, int tid) {
+  const int chunks_per_row = k0p >> 3;
+  const uint32_t base = smem_u32(sX);
+  for (int id = tid; id < kTile * chunks_per_row; id += kBwdThreads) {
+    const int r = id / chunks_per_row, c8 = id - r * chunks_per_row;
+    const int64_t grow = tile * kTile + r;
+    const bool ok = grow < M;
+    cp_async16(base + canon_off(r, c8 * 8, k0p), x + (ok ? grow : 0) * k0p + c8 * 8, ok ? 16u : 0u);
+  }
+}
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
+rgbnet_backward_kernel(MlpBwdParams P, const __nv_bfloat16* __restrict__ x, const float* __restrict__ grad_out,
+                       int64_t M, int apply_sigmoid, float* __restrict__ grad_x, float* __restrict__ rgb_out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int L = P.depth;
+  const int row = (warp & 3) * 32 + lane;   // TMEM lane = sample row of the tile this thread owns
+  const int cg = warp >> 2;                 // which quarter of an accumulator's columns this thread handles
+  const int k0p = P.k0p, kq = k0p >> 2;     // kq: this thread's share of a k0p-wide accumulator (16 or 32)
+
+  // ---- shared memory map ----
+  uint32_t off = 0;
+  uint8_t* sXbuf[2];
+  sXbuf[0] = smem;
+  sXbuf[1] = smem + kTile * k0p * 2;
+  off += 2 * kTile * k0p * 2;
+  uint8_t* sH[kBwdMaxDepth];
+  for (int l = 0; l < L - 1; ++l) {
+    sH[l] = smem + off;
+    off += kTile * kMlpWidth * 2;
+  }
+  uint8_t* sG = smem + off;
+  off += kTile * kMlpOutPad * 2;
+  uint8_t* sW[kBwdMaxDepth];
+  for (int l = 0; l < L; ++l) {
+    sW[l] = smem + off;
+    const int rows = (l == L - 1) ? kMlpOutPad : kMlpWidth;
+    const int K = (l == 0) ? k0p : kMlpWidth;
+    off += rows * K * 2;
+  }
+  uint8_t* sOnes = smem + off;   // [128 x 16] of ones: B operand of the bias-gradient MMAs
+  off += kTile * kMlpOutPad * 2;
+  float* sBias = reinterpret_cast<float*>(smem + off);
+  off += L * kMlpWidth * 4;
+  float* sDbLast = reinterpret_cast<float*>(smem + off);
+  off += 16;
+  uint64_t* sBar = reinterpret_cast<uint64_t*>(smem + off);
+  uint32_t* sTmem = reinterpret_cast<uint32_t*>(smem + off + 16);
+
+  // ---- prologue: weights -> bf16 canonical layout (one 16-byte chunk = 8 inputs of one output row per
+  //      iteration, 8 independent loads), ones tile, biases, TMEM, mbarriers ----
+  for (int l = 0; l < L; ++l) {
+    const bool last = (l == L - 1);
+    const int rows = last ? kMlpOutPad : kMlpWidth;
+    const int real_rows = last ? 3 : kMlpWidth;
+    const int K = (l == 0) ? k0p : kMlpWidth;
+    const int real_K = (l == 0) ? P.d0 : kMlpWidth;
+    const int cpr = K >> 3;
+    for (int e = tid; e < rows * cpr; e += kBwdThreads) {
+      const int r = e / cpr, k0 = (e - r * cpr) * 8;
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = (r < real_rows && k0 + j < real_K) ? __ldg(P.w[l] + r * real_K + k0 + j) : 0.f;
+      uint4 pk;
+      pk.x = pack_bf16(f[0], f[1]);
+      pk.y = pack_bf16(f[2], f[3]);
+      pk.z = pack_bf16(f[4], f[5]);
+      pk.w = pack_bf16(f[6], f[7]);
+      *reinterpret_cast<uint4*>(sW[l] + canon_off(r, k0, K)) = pk;
+    }
+    for (int e = tid; e < kMlpWidth; e += kBwdThreads)
+      sBias[l * kMlpWidth + e] = (e < real_rows) ? P.b[l][e] : 0.f;
+  }
+  for (int e = tid; e < kTile * kMlpOutPad; e += kBwdThreads)
+    reinterpret_cast<__nv_bfloat16*>(sOnes)[e] = __float2bfloat16_rn(1.f);
+  if (tid < 4) sDbLast[tid] = 0.f;
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)),
+                 "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    mbar_init(smem_u32(sBar), 1);
+    mbar_init(smem_u32(sBar + 1), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *sTmem;
+  const uint32_t barA = smem_u32(sBar), barB = smem_u32(sBar + 1);
+  uint32_t phA = 0, phB = 0;
+  const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  const uint32_t idesc_fwd = umma_idesc_bf16(kTile, kMlpWidth);
+  const int c0 = cg * 32;                   // this thread's 32 columns of a 128-wide accumulator
+
+  bool first = true;
+  int it = 0;
+  const int64_t n_tiles = (M + kTile - 1) / kTile;
+  if (blockIdx.x < n_tiles) stage_tile(x, M, blockIdx.x, k0p, sXbuf[0], tid);
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t grow = tile * kTile + row;
+    const bool valid = grow < M;
+
+    // ---- input tile: it was requested while the previous tile computed; request the next one now ----
+    uint8_t* sX = sXbuf[it & 1];
+    cp_async_wait_all();
+    float gz[3] = {0.f, 0.f, 0.f};   // d loss / d out of this thread's row, consumed after the forward
+    if (cg == 0 && valid) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) gz[j] = __ldg(grad_out + grow * 3 + j);
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (tile + gridDim.x < n_tiles) stage_tile(x, M, tile + gridDim.x, k0p, sXbuf[(it + 1) & 1], tid);
+    ++it;
+
+    // ---- forward, hidden layers: H_l = relu(H_{l-1} W_l^T + b_l), kept in shared memory ----
+    for (int l = 0; l < L - 1; ++l) {
+      if (tid == 0) {
+        tc_fence_after();
+        const int K = (l == 0) ? k0p : kMlpWidth;
+        const uint32_t a0 = smem_u32(l == 0 ? sX : sH[l - 1]), b0 = smem_u32(sW[l]);
+        for (int k = 0; k < (K >> 4); ++k)
+          umma_bf16(tmem + kColAcc, desc_kmajor(a0, K, k), desc_kmajor(b0, K, k), idesc_fwd, k > 0);
+        umma_commit(barA);
+      }
+      mbar_wait(barA, phA);
+      phA ^= 1;
+      tc_fence_after();
+      {
+        uint32_t r[32];
+        tmem_ld32_nowait(tmem + kColAcc + lane_base + c0, r);
+        const float4* b4 = reinterpret_cast<const float4*>(sBias + l * kMlpWidth + c0);
+        float4 bb[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bb[j] = b4[j];
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<uint4*>(sH[l] + canon_off(row, c0 + 8 * j, kMlpWidth)) =
+              bias_relu_pack8(r + 8 * j, bb[2 * j], bb[2 * j + 1]);
+      }
+      tc_fence_before();
+      fence_async_smem();
+      __syncthreads();
+    }
+
+    // ---- forward, output layer + gradient of the logits ----
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t a0 = smem_u32(sH[L - 2]), b0 = smem_u32(sW[L - 1]);
+      const uint32_t idesc = umma_idesc_bf16(kTile, kMlpOutPad);
+      for (int k = 0; k < (kMlpWidth >> 4); ++k)
+        umma_bf16(tmem + kColOut, desc_kmajor(a0, kMlpWidth, k), desc_kmajor(b0, kMlpWidth, k), idesc, k > 0);
+      umma_commit(barA);
+    }
+    mbar_wait(barA, phA);
+    phA ^= 1;
+    tc_fence_after();
+    if (cg == 0) {
+      float v[16];
+      tmem_ld16(tmem + kColOut + lane_base, v);
+      const float* bias = sBias + (L - 1) * kMlpWidth;
+      float dz[3];
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const float z = v[j] + bias[j];
+        const float y = apply_sigmoid ? 1.f / (1.f + __expf(-z)) : z;
+        const float g = gz[j];
+        dz[j] = apply_sigmoid ? g * y * (1.f - y) : g;
+        if (rgb_out && valid) rgb_out[grow * 3 + j] = y;
+      }
+      uint4 pk;
+      pk.x = pack_bf16(dz[0], dz[1]);
+      pk.y = pack_bf16(dz[2], 0.f);
+      pk.z = 0u;
+      pk.w = 0u;
+      *reinterpret_cast<uint4*>(sG + canon_off(row, 0, kMlpOutPad)) = pk;
+      *reinterpret_cast<uint4*>(sG + canon_off(row, 8, kMlpOutPad)) = make_uint4(0u, 0u, 0u, 0u);
+      // last-layer bias gradient: column sums of dZ_L over the tile (3 values: done on the CUDA cores)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const float s = warp_sum(dz[j]);
+        if (lane == 0) atomicAdd(&sDbLast[j], s);
+      }
+    }
+    tc_fence_before();
+    fence_async_smem();
+    __syncthreads();
+
+    // ---- backward ----
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t h0 = smem_u32(sH[L - 2]), g0 = smem_u32(sG), w0 = smem_u32(sW[L - 1]);
+      // dW_last^T += H_{L-2}^T dZ_L : M = 128 input features, N = 16, contraction over the samples
+      const uint32_t id_wl = umma_idesc_bf16_major(kTile, kMlpOutPad, 1, 1);
+      for (int s = 0; s < (kTile >> 4); ++s)
+        umma_bf16(tmem + kColDwLast, desc_mnmajor(h0, kMlpWidth, s), desc_mnmajor(g0, kMlpOutPad, s), id_wl,
+                  (!first) || s > 0);
+      // dH_{L-2} = dZ_L W_L : contraction over the 16 (padded) outputs, one K slice
+      umma_bf16(tmem + kColAcc, desc_kmajor(g0, kMlpOutPad, 0), desc_mnmajor(w0, kMlpWidth, 0),
+                umma_idesc_bf16_major(kTile, kMlpWidth, 0, 1), 0);
+      umma_commit(barA);
+    }
+    for (int l = L - 2; l >= 0; --l) {
+      mbar_wait(barA, phA);
+      phA ^= 1;
+      tc_fence_after();
+      // dZ_l = dH_l * (H_l > 0), packed to bf16 in registers
+      uint4 pk[4];
+      {
+        uint32_t r[32];
+        tmem_ld32_nowait(tmem + kColAcc + lane_base + c0, r);
+        uint4 act[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          act[j] = *reinterpret_cast<const uint4*>(sH[l] + canon_off(row, c0 + 8 * j, kMlpWidth));
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pk[j] = relu_grad_pack8(r + 8 * j, act[j]);
+      }
+      if (l < L - 2) {   // dW_{l+1} reads H_l (its B operand): it must have finished before H_l is overwritten
+        mbar_wait(barB, phB);
+        phB ^= 1;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(sH[l] + canon_off(row, c0 + 8 * j, kMlpWidth)) = pk[j];
+      tc_fence_before();
+      fence_async_smem();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t z0 = smem_u32(sH[l]), w0 = smem_u32(sW[l]);
+        if (l > 0) {
+          // dH_{l-1} = dZ_l W_l : contraction over this layer's 128 outputs
+          const uint32_t id = umma_idesc_bf16_major(kTile, kMlpWidth, 0, 1);
+          for (int s = 0; s < (kMlpWidth >> 4); ++s)
+            umma_bf16(tmem + kColAcc, desc_kmajor(z0, kMlpWidth, s), desc_mnmajor(w0, kMlpWidth, s), id, s > 0);
+        } else if (grad_x) {
+          // dX = dZ_0 W_0
+          const uint32_t id = umma_idesc_bf16_major(kTile, k0p, 0, 1);
+          for (int s = 0; s < (kMlpWidth >> 4); ++s)
+            umma_bf16(tmem + kColAcc, desc_kmajor(z0, kMlpWidth, s), desc_mnmajor(w0, k0p, s), id, s > 0);
+        }
+        umma_commit(barA);
+        // dW_l += dZ_l^T H_{l-1} : both operands MN-major, contraction over the samples
+        const int in = (l == 0) ? k0p : kMlpWidth;
+        const uint32_t t0 = smem_u32(l == 0 ? sX : sH[l - 1]);
+        const uint32_t col = (l == 0) ? kColDw0 : kColDw0 + k0p + (l - 1) * kMlpWidth;
+        const uint32_t id_w = umma_idesc_bf16_major(kTile, in, 1, 1);
+        for (int s = 0; s < (kTile >> 4); ++s)
+          umma_bf16(tmem + col, desc_mnmajor(z0, kMlpWidth, s), desc_mnmajor(t0, in, s), id_w, (!first) || s > 0);
+        // db_l += dZ_l^T 1 (every one of the layer's 16 columns receives the column sums)
+        const uint32_t o0 = smem_u32(sOnes);
+        const uint32_t id_b = umma_idesc_bf16_major(kTile, kMlpOutPad, 1, 1);
+        for (int s = 0; s < (kTile >> 4); ++s)
+          umma_bf16(tmem + kColDb + l * kMlpOutPad, desc_mnmajor(z0, kMlpWidth, s),
+                    desc_mnmajor(o0, kMlpOutPad, s), id_b, (!first) || s > 0);
+        umma_commit(barB);
+      }
+    }
+    mbar_wait(barA, phA);
+    phA ^= 1;
+    tc_fence_after();
+    if (grad_x) {
+      // this thread's kq columns of dX, fp32 rows of k0p
+      const int cx = cg * kq;
+      if (kq == 32) {
+        float v[32];
+        tmem_ld32(tmem + kColAcc + lane_base + cx, v);
+        if (valid) {
+          float4* dst = reinterpret_cast<float4*>(grad_x + grow * k0p + cx);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      } else {
+        float v[16];
+        tmem_ld16(tmem + kColAcc + lane_base + cx, v);
+        if (valid) {
+          float4* dst = reinterpret_cast<float4*>(grad_x + grow * k0p + cx);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      }
+    }
+    mbar_wait(barB, phB);   // dW_0 read the X tile: done before the next tile is staged
+    phB ^= 1;
+    tc_fence_before();
+    __syncthreads();
+    first = false;
+  }
+
+  // ---- the CTA's weight / bias gradients: TMEM -> global (fp32 atomics, once per CTA) ----
+  tc_fence_after();
+  if (!first) {
+    for (int l = 1; l < L - 1; ++l) {
+      const uint32_t col = kColDw0 + k0p + (l - 1) * kMlpWidth;
+      float v[32];
+      tmem_ld32(tmem + col + lane_base + c0, v);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) atomicAdd(P.gw[l] + row * kMlpWidth + c0 + j, v[j]);
+    }
+    {
+      const int cx = cg * kq;
+      if (kq == 32) {
+        float v[32];
+        tmem_ld32(tmem + kColDw0 + lane_base + cx, v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (cx + j < P.d0) atomicAdd(P.gw[0] + row * P.d0 + cx + j, v[j]);
+      } else {
+        float v[16];
+        tmem_ld16(tmem + kColDw0 + lane_base + cx, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (cx + j < P.d0) atomicAdd(P.gw[0] + row * P.d0 + cx + j, v[j]);
+      }
+    }
+    if (cg == 0) {
+      float v[16];
+      tmem_ld16(tmem + kColDwLast + lane_base, v);
+#pragma unroll
+      for (int o = 0; o < 3; ++o) atomicAdd(P.gw[L - 1] + o * kMlpWidth + row, v[o]);
+    } else if (cg == 1) {
+      for (int l = 0; l < L - 1; ++l) {
+        float v[16];
+        tmem_ld16(tmem + kColDb + l * kMlpOutPad + lane_base, v);
+        atomicAdd(P.gb[l] + row, v[0]);
+      }
+    }
+    if (tid < 3) atomicAdd(P.gb[L - 1] + tid, sDbLast[tid]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
+// fp32 [n,d0] rows -> bf16 [n,k0p] rows (zero padded): one thread per 8 output columns
+__global__ void rgbnet_pack_kernel(const float* __restrict__ x, int64_t n, int d0, int k0p,
+                                   __nv_bfloat16* __restrict__ out) {
+  const int cpr = k0p >> 3;
+  for (int64_t id = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; id < n * cpr;
+       id += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = id / cpr;
+    const int c0 = static_cast<int>(id - r * cpr) * 8;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = (c0 + j < d0) ? __ldg(x + r * d0 + c0 + j) : 0.f;
+    uint4 pk;
+    pk.x = pack_bf16(f[0], f[1]);
+    pk.y = pack_bf16(f[2], f[3]);
+    pk.z = pack_bf16(f[4], f[5]);
+    pk.w = pack_bf16(f[6], f[7]);
+    *reinterpret_cast<uint4*>(out + r * k0p + c0) = pk;
+  }
+}
+
+// fp32 [n,k0p] rows -> fp32 [n,d0] rows
+__global__ void rgbnet_unpack_kernel(const float* __restrict__ gx, int64_t n, int d0, int k0p,
+                                     float* __restrict__ out) {
+  for (int64_t id = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; id < n * d0;
+       id += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = id / d0;
+    const int c = static_cast<int>(id - r * d0);
+    out[id] = gx[r * k0p + c];
+  }
+}
+
+}  // namespace pp
+
+using namespace pp;
+
+extern "C" int32_t pp_rgbnet_padded_width(int32_t d0) { return d0 <= 64 ? 64 : 128; }
+
+extern "C" int64_t pp_rgbnet_workspace_bytes(int64_t n_pts, int32_t d0) {
+  if (n_pts <= 0 || d0 <= 0) return 0;
+  const int64_t k0p = pp_rgbnet_padded_width(d0);
+  return n_pts * k0p * 2 + n_pts * k0p * 4 + 256;
+}
+
+extern "C" int pp_rgbnet_pack_input(const float* x, int64_t n_pts, int32_t d0, void* x_packed,
+                                    pp_stream_t stream) {
+  PP_REQUIRE(n_pts >= 0 && d0 >= 1 && d0 <= kMlpWidth, PP_ERR_INVALID_ARG, "rgbnet_pack_input: bad extent");
+  if (n_pts == 0) return PP_OK;
+  PP_REQUIRE(x && x_packed, PP_ERR_INVALID_ARG, "rgbnet_pack_input: null pointer");
+  const int k0p = pp_rgbnet_padded_width(d0);
+  const int64_t work = n_pts * (k0p >> 3);
+  const int blocks = (int)min64((work + 255) / 256, (int64_t)sm_count() * 16);
+  rgbnet_pack_kernel<<<blocks, 256, 0, as_stream(stream)>>>(x, n_pts, d0, k0p, (__nv_bfloat16*)x_packed);
+  PP_CHECK_LAUNCH("rgbnet_pack_input");
+  return PP_OK;
+}
+
+extern "C" int pp_rgbnet_unpack_grad(const float* grad_x_padded, int64_t n_pts, int32_t d0, float* grad_x,
+                                     pp_stream_t stream) {
+  PP_REQUIRE(n_pts >= 0 && d0 >= 1 && d0 <= kMlpWidth, PP_ERR_INVALID_ARG, "rgbnet_unpack_grad: bad extent");
+  if (n_pts == 0) return PP_OK;
+  PP_REQUIRE(grad_x_padded && grad_x, PP_ERR_INVALID_ARG, "rgbnet_unpack_grad: null pointer");
+  const int k0p = pp_rgbnet_padded_width(d0);
+  const int blocks = (int)min64((n_pts * d0 + 255) / 256, (int64_t)sm_count() * 16);
+  rgbnet_unpack_kernel<<<blocks, 256, 0, as_stream(stream)>>>(grad_x_padded, n_pts, d0, k0p, grad_x);
+  PP_CHECK_LAUNCH("rgbnet_unpack_grad");
+  return PP_OK;
+}
+
+extern "C" int pp_rgbnet_backward_packed(const void* x_packed, const float* grad_out, int64_t n_pts, int32_t d0,
+                                         int32_t depth, int32_t width, const float* const* weights,
+                                         const float* const* biases, int apply_sigmoid, float* grad_x_padded,
+                                         float* const* grad_weights, float* const* grad_biases, float* rgb_out,
+                                         pp_stream_t stream) {
+  PP_REQUIRE(n_pts >= 0, PP_ERR_INVALID_ARG, "rgbnet_backward: n_pts < 0");
+  PP_REQUIRE(width == kMlpWidth, PP_ERR_UNSUPPORTED, "rgbnet_backward: hidden width must be %d", kMlpWidth);
+  PP_REQUIRE(depth >= 2 && depth <= kBwdMaxDepth, PP_ERR_UNSUPPORTED, "rgbnet_backward: depth must be 2..%d",
+             kBwdMaxDepth);
+  PP_REQUIRE(d0 >= 1 && d0 <= kMlpWidth, PP_ERR_UNSUPPORTED, "rgbnet_backward: 1 <= d0 <= %d", kMlpWidth);
+  if (n_pts == 0) return PP_OK;
+  PP_REQUIRE(x_packed && grad_out && weights && biases && grad_weights && grad_biases, PP_ERR_INVALID_ARG,
+             "rgbnet_backward: null pointer");
+  MlpBwdParams P;
+  P.depth = depth;
+  P.d0 = d0;
+  P.k0p = pp_rgbnet_padded_width(d0);
+  // TMEM budget: 192 fixed columns + dW_0 (k0p) + 128 per further hidden layer <= 512
+  PP_REQUIRE(kColDw0 + P.k0p + (depth - 2) * kMlpWidth <= 512, PP_ERR_UNSUPPORTED,
+             "rgbnet_backward: depth %d with %d input features exceeds the 512 TMEM columns "
+             "(supported: d0 <= 64 up to depth 4, d0 <= 128 up to depth 3)", depth, d0);
+  size_t smem = (size_t)2 * kTile * P.k0p * 2 + (size_t)(depth - 1) * kTile * kMlpWidth * 2 +
+                (size_t)2 * kTile * kMlpOutPad * 2 + (size_t)depth * kMlpWidth * 4 + 64;
+  for (int l = 0; l < kBwdMaxDepth; ++l) {
+    P.w[l] = l < depth ? weights[l] : nullptr;
+    P.b[l] = l < depth ? biases[l] : nullptr;
+    P.gw[l] = l < depth ? grad_weights[l] : nullptr;
+    P.gb[l] = l < depth ? grad_biases[l] : nullptr;
+    PP_REQUIRE(l >= depth || (P.w[l] && P.b[l] && P.gw[l] && P.gb[l]), PP_ERR_INVALID_ARG,
+               "rgbnet_backward: null layer %d", l);
+    if (l < depth) {
+      const int rows = (l == depth - 1) ? kMlpOutPad : kMlpWidth;
+      const int K = (l == 0) ? P.k0p : kMlpWidth;
+      smem += (size_t)rows * K * 2;
+    }
+  }
+  PP_REQUIRE(smem <= 227 * 1024, PP_ERR_UNSUPPORTED, "rgbnet_backward: %zu B of shared memory needed", smem);
+  PP_CHECK_CUDA(cudaFuncSetAttribute(rgbnet_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t n_tiles = (n_pts + kTile - 1) / kTile;
+  const int blocks = (int)min64(n_tiles, sm_count());
+  rgbnet_backward_kernel<<<blocks, kBwdThreads, smem, as_stream(stream)>>>(
+      P, (const __nv_bfloat16*)x_packed, grad_out, n_pts, apply_sigmoid, grad_x_padded, rgb_out);
+  PP_CHECK_LAUNCH("rgbnet_backward");
+  return PP_OK;
+}
+
+extern "C" int pp_rgbnet_backward(const float* x, const float* grad_out, int64_t n_pts, int32_t d0,
+                                  int32_t depth, int32_t width, const float* const* weights,
+                                  const float* const* biases, int apply_sigmoid, float* grad_x,
+                                  float* const* grad_weights, float* const* grad_biases, float* rgb_out,
+                                  void* workspace, int64_t workspace_bytes, pp_stream_t stream) {
+  PP_REQUIRE(n_pts >= 0, PP_ERR_INVALID_ARG, "rgbnet_backward: n_pts < 0");
+  if (n_pts == 0) return PP_OK;
+  PP_REQUIRE(d0 >= 1 && d0 <= kMlpWidth, PP_ERR_UNSUPPORTED, "rgbnet_backward: 1 <= d0 <= %d", kMlpWidth);
+  PP_REQUIRE(workspace && workspace_bytes >= pp_rgbnet_workspace_bytes(n_pts, d0), PP_ERR_INVALID_ARG,
+             "rgbnet_backward: workspace of %lld bytes required (pp_rgbnet_workspace_bytes)",
+             (long long)pp_rgbnet_workspace_bytes(n_pts, d0));
+  const int64_t k0p = pp_rgbnet_padded_width(d0);
+  uint8_t* ws = (uint8_t*)workspace;
+  void* xp = ws;
+  float* gxp = (float*)(ws + (n_pts * k0p * 2 + 255) / 256 * 256);
+  int rc = pp_rgbnet_pack_input(x, n_pts, d0, xp, stream);
+  if (rc != PP_OK) return rc;
+  rc = pp_rgbnet_backward_packed(xp, grad_out, n_pts, d0, depth, width, weights, biases, apply_sigmoid,
+                                 grad_x ? gxp : nullptr, grad_weights, grad_biases, rgb_out, stream);
+  if (rc != PP_OK) return rc;
+  if (grad_x) rc = pp_rgbnet_unpack_grad(gxp, n_pts, d0, grad_x, stream);
+  return rc;
+}

@@ -210,10 +210,55 @@ def rgbnet_forward(x, weights, biases, sigmoid=True):
     out = torch.empty((n, 3), dtype=torch.float32, device=x.device)
     wp = (ctypes.c_void_p * depth)(*[w.data_ptr() for w in ws])
     bp = (ctypes.c_void_p * depth)(*[b.data_ptr() for b in bs])
+    nbytes = n * int(lib.pp_rgbnet_padded_width(d0)) * 2
+    work = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=x.device)
     with torch.cuda.device(x.device):
         check(lib.pp_rgbnet_forward(ptr(x), n, d0, depth, ws[0].shape[0], wp, bp, int(bool(sigmoid)), ptr(out),
-                                    stream()), "rgbnet_forward")
+                                    ptr(work), nbytes, stream()), "rgbnet_forward")
     return out
+
+
+class _RgbNet(torch.autograd.Function):
+    """sigmoid(rgbnet(x)) with both directions on tcgen05; the backward recomputes the forward per tile."""
+
+    @staticmethod
+    def forward(ctx, x, sigmoid, depth, *params):
+        weights, biases = params[:depth], params[depth:]
+        out = rgbnet_forward(x, weights, biases, sigmoid)
+        ctx.save_for_backward(x, *params)
+        ctx.cfg = (sigmoid, depth)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        import ctypes
+        x, *params = ctx.saved_tensors
+        sigmoid, depth = ctx.cfg
+        x = x.detach().float().contiguous()
+        ws = [w.detach().float().contiguous() for w in params[:depth]]
+        bs = [b.detach().float().contiguous() for b in params[depth:]]
+        n, d0 = x.shape
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gws = [torch.zeros_like(w) for w in ws]
+        gbs = [torch.zeros_like(b) for b in bs]
+        arr = lambda ts: (ctypes.c_void_p * depth)(*[t.data_ptr() for t in ts])
+        nbytes = int(lib.pp_rgbnet_workspace_bytes(n, d0))
+        work = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            check(lib.pp_rgbnet_backward(ptr(x), ptr(grad_out.float().contiguous()), n, d0, depth, ws[0].shape[0],
+                                         arr(ws), arr(bs), int(bool(sigmoid)), ptr(gx), arr(gws), arr(gbs), None,
+                                         ptr(work), nbytes, stream()), "rgbnet_backward")
+        return (gx, None, None) + tuple(gws) + tuple(gbs)
+
+
+def rgbnet(x, weights, biases, sigmoid=True):
+    """Differentiable colour MLP: drop-in for `torch.sigmoid(self.rgbnet(rgb_feat))`
+    (lib/voxurf_coarse.py:1032-1033).  Gradients flow to x, the weights and the biases."""
+    if not x.is_cuda:
+        raise RuntimeError("rgbnet: x must be a CUDA tensor (no CPU fallback)")
+    depth = len(weights)
+    return _RgbNet.apply(x, sigmoid, depth, *weights, *biases)
 
 
 def rgbnet_from_sequential(seq):
