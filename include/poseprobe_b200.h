@@ -230,11 +230,13 @@ PP_API int pp_rgbnet_forward(const float* x, int64_t n_pts, int32_t d0, int32_t 
                              const float* const* weights, const float* const* biases, int apply_sigmoid,
                              float* out, void* workspace, int64_t workspace_bytes, pp_stream_t stream);
 /* Same on packed bf16 [n, k0p] rows; `out` may be null when the compositing epilogue is used:
- * rgb_marched[ray_id[i], :] += sample_weight[i] * out[i, :]  (segment_coo of w * rgb, voxurf_coarse.py:1034). */
+ * rgb_marched[ray_id[i], :] += sample_weight[i] * out[i, :]  (segment_coo of w * rgb, voxurf_coarse.py:1034).
+ * n_ptr (nullable): DEVICE int32 row count produced by an earlier kernel; n_pts is then the capacity. */
 PP_API int pp_rgbnet_forward_packed(const void* x_packed, int64_t n_pts, int32_t d0, int32_t depth,
                                     int32_t width, const float* const* weights, const float* const* biases,
                                     int apply_sigmoid, float* out, const float* sample_weight,
-                                    const int32_t* ray_id, float* rgb_marched, pp_stream_t stream);
+                                    const int32_t* ray_id, float* rgb_marched, const int32_t* n_ptr,
+                                    pp_stream_t stream);
 
 /* rgbnet training step on tcgen05: forward recompute + backward of the whole network per 128-sample tile
  * (autograd of lib/voxurf_coarse.py:1032-1033 `torch.sigmoid(self.rgbnet(rgb_feat))`).
@@ -265,6 +267,16 @@ PP_API int pp_rgbnet_backward_packed(const void* x_packed, const float* grad_out
                                      const float* const* biases, int apply_sigmoid, float* grad_x_padded,
                                      float* const* grad_weights, float* const* grad_biases, float* rgb_out,
                                      pp_stream_t stream);
+
+/* Fine-stage form: grad_out_i = sample_weight[i] * g_ray[sample_ray[i], :] is formed in the kernel (sigmoid
+ * output), grad_weight_out[i] = sum_c g_ray[sample_ray[i],c] * rgb_i,c, and only the 16 leading input-gradient
+ * columns are stored (grad_feat16 [capacity,16]); the row count is read from the device (n_ptr). */
+PP_API int pp_rgbnet_backward_fused(const void* x_packed, int64_t capacity, const int32_t* n_ptr, int32_t d0,
+                                    int32_t depth, int32_t width, const float* const* weights,
+                                    const float* const* biases, const float* sample_weight,
+                                    const int32_t* sample_ray, const float* g_ray, float* grad_weight_out,
+                                    float* grad_feat16, float* const* grad_weights, float* const* grad_biases,
+                                    pp_stream_t stream);
 
 /* Camera rays for selected pixels (get_rays / get_rays_of_a_view, lib/voxurf_coarse.py:1339-1368, :1402-1407,
  * mode='center' is px = i + 0.5 etc. supplied by the caller; flips are applied to px/py by the caller):

@@ -149,6 +149,73 @@ PP_API int pp_voxel_adam_exchange_mc(const void* vox_local, void* vox_mc, const 
                                      int32_t rank, int32_t step, float beta1, float beta2,
                                      float lr_density, float lr_k0, float eps, pp_stream_t stream);
 
+/* ---- Voxurf fine stage (SDF grid + 12-channel feature grid + rgbnet), fused -------------------------------
+ * Reference: Voxurf.forward, non-deform branch (lib/voxurf_coarse.py:922-1091).  A train step is
+ *   pp_voxurf_march_features -> pp_rgbnet_forward_packed (compositing epilogue) -> pp_voxurf_ray_loss ->
+ *   pp_rgbnet_backward_fused -> pp_voxurf_backward -> pp_voxurf_sdf_adam + pp_voxel_adam (feature records) ->
+ *   pp_voxurf_build_records.
+ * SDF records: float4 per voxel {s', d s'/dx, d s'/dy, d s'/dz} with s' = a (sigmoid(b s) - 0.5) (the per-step
+ * grid remap :946-949; a = 0 means s' = s) and the central-difference gradient grid of neus_sdf_gradient
+ * ('interpolate', :463-467).  Feature records: 3 float4 per voxel = the 12 channels of k0.
+ * Feature row of the MLP (bf16, 64 columns): [0,12) k0 | [12,15) normal | 15: 0 | [16,19) rays_xyz |
+ * [19,34) sin(xyz 2^k) (coordinate-major, stride 5) | [34,49) cos | [49,52) viewdirs | [52,55) sin | [55,58) cos |
+ * [58,64) 0, BARF weights applied; the caller permutes the first layer's columns accordingly (reference order,
+ * :1005-1030: k0 | xyz | sin | cos | viewdirs | sin | cos | normal). */
+typedef struct pp_voxurf_cfg {
+  float inv_s;              /* 1 / s_val (voxurf_coarse.py:495) */
+  float sdf_scale_a;        /* softplus10(sdf_alpha); 0 disables the mapping function */
+  float sdf_scale_b;        /* softplus10(sdf_beta) */
+  float voxel_size;         /* divisor of the finite-difference gradient grid */
+  int32_t pos_pe;           /* posbase_pe, <= 5 */
+  int32_t view_pe;          /* viewbase_pe, <= 1 in the fused path */
+  float pe_w_pos[8];        /* BARF coarse-to-fine weight per frequency (:721-732), 1 = off */
+  float pe_w_view[8];
+} pp_voxurf_cfg;
+
+PP_API int pp_voxurf_build_records(const pp_dvgo_scene* scene, const pp_voxurf_cfg* cfg, const float* sdf,
+                                   void* sdf_records, pp_stream_t stream);
+PP_API int pp_voxurf_k0_pack(const float* k0, int64_t n_voxels, void* k0_records, pp_stream_t stream);
+PP_API int pp_voxurf_k0_unpack(const void* k0_records, int64_t n_voxels, float* k0, pp_stream_t stream);
+
+/* Forward march of n_rays rays.  Composited samples (in the box, before early termination) are written to
+ * compacted slots [0, counter[0]) in ray-arrival order: feat [capacity,64] bf16, sample_weight, sample_ray
+ * (int32), sample_rec (float4: interpolated SDF record).  Per ray: ray_off / ray_cnt (its slot range),
+ * ray_end (exclusive step index where the march stopped), cum_w (sum of weights), alphainv_last.
+ * counter: 2 x int32 on the device; counter[0] = samples written, counter[1] = 1 if `capacity` was too small
+ * (rays that did not fit contribute nothing).  jitter (nullable): per-ray step offset in [0,1) (:712-713). */
+PP_API int pp_voxurf_march_features(const pp_dvgo_scene* scene, const pp_voxurf_cfg* cfg,
+                                    const void* sdf_records, const void* k0_records, const float* rays_o,
+                                    const float* rays_d, const float* viewdirs, const float* jitter,
+                                    int64_t n_rays, int32_t capacity, void* feat, float* sample_weight,
+                                    int32_t* sample_ray, void* sample_rec, int32_t* ray_off, int32_t* ray_cnt,
+                                    int32_t* ray_end, float* cum_w, float* alphainv_last, int32_t* counter,
+                                    pp_stream_t stream);
+
+/* rgb_marched = clamp(rgb_acc + (1 - cum_w) bg, 0, 1) (:1040-1042); photometric MSE (lib/losses.py:26-29):
+ * g_ray [N,3] = d (w_rgb * mse) / d rgb_acc, loss_out[0] += w_rgb * mse, loss_out[1] += mse. */
+PP_API int pp_voxurf_ray_loss(int64_t n_rays, const float* rgb_acc, const float* cum_w, const float* target,
+                              float bg, float w_rgb, float* g_ray, float* rgb_marched, float* loss_out,
+                              pp_stream_t stream);
+
+/* Reverse march: alpha2weight / NeuS / normal backward per ray and the scatter into grad_sdf_records
+ * ([V] float4, same layout as the SDF records) and grad_k0_records ([V][3] float4); both are accumulated into. */
+PP_API int pp_voxurf_backward(const pp_dvgo_scene* scene, const pp_voxurf_cfg* cfg, const float* rays_o,
+                              const float* rays_d, const float* viewdirs, const float* jitter, int64_t n_rays,
+                              const void* sample_rec, const float* grad_weight, const float* grad_feat16,
+                              const int32_t* ray_off, const int32_t* ray_cnt, const int32_t* ray_end,
+                              const float* g_ray, void* grad_sdf_records, void* grad_k0_records,
+                              pp_stream_t stream);
+
+/* Dense tail of the SDF grid: folds the gradient-grid components back onto the SDF (transposed central
+ * difference), applies the mapping function's chain rule and masked Adam (adam_upd_kernel.cu:35-39) in place.
+ * exp_avg / exp_avg_sq null: no update (gradient only).  grad_sdf_out (nullable) receives d loss / d sdf;
+ * grad_ab (nullable, 2 floats, accumulated) receives d loss / d (a, b).  The caller zeroes grad_sdf_records
+ * afterwards and rebuilds the records. */
+PP_API int pp_voxurf_sdf_adam(const pp_dvgo_scene* scene, const pp_voxurf_cfg* cfg, float* sdf,
+                              const void* grad_sdf_records, float* exp_avg, float* exp_avg_sq, int32_t step,
+                              float beta1, float beta2, float lr, float eps, float* grad_sdf_out, float* grad_ab,
+                              pp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

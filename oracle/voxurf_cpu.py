@@ -1,0 +1,122 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement of the Voxurf fine-stage render / train step.
+
+Follows ``Voxurf.forward`` of the reference, non-deform branch (lib/voxurf_coarse.py:922-1091), op by op in
+plain PyTorch so that autograd yields the reference's gradients:
+
+    sample (CUDA sampler semantics, render_utils_kernel.cu:196-242 via the C oracle; optional per-ray jitter of
+    sample_ray_ori :712-713) -> ``~mask_outbbox`` compaction (:686-693 / :940-945) -> sdf grid remap (:946-949)
+    -> neus_sdf_gradient 'interpolate' (:463-467) -> grid_sampler (border, :522-543) of sdf and gradient ->
+    neus_alpha_from_sdf_scatter (:494-517) -> Alphas2Weights (:1316-1332, C oracle) -> k0 DenseGrid (lib/grid.py:
+    47-58) -> rgb_feat assembly with BARF weights (:1005-1030, :721-732) -> rgbnet + sigmoid (:1032-1033) ->
+    segment_coo sums restated as index_add_ (:1034-1042) -> photometric MSE (lib/losses.py:26-29).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline may import this module.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+from . import oracle
+from .dvgo_cpu import _Alphas2Weights
+
+
+def softplus10(x):
+    return F.softplus(torch.as_tensor(float(x)), beta=10).item()
+
+
+def sdf_gradient_grid(sdf, voxel_size):
+    """neus_sdf_gradient(mode='interpolate'), voxurf_coarse.py:463-467."""
+    g = torch.zeros([1, 3] + list(sdf.shape[-3:]), dtype=sdf.dtype)
+    gx = (sdf[:, 0, 2:, :, :] - sdf[:, 0, :-2, :, :]) / 2 / voxel_size
+    gy = (sdf[:, 0, :, 2:, :] - sdf[:, 0, :, :-2, :]) / 2 / voxel_size
+    gz = (sdf[:, 0, :, :, 2:] - sdf[:, 0, :, :, :-2]) / 2 / voxel_size
+    g = torch.cat([F.pad(gx, (0, 0, 0, 0, 1, 1))[:, None], F.pad(gy, (0, 0, 1, 1, 0, 0))[:, None],
+                   F.pad(gz, (1, 1, 0, 0, 0, 0))[:, None]], 1)
+    return g
+
+
+def grid_sampler(xyz, grid, xyz_min, xyz_max, padding_mode):
+    ind = ((xyz - xyz_min) / (xyz_max - xyz_min)).flip((-1,)) * 2 - 1
+    out = F.grid_sample(grid, ind.reshape(1, 1, 1, -1, 3), mode="bilinear", align_corners=True,
+                        padding_mode=padding_mode)
+    return out.reshape(grid.shape[1], -1).T
+
+
+def barf_weights(progress, barf_c2f, L):
+    if barf_c2f is None:
+        return torch.ones(L)
+    start, end = barf_c2f
+    alpha = (progress - start) / (end - start) * L
+    k = torch.arange(L, dtype=torch.float32)
+    return (1 - (alpha - k).clamp(min=0, max=1).mul(math.pi).cos()) / 2
+
+
+def sample(rays_o, rays_d, xyz_min, xyz_max, near, far, stepdist, jitter=None):
+    """-> pts [M,3], ray_id [M], step_id [M] of the in-box samples (reference order)."""
+    pts, mask, ray_id, step_id, n_steps, t_min, t_max = oracle.sample_pts_on_rays(rays_o, rays_d, xyz_min, xyz_max,
+                                                                                   near, far, stepdist)[:7]
+    if jitter is not None:
+        # same enumeration, points shifted by jitter steps along the normalised direction
+        start, dirn = oracle.infer_ray_start_dir(rays_o, rays_d, t_min)
+        dist = stepdist * (step_id.float() + jitter[ray_id])
+        pts = start[ray_id] + dirn[ray_id] * dist[:, None]
+        mask = ((xyz_min > pts) | (pts > xyz_max)).any(-1)
+    keep = ~mask
+    return pts[keep], ray_id[keep], step_id[keep]
+
+
+def forward(sdf_grid, k0_grid, rgbnet, rays_o, rays_d, viewdirs, xyz_min, xyz_max, stepsize, voxel_size, s_val,
+            near=0.2, far=1e9, bg=0.0, sdf_alpha=None, sdf_beta=None, posbase_pe=5, viewbase_pe=1, barf_c2f=None,
+            progress=1.0, jitter=None):
+    """sdf_grid [1,1,X,Y,Z], k0_grid [1,12,X,Y,Z] (may require grad), rgbnet: callable rows -> logits."""
+    xyz_min = torch.as_tensor(xyz_min, dtype=torch.float32)
+    xyz_max = torch.as_tensor(xyz_max, dtype=torch.float32)
+    n = rays_o.shape[0]
+    stepdist = stepsize * voxel_size
+    pts, ray_id, step_id = sample(rays_o, rays_d, xyz_min, xyz_max, near, far, stepdist, jitter)
+    grid = sdf_grid
+    if sdf_alpha is not None:
+        grid = softplus10(sdf_alpha) * (torch.sigmoid(softplus10(sdf_beta) * sdf_grid) - 0.5)
+    sdf = grid_sampler(pts, grid, xyz_min, xyz_max, "border")[:, 0]
+    gradient = grid_sampler(pts, sdf_gradient_grid(grid, voxel_size), xyz_min, xyz_max, "border")
+    # neus_alpha_from_sdf_scatter, :494-517
+    dirs = viewdirs[ray_id]
+    inv_s = 1.0 / s_val
+    true_cos = (dirs * gradient).sum(-1, keepdim=True)
+    iter_cos = -F.relu(-true_cos)
+    s = sdf.unsqueeze(-1)
+    nxt = s + iter_cos * stepdist * 0.5
+    prv = s - iter_cos * stepdist * 0.5
+    prev_cdf = torch.sigmoid(prv * inv_s)
+    next_cdf = torch.sigmoid(nxt * inv_s)
+    alpha = ((prev_cdf - next_cdf + 1e-5) / (prev_cdf + 1e-5)).clip(0.0, 1.0).squeeze(-1)
+    weights, alphainv_last = _Alphas2Weights.apply(alpha, ray_id, n)
+    # colour features, :1005-1030
+    k0 = grid_sampler(pts, k0_grid, xyz_min, xyz_max, "zeros")
+    rays_xyz = (pts - xyz_min) / (xyz_max - xyz_min)
+    posfreq = torch.tensor([2.0 ** i for i in range(posbase_pe)])
+    viewfreq = torch.tensor([2.0 ** i for i in range(viewbase_pe)])
+    xyz_emb = (rays_xyz.unsqueeze(-1) * posfreq).flatten(-2)
+    xyz_emb = torch.cat([xyz_emb.sin(), xyz_emb.cos()], -1)
+    if posbase_pe:
+        xyz_emb = (xyz_emb.reshape(-1, posbase_pe) * barf_weights(progress, barf_c2f, posbase_pe)).reshape(xyz_emb.shape)
+    xyz_emb = torch.cat([rays_xyz, xyz_emb], -1)
+    view_emb = (viewdirs.unsqueeze(-1) * viewfreq).flatten(-2)
+    view_emb = torch.cat([view_emb.sin(), view_emb.cos()], -1)
+    if viewbase_pe:
+        view_emb = (view_emb.reshape(-1, viewbase_pe) * barf_weights(progress, barf_c2f, viewbase_pe)).reshape(view_emb.shape)
+    view_emb = torch.cat([viewdirs, view_emb], -1)
+    normal = gradient / (gradient.norm(dim=-1, keepdim=True) + 1e-5)
+    rgb_feat = torch.cat([k0, xyz_emb, view_emb[ray_id], normal], -1)
+    rgb = torch.sigmoid(rgbnet(rgb_feat))
+    rgb_acc = torch.zeros(n, 3).index_add_(0, ray_id, weights.unsqueeze(-1) * rgb)
+    cum_weights = torch.zeros(n, 1).index_add_(0, ray_id, weights.unsqueeze(-1))
+    rgb_marched = (rgb_acc + (1 - cum_weights) * bg).clamp(0, 1)
+    return {"rgb_marched": rgb_marched, "alphainv_cum": alphainv_last, "weights": weights, "cum_weights": cum_weights,
+            "raw_alpha": alpha, "raw_rgb": rgb, "ray_id": ray_id, "step_id": step_id, "gradient": gradient,
+            "sdf": sdf, "rgb_feat": rgb_feat, "normal": normal, "k0": k0, "pts": pts}
+
+
+def mse_loss(out, target, w_rgb=1.0):
+    return w_rgb * F.mse_loss(out["rgb_marched"], target)

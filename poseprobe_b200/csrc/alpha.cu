@@ -6,6 +6,7 @@
 // grid covers the array once.  The arithmetic keeps the reference's operand types (float/double
 // promotion of the literals) so results are bit-identical to the reference kernels for fp32.
 #include "common.cuh"
+#include "neus.cuh"
 
 namespace pp {
 
@@ -45,31 +46,6 @@ __global__ void raw2alpha_bwd_kernel(const scalar_t* __restrict__ exp_d,
     g = capped * static_cast<double>(p) * static_cast<double>(interval) * static_cast<double>(grad_back[i]);
   }
   grad[i] = static_cast<scalar_t>(g);
-}
-
-// ---- NeuS SDF -> alpha (voxurf_coarse.py:483-519, use_mid branch, cos_anneal_ratio = 1) ------------
-__device__ __forceinline__ float sigmoidf_ref(float x) { return 1.f / (1.f + expf(-x)); }
-
-struct NeusTerms {
-  float tc;          // viewdir . gradient
-  float P, Q;        // prev_cdf, next_cdf
-  float num, den;    // (P - Q + 1e-5), (P + 1e-5)
-};
-
-__device__ __forceinline__ NeusTerms neus_terms(float sdf, const float g[3], const float v[3],
-                                                float dist, float inv_s) {
-  NeusTerms t;
-  // torch: (dirs * gradients).sum(-1) - three rounded products, summed left to right
-  t.tc = add_rn(add_rn(mul_rn(v[0], g[0]), mul_rn(v[1], g[1])), mul_rn(v[2], g[2]));
-  const float iter_cos = -fmaxf(-t.tc, 0.f);
-  const float half = mul_rn(mul_rn(iter_cos, dist), 0.5f);
-  const float next = add_rn(sdf, half);
-  const float prev = add_rn(sdf, -half);
-  t.P = sigmoidf_ref(mul_rn(prev, inv_s));
-  t.Q = sigmoidf_ref(mul_rn(next, inv_s));
-  t.num = add_rn(add_rn(t.P, -t.Q), 1e-5f);
-  t.den = add_rn(t.P, 1e-5f);
-  return t;
 }
 
 __global__ void neus_alpha_fwd_kernel(const float* __restrict__ sdf, const float* __restrict__ gradient,

@@ -44,8 +44,9 @@ __device__ __forceinline__ void group_sync(int g) {
 __global__ void __launch_bounds__(kFwdThreads, 1)
 rgbnet_forward_kernel(MlpParams P, const __nv_bfloat16* __restrict__ x, int64_t M, int apply_sigmoid,
                       float* __restrict__ out, const float* __restrict__ wgt, const int32_t* __restrict__ ray_id,
-                      float* __restrict__ rgb_marched) {
+                      float* __restrict__ rgb_marched, const int32_t* __restrict__ n_ptr) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  if (n_ptr) M = min64(M, static_cast<int64_t>(*n_ptr));   // row count produced on the device (compacted samples)
   const int tid = threadIdx.x, g = tid >> 8, gt = tid & 255, warp = gt >> 5, lane = tid & 31;
   const int L = P.depth, k0p = P.k0p;
   const int row = (warp & 3) * 32 + lane, half = warp >> 2;
@@ -218,7 +219,8 @@ using namespace pp;
 extern "C" int pp_rgbnet_forward_packed(const void* x_packed, int64_t n_pts, int32_t d0, int32_t depth,
                                         int32_t width, const float* const* weights, const float* const* biases,
                                         int apply_sigmoid, float* out, const float* sample_weight,
-                                        const int32_t* ray_id, float* rgb_marched, pp_stream_t stream) {
+                                        const int32_t* ray_id, float* rgb_marched, const int32_t* n_ptr,
+                                        pp_stream_t stream) {
   PP_REQUIRE(n_pts >= 0, PP_ERR_INVALID_ARG, "rgbnet_forward: n_pts < 0");
   PP_REQUIRE(width == kMlpWidth, PP_ERR_UNSUPPORTED, "rgbnet_forward: hidden width must be %d", kMlpWidth);
   PP_REQUIRE(depth >= 2 && depth <= kMlpMaxDepth, PP_ERR_UNSUPPORTED, "rgbnet_forward: depth must be 2..%d",
@@ -250,7 +252,7 @@ extern "C" int pp_rgbnet_forward_packed(const void* x_packed, int64_t n_pts, int
   const int64_t n_tiles = (n_pts + kFwdTile - 1) / kFwdTile;
   const int blocks = (int)min64((n_tiles + 1) / 2, sm_count());
   rgbnet_forward_kernel<<<blocks, kFwdThreads, smem, as_stream(stream)>>>(
-      P, (const __nv_bfloat16*)x_packed, n_pts, apply_sigmoid, out, sample_weight, ray_id, rgb_marched);
+      P, (const __nv_bfloat16*)x_packed, n_pts, apply_sigmoid, out, sample_weight, ray_id, rgb_marched, n_ptr);
   PP_CHECK_LAUNCH("rgbnet_forward");
   return PP_OK;
 }
@@ -269,5 +271,5 @@ extern "C" int pp_rgbnet_forward(const float* x, int64_t n_pts, int32_t d0, int3
   int rc = pp_rgbnet_pack_input(x, n_pts, d0, workspace, stream);
   if (rc != PP_OK) return rc;
   return pp_rgbnet_forward_packed(workspace, n_pts, d0, depth, width, weights, biases, apply_sigmoid, out,
-                                  nullptr, nullptr, nullptr, stream);
+                                  nullptr, nullptr, nullptr, nullptr, stream);
 }

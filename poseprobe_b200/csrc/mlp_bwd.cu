@@ -36,6 +36,16 @@ constexpr int kColDb = 128;       // [128,176) hidden-layer bias gradients, 16 c
 constexpr int kColDwLast = 176;   // [176,192) dW_last^T  (lane = input feature, column = output)
 constexpr int kColDw0 = 192;      // [192,192+k0p) dW_0; then 128 columns per further hidden layer
 
+// optional fused inputs / outputs of the fine-stage step (all null / 0 for the plain operator)
+struct MlpFusedIO {
+  const int32_t* n_ptr;     // device row count (compacted samples), clamps M
+  const float* w;           // per-sample compositing weight
+  const int32_t* ray_id;    // per-sample ray
+  const float* g_ray;       // [N,3] d loss / d rgb_marched: grad_out_i = w_i * g_ray[ray_i]
+  float* gw_out;            // [M] sum_c g_ray[ray_i,c] * rgb_i,c  (d loss / d w_i through the colour sum)
+  int dx_cols;              // columns of the input gradient to store (row pitch): k0p or 16
+};
+
 struct MlpBwdParams {
   const float* w[kBwdMaxDepth];
   const float* b[kBwdMaxDepth];
@@ -69,8 +79,10 @@ __device__ __forceinline__ void stage_tile(const __nv_bfloat16* __restrict__ x, 
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
 rgbnet_backward_kernel(MlpBwdParams P, const __nv_bfloat16* __restrict__ x, const float* __restrict__ grad_out,
-                       int64_t M, int apply_sigmoid, float* __restrict__ grad_x, float* __restrict__ rgb_out) {
+                       int64_t M, int apply_sigmoid, float* __restrict__ grad_x, float* __restrict__ rgb_out,
+                       MlpFusedIO F) {
   extern __shared__ __align__(1024) uint8_t smem[];
+  if (F.n_ptr) M = min64(M, static_cast<int64_t>(*F.n_ptr));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = P.depth;
   const int row = (warp & 3) * 32 + lane;   // TMEM lane = sample row of the tile this thread owns
@@ -167,9 +179,20 @@ rgbnet_backward_kernel(MlpBwdParams P, const __nv_bfloat16* __restrict__ x, cons
     uint8_t* sX = sXbuf[it & 1];
     cp_async_wait_all();
     float gz[3] = {0.f, 0.f, 0.f};   // d loss / d out of this thread's row, consumed after the forward
+    float gr[3] = {0.f, 0.f, 0.f};   // fused mode: d loss / d rgb_marched of the row's ray
     if (cg == 0 && valid) {
+      if (F.w) {
+        const float wv = __ldg(F.w + grow);
+        const int64_t rid = __ldg(F.ray_id + grow);
 #pragma unroll
-      for (int j = 0; j < 3; ++j) gz[j] = __ldg(grad_out + grow * 3 + j);
+        for (int j = 0; j < 3; ++j) {
+          gr[j] = __ldg(F.g_ray + rid * 3 + j);
+          gz[j] = wv * gr[j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) gz[j] = __ldg(grad_out + grow * 3 + j);
+      }
     }
     fence_async_smem();
     __syncthreads();
@@ -224,14 +247,17 @@ rgbnet_backward_kernel(MlpBwdParams P, const __nv_bfloat16* __restrict__ x, cons
       tmem_ld16(tmem + kColOut + lane_base, v);
       const float* bias = sBias + (L - 1) * kMlpWidth;
       float dz[3];
+      float gw_acc = 0.f;
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         const float z = v[j] + bias[j];
         const float y = apply_sigmoid ? 1.f / (1.f + __expf(-z)) : z;
         const float g = gz[j];
         dz[j] = apply_sigmoid ? g * y * (1.f - y) : g;
+        gw_acc += gr[j] * y;
         if (rgb_out && valid) rgb_out[grow * 3 + j] = y;
       }
+      if (F.gw_out && valid) F.gw_out[grow] = gw_acc;
       uint4 pk;
       pk.x = pack_bf16(dz[0], dz[1]);
       pk.y = pack_bf16(dz[2], 0.f);
@@ -331,16 +357,16 @@ rgbnet_backward_kernel(MlpBwdParams P, const __nv_bfloat16* __restrict__ x, cons
       if (kq == 32) {
         float v[32];
         tmem_ld32(tmem + kColAcc + lane_base + cx, v);
-        if (valid) {
-          float4* dst = reinterpret_cast<float4*>(grad_x + grow * k0p + cx);
+        if (valid && cx < F.dx_cols) {
+          float4* dst = reinterpret_cast<float4*>(grad_x + grow * F.dx_cols + cx);
 #pragma unroll
           for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
       } else {
         float v[16];
         tmem_ld16(tmem + kColAcc + lane_base + cx, v);
-        if (valid) {
-          float4* dst = reinterpret_cast<float4*>(grad_x + grow * k0p + cx);
+        if (valid && cx < F.dx_cols) {
+          float4* dst = reinterpret_cast<float4*>(grad_x + grow * F.dx_cols + cx);
 #pragma unroll
           for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
@@ -467,23 +493,26 @@ extern "C" int pp_rgbnet_unpack_grad(const float* grad_x_padded, int64_t n_pts, 
   return PP_OK;
 }
 
-extern "C" int pp_rgbnet_backward_packed(const void* x_packed, const float* grad_out, int64_t n_pts, int32_t d0,
-                                         int32_t depth, int32_t width, const float* const* weights,
-                                         const float* const* biases, int apply_sigmoid, float* grad_x_padded,
-                                         float* const* grad_weights, float* const* grad_biases, float* rgb_out,
-                                         pp_stream_t stream) {
+static int launch_rgbnet_backward(const void* x_packed, const float* grad_out, int64_t n_pts, int32_t d0,
+                                  int32_t depth, int32_t width, const float* const* weights,
+                                  const float* const* biases, int apply_sigmoid, float* grad_x_padded,
+                                  float* const* grad_weights, float* const* grad_biases, float* rgb_out,
+                                  MlpFusedIO F, pp_stream_t stream) {
   PP_REQUIRE(n_pts >= 0, PP_ERR_INVALID_ARG, "rgbnet_backward: n_pts < 0");
   PP_REQUIRE(width == kMlpWidth, PP_ERR_UNSUPPORTED, "rgbnet_backward: hidden width must be %d", kMlpWidth);
   PP_REQUIRE(depth >= 2 && depth <= kBwdMaxDepth, PP_ERR_UNSUPPORTED, "rgbnet_backward: depth must be 2..%d",
              kBwdMaxDepth);
   PP_REQUIRE(d0 >= 1 && d0 <= kMlpWidth, PP_ERR_UNSUPPORTED, "rgbnet_backward: 1 <= d0 <= %d", kMlpWidth);
   if (n_pts == 0) return PP_OK;
-  PP_REQUIRE(x_packed && grad_out && weights && biases && grad_weights && grad_biases, PP_ERR_INVALID_ARG,
+  PP_REQUIRE(x_packed && (grad_out || F.w) && weights && biases && grad_weights && grad_biases, PP_ERR_INVALID_ARG,
              "rgbnet_backward: null pointer");
   MlpBwdParams P;
   P.depth = depth;
   P.d0 = d0;
   P.k0p = pp_rgbnet_padded_width(d0);
+  if (F.dx_cols == 0) F.dx_cols = P.k0p;
+  PP_REQUIRE(F.dx_cols == P.k0p || (F.dx_cols == 16 && P.k0p == 64), PP_ERR_INVALID_ARG,
+             "rgbnet_backward: dx_cols must be the padded width or 16");
   // TMEM budget: 192 fixed columns + dW_0 (k0p) + 128 per further hidden layer <= 512
   PP_REQUIRE(kColDw0 + P.k0p + (depth - 2) * kMlpWidth <= 512, PP_ERR_UNSUPPORTED,
              "rgbnet_backward: depth %d with %d input features exceeds the 512 TMEM columns "
@@ -508,9 +537,32 @@ extern "C" int pp_rgbnet_backward_packed(const void* x_packed, const float* grad
   const int64_t n_tiles = (n_pts + kTile - 1) / kTile;
   const int blocks = (int)min64(n_tiles, sm_count());
   rgbnet_backward_kernel<<<blocks, kBwdThreads, smem, as_stream(stream)>>>(
-      P, (const __nv_bfloat16*)x_packed, grad_out, n_pts, apply_sigmoid, grad_x_padded, rgb_out);
+      P, (const __nv_bfloat16*)x_packed, grad_out, n_pts, apply_sigmoid, grad_x_padded, rgb_out, F);
   PP_CHECK_LAUNCH("rgbnet_backward");
   return PP_OK;
+}
+
+extern "C" int pp_rgbnet_backward_packed(const void* x_packed, const float* grad_out, int64_t n_pts, int32_t d0,
+                                         int32_t depth, int32_t width, const float* const* weights,
+                                         const float* const* biases, int apply_sigmoid, float* grad_x_padded,
+                                         float* const* grad_weights, float* const* grad_biases, float* rgb_out,
+                                         pp_stream_t stream) {
+  MlpFusedIO F = {nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+  return launch_rgbnet_backward(x_packed, grad_out, n_pts, d0, depth, width, weights, biases, apply_sigmoid,
+                                grad_x_padded, grad_weights, grad_biases, rgb_out, F, stream);
+}
+
+extern "C" int pp_rgbnet_backward_fused(const void* x_packed, int64_t capacity, const int32_t* n_ptr, int32_t d0,
+                                        int32_t depth, int32_t width, const float* const* weights,
+                                        const float* const* biases, const float* sample_weight,
+                                        const int32_t* sample_ray, const float* g_ray, float* grad_weight_out,
+                                        float* grad_feat16, float* const* grad_weights,
+                                        float* const* grad_biases, pp_stream_t stream) {
+  PP_REQUIRE(sample_weight && sample_ray && g_ray && grad_weight_out && grad_feat16, PP_ERR_INVALID_ARG,
+             "rgbnet_backward_fused: null pointer");
+  MlpFusedIO F = {n_ptr, sample_weight, sample_ray, g_ray, grad_weight_out, 16};
+  return launch_rgbnet_backward(x_packed, nullptr, capacity, d0, depth, width, weights, biases, 1, grad_feat16,
+                                grad_weights, grad_biases, nullptr, F, stream);
 }
 
 extern "C" int pp_rgbnet_backward(const float* x, const float* grad_out, int64_t n_pts, int32_t d0,

@@ -1,0 +1,647 @@
+// Fused Voxurf fine-stage (SDF + feature grid + rgbnet) march kernels (include/poseprobe_b200_fused.h).
+//
+// Reference path (lib/voxurf_coarse.py:922-1091, non-deform branch): sample_ray -> sdf grid remap (:946-949)
+// -> grid_sampler(sdf) + grid_sampler(neus_sdf_gradient(sdf)) (:987-989, :458-481 'interpolate') ->
+// neus_alpha_from_sdf_scatter (:483-519) -> Alphas2Weights -> k0 DenseGrid (12 ch) -> positional encodings with
+// BARF weights (:1005-1030) -> rgbnet -> segment_coo sums (:1034-1042) -> loss -> autograd of all of it.
+// ~150 kernels and ~3 KB of per-sample intermediates per step.
+//
+// Here a step is five launches around the tcgen05 MLP kernels:
+//   voxurf_march_kernel    one warp per ray: gathers 16-byte SDF records {s', ds'/dx, ds'/dy, ds'/dz} (value and
+//                          finite-difference gradient grid in ONE 8-corner gather), NeuS alpha, warp-scan
+//                          compositing with early termination; then, only for composited samples, gathers the
+//                          12-channel feature records (3 x float4 per corner), builds the 64-column bf16 feature
+//                          row of the MLP in registers and writes it with its weight / ray id to a compacted slot
+//   rgbnet forward         (mlp.cu) with the compositing epilogue: rgb_marched += w * rgb
+//   voxurf_ray_loss_kernel per ray: background term, clamp, MSE, d loss / d rgb_marched
+//   rgbnet backward        (mlp_bwd.cu) with d loss/d rgb_i = w_i * g_ray formed in-kernel; emits d loss / d w_i and
+//                          the 16 leading input-gradient columns (features + normal)
+//   voxurf_backward_kernel one warp per ray, reverse walk: alpha2weight backward as a suffix scan, NeuS backward,
+//                          normal backward, 128-bit red.global.add scatters into the SDF-record and feature-record
+//                          gradients
+// and two dense passes: fold the gradient-grid gradient back onto the SDF (transposed central difference) fused
+// with the mapping function's chain rule and masked Adam, and the rebuild of the SDF records.
+#include <stdlib.h>
+
+#include <atomic>
+
+#include "march_common.cuh"
+#include "neus.cuh"
+#include <cuda_bf16.h>
+
+namespace pp {
+
+constexpr int kFeatCols = 64;       // feature row of the MLP (bf16), column map below
+constexpr int kColK0 = 0;           // [0,12)   k0 features
+constexpr int kColNormal = 12;      // [12,15)  normal, 15 = 0
+constexpr int kColXyz = 16;         // [16,19) rays_xyz, [19,34) sin(x 2^k) coordinate-major with stride 5, [34,49) cos
+constexpr int kColView = 49;        // [49,52) viewdirs, [52,55) sin, [55,58) cos; [58,64) = 0
+constexpr int kDxCols = 16;         // leading input-gradient columns the backward consumes
+
+__device__ unsigned int g_vox_queue[kQueueSlots];
+
+__device__ __forceinline__ float sdf_map(float s, float a, float b) {
+  return a > 0.f ? a * (1.f / (1.f + __expf(-b * s)) - 0.5f) : s;
+}
+
+// ---- SDF records: {s', central differences of s' / (2 voxel_size)} (neus_sdf_gradient 'interpolate':
+//      zero on the first / last slice of each axis, voxurf_coarse.py:463-467) ------------------------------
+__global__ void __launch_bounds__(256)
+sdf_records_kernel(const float* __restrict__ sdf, int sx, int sy, int sz, float a, float b, float inv_2vs,
+                   float4* __restrict__ srec) {
+  const int k = blockIdx.x * 32 + threadIdx.x;
+  const int j = blockIdx.y * 8 + threadIdx.y;
+  if (k >= sz || j >= sy) return;
+  for (int i = blockIdx.z; i < sx; i += gridDim.z) {
+    const int64_t idx = ((int64_t)i * sy + j) * sz + k;
+    const int64_t ox = (int64_t)sy * sz;
+    float4 r;
+    r.x = sdf_map(sdf[idx], a, b);
+    r.y = (i >= 1 && i <= sx - 2) ? (sdf_map(sdf[idx + ox], a, b) - sdf_map(sdf[idx - ox], a, b)) * inv_2vs : 0.f;
+    r.z = (j >= 1 && j <= sy - 2) ? (sdf_map(sdf[idx + sz], a, b) - sdf_map(sdf[idx - sz], a, b)) * inv_2vs : 0.f;
+    r.w = (k >= 1 && k <= sz - 2) ? (sdf_map(sdf[idx + 1], a, b) - sdf_map(sdf[idx - 1], a, b)) * inv_2vs : 0.f;
+    srec[idx] = r;
+  }
+}
+
+// ---- k0 [12, V] (channels first, the reference's parameter layout) <-> [V][3] float4 records ----------------
+__global__ void k0_pack_kernel(const float* __restrict__ k0, int64_t n, float4* __restrict__ rec) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      rec[i * 3 + q] = make_float4(k0[(4 * q) * n + i], k0[(4 * q + 1) * n + i], k0[(4 * q + 2) * n + i],
+                                   k0[(4 * q + 3) * n + i]);
+  }
+}
+__global__ void k0_unpack_kernel(const float4* __restrict__ rec, int64_t n, float* __restrict__ k0) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      const float4 v = rec[i * 3 + q];
+      k0[(4 * q) * n + i] = v.x;
+      k0[(4 * q + 1) * n + i] = v.y;
+      k0[(4 * q + 2) * n + i] = v.z;
+      k0[(4 * q + 3) * n + i] = v.w;
+    }
+  }
+}
+
+// position of step i of a ray (sample_pts_on_rays arithmetic; `jit` is the per-ray training jitter of
+// sample_ray_ori, voxurf_coarse.py:712-713, in steps)
+__device__ __forceinline__ bool vox_point(const pp_dvgo_scene& sc, const Ray& ray, int i, float jit, float (&p)[3]) {
+  const float dist = sc.stepdist * (static_cast<float>(i) + jit);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) p[c] = fma_rn(ray.dir[c], dist, ray.start[c]);
+  const bool out = (sc.xyz_min[0] > p[0]) | (sc.xyz_min[1] > p[1]) | (sc.xyz_min[2] > p[2]) |
+                   (sc.xyz_max[0] < p[0]) | (sc.xyz_max[1] < p[1]) | (sc.xyz_max[2] < p[2]);
+  return !out;
+}
+
+__device__ __forceinline__ float neus_alpha(const NeusTerms& t) { return fminf(fmaxf(t.num / t.den, 0.f), 1.f); }
+
+__device__ __forceinline__ uint32_t bf2(float lo, float hi) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+// ---- forward march + feature rows ---------------------------------------------------------------------------
+// dynamic shared memory per warp: s_w[cap] (weight of every step, -1 where nothing was composited) and
+// s_rec[cap] (interpolated SDF record of every step)
+__global__ void __launch_bounds__(256, 2)
+voxurf_march_kernel(pp_dvgo_scene sc, pp_voxurf_cfg cfg, const float4* __restrict__ srec,
+                    const float4* __restrict__ k0rec, const float* __restrict__ rays_o,
+                    const float* __restrict__ rays_d, const float* __restrict__ viewdirs,
+                    const float* __restrict__ jitter, int64_t n_rays, int32_t cap_m,
+                    __nv_bfloat16* __restrict__ feat, float* __restrict__ w_out, int32_t* __restrict__ rid_out,
+                    float4* __restrict__ rec_out, int32_t* __restrict__ ray_off, int32_t* __restrict__ ray_cnt,
+                    int32_t* __restrict__ ray_end, float* __restrict__ cum_w, float* __restrict__ alphainv_last,
+                    int32_t* __restrict__ counter, unsigned int* __restrict__ queue, int cap) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4* s_rec = reinterpret_cast<float4*>(smem_raw) + (size_t)warp * cap;
+  float* s_w = reinterpret_cast<float*>(smem_raw + (size_t)(blockDim.x >> 5) * cap * sizeof(float4)) + (size_t)warp * cap;
+
+  for (;;) {
+    unsigned int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(queue, 1u);
+    const int64_t r = __shfl_sync(kFull, ticket, 0);
+    if (r >= n_rays) break;
+    const Ray ray = setup_ray(sc, rays_o, rays_d, r);
+    const int n_steps = min(ray.n_steps, cap);
+    const float jit = jitter ? jitter[r] : 0.f;
+    float v[3];
+    load3(viewdirs, r, v);
+
+    // ---------------- phase 1: SDF gather, NeuS alpha, compositing ----------------
+    float T_in = 1.f, cumw = 0.f;
+    int n_live = 0, end = n_steps;
+    for (int base = 0; base < n_steps; base += kWarp) {
+      const int i = base + lane;
+      float p[3];
+      const bool inbox = (i < n_steps) && vox_point(sc, ray, i, jit, p);
+      float alpha = 0.f;
+      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (inbox) {
+        const Cell c = make_cell(sc, p[0], p[1], p[2]);
+        float4 q[8];
+        gather8(srec, c, q);
+        val = interp8(c, q);
+        const float g[3] = {val.y, val.z, val.w};
+        alpha = neus_alpha(neus_terms(val.x, g, v, sc.stepdist, cfg.inv_s));
+      }
+      float P, Pex;
+      lane_product_scan(1.f - alpha, lane, P, Pex);
+      const float T_before = T_in * Pex, T_after = T_in * P;
+      const unsigned term = __ballot_sync(kFull, inbox && (T_after < 1e-3f));
+      int last_lane = 31;
+      bool counted = inbox;
+      if (term) {
+        last_lane = __ffs(term) - 1;
+        counted = inbox && (lane <= last_lane);
+      }
+      const float w = counted ? T_before * alpha : -1.f;
+      if (i < n_steps) {
+        s_w[i] = w;
+        s_rec[i] = val;
+      }
+      if (counted) {
+        cumw += w;
+        n_live += 1;
+      }
+      T_in = __shfl_sync(kFull, T_after, last_lane);
+      if (term) {
+        end = base + last_lane + 1;
+        break;
+      }
+    }
+    n_live = __reduce_add_sync(kFull, n_live);
+    cumw = warp_sum(cumw);
+    int off = 0;
+    if (lane == 0) {
+      off = atomicAdd(counter, n_live);
+      const bool fits = off + n_live <= cap_m;
+      if (!fits) atomicMax(counter + 1, 1);   // overflow flag: the caller's sample capacity was too small
+      ray_off[r] = off;
+      ray_cnt[r] = fits ? n_live : 0;
+      ray_end[r] = end;
+      cum_w[r] = fits ? cumw : 0.f;
+      alphainv_last[r] = T_in;
+      if (!fits) off = -1;
+    }
+    off = __shfl_sync(kFull, off, 0);
+    __syncwarp();
+    if (off < 0 || n_live == 0) continue;
+
+    // ---------------- phase 2: feature rows of the composited samples ----------------
+    // per-ray view columns: viewdirs, sin / cos of viewdirs * 2^0 (view_pe <= 1), BARF weighted
+    float vf[9];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      vf[c] = v[c];
+      vf[3 + c] = cfg.view_pe > 0 ? __sinf(v[c]) * cfg.pe_w_view[0] : 0.f;
+      vf[6 + c] = cfg.view_pe > 0 ? __cosf(v[c]) * cfg.pe_w_view[0] : 0.f;
+    }
+    const int L = cfg.pos_pe;
+    int run = 0;
+    for (int base = 0; base < end; base += kWarp) {
+      const int i = base + lane;
+      const float w = (i < end) ? s_w[i] : -1.f;
+      const bool live = w >= 0.f;
+      const unsigned m = __ballot_sync(kFull, live);
+      const int slot = off + run + __popc(m & ((1u << lane) - 1u));
+      run += __popc(m);
+      if (!live) continue;
+      float p[3];
+      vox_point(sc, ray, i, jit, p);
+      const Cell c = make_cell(sc, p[0], p[1], p[2]);
+      // 12 feature channels: 3 records per corner
+      float4 f0 = make_float4(0.f, 0.f, 0.f, 0.f), f1 = f0, f2 = f0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4* src = k0rec + (int64_t)corner_off(c, q) * 3;
+        const float4 a0 = __ldg(src), a1 = __ldg(src + 1), a2 = __ldg(src + 2);
+        const float wq = corner_w(c, q);
+        f0.x = fma_rn(a0.x, wq, f0.x); f0.y = fma_rn(a0.y, wq, f0.y); f0.z = fma_rn(a0.z, wq, f0.z); f0.w = fma_rn(a0.w, wq, f0.w);
+        f1.x = fma_rn(a1.x, wq, f1.x); f1.y = fma_rn(a1.y, wq, f1.y); f1.z = fma_rn(a1.z, wq, f1.z); f1.w = fma_rn(a1.w, wq, f1.w);
+        f2.x = fma_rn(a2.x, wq, f2.x); f2.y = fma_rn(a2.y, wq, f2.y); f2.z = fma_rn(a2.z, wq, f2.z); f2.w = fma_rn(a2.w, wq, f2.w);
+      }
+      const float4 rc = s_rec[i];
+      const float gn = sqrtf(rc.y * rc.y + rc.z * rc.z + rc.w * rc.w);
+      const float inv = 1.f / (gn + 1e-5f);
+      float row[kFeatCols];
+#pragma unroll
+      for (int q = 0; q < kFeatCols; ++q) row[q] = 0.f;
+      row[0] = f0.x; row[1] = f0.y; row[2] = f0.z; row[3] = f0.w;
+      row[4] = f1.x; row[5] = f1.y; row[6] = f1.z; row[7] = f1.w;
+      row[8] = f2.x; row[9] = f2.y; row[10] = f2.z; row[11] = f2.w;
+      row[kColNormal] = rc.y * inv;
+      row[kColNormal + 1] = rc.z * inv;
+      row[kColNormal + 2] = rc.w * inv;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        const float u = (p[a] - sc.xyz_min[a]) / (sc.xyz_max[a] - sc.xyz_min[a]);
+        row[kColXyz + a] = u;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          if (k < L) {
+            float sn, cs;
+            __sincosf(u * static_cast<float>(1 << k), &sn, &cs);
+            row[kColXyz + 3 + a * 5 + k] = sn * cfg.pe_w_pos[k];
+            row[kColXyz + 18 + a * 5 + k] = cs * cfg.pe_w_pos[k];
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 9; ++q) row[kColView + q] = vf[q];
+      uint4* dst = reinterpret_cast<uint4*>(feat + (int64_t)slot * kFeatCols);
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        dst[q] = make_uint4(bf2(row[8 * q], row[8 * q + 1]), bf2(row[8 * q + 2], row[8 * q + 3]),
+                            bf2(row[8 * q + 4], row[8 * q + 5]), bf2(row[8 * q + 6], row[8 * q + 7]));
+      w_out[slot] = w;
+      rid_out[slot] = static_cast<int32_t>(r);
+      rec_out[slot] = rc;
+    }
+    __syncwarp();
+  }
+}
+
+// ---- per-ray loss: rgb_marched = acc + (1 - cum_w) * bg, clamp(0,1), MSE (voxurf_coarse.py:1040-1042,
+//      lib/losses.py:26-29).  g_ray = d loss / d (acc), loss_out[0] += w_rgb * mse, loss_out[1] += mse ---------
+__global__ void voxurf_ray_loss_kernel(int64_t n_rays, const float* __restrict__ acc, const float* __restrict__ cum_w,
+                                       const float* __restrict__ target, float bg, float w_rgb,
+                                       float* __restrict__ g_ray, float* __restrict__ rgb_marched,
+                                       float* __restrict__ loss_out) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  float mse = 0.f;
+  if (r < n_rays) {
+    const float inv_n = 1.f / (3.f * static_cast<float>(n_rays));
+    const float rest = (1.f - cum_w[r]) * bg;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float raw = acc[3 * r + c] + rest;
+      const float y = fminf(fmaxf(raw, 0.f), 1.f);
+      const float diff = y - target[3 * r + c];
+      mse += diff * diff * inv_n;
+      g_ray[3 * r + c] = (raw >= 0.f && raw <= 1.f) ? w_rgb * 2.f * diff * inv_n : 0.f;
+      if (rgb_marched) rgb_marched[3 * r + c] = y;
+    }
+  }
+  mse = warp_sum(mse);
+  if ((threadIdx.x & 31) == 0 && loss_out && mse != 0.f) {
+    atomicAdd(loss_out, w_rgb * mse);
+    atomicAdd(loss_out + 1, mse);
+  }
+}
+
+// ---- backward march -----------------------------------------------------------------------------------------
+// dynamic shared memory per warp: s_alpha[cap], s_slot[cap] (compacted slot of every step, -1 if none),
+// s_tin[cap/32]
+__global__ void __launch_bounds__(256, 2)
+voxurf_backward_kernel(pp_dvgo_scene sc, pp_voxurf_cfg cfg, const float* __restrict__ rays_o,
+                       const float* __restrict__ rays_d, const float* __restrict__ viewdirs,
+                       const float* __restrict__ jitter, int64_t n_rays, const float4* __restrict__ rec,
+                       const float* __restrict__ gw, const float* __restrict__ dx16,
+                       const int32_t* __restrict__ ray_off, const int32_t* __restrict__ ray_cnt,
+                       const int32_t* __restrict__ ray_end, const float* __restrict__ g_ray,
+                       float4* __restrict__ g_srec, float4* __restrict__ g_k0rec, unsigned int* __restrict__ queue,
+                       int cap) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int per_warp = 2 * cap + cap / kWarp;
+  float* s_alpha = reinterpret_cast<float*>(smem_raw) + (size_t)warp * per_warp;
+  int* s_slot = reinterpret_cast<int*>(s_alpha + cap);
+  float* s_tin = s_alpha + 2 * cap;
+
+  for (;;) {
+    unsigned int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(queue, 1u);
+    const int64_t r = __shfl_sync(kFull, ticket, 0);
+    if (r >= n_rays) break;
+    const int cnt = ray_cnt[r];
+    if (cnt == 0) continue;
+    const int off = ray_off[r], end = ray_end[r];
+    const Ray ray = setup_ray(sc, rays_o, rays_d, r);
+    const float jit = jitter ? jitter[r] : 0.f;
+    float v[3], g[3];
+    load3(viewdirs, r, v);
+    load3(g_ray, r, g);
+    const float gbg = (g[0] + g[1] + g[2]) * sc.bg;   // through (1 - sum w) * bg
+
+    // forward re-walk: alpha of every step from the stored records, transmittance entering every chunk
+    float T_in = 1.f;
+    int run = 0;
+    for (int base = 0; base < end; base += kWarp) {
+      const int i = base + lane;
+      float p[3];
+      const bool live = (i < end) && vox_point(sc, ray, i, jit, p);
+      const unsigned m = __ballot_sync(kFull, live);
+      const int slot = live ? off + run + __popc(m & ((1u << lane) - 1u)) : -1;
+      run += __popc(m);
+      float alpha = 0.f;
+      if (live) {
+        const float4 rc = rec[slot];
+        const float gg[3] = {rc.y, rc.z, rc.w};
+        alpha = neus_alpha(neus_terms(rc.x, gg, v, sc.stepdist, cfg.inv_s));
+      }
+      if (i < end) {
+        s_alpha[i] = alpha;
+        s_slot[i] = slot;
+      }
+      float P, Pex;
+      lane_product_scan(1.f - alpha, lane, P, Pex);
+      if (lane == 0) s_tin[base / kWarp] = T_in;
+      T_in *= __shfl_sync(kFull, P, 31);
+    }
+    __syncwarp();
+
+    // reverse walk
+    float back = 0.f;   // alphainv_last does not enter the loss (the background uses 1 - sum w)
+    const int last_base = ((end - 1) / kWarp) * kWarp;
+    for (int base = last_base; base >= 0; base -= kWarp) {
+      const int i = base + lane;
+      const int slot = (i < end) ? s_slot[i] : -1;
+      const bool live = slot >= 0;
+      const float alpha = live ? s_alpha[i] : 0.f;
+      float P, Pex;
+      lane_product_scan(1.f - alpha, lane, P, Pex);
+      const float T = s_tin[base / kWarp] * Pex;
+      const float w = live ? T * alpha : 0.f;
+      const float gwv = live ? gw[slot] - gbg : 0.f;   // d loss / d w_i
+      const float contrib = gwv * w;
+      float S = contrib;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float dn = __shfl_down_sync(kFull, S, o);
+        if (lane + o < 32) S += dn;
+      }
+      const float back_i = back + (S - contrib);
+      back += __shfl_sync(kFull, S, 0);
+      if (!live) continue;
+      const float d_alpha = gwv * T - back_i / (1.f - alpha + 1e-10f);
+      const float4 rc = rec[slot];
+      const float gg[3] = {rc.y, rc.z, rc.w};
+      float g_sdf, g_tc;
+      neus_backward(neus_terms(rc.x, gg, v, sc.stepdist, cfg.inv_s), d_alpha, sc.stepdist, cfg.inv_s, g_sdf, g_tc);
+      // input-gradient columns of the MLP: 12 feature channels, 3 normal components
+      const float4* dxp = reinterpret_cast<const float4*>(dx16 + (int64_t)slot * kDxCols);
+      const float4 d0 = dxp[0], d1 = dxp[1], d2 = dxp[2], d3 = dxp[3];
+      // normal = g / (|g| + 1e-5): d g_b = dn_b / (r + e) - g_b (g . dn) / (r (r + e)^2)
+      const float rn = sqrtf(gg[0] * gg[0] + gg[1] * gg[1] + gg[2] * gg[2]);
+      const float inv = 1.f / (rn + 1e-5f);
+      const float dot = gg[0] * d3.x + gg[1] * d3.y + gg[2] * d3.z;
+      const float kk = rn > 0.f ? dot * inv * inv / rn : 0.f;
+      float4 ds;
+      ds.x = g_sdf;
+      ds.y = g_tc * v[0] + d3.x * inv - gg[0] * kk;
+      ds.z = g_tc * v[1] + d3.y * inv - gg[1] * kk;
+      ds.w = g_tc * v[2] + d3.z * inv - gg[2] * kk;
+      float p[3];
+      vox_point(sc, ray, i, jit, p);
+      const Cell c = make_cell(sc, p[0], p[1], p[2]);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float wq = corner_w(c, q);
+        if (wq == 0.f) continue;
+        const int64_t co = corner_off(c, q);
+        red_add_v4(g_srec + co, wq * ds.x, wq * ds.y, wq * ds.z, wq * ds.w);
+        float4* kdst = g_k0rec + co * 3;
+        red_add_v4(kdst, wq * d0.x, wq * d0.y, wq * d0.z, wq * d0.w);
+        red_add_v4(kdst + 1, wq * d1.x, wq * d1.y, wq * d1.z, wq * d1.w);
+        red_add_v4(kdst + 2, wq * d2.x, wq * d2.y, wq * d2.z, wq * d2.w);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---- dense tail: fold the gradient-grid gradient onto the SDF, mapping chain rule, masked Adam ----------------
+__global__ void __launch_bounds__(256)
+sdf_fold_adam_kernel(float* __restrict__ sdf, const float4* __restrict__ g_srec, float* __restrict__ m1,
+                     float* __restrict__ m2, int sx, int sy, int sz, float a, float b, float inv_2vs,
+                     float step_size, float b1, float b2, float eps, float* __restrict__ grad_sdf_out,
+                     float* __restrict__ g_ab) {
+  const int k = blockIdx.x * 32 + threadIdx.x;
+  const int j = blockIdx.y * 8 + threadIdx.y;
+  float da = 0.f, db = 0.f;
+  if (k < sz && j < sy) {
+    const int64_t ox = (int64_t)sy * sz;
+    for (int i = blockIdx.z; i < sx; i += gridDim.z) {
+      const int64_t idx = ((int64_t)i * sy + j) * sz + k;
+      float gs = g_srec[idx].x;
+      // gradient-grid voxel n (interior along the axis) reads s'[n+1] - s'[n-1]: s'[idx] is the "+1" of n = idx-1
+      // and the "-1" of n = idx+1
+      if (i - 1 >= 1 && i - 1 <= sx - 2) gs += g_srec[idx - ox].y * inv_2vs;
+      if (i + 1 >= 1 && i + 1 <= sx - 2) gs -= g_srec[idx + ox].y * inv_2vs;
+      if (j - 1 >= 1 && j - 1 <= sy - 2) gs += g_srec[idx - sz].z * inv_2vs;
+      if (j + 1 >= 1 && j + 1 <= sy - 2) gs -= g_srec[idx + sz].z * inv_2vs;
+      if (k - 1 >= 1 && k - 1 <= sz - 2) gs += g_srec[idx - 1].w * inv_2vs;
+      if (k + 1 >= 1 && k + 1 <= sz - 2) gs -= g_srec[idx + 1].w * inv_2vs;
+      float s = sdf[idx];
+      float gr = gs;
+      if (a > 0.f) {
+        const float sg = 1.f / (1.f + __expf(-b * s));
+        const float dsg = sg * (1.f - sg);
+        da += gs * (sg - 0.5f);
+        db += gs * a * dsg * s;
+        gr = gs * a * b * dsg;
+      }
+      if (grad_sdf_out) grad_sdf_out[idx] = gr;
+      if (m1 && gr != 0.f) {   // masked_adam_upd (adam_upd_kernel.cu:35-39)
+        float mm = m1[idx], vv = m2[idx];
+        mm = fma_rn(b1, mm, mul_rn(1.f - b1, gr));
+        vv = fma_rn(b2, vv, mul_rn(mul_rn(1.f - b2, gr), gr));
+        s = s - mul_rn(step_size, mm) / (sqrtf(vv) + eps);
+        m1[idx] = mm;
+        m2[idx] = vv;
+        sdf[idx] = s;
+      }
+    }
+  }
+  if (g_ab && a > 0.f) {
+    da = warp_sum(da);
+    db = warp_sum(db);
+    if (threadIdx.x == 0 && (da != 0.f || db != 0.f)) {
+      atomicAdd(g_ab, da);
+      atomicAdd(g_ab + 1, db);
+    }
+  }
+}
+
+static int vox_step_capacity(const pp_dvgo_scene* sc) {
+  double d2 = 0;
+  for (int c = 0; c < 3; ++c) {
+    const double e = (double)sc->xyz_max[c] - (double)sc->xyz_min[c];
+    d2 += e * e;
+  }
+  const int n = (int)ceil(sqrt(d2) / (double)sc->stepdist) + 3;
+  return (n + 31) / 32 * 32;
+}
+
+static int check_vox_scene(const pp_dvgo_scene* sc, const pp_voxurf_cfg* cfg, const char* who) {
+  PP_REQUIRE(sc && cfg, PP_ERR_INVALID_ARG, "%s: scene / cfg is null", who);
+  PP_REQUIRE(sc->sx > 2 && sc->sy > 2 && sc->sz > 2, PP_ERR_INVALID_ARG, "%s: grid too small", who);
+  PP_REQUIRE((int64_t)sc->sx * sc->sy * sc->sz * 3 < (1LL << 31), PP_ERR_TOO_LARGE, "%s: grid too large", who);
+  PP_REQUIRE(sc->stepdist > 0.f, PP_ERR_INVALID_ARG, "%s: stepdist must be positive", who);
+  PP_REQUIRE(cfg->pos_pe >= 0 && cfg->pos_pe <= 5 && cfg->view_pe >= 0 && cfg->view_pe <= 1, PP_ERR_UNSUPPORTED,
+             "%s: the fused path supports posbase_pe <= 5 and viewbase_pe <= 1 (64 feature columns)", who);
+  PP_REQUIRE(cfg->voxel_size > 0.f, PP_ERR_INVALID_ARG, "%s: voxel_size must be positive", who);
+  return PP_OK;
+}
+
+static unsigned int* next_queue(cudaStream_t s, int* rc) {
+  static std::atomic<unsigned> next_slot{0};
+  static unsigned int* queue_base = nullptr;
+  *rc = PP_OK;
+  if (!queue_base && cudaGetSymbolAddress((void**)&queue_base, g_vox_queue) != cudaSuccess) {
+    set_error("cudaGetSymbolAddress failed");
+    *rc = PP_ERR_CUDA;
+    return nullptr;
+  }
+  unsigned int* q = queue_base + (next_slot.fetch_add(1) % kQueueSlots);
+  if (cudaMemsetAsync(q, 0, sizeof(unsigned int), s) != cudaSuccess) {
+    set_error("cudaMemsetAsync failed");
+    *rc = PP_ERR_CUDA;
+    return nullptr;
+  }
+  return q;
+}
+
+}  // namespace pp
+
+using namespace pp;
+
+extern "C" int pp_voxurf_build_records(const pp_dvgo_scene* scene, const pp_voxurf_cfg* cfg, const float* sdf,
+                                       void* sdf_records, pp_stream_t stream) {
+  const int rc = check_vox_scene(scene, cfg, "voxurf_build_records");
+  if (rc != PP_OK) return rc;
+  PP_REQUIRE(sdf && sdf_records, PP_ERR_INVALID_ARG, "voxurf_build_records: null pointer");
+  const dim3 block(32, 8, 1);
+  const dim3 grid((scene->sz + 31) / 32, (scene->sy + 7) / 8, (unsigned)min64(scene->sx, 65535));
+  sdf_records_kernel<<<grid, block, 0, as_stream(stream)>>>(sdf, scene->sx, scene->sy, scene->sz, cfg->sdf_scale_a,
+                                                           cfg->sdf_scale_b, 0.5f / cfg->voxel_size,
+                                                           (float4*)sdf_records);
+  PP_CHECK_LAUNCH("voxurf_build_records");
+  return PP_OK;
+}
+
+extern "C" int pp_voxurf_k0_pack(const float* k0, int64_t n_voxels, void* k0_records, pp_stream_t stream) {
+  PP_REQUIRE(n_voxels >= 0, PP_ERR_INVALID_ARG, "voxurf_k0_pack: n_voxels < 0");
+  if (n_voxels == 0) return PP_OK;
+  PP_REQUIRE(k0 && k0_records, PP_ERR_INVALID_ARG, "voxurf_k0_pack: null pointer");
+  const int blocks = (int)min64((n_voxels + 255) / 256, (int64_t)sm_count() * 16);
+  k0_pack_kernel<<<blocks, 256, 0, as_stream(stream)>>>(k0, n_voxels, (float4*)k0_records);
+  PP_CHECK_LAUNCH("voxurf_k0_pack");
+  return PP_OK;
+}
+
+extern "C" int pp_voxurf_k0_unpack(const void* k0_records, int64_t n_voxels, float* k0, pp_stream_t stream) {
+  PP_REQUIRE(n_voxels >= 0, PP_ERR_INVALID_ARG, "voxurf_k0_unpack: n_voxels < 0");
+  if (n_voxels == 0) return PP_OK;
+  PP_REQUIRE(k0 && k0_records, PP_ERR_INVALID_ARG, "voxurf_k0_unpack: null pointer");
+  const int blocks = (int)min64((n_voxels + 255) / 256, (int64_t)sm_count() * 16);
+  k0_unpack_kernel<<<blocks, 256, 0, as_stream(stream)>>>((const float4*)k0_records, n_voxels, k0);
+  PP_CHECK_LAUNCH("voxurf_k0_unpack");
+  return PP_OK;
+}
+
+extern "C" int pp_voxurf_march_features(const pp_dvgo_scene* scene, const pp_voxurf_cfg* cfg,
+                                        const void* sdf_records, const void* k0_records, const float* rays_o,
+                                        const float* rays_d, const float* viewdirs, const float* jitter,
+                                        int64_t n_rays, int32_t capacity, void* feat, float* sample_weight,
+                                        int32_t* sample_ray, void* sample_rec, int32_t* ray_off, int32_t* ray_cnt,
+                                        int32_t* ray_end, float* cum_w, float* alphainv_last, int32_t* counter,
+                                        pp_stream_t stream) {
+  const int rc = check_vox_scene(scene, cfg, "voxurf_march_features");
+  if (rc != PP_OK) return rc;
+  PP_REQUIRE(n_rays >= 0 && capacity >= 0, PP_ERR_INVALID_ARG, "voxurf_march_features: negative extent");
+  if (n_rays == 0) return PP_OK;
+  PP_REQUIRE(sdf_records && k0_records && rays_o && rays_d && viewdirs && feat && sample_weight && sample_ray &&
+                 sample_rec && ray_off && ray_cnt && ray_end && cum_w && alphainv_last && counter,
+             PP_ERR_INVALID_ARG, "voxurf_march_features: null pointer");
+  cudaStream_t s = as_stream(stream);
+  const int cap = vox_step_capacity(scene);
+  const int warps = 8;
+  const size_t smem = (size_t)warps * cap * (sizeof(float4) + sizeof(float));
+  PP_REQUIRE(smem <= 100 * 1024, PP_ERR_UNSUPPORTED,
+             "voxurf_march_features: %d steps per ray exceed the shared-memory staging capacity", cap);
+  PP_CHECK_CUDA(cudaFuncSetAttribute(voxurf_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int qrc;
+  unsigned int* queue = next_queue(s, &qrc);
+  if (qrc != PP_OK) return qrc;
+  PP_CHECK_CUDA(cudaMemsetAsync(counter, 0, 2 * sizeof(int32_t), s));
+  int per_sm = 0;
+  PP_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, voxurf_march_kernel, warps * 32, smem));
+  if (per_sm < 1) per_sm = 1;
+  const int64_t blocks = min64((n_rays + warps - 1) / warps, (int64_t)sm_count() * per_sm);
+  voxurf_march_kernel<<<(unsigned)blocks, warps * 32, smem, s>>>(
+      *scene, *cfg, (const float4*)sdf_records, (const float4*)k0_records, rays_o, rays_d, viewdirs, jitter, n_rays,
+      capacity, (__nv_bfloat16*)feat, sample_weight, sample_ray, (float4*)sample_rec, ray_off, ray_cnt, ray_end,
+      cum_w, alphainv_last, counter, queue, cap);
+  PP_CHECK_LAUNCH("voxurf_march_features");
+  return PP_OK;
+}
+
+extern "C" int pp_voxurf_ray_loss(int64_t n_rays, const float* rgb_acc, const float* cum_w, const float* target,
+                                  float bg, float w_rgb, float* g_ray, float* rgb_marched, float* loss_out,
+                                  pp_stream_t stream) {
+  PP_REQUIRE(n_rays >= 0, PP_ERR_INVALID_ARG, "voxurf_ray_loss: n_rays < 0");
+  if (n_rays == 0) return PP_OK;
+  PP_REQUIRE(rgb_acc && cum_w && target && g_ray, PP_ERR_INVALID_ARG, "voxurf_ray_loss: null pointer");
+  voxurf_ray_loss_kernel<<<ceil_div(n_rays, 256), 256, 0, as_stream(stream)>>>(n_rays, rgb_acc, cum_w, target, bg,
+                                                                                w_rgb, g_ray, rgb_marched, loss_out);
+  PP_CHECK_LAUNCH("voxurf_ray_loss");
+  return PP_OK;
+}
+
+extern "C" int pp_voxurf_backward(const pp_dvgo_scene* scene, const pp_voxurf_cfg* cfg, const float* rays_o,
+                                  const float* rays_d, const float* viewdirs, const float* jitter, int64_t n_rays,
+                                  const void* sample_rec, const float* grad_weight, const float* grad_feat16,
+                                  const int32_t* ray_off, const int32_t* ray_cnt, const int32_t* ray_end,
+                                  const float* g_ray, void* grad_sdf_records, void* grad_k0_records,
+                                  pp_stream_t stream) {
+  const int rc = check_vox_scene(scene, cfg, "voxurf_backward");
+  if (rc != PP_OK) return rc;
+  PP_REQUIRE(n_rays >= 0, PP_ERR_INVALID_ARG, "voxurf_backward: n_rays < 0");
+  if (n_rays == 0) return PP_OK;
+  PP_REQUIRE(rays_o && rays_d && viewdirs && sample_rec && grad_weight && grad_feat16 && ray_off && ray_cnt &&
+                 ray_end && g_ray && grad_sdf_records && grad_k0_records,
+             PP_ERR_INVALID_ARG, "voxurf_backward: null pointer");
+  cudaStream_t s = as_stream(stream);
+  const int cap = vox_step_capacity(scene);
+  const int warps = 8;
+  const size_t smem = (size_t)warps * (2 * cap + cap / kWarp) * sizeof(float);
+  PP_CHECK_CUDA(cudaFuncSetAttribute(voxurf_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int qrc;
+  unsigned int* queue = next_queue(s, &qrc);
+  if (qrc != PP_OK) return qrc;
+  int per_sm = 0;
+  PP_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, voxurf_backward_kernel, warps * 32, smem));
+  if (per_sm < 1) per_sm = 1;
+  const int64_t blocks = min64((n_rays + warps - 1) / warps, (int64_t)sm_count() * per_sm);
+  voxurf_backward_kernel<<<(unsigned)blocks, warps * 32, smem, s>>>(
+      *scene, *cfg, rays_o, rays_d, viewdirs, jitter, n_rays, (const float4*)sample_rec, grad_weight, grad_feat16,
+      ray_off, ray_cnt, ray_end, g_ray, (float4*)grad_sdf_records, (float4*)grad_k0_records, queue, cap);
+  PP_CHECK_LAUNCH("voxurf_backward");
+  return PP_OK;
+}
+
+extern "C" int pp_voxurf_sdf_adam(const pp_dvgo_scene* scene, const pp_voxurf_cfg* cfg, float* sdf,
+                                  const void* grad_sdf_records, float* exp_avg, float* exp_avg_sq, int32_t step,
+                                  float beta1, float beta2, float lr, float eps, float* grad_sdf_out,
+                                  float* grad_ab, pp_stream_t stream) {
+  const int rc = check_vox_scene(scene, cfg, "voxurf_sdf_adam");
+  if (rc != PP_OK) return rc;
+  PP_REQUIRE(sdf && grad_sdf_records, PP_ERR_INVALID_ARG, "voxurf_sdf_adam: null pointer");
+  PP_REQUIRE((exp_avg == nullptr) == (exp_avg_sq == nullptr), PP_ERR_INVALID_ARG,
+             "voxurf_sdf_adam: pass both Adam moments (update) or neither (gradient only)");
+  const float step_size =
+      exp_avg ? lr * sqrtf(1.f - powf(beta2, (float)step)) / (1.f - powf(beta1, (float)step)) : 0.f;
+  const dim3 block(32, 8, 1);
+  const dim3 grid((scene->sz + 31) / 32, (scene->sy + 7) / 8, (unsigned)min64(scene->sx, 65535));
+  sdf_fold_adam_kernel<<<grid, block, 0, as_stream(stream)>>>(
+      sdf, (const float4*)grad_sdf_records, exp_avg, exp_avg_sq, scene->sx, scene->sy, scene->sz, cfg->sdf_scale_a,
+      cfg->sdf_scale_b, 0.5f / cfg->voxel_size, step_size, beta1, beta2, eps, grad_sdf_out, grad_ab);
+  PP_CHECK_LAUNCH("voxurf_sdf_adam");
+  return PP_OK;
+}

@@ -1,0 +1,316 @@
+"""Host side of the fused Voxurf fine-stage train / render path (C ABI: include/poseprobe_b200_fused.h).
+
+Mirrors the surface stage of the reference (``Voxurf.forward``, lib/voxurf_coarse.py:922-1091, non-deform
+branch): ``sdf.grid`` [1,1,X,Y,Z] with the per-step mapping function and the finite-difference gradient grid,
+``k0.grid`` [1,12,X,Y,Z], ``rgbnet`` (57 -> 128 x (depth-1) -> 3), NeuS alpha, alpha compositing, photometric MSE.
+Parameter layouts interchange with the reference's checkpoints (``import_state`` / ``export_state`` use the keys
+``sdf.grid``, ``k0.grid``, ``rgbnet.*`` of lib/recon_scene.py:779-791).
+
+``FusedVoxurf.train_step`` is 10 launches: march+features, MLP forward (tcgen05, compositing epilogue), per-ray
+loss, MLP forward-recompute+backward (tcgen05), reverse march + scatter, SDF fold + Adam, SDF record rebuild,
+feature-record Adam, rgbnet Adam, gradient clears.  The deformation network (use_implict_deform) is not part of
+this path.
+"""
+import ctypes
+import math
+
+import torch
+
+from ._lib import check, lib, ptr, stream
+from .dvgo import _need_cuda, make_scene
+
+FEAT_COLS = 64
+DX_COLS = 16
+
+
+class _Cfg(ctypes.Structure):
+    _fields_ = [("inv_s", ctypes.c_float), ("sdf_scale_a", ctypes.c_float), ("sdf_scale_b", ctypes.c_float),
+                ("voxel_size", ctypes.c_float), ("pos_pe", ctypes.c_int32), ("view_pe", ctypes.c_int32),
+                ("pe_w_pos", ctypes.c_float * 8), ("pe_w_view", ctypes.c_float * 8)]
+
+
+def barf_weights(progress, barf_c2f, L):
+    """positional_encoding_barf's per-frequency weights (lib/voxurf_coarse.py:721-732)."""
+    if barf_c2f is None or L == 0:
+        return [1.0] * L
+    start, end = barf_c2f
+    alpha = (progress - start) / (end - start) * L
+    return [(1 - math.cos(min(max(alpha - k, 0.0), 1.0) * math.pi)) / 2 for k in range(L)]
+
+
+def softplus10(x):
+    return math.log1p(math.exp(10.0 * x)) / 10.0 if x < 2.0 else x + math.log1p(math.exp(-10.0 * x)) / 10.0
+
+
+def feature_permutation(pos_pe, view_pe, k0_dim=12):
+    """Column of the reference's rgb_feat row (voxurf_coarse.py:1005-1030: k0 | rays_xyz | sin | cos | viewdirs |
+    sin | cos | normal) that feeds each of the 64 kernel columns (-1 = zero padding)."""
+    if k0_dim != 12 or pos_pe > 5 or view_pe > 1:
+        raise RuntimeError("FusedVoxurf: the fused path supports rgbnet_dim=12, posbase_pe<=5, viewbase_pe<=1")
+    L, Lv = pos_pe, view_pe
+    ref_xyz = k0_dim
+    ref_sin = ref_xyz + 3
+    ref_cos = ref_sin + 3 * L
+    ref_view = ref_cos + 3 * L
+    ref_vsin = ref_view + 3
+    ref_vcos = ref_vsin + 3 * Lv
+    ref_normal = ref_vcos + 3 * Lv
+    perm = [-1] * FEAT_COLS
+    for c in range(12):
+        perm[c] = c
+    for c in range(3):
+        perm[12 + c] = ref_normal + c
+        perm[16 + c] = ref_xyz + c
+        perm[49 + c] = ref_view + c
+        if Lv:
+            perm[52 + c] = ref_vsin + c * Lv
+            perm[55 + c] = ref_vcos + c * Lv
+        for k in range(L):
+            perm[19 + c * 5 + k] = ref_sin + c * L + k
+            perm[34 + c * 5 + k] = ref_cos + c * L + k
+    return perm, ref_normal + 3
+
+
+class FusedVoxurf:
+    """Training / rendering engine of the SDF fine stage; state stays resident in HBM in the kernels' layouts."""
+
+    def __init__(self, sdf, k0, rgbnet_weights, rgbnet_biases, xyz_min, xyz_max, stepsize=0.5, near=0.2, far=1e9,
+                 bg=0.0, s_val=0.05, sdf_alpha=None, sdf_beta=None, posbase_pe=5, viewbase_pe=1, barf_c2f=None,
+                 lr_sdf=0.1, lr_k0=0.1, lr_rgbnet=1e-3, betas=(0.9, 0.99), eps=1e-8, w_rgb=1.0,
+                 samples_per_ray_cap=None):
+        _need_cuda(sdf, "sdf")
+        _need_cuda(k0, "k0")
+        self.device = sdf.device
+        self.world = tuple(int(v) for v in sdf.shape[2:])
+        if k0.shape[1] != 12 or tuple(k0.shape[2:]) != self.world:
+            raise RuntimeError("FusedVoxurf expects sdf [1,1,X,Y,Z] and k0 [1,12,X,Y,Z]")
+        self.n_voxels = sdf.numel()
+        self.xyz_min = [float(v) for v in xyz_min]
+        self.xyz_max = [float(v) for v in xyz_max]
+        vol = 1.0
+        for a, b in zip(self.xyz_min, self.xyz_max):
+            vol *= (b - a)
+        self.voxel_size = (vol / self.n_voxels) ** (1.0 / 3.0)      # voxurf_coarse.py _set_grid_resolution
+        self.stepsize = stepsize
+        self.scene = make_scene(self.world, self.xyz_min, self.xyz_max, near, far, stepsize * self.voxel_size, 0.0,
+                                stepsize, bg)
+        self.posbase_pe, self.viewbase_pe, self.barf_c2f = posbase_pe, viewbase_pe, barf_c2f
+        self.sdf_alpha, self.sdf_beta = sdf_alpha, sdf_beta
+        self.s_val = s_val
+        self.progress = 1.0
+        self.cfg = _Cfg()
+        self._refresh_cfg()
+        self.perm, self.d0_ref = feature_permutation(posbase_pe, viewbase_pe)
+        self.d0 = FEAT_COLS          # the kernels see the permuted, zero-padded first layer [128, 64]
+        self.depth = len(rgbnet_weights)
+        if rgbnet_weights[0].shape[1] != self.d0_ref or rgbnet_weights[-1].shape[0] != 3:
+            raise RuntimeError("FusedVoxurf: rgbnet expects %d inputs and 3 outputs" % self.d0_ref)
+        dev = self.device
+        # parameters in the kernels' layouts
+        self.sdf = sdf.detach().clone().reshape(-1).contiguous()
+        self.k0rec = torch.empty((self.n_voxels, 12), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.pp_voxurf_k0_pack(ptr(k0.contiguous()), self.n_voxels, ptr(self.k0rec), stream()), "k0_pack")
+        idx = torch.tensor([max(p, 0) for p in self.perm], device=dev)
+        keep = torch.tensor([1.0 if p >= 0 else 0.0 for p in self.perm], device=dev)
+        self._perm_idx, self._perm_keep = idx, keep
+        w0 = rgbnet_weights[0].detach().to(dev).float()
+        self.weights = [(w0[:, idx] * keep).contiguous()] + [w.detach().to(dev).float().contiguous()
+                                                              for w in rgbnet_weights[1:]]
+        self.biases = [b.detach().to(dev).float().contiguous() for b in rgbnet_biases]
+        self.srec = torch.empty((self.n_voxels, 4), dtype=torch.float32, device=dev)
+        # gradients and optimiser state
+        self.g_srec = torch.zeros_like(self.srec)
+        self.g_k0rec = torch.zeros_like(self.k0rec)
+        self.m_sdf, self.v_sdf = torch.zeros_like(self.sdf), torch.zeros_like(self.sdf)
+        self.m_k0, self.v_k0 = torch.zeros_like(self.k0rec), torch.zeros_like(self.k0rec)
+        self.g_w = [torch.zeros_like(w) for w in self.weights]
+        self.g_b = [torch.zeros_like(b) for b in self.biases]
+        self.m_w = [torch.zeros_like(w) for w in self.weights]
+        self.v_w = [torch.zeros_like(w) for w in self.weights]
+        self.m_b = [torch.zeros_like(b) for b in self.biases]
+        self.v_b = [torch.zeros_like(b) for b in self.biases]
+        self.g_ab = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.hp = (betas[0], betas[1], lr_sdf, lr_k0, lr_rgbnet, eps)
+        self.w_rgb = w_rgb
+        self.step = 0
+        self.loss_buf = torch.zeros(2, dtype=torch.float32, device=dev)
+        self._cap_per_ray = samples_per_ray_cap
+        self._bufs = None
+        self._arr = lambda ts: (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+        self.rebuild_records()
+
+    # ---- configuration that changes over training --------------------------------------------------------
+    def _refresh_cfg(self):
+        c = self.cfg
+        c.inv_s = 1.0 / float(self.s_val)
+        c.sdf_scale_a = softplus10(self.sdf_alpha) if self.sdf_alpha is not None else 0.0
+        c.sdf_scale_b = softplus10(self.sdf_beta) if self.sdf_beta is not None else 0.0
+        c.voxel_size = self.voxel_size
+        c.pos_pe, c.view_pe = self.posbase_pe, self.viewbase_pe
+        for k, w in enumerate(barf_weights(self.progress, self.barf_c2f, self.posbase_pe)):
+            c.pe_w_pos[k] = w
+        for k, w in enumerate(barf_weights(self.progress, self.barf_c2f, self.viewbase_pe)):
+            c.pe_w_view[k] = w
+
+    def set_schedule(self, s_val=None, progress=None):
+        """s_val of neus_alpha_from_sdf_scatter (:487) and the BARF progress (:928) for the next steps."""
+        if s_val is not None:
+            self.s_val = s_val
+        if progress is not None:
+            self.progress = progress
+        self._refresh_cfg()
+
+    def rebuild_records(self):
+        with torch.cuda.device(self.device):
+            check(lib.pp_voxurf_build_records(ctypes.byref(self.scene), ctypes.byref(self.cfg), ptr(self.sdf),
+                                              ptr(self.srec), stream()), "voxurf_build_records")
+
+    # ---- buffers ----------------------------------------------------------------------------------------------
+    def _buffers(self, n_rays):
+        per_ray = self._cap_per_ray
+        if per_ray is None:
+            diag = math.sqrt(sum((b - a) ** 2 for a, b in zip(self.xyz_min, self.xyz_max)))
+            per_ray = int(diag / (self.stepsize * self.voxel_size)) + 4        # every step of every ray
+        cap = int(n_rays) * per_ray
+        b = self._bufs
+        if b is None or b["cap"] < cap or b["n_rays"] < n_rays:
+            dev = self.device
+            b = {"cap": cap, "n_rays": n_rays,
+                 "feat": torch.empty((cap, FEAT_COLS), dtype=torch.bfloat16, device=dev),
+                 "w": torch.empty(cap, dtype=torch.float32, device=dev),
+                 "rid": torch.empty(cap, dtype=torch.int32, device=dev),
+                 "rec": torch.empty((cap, 4), dtype=torch.float32, device=dev),
+                 "gw": torch.empty(cap, dtype=torch.float32, device=dev),
+                 "dx": torch.empty((cap, DX_COLS), dtype=torch.float32, device=dev),
+                 "ray_off": torch.empty(n_rays, dtype=torch.int32, device=dev),
+                 "ray_cnt": torch.empty(n_rays, dtype=torch.int32, device=dev),
+                 "ray_end": torch.empty(n_rays, dtype=torch.int32, device=dev),
+                 "cum_w": torch.empty(n_rays, dtype=torch.float32, device=dev),
+                 "last": torch.empty(n_rays, dtype=torch.float32, device=dev),
+                 "acc": torch.empty((n_rays, 3), dtype=torch.float32, device=dev),
+                 "g_ray": torch.empty((n_rays, 3), dtype=torch.float32, device=dev),
+                 "rgb": torch.empty((n_rays, 3), dtype=torch.float32, device=dev),
+                 "counter": torch.zeros(2, dtype=torch.int32, device=dev)}
+            self._bufs = b
+        return b
+
+    # ---- forward pieces -----------------------------------------------------------------------------------------
+    def _march(self, b, rays_o, rays_d, viewdirs, jitter):
+        n = rays_o.shape[0]
+        check(lib.pp_voxurf_march_features(
+            ctypes.byref(self.scene), ctypes.byref(self.cfg), ptr(self.srec), ptr(self.k0rec), ptr(rays_o),
+            ptr(rays_d), ptr(viewdirs), ptr(jitter), n, b["cap"], ptr(b["feat"]), ptr(b["w"]), ptr(b["rid"]),
+            ptr(b["rec"]), ptr(b["ray_off"]), ptr(b["ray_cnt"]), ptr(b["ray_end"]), ptr(b["cum_w"]), ptr(b["last"]),
+            ptr(b["counter"]), stream()), "voxurf_march_features")
+
+    def _mlp_forward(self, b, n):
+        b["acc"][:n].zero_()
+        check(lib.pp_rgbnet_forward_packed(ptr(b["feat"]), b["cap"], self.d0, self.depth, 128, self._arr(self.weights),
+                                           self._arr(self.biases), 1, None, ptr(b["w"]), ptr(b["rid"]), ptr(b["acc"]),
+                                           ptr(b["counter"]), stream()), "rgbnet_forward")
+
+    def render(self, rays_o, rays_d, viewdirs):
+        """-> rgb_marched [N,3], alphainv_last [N], cum_weights [N]   (Voxurf.forward's render outputs)."""
+        for t, nme in ((rays_o, "rays_o"), (rays_d, "rays_d"), (viewdirs, "viewdirs")):
+            _need_cuda(t, nme)
+        n = rays_o.shape[0]
+        b = self._buffers(n)
+        with torch.cuda.device(self.device):
+            self._march(b, rays_o, rays_d, viewdirs, None)
+            self._mlp_forward(b, n)
+            check(lib.pp_voxurf_ray_loss(n, ptr(b["acc"]), ptr(b["cum_w"]), ptr(b["acc"]), self.scene.bg, 0.0,
+                                         ptr(b["g_ray"]), ptr(b["rgb"]), None, stream()), "voxurf_ray_loss")
+        return b["rgb"][:n].clone(), b["last"][:n].clone(), b["cum_w"][:n].clone()
+
+    def n_samples(self):
+        """Composited samples of the last march (host sync); raises if the sample capacity overflowed."""
+        c = self._bufs["counter"].tolist()
+        if c[1]:
+            raise RuntimeError("FusedVoxurf: sample capacity exceeded (raise samples_per_ray_cap)")
+        return c[0]
+
+    # ---- training -----------------------------------------------------------------------------------------------
+    def backward_only(self, rays_o, rays_d, viewdirs, target, jitter=None):
+        """march -> MLP -> loss -> MLP backward -> reverse march.  Accumulates into the gradient buffers and
+        loss_buf ([w_rgb * mse, mse]); no parameter changes."""
+        for t, nme in ((rays_o, "rays_o"), (rays_d, "rays_d"), (viewdirs, "viewdirs"), (target, "target")):
+            _need_cuda(t, nme)
+        n = rays_o.shape[0]
+        b = self._buffers(n)
+        with torch.cuda.device(self.device):
+            self._march(b, rays_o, rays_d, viewdirs, jitter)
+            self._mlp_forward(b, n)
+            check(lib.pp_voxurf_ray_loss(n, ptr(b["acc"]), ptr(b["cum_w"]), ptr(target), self.scene.bg, self.w_rgb,
+                                         ptr(b["g_ray"]), ptr(b["rgb"]), ptr(self.loss_buf), stream()),
+                  "voxurf_ray_loss")
+            check(lib.pp_rgbnet_backward_fused(ptr(b["feat"]), b["cap"], ptr(b["counter"]), self.d0, self.depth, 128,
+                                               self._arr(self.weights), self._arr(self.biases), ptr(b["w"]),
+                                               ptr(b["rid"]), ptr(b["g_ray"]), ptr(b["gw"]), ptr(b["dx"]),
+                                               self._arr(self.g_w), self._arr(self.g_b), stream()),
+                  "rgbnet_backward_fused")
+            check(lib.pp_voxurf_backward(ctypes.byref(self.scene), ctypes.byref(self.cfg), ptr(rays_o), ptr(rays_d),
+                                         ptr(viewdirs), ptr(jitter), n, ptr(b["rec"]), ptr(b["gw"]), ptr(b["dx"]),
+                                         ptr(b["ray_off"]), ptr(b["ray_cnt"]), ptr(b["ray_end"]), ptr(b["g_ray"]),
+                                         ptr(self.g_srec), ptr(self.g_k0rec), stream()), "voxurf_backward")
+        return b["rgb"][:n]
+
+    def grid_gradients(self):
+        """(d loss / d sdf [1,1,X,Y,Z], d loss / d k0 [1,12,X,Y,Z], [dW], [db]) of the accumulated gradients, in
+        the reference's layouts (first-layer columns un-permuted)."""
+        g_sdf = torch.empty_like(self.sdf)
+        with torch.cuda.device(self.device):
+            check(lib.pp_voxurf_sdf_adam(ctypes.byref(self.scene), ctypes.byref(self.cfg), ptr(self.sdf),
+                                         ptr(self.g_srec), None, None, 1, 0.9, 0.99, 0.0, 1e-8, ptr(g_sdf),
+                                         ptr(self.g_ab), stream()), "voxurf_sdf_adam")
+            g_k0 = torch.empty((1, 12) + self.world, dtype=torch.float32, device=self.device)
+            check(lib.pp_voxurf_k0_unpack(ptr(self.g_k0rec), self.n_voxels, ptr(g_k0), stream()), "k0_unpack")
+        gw0 = torch.zeros((128, self.d0_ref), dtype=torch.float32, device=self.device)
+        cols = [(c, p) for c, p in enumerate(self.perm) if p >= 0]
+        gw0[:, [p for _, p in cols]] = self.g_w[0][:, [c for c, _ in cols]]
+        return g_sdf.reshape((1, 1) + self.world), g_k0, [gw0] + [g.clone() for g in self.g_w[1:]], \
+            [g.clone() for g in self.g_b]
+
+    def optimizer_step(self):
+        b1, b2, lr_sdf, lr_k0, lr_net, eps = self.hp
+        self.step += 1
+        with torch.cuda.device(self.device):
+            s = stream()
+            check(lib.pp_voxurf_sdf_adam(ctypes.byref(self.scene), ctypes.byref(self.cfg), ptr(self.sdf),
+                                         ptr(self.g_srec), ptr(self.m_sdf), ptr(self.v_sdf), self.step, b1, b2,
+                                         lr_sdf, eps, None, ptr(self.g_ab), s), "voxurf_sdf_adam")
+            self.g_srec.zero_()
+            check(lib.pp_voxurf_build_records(ctypes.byref(self.scene), ctypes.byref(self.cfg), ptr(self.sdf),
+                                              ptr(self.srec), s), "voxurf_build_records")
+            # feature records: masked Adam over 3 V float4 records, gradient reset fused
+            check(lib.pp_voxel_adam(ptr(self.k0rec), ptr(self.g_k0rec), ptr(self.m_k0), ptr(self.v_k0),
+                                    3 * self.n_voxels, self.step, b1, b2, lr_k0, lr_k0, eps, 1, s), "voxel_adam")
+            for p, g, m, v in zip(self.weights + self.biases, self.g_w + self.g_b, self.m_w + self.m_b,
+                                  self.v_w + self.v_b):
+                check(lib.pp_adam_upd(0, 0, ptr(p), ptr(g), ptr(m), ptr(v), None, p.numel(), self.step, b1, b2,
+                                      lr_net, eps, s), "adam_upd")
+                g.zero_()
+
+    def train_step(self, rays_o, rays_d, viewdirs, target, jitter=None):
+        self.loss_buf.zero_()
+        self.backward_only(rays_o, rays_d, viewdirs, target, jitter)
+        self.optimizer_step()
+        return self.loss_buf
+
+    # ---- checkpoints ----------------------------------------------------------------------------------------------
+    def export_state(self):
+        """{'sdf.grid', 'k0.grid', 'rgbnet.<i>.weight/bias'} in the reference's layouts."""
+        k0 = torch.empty((1, 12) + self.world, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib.pp_voxurf_k0_unpack(ptr(self.k0rec), self.n_voxels, ptr(k0), stream()), "k0_unpack")
+        out = {"sdf.grid": self.sdf.reshape((1, 1) + self.world).clone(), "k0.grid": k0}
+        w0 = torch.zeros((128, self.d0_ref), dtype=torch.float32, device=self.device)
+        cols = [(c, p) for c, p in enumerate(self.perm) if p >= 0]
+        w0[:, [p for _, p in cols]] = self.weights[0][:, [c for c, _ in cols]]
+        ws = [w0] + [w.clone() for w in self.weights[1:]]
+        # nn.Sequential indices of the reference's rgbnet (voxurf_coarse.py:208-216): 0, 2.0, 3.0, ..., last
+        names = ["0"] + ["%d.0" % (i + 1) for i in range(1, self.depth - 1)] + [str(self.depth)]
+        for nme, w, bb in zip(names, ws, self.biases):
+            out["rgbnet.%s.weight" % nme] = w
+            out["rgbnet.%s.bias" % nme] = bb.clone()
+        return out

@@ -1,0 +1,229 @@
+"""Fused Voxurf fine-stage path (voxurf_fused.cu + the tcgen05 rgbnet kernels) against the CPU restatement of
+``Voxurf.forward`` (oracle/voxurf_cpu.py, lib/voxurf_coarse.py:922-1091 non-deform branch).
+
+Tolerances, stated once:
+* grid-side quantities that do not pass through the MLP (weights, cum_weights, alphainv_last, the SDF / normal /
+  k0 columns of the feature rows before bf16 rounding) are fp32: 2e-4 absolute on weights (transmittance is a
+  parallel scan here and a serial double-rounded loop in alpha2weight; rays whose transmittance lands within
+  rounding of 1e-3 may stop one sample apart, see test_fused_gpu.py);
+* feature rows are stored as bf16: 2^-8 relative;
+* anything downstream of the rgbnet (rgb_marched, loss, every gradient) carries the MLP's bf16 operands:
+  rgb 2e-2 absolute, gradients by direction (cosine > 0.99) and norm (10 %).
+"""
+import math
+
+import pytest
+import torch
+import torch.nn as nn
+
+pytestmark = pytest.mark.gpu
+
+MN, MX = [-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]
+
+
+def make_scene(G, n_rays, seed=0, depth=4, mapping=True):
+    from poseprobe_b200 import synthetic
+    torch.manual_seed(seed)
+    sdf = synthetic.make_sdf_grid(G, radius=0.5, noise=0.01)
+    k0 = 0.3 * torch.randn(1, 12, G, G, G)
+    net = nn.Sequential(nn.Linear(57, 128), nn.ReLU(inplace=True),
+                        *[nn.Sequential(nn.Linear(128, 128), nn.ReLU(inplace=True)) for _ in range(depth - 2)],
+                        nn.Linear(128, 3))
+    nn.init.constant_(net[-1].bias, 0)
+    with torch.no_grad():      # spread the colours out so that the render test is sensitive to the feature columns
+        net[0].weight.mul_(2.0)
+        net[-1].weight.mul_(4.0)
+    o, d, v = synthetic.make_rays(n_rays, seed=seed + 5)
+    target = torch.rand(n_rays, 3)
+    kw = dict(stepsize=0.5, s_val=0.05, bg=0.3, posbase_pe=5, viewbase_pe=1, barf_c2f=(0.1, 0.5))
+    if mapping:
+        kw.update(sdf_alpha=10.0, sdf_beta=0.35)   # softplus10(0.35) ~ 0.353: keeps s' ~ 0.88 s (a usable surface)
+    return sdf, k0, net, o, d, v, target, kw
+
+
+def make_engine(sdf, k0, net, kw, dev, **extra):
+    from poseprobe_b200 import ops, voxurf
+    ws, bs = ops.rgbnet_from_sequential(net)
+    return voxurf.FusedVoxurf(sdf.to(dev), k0.to(dev), [w.detach() for w in ws], [b.detach() for b in bs], MN, MX,
+                              **kw, **extra)
+
+
+def oracle_forward(sdf, k0, net, o, d, v, kw, voxel_size, progress, jitter=None):
+    from oracle import voxurf_cpu
+    return voxurf_cpu.forward(sdf, k0, net, o, d, v, MN, MX, kw["stepsize"], voxel_size, kw["s_val"], bg=kw["bg"],
+                              sdf_alpha=kw.get("sdf_alpha"), sdf_beta=kw.get("sdf_beta"), posbase_pe=kw["posbase_pe"],
+                              viewbase_pe=kw["viewbase_pe"], barf_c2f=kw["barf_c2f"], progress=progress, jitter=jitter)
+
+
+@pytest.mark.parametrize("mapping,use_jitter", [(True, False), (False, True)])
+def test_march_features_vs_oracle(cuda, mapping, use_jitter):
+    G, N = 48, 512
+    sdf, k0, net, o, d, v, target, kw = make_scene(G, N, seed=1, mapping=mapping)
+    eng = make_engine(sdf, k0, net, kw, cuda)
+    eng.set_schedule(progress=0.3)
+    jitter = torch.rand(N) if use_jitter else None
+    with torch.no_grad():
+        want = oracle_forward(sdf, k0, net, o, d, v, kw, eng.voxel_size, 0.3, jitter)
+    b = eng._buffers(N)
+    with torch.cuda.device(cuda):
+        eng._march(b, o.to(cuda), d.to(cuda), v.to(cuda), jitter.to(cuda) if use_jitter else None)
+    torch.cuda.synchronize()
+    m = eng.n_samples()
+    ray_cnt = b["ray_cnt"][:N].cpu().long()
+    ray_off = b["ray_off"][:N].cpu().long()
+    # oracle: composited samples per ray = samples with weight > 0 up to the early-termination index
+    w_ref, rid_ref = want["weights"], want["ray_id"]
+    per_ray_ref = torch.zeros(N, dtype=torch.long).index_add_(0, rid_ref, torch.ones_like(rid_ref))
+    cum_ref = want["cum_weights"][:, 0]
+    torch.testing.assert_close(b["cum_w"][:N].cpu(), cum_ref, rtol=0, atol=2e-4)
+    torch.testing.assert_close(b["last"][:N].cpu(), want["alphainv_cum"], rtol=0, atol=2e-4)
+    assert m == int(ray_cnt.sum()) and m <= int(per_ray_ref.sum())
+    # per-ray comparison of the compacted rows against the oracle's first `cnt` in-box samples of that ray
+    feat = b["feat"][:m].float().cpu()
+    w_got = b["w"][:m].cpu()
+    rid_got = b["rid"][:m].cpu().long()
+    starts_ref = torch.cumsum(per_ray_ref, 0) - per_ray_ref
+    from poseprobe_b200 import voxurf
+    perm, d0 = voxurf.feature_permutation(5, 1)
+    cols = [(c, p) for c, p in enumerate(perm) if p >= 0]
+    checked = 0
+    for r in range(0, N, 7):
+        c = int(ray_cnt[r])
+        if c == 0:
+            continue
+        sl = slice(int(ray_off[r]), int(ray_off[r]) + c)
+        rs = slice(int(starts_ref[r]), int(starts_ref[r]) + c)
+        assert bool((rid_got[sl] == r).all())
+        torch.testing.assert_close(w_got[sl], w_ref[rs], rtol=0, atol=2e-4)
+        ref_rows = want["rgb_feat"][rs]
+        got_rows = feat[sl]
+        for kc, rc in cols:
+            torch.testing.assert_close(got_rows[:, kc], ref_rows[:, rc], rtol=2 ** -7, atol=2e-3)
+        checked += c
+    assert checked > 1000
+
+
+def test_render_vs_oracle(cuda):
+    G, N = 48, 1024
+    sdf, k0, net, o, d, v, target, kw = make_scene(G, N, seed=2)
+    eng = make_engine(sdf, k0, net, kw, cuda)
+    rgb, last, cumw = eng.render(o.to(cuda), d.to(cuda), v.to(cuda))
+    with torch.no_grad():
+        want = oracle_forward(sdf, k0, net, o, d, v, kw, eng.voxel_size, 1.0)
+    torch.testing.assert_close(cumw.cpu(), want["cum_weights"][:, 0], rtol=0, atol=2e-4)
+    torch.testing.assert_close(rgb.cpu(), want["rgb_marched"], rtol=0, atol=2e-2)
+    assert float((rgb.cpu() - want["rgb_marched"]).abs().mean()) < 3e-3
+
+
+def _cos(a, b):
+    return float((a * b).sum() / (a.norm() * b.norm() + 1e-30))
+
+
+def test_gradients_vs_oracle(cuda):
+    """d loss / d (sdf grid, k0 grid, rgbnet weights) of one batch against torch autograd on the CPU restatement."""
+    from oracle import voxurf_cpu
+    G, N = 40, 1024
+    sdf, k0, net, o, d, v, target, kw = make_scene(G, N, seed=3)
+    eng = make_engine(sdf, k0, net, kw, cuda)
+    eng.loss_buf.zero_()
+    eng.backward_only(o.to(cuda), d.to(cuda), v.to(cuda), target.to(cuda))
+    g_sdf, g_k0, g_w, g_b = eng.grid_gradients()
+    torch.cuda.synchronize()
+    sdf_r = sdf.clone().requires_grad_(True)
+    k0_r = k0.clone().requires_grad_(True)
+    out = oracle_forward(sdf_r, k0_r, net, o, d, v, kw, eng.voxel_size, 1.0)
+    loss = voxurf_cpu.mse_loss(out, target)
+    loss.backward()
+    got_loss = float(eng.loss_buf[0])
+    assert abs(got_loss - float(loss)) < 2e-2 * float(loss) + 1e-6, (got_loss, float(loss))
+    lin = [m for m in net.modules() if isinstance(m, nn.Linear)]
+    report = {"sdf": (_cos(g_sdf.cpu(), sdf_r.grad), float(g_sdf.norm() / sdf_r.grad.norm())),
+              "k0": (_cos(g_k0.cpu(), k0_r.grad), float(g_k0.norm() / k0_r.grad.norm()))}
+    for i, m in enumerate(lin):
+        report["W%d" % i] = (_cos(g_w[i].cpu(), m.weight.grad), float(g_w[i].norm() / m.weight.grad.norm()))
+        report["b%d" % i] = (_cos(g_b[i].cpu(), m.bias.grad), float(g_b[i].norm() / (m.bias.grad.norm() + 1e-30)))
+    print(report)
+    for k, (c, ratio) in report.items():
+        assert c > 0.99, "%s: cosine %.4f (%s)" % (k, c, report)
+        assert 0.9 < ratio < 1.1, "%s: norm ratio %.3f (%s)" % (k, ratio, report)
+
+
+def test_backward_kernel_exact_inputs(cuda):
+    """The reverse-march kernel alone with synthetic upstream gradients (no MLP in the loop): fp32 agreement
+    with autograd on the oracle's pre-MLP graph.  loss' = sum_i gw_i w_i - sum_r gbg_r cum_w_r
+    + sum_i <G_i, [k0_i | normal_i]>."""
+    import ctypes
+    from poseprobe_b200._lib import check, lib, ptr, stream
+    G, N = 40, 512
+    sdf, k0, net, o, d, v, target, kw = make_scene(G, N, seed=4)
+    eng = make_engine(sdf, k0, net, kw, cuda)
+    b = eng._buffers(N)
+    oc, dc, vc = o.to(cuda), d.to(cuda), v.to(cuda)
+    with torch.cuda.device(cuda):
+        eng._march(b, oc, dc, vc, None)
+    torch.cuda.synchronize()
+    m = eng.n_samples()
+    gen = torch.Generator().manual_seed(9)
+    gw = torch.randn(m, generator=gen)
+    G16 = torch.randn(m, 16, generator=gen) * 0.1
+    G16[:, 15] = 0
+    g_ray = torch.randn(N, 3, generator=gen) * 0.1
+    b["gw"][:m] = gw.to(cuda)
+    b["dx"][:m] = G16.to(cuda)
+    b["g_ray"][:N] = g_ray.to(cuda)
+    with torch.cuda.device(cuda):
+        check(lib.pp_voxurf_backward(ctypes.byref(eng.scene), ctypes.byref(eng.cfg), ptr(oc), ptr(dc), ptr(vc), None, N,
+                                     ptr(b["rec"]), ptr(b["gw"]), ptr(b["dx"]), ptr(b["ray_off"]), ptr(b["ray_cnt"]),
+                                     ptr(b["ray_end"]), ptr(b["g_ray"]), ptr(eng.g_srec), ptr(eng.g_k0rec), stream()),
+              "voxurf_backward")
+    g_sdf, g_k0, _, _ = eng.grid_gradients()
+    torch.cuda.synchronize()
+    # oracle: same scalar through autograd.  Map our compacted slots to the oracle's sample order per ray.
+    sdf_r = sdf.clone().requires_grad_(True)
+    k0_r = k0.clone().requires_grad_(True)
+    out = oracle_forward(sdf_r, k0_r, net, o, d, v, kw, eng.voxel_size, 1.0)
+    rid_ref = out["ray_id"]
+    per_ray_ref = torch.zeros(N, dtype=torch.long).index_add_(0, rid_ref, torch.ones_like(rid_ref))
+    starts_ref = torch.cumsum(per_ray_ref, 0) - per_ray_ref
+    ray_cnt = b["ray_cnt"][:N].cpu().long()
+    ray_off = b["ray_off"][:N].cpu().long()
+    idx_ref, idx_got = [], []
+    for r in range(N):
+        c = int(ray_cnt[r])
+        idx_ref.append(torch.arange(int(starts_ref[r]), int(starts_ref[r]) + c))
+        idx_got.append(torch.arange(int(ray_off[r]), int(ray_off[r]) + c))
+    idx_ref, idx_got = torch.cat(idx_ref), torch.cat(idx_got)
+    gbg = g_ray.sum(-1) * kw["bg"]
+    w = out["weights"]
+    scalar = (gw[idx_got] * w[idx_ref]).sum() - (gbg * out["cum_weights"][:, 0]).sum() \
+        + (G16[idx_got, :12] * out["k0"][idx_ref]).sum() + (G16[idx_got, 12:15] * out["normal"][idx_ref]).sum()
+    scalar.backward()
+    c_sdf, c_k0 = _cos(g_sdf.cpu(), sdf_r.grad), _cos(g_k0.cpu(), k0_r.grad)
+    r_sdf = float(g_sdf.cpu().norm() / sdf_r.grad.norm())
+    r_k0 = float(g_k0.cpu().norm() / k0_r.grad.norm())
+    print("cos", c_sdf, c_k0, "ratio", r_sdf, r_k0)
+    assert c_sdf > 0.9999 and c_k0 > 0.99999
+    assert abs(r_sdf - 1) < 1e-3 and abs(r_k0 - 1) < 1e-4
+    torch.testing.assert_close(g_k0.cpu(), k0_r.grad, rtol=1e-4, atol=1e-6)
+
+
+def test_train_step_reduces_loss_and_roundtrips_state(cuda):
+    G, N = 48, 2048
+    sdf, k0, net, o, d, v, target, kw = make_scene(G, N, seed=6)
+    eng = make_engine(sdf, k0, net, kw, cuda, lr_sdf=1e-3, lr_k0=5e-2, lr_rgbnet=2e-3)
+    oc, dc, vc, tc = o.to(cuda), d.to(cuda), v.to(cuda), target.to(cuda)
+    losses = []
+    for _ in range(30):
+        losses.append(float(eng.train_step(oc, dc, vc, tc)[1]))
+    assert losses[-1] < 0.8 * losses[0], losses
+    st = eng.export_state()
+    assert st["sdf.grid"].shape == (1, 1, G, G, G) and st["k0.grid"].shape == (1, 12, G, G, G)
+    assert st["rgbnet.0.weight"].shape == (128, 57) and st["rgbnet.4.weight"].shape == (3, 128)
+    # a fresh engine built from the exported state renders the same image
+    from poseprobe_b200 import voxurf
+    names = ["0", "2.0", "3.0", "4"]
+    eng2 = voxurf.FusedVoxurf(st["sdf.grid"], st["k0.grid"], [st["rgbnet.%s.weight" % n] for n in names],
+                              [st["rgbnet.%s.bias" % n] for n in names], MN, MX, **kw)
+    a = eng.render(oc, dc, vc)[0]
+    bb = eng2.render(oc, dc, vc)[0]
+    torch.testing.assert_close(a, bb, rtol=0, atol=1e-5)
