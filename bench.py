@@ -242,6 +242,21 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_ms)
+    # ---- forward-only render throughput (the metric's "render Mrays/s"): rays are sharded, no communication ----
+    render_iters = 40
+    for i in range(3):
+        eng.render(*resident[i % N_BATCHES][:2], want_depth=True)
+    barrier()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    for i in range(render_iters):
+        eng.render(*resident[i % N_BATCHES][:2], want_depth=True)
+    r1.record()
+    barrier()
+    render_ms = torch.tensor([r0.elapsed_time(r1)], device=dev)
+    if world > 1:
+        dist.all_reduce(render_ms, op=dist.ReduceOp.MAX)
+    render_ms = float(render_ms) / render_iters
     # keep the GPU busy a little longer so the clock sampler sees the loaded state (the timed region is short)
     t_end = time.perf_counter() + 0.6
     i = 0
@@ -304,9 +319,19 @@ def run_ours(args, rank, world, local_rank):
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
+        "render": {"metric": "render_mrays_per_s", "value": world * RAYS / (render_ms * 1e-3) / 1e6, "unit": "Mrays/s",
+                   "ms_per_chunk": render_ms, "workload": "forward only (rgb, depth, alphainv_last), same 160^3 grid, "
+                   "%d-ray chunks per GPU, device timed" % RAYS,
+                   "achieved_gbs": (48 * RAYS + 32 * (C_d + C_f) * m_bar) / (render_ms * 1e-3) / 1e9,
+                   "frac_of_hbm_peak": (48 * RAYS + 32 * (C_d + C_f) * m_bar) / (render_ms * 1e-3) / 1e9 / pk["hbm_gbs"]},
     }
     if exchange_breakdown:
         line["step_roofline"]["exchange_breakdown"] = exchange_breakdown
+    if world == 1 and not args.no_fine_stage:
+        try:
+            line["fine_stage"] = fine_stage_bench(dev)
+        except Exception as e:   # an extra, never allowed to take the headline line down
+            line["fine_stage"] = {"error": str(e)[:200]}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
     print(json.dumps(line))
@@ -314,6 +339,54 @@ def run_ours(args, rank, world, local_rank):
         trainer.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def fine_stage_bench(dev):
+    """BASELINE configs[2] on one rank: Voxurf SDF fine stage (160^3 sdf + 12-channel k0 + rgbnet 57-128x3-3 on
+    tcgen05), 8192 rays / step, fwd + bwd + Adam.  Reported beside the headline, not instead of it."""
+    import torch.nn as nn
+    from poseprobe_b200 import ops, synthetic, voxurf
+    torch.manual_seed(777)
+    sdf = synthetic.make_sdf_grid(GRID, radius=0.5, noise=0.02)
+    k0 = 0.1 * torch.randn(1, 12, GRID, GRID, GRID)
+    net = nn.Sequential(nn.Linear(57, 128), nn.ReLU(inplace=True),
+                        nn.Sequential(nn.Linear(128, 128), nn.ReLU(inplace=True)),
+                        nn.Sequential(nn.Linear(128, 128), nn.ReLU(inplace=True)), nn.Linear(128, 3))
+    nn.init.constant_(net[-1].bias, 0)
+    ws, bs = ops.rgbnet_from_sequential(net)
+    eng = voxurf.FusedVoxurf(sdf.to(dev), k0.to(dev), [w.detach() for w in ws], [b.detach() for b in bs], XYZ_MIN,
+                             XYZ_MAX, stepsize=STEPSIZE, s_val=0.05, bg=0.0, sdf_alpha=10.0, sdf_beta=0.35,
+                             posbase_pe=5, viewbase_pe=1, lr_sdf=1e-4, lr_k0=1e-2, lr_rgbnet=1e-3)
+    from poseprobe_b200 import synthetic as syn
+    batches = []
+    for b in range(4):
+        o, d, v = syn.make_rays(RAYS, seed=777 + b)
+        t = torch.rand(RAYS, 3, generator=torch.Generator().manual_seed(99 + b))
+        batches.append(tuple(x.to(dev) for x in (o, d, v, t)))
+    for i in range(4):
+        eng.train_step(*batches[i % 4])
+    torch.cuda.synchronize()
+    m = eng.n_samples()
+    steps = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        eng.train_step(*batches[i % 4])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    V = GRID ** 3
+    step_bytes = 60 * RAYS + 96 * (4 + 12) * m + 32 * V * 13
+    mlp_flops = 3 * 2.0 * m * (57 * 128 + 2 * 128 * 128 + 128 * 3)
+    pk, _ = peaks()
+    return {"workload": "Voxurf SDF fine stage (BASELINE configs[2], one rank): 160^3 sdf + 12-ch k0 + rgbnet "
+                        "57-128-128-128-3 (tcgen05), 8192 rays/step, fwd+bwd+Adam",
+            "train_rays_per_s": RAYS / (ms * 1e-3), "ms_per_step": ms, "composited_samples_per_ray": m / RAYS,
+            "M_c_over_M": 1.0, "algorithmic_bytes_per_step": step_bytes, "mlp_algorithmic_tflop_per_step": mlp_flops / 1e12,
+            "roofline_ms": {"hbm": step_bytes / (pk["hbm_gbs"] * 1e9) * 1e3,
+                            "tensor": mlp_flops / (pk.get("bf16_tflops_sustained", pk["bf16_tflops"]) * 1e12) * 1e3},
+            "frac_of_hbm_plus_tensor_bound": (step_bytes / (pk["hbm_gbs"] * 1e9) * 1e3 + mlp_flops / (
+                pk.get("bf16_tflops_sustained", pk["bf16_tflops"]) * 1e12) * 1e3) / ms}
 
 
 def cpu_baseline():
@@ -344,6 +417,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", dest="no_cpu_baseline", action="store_true")
+    ap.add_argument("--no-fine-stage", dest="no_fine_stage", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -638,7 +638,11 @@ extern "C" int pp_voxurf_sdf_adam(const pp_dvgo_scene* scene, const pp_voxurf_cf
   const float step_size =
       exp_avg ? lr * sqrtf(1.f - powf(beta2, (float)step)) / (1.f - powf(beta1, (float)step)) : 0.f;
   const dim3 block(32, 8, 1);
-  const dim3 grid((scene->sz + 31) / 32, (scene->sy + 7) / 8, (unsigned)min64(scene->sx, 65535));
+  // few slices of X per block column: the (a, b) gradient costs two same-address atomics per warp, so the grid is
+  // kept near 8 blocks per SM instead of one block per (y, z) tile and slice
+  const int tiles = ((scene->sz + 31) / 32) * ((scene->sy + 7) / 8);
+  const int zdim = (int)min64(scene->sx, (int64_t)((8 * sm_count() + tiles - 1) / tiles));
+  const dim3 grid((scene->sz + 31) / 32, (scene->sy + 7) / 8, (unsigned)(zdim < 1 ? 1 : zdim));
   sdf_fold_adam_kernel<<<grid, block, 0, as_stream(stream)>>>(
       sdf, (const float4*)grad_sdf_records, exp_avg, exp_avg_sq, scene->sx, scene->sy, scene->sz, cfg->sdf_scale_a,
       cfg->sdf_scale_b, 0.5f / cfg->voxel_size, step_size, beta1, beta2, eps, grad_sdf_out, grad_ab);

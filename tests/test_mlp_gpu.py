@@ -142,7 +142,7 @@ def test_rgbnet_forward_composite_epilogue(cuda):
     marched = torch.zeros(n_rays, 3, device="cuda")
     arr = lambda ts: (ctypes.c_void_p * depth)(*[t.data_ptr() for t in ts])
     check(lib.pp_rgbnet_forward_packed(ptr(xp), n, d0, depth, 128, arr(ws), arr(bs), 1, ptr(out), ptr(w), ptr(ray_id),
-                                       ptr(marched), stream()), "fwd")
+                                       ptr(marched), None, stream()), "fwd")
     want = torch.zeros(n_rays, 3, device="cuda").index_add_(0, ray_id.long(), w[:, None] * out)
     torch.testing.assert_close(marched, want, rtol=1e-4, atol=1e-4)
     torch.testing.assert_close(out, ops.rgbnet_forward(x, ws, bs), rtol=0, atol=0)

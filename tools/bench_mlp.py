@@ -86,7 +86,7 @@ def main():
 
     def fwd_packed():
         check(lib.pp_rgbnet_forward_packed(ptr(xp), n, d0, depth, 128, arr(wsd), arr(bsd), 1, ptr(outp), None, None,
-                                           None, stream()), "fwd")
+                                           None, None, stream()), "fwd")
     t_fwdp = timeit(fwd_packed)
     print("rgbnet 57-128-128-128-3, n=%d" % n)
     print("  forward kernel alone (packed bf16 in): %.3f ms  (%.0f TFLOP/s)" % (t_fwdp, flops_fwd / t_fwdp / 1e9))
