@@ -119,13 +119,22 @@ class FusedVoxurf:
                                                               for w in rgbnet_weights[1:]]
         self.biases = [b.detach().to(dev).float().contiguous() for b in rgbnet_biases]
         self.srec = torch.empty((self.n_voxels, 4), dtype=torch.float32, device=dev)
-        # gradients and optimiser state
-        self.g_srec = torch.zeros_like(self.srec)
-        self.g_k0rec = torch.zeros_like(self.k0rec)
+        # gradients: ONE flat buffer (SDF-record gradients | feature-record gradients | rgbnet gradients), so a
+        # multi-GPU step reduces everything with a single all-reduce (DistributedVoxurf)
+        n_net = sum(w.numel() for w in self.weights) + sum(b.numel() for b in self.biases)
+        self.grad_flat = torch.zeros(16 * self.n_voxels + n_net, dtype=torch.float32, device=dev)
+        self.g_srec = self.grad_flat[:4 * self.n_voxels].view(self.n_voxels, 4)
+        self.g_k0rec = self.grad_flat[4 * self.n_voxels:16 * self.n_voxels].view(self.n_voxels, 12)
+        self.g_w, self.g_b = [], []
+        off = 16 * self.n_voxels
+        for w in self.weights:
+            self.g_w.append(self.grad_flat[off:off + w.numel()].view_as(w))
+            off += w.numel()
+        for bb in self.biases:
+            self.g_b.append(self.grad_flat[off:off + bb.numel()].view_as(bb))
+            off += bb.numel()
         self.m_sdf, self.v_sdf = torch.zeros_like(self.sdf), torch.zeros_like(self.sdf)
         self.m_k0, self.v_k0 = torch.zeros_like(self.k0rec), torch.zeros_like(self.k0rec)
-        self.g_w = [torch.zeros_like(w) for w in self.weights]
-        self.g_b = [torch.zeros_like(b) for b in self.biases]
         self.m_w = [torch.zeros_like(w) for w in self.weights]
         self.v_w = [torch.zeros_like(w) for w in self.weights]
         self.m_b = [torch.zeros_like(b) for b in self.biases]
@@ -314,3 +323,52 @@ class FusedVoxurf:
             out["rgbnet.%s.weight" % nme] = w
             out["rgbnet.%s.bias" % nme] = bb.clone()
         return out
+
+
+def smoke(dev):
+    """Tiny fused fine-stage train step (used by __graft_entry__.smoke): runs the march, both tcgen05 rgbnet
+    kernels, the reverse march and the optimiser tail once."""
+    import torch.nn as nn
+    from . import ops, synthetic
+    G, N = 24, 256
+    torch.manual_seed(0)
+    sdf = synthetic.make_sdf_grid(G, 0.5, 0.01)
+    k0 = 0.3 * torch.randn(1, 12, G, G, G)
+    net = nn.Sequential(nn.Linear(57, 128), nn.ReLU(), nn.Linear(128, 128), nn.ReLU(), nn.Linear(128, 3))
+    ws, bs = ops.rgbnet_from_sequential(net)
+    eng = FusedVoxurf(sdf.to(dev), k0.to(dev), [w.detach() for w in ws], [b.detach() for b in bs], [-1, -1, -1],
+                      [1, 1, 1], stepsize=0.5, s_val=0.05, bg=0.5, sdf_alpha=10.0, sdf_beta=0.35)
+    o, d, v = synthetic.make_rays(N)
+    tgt = torch.rand(N, 3, device=dev)
+    loss = eng.train_step(o.to(dev), d.to(dev), v.to(dev), tgt)
+    torch.cuda.synchronize()
+    assert torch.isfinite(loss).all() and float(loss[0]) > 0 and eng.n_samples() > 0
+    return float(loss[0]), eng, (o, d, v)
+
+
+class DistributedVoxurf:
+    """FusedVoxurf replicated over the ranks of a process group: every rank marches its own ray batch, the flat
+    gradient buffer (SDF-record, feature-record and rgbnet gradients) is summed with ONE NCCL all-reduce over
+    NVLink, and every rank applies the same optimiser step.  The loss is the global mean over all ranks' rays,
+    so N ranks with batches b_0..b_{N-1} equal one rank stepping on their concatenation (up to fp32 summation
+    order)."""
+
+    def __init__(self, *args, group=None, **kw):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        kw = dict(kw)
+        kw["w_rgb"] = kw.get("w_rgb", 1.0) / self.world
+        self.eng = FusedVoxurf(*args, **kw)
+
+    def train_step(self, rays_o, rays_d, viewdirs, target, jitter=None):
+        eng = self.eng
+        eng.loss_buf.zero_()
+        eng.backward_only(rays_o, rays_d, viewdirs, target, jitter)
+        if self.world > 1:
+            self.dist.all_reduce(eng.grad_flat, group=self.group)
+            self.dist.all_reduce(eng.loss_buf, group=self.group)
+        eng.optimizer_step()
+        eng.loss_buf[1] /= self.world          # [global w_rgb-weighted loss, global mean-squared error]
+        return eng.loss_buf

@@ -1,0 +1,78 @@
+"""CPU tier for the fine-stage path: the Voxurf oracle (oracle/voxurf_cpu.py) is pinned on closed forms stated by
+the reference's code, and the host-side column map of the fused kernels is checked without a GPU."""
+import math
+
+import torch
+import torch.nn as nn
+
+from oracle import voxurf_cpu
+
+
+def test_gradient_grid_is_the_reference_central_difference():
+    """neus_sdf_gradient(mode='interpolate'), lib/voxurf_coarse.py:463-467, literally."""
+    torch.manual_seed(0)
+    sdf = torch.randn(1, 1, 7, 6, 5)
+    vs = 0.25
+    want = torch.zeros(1, 3, 7, 6, 5)
+    want[:, 0, 1:-1, :, :] = (sdf[:, 0, 2:, :, :] - sdf[:, 0, :-2, :, :]) / 2 / vs
+    want[:, 1, :, 1:-1, :] = (sdf[:, 0, :, 2:, :] - sdf[:, 0, :, :-2, :]) / 2 / vs
+    want[:, 2, :, :, 1:-1] = (sdf[:, 0, :, :, 2:] - sdf[:, 0, :, :, :-2]) / 2 / vs
+    assert torch.equal(voxurf_cpu.sdf_gradient_grid(sdf, vs), want)
+
+
+def test_linear_sdf_gives_constant_gradient_and_normal():
+    """An SDF that is linear in x: the sampled gradient is (slope, 0, 0) away from the border slices."""
+    G = 16
+    lin = torch.linspace(-1, 1, G)
+    sdf = (0.7 * lin)[:, None, None].expand(G, G, G)[None, None].contiguous()
+    vs = 2.0 / (G - 1)
+    g = voxurf_cpu.sdf_gradient_grid(sdf, vs)
+    torch.testing.assert_close(g[0, 0, 1:-1], torch.full((G - 2, G, G), 0.7), rtol=1e-5, atol=1e-6)
+    assert float(g[0, 1].abs().max()) == 0 and float(g[0, 2].abs().max()) == 0
+
+
+def test_barf_weights_closed_form():
+    """positional_encoding_barf, :721-732: w_k = (1 - cos(pi clamp(alpha - k, 0, 1))) / 2."""
+    from poseprobe_b200.voxurf import barf_weights as host_w
+    for progress in (0.0, 0.12, 0.3, 0.49, 0.9):
+        w = voxurf_cpu.barf_weights(progress, (0.1, 0.5), 5)
+        alpha = (progress - 0.1) / 0.4 * 5
+        for k in range(5):
+            c = min(max(alpha - k, 0.0), 1.0)
+            assert abs(float(w[k]) - (1 - math.cos(c * math.pi)) / 2) < 1e-6
+        torch.testing.assert_close(w, torch.tensor(host_w(progress, (0.1, 0.5), 5)), rtol=1e-6, atol=1e-6)
+    assert torch.equal(voxurf_cpu.barf_weights(0.3, None, 5), torch.ones(5))
+
+
+def test_feature_permutation_covers_the_reference_row():
+    from poseprobe_b200.voxurf import feature_permutation
+    perm, d0 = feature_permutation(5, 1)
+    assert d0 == 57                                   # 12 + 33 + 9 + 3 (voxurf_coarse.py:198-206)
+    used = [p for p in perm if p >= 0]
+    assert sorted(used) == list(range(57))            # every reference column feeds exactly one kernel column
+    assert perm[:12] == list(range(12))               # k0 first
+    assert perm[12:15] == [54, 55, 56] and perm[15] == -1   # normal next: the backward stores 16 gradient columns
+    perm3, d3 = feature_permutation(3, 0)
+    assert d3 == 12 + 3 + 18 + 3 + 3 and sorted(p for p in perm3 if p >= 0) == list(range(d3))
+
+
+def test_oracle_forward_properties():
+    """Partition of unity of the compositing, clamp range, feature row layout, finite gradients."""
+    from poseprobe_b200 import synthetic
+    G, N = 20, 48
+    sdf = synthetic.make_sdf_grid(G, 0.5, 0.01).requires_grad_(True)
+    k0 = (0.3 * torch.randn(1, 12, G, G, G)).requires_grad_(True)
+    net = nn.Sequential(nn.Linear(57, 128), nn.ReLU(), nn.Linear(128, 3))
+    o, d, v = synthetic.make_rays(N, seed=3)
+    out = voxurf_cpu.forward(sdf, k0, net, o, d, v, [-1, -1, -1], [1, 1, 1], 0.5, 2.0 / G, 0.05, bg=0.5,
+                             sdf_alpha=10.0, sdf_beta=0.35, barf_c2f=(0.1, 0.5), progress=0.3)
+    cum = out["cum_weights"][:, 0]
+    torch.testing.assert_close(cum + out["alphainv_cum"], torch.ones(N), rtol=0, atol=1e-4)
+    assert float(out["rgb_marched"].min()) >= 0 and float(out["rgb_marched"].max()) <= 1
+    f = out["rgb_feat"]
+    assert f.shape[1] == 57
+    torch.testing.assert_close(f[:, 54:57].norm(dim=-1), torch.ones(f.shape[0]), rtol=1e-3, atol=1e-3)   # normal
+    torch.testing.assert_close(f[:, 45:48], v[out["ray_id"]])                                          # viewdirs
+    voxurf_cpu.mse_loss(out, torch.rand(N, 3)).backward()
+    assert torch.isfinite(sdf.grad).all() and float(sdf.grad.abs().sum()) > 0
+    assert torch.isfinite(k0.grad).all() and float(k0.grad.abs().sum()) > 0

@@ -147,6 +147,30 @@ def main():
         f16 = feat.to(torch.bfloat16)
         t_r2 = timeit(lambda: torch.sigmoid(net16(f16)))
         row("rgbnet fwd (same)", t_o, t_r2, "nn.Sequential bf16 (cuBLAS)", (57 * 4 + 12) * Mc)
+    feat_g = feat.clone().requires_grad_(True)
+    gout = torch.randn(Mc, 3, device=dev) / Mc
+    wsg = [w.detach().clone().requires_grad_(True) for w in ws]
+    bsg = [b.detach().clone().requires_grad_(True) for b in bs]
+
+    def ours_fb():
+        for t in wsg + bsg + [feat_g]:
+            t.grad = None
+        ops.rgbnet(feat_g, wsg, bsg).backward(gout)
+    net32 = nn.Sequential(nn.Linear(57, 128), nn.ReLU(), nn.Linear(128, 128), nn.ReLU(), nn.Linear(128, 128), nn.ReLU(),
+                          nn.Linear(128, 3)).to(dev)
+
+    def ref_fb(nt, x_, g_):
+        nt.zero_grad(set_to_none=True)
+        x_.grad = None
+        torch.sigmoid(nt(x_)).backward(g_)
+    t_o = timeit(ours_fb)
+    t_r = timeit(lambda: ref_fb(net32, feat_g, gout))
+    row("rgbnet fwd+bwd (dX, dW, db), fp32 [M,57] in/out", t_o, t_r, "nn.Sequential fp32 autograd (cuBLAS)",
+        (57 * 4 * 2 + 24) * Mc)
+    f16g = feat.to(torch.bfloat16).requires_grad_(True)
+    g16 = gout.to(torch.bfloat16)
+    t_r2 = timeit(lambda: ref_fb(net16, f16g, g16))
+    row("rgbnet fwd+bwd (same)", t_o, t_r2, "nn.Sequential bf16 autograd (cuBLAS)", (57 * 4 * 2 + 24) * Mc)
     # ---- fused render vs the composed operator chain
     sc = dvgo.make_scene((G, G, G), [-1, -1, -1], [1, 1, 1], 0.2, 1e9, stepdist, shift, 0.5)
     vox = dvgo.pack_voxels(density, k0)
@@ -166,6 +190,62 @@ def main():
         t_r = timeit(lambda: chain(ref_ru))
         row("render forward, 8192 rays (fused march kernel)", t_o, t_r, "reference ops + ATen chain",
             48 * N + 32 * 4 * M)
+    # ---- whole train step: reference operator chain + autograd + reference masked Adam vs the fused step
+    if ref_ru and ref_ad:
+        class RefR2A(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, dn_, sh_, iv_):
+                e_, a_ = ref_ru.raw2alpha(dn_, sh_, iv_)
+                ctx.save_for_backward(e_)
+                ctx.iv = iv_
+                return a_
+
+            @staticmethod
+            def backward(ctx, g_):
+                return ref_ru.raw2alpha_backward(ctx.saved_tensors[0], g_.contiguous(), ctx.iv), None, None
+
+        class RefA2W(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, al_, rid_, n_):
+                w_, T_, la_, is_, ie_ = ref_ru.alpha2weight(al_, rid_, n_)
+                ctx.save_for_backward(al_, w_, T_, la_, is_, ie_)
+                ctx.n = n_
+                return w_, la_
+
+            @staticmethod
+            def backward(ctx, gw_, gl_):
+                al_, w_, T_, la_, is_, ie_ = ctx.saved_tensors
+                return ref_ru.alpha2weight_backward(al_, w_, T_, la_, is_, ie_, ctx.n, gw_.contiguous(),
+                                                    gl_.contiguous()), None, None
+        dens_p = density.clone().requires_grad_(True)
+        k0_p = k0.clone().requires_grad_(True)
+        st = [torch.zeros_like(dens_p), torch.zeros_like(dens_p), torch.zeros_like(k0_p), torch.zeros_like(k0_p)]
+        tgt = torch.rand(N, 3, device=dev)
+        step_no = [0]
+
+        def ref_step():
+            dens_p.grad = None
+            k0_p.grad = None
+            p_, m_k, rid, sid, *_ = ref_ru.sample_pts_on_rays(o, d, mn, mx, 0.2, 1e9, stepdist)
+            kk = ~m_k
+            p_, rid = p_[kk], rid[kk]
+            ind = ((p_.reshape(1, 1, 1, -1, 3) - mn) / (mx - mn)).flip((-1,)) * 2 - 1
+            dn = F.grid_sample(dens_p, ind, mode="bilinear", align_corners=True).reshape(-1)
+            al = RefR2A.apply(dn, shift, 0.5)
+            ww, la = RefA2W.apply(al, rid, N)
+            col = torch.sigmoid(F.grid_sample(k0_p, ind, mode="bilinear", align_corners=True).reshape(3, -1).T)
+            rgbm = torch.zeros(N, 3, device=dev).index_add_(0, rid, ww[:, None] * col) + la[:, None] * 0.0
+            F.mse_loss(rgbm, tgt).backward()
+            step_no[0] += 1
+            with torch.no_grad():
+                ref_ad.masked_adam_upd(dens_p, dens_p.grad, st[0], st[1], step_no[0], 0.9, 0.99, 0.1, 1e-8)
+                ref_ad.masked_adam_upd(k0_p, k0_p.grad, st[2], st[3], step_no[0], 0.9, 0.99, 0.1, 1e-8)
+        eng = dvgo.FusedDVGO(density, k0, [-1, -1, -1], [1, 1, 1], stepsize=0.5)
+        t_o = timeit(lambda: eng.train_step(o, d, tgt))
+        t_r = timeit(ref_step, 5)
+        row("TRAIN STEP 8192 rays: fwd + bwd + masked Adam (fused: 2 launches)", t_o, t_r,
+            "reference kernels + ATen grid_sample/index_add_ + autograd + reference masked_adam_upd",
+            60 * N + 96 * 4 * M + 32 * 4 * G ** 3)
     print("# Per-operator timings, B200, config-B shapes (us per call; GB/s = algorithmic bytes / our time)\n")
     print("| operator | ours (us) | reference (us) | speed-up | reference is | ours GB/s |")
     print("|---|---|---|---|---|---|")
