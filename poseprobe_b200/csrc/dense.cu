@@ -29,34 +29,44 @@ template <typename scalar_t, bool kDense, bool kMasked>
 __global__ void __launch_bounds__(256)
 tv_add_grad_kernel(const scalar_t* __restrict__ param, scalar_t* __restrict__ grad,
                    const scalar_t* __restrict__ mask, float wk, float wj, float wi, int sz_i,
-                   int sz_j, int sz_k, int64_t n_slabs) {
+                   int sz_j, int sz_k, int chunk, int chunks_per_plane) {
   const int k = blockIdx.x * 32 + threadIdx.x;
   const int j = blockIdx.y * 8 + threadIdx.y;
   if (k >= sz_k || j >= sz_j) return;
-  for (int64_t pi = blockIdx.z; pi < n_slabs; pi += gridDim.z) {  // pi = plane * sz_i + i
-  const int i = static_cast<int>(pi % sz_i);
+  // blockIdx.z = plane * chunks_per_plane + chunk index: the thread walks `chunk` consecutive slices of X with a
+  // sliding window (previous, current, next) of its own column, so every parameter is loaded once for the three
+  // X terms it takes part in, and one block does `chunk` slices of work per launch slot
+  const int plane = blockIdx.z / chunks_per_plane;
+  const int i_begin = (blockIdx.z - plane * chunks_per_plane) * chunk;
+  const int i_end = min(i_begin + chunk, sz_i);
   const int64_t sk = 1, sj = sz_k, si = (int64_t)sz_k * sz_j;
-  const int64_t idx = ((int64_t)pi * sz_j + j) * sz_k + k;
-  scalar_t g = grad[idx];
-  if (!kDense && g == scalar_t(0)) continue;
-  const scalar_t p = param[idx];
-  const scalar_t m0 = kMasked ? mask[idx] : scalar_t(1);
-  float acc = 0.f;  // the reference accumulates in a float local
-  auto term = [&](bool edge, int64_t off, float w) {
-    if (edge) return;
-    // w * clamp(p - p_nbr, -1, 1) [* mask * mask_nbr], added to the float accumulator
-    // (reference SASS: rounded product, then plain adds -- no FMA contraction here)
-    scalar_t t = mul_rn(static_cast<scalar_t>(w), clamp1(p - param[idx + off]));
-    if (kMasked) t = mul_rn(mul_rn(t, m0), mask[idx + off]);
-    acc = static_cast<float>(add_rn(static_cast<scalar_t>(acc), t));
-  };
-  term(k == 0, -sk, wk);
-  term(k == sz_k - 1, sk, wk);
-  term(j == 0, -sj, wj);
-  term(j == sz_j - 1, sj, wj);
-  term(i == 0, -si, wi);
-  term(i == sz_i - 1, si, wi);
-  grad[idx] = add_rn(g, static_cast<scalar_t>(acc));
+  int64_t idx = (((int64_t)plane * sz_i + i_begin) * sz_j + j) * sz_k + k;
+  scalar_t p_prev = (i_begin > 0) ? param[idx - si] : scalar_t(0);
+  scalar_t p = param[idx];
+  for (int i = i_begin; i < i_end; ++i, idx += si) {
+    const scalar_t p_next = (i + 1 < sz_i) ? param[idx + si] : scalar_t(0);
+    const scalar_t g = grad[idx];
+    if (kDense || g != scalar_t(0)) {
+      const scalar_t m0 = kMasked ? mask[idx] : scalar_t(1);
+      float acc = 0.f;  // the reference accumulates in a float local
+      auto term = [&](bool edge, scalar_t nbr, int64_t off, float w) {
+        if (edge) return;
+        // w * clamp(p - p_nbr, -1, 1) [* mask * mask_nbr], added to the float accumulator
+        // (reference SASS: rounded product, then plain adds -- no FMA contraction here)
+        scalar_t t = mul_rn(static_cast<scalar_t>(w), clamp1(p - nbr));
+        if (kMasked) t = mul_rn(mul_rn(t, m0), mask[idx + off]);
+        acc = static_cast<float>(add_rn(static_cast<scalar_t>(acc), t));
+      };
+      if (k != 0) term(false, param[idx - sk], -sk, wk);
+      if (k != sz_k - 1) term(false, param[idx + sk], sk, wk);
+      if (j != 0) term(false, param[idx - sj], -sj, wj);
+      if (j != sz_j - 1) term(false, param[idx + sj], sj, wj);
+      term(i == 0, p_prev, -si, wi);
+      term(i == sz_i - 1, p_next, si, wi);
+      grad[idx] = add_rn(g, static_cast<scalar_t>(acc));
+    }
+    p_prev = p;
+    p = p_next;
   }
 }
 
@@ -180,13 +190,15 @@ extern "C" int pp_total_variation_add_grad(pp_dtype dtype, const void* param, vo
   if (n_planes * sz_i * sz_j * sz_k == 0) return PP_OK;
   PP_REQUIRE(param && grad, PP_ERR_INVALID_ARG, "total_variation_add_grad: null pointer");
   PP_REQUIRE((sz_j + 7) / 8 <= 65535, PP_ERR_TOO_LARGE, "total_variation_add_grad: sz_j too large");
-  const int64_t n_slabs = n_planes * sz_i;
   // the reference host code divides the three weights by 6 (total_variation_kernel.cu:76-78)
   wx /= 6;
   wy /= 6;
   wz /= 6;
   const dim3 block(32, 8, 1);
-  const dim3 grid((unsigned)((sz_k + 31) / 32), (unsigned)((sz_j + 7) / 8), (unsigned)min64(n_slabs, 65535));
+  const int chunk = 16;
+  const int chunks_per_plane = (int)((sz_i + chunk - 1) / chunk);
+  PP_REQUIRE(n_planes * chunks_per_plane <= 65535, PP_ERR_TOO_LARGE, "total_variation_add_grad: too many planes");
+  const dim3 grid((unsigned)((sz_k + 31) / 32), (unsigned)((sz_j + 7) / 8), (unsigned)(n_planes * chunks_per_plane));
   cudaStream_t s = as_stream(stream);
   PP_DISPATCH(dtype, {
     const scalar_t* p = (const scalar_t*)param;
@@ -195,15 +207,15 @@ extern "C" int pp_total_variation_add_grad(pp_dtype dtype, const void* param, vo
     if (!mask) {
       // old kernel: k -> wz, j -> wy, i -> wz
       if (dense_mode)
-        tv_add_grad_kernel<scalar_t, true, false><<<grid, block, 0, s>>>(p, g, nullptr, wz, wy, wz, (int)sz_i, (int)sz_j, (int)sz_k, n_slabs);
+        tv_add_grad_kernel<scalar_t, true, false><<<grid, block, 0, s>>>(p, g, nullptr, wz, wy, wz, (int)sz_i, (int)sz_j, (int)sz_k, chunk, chunks_per_plane);
       else
-        tv_add_grad_kernel<scalar_t, false, false><<<grid, block, 0, s>>>(p, g, nullptr, wz, wy, wz, (int)sz_i, (int)sz_j, (int)sz_k, n_slabs);
+        tv_add_grad_kernel<scalar_t, false, false><<<grid, block, 0, s>>>(p, g, nullptr, wz, wy, wz, (int)sz_i, (int)sz_j, (int)sz_k, chunk, chunks_per_plane);
     } else {
       // new kernel: k -> wx, j -> wy, i -> wz
       if (dense_mode)
-        tv_add_grad_kernel<scalar_t, true, true><<<grid, block, 0, s>>>(p, g, m, wx, wy, wz, (int)sz_i, (int)sz_j, (int)sz_k, n_slabs);
+        tv_add_grad_kernel<scalar_t, true, true><<<grid, block, 0, s>>>(p, g, m, wx, wy, wz, (int)sz_i, (int)sz_j, (int)sz_k, chunk, chunks_per_plane);
       else
-        tv_add_grad_kernel<scalar_t, false, true><<<grid, block, 0, s>>>(p, g, m, wx, wy, wz, (int)sz_i, (int)sz_j, (int)sz_k, n_slabs);
+        tv_add_grad_kernel<scalar_t, false, true><<<grid, block, 0, s>>>(p, g, m, wx, wy, wz, (int)sz_i, (int)sz_j, (int)sz_k, chunk, chunks_per_plane);
     }
   });
   PP_CHECK_LAUNCH("total_variation_add_grad");
