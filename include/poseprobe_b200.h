@@ -219,6 +219,17 @@ PP_API int pp_neus_alpha_backward(const float* sdf, const float* gradient, const
                            const float* grad_alpha, float* grad_sdf, float* grad_gradient,
                            pp_stream_t stream);
 
+/* Python-side total variation loss the reference actually uses (`total_variation`, lib/voxurf_coarse.py:1298-1313,
+ * via k0_total_variation :443-456 / density_total_variation :407-411): sum over the three axes of |forward
+ * difference|, optionally restricted to pairs whose two voxels are both set in `mask` ([X,Y,Z] bool, shared by all
+ * planes = nonempty_mask.repeat).  Forward writes the un-normalised sum to *sum_out (double, device); the caller
+ * divides by 3 * count (count = numel, or planes * mask.sum()).  Backward: grad += scale * d(sum)/dv. */
+PP_API int pp_total_variation_loss(const float* v, const uint8_t* mask, int64_t n_planes, int64_t sz_i,
+                                   int64_t sz_j, int64_t sz_k, double* sum_out, pp_stream_t stream);
+PP_API int pp_total_variation_loss_backward(const float* v, const uint8_t* mask, int64_t n_planes, int64_t sz_i,
+                                            int64_t sz_j, int64_t sz_k, float scale, float* grad,
+                                            pp_stream_t stream);
+
 /* rgbnet / colour MLP forward on tcgen05 tensor cores (lib/voxurf_coarse.py:208-216, :1032-1033;
  * lib/dvgo_ori.py:82-89): out[n,3] = [sigmoid](W_L relu(... relu(W_1 x + b_1) ...) + b_L).
  * x [n, d0] fp32 row-major (the concatenated feature rows the reference builds);
@@ -269,14 +280,15 @@ PP_API int pp_rgbnet_backward_packed(const void* x_packed, const float* grad_out
                                      pp_stream_t stream);
 
 /* Fine-stage form: grad_out_i = sample_weight[i] * g_ray[sample_ray[i], :] is formed in the kernel (sigmoid
- * output), grad_weight_out[i] = sum_c g_ray[sample_ray[i],c] * rgb_i,c, and only the 16 leading input-gradient
- * columns are stored (grad_feat16 [capacity,16]); the row count is read from the device (n_ptr). */
+ * output), grad_weight_out[i] = sum_c g_ray[sample_ray[i],c] * rgb_i,c, and grad_feat_cols = 16 (only the leading
+ * input-gradient columns, row pitch 16) or the padded width (all columns) are stored in grad_feat; the row count
+ * is read from the device (n_ptr). */
 PP_API int pp_rgbnet_backward_fused(const void* x_packed, int64_t capacity, const int32_t* n_ptr, int32_t d0,
                                     int32_t depth, int32_t width, const float* const* weights,
                                     const float* const* biases, const float* sample_weight,
                                     const int32_t* sample_ray, const float* g_ray, float* grad_weight_out,
-                                    float* grad_feat16, float* const* grad_weights, float* const* grad_biases,
-                                    pp_stream_t stream);
+                                    float* grad_feat, int32_t grad_feat_cols, float* const* grad_weights,
+                                    float* const* grad_biases, pp_stream_t stream);
 
 /* Camera rays for selected pixels (get_rays / get_rays_of_a_view, lib/voxurf_coarse.py:1339-1368, :1402-1407,
  * mode='center' is px = i + 0.5 etc. supplied by the caller; flips are applied to px/py by the caller):

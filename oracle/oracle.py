@@ -290,6 +290,20 @@ def total_variation_loss(v):
     return (tv2.mean() + tv3.mean() + tv4.mean()) / 3
 
 
+def total_variation(v, mask=None):
+    """lib/voxurf_coarse.py:1298-1313, restated literally (mask: bool tensor of v's shape)."""
+    tv2 = (v[:, :, 1:, :, :] - v[:, :, :-1, :, :]).abs()
+    tv3 = (v[:, :, :, 1:, :] - v[:, :, :, :-1, :]).abs()
+    tv4 = (v[:, :, :, :, 1:] - v[:, :, :, :, :-1]).abs()
+    if mask is not None:
+        tv2 = tv2[mask[:, :, :-1] & mask[:, :, 1:]]
+        tv3 = tv3[mask[:, :, :, :-1] & mask[:, :, :, 1:]]
+        tv4 = tv4[mask[:, :, :, :, :-1] & mask[:, :, :, :, 1:]]
+    if mask is None:
+        mask = torch.ones_like(v)
+    return (tv2.sum() + tv3.sum() + tv4.sum()) / 3 / mask.sum()
+
+
 def python_adam_step(param, grad, exp_avg, exp_avg_sq, step, beta1, beta2, lr, eps, per_lr=None):
     """The live optimiser's math, lib/utils.py:176-198 (in place)."""
     bc1 = 1 - beta1 ** step

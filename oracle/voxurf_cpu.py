@@ -68,13 +68,22 @@ def sample(rays_o, rays_d, xyz_min, xyz_max, near, far, stepdist, jitter=None):
 
 def forward(sdf_grid, k0_grid, rgbnet, rays_o, rays_d, viewdirs, xyz_min, xyz_max, stepsize, voxel_size, s_val,
             near=0.2, far=1e9, bg=0.0, sdf_alpha=None, sdf_beta=None, posbase_pe=5, viewbase_pe=1, barf_c2f=None,
-            progress=1.0, jitter=None):
-    """sdf_grid [1,1,X,Y,Z], k0_grid [1,12,X,Y,Z] (may require grad), rgbnet: callable rows -> logits."""
+            progress=1.0, jitter=None, differentiable_points=False):
+    """sdf_grid [1,1,X,Y,Z], k0_grid [1,12,X,Y,Z] (may require grad), rgbnet: callable rows -> logits.
+    differentiable_points: rebuild the sample positions from (rays_o, rays_d) with torch ops (the formulas of
+    sample_ray_ori, voxurf_coarse.py:702-716) so that autograd reaches the rays (pose gradient)."""
     xyz_min = torch.as_tensor(xyz_min, dtype=torch.float32)
     xyz_max = torch.as_tensor(xyz_max, dtype=torch.float32)
     n = rays_o.shape[0]
     stepdist = stepsize * voxel_size
-    pts, ray_id, step_id = sample(rays_o, rays_d, xyz_min, xyz_max, near, far, stepdist, jitter)
+    with torch.no_grad():
+        pts, ray_id, step_id = sample(rays_o.detach(), rays_d.detach(), xyz_min, xyz_max, near, far, stepdist, jitter)
+    if differentiable_points:
+        vec = torch.where(rays_d == 0, torch.full_like(rays_d, 1e-6), rays_d)
+        t_min = torch.minimum((xyz_max - rays_o) / vec, (xyz_min - rays_o) / vec).amax(-1).clamp(min=near, max=far)
+        steps = step_id.float() + (jitter[ray_id] if jitter is not None else 0.0)
+        interpx = t_min[ray_id] + stepdist * steps / rays_d.norm(dim=-1)[ray_id]
+        pts = rays_o[ray_id] + rays_d[ray_id] * interpx[:, None]
     grid = sdf_grid
     if sdf_alpha is not None:
         grid = softplus10(sdf_alpha) * (torch.sigmoid(softplus10(sdf_beta) * sdf_grid) - 0.5)

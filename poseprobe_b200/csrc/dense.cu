@@ -70,6 +70,66 @@ tv_add_grad_kernel(const scalar_t* __restrict__ param, scalar_t* __restrict__ gr
   }
 }
 
+// ---- Python-side total variation loss actually used by the reference (voxurf_coarse.py:1298-1313, called from
+//      k0_total_variation :443-456 and density_total_variation :407-411): (sum|d2| + sum|d3| + sum|d4|) / 3 / count.
+// The reference builds >= 9 grid-sized temporaries per call (forward and autograd).  Here: one pass each way, the
+// same sliding window along X as the add-grad kernel.  kBackward: grad += scale * d(sum)/dv.
+template <bool kBackward>
+__global__ void __launch_bounds__(256)
+tv_loss_kernel(const float* __restrict__ v, const uint8_t* __restrict__ mask, int sz_i, int sz_j, int sz_k,
+               int chunk, int chunks_per_plane, float scale, float* __restrict__ grad, double* __restrict__ sum_out) {
+  const int k = blockIdx.x * 32 + threadIdx.x;
+  const int j = blockIdx.y * 8 + threadIdx.y;
+  float acc = 0.f;
+  if (k < sz_k && j < sz_j) {
+    const int plane = blockIdx.z / chunks_per_plane;
+    const int i_begin = (blockIdx.z - plane * chunks_per_plane) * chunk;
+    const int i_end = min(i_begin + chunk, sz_i);
+    const int64_t sj = sz_k, si = (int64_t)sz_k * sz_j;
+    int64_t cell = ((int64_t)i_begin * sz_j + j) * sz_k + k;           // index inside one plane (mask index)
+    int64_t idx = (int64_t)plane * sz_i * si + cell;
+    auto ok = [&](int64_t c) { return mask == nullptr || mask[c] != 0; };
+    float p_prev = (i_begin > 0) ? v[idx - si] : 0.f;
+    float p = v[idx];
+    for (int i = i_begin; i < i_end; ++i, idx += si, cell += si) {
+      const float p_next = (i + 1 < sz_i) ? v[idx + si] : 0.f;
+      const bool m0 = ok(cell);
+      if (!kBackward) {
+        // forward differences owned by this voxel: towards +X, +Y, +Z
+        if (m0) {
+          if (i + 1 < sz_i && ok(cell + si)) acc += fabsf(p_next - p);
+          if (j + 1 < sz_j && ok(cell + sj)) acc += fabsf(v[idx + sj] - p);
+          if (k + 1 < sz_k && ok(cell + 1)) acc += fabsf(v[idx + 1] - p);
+        }
+      } else if (m0) {
+        // d/dp of |p - p_prev| + |p_next - p| per axis (torch.abs backward: sign, 0 at 0)
+        auto sgn = [](float x) { return (x > 0.f) - (x < 0.f); };
+        int g = 0;
+        if (i > 0 && ok(cell - si)) g += sgn(p - p_prev);
+        if (i + 1 < sz_i && ok(cell + si)) g -= sgn(p_next - p);
+        if (j > 0 && ok(cell - sj)) g += sgn(p - v[idx - sj]);
+        if (j + 1 < sz_j && ok(cell + sj)) g -= sgn(v[idx + sj] - p);
+        if (k > 0 && ok(cell - 1)) g += sgn(p - v[idx - 1]);
+        if (k + 1 < sz_k && ok(cell + 1)) g -= sgn(v[idx + 1] - p);
+        if (g != 0) grad[idx] += scale * static_cast<float>(g);
+      }
+      p_prev = p;
+      p = p_next;
+    }
+  }
+  if (!kBackward) {
+    __shared__ float s_part[8];
+    acc = warp_sum(acc);
+    if (threadIdx.x == 0) s_part[threadIdx.y] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+      double tot = 0.;
+      for (int w = 0; w < 8; ++w) tot += static_cast<double>(s_part[w]);
+      if (tot != 0.) atomicAdd(sum_out, tot);
+    }
+  }
+}
+
 // ---- Adam ------------------------------------------------------------------------------------------
 // mode 0 plain, 1 masked (skip grad == 0), 2 per-element lr.  Reference :18-22 / :35-39 / :53-57.
 template <typename scalar_t, int kMode>
@@ -285,5 +345,44 @@ extern "C" int pp_cumdist_thres(pp_dtype dtype, const void* dist, float thres, i
         (const scalar_t*)dist, thres, n_rays, n_pts, mask);
   });
   PP_CHECK_LAUNCH("cumdist_thres");
+  return PP_OK;
+}
+
+extern "C" int pp_total_variation_loss(const float* v, const uint8_t* mask, int64_t n_planes, int64_t sz_i,
+                                       int64_t sz_j, int64_t sz_k, double* sum_out, pp_stream_t stream) {
+  PP_REQUIRE(n_planes >= 0 && sz_i >= 0 && sz_j >= 0 && sz_k >= 0, PP_ERR_INVALID_ARG,
+             "total_variation_loss: negative extent");
+  PP_REQUIRE(sum_out, PP_ERR_INVALID_ARG, "total_variation_loss: sum_out is null");
+  cudaStream_t s = as_stream(stream);
+  PP_CHECK_CUDA(cudaMemsetAsync(sum_out, 0, sizeof(double), s));
+  if (n_planes * sz_i * sz_j * sz_k == 0) return PP_OK;
+  PP_REQUIRE(v, PP_ERR_INVALID_ARG, "total_variation_loss: null pointer");
+  const int chunk = 16;
+  const int cpp = (int)((sz_i + chunk - 1) / chunk);
+  PP_REQUIRE(n_planes * cpp <= 65535 && (sz_j + 7) / 8 <= 65535, PP_ERR_TOO_LARGE, "total_variation_loss: too large");
+  const dim3 block(32, 8, 1);
+  const dim3 grid((unsigned)((sz_k + 31) / 32), (unsigned)((sz_j + 7) / 8), (unsigned)(n_planes * cpp));
+  tv_loss_kernel<false><<<grid, block, 0, s>>>(v, mask, (int)sz_i, (int)sz_j, (int)sz_k, chunk, cpp, 0.f, nullptr,
+                                               sum_out);
+  PP_CHECK_LAUNCH("total_variation_loss");
+  return PP_OK;
+}
+
+extern "C" int pp_total_variation_loss_backward(const float* v, const uint8_t* mask, int64_t n_planes, int64_t sz_i,
+                                                int64_t sz_j, int64_t sz_k, float scale, float* grad,
+                                                pp_stream_t stream) {
+  PP_REQUIRE(n_planes >= 0 && sz_i >= 0 && sz_j >= 0 && sz_k >= 0, PP_ERR_INVALID_ARG,
+             "total_variation_loss_backward: negative extent");
+  if (n_planes * sz_i * sz_j * sz_k == 0) return PP_OK;
+  PP_REQUIRE(v && grad, PP_ERR_INVALID_ARG, "total_variation_loss_backward: null pointer");
+  const int chunk = 16;
+  const int cpp = (int)((sz_i + chunk - 1) / chunk);
+  PP_REQUIRE(n_planes * cpp <= 65535 && (sz_j + 7) / 8 <= 65535, PP_ERR_TOO_LARGE,
+             "total_variation_loss_backward: too large");
+  const dim3 block(32, 8, 1);
+  const dim3 grid((unsigned)((sz_k + 31) / 32), (unsigned)((sz_j + 7) / 8), (unsigned)(n_planes * cpp));
+  tv_loss_kernel<true><<<grid, block, 0, as_stream(stream)>>>(v, mask, (int)sz_i, (int)sz_j, (int)sz_k, chunk, cpp,
+                                                             scale, grad, nullptr);
+  PP_CHECK_LAUNCH("total_variation_loss_backward");
   return PP_OK;
 }

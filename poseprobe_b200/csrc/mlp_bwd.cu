@@ -556,12 +556,12 @@ extern "C" int pp_rgbnet_backward_fused(const void* x_packed, int64_t capacity, 
                                         int32_t depth, int32_t width, const float* const* weights,
                                         const float* const* biases, const float* sample_weight,
                                         const int32_t* sample_ray, const float* g_ray, float* grad_weight_out,
-                                        float* grad_feat16, float* const* grad_weights,
+                                        float* grad_feat, int32_t grad_feat_cols, float* const* grad_weights,
                                         float* const* grad_biases, pp_stream_t stream) {
-  PP_REQUIRE(sample_weight && sample_ray && g_ray && grad_weight_out && grad_feat16, PP_ERR_INVALID_ARG,
+  PP_REQUIRE(sample_weight && sample_ray && g_ray && grad_weight_out && grad_feat, PP_ERR_INVALID_ARG,
              "rgbnet_backward_fused: null pointer");
-  MlpFusedIO F = {n_ptr, sample_weight, sample_ray, g_ray, grad_weight_out, 16};
-  return launch_rgbnet_backward(x_packed, nullptr, capacity, d0, depth, width, weights, biases, 1, grad_feat16,
+  MlpFusedIO F = {n_ptr, sample_weight, sample_ray, g_ray, grad_weight_out, grad_feat_cols};
+  return launch_rgbnet_backward(x_packed, nullptr, capacity, d0, depth, width, weights, biases, 1, grad_feat,
                                 grad_weights, grad_biases, nullptr, F, stream);
 }
 

@@ -297,6 +297,26 @@ __global__ void voxurf_ray_loss_kernel(int64_t n_rays, const float* __restrict__
 // ---- backward march -----------------------------------------------------------------------------------------
 // dynamic shared memory per warp: s_alpha[cap], s_slot[cap] (compacted slot of every step, -1 if none),
 // s_tin[cap/32]
+// d loss / d point of one sample through the trilinear interpolation of 4 record channels (voxel units):
+// gp += sum_ch d[ch] * grad_xyz(interp_ch); corner q: bit 0 = +Z, bit 1 = +Y, bit 2 = +X
+__device__ __forceinline__ void spatial_grad4(const Cell& c, const float4 (&v)[8], const float4& d, float (&gp)[3]) {
+  const float fx = c.fx, fy = c.fy, fz = c.fz, gx = c.gx(), gy = c.gy(), gz = c.gz();
+  const float dch[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    float u[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) u[q] = ch == 0 ? v[q].x : ch == 1 ? v[q].y : ch == 2 ? v[q].z : v[q].w;
+    const float dX = ((u[4] - u[0]) * gz + (u[5] - u[1]) * fz) * gy + ((u[6] - u[2]) * gz + (u[7] - u[3]) * fz) * fy;
+    const float dY = ((u[2] - u[0]) * gz + (u[3] - u[1]) * fz) * gx + ((u[6] - u[4]) * gz + (u[7] - u[5]) * fz) * fx;
+    const float dZ = ((u[1] - u[0]) * gy + (u[3] - u[2]) * fy) * gx + ((u[5] - u[4]) * gy + (u[7] - u[6]) * fy) * fx;
+    gp[0] += dch[ch] * dX;
+    gp[1] += dch[ch] * dY;
+    gp[2] += dch[ch] * dZ;
+  }
+}
+
+template <bool kPose>
 __global__ void __launch_bounds__(256, 2)
 voxurf_backward_kernel(pp_dvgo_scene sc, pp_voxurf_cfg cfg, const float* __restrict__ rays_o,
                        const float* __restrict__ rays_d, const float* __restrict__ viewdirs,
@@ -305,7 +325,8 @@ voxurf_backward_kernel(pp_dvgo_scene sc, pp_voxurf_cfg cfg, const float* __restr
                        const int32_t* __restrict__ ray_off, const int32_t* __restrict__ ray_cnt,
                        const int32_t* __restrict__ ray_end, const float* __restrict__ g_ray,
                        float4* __restrict__ g_srec, float4* __restrict__ g_k0rec, unsigned int* __restrict__ queue,
-                       int cap) {
+                       int cap, int dx_pitch, const float4* __restrict__ srec, const float4* __restrict__ k0rec,
+                       float* __restrict__ grad_rays, float* __restrict__ grad_viewdirs) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int per_warp = 2 * cap + cap / kWarp;
@@ -319,8 +340,14 @@ voxurf_backward_kernel(pp_dvgo_scene sc, pp_voxurf_cfg cfg, const float* __restr
     const int64_t r = __shfl_sync(kFull, ticket, 0);
     if (r >= n_rays) break;
     const int cnt = ray_cnt[r];
-    if (cnt == 0) continue;
+    if (cnt == 0) {
+      if (kPose && lane < 9) {
+        if (lane < 6) grad_rays[6 * r + lane] = 0.f; else grad_viewdirs[3 * r + lane - 6] = 0.f;
+      }
+      continue;
+    }
     const int off = ray_off[r], end = ray_end[r];
+    float G0[3] = {0.f, 0.f, 0.f}, G1[3] = {0.f, 0.f, 0.f}, GV[3] = {0.f, 0.f, 0.f};
     const Ray ray = setup_ray(sc, rays_o, rays_d, r);
     const float jit = jitter ? jitter[r] : 0.f;
     float v[3], g[3];
@@ -384,7 +411,7 @@ voxurf_backward_kernel(pp_dvgo_scene sc, pp_voxurf_cfg cfg, const float* __restr
       float g_sdf, g_tc;
       neus_backward(neus_terms(rc.x, gg, v, sc.stepdist, cfg.inv_s), d_alpha, sc.stepdist, cfg.inv_s, g_sdf, g_tc);
       // input-gradient columns of the MLP: 12 feature channels, 3 normal components
-      const float4* dxp = reinterpret_cast<const float4*>(dx16 + (int64_t)slot * kDxCols);
+      const float4* dxp = reinterpret_cast<const float4*>(dx16 + (int64_t)slot * dx_pitch);
       const float4 d0 = dxp[0], d1 = dxp[1], d2 = dxp[2], d3 = dxp[3];
       // normal = g / (|g| + 1e-5): d g_b = dn_b / (r + e) - g_b (g . dn) / (r (r + e)^2)
       const float rn = sqrtf(gg[0] * gg[0] + gg[1] * gg[1] + gg[2] * gg[2]);
@@ -409,6 +436,90 @@ voxurf_backward_kernel(pp_dvgo_scene sc, pp_voxurf_cfg cfg, const float* __restr
         red_add_v4(kdst, wq * d0.x, wq * d0.y, wq * d0.z, wq * d0.w);
         red_add_v4(kdst + 1, wq * d1.x, wq * d1.y, wq * d1.z, wq * d1.w);
         red_add_v4(kdst + 2, wq * d2.x, wq * d2.y, wq * d2.z, wq * d2.w);
+      }
+      if (kPose) {
+        // d loss / d point: through the SDF record interpolation, the 12 feature channels, the positional
+        // encoding columns of the MLP input; d loss / d viewdirs: NeuS cosine and the view columns
+        float gp[3] = {0.f, 0.f, 0.f};
+        {
+          float4 q8[8];
+          gather8(srec, c, q8);
+          spatial_grad4(c, q8, ds, gp);
+        }
+#pragma unroll
+        for (int grp = 0; grp < 3; ++grp) {
+          float4 q8[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) q8[q] = __ldg(k0rec + (int64_t)corner_off(c, q) * 3 + grp);
+          spatial_grad4(c, q8, grp == 0 ? d0 : grp == 1 ? d1 : d2, gp);
+        }
+        gp[0] *= (sc.sx - 1) / (sc.xyz_max[0] - sc.xyz_min[0]);
+        gp[1] *= (sc.sy - 1) / (sc.xyz_max[1] - sc.xyz_min[1]);
+        gp[2] *= (sc.sz - 1) / (sc.xyz_max[2] - sc.xyz_min[2]);
+        const float* dxr = dx16 + (int64_t)slot * dx_pitch;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const float ext = sc.xyz_max[a] - sc.xyz_min[a];
+          const float u = (p[a] - sc.xyz_min[a]) / ext;
+          float du = dxr[kColXyz + a];
+#pragma unroll
+          for (int k = 0; k < 5; ++k) {
+            if (k < cfg.pos_pe) {
+              float sn, cs;
+              const float f = static_cast<float>(1 << k);
+              __sincosf(u * f, &sn, &cs);
+              du += cfg.pe_w_pos[k] * f * (dxr[kColXyz + 3 + a * 5 + k] * cs - dxr[kColXyz + 18 + a * 5 + k] * sn);
+            }
+          }
+          gp[a] += du / ext;
+        }
+        const float sdist = sc.stepdist * (static_cast<float>(i) + jit);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          G0[k] += gp[k];
+          G1[k] += gp[k] * sdist;
+          float gv = g_tc * gg[k] + dxr[kColView + k];
+          if (cfg.view_pe > 0)
+            gv += cfg.pe_w_view[0] * (dxr[kColView + 3 + k] * __cosf(v[k]) - dxr[kColView + 6 + k] * __sinf(v[k]));
+          GV[k] += gv;
+        }
+      }
+    }
+    if (kPose) {
+      // point_i = o + d*t_min + (d/|d|) * s_i; t_min is locally constant in (o, d) except through the entering slab
+      // (same chain as the coarse kernel, dvgo_fused.cu)
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        G0[k] = warp_sum(G0[k]);
+        G1[k] = warp_sum(G1[k]);
+        GV[k] = warp_sum(GV[k]);
+      }
+      if (lane == 0) {
+        float go[3] = {G0[0], G0[1], G0[2]};
+        float gd[3] = {G0[0] * ray.t_min, G0[1] * ray.t_min, G0[2] * ray.t_min};
+        int axis = -1;
+        float best = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const float vv = (ray.d[k] == 0.f) ? 1e-6f : ray.d[k];
+          const float a = (sc.xyz_max[k] - ray.o[k]) / vv;
+          const float b = (sc.xyz_min[k] - ray.o[k]) / vv;
+          const float m = fminf(a, b);
+          if (m > best) { best = m; axis = k; }
+        }
+        if (best == ray.t_min && ray.d[axis] != 0.f) {   // not clamped by near / far
+          const float gdot = G0[0] * ray.d[0] + G0[1] * ray.d[1] + G0[2] * ray.d[2];
+          go[axis] += gdot * (-1.f / ray.d[axis]);
+          gd[axis] += gdot * (-ray.t_min / ray.d[axis]);
+        }
+        const float inv = 1.f / ray.rnorm;
+        const float dotg = (G1[0] * ray.d[0] + G1[1] * ray.d[1] + G1[2] * ray.d[2]) * inv * inv * inv;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          grad_rays[6 * r + k] = go[k];
+          grad_rays[6 * r + 3 + k] = gd[k] + G1[k] * inv - ray.d[k] * dotg;
+          grad_viewdirs[3 * r + k] = GV[k];
+        }
       }
     }
     __syncwarp();
@@ -596,10 +707,12 @@ extern "C" int pp_voxurf_ray_loss(int64_t n_rays, const float* rgb_acc, const fl
 
 extern "C" int pp_voxurf_backward(const pp_dvgo_scene* scene, const pp_voxurf_cfg* cfg, const float* rays_o,
                                   const float* rays_d, const float* viewdirs, const float* jitter, int64_t n_rays,
-                                  const void* sample_rec, const float* grad_weight, const float* grad_feat16,
-                                  const int32_t* ray_off, const int32_t* ray_cnt, const int32_t* ray_end,
-                                  const float* g_ray, void* grad_sdf_records, void* grad_k0_records,
-                                  pp_stream_t stream) {
+                                  const void* sample_rec, const float* grad_weight, const float* grad_feat,
+                                  int32_t grad_feat_cols, const int32_t* ray_off, const int32_t* ray_cnt,
+                                  const int32_t* ray_end, const float* g_ray, void* grad_sdf_records,
+                                  void* grad_k0_records, const void* sdf_records, const void* k0_records,
+                                  float* grad_rays, float* grad_viewdirs, pp_stream_t stream) {
+  const float* grad_feat16 = grad_feat;
   const int rc = check_vox_scene(scene, cfg, "voxurf_backward");
   if (rc != PP_OK) return rc;
   PP_REQUIRE(n_rays >= 0, PP_ERR_INVALID_ARG, "voxurf_backward: n_rays < 0");
@@ -607,21 +720,29 @@ extern "C" int pp_voxurf_backward(const pp_dvgo_scene* scene, const pp_voxurf_cf
   PP_REQUIRE(rays_o && rays_d && viewdirs && sample_rec && grad_weight && grad_feat16 && ray_off && ray_cnt &&
                  ray_end && g_ray && grad_sdf_records && grad_k0_records,
              PP_ERR_INVALID_ARG, "voxurf_backward: null pointer");
+  const bool pose = grad_rays != nullptr;
+  PP_REQUIRE(grad_feat_cols == kDxCols || grad_feat_cols == kFeatCols, PP_ERR_INVALID_ARG,
+             "voxurf_backward: grad_feat_cols must be 16 or 64");
+  PP_REQUIRE(!pose || (grad_feat_cols == kFeatCols && sdf_records && k0_records && grad_viewdirs),
+             PP_ERR_INVALID_ARG,
+             "voxurf_backward: the pose gradient needs 64 gradient columns, the records and grad_viewdirs");
   cudaStream_t s = as_stream(stream);
   const int cap = vox_step_capacity(scene);
   const int warps = 8;
   const size_t smem = (size_t)warps * (2 * cap + cap / kWarp) * sizeof(float);
-  PP_CHECK_CUDA(cudaFuncSetAttribute(voxurf_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  auto kernel = pose ? voxurf_backward_kernel<true> : voxurf_backward_kernel<false>;
+  PP_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int qrc;
   unsigned int* queue = next_queue(s, &qrc);
   if (qrc != PP_OK) return qrc;
   int per_sm = 0;
-  PP_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, voxurf_backward_kernel, warps * 32, smem));
+  PP_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem));
   if (per_sm < 1) per_sm = 1;
   const int64_t blocks = min64((n_rays + warps - 1) / warps, (int64_t)sm_count() * per_sm);
-  voxurf_backward_kernel<<<(unsigned)blocks, warps * 32, smem, s>>>(
+  kernel<<<(unsigned)blocks, warps * 32, smem, s>>>(
       *scene, *cfg, rays_o, rays_d, viewdirs, jitter, n_rays, (const float4*)sample_rec, grad_weight, grad_feat16,
-      ray_off, ray_cnt, ray_end, g_ray, (float4*)grad_sdf_records, (float4*)grad_k0_records, queue, cap);
+      ray_off, ray_cnt, ray_end, g_ray, (float4*)grad_sdf_records, (float4*)grad_k0_records, queue, cap,
+      grad_feat_cols, (const float4*)sdf_records, (const float4*)k0_records, grad_rays, grad_viewdirs);
   PP_CHECK_LAUNCH("voxurf_backward");
   return PP_OK;
 }

@@ -192,6 +192,46 @@ def neus_alpha(viewdirs, ray_id, dist, sdf, gradients, inv_s):
     return _NeusAlpha.apply(sdf, gradients, viewdirs, ray_id, float(dist), float(inv_s))
 
 
+class _TotalVariation(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, v, mask):
+        vc = v.contiguous()
+        _, c, x, y, z = vc.shape
+        total = torch.zeros(1, dtype=torch.float64, device=v.device)
+        mk = None
+        if mask is not None:
+            mk = mask.reshape(-1, x, y, z)[0].to(torch.uint8).contiguous()
+        with torch.cuda.device(v.device):
+            check(lib.pp_total_variation_loss(ptr(vc), ptr(mk), c, x, y, z, ptr(total), stream()),
+                  "total_variation_loss")
+        count = float(vc.numel()) if mask is None else float(c) * float(mk.sum())
+        ctx.save_for_backward(vc)
+        ctx.mask, ctx.count = mk, count
+        return (total / 3.0 / count).float().reshape(())
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        (vc,) = ctx.saved_tensors
+        _, c, x, y, z = vc.shape
+        grad = torch.zeros_like(vc)
+        scale = float(grad_out) / 3.0 / ctx.count
+        with torch.cuda.device(vc.device):
+            check(lib.pp_total_variation_loss_backward(ptr(vc), ptr(ctx.mask), c, x, y, z, scale, ptr(grad),
+                                                       stream()), "total_variation_loss_backward")
+        return grad, None
+
+
+def total_variation(v, mask=None):
+    """`total_variation(v, mask)` of the reference (lib/voxurf_coarse.py:1298-1313): v [1,C,X,Y,Z] fp32, mask
+    None or a bool grid broadcast over the channels (nonempty_mask); differentiable in v."""
+    if not v.is_cuda:
+        raise RuntimeError("total_variation: v must be a CUDA tensor (no CPU fallback)")
+    if v.dtype != torch.float32 or v.dim() != 5 or v.shape[0] != 1:
+        raise RuntimeError("total_variation expects a float32 [1,C,X,Y,Z] grid")
+    return _TotalVariation.apply(v, mask)
+
+
 def rgbnet_forward(x, weights, biases, sigmoid=True):
     """Colour MLP forward on the tcgen05 tensor cores (no autograd; the render / inference path).
 

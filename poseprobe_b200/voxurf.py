@@ -77,7 +77,7 @@ class FusedVoxurf:
     def __init__(self, sdf, k0, rgbnet_weights, rgbnet_biases, xyz_min, xyz_max, stepsize=0.5, near=0.2, far=1e9,
                  bg=0.0, s_val=0.05, sdf_alpha=None, sdf_beta=None, posbase_pe=5, viewbase_pe=1, barf_c2f=None,
                  lr_sdf=0.1, lr_k0=0.1, lr_rgbnet=1e-3, betas=(0.9, 0.99), eps=1e-8, w_rgb=1.0,
-                 samples_per_ray_cap=None):
+                 samples_per_ray_cap=None, pose_grad=False):
         _need_cuda(sdf, "sdf")
         _need_cuda(k0, "k0")
         self.device = sdf.device
@@ -145,6 +145,8 @@ class FusedVoxurf:
         self.step = 0
         self.loss_buf = torch.zeros(2, dtype=torch.float32, device=dev)
         self._cap_per_ray = samples_per_ray_cap
+        self.pose_grad = bool(pose_grad)     # also emit d loss / d (rays_o, rays_d, viewdirs) (SE3 refinement)
+        self.dx_cols = FEAT_COLS if self.pose_grad else DX_COLS
         self._bufs = None
         self._arr = lambda ts: (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
         self.rebuild_records()
@@ -191,7 +193,9 @@ class FusedVoxurf:
                  "rid": torch.empty(cap, dtype=torch.int32, device=dev),
                  "rec": torch.empty((cap, 4), dtype=torch.float32, device=dev),
                  "gw": torch.empty(cap, dtype=torch.float32, device=dev),
-                 "dx": torch.empty((cap, DX_COLS), dtype=torch.float32, device=dev),
+                 "dx": torch.empty((cap, self.dx_cols), dtype=torch.float32, device=dev),
+                 "grad_rays": torch.zeros((n_rays, 6), dtype=torch.float32, device=dev) if self.pose_grad else None,
+                 "grad_view": torch.zeros((n_rays, 3), dtype=torch.float32, device=dev) if self.pose_grad else None,
                  "ray_off": torch.empty(n_rays, dtype=torch.int32, device=dev),
                  "ray_cnt": torch.empty(n_rays, dtype=torch.int32, device=dev),
                  "ray_end": torch.empty(n_rays, dtype=torch.int32, device=dev),
@@ -256,13 +260,31 @@ class FusedVoxurf:
             check(lib.pp_rgbnet_backward_fused(ptr(b["feat"]), b["cap"], ptr(b["counter"]), self.d0, self.depth, 128,
                                                self._arr(self.weights), self._arr(self.biases), ptr(b["w"]),
                                                ptr(b["rid"]), ptr(b["g_ray"]), ptr(b["gw"]), ptr(b["dx"]),
-                                               self._arr(self.g_w), self._arr(self.g_b), stream()),
+                                               self.dx_cols, self._arr(self.g_w), self._arr(self.g_b), stream()),
                   "rgbnet_backward_fused")
             check(lib.pp_voxurf_backward(ctypes.byref(self.scene), ctypes.byref(self.cfg), ptr(rays_o), ptr(rays_d),
                                          ptr(viewdirs), ptr(jitter), n, ptr(b["rec"]), ptr(b["gw"]), ptr(b["dx"]),
-                                         ptr(b["ray_off"]), ptr(b["ray_cnt"]), ptr(b["ray_end"]), ptr(b["g_ray"]),
-                                         ptr(self.g_srec), ptr(self.g_k0rec), stream()), "voxurf_backward")
+                                         self.dx_cols, ptr(b["ray_off"]), ptr(b["ray_cnt"]), ptr(b["ray_end"]),
+                                         ptr(b["g_ray"]), ptr(self.g_srec), ptr(self.g_k0rec), ptr(self.srec),
+                                         ptr(self.k0rec), ptr(b["grad_rays"]), ptr(b["grad_view"]), stream()),
+                  "voxurf_backward")
         return b["rgb"][:n]
+
+    def ray_gradients(self, rays_d=None):
+        """d loss / d (rays_o | rays_d) [N,6] and d loss / d viewdirs [N,3] of the last backward (pose_grad=True).
+        With rays_d given, the viewdirs gradient is folded through viewdirs = rays_d / |rays_d|
+        (voxurf_coarse.py:1365) into the rays_d half, ready for pp_pose_grad_reduce / camera.pose_grad."""
+        if not self.pose_grad:
+            raise RuntimeError("FusedVoxurf was built with pose_grad=False")
+        b = self._bufs
+        n = b["n_rays"]
+        g_rays, g_view = b["grad_rays"][:n].clone(), b["grad_view"][:n].clone()
+        if rays_d is None:
+            return g_rays, g_view
+        nrm = rays_d.norm(dim=-1, keepdim=True)
+        v = rays_d / nrm
+        g_rays[:, 3:] += (g_view - v * (v * g_view).sum(-1, keepdim=True)) / nrm
+        return g_rays
 
     def grid_gradients(self):
         """(d loss / d sdf [1,1,X,Y,Z], d loss / d k0 [1,12,X,Y,Z], [dW], [db]) of the accumulated gradients, in

@@ -500,3 +500,24 @@ def test_error_behaviour(pp):
         ru.raw2alpha(torch.rand(4).cuda().half(), 0.0, 0.5)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         pp.ops.trilinear(torch.zeros(1, 1, 2, 2, 2), torch.zeros(1, 3), torch.zeros(3), torch.ones(3))
+
+
+@pytest.mark.parametrize("masked", [False, True])
+def test_total_variation_loss_python_side(cuda, masked):
+    """ops.total_variation == the reference's Python `total_variation` (voxurf_coarse.py:1298-1313) and its autograd."""
+    from oracle import oracle
+    from poseprobe_b200 import ops
+    torch.manual_seed(3)
+    v = torch.randn(1, 5, 19, 33, 21)
+    v[0, 0, 3:6, 4:9] = 0.25                       # flat region: |x|' = 0 at 0, like torch.abs
+    mask = None
+    if masked:
+        mask = (torch.rand(1, 1, 19, 33, 21) > 0.3).repeat(1, 5, 1, 1, 1)
+    vr = v.clone().requires_grad_(True)
+    want = oracle.total_variation(vr, mask)
+    want.backward()
+    vc = v.cuda().requires_grad_(True)
+    got = ops.total_variation(vc, mask.cuda() if masked else None)
+    (2.5 * got).backward()
+    torch.testing.assert_close(got.detach().cpu(), want.detach(), rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(vc.grad.cpu(), 2.5 * vr.grad, rtol=1e-5, atol=1e-9)

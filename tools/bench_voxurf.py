@@ -72,12 +72,12 @@ def main():
                                  ptr(eng.loss_buf), stream()), "loss")
     t_bwd_mlp = timeit(lambda: check(lib.pp_rgbnet_backward_fused(
         ptr(b["feat"]), b["cap"], ptr(b["counter"]), eng.d0, eng.depth, 128, eng._arr(eng.weights), eng._arr(eng.biases),
-        ptr(b["w"]), ptr(b["rid"]), ptr(b["g_ray"]), ptr(b["gw"]), ptr(b["dx"]), eng._arr(eng.g_w), eng._arr(eng.g_b),
+        ptr(b["w"]), ptr(b["rid"]), ptr(b["g_ray"]), ptr(b["gw"]), ptr(b["dx"]), 16, eng._arr(eng.g_w), eng._arr(eng.g_b),
         stream()), "bwd"))
     t_back = timeit(lambda: check(lib.pp_voxurf_backward(
         ctypes.byref(eng.scene), ctypes.byref(eng.cfg), ptr(o), ptr(d), ptr(v), None, N, ptr(b["rec"]), ptr(b["gw"]),
-        ptr(b["dx"]), ptr(b["ray_off"]), ptr(b["ray_cnt"]), ptr(b["ray_end"]), ptr(b["g_ray"]), ptr(eng.g_srec),
-        ptr(eng.g_k0rec), stream()), "back"))
+        ptr(b["dx"]), 16, ptr(b["ray_off"]), ptr(b["ray_cnt"]), ptr(b["ray_end"]), ptr(b["g_ray"]), ptr(eng.g_srec),
+        ptr(eng.g_k0rec), None, None, None, None, stream()), "back"))
     t_opt = timeit(eng.optimizer_step)
     flops = 2.0 * m * (64 * 128 + 128 * 128 * 2 + 128 * 16) * 4     # fwd + recompute + 2x bwd, padded shapes
     line = {"workload": "Voxurf SDF fine stage (BASELINE configs[2], one rank): %d^3 sdf + 12-ch k0, rgbnet 57-128x3-3, "
