@@ -16,11 +16,13 @@
 //     converts to bf16 and writes the row straight back into the A tile for the next layer; the last layer
 //     applies the sigmoid and writes [M,3].
 // Activations never touch HBM: traffic is d0*4 B in and 12 B out per sample.
+#include <stdlib.h>
+
 #include "mlp_common.cuh"
 
 namespace pp {
 
-constexpr int kFwdThreads = 512;   // two independent 8-warp pipelines per CTA
+constexpr int kFwdThreads = 512;   // kPipes independent pipelines of 16 / kPipes warps per CTA
 constexpr int kFwdTile = 128;
 
 struct MlpParams {
@@ -31,27 +33,32 @@ struct MlpParams {
   int k0p;        // input row width of the packed bf16 input: 64 or 128
 };
 
+template <int kThreadsPerPipe>
 __device__ __forceinline__ void group_sync(int g) {
-  asm volatile("bar.sync %0, 256;" ::"r"(g + 1) : "memory");
+  asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(kThreadsPerPipe) : "memory");
 }
 
-// Two pipelines (warps 0-7 and 8-15) share the weights in shared memory; each owns an activation tile, a
-// TMEM accumulator and an mbarrier and walks its own tiles.  While one pipeline's warps run an epilogue
-// (TMEM -> bias/ReLU -> bf16 -> shared memory) or wait for their next input tile, the other pipeline's MMAs
-// occupy the tensor pipe, so neither the MMA latency nor the load latency is exposed.
-// shared memory map: A tile of pipeline 0, A tile of pipeline 1 (128 x 128 bf16 each), weights, biases,
-// 2 mbarriers, tmem base.
+// kPipes pipelines (4 with 4 warps each when the weights leave room for four activation tiles, else 2 with 8
+// warps) share the weights in shared memory; each owns an activation tile, a 128-column TMEM accumulator (the
+// logits alias its first 16 columns) and an mbarrier and walks its own tiles.  The epilogue of a 128 x 128 fp32
+// accumulator is bounded by the TMEM read port (64 B/clk: 1024 cycles against 544 cycles of MMA for the layer), so
+// the goal is to keep tcgen05.ld busy: while one pipeline waits (MMA latency, input tile, barrier) the others
+// drain their accumulators.
+// shared memory map: kPipes A tiles (128 x 128 bf16 each), weights, biases, kPipes mbarriers, tmem base.
+template <int kPipes>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 rgbnet_forward_kernel(MlpParams P, const __nv_bfloat16* __restrict__ x, int64_t M, int apply_sigmoid,
                       float* __restrict__ out, const float* __restrict__ wgt, const int32_t* __restrict__ ray_id,
                       float* __restrict__ rgb_marched, const int32_t* __restrict__ n_ptr) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if (n_ptr) M = min64(M, static_cast<int64_t>(*n_ptr));   // row count produced on the device (compacted samples)
-  const int tid = threadIdx.x, g = tid >> 8, gt = tid & 255, warp = gt >> 5, lane = tid & 31;
+  constexpr int kPipeThreads = kFwdThreads / kPipes;       // 256 or 128
+  constexpr int kColsPerThread = kMlpWidth / (kPipeThreads / kFwdTile);   // 64 or 128 accumulator columns
+  const int tid = threadIdx.x, g = tid / kPipeThreads, gt = tid % kPipeThreads, warp = gt >> 5, lane = tid & 31;
   const int L = P.depth, k0p = P.k0p;
   const int row = (warp & 3) * 32 + lane, half = warp >> 2;
   uint8_t* sA = smem + g * (kFwdTile * kMlpWidth * 2);
-  uint32_t off = 2 * kFwdTile * kMlpWidth * 2;
+  uint32_t off = kPipes * kFwdTile * kMlpWidth * 2;
   uint8_t* sW[kMlpMaxDepth];
   for (int l = 0; l < L; ++l) {
     sW[l] = smem + off;
@@ -94,15 +101,14 @@ rgbnet_forward_kernel(MlpParams P, const __nv_bfloat16* __restrict__ x, int64_t 
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-    mbar_init(smem_u32(sBar), 1);
-    mbar_init(smem_u32(sBar + 1), 1);
+    for (int q = 0; q < kPipes; ++q) mbar_init(smem_u32(sBar + q), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *sTmem + g * 256;         // this pipeline's accumulator: [0,128) hidden, [128,144) logits
+  const uint32_t tmem = *sTmem + g * kMlpWidth;   // this pipeline's accumulator: 128 columns, logits in the first 16
   const uint32_t bar = smem_u32(sBar + g);
   uint32_t phase = 0;
   const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
@@ -110,10 +116,10 @@ rgbnet_forward_kernel(MlpParams P, const __nv_bfloat16* __restrict__ x, int64_t 
   const int chunks_per_row = k0p >> 3;
 
   const int64_t n_tiles = (M + kFwdTile - 1) / kFwdTile;
-  const int64_t tile_stride = (int64_t)gridDim.x * 2;
+  const int64_t tile_stride = (int64_t)gridDim.x * kPipes;
   auto stage = [&](int64_t tile) {   // request a tile of packed rows straight into the A buffer (UMMA layout)
     const uint32_t base = smem_u32(sA);
-    for (int id = gt; id < kFwdTile * chunks_per_row; id += 256) {
+    for (int id = gt; id < kFwdTile * chunks_per_row; id += kPipeThreads) {
       const int r = id / chunks_per_row, c8 = id - r * chunks_per_row;
       const int64_t grow = tile * kFwdTile + r;
       const bool ok = grow < M;
@@ -122,19 +128,19 @@ rgbnet_forward_kernel(MlpParams P, const __nv_bfloat16* __restrict__ x, int64_t 
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u) : "memory");
     }
   };
-  int64_t tile = (int64_t)blockIdx.x * 2 + g;
+  int64_t tile = (int64_t)blockIdx.x * kPipes + g;
   if (tile < n_tiles) stage(tile);
   for (; tile < n_tiles; tile += tile_stride) {
     const int64_t grow = tile * kFwdTile + row;
     const bool valid = grow < M;
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
     fence_async_smem();
-    group_sync(g);
+    group_sync<kPipeThreads>(g);
 
     for (int l = 0; l < L; ++l) {
       const bool last = (l == L - 1);
       const int K = (l == 0) ? k0p : kMlpWidth;
-      const uint32_t d_tmem = tmem + (last ? kMlpWidth : 0);
+      const uint32_t d_tmem = tmem;
       if (gt == 0) {
         tc_fence_after();
         const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sW[l]);
@@ -148,8 +154,8 @@ rgbnet_forward_kernel(MlpParams P, const __nv_bfloat16* __restrict__ x, int64_t 
       if (!last) {
         const float* bias = sBias + l * kMlpWidth;
 #pragma unroll 1
-        for (int i = 0; i < 2; ++i) {
-          const int c0 = half * 64 + i * 32;
+        for (int i = 0; i < kColsPerThread / 32; ++i) {
+          const int c0 = half * kColsPerThread + i * 32;
           uint32_t r[32];
           tmem_ld32_nowait(d_tmem + lane_base + c0, r);
           const float4* b4 = reinterpret_cast<const float4*>(bias + c0);
@@ -164,7 +170,7 @@ rgbnet_forward_kernel(MlpParams P, const __nv_bfloat16* __restrict__ x, int64_t 
         }
         tc_fence_before();
         fence_async_smem();
-        group_sync(g);
+        group_sync<kPipeThreads>(g);
       } else {
         // the A tile is free: the next tile's rows start moving while the outputs are written
         if (tile + tile_stride < n_tiles) stage(tile + tile_stride);
@@ -235,7 +241,7 @@ extern "C" int pp_rgbnet_forward_packed(const void* x_packed, int64_t n_pts, int
   P.depth = depth;
   P.d0 = d0;
   P.k0p = d0 <= 64 ? 64 : 128;
-  size_t smem = (size_t)2 * kFwdTile * kMlpWidth * 2;
+  size_t smem = 0;
   for (int l = 0; l < kMlpMaxDepth; ++l) {
     P.w[l] = l < depth ? weights[l] : nullptr;
     P.b[l] = l < depth ? biases[l] : nullptr;
@@ -247,12 +253,23 @@ extern "C" int pp_rgbnet_forward_packed(const void* x_packed, int64_t n_pts, int
     }
   }
   smem += (size_t)depth * kMlpWidth * 4 + 64;
+  const size_t tile_bytes = (size_t)kFwdTile * kMlpWidth * 2;
+  const char* pe = getenv("PP_MLP_PIPES");
+  int pipes = (smem + 4 * tile_bytes <= 227 * 1024) ? 4 : 2;
+  if (pe && atoi(pe) == 2) pipes = 2;
+  smem += pipes * tile_bytes;
   PP_REQUIRE(smem <= 227 * 1024, PP_ERR_UNSUPPORTED, "rgbnet_forward: %zu B of shared memory needed", smem);
-  PP_CHECK_CUDA(cudaFuncSetAttribute(rgbnet_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t n_tiles = (n_pts + kFwdTile - 1) / kFwdTile;
-  const int blocks = (int)min64((n_tiles + 1) / 2, sm_count());
-  rgbnet_forward_kernel<<<blocks, kFwdThreads, smem, as_stream(stream)>>>(
-      P, (const __nv_bfloat16*)x_packed, n_pts, apply_sigmoid, out, sample_weight, ray_id, rgb_marched, n_ptr);
+  const int blocks = (int)min64((n_tiles + pipes - 1) / pipes, sm_count());
+  if (pipes == 4) {
+    PP_CHECK_CUDA(cudaFuncSetAttribute(rgbnet_forward_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rgbnet_forward_kernel<4><<<blocks, kFwdThreads, smem, as_stream(stream)>>>(
+        P, (const __nv_bfloat16*)x_packed, n_pts, apply_sigmoid, out, sample_weight, ray_id, rgb_marched, n_ptr);
+  } else {
+    PP_CHECK_CUDA(cudaFuncSetAttribute(rgbnet_forward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rgbnet_forward_kernel<2><<<blocks, kFwdThreads, smem, as_stream(stream)>>>(
+        P, (const __nv_bfloat16*)x_packed, n_pts, apply_sigmoid, out, sample_weight, ray_id, rgb_marched, n_ptr);
+  }
   PP_CHECK_LAUNCH("rgbnet_forward");
   return PP_OK;
 }

@@ -672,8 +672,12 @@ extern "C" int pp_voxurf_march_features(const pp_dvgo_scene* scene, const pp_vox
              PP_ERR_INVALID_ARG, "voxurf_march_features: null pointer");
   cudaStream_t s = as_stream(stream);
   const int cap = vox_step_capacity(scene);
-  const int warps = 8;
-  const size_t smem = (size_t)warps * cap * (sizeof(float4) + sizeof(float));
+  int warps = 8;   // fewer warps per block when a ray's staging (20 B per step) is large (256^3 and up)
+  size_t smem = (size_t)warps * cap * (sizeof(float4) + sizeof(float));
+  while (smem > 100 * 1024 && warps > 1) {
+    warps /= 2;
+    smem = (size_t)warps * cap * (sizeof(float4) + sizeof(float));
+  }
   PP_REQUIRE(smem <= 100 * 1024, PP_ERR_UNSUPPORTED,
              "voxurf_march_features: %d steps per ray exceed the shared-memory staging capacity", cap);
   PP_CHECK_CUDA(cudaFuncSetAttribute(voxurf_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
