@@ -143,11 +143,15 @@ PP_API int pp_voxel_adam_exchange(void* const* vox_ptrs, void* const* grad_ptrs,
 /* NVSwitch (NVLS) variant of pp_voxel_adam_exchange: vox_mc / grad_mc are MULTICAST addresses bound to every
  * rank's parameter / gradient records (e.g. torch symmetric memory's multicast_ptr).  The gradient slice is
  * reduced in the switch (multimem.ld_reduce.add.v4.f32) and the updated records are replicated by the switch
- * (multimem.st.v4.f32): per GPU and link direction (w+1)/w of the record array instead of 2(w-1)/w. */
+ * (multimem.st.v4.f32): per GPU and link direction (w+1)/w of the record array instead of 2(w-1)/w.
+ * epoch != 0 fuses the "all gradients complete" barrier of pp_peer_sync into the kernel's prologue (sync_ptrs,
+ * payload_in, payload_sum_out as for pp_peer_sync); epoch == 0: the caller synchronised the ranks itself. */
 PP_API int pp_voxel_adam_exchange_mc(const void* vox_local, void* vox_mc, const void* grad_mc,
                                      void* exp_avg, void* exp_avg_sq, int64_t n_voxels, int32_t world,
                                      int32_t rank, int32_t step, float beta1, float beta2,
-                                     float lr_density, float lr_k0, float eps, pp_stream_t stream);
+                                     float lr_density, float lr_k0, float eps, void* const* sync_ptrs,
+                                     uint32_t epoch, const float* payload_in, float* payload_sum_out,
+                                     pp_stream_t stream);
 
 /* ---- Voxurf fine stage (SDF grid + 12-channel feature grid + rgbnet), fused -------------------------------
  * Reference: Voxurf.forward, non-deform branch (lib/voxurf_coarse.py:922-1091).  A train step is

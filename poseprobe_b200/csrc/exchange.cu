@@ -19,6 +19,44 @@ struct PeerPtrs {
   const float4* grad[kMaxWorld];
 };
 
+struct SyncBlock {
+  unsigned int flags[kMaxWorld];
+  float payload[kMaxWorld][2];
+  unsigned int timed_out;
+};
+struct SyncPtrs {
+  SyncBlock* blk[kMaxWorld];
+};
+
+// announce epoch E to every peer (optionally with a 2-float payload) and wait until every peer announced it
+// (release / acquire at system scope on flags in peer memory).  Executed by threads r < world of a warp.
+__device__ __forceinline__ void peer_announce_and_wait(const SyncPtrs& sp, int world, int me, unsigned int epoch,
+                                                       const float* payload_in, bool announce) {
+  const int r = threadIdx.x;
+  SyncBlock* mine = sp.blk[me];
+  if (r < world) {
+    if (announce) {
+      SyncBlock* peer = sp.blk[r];
+      if (payload_in) {
+        peer->payload[me][0] = payload_in[0];
+        peer->payload[me][1] = payload_in[1];
+      }
+      __threadfence_system();
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&peer->flags[me]), "r"(epoch) : "memory");
+    }
+    const long long t0 = clock64();
+    for (;;) {
+      unsigned int v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(&mine->flags[r]) : "memory");
+      if ((int)(v - epoch) >= 0) break;
+      if (clock64() - t0 > 20000000000LL) {   // ~10 s: a peer died; do not hang the device
+        mine->timed_out = 1;
+        break;
+      }
+    }
+  }
+}
+
 __device__ __forceinline__ void adam_elem_x(float& p, float g, float& m, float& v, float step_size,
                                             float b1, float b2, float eps) {
   if (g == 0.f) return;   // masked_adam_upd (adam_upd_kernel.cu:35)
@@ -118,13 +156,31 @@ __device__ __forceinline__ void mc_st(float4* mc_addr, const float4& v) {
                : "memory");
 }
 
+template <int kDepth>
 __global__ void __launch_bounds__(kXchgThreads)
 voxel_adam_exchange_mc_kernel(const float4* __restrict__ vox_local, float4* vox_mc, const float4* grad_mc,
                               float4* __restrict__ m4, float4* __restrict__ v4, int64_t begin, int64_t end,
-                              float ss_density, float ss_k0, float b1, float b2, float eps) {
+                              float ss_density, float ss_k0, float b1, float b2, float eps, SyncPtrs sp, int world,
+                              int me, unsigned int epoch, const float* __restrict__ payload_in,
+                              float* __restrict__ payload_sum) {
+  // optional fused "all gradients complete" barrier: block 0 announces, every block waits for all peers before
+  // its first in-switch reduction (saves the separate one-warp barrier launch in front of this kernel)
+  if (epoch != 0u) {
+    if (threadIdx.x < 32) peer_announce_and_wait(sp, world, me, epoch, payload_in, blockIdx.x == 0);
+    __syncthreads();
+    if (payload_sum && blockIdx.x == 0 && threadIdx.x == 0) {
+      const SyncBlock* mine = sp.blk[me];
+      float a = 0.f, b = 0.f;
+      for (int q = 0; q < world; ++q) {
+        a += mine->payload[q][0];
+        b += mine->payload[q][1];
+      }
+      payload_sum[0] = a;
+      payload_sum[1] = b;
+    }
+  }
   // same software pipeline as the peer-load variant: the in-switch reductions of the next records are in
   // flight (up-link: every GPU's contribution) while this record's multicast store goes out (down-link)
-  constexpr int kDepth = 3;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t first = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -173,40 +229,12 @@ voxel_adam_exchange_mc_kernel(const float4* __restrict__ vox_local, float4* vox_
 // (acquire).  An optional 2-float payload travels with the announcement and is summed in rank order, which
 // is how the global loss is formed without a collective.  One warp; launched in stream order, so it
 // separates "my gradient scatter is complete" from "I start reading everybody's gradients".
-struct SyncBlock {
-  unsigned int flags[kMaxWorld];
-  float payload[kMaxWorld][2];
-  unsigned int timed_out;
-};
-struct SyncPtrs {
-  SyncBlock* blk[kMaxWorld];
-};
-
 __global__ void peer_sync_kernel(SyncPtrs sp, int world, int me, unsigned int epoch,
                                  const float* __restrict__ payload_in, float* __restrict__ payload_sum) {
-  const int r = threadIdx.x;
-  SyncBlock* mine = sp.blk[me];
-  if (r < world) {
-    SyncBlock* peer = sp.blk[r];
-    if (payload_in) {
-      peer->payload[me][0] = payload_in[0];
-      peer->payload[me][1] = payload_in[1];
-    }
-    __threadfence_system();
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&peer->flags[me]), "r"(epoch) : "memory");
-    const long long t0 = clock64();
-    for (;;) {
-      unsigned int v;
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(&mine->flags[r]) : "memory");
-      if ((int)(v - epoch) >= 0) break;
-      if (clock64() - t0 > 20000000000LL) {   // ~10 s: a peer died; do not hang the device
-        mine->timed_out = 1;
-        break;
-      }
-    }
-  }
+  peer_announce_and_wait(sp, world, me, epoch, payload_in, true);
   __syncwarp();
-  if (payload_sum && r == 0) {
+  if (payload_sum && threadIdx.x == 0) {
+    const SyncBlock* mine = sp.blk[me];
     float a = 0.f, b = 0.f;
     for (int q = 0; q < world; ++q) {
       a += mine->payload[q][0];
@@ -273,20 +301,34 @@ extern "C" int pp_voxel_adam_exchange_mc(const void* vox_local, void* vox_mc, co
                                          void* exp_avg, void* exp_avg_sq, int64_t n_voxels,
                                          int32_t world, int32_t rank, int32_t step, float beta1,
                                          float beta2, float lr_density, float lr_k0, float eps,
-                                         pp_stream_t stream) {
+                                         void* const* sync_ptrs, uint32_t epoch, const float* payload_in,
+                                         float* payload_sum_out, pp_stream_t stream) {
   PP_REQUIRE(vox_local && vox_mc && grad_mc && exp_avg && exp_avg_sq, PP_ERR_INVALID_ARG,
              "voxel_adam_exchange_mc: null pointer");
-  PP_REQUIRE(world >= 1 && rank >= 0 && rank < world, PP_ERR_INVALID_ARG,
+  PP_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, PP_ERR_INVALID_ARG,
              "voxel_adam_exchange_mc: bad world/rank %d/%d", rank, world);
+  PP_REQUIRE(epoch == 0 || sync_ptrs, PP_ERR_INVALID_ARG, "voxel_adam_exchange_mc: fused barrier needs sync_ptrs");
   const int64_t shard = pp_voxel_shard_size(n_voxels, world);
   const int64_t begin = shard * rank < n_voxels ? shard * rank : n_voxels;
   const int64_t end = begin + shard < n_voxels ? begin + shard : n_voxels;
-  if (end <= begin) return PP_OK;
-  const int blocks = exchange_blocks(end - begin);
-  voxel_adam_exchange_mc_kernel<<<blocks, kXchgThreads, 0, as_stream(stream)>>>(
-      (const float4*)vox_local, (float4*)vox_mc, (const float4*)grad_mc, (float4*)exp_avg,
-      (float4*)exp_avg_sq, begin, end, adam_step_size_x(lr_density, beta1, beta2, step),
-      adam_step_size_x(lr_k0, beta1, beta2, step), beta1, beta2, eps);
+  SyncPtrs sp;
+  for (int r = 0; r < kMaxWorld; ++r) sp.blk[r] = (epoch != 0 && r < world) ? (SyncBlock*)sync_ptrs[r] : nullptr;
+  // an empty slice still takes part in the fused barrier (one block, no records)
+  if (end <= begin && epoch == 0) return PP_OK;
+  const int64_t n_rec = end > begin ? end - begin : 0;
+  const int blocks = n_rec > 0 ? exchange_blocks(n_rec) : 1;
+  const char* de = getenv("PP_XCHG_DEPTH");
+  const int depth = de ? atoi(de) : 3;
+  const float ssd = adam_step_size_x(lr_density, beta1, beta2, step), ssk = adam_step_size_x(lr_k0, beta1, beta2, step);
+#define PP_LAUNCH_MC(D)                                                                                          \
+  voxel_adam_exchange_mc_kernel<D><<<blocks, kXchgThreads, 0, as_stream(stream)>>>(                              \
+      (const float4*)vox_local, (float4*)vox_mc, (const float4*)grad_mc, (float4*)exp_avg, (float4*)exp_avg_sq, \
+      begin, end, ssd, ssk, beta1, beta2, eps, sp, world, rank, epoch, payload_in, payload_sum_out)
+  if (depth <= 2) PP_LAUNCH_MC(2);
+  else if (depth == 3) PP_LAUNCH_MC(3);
+  else if (depth == 4) PP_LAUNCH_MC(4);
+  else PP_LAUNCH_MC(6);
+#undef PP_LAUNCH_MC
   PP_CHECK_LAUNCH("voxel_adam_exchange_mc");
   return PP_OK;
 }

@@ -130,6 +130,8 @@ class DistributedDVGO:
             # loads/stores at 2 and 4 (their link traffic 2(w-1)/w is below NVLS's (w+1)/w there)
             mode = "nvls" if (self.world >= 8 and nvls_available()) else "p2p"
         self.mode = mode if self.world > 1 else "single"
+        import os
+        self.fused_sync = os.environ.get("PP_XCHG_FUSED_SYNC", "1") != "0"
         dev = density.device
         kw = dict(kw)
         kw["w_rgb"] = kw.get("w_rgb", 1.0) / self.world          # global mean over all ranks' rays
@@ -207,17 +209,24 @@ class DistributedDVGO:
             s = stream()
             if prof is not None:
                 prof[0].record()
-            # barrier: every rank finished scattering; the local [loss, mse] rides along and comes back summed
+            # barrier: every rank finished scattering; the local [loss, mse] rides along and comes back summed.
+            # NVLS mode fuses it into the exchange kernel's prologue (one launch less on the critical path).
             self.epoch += 1
-            check(lib.pp_peer_sync(self.sync_ptrs, self.world, self.rank, self.epoch, ptr(eng.loss_buf),
-                                   ptr(self.loss_global), s), "peer_sync")
+            fused = self.mode == "nvls" and self.fused_sync
+            if not fused:
+                check(lib.pp_peer_sync(self.sync_ptrs, self.world, self.rank, self.epoch, ptr(eng.loss_buf),
+                                       ptr(self.loss_global), s), "peer_sync")
             if prof is not None:
                 prof[1].record()
             if self.mode == "nvls":
                 check(lib.pp_voxel_adam_exchange_mc(ptr(eng.vox), self.vox_mem.multicast_ptr,
                                                     self.grad_mems[self.cur].multicast_ptr, ptr(eng.exp_avg),
                                                     ptr(eng.exp_avg_sq), eng.n_voxels, self.world, self.rank,
-                                                    eng.step, b1, b2, lr_d, lr_k, eps, s), "voxel_adam_exchange_mc")
+                                                    eng.step, b1, b2, lr_d, lr_k, eps,
+                                                    self.sync_ptrs if fused else None, self.epoch if fused else 0,
+                                                    ptr(eng.loss_buf) if fused else None,
+                                                    ptr(self.loss_global) if fused else None, s),
+                      "voxel_adam_exchange_mc")
             else:
                 check(lib.pp_voxel_adam_exchange(self.vox_ptrs, self.grad_ptrs[self.cur], ptr(eng.exp_avg),
                                                  ptr(eng.exp_avg_sq), eng.n_voxels, self.world, self.rank,
