@@ -265,6 +265,13 @@ PP_API int pp_rgbnet_backward(const float* x, const float* grad_out, int64_t n_p
                               float* const* grad_weights, float* const* grad_biases, float* rgb_out,
                               void* workspace, int64_t workspace_bytes, pp_stream_t stream);
 PP_API int64_t pp_rgbnet_workspace_bytes(int64_t n_pts, int32_t d0);
+/* Diagnostic: 1 if a barrier wait inside the backward kernel ever exceeded its cycle budget (never expected; the
+ * kernel then finishes without hanging the device and its results are invalid).  Synchronises the device. */
+PP_API int pp_rgbnet_backward_stalled(void);
+/* Diagnostic (env PP_MLP_PROF=1): cycle counters of CTA 0 of the last backward launch: [0..6] MMA warp (wait for
+ * epilogue half 0, half 1, input tile, -, -, -, total), [8..14] epilogue warp 0, [16..22] epilogue warp 8 (wait for
+ * accumulator, for dW inside the tile, for dW at the tile end, for cp.async, -, -, total). */
+PP_API int pp_rgbnet_backward_profile(long long* out24);
 
 /* The pieces of pp_rgbnet_backward, for callers that keep features in the kernels' own format (the fused
  * fine-stage path): x_packed = bf16 [n, k0p] rows, grad_x_padded = fp32 [n, k0p] rows,

@@ -24,7 +24,7 @@ PP_F32, PP_F64 = 0, 1
 _CTYPES = {
     "float": ctypes.c_float, "double": ctypes.c_double, "int": ctypes.c_int,
     "int32_t": ctypes.c_int32, "int64_t": ctypes.c_int64, "uint64_t": ctypes.c_uint64, "uint32_t": ctypes.c_uint32,
-    "pp_dtype": ctypes.c_int, "pp_stream_t": ctypes.c_void_p, "size_t": ctypes.c_size_t,
+    "long": ctypes.c_longlong, "pp_dtype": ctypes.c_int, "pp_stream_t": ctypes.c_void_p, "size_t": ctypes.c_size_t,
 }
 _PROTO = re.compile(r"PP_API\s+([\w\s\*]+?)\s*\b(pp_\w+)\s*\(([^;]*?)\)\s*;", re.S)
 

@@ -141,7 +141,7 @@ rgbnet_forward_kernel(MlpParams P, const __nv_bfloat16* __restrict__ x, int64_t 
       const bool last = (l == L - 1);
       const int K = (l == 0) ? k0p : kMlpWidth;
       const uint32_t d_tmem = tmem;
-      if (gt == 0) {
+      if (gt < 32) {   // the pipeline's first warp issues (warp-uniform loop, one elected lane)
         tc_fence_after();
         const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sW[l]);
         for (int k = 0; k < (K >> 4); ++k)

@@ -34,21 +34,33 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// MMA issue.  MUST be called by all 32 lanes of a warp with identical arguments: the loop around it then runs on
+// warp-uniform values (descriptors live in uniform registers) and `elect.sync` picks the one lane that issues.
+// Measured on B200 (tools/probe/umma_probe.cu): a loop executed by a single thread (`if (lane == 0)`) issues one
+// tcgen05.mma per ~120 cycles whatever its size; the warp-uniform form reaches the execution rate (64 cycles for
+// M=128, N=128, K=16; 48 for N=64; ~40 for N=16), K-major and MN-major operands alike.
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(
       "{\n\t"
-      ".reg .pred p;\n\t"
+      ".reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(d_tmem),
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 
+// commit of everything the warp's elected lane issued so far (same calling convention as umma_bf16)
 __device__ __forceinline__ void umma_commit(uint32_t bar_smem) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_smem)
-               : "memory");
+  asm volatile(
+      "{\n\t"
+      ".reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}\n" ::"r"(bar_smem)
+      : "memory");
 }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar_smem, uint32_t count) {

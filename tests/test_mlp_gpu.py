@@ -119,6 +119,8 @@ def test_rgbnet_backward(cuda, d0, depth, n):
     ops.rgbnet(x.cuda(), ws2, bs2).backward(gout.cuda())
     for a, b in zip(ws, ws2):
         torch.testing.assert_close(a.grad, b.grad, rtol=1e-3, atol=1e-6)
+    from poseprobe_b200._lib import lib
+    assert lib.pp_rgbnet_backward_stalled() == 0      # no barrier wait ran out of its cycle budget
 
 
 def test_rgbnet_forward_composite_epilogue(cuda):

@@ -82,6 +82,19 @@ def main():
         check(lib.pp_rgbnet_backward_packed(ptr(xp), ptr(gout), n, d0, depth, 128, arr(wsd), arr(bsd), 1, None,
                                             arr(gws), arr(gbs), None, stream()), "bwd")
     t_packed_nodx = timeit(packed_nodx)
+    if os.environ.get("PP_MLP_PROF"):
+        packed()
+        torch.cuda.synchronize()
+        buf = (ctypes.c_longlong * 24)()
+        if lib.pp_rgbnet_backward_profile(buf) == 0:
+            v = list(buf)
+            tiles = ((n + 127) // 128 + 147) // 148
+            print("  prof (cycles per tile, CTA 0, %d tiles): mma warp: wait epi0 %d, epi1 %d, x %d, total %d | "
+                  "epi warp0: wait acc %d, dw-in-tile %d, dw-end %d, cp.async %d, total %d | epi warp8: wait acc %d, "
+                  "dw-in-tile %d, dw-end %d, total %d" % (tiles, v[0] // tiles, v[1] // tiles, v[2] // tiles, v[6] // tiles,
+                                                          v[8] // tiles, v[9] // tiles, v[10] // tiles, v[11] // tiles,
+                                                          v[14] // tiles, v[16] // tiles, v[17] // tiles, v[18] // tiles,
+                                                          v[22] // tiles))
     outp = torch.empty(n, 3, device="cuda")
 
     def fwd_packed():
