@@ -264,3 +264,111 @@ def test_pose_gradient_vs_oracle(cuda):
     voxurf_cpu.mse_loss(out2, target).backward()
     want = torch.cat([od2.grad, dd2.grad], -1)
     assert _cos(folded.cpu(), want) > 0.99
+
+
+def test_fine_stage_se3_gradient_vs_oracle(cuda):
+    """The whole pose chain of the fine stage (SURVEY a20 + a21): se3_refine -> se3_to_SE3 -> compose -> invert ->
+    rays of the selected pixels (kernel) -> fused Voxurf step with pose_grad -> per-image reduction (kernel) ->
+    d loss / d se3_refine, against CPU autograd through the same chain written with torch ops and the oracle's
+    differentiable sample positions."""
+    from oracle import oracle as orc
+    from oracle import voxurf_cpu
+    from poseprobe_b200 import camera
+    from tests.test_pose_gpu import _cams
+    n_img, G, N = 3, 40, 1024
+    sdf, k0, net, _, _, _, _, kw = make_scene(G, N, seed=12)
+    c2w0, K, H, W = _cams(n_img, seed=3)
+    g = torch.Generator().manual_seed(4)
+    img_id = torch.randint(0, n_img, (N,), generator=g, dtype=torch.int32)
+    px, py = torch.rand(N, generator=g) * W, torch.rand(N, generator=g) * H
+    target = torch.rand(N, 3, generator=g)
+    se3_init = torch.randn(n_img, 6, generator=g) * 0.01
+    eng = make_engine(sdf, k0, net, kw, cuda, pose_grad=True)
+    # ---- ours ----
+    se3 = se3_init.clone().cuda().requires_grad_(True)
+    pose = camera.compose_pair(camera.se3_to_SE3(se3), camera.invert(c2w0).cuda())     # recon_scene.py:67-69
+    o, d = camera.rays_from_pixels(camera.invert(pose), K.cuda(), img_id.cuda(), px.cuda(), py.cuda())
+    oc, dc = o.detach().contiguous(), d.detach().contiguous()
+    eng.loss_buf.zero_()
+    eng.backward_only(oc, dc, dc, target.cuda())
+    g_rays = eng.ray_gradients(dc)                      # viewdirs = rays_d / |rays_d| folded in
+    torch.autograd.backward([o, d], [g_rays[:, :3].contiguous(), g_rays[:, 3:].contiguous()])
+    # ---- oracle: same chain in torch on the CPU ----
+    se3_r = se3_init.clone().requires_grad_(True)
+    pose_r = camera.compose_pair(camera.se3_to_SE3(se3_r), camera.invert(c2w0))
+    c2w_r = camera.invert(pose_r)
+    ii = img_id.long()
+    dirs = torch.stack([(px - K[ii, 0, 2]) / K[ii, 0, 0], -(py - K[ii, 1, 2]) / K[ii, 1, 1], -torch.ones(N)], -1)
+    rd = (dirs[:, None, :] * c2w_r[ii, :3, :3]).sum(-1)
+    rd = rd / rd.norm(dim=-1, keepdim=True)
+    ro = c2w_r[ii, :3, 3]
+    torch.testing.assert_close(oc.cpu(), ro.detach(), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(dc.cpu(), rd.detach(), rtol=1e-5, atol=1e-5)
+    out = voxurf_cpu.forward(sdf, k0, net, ro, rd, rd / rd.norm(dim=-1, keepdim=True), MN, MX, kw["stepsize"],
+                             eng.voxel_size, kw["s_val"], bg=kw["bg"], sdf_alpha=kw.get("sdf_alpha"),
+                             sdf_beta=kw.get("sdf_beta"), posbase_pe=5, viewbase_pe=1, barf_c2f=kw["barf_c2f"],
+                             progress=1.0, differentiable_points=True)
+    voxurf_cpu.mse_loss(out, target).backward()
+    c = _cos(se3.grad.cpu(), se3_r.grad)
+    ratio = float(se3.grad.norm() / se3_r.grad.norm())
+    print("se3 gradient: cosine %.5f, norm ratio %.4f" % (c, ratio), se3.grad.cpu(), se3_r.grad)
+    assert c > 0.99 and 0.9 < ratio < 1.1
+
+
+def test_edge_cases_missing_rays_and_capacity(cuda):
+    """Rays that miss the box composite nothing (rgb = bg, no MLP rows, zero gradients); a sample capacity that is
+    too small is reported instead of overrunning the buffers."""
+    G, N = 32, 256
+    sdf, k0, net, o, d, v, target, kw = make_scene(G, N, seed=21)
+    eng = make_engine(sdf, k0, net, kw, cuda)
+    o_miss = torch.tensor([[5.0, 5.0, 5.0]]).repeat(N, 1)
+    d_miss = torch.tensor([[1.0, 0.0, 0.0]]).repeat(N, 1)
+    rgb, last, cumw = eng.render(o_miss.to(cuda), d_miss.to(cuda), d_miss.to(cuda))
+    assert eng.n_samples() == 0
+    assert torch.equal(cumw.cpu(), torch.zeros(N)) and torch.equal(last.cpu(), torch.ones(N))
+    torch.testing.assert_close(rgb.cpu(), torch.full((N, 3), kw["bg"]))
+    eng.loss_buf.zero_()
+    eng.backward_only(o_miss.to(cuda), d_miss.to(cuda), d_miss.to(cuda), target.to(cuda))
+    g_sdf, g_k0, g_w, g_b = eng.grid_gradients()
+    assert float(g_sdf.abs().max()) == 0 and float(g_k0.abs().max()) == 0 and float(g_w[0].abs().max()) == 0
+    # capacity of 3 samples per ray: the overflow flag is raised, nothing is written past the buffers
+    small = make_engine(sdf, k0, net, kw, cuda, samples_per_ray_cap=3)
+    small.render(o.to(cuda), d.to(cuda), v.to(cuda))
+    with pytest.raises(RuntimeError, match="capacity"):
+        small.n_samples()
+
+
+def test_config_c_full_size_properties(cuda):
+    """BASELINE configs[2] shapes on one GPU (160^3, 8192 rays): size-independent properties of the fused step."""
+    G, N = 160, 8192
+    sdf, k0, net, o, d, v, target, kw = make_scene(G, N, seed=30)
+    eng = make_engine(sdf, k0, net, kw, cuda, lr_sdf=1e-4, lr_k0=1e-2, lr_rgbnet=1e-3)
+    oc, dc, vc, tc = o.to(cuda), d.to(cuda), v.to(cuda), target.to(cuda)
+    rgb, last, cumw = eng.render(oc, dc, vc)
+    m = eng.n_samples()
+    assert 0 < m <= eng._bufs["cap"]
+    # partition of unity of the compositing: sum of weights + final transmittance = 1
+    torch.testing.assert_close(cumw + last, torch.ones(N, device=cuda), rtol=0, atol=2e-4)
+    assert float(rgb.min()) >= 0 and float(rgb.max()) <= 1
+    # slot ranges tile [0, m) exactly once
+    b = eng._bufs
+    cnt, off = b["ray_cnt"][:N].long(), b["ray_off"][:N].long()
+    assert int(cnt.sum()) == m
+    order = torch.argsort(off)
+    live = cnt[order] > 0
+    starts, lens = off[order][live], cnt[order][live]
+    assert int(starts[0]) == 0 and torch.equal(starts[1:], (starts + lens)[:-1])
+    # every row's ray id matches the range it sits in; weights are probabilities
+    rid = b["rid"][:m].long()
+    assert bool((off[rid] <= torch.arange(m, device=cuda)).all()) and bool((torch.arange(m, device=cuda) < off[rid] + cnt[rid]).all())
+    w = b["w"][:m]
+    assert float(w.min()) >= 0 and float(w.max()) <= 1
+    # the same render twice: identical compositing, colours equal up to the order of the atomics
+    rgb2, last2, cumw2 = eng.render(oc, dc, vc)
+    assert torch.equal(last, last2) and torch.equal(cumw, cumw2)
+    torch.testing.assert_close(rgb, rgb2, rtol=0, atol=1e-5)
+    # a few optimisation steps reduce the loss on a fixed batch
+    losses = [float(eng.train_step(oc, dc, vc, tc)[1]) for _ in range(8)]
+    assert losses[-1] < losses[0], losses
+    from poseprobe_b200._lib import lib
+    assert lib.pp_rgbnet_backward_stalled() == 0
