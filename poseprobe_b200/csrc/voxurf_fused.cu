@@ -186,11 +186,25 @@ voxurf_march_kernel(pp_dvgo_scene sc, pp_voxurf_cfg cfg, const float4* __restric
       ray_end[r] = end;
       cum_w[r] = fits ? cumw : 0.f;
       alphainv_last[r] = T_in;
-      if (!fits) off = -1;
+      if (!fits) off = -1 - off;   // encode "reserved but does not fit" (off >= 0 is kept for the fill below)
     }
     off = __shfl_sync(kFull, off, 0);
     __syncwarp();
-    if (off < 0 || n_live == 0) continue;
+    if (off < 0) {
+      // the reservation cannot be undone: neutralise the part of it that lies inside the buffers (weight 0, a
+      // valid ray id, zero features) so that the consumers of [0, capacity) never see uninitialised rows
+      const int begin = -1 - off;
+      for (int slot = begin + lane; slot < cap_m; slot += kWarp) {
+        uint4* dst = reinterpret_cast<uint4*>(feat + (int64_t)slot * kFeatCols);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) dst[q] = make_uint4(0u, 0u, 0u, 0u);
+        w_out[slot] = 0.f;
+        rid_out[slot] = static_cast<int32_t>(r);
+        rec_out[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      continue;
+    }
+    if (n_live == 0) continue;
 
     // ---------------- phase 2: feature rows of the composited samples ----------------
     // per-ray view columns: viewdirs, sin / cos of viewdirs * 2^0 (view_pe <= 1), BARF weighted

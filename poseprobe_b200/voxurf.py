@@ -8,8 +8,10 @@ Parameter layouts interchange with the reference's checkpoints (``import_state``
 
 ``FusedVoxurf.train_step`` is 10 launches: march+features, MLP forward (tcgen05, compositing epilogue), per-ray
 loss, MLP forward-recompute+backward (tcgen05), reverse march + scatter, SDF fold + Adam, SDF record rebuild,
-feature-record Adam, rgbnet Adam, gradient clears.  The deformation network (use_implict_deform) is not part of
-this path.
+feature-record Adam, rgbnet Adam, gradient clears.  With ``pose_grad=True`` the reverse march also emits
+d loss / d (rays_o, rays_d, viewdirs) for the SE3 refinement (``ray_gradients`` -> ``camera.rays_from_pixels``'
+backward = the fused per-image reduction).  The deformation network (use_implict_deform) is not part of this path
+(SURVEY.md 8f rank 3).
 """
 import ctypes
 import math
@@ -113,7 +115,6 @@ class FusedVoxurf:
             check(lib.pp_voxurf_k0_pack(ptr(k0.contiguous()), self.n_voxels, ptr(self.k0rec), stream()), "k0_pack")
         idx = torch.tensor([max(p, 0) for p in self.perm], device=dev)
         keep = torch.tensor([1.0 if p >= 0 else 0.0 for p in self.perm], device=dev)
-        self._perm_idx, self._perm_keep = idx, keep
         w0 = rgbnet_weights[0].detach().to(dev).float()
         self.weights = [(w0[:, idx] * keep).contiguous()] + [w.detach().to(dev).float().contiguous()
                                                               for w in rgbnet_weights[1:]]
