@@ -207,14 +207,18 @@ PP_API int pp_voxurf_ray_loss(int64_t n_rays, const float* rgb_acc, const float*
  * Pose gradient (optional, needs 64 columns): grad_rays [N,6] = d loss / d (rays_o | rays_d) through the sample
  * positions (SDF value and gradient interpolation, feature interpolation, positional encoding), grad_viewdirs [N,3]
  * = d loss / d viewdirs (NeuS cosine, view encoding); the caller chains viewdirs = rays_d / |rays_d| and
- * pp_pose_grad_reduce (the autograd reduction of SURVEY.md a21).  Pass null to skip. */
+ * pp_pose_grad_reduce (the autograd reduction of SURVEY.md a21).  Pass null to skip.
+ * grad_cum_weights [N] / grad_alphainv_last [N] (nullable): d loss / d cum_weights and d loss / d alphainv_last of
+ * an external (autograd) loss; when grad_cum_weights is null the fused loss' background term -(sum g_ray) * bg is
+ * used, when grad_alphainv_last is null it is zero. */
 PP_API int pp_voxurf_backward(const pp_dvgo_scene* scene, const pp_voxurf_cfg* cfg, const float* rays_o,
                               const float* rays_d, const float* viewdirs, const float* jitter, int64_t n_rays,
                               const void* sample_rec, const float* grad_weight, const float* grad_feat,
                               int32_t grad_feat_cols, const int32_t* ray_off, const int32_t* ray_cnt,
                               const int32_t* ray_end, const float* g_ray, void* grad_sdf_records,
                               void* grad_k0_records, const void* sdf_records, const void* k0_records,
-                              float* grad_rays, float* grad_viewdirs, pp_stream_t stream);
+                              float* grad_rays, float* grad_viewdirs, const float* grad_cum_weights,
+                              const float* grad_alphainv_last, pp_stream_t stream);
 
 /* Dense tail of the SDF grid: folds the gradient-grid components back onto the SDF (transposed central
  * difference), applies the mapping function's chain rule and masked Adam (adam_upd_kernel.cu:35-39) in place.

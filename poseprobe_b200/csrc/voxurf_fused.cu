@@ -340,7 +340,8 @@ voxurf_backward_kernel(pp_dvgo_scene sc, pp_voxurf_cfg cfg, const float* __restr
                        const int32_t* __restrict__ ray_end, const float* __restrict__ g_ray,
                        float4* __restrict__ g_srec, float4* __restrict__ g_k0rec, unsigned int* __restrict__ queue,
                        int cap, int dx_pitch, const float4* __restrict__ srec, const float4* __restrict__ k0rec,
-                       float* __restrict__ grad_rays, float* __restrict__ grad_viewdirs) {
+                       float* __restrict__ grad_rays, float* __restrict__ grad_viewdirs,
+                       const float* __restrict__ g_cumw, const float* __restrict__ g_last) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int per_warp = 2 * cap + cap / kWarp;
@@ -367,7 +368,9 @@ voxurf_backward_kernel(pp_dvgo_scene sc, pp_voxurf_cfg cfg, const float* __restr
     float v[3], g[3];
     load3(viewdirs, r, v);
     load3(g_ray, r, g);
-    const float gbg = (g[0] + g[1] + g[2]) * sc.bg;   // through (1 - sum w) * bg
+    // d loss / d w_i beyond the colour sum: the fused loss routes it through (1 - sum w) * bg; an autograd caller
+    // passes d loss / d cum_weights per ray instead
+    const float gbg = g_cumw ? -g_cumw[r] : (g[0] + g[1] + g[2]) * sc.bg;
 
     // forward re-walk: alpha of every step from the stored records, transmittance entering every chunk
     float T_in = 1.f;
@@ -396,8 +399,9 @@ voxurf_backward_kernel(pp_dvgo_scene sc, pp_voxurf_cfg cfg, const float* __restr
     }
     __syncwarp();
 
-    // reverse walk
-    float back = 0.f;   // alphainv_last does not enter the loss (the background uses 1 - sum w)
+    // reverse walk; back_cum of alpha2weight_backward starts at grad_last * alphainv_last (reference :671): zero for
+    // the fused loss (the background uses 1 - sum w), the caller's d loss / d alphainv_last otherwise
+    float back = g_last ? g_last[r] * T_in : 0.f;
     const int last_base = ((end - 1) / kWarp) * kWarp;
     for (int base = last_base; base >= 0; base -= kWarp) {
       const int i = base + lane;
@@ -729,7 +733,8 @@ extern "C" int pp_voxurf_backward(const pp_dvgo_scene* scene, const pp_voxurf_cf
                                   int32_t grad_feat_cols, const int32_t* ray_off, const int32_t* ray_cnt,
                                   const int32_t* ray_end, const float* g_ray, void* grad_sdf_records,
                                   void* grad_k0_records, const void* sdf_records, const void* k0_records,
-                                  float* grad_rays, float* grad_viewdirs, pp_stream_t stream) {
+                                  float* grad_rays, float* grad_viewdirs, const float* grad_cum_weights,
+                                  const float* grad_alphainv_last, pp_stream_t stream) {
   const float* grad_feat16 = grad_feat;
   const int rc = check_vox_scene(scene, cfg, "voxurf_backward");
   if (rc != PP_OK) return rc;
@@ -760,7 +765,8 @@ extern "C" int pp_voxurf_backward(const pp_dvgo_scene* scene, const pp_voxurf_cf
   kernel<<<(unsigned)blocks, warps * 32, smem, s>>>(
       *scene, *cfg, rays_o, rays_d, viewdirs, jitter, n_rays, (const float4*)sample_rec, grad_weight, grad_feat16,
       ray_off, ray_cnt, ray_end, g_ray, (float4*)grad_sdf_records, (float4*)grad_k0_records, queue, cap,
-      grad_feat_cols, (const float4*)sdf_records, (const float4*)k0_records, grad_rays, grad_viewdirs);
+      grad_feat_cols, (const float4*)sdf_records, (const float4*)k0_records, grad_rays, grad_viewdirs,
+      grad_cum_weights, grad_alphainv_last);
   PP_CHECK_LAUNCH("voxurf_backward");
   return PP_OK;
 }

@@ -79,7 +79,7 @@ class FusedVoxurf:
     def __init__(self, sdf, k0, rgbnet_weights, rgbnet_biases, xyz_min, xyz_max, stepsize=0.5, near=0.2, far=1e9,
                  bg=0.0, s_val=0.05, sdf_alpha=None, sdf_beta=None, posbase_pe=5, viewbase_pe=1, barf_c2f=None,
                  lr_sdf=0.1, lr_k0=0.1, lr_rgbnet=1e-3, betas=(0.9, 0.99), eps=1e-8, w_rgb=1.0,
-                 samples_per_ray_cap=None, pose_grad=False):
+                 samples_per_ray_cap=None, pose_grad=False, voxel_size=None):
         _need_cuda(sdf, "sdf")
         _need_cuda(k0, "k0")
         self.device = sdf.device
@@ -92,7 +92,9 @@ class FusedVoxurf:
         vol = 1.0
         for a, b in zip(self.xyz_min, self.xyz_max):
             vol *= (b - a)
-        self.voxel_size = (vol / self.n_voxels) ** (1.0 / 3.0)      # voxurf_coarse.py _set_grid_resolution
+        # voxurf_coarse.py _set_grid_resolution: (volume / num_voxels)^(1/3); pass it when num_voxels is not the
+        # product of the grid extents (the reference floors the extents)
+        self.voxel_size = float(voxel_size) if voxel_size is not None else (vol / self.n_voxels) ** (1.0 / 3.0)
         self.stepsize = stepsize
         self.scene = make_scene(self.world, self.xyz_min, self.xyz_max, near, far, stepsize * self.voxel_size, 0.0,
                                 stepsize, bg)
@@ -267,9 +269,58 @@ class FusedVoxurf:
                                          ptr(viewdirs), ptr(jitter), n, ptr(b["rec"]), ptr(b["gw"]), ptr(b["dx"]),
                                          self.dx_cols, ptr(b["ray_off"]), ptr(b["ray_cnt"]), ptr(b["ray_end"]),
                                          ptr(b["g_ray"]), ptr(self.g_srec), ptr(self.g_k0rec), ptr(self.srec),
-                                         ptr(self.k0rec), ptr(b["grad_rays"]), ptr(b["grad_view"]), stream()),
-                  "voxurf_backward")
+                                         ptr(self.k0rec), ptr(b["grad_rays"]), ptr(b["grad_view"]), None, None,
+                                         stream()), "voxurf_backward")
         return b["rgb"][:n]
+
+    # ---- autograd-facing pieces (used by the Voxurf module below) ---------------------------------------------
+    def load_params(self, sdf, k0, weights, biases, sdf_alpha=None, sdf_beta=None):
+        """Copy parameters given in the reference's layouts into the engine's layouts and rebuild the records."""
+        self.sdf.copy_(sdf.detach().reshape(-1))
+        with torch.cuda.device(self.device):
+            check(lib.pp_voxurf_k0_pack(ptr(k0.detach().contiguous()), self.n_voxels, ptr(self.k0rec), stream()),
+                  "k0_pack")
+        idx = torch.tensor([max(p, 0) for p in self.perm], device=self.device)
+        keep = torch.tensor([1.0 if p >= 0 else 0.0 for p in self.perm], device=self.device)
+        self.weights[0].copy_(weights[0].detach()[:, idx] * keep)
+        for dst, src in zip(self.weights[1:], weights[1:]):
+            dst.copy_(src.detach())
+        for dst, src in zip(self.biases, biases):
+            dst.copy_(src.detach())
+        if sdf_alpha is not None:
+            self.sdf_alpha, self.sdf_beta = float(sdf_alpha), float(sdf_beta)
+        self._refresh_cfg()
+        self.rebuild_records()
+
+    def forward_sums(self, rays_o, rays_d, viewdirs, jitter=None):
+        """-> (rgb_acc [N,3] = sum_i w_i rgb_i, cum_weights [N], alphainv_last [N]); state is kept for
+        backward_from_ray_grads."""
+        n = rays_o.shape[0]
+        b = self._buffers(n)
+        with torch.cuda.device(self.device):
+            self._march(b, rays_o, rays_d, viewdirs, jitter)
+            self._mlp_forward(b, n)
+        return b["acc"][:n], b["cum_w"][:n], b["last"][:n]
+
+    def backward_from_ray_grads(self, rays_o, rays_d, viewdirs, g_acc, g_cumw, g_last, jitter=None):
+        """Back-propagate d loss / d (rgb_acc, cum_weights, alphainv_last) of the last forward_sums into the
+        gradient buffers (accumulating)."""
+        n = rays_o.shape[0]
+        b = self._bufs
+        g_acc = g_acc.contiguous()
+        with torch.cuda.device(self.device):
+            check(lib.pp_rgbnet_backward_fused(ptr(b["feat"]), b["cap"], ptr(b["counter"]), self.d0, self.depth, 128,
+                                               self._arr(self.weights), self._arr(self.biases), ptr(b["w"]),
+                                               ptr(b["rid"]), ptr(g_acc), ptr(b["gw"]), ptr(b["dx"]),
+                                               self.dx_cols, self._arr(self.g_w), self._arr(self.g_b), stream()),
+                  "rgbnet_backward_fused")
+            check(lib.pp_voxurf_backward(ctypes.byref(self.scene), ctypes.byref(self.cfg), ptr(rays_o), ptr(rays_d),
+                                         ptr(viewdirs), ptr(jitter), n, ptr(b["rec"]), ptr(b["gw"]), ptr(b["dx"]),
+                                         self.dx_cols, ptr(b["ray_off"]), ptr(b["ray_cnt"]), ptr(b["ray_end"]),
+                                         ptr(g_acc), ptr(self.g_srec), ptr(self.g_k0rec), ptr(self.srec),
+                                         ptr(self.k0rec), ptr(b["grad_rays"]), ptr(b["grad_view"]),
+                                         ptr(g_cumw.contiguous()), ptr(g_last.contiguous()) if g_last is not None else None,
+                                         stream()), "voxurf_backward")
 
     def ray_gradients(self, rays_d=None):
         """d loss / d (rays_o | rays_d) [N,6] and d loss / d viewdirs [N,3] of the last backward (pose_grad=True).
@@ -346,6 +397,107 @@ class FusedVoxurf:
             out["rgbnet.%s.weight" % nme] = w
             out["rgbnet.%s.bias" % nme] = bb.clone()
         return out
+
+
+class _VoxurfRenderFn(torch.autograd.Function):
+    """(sdf.grid, k0.grid, sdf_alpha, sdf_beta, rgbnet parameters) -> (rgb_acc, cum_weights, alphainv_last) with both
+    directions on the fused kernels; any loss written on those outputs trains the reference's parameters."""
+
+    @staticmethod
+    def forward(ctx, eng, rays_o, rays_d, viewdirs, jitter, depth, sdf, k0, ab, *params):
+        eng.load_params(sdf, k0, params[:depth], params[depth:], float(ab[0]), float(ab[1]))
+        rays_o, rays_d, viewdirs = rays_o.contiguous(), rays_d.contiguous(), viewdirs.contiguous()
+        acc, cumw, last = eng.forward_sums(rays_o, rays_d, viewdirs, jitter)
+        ctx.eng, ctx.depth = eng, depth
+        ctx.save_for_backward(rays_o, rays_d, viewdirs, jitter if jitter is not None else torch.empty(0), ab)
+        return acc.clone(), cumw.clone(), last.clone()
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_acc, g_cumw, g_last):
+        eng, depth = ctx.eng, ctx.depth
+        rays_o, rays_d, viewdirs, jitter, ab = ctx.saved_tensors
+        jitter = jitter if jitter.numel() else None
+        eng.grad_flat.zero_()
+        eng.g_ab.zero_()
+        eng.backward_from_ray_grads(rays_o, rays_d, viewdirs, g_acc, g_cumw, g_last, jitter)
+        g_sdf, g_k0, g_w, g_b = eng.grid_gradients()
+        # (a, b) = softplus10(sdf_alpha, sdf_beta): d softplus_beta(x) / dx = sigmoid(beta x)
+        g_param_ab = eng.g_ab * torch.sigmoid(10.0 * ab)
+        return (None, None, None, None, None, None, g_sdf, g_k0, g_param_ab) + tuple(g_w) + tuple(g_b)
+
+
+class Voxurf(torch.nn.Module):
+    """Surface-stage ``Voxurf`` (lib/voxurf_coarse.py:44-1091) on the fused kernels, non-deform branch.
+
+    Same parameter names as the reference (``sdf.grid`` [1,1,X,Y,Z], ``k0.grid`` [1,12,X,Y,Z], ``rgbnet.*``,
+    ``sdf_alpha``, ``sdf_beta``, ``s_val``), so ``last_ckpt.tar`` state dicts load with ``strict=False``, and the same
+    ``forward(rays_o, rays_d, viewdirs, global_step=None, **render_kwargs)`` returning the per-ray entries of the
+    reference's result dict (``rgb_marched``, ``alphainv_cum``, ``cum_weights``, ``s_val``).  The loss stays in the
+    caller's Python (lib/losses.py); autograd reaches every parameter through two fused kernels per direction plus
+    the tcgen05 rgbnet.  Per-sample entries of the reference's dict (``weights``, ``raw_alpha``, ``gradient`` ...) are
+    not materialised."""
+
+    def __init__(self, xyz_min, xyz_max, num_voxels=0, num_voxels_base=0, rgbnet_dim=12, rgbnet_depth=3,
+                 rgbnet_width=128, posbase_pe=5, viewbase_pe=1, geo_rgb_dim=3, s_ratio=2000, s_start=0.2,
+                 step_start=0, barf_c2f=None, N_iters=20000, **kwargs):
+        super().__init__()
+        from .grid import DenseGrid
+        if rgbnet_dim != 12 or rgbnet_width != 128 or geo_rgb_dim != 3:
+            raise NotImplementedError("fused Voxurf: rgbnet_dim=12, rgbnet_width=128, geo_rgb_dim=3")
+        self.register_buffer("xyz_min", torch.Tensor(xyz_min))
+        self.register_buffer("xyz_max", torch.Tensor(xyz_max))
+        self.num_voxels_base = num_voxels_base
+        self.voxel_size = ((self.xyz_max - self.xyz_min).prod() / num_voxels).pow(1 / 3)          # :_set_grid_resolution
+        self.world_size = ((self.xyz_max - self.xyz_min) / self.voxel_size).long()
+        ws = self.world_size.tolist()
+        self.sdf = DenseGrid(channels=1, world_size=ws, xyz_min=self.xyz_min, xyz_max=self.xyz_max)
+        self.k0 = DenseGrid(channels=rgbnet_dim, world_size=ws, xyz_min=self.xyz_min, xyz_max=self.xyz_max)
+        self.posbase_pe, self.viewbase_pe, self.barf_c2f, self.N_iters = posbase_pe, viewbase_pe, barf_c2f, N_iters
+        dim0 = (3 + 3 * posbase_pe * 2) + (3 + 3 * viewbase_pe * 2) + rgbnet_dim + geo_rgb_dim             # :198-206
+        nn = torch.nn
+        self.rgbnet = nn.Sequential(
+            nn.Linear(dim0, rgbnet_width), nn.ReLU(inplace=True),
+            *[nn.Sequential(nn.Linear(rgbnet_width, rgbnet_width), nn.ReLU(inplace=True)) for _ in range(rgbnet_depth - 2)],
+            nn.Linear(rgbnet_width, 3))
+        nn.init.constant_(self.rgbnet[-1].bias, 0)
+        self.sdf_alpha = nn.Parameter(torch.Tensor([10.0]))          # :118-119, use_mapping_fun
+        self.sdf_beta = nn.Parameter(torch.Tensor([2.0]))
+        self.s_val = nn.Parameter(torch.ones(1), requires_grad=False)
+        self.s_ratio, self.s_start, self.step_start = s_ratio, s_start, step_start
+        self._eng = None
+
+    def _engine(self, render_kwargs):
+        from .ops import rgbnet_from_sequential
+        ws, bs = rgbnet_from_sequential(self.rgbnet)
+        key = (float(render_kwargs["near"]), float(render_kwargs["far"]), float(render_kwargs["stepsize"]),
+               float(render_kwargs.get("bg", 0.0)))
+        if self._eng is None or self._eng_key != key:
+            self._eng = FusedVoxurf(self.sdf.grid.detach(), self.k0.grid.detach(), [w.detach() for w in ws],
+                                    [b.detach() for b in bs], self.xyz_min.tolist(), self.xyz_max.tolist(),
+                                    stepsize=key[2], near=key[0], far=key[1], bg=key[3], s_val=float(self.s_val),
+                                    sdf_alpha=float(self.sdf_alpha), sdf_beta=float(self.sdf_beta),
+                                    posbase_pe=self.posbase_pe, viewbase_pe=self.viewbase_pe, barf_c2f=self.barf_c2f,
+                                    voxel_size=float(self.voxel_size))
+            self._eng_key = key
+        return self._eng, ws, bs
+
+    def forward(self, rays_o, rays_d, viewdirs, global_step=None, **render_kwargs):
+        eng, ws, bs = self._engine(render_kwargs)
+        if global_step is not None:                      # neus_alpha_from_sdf_scatter, :485-488, and the BARF progress
+            s_val = 1.0 / (global_step + self.s_ratio / self.s_start - self.step_start) * self.s_ratio
+            self.s_val.data.fill_(s_val)
+            eng.set_schedule(progress=global_step / self.N_iters)
+        else:
+            eng.set_schedule(progress=1.0)
+        eng.s_val = float(self.s_val)
+        jitter = torch.rand(rays_o.shape[0], device=rays_o.device) if global_step is not None else None
+        ab = torch.cat([self.sdf_alpha, self.sdf_beta])
+        acc, cumw, last = _VoxurfRenderFn.apply(eng, rays_o, rays_d, viewdirs, jitter, len(ws), self.sdf.grid,
+                                                self.k0.grid, ab, *ws, *bs)
+        rgb_marched = (acc + (1 - cumw[:, None]) * render_kwargs.get("bg", 0.0)).clamp(0, 1)          # :1040-1042
+        return {"alphainv_cum": last, "cum_weights": cumw[:, None], "rgb_marched": rgb_marched,
+                "s_val": float(self.s_val)}
 
 
 def smoke(dev):

@@ -175,7 +175,7 @@ def test_backward_kernel_exact_inputs(cuda):
         check(lib.pp_voxurf_backward(ctypes.byref(eng.scene), ctypes.byref(eng.cfg), ptr(oc), ptr(dc), ptr(vc), None, N,
                                      ptr(b["rec"]), ptr(b["gw"]), ptr(b["dx"]), 16, ptr(b["ray_off"]), ptr(b["ray_cnt"]),
                                      ptr(b["ray_end"]), ptr(b["g_ray"]), ptr(eng.g_srec), ptr(eng.g_k0rec), None, None,
-                                     None, None, stream()),
+                                     None, None, None, None, stream()),
               "voxurf_backward")
     g_sdf, g_k0, _, _ = eng.grid_gradients()
     torch.cuda.synchronize()
@@ -372,3 +372,58 @@ def test_config_c_full_size_properties(cuda):
     assert losses[-1] < losses[0], losses
     from poseprobe_b200._lib import lib
     assert lib.pp_rgbnet_backward_stalled() == 0
+
+
+def test_voxurf_module_autograd_vs_oracle(cuda):
+    """The nn.Module face (reference parameter names, forward(...) -> result dict) with a loss written in Python on
+    its outputs - photometric MSE + a term on alphainv_cum + a term on cum_weights - against CPU autograd on the
+    oracle: gradients of sdf.grid, k0.grid, every rgbnet tensor, sdf_alpha and sdf_beta."""
+    from oracle import voxurf_cpu
+    from poseprobe_b200 import voxurf
+    G, N = 40, 1024
+    sdf, k0, net, o, d, v, target, kw = make_scene(G, N, seed=40)
+    mod = voxurf.Voxurf(MN, MX, num_voxels=G ** 3, num_voxels_base=G ** 3, rgbnet_depth=4, posbase_pe=5, viewbase_pe=1,
+                        barf_c2f=None).to(cuda)
+    assert tuple(mod.sdf.grid.shape) == (1, 1, G, G, G)
+    state = {"sdf.grid": sdf, "k0.grid": k0}
+    for name, p in net.state_dict().items():
+        state["rgbnet." + name] = p
+    missing, unexpected = mod.load_state_dict(state, strict=False)
+    assert not unexpected and set(missing) <= {"xyz_min", "xyz_max", "sdf.xyz_min", "sdf.xyz_max", "k0.xyz_min",
+                                               "k0.xyz_max", "sdf_alpha", "sdf_beta", "s_val"}
+    with torch.no_grad():
+        mod.sdf_alpha.fill_(10.0)
+        mod.sdf_beta.fill_(0.35)
+        mod.s_val.fill_(kw["s_val"])
+    rk = dict(near=0.2, far=1e9, stepsize=kw["stepsize"], bg=kw["bg"])
+
+    def loss_of(out, tgt):
+        last = out["alphainv_cum"].clamp(1e-6, 1 - 1e-6)
+        return torch.nn.functional.mse_loss(out["rgb_marched"], tgt) \
+            + 0.01 * (-(last * last.log() + (1 - last) * (1 - last).log())).mean() + 0.05 * out["cum_weights"].mean()
+
+    out = mod(o.to(cuda), d.to(cuda), v.to(cuda), global_step=None, **rk)
+    loss = loss_of(out, target.to(cuda))
+    loss.backward()
+    # oracle with differentiable mapping parameters
+    sdf_r, k0_r = sdf.clone().requires_grad_(True), k0.clone().requires_grad_(True)
+    al, be = torch.tensor(10.0, requires_grad=True), torch.tensor(0.35, requires_grad=True)
+    a_eff = torch.nn.functional.softplus(al, beta=10)
+    b_eff = torch.nn.functional.softplus(be, beta=10)
+    mapped = a_eff * (torch.sigmoid(b_eff * sdf_r) - 0.5)
+    ref = voxurf_cpu.forward(mapped, k0_r, net, o, d, v, MN, MX, kw["stepsize"], float(mod.voxel_size), kw["s_val"],
+                             bg=kw["bg"], sdf_alpha=None, posbase_pe=5, viewbase_pe=1, barf_c2f=None)
+    loss_r = loss_of(ref, target)
+    loss_r.backward()
+    assert abs(float(loss) - float(loss_r)) < 2e-2 * float(loss_r)
+    lin = [m for m in net.modules() if isinstance(m, nn.Linear)]
+    lin_m = [m for m in mod.rgbnet.modules() if isinstance(m, nn.Linear)]
+    rep = {"sdf": (_cos(mod.sdf.grid.grad.cpu(), sdf_r.grad), float(mod.sdf.grid.grad.norm() / sdf_r.grad.norm())),
+           "k0": (_cos(mod.k0.grid.grad.cpu(), k0_r.grad), float(mod.k0.grid.grad.norm() / k0_r.grad.norm()))}
+    for i, (a, b) in enumerate(zip(lin_m, lin)):
+        rep["W%d" % i] = (_cos(a.weight.grad.cpu(), b.weight.grad), float(a.weight.grad.norm() / b.weight.grad.norm()))
+    print(rep, float(mod.sdf_alpha.grad), float(al.grad), float(mod.sdf_beta.grad), float(be.grad))
+    for k, (c, ratio) in rep.items():
+        assert c > 0.99 and 0.9 < ratio < 1.1, (k, rep)
+    assert abs(float(mod.sdf_alpha.grad) - float(al.grad)) < 0.05 * abs(float(al.grad)) + 1e-7
+    assert abs(float(mod.sdf_beta.grad) - float(be.grad)) < 0.05 * abs(float(be.grad)) + 1e-7

@@ -77,7 +77,7 @@ def main():
     t_back = timeit(lambda: check(lib.pp_voxurf_backward(
         ctypes.byref(eng.scene), ctypes.byref(eng.cfg), ptr(o), ptr(d), ptr(v), None, N, ptr(b["rec"]), ptr(b["gw"]),
         ptr(b["dx"]), 16, ptr(b["ray_off"]), ptr(b["ray_cnt"]), ptr(b["ray_end"]), ptr(b["g_ray"]), ptr(eng.g_srec),
-        ptr(eng.g_k0rec), None, None, None, None, stream()), "back"))
+        ptr(eng.g_k0rec), None, None, None, None, None, None, stream()), "back"))
     t_opt = timeit(eng.optimizer_step)
     flops = 2.0 * m * (64 * 128 + 128 * 128 * 2 + 128 * 16) * 4     # fwd + recompute + 2x bwd, padded shapes
     line = {"workload": "Voxurf SDF fine stage (BASELINE configs[2], one rank): %d^3 sdf + 12-ch k0, rgbnet 57-128x3-3, "
