@@ -327,6 +327,28 @@ def run_ours(args, rank, world, local_rank):
     }
     if exchange_breakdown:
         line["step_roofline"]["exchange_breakdown"] = exchange_breakdown
+    if world == 1:
+        try:    # the same step with the total-variation term of SURVEY 8(d) switched on (dense mode, fused with Adam)
+            tv_eng = dvgo.FusedDVGO(density.to(dev), k0.to(dev), XYZ_MIN, XYZ_MAX, stepsize=STEPSIZE, tv_density=5e-3,
+                                    tv_k0=1e-2, tv_dense=True)
+            for i in range(5):
+                tv_eng.train_step(*resident[i % N_BATCHES])
+            torch.cuda.synchronize()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for i in range(30):
+                tv_eng.train_step(*resident[i % N_BATCHES])
+            t1.record()
+            torch.cuda.synchronize()
+            tv_ms = t0.elapsed_time(t1) / 30
+            tv_bytes = step_bytes + 12 * V * (C_d + C_f)
+            line["tv_on"] = {"workload": "same step with total_variation_add_grad (dense mode) fused into the Adam pass",
+                             "train_rays_per_s": RAYS / (tv_ms * 1e-3), "ms_per_step": tv_ms,
+                             "algorithmic_bytes_per_step": tv_bytes,
+                             "frac_of_hbm_peak": tv_bytes / (tv_ms * 1e-3) / 1e9 / pk["hbm_gbs"]}
+            del tv_eng
+        except Exception as e:
+            line["tv_on"] = {"error": str(e)[:200]}
     if world == 1 and not args.no_fine_stage:
         try:
             line["fine_stage"] = fine_stage_bench(dev)
