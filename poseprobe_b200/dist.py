@@ -125,6 +125,7 @@ class DistributedDVGO:
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        auto = mode == "auto"
         if mode == "auto":
             # measured on 8xB200 (profiles/r1_results.md): in-switch reduction wins at 8 ranks, plain peer
             # loads/stores at 2 and 4 (their link traffic 2(w-1)/w is below NVLS's (w+1)/w there)
@@ -143,10 +144,23 @@ class DistributedDVGO:
         # two gradient buffers: while step k+1 marches into one, the other (already consumed by step k's
         # exchange) is zeroed on a side stream, off the critical path
         if self.mode == "nvls":
-            self.vox_mem = SymmRecords(n, dev, group, self.world)
-            self.grad_mems = [SymmRecords(n, dev, group, self.world) for _ in range(2)]
-            if not (self.vox_mem.multicast_ptr and all(g.multicast_ptr for g in self.grad_mems)):
-                raise RuntimeError("DistributedDVGO(mode='nvls'): no multicast address (NVSwitch/NVLS not available)")
+            ok = True
+            try:
+                self.vox_mem = SymmRecords(n, dev, group, self.world)
+                self.grad_mems = [SymmRecords(n, dev, group, self.world) for _ in range(2)]
+                ok = bool(self.vox_mem.multicast_ptr and all(g.multicast_ptr for g in self.grad_mems))
+            except Exception as e:      # no symmetric memory / multicast on this system
+                ok = False
+                err = e
+            # every rank must take the same path: agree on the outcome before continuing
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if not int(flag):
+                if not auto:
+                    raise RuntimeError("DistributedDVGO(mode='nvls'): no multicast address "
+                                       "(NVSwitch/NVLS or torch symmetric memory not available)")
+                self.mode = "p2p"       # auto mode: fall back to peer loads / stores over NVLink
+                self.vox_mem = self.grad_mems = None
         if self.mode == "p2p":
             self.vox_mem = SharedRecords(n, dev)
             self.grad_mems = [SharedRecords(n, dev) for _ in range(2)]
