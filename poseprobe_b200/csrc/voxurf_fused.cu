@@ -422,39 +422,72 @@ voxurf_backward_kernel(pp_dvgo_scene sc, pp_voxurf_cfg cfg, const float* __restr
       }
       const float back_i = back + (S - contrib);
       back += __shfl_sync(kFull, S, 0);
-      if (!live) continue;
-      const float d_alpha = gwv * T - back_i / (1.f - alpha + 1e-10f);
-      const float4 rc = rec[slot];
-      const float gg[3] = {rc.y, rc.z, rc.w};
-      float g_sdf, g_tc;
-      neus_backward(neus_terms(rc.x, gg, v, sc.stepdist, cfg.inv_s), d_alpha, sc.stepdist, cfg.inv_s, g_sdf, g_tc);
-      // input-gradient columns of the MLP: 12 feature channels, 3 normal components
-      const float4* dxp = reinterpret_cast<const float4*>(dx16 + (int64_t)slot * dx_pitch);
-      const float4 d0 = dxp[0], d1 = dxp[1], d2 = dxp[2], d3 = dxp[3];
-      // normal = g / (|g| + 1e-5): d g_b = dn_b / (r + e) - g_b (g . dn) / (r (r + e)^2)
-      const float rn = sqrtf(gg[0] * gg[0] + gg[1] * gg[1] + gg[2] * gg[2]);
-      const float inv = 1.f / (rn + 1e-5f);
-      const float dot = gg[0] * d3.x + gg[1] * d3.y + gg[2] * d3.z;
-      const float kk = rn > 0.f ? dot * inv * inv / rn : 0.f;
-      float4 ds;
-      ds.x = g_sdf;
-      ds.y = g_tc * v[0] + d3.x * inv - gg[0] * kk;
-      ds.z = g_tc * v[1] + d3.y * inv - gg[1] * kk;
-      ds.w = g_tc * v[2] + d3.z * inv - gg[2] * kk;
-      float p[3];
-      vox_point(sc, ray, i, jit, p);
-      const Cell c = make_cell(sc, p[0], p[1], p[2]);
+      // per-sample gradients of the interpolated records (zero for lanes without a sample)
+      const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 ds = zero4, d0 = zero4, d1 = zero4, d2 = zero4;
+      float gg[3] = {0.f, 0.f, 0.f};
+      float g_tc = 0.f;
+      float p[3] = {ray.start[0], ray.start[1], ray.start[2]};
+      Cell c;
+      c.base = 0;
+      if (live) {
+        const float d_alpha = gwv * T - back_i / (1.f - alpha + 1e-10f);
+        const float4 rc = rec[slot];
+        gg[0] = rc.y;
+        gg[1] = rc.z;
+        gg[2] = rc.w;
+        float g_sdf;
+        neus_backward(neus_terms(rc.x, gg, v, sc.stepdist, cfg.inv_s), d_alpha, sc.stepdist, cfg.inv_s, g_sdf, g_tc);
+        // input-gradient columns of the MLP: 12 feature channels, 3 normal components
+        const float4* dxp = reinterpret_cast<const float4*>(dx16 + (int64_t)slot * dx_pitch);
+        d0 = dxp[0];
+        d1 = dxp[1];
+        d2 = dxp[2];
+        const float4 d3 = dxp[3];
+        // normal = g / (|g| + 1e-5): d g_b = dn_b / (r + e) - g_b (g . dn) / (r (r + e)^2)
+        const float rn = sqrtf(gg[0] * gg[0] + gg[1] * gg[1] + gg[2] * gg[2]);
+        const float inv = 1.f / (rn + 1e-5f);
+        const float dot = gg[0] * d3.x + gg[1] * d3.y + gg[2] * d3.z;
+        const float kk = rn > 0.f ? dot * inv * inv / rn : 0.f;
+        ds.x = g_sdf;
+        ds.y = g_tc * v[0] + d3.x * inv - gg[0] * kk;
+        ds.z = g_tc * v[1] + d3.y * inv - gg[1] * kk;
+        ds.w = g_tc * v[2] + d3.z * inv - gg[2] * kk;
+        vox_point(sc, ray, i, jit, p);
+        c = make_cell(sc, p[0], p[1], p[2]);
+      }
+      // scatter.  Neighbouring lanes are neighbouring steps (half a voxel apart) and often sit in the same cell:
+      // such pairs are merged with shuffles so that the pair issues 32 reductions instead of 64 (the kernel is
+      // bound by the L2 reduction rate: 32 sector operations per sample otherwise)
+      const int key = live ? c.base : (-1 - lane);
+      const int key_up = __shfl_down_sync(kFull, key, 1);
+      const int key_dn = __shfl_up_sync(kFull, key, 1);
+      const unsigned heads = __ballot_sync(kFull, lane == 0 || key != key_dn);
+      const int run_start = 31 - __clz(heads & ((2u << lane) - 1u));
+      const bool even_pos = ((lane - run_start) & 1) == 0;
+      const bool absorb = live && lane < 31 && key_up == key && even_pos;
+      const bool absorbed = live && lane > 0 && key_dn == key && !even_pos;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const float wq = corner_w(c, q);
-        if (wq == 0.f) continue;
-        const int64_t co = corner_off(c, q);
-        red_add_v4(g_srec + co, wq * ds.x, wq * ds.y, wq * ds.z, wq * ds.w);
-        float4* kdst = g_k0rec + co * 3;
-        red_add_v4(kdst, wq * d0.x, wq * d0.y, wq * d0.z, wq * d0.w);
-        red_add_v4(kdst + 1, wq * d1.x, wq * d1.y, wq * d1.z, wq * d1.w);
-        red_add_v4(kdst + 2, wq * d2.x, wq * d2.y, wq * d2.z, wq * d2.w);
+        const float wq = live ? corner_w(c, q) : 0.f;
+        float a[16] = {wq * ds.x, wq * ds.y, wq * ds.z, wq * ds.w, wq * d0.x, wq * d0.y, wq * d0.z, wq * d0.w,
+                       wq * d1.x, wq * d1.y, wq * d1.z, wq * d1.w, wq * d2.x, wq * d2.y, wq * d2.z, wq * d2.w};
+        const float wq_up = __shfl_down_sync(kFull, wq, 1);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float up = __shfl_down_sync(kFull, a[j], 1);
+          if (absorb) a[j] += up;
+        }
+        if (live && !absorbed && (wq != 0.f || (absorb && wq_up != 0.f))) {
+          const int64_t co = corner_off(c, q);
+          red_add_v4(g_srec + co, a[0], a[1], a[2], a[3]);
+          float4* kdst = g_k0rec + co * 3;
+          red_add_v4(kdst, a[4], a[5], a[6], a[7]);
+          red_add_v4(kdst + 1, a[8], a[9], a[10], a[11]);
+          red_add_v4(kdst + 2, a[12], a[13], a[14], a[15]);
+        }
       }
+      if (!live) continue;
       if (kPose) {
         // d loss / d point: through the SDF record interpolation, the 12 feature channels, the positional
         // encoding columns of the MLP input; d loss / d viewdirs: NeuS cosine and the view columns
