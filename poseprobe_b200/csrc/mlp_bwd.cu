@@ -3,8 +3,8 @@
 //
 // The reference trains the colour network through autograd over nn.Linear / ReLU (cuBLAS sgemm) with the
 // [M,d0] feature matrix, three [M,128] activations and their gradients round-tripping HBM
-// (lib/voxurf_coarse.py:208-216, :1032-1033).  Here one persistent CTA per SM (8 warps) owns tiles of 128
-// samples:
+// (lib/voxurf_coarse.py:208-216, :1032-1033).  Here one persistent CTA per SM (16 epilogue warps + 1 MMA-issue
+// warp) owns tiles of 128 samples:
 //   forward   : as mlp.cu, but every hidden activation tile H_l stays in shared memory (bf16, UMMA canonical
 //               layout) - they are the operands of the backward;
 //   dZ_L      : (d loss / d rgb) * rgb (1 - rgb), rounded to bf16 into a [128 x 16] tile;
@@ -12,9 +12,9 @@
 //                                              shared-memory copy the forward used (no transposed copy)
 //               dW_l    += dZ_l^T H_{l-1}      both operands read MN-major from the activation tiles: the
 //                                              contraction runs over the tile's 128 samples
-//               db_l    += dZ_l^T 1            an N=16 MMA against an indicator tile (column l is ones)
+//               db_l    += dZ_l^T 1            an N=16 MMA against a tile of ones
 //               dZ_{l-1} = dH_{l-1} * (H_{l-1} > 0) is written in place of H_{l-1};
-//   the weight / bias gradients of ALL the CTA's tiles accumulate in TMEM (fp32, 336..496 of the 512 columns)
+//   the weight / bias gradients of ALL the CTA's tiles accumulate in TMEM (fp32, up to 496 of the 512 columns)
 //   and are added to global memory once per CTA at the end.
 // MMAs that nothing waits for (dW, db) are issued behind the dH MMA of the same layer and run while the
 // epilogue warps turn dH into the next dZ.  Input rows arrive as bf16 [M, k0p] (k0p = 64 or 128; the feature
@@ -28,7 +28,6 @@
 
 namespace pp {
 
-constexpr int kBwdThreads = 512;
 constexpr int kBwdMaxDepth = 4;
 constexpr int kTile = 128;
 // TMEM columns (fp32, 128 lanes)
@@ -65,378 +64,17 @@ __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
-// request one 128-row tile of bf16 [M, k0p] rows: 16-byte pieces land at their UMMA canonical positions;
-// 8 consecutive threads read one 128-byte row segment, rows past M are zero-filled
-__device__ __forceinline__ void stage_tile(const __nv_bfloat16* __restrict__ x, int64_t M, int64_t tile, int k0p,
-                                           uint8_t* sX, int tid) {
-  const int chunks_per_row = k0p >> 3;
-  const uint32_t base = smem_u32(sX);
-  for (int id = tid; id < kTile * chunks_per_row; id += kBwdThreads) {
-    const int r = id / chunks_per_row, c8 = id - r * chunks_per_row;
-    const int64_t grow = tile * kTile + r;
-    const bool ok = grow < M;
-    cp_async16(base + canon_off(r, c8 * 8, k0p), x + (ok ? grow : 0) * k0p + c8 * 8, ok ? 16u : 0u);
-  }
-}
-
-__global__ void __launch_bounds__(kBwdThreads, 1)
-rgbnet_backward_kernel(MlpBwdParams P, const __nv_bfloat16* __restrict__ x, const float* __restrict__ grad_out,
-                       int64_t M, int apply_sigmoid, float* __restrict__ grad_x, float* __restrict__ rgb_out,
-                       MlpFusedIO F) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  if (F.n_ptr) M = min64(M, static_cast<int64_t>(*F.n_ptr));
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int L = P.depth;
-  const int row = (warp & 3) * 32 + lane;   // TMEM lane = sample row of the tile this thread owns
-  const int cg = warp >> 2;                 // which quarter of an accumulator's columns this thread handles
-  const int k0p = P.k0p, kq = k0p >> 2;     // kq: this thread's share of a k0p-wide accumulator (16 or 32)
-
-  // ---- shared memory map ----
-  uint32_t off = 0;
-  uint8_t* sXbuf[2];
-  sXbuf[0] = smem;
-  sXbuf[1] = smem + kTile * k0p * 2;
-  off += 2 * kTile * k0p * 2;
-  uint8_t* sH[kBwdMaxDepth];
-  for (int l = 0; l < L - 1; ++l) {
-    sH[l] = smem + off;
-    off += kTile * kMlpWidth * 2;
-  }
-  uint8_t* sG = smem + off;
-  off += kTile * kMlpOutPad * 2;
-  uint8_t* sW[kBwdMaxDepth];
-  for (int l = 0; l < L; ++l) {
-    sW[l] = smem + off;
-    const int rows = (l == L - 1) ? kMlpOutPad : kMlpWidth;
-    const int K = (l == 0) ? k0p : kMlpWidth;
-    off += rows * K * 2;
-  }
-  uint8_t* sOnes = smem + off;   // [128 x 16] of ones: B operand of the bias-gradient MMAs
-  off += kTile * kMlpOutPad * 2;
-  float* sBias = reinterpret_cast<float*>(smem + off);
-  off += L * kMlpWidth * 4;
-  float* sDbLast = reinterpret_cast<float*>(smem + off);
-  off += 16;
-  uint64_t* sBar = reinterpret_cast<uint64_t*>(smem + off);
-  uint32_t* sTmem = reinterpret_cast<uint32_t*>(smem + off + 16);
-
-  // ---- prologue: weights -> bf16 canonical layout (one 16-byte chunk = 8 inputs of one output row per
-  //      iteration, 8 independent loads), ones tile, biases, TMEM, mbarriers ----
-  for (int l = 0; l < L; ++l) {
-    const bool last = (l == L - 1);
-    const int rows = last ? kMlpOutPad : kMlpWidth;
-    const int real_rows = last ? 3 : kMlpWidth;
-    const int K = (l == 0) ? k0p : kMlpWidth;
-    const int real_K = (l == 0) ? P.d0 : kMlpWidth;
-    const int cpr = K >> 3;
-    for (int e = tid; e < rows * cpr; e += kBwdThreads) {
-      const int r = e / cpr, k0 = (e - r * cpr) * 8;
-      float f[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = (r < real_rows && k0 + j < real_K) ? __ldg(P.w[l] + r * real_K + k0 + j) : 0.f;
-      uint4 pk;
-      pk.x = pack_bf16(f[0], f[1]);
-      pk.y = pack_bf16(f[2], f[3]);
-      pk.z = pack_bf16(f[4], f[5]);
-      pk.w = pack_bf16(f[6], f[7]);
-      *reinterpret_cast<uint4*>(sW[l] + canon_off(r, k0, K)) = pk;
-    }
-    for (int e = tid; e < kMlpWidth; e += kBwdThreads)
-      sBias[l * kMlpWidth + e] = (e < real_rows) ? P.b[l][e] : 0.f;
-  }
-  for (int e = tid; e < kTile * kMlpOutPad; e += kBwdThreads)
-    reinterpret_cast<__nv_bfloat16*>(sOnes)[e] = __float2bfloat16_rn(1.f);
-  if (tid < 4) sDbLast[tid] = 0.f;
-  if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(sTmem)),
-                 "r"(512)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (tid == 0) {
-    mbar_init(smem_u32(sBar), 1);
-    mbar_init(smem_u32(sBar + 1), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  fence_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *sTmem;
-  const uint32_t barA = smem_u32(sBar), barB = smem_u32(sBar + 1);
-  uint32_t phA = 0, phB = 0;
-  const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-  const uint32_t idesc_fwd = umma_idesc_bf16(kTile, kMlpWidth);
-  const int c0 = cg * 32;                   // this thread's 32 columns of a 128-wide accumulator
-
-  bool first = true;
-  int it = 0;
-  const int64_t n_tiles = (M + kTile - 1) / kTile;
-  if (blockIdx.x < n_tiles) stage_tile(x, M, blockIdx.x, k0p, sXbuf[0], tid);
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t grow = tile * kTile + row;
-    const bool valid = grow < M;
-
-    // ---- input tile: it was requested while the previous tile computed; request the next one now ----
-    uint8_t* sX = sXbuf[it & 1];
-    cp_async_wait_all();
-    float gz[3] = {0.f, 0.f, 0.f};   // d loss / d out of this thread's row, consumed after the forward
-    float gr[3] = {0.f, 0.f, 0.f};   // fused mode: d loss / d rgb_marched of the row's ray
-    if (cg == 0 && valid) {
-      if (F.w) {
-        const float wv = __ldg(F.w + grow);
-        const int64_t rid = __ldg(F.ray_id + grow);
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          gr[j] = __ldg(F.g_ray + rid * 3 + j);
-          gz[j] = wv * gr[j];
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 3; ++j) gz[j] = __ldg(grad_out + grow * 3 + j);
-      }
-    }
-    fence_async_smem();
-    __syncthreads();
-    if (tile + gridDim.x < n_tiles) stage_tile(x, M, tile + gridDim.x, k0p, sXbuf[(it + 1) & 1], tid);
-    ++it;
-
-    // ---- forward, hidden layers: H_l = relu(H_{l-1} W_l^T + b_l), kept in shared memory ----
-    for (int l = 0; l < L - 1; ++l) {
-      if (warp == 0) {   // warp-uniform MMA issue
-        tc_fence_after();
-        const int K = (l == 0) ? k0p : kMlpWidth;
-        const uint32_t a0 = smem_u32(l == 0 ? sX : sH[l - 1]), b0 = smem_u32(sW[l]);
-        for (int k = 0; k < (K >> 4); ++k)
-          umma_bf16(tmem + kColAcc, desc_kmajor(a0, K, k), desc_kmajor(b0, K, k), idesc_fwd, k > 0);
-        umma_commit(barA);
-      }
-      mbar_wait(barA, phA);
-      phA ^= 1;
-      tc_fence_after();
-      {
-        uint32_t r[32];
-        tmem_ld32_nowait(tmem + kColAcc + lane_base + c0, r);
-        const float4* b4 = reinterpret_cast<const float4*>(sBias + l * kMlpWidth + c0);
-        float4 bb[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) bb[j] = b4[j];
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          *reinterpret_cast<uint4*>(sH[l] + canon_off(row, c0 + 8 * j, kMlpWidth)) =
-              bias_relu_pack8(r + 8 * j, bb[2 * j], bb[2 * j + 1]);
-      }
-      tc_fence_before();
-      fence_async_smem();
-      __syncthreads();
-    }
-
-    // ---- forward, output layer + gradient of the logits ----
-    if (warp == 0) {   // warp-uniform MMA issue
-      tc_fence_after();
-      const uint32_t a0 = smem_u32(sH[L - 2]), b0 = smem_u32(sW[L - 1]);
-      const uint32_t idesc = umma_idesc_bf16(kTile, kMlpOutPad);
-      for (int k = 0; k < (kMlpWidth >> 4); ++k)
-        umma_bf16(tmem + kColOut, desc_kmajor(a0, kMlpWidth, k), desc_kmajor(b0, kMlpWidth, k), idesc, k > 0);
-      umma_commit(barA);
-    }
-    mbar_wait(barA, phA);
-    phA ^= 1;
-    tc_fence_after();
-    if (cg == 0) {
-      float v[16];
-      tmem_ld16(tmem + kColOut + lane_base, v);
-      const float* bias = sBias + (L - 1) * kMlpWidth;
-      float dz[3];
-      float gw_acc = 0.f;
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const float z = v[j] + bias[j];
-        const float y = apply_sigmoid ? 1.f / (1.f + __expf(-z)) : z;
-        const float g = gz[j];
-        dz[j] = apply_sigmoid ? g * y * (1.f - y) : g;
-        gw_acc += gr[j] * y;
-        if (rgb_out && valid) rgb_out[grow * 3 + j] = y;
-      }
-      if (F.gw_out && valid) F.gw_out[grow] = gw_acc;
-      uint4 pk;
-      pk.x = pack_bf16(dz[0], dz[1]);
-      pk.y = pack_bf16(dz[2], 0.f);
-      pk.z = 0u;
-      pk.w = 0u;
-      *reinterpret_cast<uint4*>(sG + canon_off(row, 0, kMlpOutPad)) = pk;
-      *reinterpret_cast<uint4*>(sG + canon_off(row, 8, kMlpOutPad)) = make_uint4(0u, 0u, 0u, 0u);
-      // last-layer bias gradient: column sums of dZ_L over the tile (3 values: done on the CUDA cores)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const float s = warp_sum(dz[j]);
-        if (lane == 0) atomicAdd(&sDbLast[j], s);
-      }
-    }
-    tc_fence_before();
-    fence_async_smem();
-    __syncthreads();
-
-    // ---- backward ----
-    if (warp == 0) {   // warp-uniform MMA issue
-      tc_fence_after();
-      const uint32_t h0 = smem_u32(sH[L - 2]), g0 = smem_u32(sG), w0 = smem_u32(sW[L - 1]);
-      // dW_last^T += H_{L-2}^T dZ_L : M = 128 input features, N = 16, contraction over the samples
-      const uint32_t id_wl = umma_idesc_bf16_major(kTile, kMlpOutPad, 1, 1);
-      for (int s = 0; s < (kTile >> 4); ++s)
-        umma_bf16(tmem + kColDwLast, desc_mnmajor(h0, kMlpWidth, s), desc_mnmajor(g0, kMlpOutPad, s), id_wl,
-                  (!first) || s > 0);
-      // dH_{L-2} = dZ_L W_L : contraction over the 16 (padded) outputs, one K slice
-      umma_bf16(tmem + kColAcc, desc_kmajor(g0, kMlpOutPad, 0), desc_mnmajor(w0, kMlpWidth, 0),
-                umma_idesc_bf16_major(kTile, kMlpWidth, 0, 1), 0);
-      umma_commit(barA);
-    }
-    for (int l = L - 2; l >= 0; --l) {
-      mbar_wait(barA, phA);
-      phA ^= 1;
-      tc_fence_after();
-      // dZ_l = dH_l * (H_l > 0), packed to bf16 in registers
-      uint4 pk[4];
-      {
-        uint32_t r[32];
-        tmem_ld32_nowait(tmem + kColAcc + lane_base + c0, r);
-        uint4 act[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          act[j] = *reinterpret_cast<const uint4*>(sH[l] + canon_off(row, c0 + 8 * j, kMlpWidth));
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 4; ++j) pk[j] = relu_grad_pack8(r + 8 * j, act[j]);
-      }
-      if (l < L - 2) {   // dW_{l+1} reads H_l (its B operand): it must have finished before H_l is overwritten
-        mbar_wait(barB, phB);
-        phB ^= 1;
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        *reinterpret_cast<uint4*>(sH[l] + canon_off(row, c0 + 8 * j, kMlpWidth)) = pk[j];
-      tc_fence_before();
-      fence_async_smem();
-      __syncthreads();
-      if (warp == 0) {   // warp-uniform MMA issue
-        tc_fence_after();
-        const uint32_t z0 = smem_u32(sH[l]), w0 = smem_u32(sW[l]);
-        if (l > 0) {
-          // dH_{l-1} = dZ_l W_l : contraction over this layer's 128 outputs
-          const uint32_t id = umma_idesc_bf16_major(kTile, kMlpWidth, 0, 1);
-          for (int s = 0; s < (kMlpWidth >> 4); ++s)
-            umma_bf16(tmem + kColAcc, desc_kmajor(z0, kMlpWidth, s), desc_mnmajor(w0, kMlpWidth, s), id, s > 0);
-        } else if (grad_x) {
-          // dX = dZ_0 W_0
-          const uint32_t id = umma_idesc_bf16_major(kTile, k0p, 0, 1);
-          for (int s = 0; s < (kMlpWidth >> 4); ++s)
-            umma_bf16(tmem + kColAcc, desc_kmajor(z0, kMlpWidth, s), desc_mnmajor(w0, k0p, s), id, s > 0);
-        }
-        umma_commit(barA);
-        // dW_l += dZ_l^T H_{l-1} : both operands MN-major, contraction over the samples
-        const int in = (l == 0) ? k0p : kMlpWidth;
-        const uint32_t t0 = smem_u32(l == 0 ? sX : sH[l - 1]);
-        const uint32_t col = (l == 0) ? kColDw0 : kColDw0 + k0p + (l - 1) * kMlpWidth;
-        const uint32_t id_w = umma_idesc_bf16_major(kTile, in, 1, 1);
-        for (int s = 0; s < (kTile >> 4); ++s)
-          umma_bf16(tmem + col, desc_mnmajor(z0, kMlpWidth, s), desc_mnmajor(t0, in, s), id_w, (!first) || s > 0);
-        // db_l += dZ_l^T 1 (every one of the layer's 16 columns receives the column sums)
-        const uint32_t o0 = smem_u32(sOnes);
-        const uint32_t id_b = umma_idesc_bf16_major(kTile, kMlpOutPad, 1, 1);
-        for (int s = 0; s < (kTile >> 4); ++s)
-          umma_bf16(tmem + kColDb + l * kMlpOutPad, desc_mnmajor(z0, kMlpWidth, s),
-                    desc_mnmajor(o0, kMlpOutPad, s), id_b, (!first) || s > 0);
-        umma_commit(barB);
-      }
-    }
-    mbar_wait(barA, phA);
-    phA ^= 1;
-    tc_fence_after();
-    if (grad_x) {
-      // this thread's kq columns of dX, fp32 rows of k0p
-      const int cx = cg * kq;
-      if (kq == 32) {
-        float v[32];
-        tmem_ld32(tmem + kColAcc + lane_base + cx, v);
-        if (valid && cx < F.dx_cols) {
-          float4* dst = reinterpret_cast<float4*>(grad_x + grow * F.dx_cols + cx);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
-      } else {
-        float v[16];
-        tmem_ld16(tmem + kColAcc + lane_base + cx, v);
-        if (valid && cx < F.dx_cols) {
-          float4* dst = reinterpret_cast<float4*>(grad_x + grow * F.dx_cols + cx);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
-      }
-    }
-    mbar_wait(barB, phB);   // dW_0 read the X tile: done before the next tile is staged
-    phB ^= 1;
-    tc_fence_before();
-    __syncthreads();
-    first = false;
-  }
-
-  // ---- the CTA's weight / bias gradients: TMEM -> global (fp32 atomics, once per CTA) ----
-  tc_fence_after();
-  if (!first) {
-    for (int l = 1; l < L - 1; ++l) {
-      const uint32_t col = kColDw0 + k0p + (l - 1) * kMlpWidth;
-      float v[32];
-      tmem_ld32(tmem + col + lane_base + c0, v);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) atomicAdd(P.gw[l] + row * kMlpWidth + c0 + j, v[j]);
-    }
-    {
-      const int cx = cg * kq;
-      if (kq == 32) {
-        float v[32];
-        tmem_ld32(tmem + kColDw0 + lane_base + cx, v);
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (cx + j < P.d0) atomicAdd(P.gw[0] + row * P.d0 + cx + j, v[j]);
-      } else {
-        float v[16];
-        tmem_ld16(tmem + kColDw0 + lane_base + cx, v);
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (cx + j < P.d0) atomicAdd(P.gw[0] + row * P.d0 + cx + j, v[j]);
-      }
-    }
-    if (cg == 0) {
-      float v[16];
-      tmem_ld16(tmem + kColDwLast + lane_base, v);
-#pragma unroll
-      for (int o = 0; o < 3; ++o) atomicAdd(P.gw[L - 1] + o * kMlpWidth + row, v[o]);
-    } else if (cg == 1) {
-      for (int l = 0; l < L - 1; ++l) {
-        float v[16];
-        tmem_ld16(tmem + kColDb + l * kMlpOutPad + lane_base, v);
-        atomicAdd(P.gb[l] + row, v[0]);
-      }
-    }
-    if (tid < 3) atomicAdd(P.gb[L - 1] + tid, sDbLast[tid]);
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
-}
-
 // =====================================================================================================
-// v2: warp-specialised, half-pipelined schedule of the same computation.
+// Schedule: warp-specialised and half-pipelined.
 //
 // The epilogue of a 128 x 128 fp32 accumulator is bounded by the TMEM read port (64 B/clk = 1024 cycles), the
-// layer's MMAs take 544 cycles, and in v1 the two run strictly one after the other with a block barrier in
-// between.  Here warp 16 only issues MMAs and the 16 epilogue warps are split in two halves by accumulator
-// column (0..63 / 64..127), each with its own "drained / written" barrier: the next layer's first four K-slices
-// only need the first half of this layer's output:
-//     drain(half 0) | MMA(next, k 0..3) overlaps drain(half 1) | MMA(next, k 4..7) -> drain(next) ...
-// so tcgen05.ld is busy almost continuously and the tensor pipe works underneath it (dW / db MMAs fill the rest).
+// layer's MMAs take 516 cycles; a schedule that runs the two strictly one after the other with a block barrier in
+// between (the first version of this kernel, 1.79 ms for 2.73 M samples against 1.77 ms here) leaves both idle
+// half of the time.  Here warp 16 only issues MMAs and the 16 epilogue warps are split in two halves by accumulator
+// column (0..63 / 64..127), each with its own "drained / written" barrier.  The next layer's N=128 MMAs overwrite the
+// whole working accumulator, so they are issued once both halves have published; the layer's dW / db MMAs are
+// queued behind them and run underneath the next drain.  (Splitting every layer into N=64 groups so that half 0's
+// successor can start early was measured: same time, 50 % more MMA issue slots - N=64 costs 48 cycles, N=128 64.)
 // Synchronisation is mbarrier-only (no block barrier inside a tile):
 //     acc_ready[h]  MMA -> epilogue half h   (tcgen05.commit)
 //     epi_done[h]   epilogue half h -> MMA   (256 arrivals: operand tile written / accumulator half drained)
@@ -643,14 +281,14 @@ rgbnet_backward2_kernel(MlpBwdParams P, const __nv_bfloat16* __restrict__ x, con
         group(tmem + kColAcc, xb ? dXk[1] : dXk[0], kStepK, dWk[0], kStepK, id_f128, k0p >> 4, 0);
         umma_commit(bAcc[0]);
         umma_commit(bAcc[1]);
-        // ---- forward layers 1 .. L-2: the first four K slices only need the first half of the layer below ----
+        // ---- forward layers 1 .. L-2.  An N=128 MMA overwrites all 128 accumulator columns, so BOTH halves of
+        //      the previous layer must have been drained (and written) before the first one is issued ----
 #pragma unroll
         for (int l = 1; l < kBwdMaxDepth - 1; ++l) {
           if (l < L - 1) {
             wait_epi(0);
-            group(tmem + kColAcc, dHk[l - 1], kStepK, dWk[l], kStepK, id_f128, 4, 0);
             wait_epi(1);
-            group(tmem + kColAcc, dHk[l - 1] + 4 * kStepK, kStepK, dWk[l] + 4 * kStepK, kStepK, id_f128, 4, 1);
+            group(tmem + kColAcc, dHk[l - 1], kStepK, dWk[l], kStepK, id_f128, 8, 0);
             umma_commit(bAcc[0]);
             umma_commit(bAcc[1]);
           }
@@ -682,9 +320,8 @@ rgbnet_backward2_kernel(MlpBwdParams P, const __nv_bfloat16* __restrict__ x, con
             const uint32_t stepB = (l == 0) ? stepMnX : kStepMn128;
             const uint32_t id0 = (l == 0) ? id_dx : id_b128;
             wait_epi(0);
-            if (want) group(tmem + kColAcc, dHk[l], kStepK, dWmn[l], stepB, id0, 4, 0);
             wait_epi(1);
-            if (want) group(tmem + kColAcc, dHk[l] + 4 * kStepK, kStepK, dWmn[l] + 4 * stepB, stepB, id0, 4, 1);
+            if (want) group(tmem + kColAcc, dHk[l], kStepK, dWmn[l], stepB, id0, 8, 0);
             umma_commit(bAcc[0]);
             umma_commit(bAcc[1]);
             // dW_l += dZ_l^T H_{l-1}, db_l += dZ_l^T 1 : nothing waits for them except the tiles' next writers
@@ -1049,12 +686,7 @@ static int launch_rgbnet_backward(const void* x_packed, const float* grad_out, i
   PP_REQUIRE(smem <= 227 * 1024, PP_ERR_UNSUPPORTED, "rgbnet_backward: %zu B of shared memory needed", smem);
   const int64_t n_tiles = (n_pts + kTile - 1) / kTile;
   const int blocks = (int)min64(n_tiles, sm_count());
-  const char* ve = getenv("PP_MLP_BWD");
-  if (ve && atoi(ve) == 1) {   // v1 schedule (block barriers, one phase at a time): kept for A/B timing
-    PP_CHECK_CUDA(cudaFuncSetAttribute(rgbnet_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rgbnet_backward_kernel<<<blocks, kBwdThreads, smem, as_stream(stream)>>>(
-        P, (const __nv_bfloat16*)x_packed, grad_out, n_pts, apply_sigmoid, grad_x_padded, rgb_out, F);
-  } else {
+  {
     static int* err_flag = nullptr;   // device flag raised by a wait that ran out of its cycle budget
     static long long* prof = nullptr;
     if (!err_flag) {
