@@ -186,14 +186,16 @@ PP_API int pp_voxurf_k0_unpack(const void* k0_records, int64_t n_voxels, float* 
  * (int32), sample_rec (float4: interpolated SDF record).  Per ray: ray_off / ray_cnt (its slot range),
  * ray_end (exclusive step index where the march stopped), cum_w (sum of weights), alphainv_last.
  * counter: 2 x int32 on the device; counter[0] = samples written, counter[1] = 1 if `capacity` was too small
- * (rays that did not fit contribute nothing).  jitter (nullable): per-ray step offset in [0,1) (:712-713). */
+ * (rays that did not fit contribute nothing).  jitter (nullable): per-ray step offset in [0,1) (:712-713).
+ * depth [N] (nullable) = sum_i w_i * step_i with step_i = stepdist * (i + jitter) (n_step of :1052-1056; the render
+ * depth of :1198-1202), normal_marched [N,3] (nullable) = sum_i w_i * gradient_i / (|gradient_i| + 1e-6) (:1044-1048). */
 PP_API int pp_voxurf_march_features(const pp_dvgo_scene* scene, const pp_voxurf_cfg* cfg,
                                     const void* sdf_records, const void* k0_records, const float* rays_o,
                                     const float* rays_d, const float* viewdirs, const float* jitter,
                                     int64_t n_rays, int32_t capacity, void* feat, float* sample_weight,
                                     int32_t* sample_ray, void* sample_rec, int32_t* ray_off, int32_t* ray_cnt,
                                     int32_t* ray_end, float* cum_w, float* alphainv_last, int32_t* counter,
-                                    pp_stream_t stream);
+                                    float* depth, float* normal_marched, pp_stream_t stream);
 
 /* rgb_marched = clamp(rgb_acc + (1 - cum_w) bg, 0, 1) (:1040-1042); photometric MSE (lib/losses.py:26-29):
  * g_ray [N,3] = d (w_rgb * mse) / d rgb_acc, loss_out[0] += w_rgb * mse, loss_out[1] += mse. */

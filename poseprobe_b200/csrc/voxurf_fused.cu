@@ -115,7 +115,8 @@ voxurf_march_kernel(pp_dvgo_scene sc, pp_voxurf_cfg cfg, const float4* __restric
                     __nv_bfloat16* __restrict__ feat, float* __restrict__ w_out, int32_t* __restrict__ rid_out,
                     float4* __restrict__ rec_out, int32_t* __restrict__ ray_off, int32_t* __restrict__ ray_cnt,
                     int32_t* __restrict__ ray_end, float* __restrict__ cum_w, float* __restrict__ alphainv_last,
-                    int32_t* __restrict__ counter, unsigned int* __restrict__ queue, int cap) {
+                    int32_t* __restrict__ counter, unsigned int* __restrict__ queue, int cap,
+                    float* __restrict__ depth_out, float* __restrict__ normal_out) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4* s_rec = reinterpret_cast<float4*>(smem_raw) + (size_t)warp * cap;
@@ -134,6 +135,7 @@ voxurf_march_kernel(pp_dvgo_scene sc, pp_voxurf_cfg cfg, const float4* __restric
 
     // ---------------- phase 1: SDF gather, NeuS alpha, compositing ----------------
     float T_in = 1.f, cumw = 0.f;
+    float acc_depth = 0.f, acc_n[3] = {0.f, 0.f, 0.f};   // optional per-ray render outputs
     int n_live = 0, end = n_steps;
     for (int base = 0; base < n_steps; base += kWarp) {
       const int i = base + lane;
@@ -167,6 +169,14 @@ voxurf_march_kernel(pp_dvgo_scene sc, pp_voxurf_cfg cfg, const float4* __restric
       if (counted) {
         cumw += w;
         n_live += 1;
+        if (depth_out) acc_depth = fma_rn(w, sc.stepdist * (static_cast<float>(i) + jit), acc_depth);
+        if (normal_out) {
+          // normal_marched: segment_coo(w * gradient / (|gradient| + 1e-6)), voxurf_coarse.py:1044-1048
+          const float inv = w / (sqrtf(val.y * val.y + val.z * val.z + val.w * val.w) + 1e-6f);
+          acc_n[0] = fma_rn(val.y, inv, acc_n[0]);
+          acc_n[1] = fma_rn(val.z, inv, acc_n[1]);
+          acc_n[2] = fma_rn(val.w, inv, acc_n[2]);
+        }
       }
       T_in = __shfl_sync(kFull, T_after, last_lane);
       if (term) {
@@ -176,6 +186,19 @@ voxurf_march_kernel(pp_dvgo_scene sc, pp_voxurf_cfg cfg, const float4* __restric
     }
     n_live = __reduce_add_sync(kFull, n_live);
     cumw = warp_sum(cumw);
+    if (depth_out) {
+      acc_depth = warp_sum(acc_depth);
+      if (lane == 0) depth_out[r] = acc_depth;
+    }
+    if (normal_out) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) acc_n[k] = warp_sum(acc_n[k]);
+      if (lane == 0) {
+        normal_out[3 * r] = acc_n[0];
+        normal_out[3 * r + 1] = acc_n[1];
+        normal_out[3 * r + 2] = acc_n[2];
+      }
+    }
     int off = 0;
     if (lane == 0) {
       off = atomicAdd(counter, n_live);
@@ -713,7 +736,7 @@ extern "C" int pp_voxurf_march_features(const pp_dvgo_scene* scene, const pp_vox
                                         int64_t n_rays, int32_t capacity, void* feat, float* sample_weight,
                                         int32_t* sample_ray, void* sample_rec, int32_t* ray_off, int32_t* ray_cnt,
                                         int32_t* ray_end, float* cum_w, float* alphainv_last, int32_t* counter,
-                                        pp_stream_t stream) {
+                                        float* depth, float* normal_marched, pp_stream_t stream) {
   const int rc = check_vox_scene(scene, cfg, "voxurf_march_features");
   if (rc != PP_OK) return rc;
   PP_REQUIRE(n_rays >= 0 && capacity >= 0, PP_ERR_INVALID_ARG, "voxurf_march_features: negative extent");
@@ -743,7 +766,7 @@ extern "C" int pp_voxurf_march_features(const pp_dvgo_scene* scene, const pp_vox
   voxurf_march_kernel<<<(unsigned)blocks, warps * 32, smem, s>>>(
       *scene, *cfg, (const float4*)sdf_records, (const float4*)k0_records, rays_o, rays_d, viewdirs, jitter, n_rays,
       capacity, (__nv_bfloat16*)feat, sample_weight, sample_ray, (float4*)sample_rec, ray_off, ray_cnt, ray_end,
-      cum_w, alphainv_last, counter, queue, cap);
+      cum_w, alphainv_last, counter, queue, cap, depth, normal_marched);
   PP_CHECK_LAUNCH("voxurf_march_features");
   return PP_OK;
 }

@@ -212,13 +212,13 @@ class FusedVoxurf:
         return b
 
     # ---- forward pieces -----------------------------------------------------------------------------------------
-    def _march(self, b, rays_o, rays_d, viewdirs, jitter):
+    def _march(self, b, rays_o, rays_d, viewdirs, jitter, depth=None, normal=None):
         n = rays_o.shape[0]
         check(lib.pp_voxurf_march_features(
             ctypes.byref(self.scene), ctypes.byref(self.cfg), ptr(self.srec), ptr(self.k0rec), ptr(rays_o),
             ptr(rays_d), ptr(viewdirs), ptr(jitter), n, b["cap"], ptr(b["feat"]), ptr(b["w"]), ptr(b["rid"]),
             ptr(b["rec"]), ptr(b["ray_off"]), ptr(b["ray_cnt"]), ptr(b["ray_end"]), ptr(b["cum_w"]), ptr(b["last"]),
-            ptr(b["counter"]), stream()), "voxurf_march_features")
+            ptr(b["counter"]), ptr(depth), ptr(normal), stream()), "voxurf_march_features")
 
     def _mlp_forward(self, b, n):
         b["acc"][:n].zero_()
@@ -226,18 +226,26 @@ class FusedVoxurf:
                                            self._arr(self.biases), 1, None, ptr(b["w"]), ptr(b["rid"]), ptr(b["acc"]),
                                            ptr(b["counter"]), stream()), "rgbnet_forward")
 
-    def render(self, rays_o, rays_d, viewdirs):
-        """-> rgb_marched [N,3], alphainv_last [N], cum_weights [N]   (Voxurf.forward's render outputs)."""
+    def render(self, rays_o, rays_d, viewdirs, want_depth=False, want_normal=False):
+        """-> rgb_marched [N,3], alphainv_last [N], cum_weights [N] (+ depth [N], normal_marched [N,3] on request):
+        the per-ray outputs of Voxurf.forward / inference that lib/nvs_fun.py:74-88 reads."""
         for t, nme in ((rays_o, "rays_o"), (rays_d, "rays_d"), (viewdirs, "viewdirs")):
             _need_cuda(t, nme)
         n = rays_o.shape[0]
         b = self._buffers(n)
+        depth = torch.empty(n, dtype=torch.float32, device=self.device) if want_depth else None
+        normal = torch.empty((n, 3), dtype=torch.float32, device=self.device) if want_normal else None
         with torch.cuda.device(self.device):
-            self._march(b, rays_o, rays_d, viewdirs, None)
+            self._march(b, rays_o, rays_d, viewdirs, None, depth, normal)
             self._mlp_forward(b, n)
             check(lib.pp_voxurf_ray_loss(n, ptr(b["acc"]), ptr(b["cum_w"]), ptr(b["acc"]), self.scene.bg, 0.0,
                                          ptr(b["g_ray"]), ptr(b["rgb"]), None, stream()), "voxurf_ray_loss")
-        return b["rgb"][:n].clone(), b["last"][:n].clone(), b["cum_w"][:n].clone()
+        out = (b["rgb"][:n].clone(), b["last"][:n].clone(), b["cum_w"][:n].clone())
+        if want_depth:
+            out = out + (depth,)
+        if want_normal:
+            out = out + (normal,)
+        return out
 
     def n_samples(self):
         """Composited samples of the last march (host sync); raises if the sample capacity overflowed."""

@@ -107,10 +107,18 @@ def test_render_vs_oracle(cuda):
     G, N = 48, 1024
     sdf, k0, net, o, d, v, target, kw = make_scene(G, N, seed=2)
     eng = make_engine(sdf, k0, net, kw, cuda)
-    rgb, last, cumw = eng.render(o.to(cuda), d.to(cuda), v.to(cuda))
+    rgb, last, cumw, depth, normal = eng.render(o.to(cuda), d.to(cuda), v.to(cuda), want_depth=True, want_normal=True)
     with torch.no_grad():
         want = oracle_forward(sdf, k0, net, o, d, v, kw, eng.voxel_size, 1.0)
     torch.testing.assert_close(cumw.cpu(), want["cum_weights"][:, 0], rtol=0, atol=2e-4)
+    # depth (voxurf_coarse.py:1198-1202: segsum(w * step_id * dist)) and normal_marched (:1044-1048)
+    rid, w = want["ray_id"], want["weights"]
+    dist = kw["stepsize"] * eng.voxel_size
+    want_depth = torch.zeros(N).index_add_(0, rid, w * want["step_id"].float() * dist)
+    g = want["gradient"]
+    want_normal = torch.zeros(N, 3).index_add_(0, rid, w[:, None] * g / (g.norm(2, -1, keepdim=True) + 1e-6))
+    torch.testing.assert_close(depth.cpu(), want_depth, rtol=1e-4, atol=2e-4)
+    torch.testing.assert_close(normal.cpu(), want_normal, rtol=1e-3, atol=5e-4)
     torch.testing.assert_close(rgb.cpu(), want["rgb_marched"], rtol=0, atol=2e-2)
     assert float((rgb.cpu() - want["rgb_marched"]).abs().mean()) < 3e-3
 
