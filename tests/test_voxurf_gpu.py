@@ -435,3 +435,43 @@ def test_voxurf_module_autograd_vs_oracle(cuda):
         assert c > 0.99 and 0.9 < ratio < 1.1, (k, rep)
     assert abs(float(mod.sdf_alpha.grad) - float(al.grad)) < 0.05 * abs(float(al.grad)) + 1e-7
     assert abs(float(mod.sdf_beta.grad) - float(be.grad)) < 0.05 * abs(float(be.grad)) + 1e-7
+
+
+def test_non_cubic_grid_and_box(cuda):
+    """Anisotropic extents (X != Y != Z) and a non-cubic box as in configs/dtu_e2e/scan1.py (xyz_min/xyz_max):
+    record strides, the transposed central difference and the feature permutation must not assume a cube."""
+    from oracle import voxurf_cpu
+    from poseprobe_b200 import ops, synthetic, voxurf
+    torch.manual_seed(50)
+    X, Y, Z = 36, 28, 44
+    mn, mx = [-0.4, -0.35, -0.5], [0.45, 0.35, 0.6]
+    lx, ly, lz = [torch.linspace(a, b, n) for a, b, n in zip(mn, mx, (X, Y, Z))]
+    gx, gy, gz = torch.meshgrid(lx, ly, lz, indexing="ij")
+    sdf = ((gx * gx + gy * gy + gz * gz).sqrt() - 0.25 + 0.005 * torch.randn(X, Y, Z))[None, None].contiguous()
+    k0 = 0.3 * torch.randn(1, 12, X, Y, Z)
+    net = nn.Sequential(nn.Linear(57, 128), nn.ReLU(), nn.Linear(128, 128), nn.ReLU(), nn.Linear(128, 3))
+    with torch.no_grad():
+        net[0].weight.mul_(2.0)
+        net[-1].weight.mul_(4.0)
+    N = 768
+    o, d, v = synthetic.make_rays(N, seed=51, radius=1.5, target_half=0.3)
+    target = torch.rand(N, 3)
+    ws, bs = ops.rgbnet_from_sequential(net)
+    kw = dict(stepsize=0.5, s_val=0.03, bg=0.2, posbase_pe=5, viewbase_pe=1, barf_c2f=None, sdf_alpha=10.0,
+              sdf_beta=0.35)
+    eng = voxurf.FusedVoxurf(sdf.to(cuda), k0.to(cuda), [w.detach() for w in ws], [b.detach() for b in bs], mn, mx, **kw)
+    eng.loss_buf.zero_()
+    eng.backward_only(o.to(cuda), d.to(cuda), v.to(cuda), target.to(cuda))
+    g_sdf, g_k0, g_w, g_b = eng.grid_gradients()
+    assert eng.n_samples() > 10000
+    sdf_r, k0_r = sdf.clone().requires_grad_(True), k0.clone().requires_grad_(True)
+    out = voxurf_cpu.forward(sdf_r, k0_r, net, o, d, v, mn, mx, kw["stepsize"], eng.voxel_size, kw["s_val"], bg=kw["bg"],
+                             sdf_alpha=10.0, sdf_beta=0.35, posbase_pe=5, viewbase_pe=1, barf_c2f=None)
+    loss = voxurf_cpu.mse_loss(out, target)
+    loss.backward()
+    assert abs(float(eng.loss_buf[0]) - float(loss)) < 2e-2 * float(loss)
+    lin = [m for m in net.modules() if isinstance(m, nn.Linear)]
+    rep = {"sdf": _cos(g_sdf.cpu(), sdf_r.grad), "k0": _cos(g_k0.cpu(), k0_r.grad),
+           "W0": _cos(g_w[0].cpu(), lin[0].weight.grad), "W2": _cos(g_w[2].cpu(), lin[2].weight.grad)}
+    print(rep)
+    assert min(rep.values()) > 0.99, rep
