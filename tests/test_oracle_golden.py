@@ -99,3 +99,49 @@ def test_golden_adam():
 def test_golden_cumdist():
     z = load("cumdist")
     exact(oracle.cumdist_thres(z["dist"], float(z["thres"])), z["mask"])
+
+
+def test_voxurf_oracle_matches_the_references_own_forward():
+    """oracle/voxurf_cpu.py against tests/golden/voxurf_forward.npz = outputs of the reference's OWN `Voxurf.forward`
+    (use_deform=False), `neus_sdf_gradient`, `neus_alpha_from_sdf_scatter`, `positional_encoding_barf`,
+    `sample_ray_ori` and `total_variation`, executed unmodified on the CPU by tests/golden/make_golden_voxurf.py
+    (only torch_scatter.segment_coo and the CUDA alpha2weight are replaced).  The reference samples with the dense
+    torch sampler (`o + d * (t_min + step / |d|)`), the oracle with the enumerating sampler's arithmetic
+    (`start + dir * dist`): positions differ by fp32 rounding, hence 2e-5 on per-ray outputs."""
+    import os
+    import numpy as np
+    import torch
+    import torch.nn as nn
+    from oracle import oracle, voxurf_cpu
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "voxurf_forward.npz"))
+    sdf, k0 = torch.from_numpy(g["sdf"]), torch.from_numpy(g["k0"].astype(np.float32))
+    net = nn.Sequential(nn.Linear(57, 128), nn.ReLU(), nn.Linear(128, 128), nn.ReLU(), nn.Linear(128, 3))
+    with torch.no_grad():
+        for i, lin in enumerate([net[0], net[2], net[4]]):
+            lin.weight.copy_(torch.from_numpy(g["w%d" % i]))
+            lin.bias.copy_(torch.from_numpy(g["b%d" % i]))
+    o, d, v = (torch.from_numpy(g[k]) for k in ("rays_o", "rays_d", "viewdirs"))
+    vs = float(g["voxel_size"])
+    cases = (("eval", None, 1.0), ("train", torch.from_numpy(g["train_jitter"]), float(g["gstep"]) / float(g["N_iters"])))
+    for tag, jitter, progress in cases:
+        with torch.no_grad():
+            out = voxurf_cpu.forward(sdf, k0, net, o, d, v, [-1, -1, -1], [1, 1, 1], 0.5, vs, float(g[tag + "_s_val"]),
+                                     bg=0.3, sdf_alpha=10.0, sdf_beta=0.35, posbase_pe=5, viewbase_pe=1,
+                                     barf_c2f=(0.1, 0.5), progress=progress, jitter=jitter)
+        for key in ("rgb_marched", "alphainv_cum", "cum_weights"):
+            torch.testing.assert_close(out[key], torch.from_numpy(g["%s_%s" % (tag, key)]), rtol=0, atol=2e-5,
+                                       msg=lambda m, key=key, tag=tag: "%s %s: %s" % (tag, key, m))
+        # per-sample outputs: same in-box sample set (a point within rounding of a face may differ: not in this scene)
+        assert out["weights"].shape[0] == g[tag + "_weights"].shape[0]
+        torch.testing.assert_close(out["raw_alpha"], torch.from_numpy(g[tag + "_raw_alpha"]), rtol=0, atol=2e-5)
+        torch.testing.assert_close(out["weights"], torch.from_numpy(g[tag + "_weights"]), rtol=0, atol=2e-5)
+        torch.testing.assert_close(out["raw_rgb"], torch.from_numpy(g[tag + "_raw_rgb"]), rtol=0, atol=2e-5)
+        torch.testing.assert_close(out["gradient"], torch.from_numpy(g[tag + "_gradient"]), rtol=1e-4, atol=2e-4)
+    # the s_val schedule of neus_alpha_from_sdf_scatter (:487)
+    assert abs(float(g["train_s_val"]) - 1.0 / (float(g["gstep"]) + 50 / 0.2) * 50) < 1e-7
+    # total_variation (:1298-1313)
+    tv_v, tv_mask = torch.from_numpy(g["tv_v"]), torch.from_numpy(g["tv_mask"])
+    assert abs(float(oracle.total_variation(tv_v)) - float(g["tv_plain"])) < 1e-6
+    assert abs(float(oracle.total_variation(tv_v, tv_mask)) - float(g["tv_masked"])) < 1e-6
+    # k0_total_variation() of the forward (:1067) is total_variation(k0.grid)
+    assert abs(float(oracle.total_variation(k0)) - float(g["eval_k0_tv"])) < 1e-6
