@@ -10,6 +10,9 @@ plain PyTorch so that autograd yields the reference's gradients:
     47-58) -> rgb_feat assembly with BARF weights (:1005-1030, :721-732) -> rgbnet + sigmoid (:1032-1033) ->
     segment_coo sums restated as index_add_ (:1034-1042) -> photometric MSE (lib/losses.py:26-29).
 
+Pinned: tests/golden/voxurf_forward.npz holds the outputs of the reference's OWN Voxurf.forward (executed unmodified on
+the CPU by tests/golden/make_golden_voxurf.py); tests/test_oracle_golden.py replays them against this module (2e-5).
+
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline may import this module.
 """
 import math

@@ -145,3 +145,27 @@ def test_voxurf_oracle_matches_the_references_own_forward():
     assert abs(float(oracle.total_variation(tv_v, tv_mask)) - float(g["tv_masked"])) < 1e-6
     # k0_total_variation() of the forward (:1067) is total_variation(k0.grid)
     assert abs(float(oracle.total_variation(k0)) - float(g["eval_k0_tv"])) < 1e-6
+
+
+def test_dense_baseline_matches_the_references_own_dvgo_and_adam():
+    """oracle/dvgo_cpu.DenseBaseline (bench.py's CPU baseline / reference arm) against tests/golden/dvgo_dense.npz =
+    the reference's OWN `DirectVoxGO.forward` (lib/dvgo_ori.py:289-379) and optimiser (`Adam`, lib/utils.py:53-198),
+    executed unmodified on the CPU by tests/golden/make_golden_dvgo.py: render, then three optimisation steps."""
+    import os
+    import numpy as np
+    import torch
+    from oracle import dvgo_cpu
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "dvgo_dense.npz"))
+    base = dvgo_cpu.DenseBaseline(torch.from_numpy(g["density0"]), torch.from_numpy(g["k00"]), [-1, -1, -1], [1, 1, 1],
+                                  0.5, alpha_init=1e-2, near=0.2, far=1e9, bg=0.3, lr=0.1, betas=(0.9, 0.99))
+    assert abs(base.voxel_size - float(g["voxel_size"])) < 1e-7
+    o, d, t = (torch.from_numpy(g[k]) for k in ("rays_o", "rays_d", "target"))
+    with torch.no_grad():
+        rgb, last, n_inbox = base.forward(o, d)
+    assert n_inbox == int(g["n_inbox"])
+    torch.testing.assert_close(rgb, torch.from_numpy(g["rgb_marched"]), rtol=0, atol=1e-6)
+    torch.testing.assert_close(last, torch.from_numpy(g["alphainv_last"]), rtol=0, atol=1e-6)
+    losses = [base.train_step(o, d, t)[0] for _ in range(3)]
+    np.testing.assert_allclose(losses, g["losses"], rtol=1e-5)
+    torch.testing.assert_close(base.density.detach(), torch.from_numpy(g["density3"]), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(base.k0.detach(), torch.from_numpy(g["k03"]), rtol=1e-4, atol=1e-5)
