@@ -169,3 +169,30 @@ def test_dense_baseline_matches_the_references_own_dvgo_and_adam():
     np.testing.assert_allclose(losses, g["losses"], rtol=1e-5)
     torch.testing.assert_close(base.density.detach(), torch.from_numpy(g["density3"]), rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(base.k0.detach(), torch.from_numpy(g["k03"]), rtol=1e-4, atol=1e-5)
+
+
+def test_pose_chain_and_rays_match_the_references_own_code():
+    """oracle.se3_to_SE3 / get_rays_of_a_view AND the product's host-side pose algebra (poseprobe_b200/camera.py, pure
+    torch, runs on the CPU) against tests/golden/camera.npz = the reference's own `Lie.se3_to_SE3`,
+    `Pose.compose_pair`, `Pose.invert` (lib/camera.py) and `get_rays_of_a_view` (lib/voxurf_coarse.py:1339-1407)
+    executed unmodified by tests/golden/make_golden_camera.py (incl. theta = 0 and theta ~ 1e-4 twists)."""
+    import os
+    import numpy as np
+    import torch
+    from oracle import oracle
+    from poseprobe_b200 import camera
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "camera.npz"))
+    wu = torch.from_numpy(g["wu"])
+    for impl in (oracle.se3_to_SE3, camera.se3_to_SE3):
+        torch.testing.assert_close(impl(wu), torch.from_numpy(g["SE3"]), rtol=1e-6, atol=1e-7)
+    composed = camera.compose_pair(torch.from_numpy(g["SE3"]), torch.from_numpy(g["pnp"]))
+    torch.testing.assert_close(composed, torch.from_numpy(g["composed"]), rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(camera.invert(composed), torch.from_numpy(g["c2w"]), rtol=1e-6, atol=1e-6)
+    H, W = [int(x) for x in g["HW"]]
+    K, c2w = torch.from_numpy(g["K"]), torch.from_numpy(g["c2w"])[2]
+    for inverse_y in (False, True):
+        tag = "iy%d" % int(inverse_y)
+        ro, rd, vd = oracle.get_rays_of_a_view(H, W, K, c2w, inverse_y=inverse_y, flip_y=inverse_y)
+        assert torch.equal(ro, torch.from_numpy(g["rays_o_" + tag]))
+        torch.testing.assert_close(rd, torch.from_numpy(g["rays_d_" + tag]), rtol=1e-6, atol=1e-7)
+        torch.testing.assert_close(vd, torch.from_numpy(g["viewdirs_" + tag]), rtol=1e-6, atol=1e-7)
