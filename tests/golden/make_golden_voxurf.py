@@ -128,6 +128,14 @@ def main():
         out["%s_k0_tv" % tag] = np.float64(float(ret["k0_tv"]))
     torch.manual_seed(4321)
     out["train_jitter"] = torch.rand(N, 1)[:, 0].numpy()      # rand_like(rng[:, [0]]) under the same seed
+    # Voxurf.grid_sampler with the custom 8-gather sampler (`use_custom=True` -> grid_sample_3d, :545-659) and with
+    # F.grid_sample (border), on points inside and slightly outside the box
+    gs_grid = torch.randn(1, 4, 6, 7, 5)
+    gs_xyz = (torch.rand(400, 3) * 2.2 - 1.1)
+    out["gs_grid"], out["gs_xyz"] = gs_grid.numpy(), gs_xyz.numpy()
+    with torch.no_grad():
+        out["gs_custom"] = m.grid_sampler(gs_xyz, gs_grid, use_custom=True).numpy()
+        out["gs_border"] = m.grid_sampler(gs_xyz, gs_grid).numpy()
     # total_variation with and without mask
     v = torch.randn(1, 3, 7, 6, 5)
     mask = torch.rand(1, 3, 7, 6, 5) > 0.3

@@ -137,6 +137,16 @@ def test_voxurf_oracle_matches_the_references_own_forward():
         torch.testing.assert_close(out["weights"], torch.from_numpy(g[tag + "_weights"]), rtol=0, atol=2e-5)
         torch.testing.assert_close(out["raw_rgb"], torch.from_numpy(g[tag + "_raw_rgb"]), rtol=0, atol=2e-5)
         torch.testing.assert_close(out["gradient"], torch.from_numpy(g[tag + "_gradient"]), rtol=1e-4, atol=2e-4)
+    # Voxurf.grid_sampler: F.grid_sample(border) and the custom 8-gather `grid_sample_3d` (:545-659) vs the oracle's
+    # trilinear with border padding; the custom sampler extrapolates its weights outside the box, so it is compared
+    # on the in-box points only (the reference only feeds it in-box samples)
+    gs_grid, gs_xyz = torch.from_numpy(g["gs_grid"]), torch.from_numpy(g["gs_xyz"])
+    mn, mx = torch.tensor([-1.0, -1, -1]), torch.tensor([1.0, 1, 1])
+    got = oracle.dense_grid_forward(gs_grid, gs_xyz, mn, mx, padding_mode="border")
+    torch.testing.assert_close(got, torch.from_numpy(g["gs_border"]), rtol=1e-6, atol=1e-6)
+    inside = ((gs_xyz >= -1) & (gs_xyz <= 1)).all(-1)
+    assert int(inside.sum()) > 200 and int((~inside).sum()) > 20
+    torch.testing.assert_close(got[inside], torch.from_numpy(g["gs_custom"])[inside], rtol=1e-5, atol=1e-5)
     # the s_val schedule of neus_alpha_from_sdf_scatter (:487)
     assert abs(float(g["train_s_val"]) - 1.0 / (float(g["gstep"]) + 50 / 0.2) * 50) < 1e-7
     # total_variation (:1298-1313)
