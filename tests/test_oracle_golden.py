@@ -206,3 +206,38 @@ def test_pose_chain_and_rays_match_the_references_own_code():
         assert torch.equal(ro, torch.from_numpy(g["rays_o_" + tag]))
         torch.testing.assert_close(rd, torch.from_numpy(g["rays_d_" + tag]), rtol=1e-6, atol=1e-7)
         torch.testing.assert_close(vd, torch.from_numpy(g["viewdirs_" + tag]), rtol=1e-6, atol=1e-7)
+
+
+def test_grid_modules_host_logic_matches_the_references_own_classes(tmp_path):
+    """poseprobe_b200/grid.py (the drop-in DenseGrid / MaskGrid) against tests/golden/grid_modules.npz = the reference's
+    own classes (lib/grid.py:38-89, :212-245) executed unmodified by tests/golden/make_golden_grid.py.  CPU part: the
+    world->index affine buffers (bit-exact), the checkpoint -> occupancy recipe, `-=` and scale_volume_grid; the
+    kernel-backed methods replay the same file in tests/test_parity_gpu.py."""
+    import os
+    import numpy as np
+    import torch
+    from poseprobe_b200.grid import DenseGrid, MaskGrid
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "grid_modules.npz"))
+    lo, hi = g["mg_lo"].tolist(), g["mg_hi"].tolist()
+    mg = MaskGrid(mask=torch.from_numpy(g["mg_mask"]), xyz_min=lo, xyz_max=hi)
+    assert mg.mask.dtype == torch.bool and set(mg.state_dict()) == {"mask", "xyz2ijk_scale", "xyz2ijk_shift"}
+    assert np.array_equal(mg.xyz2ijk_scale.numpy(), g["mg_scale"])
+    assert np.array_equal(mg.xyz2ijk_shift.numpy(), g["mg_shift"])
+    ckpt = {"model_state_dict": {"density.grid": torch.from_numpy(g["ck_density"]), "act_shift": torch.tensor(-2.0)},
+            "model_kwargs": {"voxel_size_ratio": 0.75, "xyz_min": lo, "xyz_max": hi}}
+    path = str(tmp_path / "coarse_last.tar")
+    torch.save(ckpt, path)
+    mc = MaskGrid(path=path, mask_cache_thres=0.3)
+    assert mc.mask_cache_thres == 0.3 and np.array_equal(mc.mask.numpy(), g["ck_mask"])
+    assert np.array_equal(mc.xyz2ijk_scale.numpy(), g["ck_scale"])
+    assert np.array_equal(mc.xyz2ijk_shift.numpy(), g["ck_shift"])
+    dg = DenseGrid(channels=3, world_size=[4, 6, 5], xyz_min=lo, xyz_max=hi)
+    assert set(dg.state_dict()) == {"grid", "xyz_min", "xyz_max"} and tuple(dg.grid.shape) == (1, 3, 4, 6, 5)
+    with torch.no_grad():
+        dg.grid.copy_(torch.from_numpy(g["dg_grid"]))
+    dg -= 0.25
+    assert np.array_equal(dg.grid.detach().numpy(), g["dg_isub"])
+    dg.scale_volume_grid([7, 5, 9])
+    assert isinstance(dg.grid, torch.nn.Parameter) and dg.grid.requires_grad
+    np.testing.assert_allclose(dg.grid.detach().numpy(), g["dg_scaled"], rtol=0, atol=1e-6)
+    assert dg.get_dense_grid() is dg.grid

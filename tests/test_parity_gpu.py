@@ -414,6 +414,33 @@ def test_dense_grid_module(pp):
         dg.total_variation_add_grad(1.0, 1.0, 1.0, True)
 
 
+def test_grid_modules_replay_reference_golden(pp):
+    """DenseGrid / MaskGrid on the GPU against tests/golden/grid_modules.npz (the reference's own lib/grid.py classes,
+    see tests/golden/make_golden_grid.py): forward values and shapes, TV add-grad with and without the broadcast
+    [1,1,X,Y,Z] mask, the mask lookup (bit-exact)."""
+    import os
+    import numpy as np
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "grid_modules.npz"))
+    lo, hi = g["mg_lo"].tolist(), g["mg_hi"].tolist()
+    mg = pp.MaskGrid(mask=torch.from_numpy(g["mg_mask"]), xyz_min=lo, xyz_max=hi).cuda()
+    hit = mg(torch.from_numpy(g["mg_pts"]).cuda())
+    assert hit.dtype == torch.bool and hit.shape == g["mg_hit"].shape
+    assert np.array_equal(hit.cpu().numpy(), g["mg_hit"])
+    dg = pp.DenseGrid(channels=3, world_size=[4, 6, 5], xyz_min=lo, xyz_max=hi).cuda()
+    with torch.no_grad():
+        dg.grid.copy_(torch.from_numpy(g["dg_grid"]))
+    dg.grid.grad = torch.from_numpy(g["dg_grad0"]).cuda()
+    dg.total_variation_add_grad(0.3, 0.2, 0.1, True)
+    close(dg.grid.grad, torch.from_numpy(g["dg_grad_tv"]), rtol=1e-6, atol=1e-6)
+    dg.total_variation_add_grad(0.3, 0.2, 0.1, False, mask=torch.from_numpy(g["dg_tvmask"]).cuda())
+    close(dg.grid.grad, torch.from_numpy(g["dg_grad_tv_masked"]), rtol=1e-6, atol=1e-6)
+    val = dg(torch.from_numpy(g["dg_q"]).cuda())
+    assert val.shape == g["dg_val"].shape
+    close(val, torch.from_numpy(g["dg_val"]), rtol=1e-5, atol=1e-6)
+    d1 = pp.DenseGrid(channels=1, world_size=[4, 6, 5], xyz_min=lo, xyz_max=hi).cuda()
+    assert list(d1(torch.from_numpy(g["dg_q"]).cuda()).shape) == g["d1_shape"].tolist()
+
+
 @pytest.mark.parametrize("C", [1, 3])
 def test_segment_sum_and_cumsum(pp, C):
     alpha, ray_id, lens = cases.alpha_and_ray_id(300, 700, seed=61)
