@@ -10,6 +10,13 @@ plain PyTorch so that autograd yields the reference's gradients:
     47-58) -> rgb_feat assembly with BARF weights (:1005-1030, :721-732) -> rgbnet + sigmoid (:1032-1033) ->
     segment_coo sums restated as index_add_ (:1034-1042) -> photometric MSE (lib/losses.py:26-29).
 
+With ``warp=`` the implicit-deformation branch (:958-985) runs instead of the plain SDF lookup: the warp MLP
+(``DeformedImplicitField``, lib/deformation/deform_net.py:12-29: 3 -> 128 x4 -> 4, ReLU, output times the box extent),
+the template SDF at the warped point through the twice-differentiable 8-gather sampler ``grid_sample_3d`` (:545-659),
+the Jacobian of the warped point (``grad_deform``), the scalar correction, and the normal as d sdf_final / d point by
+``autograd.grad(create_graph=True)``; ``deform_implicit_loss`` restates lib/losses.py:6-24.  Pinned by
+tests/golden/voxurf_deform.npz (reference code run by tests/golden/make_golden_deform.py).
+
 Pinned: tests/golden/voxurf_forward.npz holds the outputs of the reference's OWN Voxurf.forward (executed unmodified on
 the CPU by tests/golden/make_golden_voxurf.py); tests/test_oracle_golden.py replays them against this module (2e-5).
 
@@ -46,6 +53,58 @@ def grid_sampler(xyz, grid, xyz_min, xyz_max, padding_mode):
     return out.reshape(grid.shape[1], -1).T
 
 
+def grid_sample_custom(xyz, grid, xyz_min, xyz_max):
+    """Voxurf.grid_sampler(use_custom=True) -> grid_sample_3d, voxurf_coarse.py:522-538, :545-659: trilinear weights from
+    the UNCLAMPED floor of the continuous voxel coordinate, corner indices clamped into the grid afterwards; written
+    with differentiable torch ops only so that it can be differentiated twice with respect to the points.
+    xyz [M,3], grid [1,C,X,Y,Z] -> [M,C]."""
+    _, C, X, Y, Z = grid.shape
+    dims = torch.tensor([X, Y, Z], dtype=xyz.dtype)
+    ind_norm = ((xyz - xyz_min) / (xyz_max - xyz_min)) * 2 - 1
+    pos = ((ind_norm + 1) / 2) * (dims - 1)                      # continuous voxel coordinate per axis
+    with torch.no_grad():
+        base = torch.floor(pos)
+    hi_w = pos - base                                            # weight of the +1 corner along each axis
+    lo_w = (base + 1) - pos
+    flat = grid.reshape(C, -1)
+    out = 0
+    for dx in (0, 1):
+        for dy in (0, 1):
+            for dz in (0, 1):
+                with torch.no_grad():
+                    ix = (base[:, 0] + dx).clamp(0, X - 1)
+                    iy = (base[:, 1] + dy).clamp(0, Y - 1)
+                    iz = (base[:, 2] + dz).clamp(0, Z - 1)
+                    lin = ((ix * Y + iy) * Z + iz).long()
+                w = (hi_w[:, 0] if dx else lo_w[:, 0]) * (hi_w[:, 1] if dy else lo_w[:, 1]) * \
+                    (hi_w[:, 2] if dz else lo_w[:, 2])
+                out = out + flat[:, lin].T * w[:, None]
+    return out
+
+
+def warp_mlp(x, weights, biases, out_range):
+    """DeformedImplicitField.forward (deform_net.py:23-29) on top of SingleBVPNet / FCBlock (modules.py:43-124):
+    Linear+ReLU x (len-1), Linear; output scaled by ``out_range`` (= range_shape.max()).
+    -> (deformation [M,3], correction [M,1])."""
+    h = x
+    for i, (w, b) in enumerate(zip(weights, biases)):
+        h = F.linear(h, w, b)
+        if i < len(weights) - 1:
+            h = torch.relu(h)
+    h = h * out_range
+    return h[:, :3], h[:, 3:]
+
+
+def deform_implicit_loss(out, use_deform=True):
+    """lib/losses.py:6-24 -> dict of the mean constraints (Eikonal, Jacobian norm, correction, deformation)."""
+    d = {"grad_constraint": (out["gradient"].norm(dim=-1) - 1).abs().mean()}
+    if use_deform:
+        d["grad_deform_constraint"] = out["grad_deform"].norm(dim=-1).mean()
+        d["sdf_correct_constraint"] = out["sdf_correct"].abs().mean()
+        d["sdf_deform_constraint"] = out["sdf_deform"].abs().mean()
+    return d
+
+
 def barf_weights(progress, barf_c2f, L):
     if barf_c2f is None:
         return torch.ones(L)
@@ -71,8 +130,9 @@ def sample(rays_o, rays_d, xyz_min, xyz_max, near, far, stepdist, jitter=None):
 
 def forward(sdf_grid, k0_grid, rgbnet, rays_o, rays_d, viewdirs, xyz_min, xyz_max, stepsize, voxel_size, s_val,
             near=0.2, far=1e9, bg=0.0, sdf_alpha=None, sdf_beta=None, posbase_pe=5, viewbase_pe=1, barf_c2f=None,
-            progress=1.0, jitter=None, differentiable_points=False):
+            progress=1.0, jitter=None, differentiable_points=False, warp=None):
     """sdf_grid [1,1,X,Y,Z], k0_grid [1,12,X,Y,Z] (may require grad), rgbnet: callable rows -> logits.
+    warp: None, or (weights, biases, out_range) of the deformation network -> implicit-deformation branch.
     differentiable_points: rebuild the sample positions from (rays_o, rays_d) with torch ops (the formulas of
     sample_ray_ori, voxurf_coarse.py:702-716) so that autograd reaches the rays (pose gradient)."""
     xyz_min = torch.as_tensor(xyz_min, dtype=torch.float32)
@@ -90,8 +150,24 @@ def forward(sdf_grid, k0_grid, rgbnet, rays_o, rays_d, viewdirs, xyz_min, xyz_ma
     grid = sdf_grid
     if sdf_alpha is not None:
         grid = softplus10(sdf_alpha) * (torch.sigmoid(softplus10(sdf_beta) * sdf_grid) - 0.5)
-    sdf = grid_sampler(pts, grid, xyz_min, xyz_max, "border")[:, 0]
-    gradient = grid_sampler(pts, sdf_gradient_grid(grid, voxel_size), xyz_min, xyz_max, "border")
+    extra = {}
+    if warp is None:
+        sdf = grid_sampler(pts, grid, xyz_min, xyz_max, "border")[:, 0]
+        gradient = grid_sampler(pts, sdf_gradient_grid(grid, voxel_size), xyz_min, xyz_max, "border")
+    else:
+        # implicit deformation, voxurf_coarse.py:958-985 (bool_mapping_deformspace = False, :104)
+        if not pts.requires_grad:
+            pts = pts.detach().requires_grad_(True)
+        deform, correction = warp_mlp(pts, *warp)
+        new_coords = deform + pts
+        sdf_template = grid_sample_custom(new_coords, grid, xyz_min, xyz_max)[:, 0]
+        ones = torch.ones_like(new_coords[:, 0])
+        grad_deform = torch.stack([torch.autograd.grad(new_coords[:, k], [pts], grad_outputs=ones, create_graph=True)[0]
+                                   for k in range(3)], dim=2)
+        sdf = sdf_template + correction.squeeze(-1)
+        sdf_deform = sdf - grid_sample_custom(pts, grid, xyz_min, xyz_max)[:, 0]
+        gradient = torch.autograd.grad(sdf, [pts], grad_outputs=torch.ones_like(sdf), create_graph=True)[0]
+        extra = {"sdf_deform": sdf_deform, "grad_deform": grad_deform, "sdf_correct": correction}
     # neus_alpha_from_sdf_scatter, :494-517
     dirs = viewdirs[ray_id]
     inv_s = 1.0 / s_val
@@ -127,7 +203,7 @@ def forward(sdf_grid, k0_grid, rgbnet, rays_o, rays_d, viewdirs, xyz_min, xyz_ma
     rgb_marched = (rgb_acc + (1 - cum_weights) * bg).clamp(0, 1)
     return {"rgb_marched": rgb_marched, "alphainv_cum": alphainv_last, "weights": weights, "cum_weights": cum_weights,
             "raw_alpha": alpha, "raw_rgb": rgb, "ray_id": ray_id, "step_id": step_id, "gradient": gradient,
-            "sdf": sdf, "rgb_feat": rgb_feat, "normal": normal, "k0": k0, "pts": pts}
+            "sdf": sdf, "rgb_feat": rgb_feat, "normal": normal, "k0": k0, "pts": pts, **extra}
 
 
 def mse_loss(out, target, w_rgb=1.0):

@@ -51,7 +51,8 @@ def segment_coo(src, index, out, reduce="sum"):
     return out.index_add_(0, index, src)
 
 
-def main():
+def reference_model():
+    """-> (reference Voxurf instance on the CPU, namespace the class was executed in, dict of the sizes used)"""
     from einops import rearrange
     from oracle import oracle
     torch.Tensor.cuda = lambda self, *a, **k: self            # CPU run
@@ -113,7 +114,13 @@ def main():
     m.progress = nn.Parameter(torch.tensor(0.))
     m.warp_network = types.SimpleNamespace(progress=nn.Parameter(torch.tensor(0.)))
     m.nonempty_mask = None
+    return m, ns, dict(G=G, N=N, N_iters=N_iters, gstep=gstep)
 
+
+def main():
+    m, ns, sz = reference_model()
+    total_variation = ns["total_variation"]
+    N, N_iters, gstep = sz["N"], sz["N_iters"], sz["gstep"]
     from poseprobe_b200 import synthetic
     rays_o, rays_d, viewdirs = synthetic.make_rays(N, seed=77)
     render_kwargs = dict(near=0.2, far=1e9, stepsize=0.5, bg=0.3)

@@ -241,3 +241,63 @@ def test_grid_modules_host_logic_matches_the_references_own_classes(tmp_path):
     assert isinstance(dg.grid, torch.nn.Parameter) and dg.grid.requires_grad
     np.testing.assert_allclose(dg.grid.detach().numpy(), g["dg_scaled"], rtol=0, atol=1e-6)
     assert dg.get_dense_grid() is dg.grid
+
+
+def test_voxurf_deform_oracle_matches_the_references_own_forward_and_gradients():
+    """oracle/voxurf_cpu.py, implicit-deformation branch (``warp=``), against tests/golden/voxurf_deform.npz = the
+    reference's OWN `Voxurf.forward(use_deform=True)` with its `DeformedImplicitField` and `deform_implicit_loss`,
+    executed unmodified on the CPU by tests/golden/make_golden_deform.py: forward outputs (incl. the warp Jacobian
+    `grad_deform`, the correction and `sdf_deform`), the four constraint terms, and the gradients of the combined loss
+    with respect to the warp network, the colour network, k0 and the rays (second-order terms through the normal)."""
+    import os
+    import numpy as np
+    import torch
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from oracle import voxurf_cpu
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "voxurf_deform.npz"))
+    t = lambda k: torch.from_numpy(g[k])  # noqa: E731
+    sdf = t("sdf")
+    k0 = torch.from_numpy(g["k0"].astype(np.float32)).requires_grad_(True)
+    net = nn.Sequential(nn.Linear(57, 128), nn.ReLU(), nn.Linear(128, 128), nn.ReLU(), nn.Linear(128, 3))
+    rgb_lin = [net[0], net[2], net[4]]
+    with torch.no_grad():
+        for i, lin in enumerate(rgb_lin):
+            lin.weight.copy_(t("w%d" % i))
+            lin.bias.copy_(t("b%d" % i))
+    ww = [t("ww%d" % i).clone().requires_grad_(True) for i in range(5)]
+    wb = [t("wb%d" % i).clone().requires_grad_(True) for i in range(5)]
+    o, d = t("rays_o").clone().requires_grad_(True), t("rays_d").clone().requires_grad_(True)
+    progress = float(g["gstep"]) / float(g["N_iters"])
+    out = voxurf_cpu.forward(sdf, k0, net, o, d, t("viewdirs"), [-1, -1, -1], [1, 1, 1], 0.5, float(g["voxel_size"]),
+                             float(g["s_val"]), bg=0.3, sdf_alpha=10.0, sdf_beta=0.35, posbase_pe=5, viewbase_pe=1,
+                             barf_c2f=(0.1, 0.5), progress=progress, jitter=t("jitter"), differentiable_points=True,
+                             warp=(ww, wb, float(g["out_range"])))
+    assert out["weights"].shape[0] == g["ret_weights"].shape[0]
+    for key in ("rgb_marched", "alphainv_cum", "cum_weights", "weights", "raw_alpha", "sdf_deform", "sdf_correct"):
+        torch.testing.assert_close(out[key].detach().reshape(g["ret_" + key].shape), t("ret_" + key), rtol=0, atol=3e-5,
+                                   msg=lambda m, key=key: "%s: %s" % (key, m))
+    torch.testing.assert_close(out["gradient"].detach(), t("ret_gradient"), rtol=1e-4, atol=2e-4)
+    torch.testing.assert_close(out["grad_deform"].detach(), t("ret_grad_deform"), rtol=1e-4, atol=1e-5)
+    terms = voxurf_cpu.deform_implicit_loss(out)
+    for k, v in terms.items():
+        assert abs(float(v.detach()) - float(g["term_" + k])) < 2e-5, k
+    loss = F.mse_loss(out["rgb_marched"], t("target")) + terms["grad_constraint"] + 0.05 * (
+        terms["grad_deform_constraint"] + terms["sdf_correct_constraint"] + terms["sdf_deform_constraint"])
+    assert abs(float(loss.detach()) - float(g["loss"])) < 2e-5
+    rgb_params = [p for lin in rgb_lin for p in (lin.weight, lin.bias)]
+    grads = torch.autograd.grad(loss, ww + wb + rgb_params + [k0, o, d])
+
+    def rel(a, b):
+        return float((a - b).norm() / (b.norm() + 1e-12))
+
+    for i in range(5):
+        assert rel(grads[i], t("g_ww%d" % i)) < 2e-3, ("warp weight", i, rel(grads[i], t("g_ww%d" % i)))
+        assert rel(grads[5 + i], t("g_wb%d" % i)) < 2e-3, ("warp bias", i)
+    for i in range(3):
+        assert rel(grads[10 + 2 * i], t("g_w%d" % i)) < 2e-3, ("rgbnet weight", i)
+        assert rel(grads[11 + 2 * i], t("g_b%d" % i)) < 2e-3, ("rgbnet bias", i)
+    g_k0 = torch.zeros(k0.numel())
+    g_k0[torch.from_numpy(g["g_k0_idx"]).long()] = t("g_k0_val")
+    assert rel(grads[16].reshape(-1), g_k0) < 2e-3
+    assert rel(grads[17], t("g_rays_o")) < 5e-3 and rel(grads[18], t("g_rays_d")) < 5e-3
