@@ -249,6 +249,22 @@ PP_API int pp_rgbnet_forward_packed(const void* x_packed, int64_t n_pts, int32_t
                                     const int32_t* ray_id, float* rgb_marched, const int32_t* n_ptr,
                                     pp_stream_t stream);
 
+/* Deformation ("warp") network WITH its input Jacobian, forward only: DeformedImplicitField (lib/deformation/
+ * deform_net.py:12-29; SingleBVPNet 3 -> 128 x4 -> 4, ReLU, lib/deformation/modules.py:43-124) and the
+ * torch.autograd.grad(..., [ray_pts]) calls around it (lib/voxurf_coarse.py:966-985, :1116-1135).
+ * A ReLU network is piecewise linear: the tangent of each hidden layer is the layer's linear map gated by the value
+ * row's activation pattern, so one pass over FOUR rows per sample yields net(x) and d net / d x.
+ * x_rows: fp16 [n_rows,16], n_rows = 4 * samples; per sample the value row {x_hi[3], x_lo[3], 0 ...} (x = x_hi + x_lo:
+ * the point keeps 22 mantissa bits) and the tangent rows e_0, e_1, e_2 (pp_voxurf_deform_rows writes this format).
+ * weights[0]: [128,6] = [W_0 | W_0]; weights[1..depth-2]: [128,128]; weights[depth-1]: [4,128]; biases as nn.Linear.
+ * out: fp32 [n_rows,4]: row 4s = net(x_s) (NOT yet multiplied by the output range), row 4s+1+k = d net / d x_k.
+ * n_rows_ptr (nullable): DEVICE int32 row count (n_rows is then the capacity). */
+PP_API int pp_warpnet_forward_packed(const void* x_rows, int64_t n_rows, int32_t depth, int32_t width,
+                                     const float* const* weights, const float* const* biases, float* out,
+                                     const int32_t* n_rows_ptr, pp_stream_t stream);
+/* x fp32 [n,3] -> the four fp16 [16] rows per point that pp_warpnet_forward_packed consumes ([4n,16]). */
+PP_API int pp_warpnet_pack_points(const float* x, int64_t n_pts, void* rows, pp_stream_t stream);
+
 /* rgbnet training step on tcgen05: forward recompute + backward of the whole network per 128-sample tile
  * (autograd of lib/voxurf_coarse.py:1032-1033 `torch.sigmoid(self.rgbnet(rgb_feat))`).
  * grad_out [n,3]: d loss / d out (post-sigmoid when apply_sigmoid, else d loss / d logits).

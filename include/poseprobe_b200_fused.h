@@ -197,6 +197,30 @@ PP_API int pp_voxurf_march_features(const pp_dvgo_scene* scene, const pp_voxurf_
                                     int32_t* ray_end, float* cum_w, float* alphainv_last, int32_t* counter,
                                     float* depth, float* normal_marched, pp_stream_t stream);
 
+/* ---- implicit deformation, forward (Voxurf.inference :1093-1215 and forward(use_deform=True) :958-985) ---------
+ *   (deform, correction) = warp_network(x) * out_range;  x' = x + deform
+ *   sdf_final = grid_sample_3d(sdf', x') + correction;  gradient = d sdf_final / d x
+ * pp_voxurf_deform_rows: one run of slots per ray for ALL its in-box samples (the reference's compacted ray_pts
+ * order) and the warp network's input rows: rows fp16 [4 * sample_capacity, 16]; warp_ray_off [N] (first slot of
+ * the ray, -1 if it did not fit); counter: 4 x int32 on the device: [0] samples, [1] overflow flag, [2] rows = 4 *
+ * samples (pass &counter[2] to pp_warpnet_forward_packed as its device row count).
+ * pp_voxurf_march_features_deform: pp_voxurf_march_features with the SDF value / normal of every sample taken from
+ * the warped lookup: warp_out = the network's fp32 [rows,4] output.  The template SDF is read with the arithmetic of
+ * the reference's custom sampler (weights from the unclamped floor, clamped corner indices, :545-659) and its
+ * analytic gradient is chained through the warp Jacobian - the closed form of the reference's autograd.grad. */
+PP_API int pp_voxurf_deform_rows(const pp_dvgo_scene* scene, const float* rays_o, const float* rays_d,
+                                 const float* jitter, int64_t n_rays, int32_t sample_capacity, void* rows,
+                                 int32_t* warp_ray_off, int32_t* counter, pp_stream_t stream);
+PP_API int pp_voxurf_march_features_deform(const pp_dvgo_scene* scene, const pp_voxurf_cfg* cfg,
+                                           const void* sdf_records, const void* k0_records, const float* rays_o,
+                                           const float* rays_d, const float* viewdirs, const float* jitter,
+                                           int64_t n_rays, int32_t capacity, void* feat, float* sample_weight,
+                                           int32_t* sample_ray, void* sample_rec, int32_t* ray_off,
+                                           int32_t* ray_cnt, int32_t* ray_end, float* cum_w, float* alphainv_last,
+                                           int32_t* counter, float* depth, float* normal_marched,
+                                           const float* warp_out, const int32_t* warp_ray_off, float out_range,
+                                           pp_stream_t stream);
+
 /* rgb_marched = clamp(rgb_acc + (1 - cum_w) bg, 0, 1) (:1040-1042); photometric MSE (lib/losses.py:26-29):
  * g_ray [N,3] = d (w_rgb * mse) / d rgb_acc, loss_out[0] += w_rgb * mse, loss_out[1] += mse. */
 PP_API int pp_voxurf_ray_loss(int64_t n_rays, const float* rgb_acc, const float* cum_w, const float* target,

@@ -30,7 +30,8 @@ struct MlpParams {
   const float* b[kMlpMaxDepth];
   int depth;      // number of Linear layers
   int d0;         // input features
-  int k0p;        // input row width of the packed bf16 input: 64 or 128
+  int k0p;        // input row width of the packed bf16 input: 64 or 128 (16 for the warp network)
+  int n_out;      // real outputs of the last layer (3 colour channels; 4 for the warp network)
 };
 
 template <int kThreadsPerPipe>
@@ -45,7 +46,17 @@ __device__ __forceinline__ void group_sync(int g) {
 // the goal is to keep tcgen05.ld busy: while one pipeline waits (MMA latency, input tile, barrier) the others
 // drain their accumulators.
 // shared memory map: kPipes A tiles (128 x 128 bf16 each), weights, biases, kPipes mbarriers, tmem base.
-template <int kPipes>
+//
+// kJac (the deformation network with its input Jacobian, lib/deformation/deform_net.py:12-29 and the autograd.grad
+// calls of lib/voxurf_coarse.py:966-985): every sample occupies FOUR consecutive rows - the value row (x, with
+// biases) and three tangent rows (the unit vectors e_k, no biases).  A ReLU network is piecewise linear, so the
+// tangent of a hidden layer is the layer's linear map gated by the VALUE row's activation pattern:
+// t_l = (z_l > 0) * (W_l t_{l-1}).  The four rows are four lanes of one warp in the epilogue, the gate is one
+// shuffle per accumulator element.  Row 4s carries net(x), rows 4s+1..3 carry d net / d x_k.
+// Operands are fp16 here (11 significant bits, same MMA rate as bf16): a gate that flips because z_l was rounded
+// changes the Jacobian of that sample by a whole rank-1 term, and the flip rate scales with the operand rounding;
+// the values of this small network (|h| < ~1e2) are far inside the fp16 range.
+template <int kPipes, bool kJac>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 rgbnet_forward_kernel(MlpParams P, const __nv_bfloat16* __restrict__ x, int64_t M, int apply_sigmoid,
                       float* __restrict__ out, const float* __restrict__ wgt, const int32_t* __restrict__ ray_id,
@@ -75,7 +86,7 @@ rgbnet_forward_kernel(MlpParams P, const __nv_bfloat16* __restrict__ x, int64_t 
   for (int l = 0; l < L; ++l) {
     const bool last = (l == L - 1);
     const int rows = last ? kMlpOutPad : kMlpWidth;
-    const int real_rows = last ? 3 : kMlpWidth;
+    const int real_rows = last ? P.n_out : kMlpWidth;
     const int K = (l == 0) ? k0p : kMlpWidth;
     const int real_K = (l == 0) ? P.d0 : kMlpWidth;
     const int cpr = K >> 3;
@@ -85,10 +96,17 @@ rgbnet_forward_kernel(MlpParams P, const __nv_bfloat16* __restrict__ x, int64_t 
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = (r < real_rows && k0 + j < real_K) ? __ldg(P.w[l] + r * real_K + k0 + j) : 0.f;
       uint4 pk;
-      pk.x = pack_bf16(f[0], f[1]);
-      pk.y = pack_bf16(f[2], f[3]);
-      pk.z = pack_bf16(f[4], f[5]);
-      pk.w = pack_bf16(f[6], f[7]);
+      if constexpr (kJac) {   // the warp network runs on fp16 operands, see the kernel comment
+        pk.x = pack_f16(f[0], f[1]);
+        pk.y = pack_f16(f[2], f[3]);
+        pk.z = pack_f16(f[4], f[5]);
+        pk.w = pack_f16(f[6], f[7]);
+      } else {
+        pk.x = pack_bf16(f[0], f[1]);
+        pk.y = pack_bf16(f[2], f[3]);
+        pk.z = pack_bf16(f[4], f[5]);
+        pk.w = pack_bf16(f[6], f[7]);
+      }
       *reinterpret_cast<uint4*>(sW[l] + canon_off(r, k0, K)) = pk;
     }
     for (int e = tid; e < kMlpWidth; e += kFwdThreads)
@@ -112,7 +130,8 @@ rgbnet_forward_kernel(MlpParams P, const __nv_bfloat16* __restrict__ x, int64_t 
   const uint32_t bar = smem_u32(sBar + g);
   uint32_t phase = 0;
   const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-  const uint32_t idesc_h = umma_idesc_bf16(kFwdTile, kMlpWidth), idesc_o = umma_idesc_bf16(kFwdTile, kMlpOutPad);
+  const uint32_t idesc_h = kJac ? umma_idesc_f16(kFwdTile, kMlpWidth) : umma_idesc_bf16(kFwdTile, kMlpWidth);
+  const uint32_t idesc_o = kJac ? umma_idesc_f16(kFwdTile, kMlpOutPad) : umma_idesc_bf16(kFwdTile, kMlpOutPad);
   const int chunks_per_row = k0p >> 3;
 
   const int64_t n_tiles = (M + kFwdTile - 1) / kFwdTile;
@@ -163,10 +182,28 @@ rgbnet_forward_kernel(MlpParams P, const __nv_bfloat16* __restrict__ x, int64_t 
 #pragma unroll
           for (int j = 0; j < 8; ++j) bb[j] = b4[j];
           tmem_ld_wait();
+          if constexpr (kJac) {
+            const float* bf = reinterpret_cast<const float*>(bb);
+            const bool is_value = (lane & 3) == 0;
+            uint32_t pk[16];
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<uint4*>(sA + canon_off(row, c0 + 8 * j, kMlpWidth)) =
-                bias_relu_pack8(r + 8 * j, bb[2 * j], bb[2 * j + 1]);
+            for (int j = 0; j < 32; j += 2) {
+              const float a0 = __uint_as_float(r[j]), a1 = __uint_as_float(r[j + 1]);
+              const float z0 = a0 + bf[j], z1 = a1 + bf[j + 1];
+              const float v0 = __shfl_sync(kFull, z0, lane & ~3), v1 = __shfl_sync(kFull, z1, lane & ~3);
+              pk[j >> 1] = pack_f16(is_value ? fmaxf(z0, 0.f) : (v0 > 0.f ? a0 : 0.f),
+                                    is_value ? fmaxf(z1, 0.f) : (v1 > 0.f ? a1 : 0.f));
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(sA + canon_off(row, c0 + 8 * j, kMlpWidth)) =
+                  make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              *reinterpret_cast<uint4*>(sA + canon_off(row, c0 + 8 * j, kMlpWidth)) =
+                  bias_relu_pack8(r + 8 * j, bb[2 * j], bb[2 * j + 1]);
+          }
         }
         tc_fence_before();
         fence_async_smem();
@@ -178,6 +215,17 @@ rgbnet_forward_kernel(MlpParams P, const __nv_bfloat16* __restrict__ x, int64_t 
           float v[16];
           tmem_ld16(d_tmem + lane_base, v);
           const float* bias = sBias + l * kMlpWidth;
+          if constexpr (kJac) {
+            // [rows, 4] fp32: net(x) on the value rows (with bias), d net / d x_k on the tangent rows
+            if (valid) {
+              const float bsel = (lane & 3) == 0 ? 1.f : 0.f;
+              *reinterpret_cast<float4*>(out + grow * 4) =
+                  make_float4(fma_rn(bias[0], bsel, v[0]), fma_rn(bias[1], bsel, v[1]), fma_rn(bias[2], bsel, v[2]),
+                              fma_rn(bias[3], bsel, v[3]));
+            }
+            tc_fence_before();
+            continue;
+          }
           float y[3];
 #pragma unroll
           for (int j = 0; j < 3; ++j) {
@@ -218,9 +266,41 @@ rgbnet_forward_kernel(MlpParams P, const __nv_bfloat16* __restrict__ x, int64_t 
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*sTmem), "r"(512) : "memory");
 }
 
+// rows of pp_warpnet_forward_packed for free-standing points: x fp32 [n,3] -> fp16 [4n,16]
+__global__ void warpnet_pack_points_kernel(const float* __restrict__ x, int64_t n, uint4* __restrict__ rows) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float hi[3], lo[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float v = x[3 * i + a];
+    hi[a] = __half2float(__float2half_rn(v));
+    lo[a] = v - hi[a];
+  }
+  uint4* dst = rows + i * 8;
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  dst[0] = make_uint4(pack_f16(hi[0], hi[1]), pack_f16(hi[2], lo[0]), pack_f16(lo[1], lo[2]), 0u);
+  dst[1] = zero;
+  dst[2] = make_uint4(0x00003C00u, 0u, 0u, 0u);   // e_0 (fp16 1.0 = 0x3C00)
+  dst[3] = zero;
+  dst[4] = make_uint4(0x3C000000u, 0u, 0u, 0u);   // e_1
+  dst[5] = zero;
+  dst[6] = make_uint4(0u, 0x00003C00u, 0u, 0u);   // e_2
+  dst[7] = zero;
+}
+
 }  // namespace pp
 
 using namespace pp;
+
+extern "C" int pp_warpnet_pack_points(const float* x, int64_t n_pts, void* rows, pp_stream_t stream) {
+  PP_REQUIRE(n_pts >= 0, PP_ERR_INVALID_ARG, "warpnet_pack_points: n_pts < 0");
+  if (n_pts == 0) return PP_OK;
+  PP_REQUIRE(x && rows, PP_ERR_INVALID_ARG, "warpnet_pack_points: null pointer");
+  warpnet_pack_points_kernel<<<ceil_div(n_pts, 256), 256, 0, as_stream(stream)>>>(x, n_pts, (uint4*)rows);
+  PP_CHECK_LAUNCH("warpnet_pack_points");
+  return PP_OK;
+}
 
 extern "C" int pp_rgbnet_forward_packed(const void* x_packed, int64_t n_pts, int32_t d0, int32_t depth,
                                         int32_t width, const float* const* weights, const float* const* biases,
@@ -241,6 +321,7 @@ extern "C" int pp_rgbnet_forward_packed(const void* x_packed, int64_t n_pts, int
   P.depth = depth;
   P.d0 = d0;
   P.k0p = d0 <= 64 ? 64 : 128;
+  P.n_out = 3;
   size_t smem = 0;
   for (int l = 0; l < kMlpMaxDepth; ++l) {
     P.w[l] = l < depth ? weights[l] : nullptr;
@@ -262,15 +343,58 @@ extern "C" int pp_rgbnet_forward_packed(const void* x_packed, int64_t n_pts, int
   const int64_t n_tiles = (n_pts + kFwdTile - 1) / kFwdTile;
   const int blocks = (int)min64((n_tiles + pipes - 1) / pipes, sm_count());
   if (pipes == 4) {
-    PP_CHECK_CUDA(cudaFuncSetAttribute(rgbnet_forward_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rgbnet_forward_kernel<4><<<blocks, kFwdThreads, smem, as_stream(stream)>>>(
+    PP_CHECK_CUDA(cudaFuncSetAttribute(rgbnet_forward_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rgbnet_forward_kernel<4, false><<<blocks, kFwdThreads, smem, as_stream(stream)>>>(
         P, (const __nv_bfloat16*)x_packed, n_pts, apply_sigmoid, out, sample_weight, ray_id, rgb_marched, n_ptr);
   } else {
-    PP_CHECK_CUDA(cudaFuncSetAttribute(rgbnet_forward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rgbnet_forward_kernel<2><<<blocks, kFwdThreads, smem, as_stream(stream)>>>(
+    PP_CHECK_CUDA(cudaFuncSetAttribute(rgbnet_forward_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rgbnet_forward_kernel<2, false><<<blocks, kFwdThreads, smem, as_stream(stream)>>>(
         P, (const __nv_bfloat16*)x_packed, n_pts, apply_sigmoid, out, sample_weight, ray_id, rgb_marched, n_ptr);
   }
   PP_CHECK_LAUNCH("rgbnet_forward");
+  return PP_OK;
+}
+
+// Deformation network with its input Jacobian (kJac).  x_rows: fp16 [n_rows, 16], four rows per sample: the value
+// row {x_hi[3], x_lo[3], 0...} (the point split into two fp16 terms so that the input keeps 22 mantissa bits) and the
+// three tangent rows e_k; weights[0] is [128, 6] = [W_0 | W_0] (the same columns multiply x_hi and x_lo), the other
+// layers as the reference stores them, the last one [4, 128].  out: fp32 [n_rows, 4].
+extern "C" int pp_warpnet_forward_packed(const void* x_rows, int64_t n_rows, int32_t depth, int32_t width,
+                                         const float* const* weights, const float* const* biases, float* out,
+                                         const int32_t* n_rows_ptr, pp_stream_t stream) {
+  PP_REQUIRE(n_rows >= 0 && (n_rows & 3) == 0, PP_ERR_INVALID_ARG, "warpnet_forward: n_rows must be a multiple of 4");
+  PP_REQUIRE(width == kMlpWidth, PP_ERR_UNSUPPORTED, "warpnet_forward: hidden width must be %d", kMlpWidth);
+  PP_REQUIRE(depth >= 2 && depth <= kMlpMaxDepth, PP_ERR_UNSUPPORTED, "warpnet_forward: depth must be 2..%d",
+             kMlpMaxDepth);
+  if (n_rows == 0) return PP_OK;
+  PP_REQUIRE(x_rows && weights && biases && out, PP_ERR_INVALID_ARG, "warpnet_forward: null pointer");
+  MlpParams P;
+  P.depth = depth;
+  P.d0 = 6;
+  P.k0p = 16;
+  P.n_out = 4;
+  size_t smem = 0;
+  for (int l = 0; l < kMlpMaxDepth; ++l) {
+    P.w[l] = l < depth ? weights[l] : nullptr;
+    P.b[l] = l < depth ? biases[l] : nullptr;
+    PP_REQUIRE(l >= depth || (P.w[l] && P.b[l]), PP_ERR_INVALID_ARG, "warpnet_forward: null layer %d", l);
+    if (l < depth) {
+      const int rows = (l == depth - 1) ? kMlpOutPad : kMlpWidth;
+      const int K = (l == 0) ? P.k0p : kMlpWidth;
+      smem += (size_t)rows * K * 2;
+    }
+  }
+  smem += (size_t)depth * kMlpWidth * 4 + 64;
+  const size_t tile_bytes = (size_t)kFwdTile * kMlpWidth * 2;
+  smem += 2 * tile_bytes;
+  PP_REQUIRE(smem <= 227 * 1024, PP_ERR_UNSUPPORTED, "warpnet_forward: %zu B of shared memory needed", smem);
+  const int64_t n_tiles = (n_rows + kFwdTile - 1) / kFwdTile;
+  const int blocks = (int)min64((n_tiles + 1) / 2, sm_count());
+  PP_CHECK_CUDA(cudaFuncSetAttribute(rgbnet_forward_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)smem));
+  rgbnet_forward_kernel<2, true><<<blocks, kFwdThreads, smem, as_stream(stream)>>>(
+      P, (const __nv_bfloat16*)x_rows, n_rows, 0, out, nullptr, nullptr, nullptr, n_rows_ptr);
+  PP_CHECK_LAUNCH("warpnet_forward");
   return PP_OK;
 }
 

@@ -28,6 +28,7 @@
 #include "march_common.cuh"
 #include "neus.cuh"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace pp {
 
@@ -99,14 +100,150 @@ __device__ __forceinline__ bool vox_point(const pp_dvgo_scene& sc, const Ray& ra
 
 __device__ __forceinline__ float neus_alpha(const NeusTerms& t) { return fminf(fmaxf(t.num / t.den, 0.f), 1.f); }
 
+__device__ __forceinline__ uint32_t h2(float lo, float hi) {
+  const __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
 __device__ __forceinline__ uint32_t bf2(float lo, float hi) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+
+// ---- implicit deformation: warped SDF lookup -------------------------------------------------------------
+// Voxurf.inference / forward(use_deform=True), voxurf_coarse.py:958-985 and :1116-1135:
+//   (deform, correction) = warp_network(x) * range;  x' = x + deform
+//   sdf_final = grid_sample_3d(sdf', x') + correction;   gradient = d sdf_final / d x  (autograd.grad in the reference)
+// The warp network runs on the tensor cores (mlp.cu, kJac) and delivers 16 floats per sample: net(x) and the three
+// tangent rows d net / d x_k.  The template SDF is read with the arithmetic of the reference's custom sampler
+// grid_sample_3d (:545-659): trilinear weights from the UNCLAMPED floor of the voxel coordinate, corner indices
+// clamped into the grid, so the warped point may leave the box; its analytic gradient (what autograd derives from
+// that expression) is chained through the warp Jacobian.
+__device__ __forceinline__ Cell make_cell_free(const pp_dvgo_scene& sc, float px, float py, float pz) {
+  Cell c;
+  const float ix = vcoord(px, sc.xyz_min[0], sc.xyz_max[0], sc.sx);
+  const float iy = vcoord(py, sc.xyz_min[1], sc.xyz_max[1], sc.sy);
+  const float iz = vcoord(pz, sc.xyz_min[2], sc.xyz_max[2], sc.sz);
+  const float x0 = floorf(ix), y0 = floorf(iy), z0 = floorf(iz);
+  c.fx = ix - x0;
+  c.fy = iy - y0;
+  c.fz = iz - z0;
+  // clamp in float first: a far-away point must not overflow the int conversion
+  const int xa = static_cast<int>(fminf(fmaxf(x0, 0.f), static_cast<float>(sc.sx - 1)));
+  const int ya = static_cast<int>(fminf(fmaxf(y0, 0.f), static_cast<float>(sc.sy - 1)));
+  const int za = static_cast<int>(fminf(fmaxf(z0, 0.f), static_cast<float>(sc.sz - 1)));
+  const int xb = static_cast<int>(fminf(fmaxf(x0 + 1.f, 0.f), static_cast<float>(sc.sx - 1)));
+  const int yb = static_cast<int>(fminf(fmaxf(y0 + 1.f, 0.f), static_cast<float>(sc.sy - 1)));
+  const int zb = static_cast<int>(fminf(fmaxf(z0 + 1.f, 0.f), static_cast<float>(sc.sz - 1)));
+  c.base = (xa * sc.sy + ya) * sc.sz + za;
+  c.ex = (xb - xa) * sc.sy * sc.sz;
+  c.ey = (yb - ya) * sc.sz;
+  c.ez = zb - za;
+  return c;
+}
+
+// -> {sdf_final, d sdf_final / d x}; D = the sample's 16 network outputs, R = output range of the network
+__device__ __forceinline__ float4 deform_sample(const pp_dvgo_scene& sc, const float4* __restrict__ srec,
+                                                const float (&p)[3], const float* __restrict__ D, float R) {
+  const float4 o = __ldg(reinterpret_cast<const float4*>(D));
+  const float4 j0 = __ldg(reinterpret_cast<const float4*>(D) + 1);   // d (deform, correction) / d x
+  const float4 j1 = __ldg(reinterpret_cast<const float4*>(D) + 2);   // ... / d y
+  const float4 j2 = __ldg(reinterpret_cast<const float4*>(D) + 3);   // ... / d z
+  const Cell c = make_cell_free(sc, fma_rn(R, o.x, p[0]), fma_rn(R, o.y, p[1]), fma_rn(R, o.z, p[2]));
+  float u[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) u[q] = __ldg(&srec[corner_off(c, q)].x);
+  const float fx = c.fx, fy = c.fy, fz = c.fz, gx = c.gx(), gy = c.gy(), gz = c.gz();
+  float s = 0.f;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) s = fma_rn(u[q], corner_w(c, q), s);
+  // derivative with respect to the continuous voxel coordinate, then to world units
+  const float dX = ((u[4] - u[0]) * gz + (u[5] - u[1]) * fz) * gy + ((u[6] - u[2]) * gz + (u[7] - u[3]) * fz) * fy;
+  const float dY = ((u[2] - u[0]) * gz + (u[3] - u[1]) * fz) * gx + ((u[6] - u[4]) * gz + (u[7] - u[5]) * fz) * fx;
+  const float dZ = ((u[1] - u[0]) * gy + (u[3] - u[2]) * fy) * gx + ((u[5] - u[4]) * gy + (u[7] - u[6]) * fy) * fx;
+  const float g[3] = {dX * static_cast<float>(sc.sx - 1) / (sc.xyz_max[0] - sc.xyz_min[0]),
+                      dY * static_cast<float>(sc.sy - 1) / (sc.xyz_max[1] - sc.xyz_min[1]),
+                      dZ * static_cast<float>(sc.sz - 1) / (sc.xyz_max[2] - sc.xyz_min[2])};
+  float4 out;
+  out.x = fma_rn(R, o.w, s);
+  out.y = g[0] + R * (j0.x * g[0] + j0.y * g[1] + j0.z * g[2] + j0.w);
+  out.z = g[1] + R * (j1.x * g[0] + j1.y * g[1] + j1.z * g[2] + j1.w);
+  out.w = g[2] + R * (j2.x * g[0] + j2.y * g[1] + j2.z * g[2] + j2.w);
+  return out;
+}
+
+// One warp per ray: reserve a run of slots for the ray's in-box samples (sample order = the reference's compacted
+// ray_pts) and write the warp network's input rows, four bf16 [16] rows per sample: {x_hi, x_lo, 0..} and e_0..e_2.
+// counter: [0] samples, [1] overflow flag, [2] rows (= 4 * samples, the MLP kernel's device-side row count).
+__global__ void __launch_bounds__(256)
+voxurf_deform_rows_kernel(pp_dvgo_scene sc, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                          const float* __restrict__ jitter, int64_t n_rays, int32_t cap_samples,
+                          uint4* __restrict__ rows, int32_t* __restrict__ dray_off, int32_t* __restrict__ counter,
+                          unsigned int* __restrict__ queue, int cap) {
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    unsigned int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(queue, 1u);
+    const int64_t r = __shfl_sync(kFull, ticket, 0);
+    if (r >= n_rays) break;
+    const Ray ray = setup_ray(sc, rays_o, rays_d, r);
+    const int n_steps = min(ray.n_steps, cap);
+    const float jit = jitter ? jitter[r] : 0.f;
+    int n_in = 0;
+    for (int base = 0; base < n_steps; base += kWarp) {
+      float p[3];
+      const int i = base + lane;
+      n_in += __popc(__ballot_sync(kFull, (i < n_steps) && vox_point(sc, ray, i, jit, p)));
+    }
+    int off = 0;
+    if (lane == 0) {
+      off = atomicAdd(counter, n_in);
+      if (off + n_in > cap_samples) {
+        atomicMax(counter + 1, 1);
+        off = -1;
+      } else {
+        atomicAdd(counter + 2, 4 * n_in);
+      }
+      dray_off[r] = off;
+    }
+    off = __shfl_sync(kFull, off, 0);
+    if (off < 0) continue;
+    int run = 0;
+    for (int base = 0; base < n_steps; base += kWarp) {
+      float p[3];
+      const int i = base + lane;
+      const bool inbox = (i < n_steps) && vox_point(sc, ray, i, jit, p);
+      const unsigned m = __ballot_sync(kFull, inbox);
+      const int slot = off + run + __popc(m & ((1u << lane) - 1u));
+      run += __popc(m);
+      if (!inbox) continue;
+      float hi[3], lo[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        hi[a] = __half2float(__float2half_rn(p[a]));
+        lo[a] = p[a] - hi[a];
+      }
+      uint4* dst = rows + (int64_t)slot * 8;   // 4 rows x 2 chunks of 8 fp16
+      const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+      dst[0] = make_uint4(h2(hi[0], hi[1]), h2(hi[2], lo[0]), h2(lo[1], lo[2]), 0u);
+      dst[1] = zero;
+      dst[2] = make_uint4(0x00003C00u, 0u, 0u, 0u);   // e_0 (fp16 1.0 = 0x3C00)
+      dst[3] = zero;
+      dst[4] = make_uint4(0x3C000000u, 0u, 0u, 0u);   // e_1
+      dst[5] = zero;
+      dst[6] = make_uint4(0u, 0x00003C00u, 0u, 0u);   // e_2
+      dst[7] = zero;
+    }
+  }
+}
+
 // ---- forward march + feature rows ---------------------------------------------------------------------------
 // dynamic shared memory per warp: s_w[cap] (weight of every step, -1 where nothing was composited) and
 // s_rec[cap] (interpolated SDF record of every step)
+// kDeform: the SDF value / normal of a sample come from deform_sample (warp network outputs `dout`, 16 floats per
+// in-box sample, the ray's run starting at dray_off[r]) instead of the record gather.
+template <bool kDeform>
 __global__ void __launch_bounds__(256, 2)
 voxurf_march_kernel(pp_dvgo_scene sc, pp_voxurf_cfg cfg, const float4* __restrict__ srec,
                     const float4* __restrict__ k0rec, const float* __restrict__ rays_o,
@@ -116,7 +253,8 @@ voxurf_march_kernel(pp_dvgo_scene sc, pp_voxurf_cfg cfg, const float4* __restric
                     float4* __restrict__ rec_out, int32_t* __restrict__ ray_off, int32_t* __restrict__ ray_cnt,
                     int32_t* __restrict__ ray_end, float* __restrict__ cum_w, float* __restrict__ alphainv_last,
                     int32_t* __restrict__ counter, unsigned int* __restrict__ queue, int cap,
-                    float* __restrict__ depth_out, float* __restrict__ normal_out) {
+                    float* __restrict__ depth_out, float* __restrict__ normal_out, const float* __restrict__ dout,
+                    const int32_t* __restrict__ dray_off, float out_range) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4* s_rec = reinterpret_cast<float4*>(smem_raw) + (size_t)warp * cap;
@@ -128,10 +266,15 @@ voxurf_march_kernel(pp_dvgo_scene sc, pp_voxurf_cfg cfg, const float4* __restric
     const int64_t r = __shfl_sync(kFull, ticket, 0);
     if (r >= n_rays) break;
     const Ray ray = setup_ray(sc, rays_o, rays_d, r);
-    const int n_steps = min(ray.n_steps, cap);
+    int n_steps = min(ray.n_steps, cap);
     const float jit = jitter ? jitter[r] : 0.f;
     float v[3];
     load3(viewdirs, r, v);
+    int doff = 0, drun = 0;
+    if constexpr (kDeform) {
+      doff = dray_off[r];
+      if (doff < 0) n_steps = 0;   // the ray's samples did not fit the row buffer (overflow flag already raised)
+    }
 
     // ---------------- phase 1: SDF gather, NeuS alpha, compositing ----------------
     float T_in = 1.f, cumw = 0.f;
@@ -143,11 +286,20 @@ voxurf_march_kernel(pp_dvgo_scene sc, pp_voxurf_cfg cfg, const float4* __restric
       const bool inbox = (i < n_steps) && vox_point(sc, ray, i, jit, p);
       float alpha = 0.f;
       float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (inbox) {
+      if constexpr (kDeform) {
+        const unsigned inb = __ballot_sync(kFull, inbox);
+        if (inbox) {
+          const int sidx = doff + drun + __popc(inb & ((1u << lane) - 1u));
+          val = deform_sample(sc, srec, p, dout + (int64_t)sidx * 16, out_range);
+        }
+        drun += __popc(inb);
+      } else if (inbox) {
         const Cell c = make_cell(sc, p[0], p[1], p[2]);
         float4 q[8];
         gather8(srec, c, q);
         val = interp8(c, q);
+      }
+      if (inbox) {
         const float g[3] = {val.y, val.z, val.w};
         alpha = neus_alpha(neus_terms(val.x, g, v, sc.stepdist, cfg.inv_s));
       }
@@ -730,20 +882,22 @@ extern "C" int pp_voxurf_k0_unpack(const void* k0_records, int64_t n_voxels, flo
   return PP_OK;
 }
 
-extern "C" int pp_voxurf_march_features(const pp_dvgo_scene* scene, const pp_voxurf_cfg* cfg,
-                                        const void* sdf_records, const void* k0_records, const float* rays_o,
-                                        const float* rays_d, const float* viewdirs, const float* jitter,
-                                        int64_t n_rays, int32_t capacity, void* feat, float* sample_weight,
-                                        int32_t* sample_ray, void* sample_rec, int32_t* ray_off, int32_t* ray_cnt,
-                                        int32_t* ray_end, float* cum_w, float* alphainv_last, int32_t* counter,
-                                        float* depth, float* normal_marched, pp_stream_t stream) {
-  const int rc = check_vox_scene(scene, cfg, "voxurf_march_features");
+template <bool kDeform>
+static int launch_vox_march(const char* what, const pp_dvgo_scene* scene, const pp_voxurf_cfg* cfg,
+                            const void* sdf_records, const void* k0_records, const float* rays_o, const float* rays_d,
+                            const float* viewdirs, const float* jitter, int64_t n_rays, int32_t capacity, void* feat,
+                            float* sample_weight, int32_t* sample_ray, void* sample_rec, int32_t* ray_off,
+                            int32_t* ray_cnt, int32_t* ray_end, float* cum_w, float* alphainv_last, int32_t* counter,
+                            float* depth, float* normal_marched, const float* dout, const int32_t* dray_off,
+                            float out_range, pp_stream_t stream) {
+  const int rc = check_vox_scene(scene, cfg, what);
   if (rc != PP_OK) return rc;
-  PP_REQUIRE(n_rays >= 0 && capacity >= 0, PP_ERR_INVALID_ARG, "voxurf_march_features: negative extent");
+  PP_REQUIRE(n_rays >= 0 && capacity >= 0, PP_ERR_INVALID_ARG, "%s: negative extent", what);
   if (n_rays == 0) return PP_OK;
   PP_REQUIRE(sdf_records && k0_records && rays_o && rays_d && viewdirs && feat && sample_weight && sample_ray &&
                  sample_rec && ray_off && ray_cnt && ray_end && cum_w && alphainv_last && counter,
-             PP_ERR_INVALID_ARG, "voxurf_march_features: null pointer");
+             PP_ERR_INVALID_ARG, "%s: null pointer", what);
+  PP_REQUIRE(!kDeform || (dout && dray_off), PP_ERR_INVALID_ARG, "%s: null deformation buffers", what);
   cudaStream_t s = as_stream(stream);
   const int cap = vox_step_capacity(scene);
   int warps = 8;   // fewer warps per block when a ray's staging (20 B per step) is large (256^3 and up)
@@ -752,22 +906,72 @@ extern "C" int pp_voxurf_march_features(const pp_dvgo_scene* scene, const pp_vox
     warps /= 2;
     smem = (size_t)warps * cap * (sizeof(float4) + sizeof(float));
   }
-  PP_REQUIRE(smem <= 100 * 1024, PP_ERR_UNSUPPORTED,
-             "voxurf_march_features: %d steps per ray exceed the shared-memory staging capacity", cap);
-  PP_CHECK_CUDA(cudaFuncSetAttribute(voxurf_march_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PP_REQUIRE(smem <= 100 * 1024, PP_ERR_UNSUPPORTED, "%s: %d steps per ray exceed the shared-memory staging capacity",
+             what, cap);
+  auto kernel = voxurf_march_kernel<kDeform>;
+  PP_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int qrc;
   unsigned int* queue = next_queue(s, &qrc);
   if (qrc != PP_OK) return qrc;
   PP_CHECK_CUDA(cudaMemsetAsync(counter, 0, 2 * sizeof(int32_t), s));
   int per_sm = 0;
-  PP_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, voxurf_march_kernel, warps * 32, smem));
+  PP_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem));
   if (per_sm < 1) per_sm = 1;
   const int64_t blocks = min64((n_rays + warps - 1) / warps, (int64_t)sm_count() * per_sm);
-  voxurf_march_kernel<<<(unsigned)blocks, warps * 32, smem, s>>>(
+  kernel<<<(unsigned)blocks, warps * 32, smem, s>>>(
       *scene, *cfg, (const float4*)sdf_records, (const float4*)k0_records, rays_o, rays_d, viewdirs, jitter, n_rays,
       capacity, (__nv_bfloat16*)feat, sample_weight, sample_ray, (float4*)sample_rec, ray_off, ray_cnt, ray_end,
-      cum_w, alphainv_last, counter, queue, cap, depth, normal_marched);
-  PP_CHECK_LAUNCH("voxurf_march_features");
+      cum_w, alphainv_last, counter, queue, cap, depth, normal_marched, dout, dray_off, out_range);
+  PP_CHECK_LAUNCH(what);
+  return PP_OK;
+}
+
+extern "C" int pp_voxurf_march_features(const pp_dvgo_scene* scene, const pp_voxurf_cfg* cfg,
+                                        const void* sdf_records, const void* k0_records, const float* rays_o,
+                                        const float* rays_d, const float* viewdirs, const float* jitter,
+                                        int64_t n_rays, int32_t capacity, void* feat, float* sample_weight,
+                                        int32_t* sample_ray, void* sample_rec, int32_t* ray_off, int32_t* ray_cnt,
+                                        int32_t* ray_end, float* cum_w, float* alphainv_last, int32_t* counter,
+                                        float* depth, float* normal_marched, pp_stream_t stream) {
+  return launch_vox_march<false>("voxurf_march_features", scene, cfg, sdf_records, k0_records, rays_o, rays_d, viewdirs,
+                                 jitter, n_rays, capacity, feat, sample_weight, sample_ray, sample_rec, ray_off,
+                                 ray_cnt, ray_end, cum_w, alphainv_last, counter, depth, normal_marched, nullptr,
+                                 nullptr, 0.f, stream);
+}
+
+extern "C" int pp_voxurf_march_features_deform(const pp_dvgo_scene* scene, const pp_voxurf_cfg* cfg,
+                                               const void* sdf_records, const void* k0_records, const float* rays_o,
+                                               const float* rays_d, const float* viewdirs, const float* jitter,
+                                               int64_t n_rays, int32_t capacity, void* feat, float* sample_weight,
+                                               int32_t* sample_ray, void* sample_rec, int32_t* ray_off,
+                                               int32_t* ray_cnt, int32_t* ray_end, float* cum_w, float* alphainv_last,
+                                               int32_t* counter, float* depth, float* normal_marched,
+                                               const float* warp_out, const int32_t* warp_ray_off, float out_range,
+                                               pp_stream_t stream) {
+  return launch_vox_march<true>("voxurf_march_features_deform", scene, cfg, sdf_records, k0_records, rays_o, rays_d,
+                                viewdirs, jitter, n_rays, capacity, feat, sample_weight, sample_ray, sample_rec,
+                                ray_off, ray_cnt, ray_end, cum_w, alphainv_last, counter, depth, normal_marched,
+                                warp_out, warp_ray_off, out_range, stream);
+}
+
+extern "C" int pp_voxurf_deform_rows(const pp_dvgo_scene* scene, const float* rays_o, const float* rays_d,
+                                     const float* jitter, int64_t n_rays, int32_t sample_capacity, void* rows,
+                                     int32_t* warp_ray_off, int32_t* counter, pp_stream_t stream) {
+  PP_REQUIRE(scene, PP_ERR_INVALID_ARG, "voxurf_deform_rows: null scene");
+  PP_REQUIRE(n_rays >= 0 && sample_capacity >= 0, PP_ERR_INVALID_ARG, "voxurf_deform_rows: negative extent");
+  if (n_rays == 0) return PP_OK;
+  PP_REQUIRE(rays_o && rays_d && rows && warp_ray_off && counter, PP_ERR_INVALID_ARG,
+             "voxurf_deform_rows: null pointer");
+  cudaStream_t s = as_stream(stream);
+  int qrc;
+  unsigned int* queue = next_queue(s, &qrc);
+  if (qrc != PP_OK) return qrc;
+  PP_CHECK_CUDA(cudaMemsetAsync(counter, 0, 4 * sizeof(int32_t), s));
+  const int64_t blocks = min64((n_rays + 7) / 8, (int64_t)sm_count() * 8);
+  voxurf_deform_rows_kernel<<<(unsigned)blocks, 256, 0, s>>>(*scene, rays_o, rays_d, jitter, n_rays, sample_capacity,
+                                                             (uint4*)rows, warp_ray_off, counter, queue,
+                                                             vox_step_capacity(scene));
+  PP_CHECK_LAUNCH("voxurf_deform_rows");
   return PP_OK;
 }
 

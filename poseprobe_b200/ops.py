@@ -258,6 +258,41 @@ def rgbnet_forward(x, weights, biases, sigmoid=True):
     return out
 
 
+def warpnet_params(weights, biases):
+    """nn.Linear parameters of the deformation network (3 -> 128 x (depth-1) -> 4) -> the device arrays
+    pp_warpnet_forward_packed takes: the first layer doubled to [128,6] (same columns for x_hi and x_lo)."""
+    ws = [w.detach().float().contiguous() for w in weights]
+    bs = [b.detach().float().contiguous() for b in biases]
+    if ws[0].shape != (128, 3) or ws[-1].shape != (4, 128):
+        raise RuntimeError("warpnet: expected layers 3 -> 128 ... 128 -> 4, got %s" % [tuple(w.shape) for w in ws])
+    ws[0] = torch.cat([ws[0], ws[0]], dim=1).contiguous()
+    return ws, bs
+
+
+def warpnet_forward(x, weights, biases, out_range=1.0):
+    """DeformedImplicitField.forward (lib/deformation/deform_net.py:23-29) together with its input Jacobian (what the
+    reference obtains with torch.autograd.grad, lib/voxurf_coarse.py:966-985), one tcgen05 pass, no autograd.
+
+    x [n,3] fp32 -> (deformation [n,3], correction [n,1], jac [n,4,3] = d (deformation, correction) / d x), all
+    multiplied by ``out_range`` (= range_shape.max())."""
+    import ctypes
+    if not x.is_cuda:
+        raise RuntimeError("warpnet_forward: x must be a CUDA tensor (no CPU fallback)")
+    x = x.detach().float().contiguous()
+    ws, bs = warpnet_params(weights, biases)
+    depth, n = len(ws), x.shape[0]
+    rows = torch.empty((4 * n, 16), dtype=torch.float16, device=x.device)
+    out = torch.empty((4 * n, 4), dtype=torch.float32, device=x.device)
+    wp = (ctypes.c_void_p * depth)(*[w.data_ptr() for w in ws])
+    bp = (ctypes.c_void_p * depth)(*[b.data_ptr() for b in bs])
+    with torch.cuda.device(x.device):
+        check(lib.pp_warpnet_pack_points(ptr(x), n, ptr(rows), stream()), "warpnet_pack_points")
+        check(lib.pp_warpnet_forward_packed(ptr(rows), 4 * n, depth, 128, wp, bp, ptr(out), None, stream()),
+              "warpnet_forward")
+    out = out.reshape(n, 4, 4) * out_range
+    return out[:, 0, :3], out[:, 0, 3:], out[:, 1:, :].transpose(1, 2)
+
+
 class _RgbNet(torch.autograd.Function):
     """sigmoid(rgbnet(x)) with both directions on tcgen05; the backward recomputes the forward per tile."""
 

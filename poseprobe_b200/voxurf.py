@@ -152,6 +152,7 @@ class FusedVoxurf:
         self.dx_cols = FEAT_COLS if self.pose_grad else DX_COLS
         self._bufs = None
         self._arr = lambda ts: (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])
+        self.warp = None                     # (weights, biases, out_range) of the deformation network, see below
         self.rebuild_records()
 
     # ---- configuration that changes over training --------------------------------------------------------
@@ -211,6 +212,36 @@ class FusedVoxurf:
             self._bufs = b
         return b
 
+    # ---- implicit deformation (render path) --------------------------------------------------------------------
+    def set_warp_network(self, weights, biases, out_range):
+        """Attach the deformation network (DeformedImplicitField: Linear 3->128, 128->128 x3, 128->4, lib/deformation/
+        deform_net.py:12-29; ``out_range`` = range_shape.max()).  `render` then follows Voxurf.inference
+        (voxurf_coarse.py:1093-1215): SDF and normal of every sample come from the warped template lookup."""
+        from .ops import warpnet_params
+        ws, bs = warpnet_params([w.to(self.device) for w in weights], [b.to(self.device) for b in biases])
+        self.warp = (ws, bs, float(out_range))
+
+    def _march_deform(self, b, rays_o, rays_d, viewdirs, jitter, depth=None, normal=None):
+        n, cap = rays_o.shape[0], b["cap"]
+        if "drows" not in b:
+            dev = self.device
+            b["drows"] = torch.empty((4 * cap, 16), dtype=torch.float16, device=dev)
+            b["dout"] = torch.empty((4 * cap, 4), dtype=torch.float32, device=dev)
+            b["dray_off"] = torch.empty(b["n_rays"], dtype=torch.int32, device=dev)
+            b["dcounter"] = torch.zeros(4, dtype=torch.int32, device=dev)
+        ws, bs, out_range = self.warp
+        check(lib.pp_voxurf_deform_rows(ctypes.byref(self.scene), ptr(rays_o), ptr(rays_d), ptr(jitter), n, cap,
+                                        ptr(b["drows"]), ptr(b["dray_off"]), ptr(b["dcounter"]), stream()),
+              "voxurf_deform_rows")
+        check(lib.pp_warpnet_forward_packed(ptr(b["drows"]), 4 * cap, len(ws), 128, self._arr(ws), self._arr(bs),
+                                            ptr(b["dout"]), ptr(b["dcounter"][2:]), stream()), "warpnet_forward")
+        check(lib.pp_voxurf_march_features_deform(
+            ctypes.byref(self.scene), ctypes.byref(self.cfg), ptr(self.srec), ptr(self.k0rec), ptr(rays_o),
+            ptr(rays_d), ptr(viewdirs), ptr(jitter), n, cap, ptr(b["feat"]), ptr(b["w"]), ptr(b["rid"]),
+            ptr(b["rec"]), ptr(b["ray_off"]), ptr(b["ray_cnt"]), ptr(b["ray_end"]), ptr(b["cum_w"]), ptr(b["last"]),
+            ptr(b["counter"]), ptr(depth), ptr(normal), ptr(b["dout"]), ptr(b["dray_off"]), out_range, stream()),
+            "voxurf_march_features_deform")
+
     # ---- forward pieces -----------------------------------------------------------------------------------------
     def _march(self, b, rays_o, rays_d, viewdirs, jitter, depth=None, normal=None):
         n = rays_o.shape[0]
@@ -226,9 +257,14 @@ class FusedVoxurf:
                                            self._arr(self.biases), 1, None, ptr(b["w"]), ptr(b["rid"]), ptr(b["acc"]),
                                            ptr(b["counter"]), stream()), "rgbnet_forward")
 
-    def render(self, rays_o, rays_d, viewdirs, want_depth=False, want_normal=False):
+    def render(self, rays_o, rays_d, viewdirs, want_depth=False, want_normal=False, use_deform=None, jitter=None):
         """-> rgb_marched [N,3], alphainv_last [N], cum_weights [N] (+ depth [N], normal_marched [N,3] on request):
-        the per-ray outputs of Voxurf.forward / inference that lib/nvs_fun.py:74-88 reads."""
+        the per-ray outputs of Voxurf.forward / inference that lib/nvs_fun.py:74-88 reads.  use_deform (default: True
+        once set_warp_network was called) selects the implicit-deformation lookup of Voxurf.inference."""
+        if use_deform is None:
+            use_deform = self.warp is not None
+        if use_deform and self.warp is None:
+            raise RuntimeError("FusedVoxurf.render: use_deform=True needs set_warp_network first")
         for t, nme in ((rays_o, "rays_o"), (rays_d, "rays_d"), (viewdirs, "viewdirs")):
             _need_cuda(t, nme)
         n = rays_o.shape[0]
@@ -236,7 +272,7 @@ class FusedVoxurf:
         depth = torch.empty(n, dtype=torch.float32, device=self.device) if want_depth else None
         normal = torch.empty((n, 3), dtype=torch.float32, device=self.device) if want_normal else None
         with torch.cuda.device(self.device):
-            self._march(b, rays_o, rays_d, viewdirs, None, depth, normal)
+            (self._march_deform if use_deform else self._march)(b, rays_o, rays_d, viewdirs, jitter, depth, normal)
             self._mlp_forward(b, n)
             check(lib.pp_voxurf_ray_loss(n, ptr(b["acc"]), ptr(b["cum_w"]), ptr(b["acc"]), self.scene.bg, 0.0,
                                          ptr(b["g_ray"]), ptr(b["rgb"]), None, stream()), "voxurf_ray_loss")
@@ -473,6 +509,10 @@ class Voxurf(torch.nn.Module):
         self.sdf_beta = nn.Parameter(torch.Tensor([2.0]))
         self.s_val = nn.Parameter(torch.ones(1), requires_grad=False)
         self.s_ratio, self.s_start, self.step_start = s_ratio, s_start, step_start
+        from .deform import DeformedImplicitField
+        range_shape = kwargs.get("range_shape")
+        self.range_shape = (self.xyz_max - self.xyz_min) if range_shape is None else torch.as_tensor(range_shape)
+        self.warp_network = DeformedImplicitField(range_shape=self.range_shape)                       # :84-85
         self._eng = None
 
     def _engine(self, render_kwargs):
@@ -506,6 +546,31 @@ class Voxurf(torch.nn.Module):
         rgb_marched = (acc + (1 - cumw[:, None]) * render_kwargs.get("bg", 0.0)).clamp(0, 1)          # :1040-1042
         return {"alphainv_cum": last, "cum_weights": cumw[:, None], "rgb_marched": rgb_marched,
                 "s_val": float(self.s_val)}
+
+
+def _voxurf_inference(self, rays_o, rays_d, viewdirs, global_step=None, **render_kwargs):
+    """Voxurf.inference (lib/voxurf_coarse.py:1093-1215): render with the implicit deformation - SDF and normal of
+    every in-box sample from the warped template lookup - forward only.  Returns the per-ray entries that
+    lib/nvs_fun.py:74-88 reads: rgb_marched, alphainv_cum, cum_weights, depth, disp, normal_marched."""
+    eng, _, _ = self._engine(render_kwargs)
+    ws, bs = self.warp_network.parameters_for_kernel()
+    eng.load_params(self.sdf.grid, self.k0.grid, *self._rgbnet_params(), float(self.sdf_alpha), float(self.sdf_beta))
+    eng.set_warp_network([w.detach() for w in ws], [b.detach() for b in bs], self.warp_network.output_range)
+    eng.set_schedule(s_val=float(self.s_val), progress=1.0 if global_step is None else global_step / self.N_iters)
+    rgb, last, cumw, depth, normal = eng.render(rays_o, rays_d, viewdirs, want_depth=True, want_normal=True,
+                                                use_deform=True)
+    return {"rgb_marched": rgb, "alphainv_cum": last, "cum_weights": cumw[:, None], "depth": depth,
+            "disp": 1 / depth, "normal_marched": normal, "s_val": float(self.s_val)}
+
+
+def _rgbnet_params(self):
+    from .ops import rgbnet_from_sequential
+    ws, bs = rgbnet_from_sequential(self.rgbnet)
+    return [w.detach() for w in ws], [b.detach() for b in bs]
+
+
+Voxurf.inference = torch.no_grad()(_voxurf_inference)
+Voxurf._rgbnet_params = _rgbnet_params
 
 
 def smoke(dev):

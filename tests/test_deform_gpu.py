@@ -1,0 +1,217 @@
+"""Implicit-deformation render path (forward): the deformation network with its input Jacobian
+on tcgen05 (mlp.cu, kJac) and the warped SDF lookup of Voxurf.inference (voxurf_fused.cu, kDeform) against
+
+* plain PyTorch: the same network evaluated in fp32 with torch.autograd for the Jacobian, and an emulation of the
+  kernel's arithmetic (bf16 operands, fp32 accumulation, tangents gated by the value row) for a tight check;
+* oracle/voxurf_cpu.forward(warp=...), the restatement of the reference's deform branch that
+  tests/test_oracle_golden.py pins against the reference's own code (tests/golden/voxurf_deform.npz).
+
+Tolerances: the warp network runs on fp16 operands (2^-12 relative rounding per operand, accumulation in the tensor
+core's fp32 datapath): 2e-3 of the output scale against fp32, 1e-3 against the fp16 emulation (measured 3e-4: the
+MMA's internal accumulation is not a sequence of IEEE fp32 adds).  Its Jacobian is compared per sample because a ReLU
+gate that flips under rounding changes one sample's Jacobian by a rank-1 term: >= 90 % of the samples within 5e-3
+relative (measured 94-97 %, the same fraction the fp16 emulation shows against fp32), median < 2e-3 (fp32 autograd) /
+1e-3 (emulation).  Per-ray render outputs downstream of the bf16 colour network: 2e-2 absolute.
+"""
+import pytest
+import torch
+import torch.nn as nn
+
+pytestmark = pytest.mark.gpu
+
+MN, MX = [-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]
+
+
+def make_warp(seed, last_scale=0.005, depth=5):
+    torch.manual_seed(seed)
+    dims = [3] + [128] * (depth - 1) + [4]
+    ws, bs = [], []
+    for i in range(depth):
+        w = torch.empty(dims[i + 1], dims[i])
+        nn.init.kaiming_normal_(w, a=0.0, nonlinearity="relu", mode="fan_in")       # modules.py:127-130
+        ws.append(w)
+        bs.append(0.1 * torch.randn(dims[i + 1]))
+    ws[-1] = last_scale * torch.randn(4, 128)
+    bs[-1] = 0.01 * torch.randn(4)
+    return ws, bs
+
+
+def net_fp32(x, ws, bs):
+    h = x
+    for i, (w, b) in enumerate(zip(ws, bs)):
+        h = torch.nn.functional.linear(h, w, b)
+        if i < len(ws) - 1:
+            h = torch.relu(h)
+    return h
+
+
+def bf(t):
+    return t.to(torch.float16).to(torch.float32)      # the warp network's operand format
+
+
+def net_emulated(x, ws, bs):
+    """the kernel's arithmetic: fp16 operands, fp32 accumulation, tangents gated by the value row's pattern"""
+    hi = bf(x)
+    lo = bf(x - hi)
+    w0 = bf(ws[0])
+    z = hi @ w0.T + lo @ w0.T + bs[0]
+    gate = (z > 0).float()
+    h = bf(torch.relu(z))
+    t = bf(gate[:, None, :] * w0.T[None])                  # [n, 3, 128]: tangent k = column k of W_0
+    for w, b in zip(ws[1:-1], bs[1:-1]):
+        wb = bf(w)
+        z = h @ wb.T + b
+        gate = (z > 0).float()
+        t = bf(gate[:, None, :] * (t @ wb.T))
+        h = bf(torch.relu(z))
+    wl = bf(ws[-1])
+    return h @ wl.T + bs[-1], (t @ wl.T).transpose(1, 2)   # [n,4], [n,4,3]
+
+
+@pytest.mark.parametrize("n,depth", [(1000, 5), (37, 3), (4096, 5)])
+def test_warpnet_forward_with_jacobian(cuda, n, depth):
+    from poseprobe_b200 import ops
+    ws, bs = make_warp(3 + depth, last_scale=0.05, depth=depth)
+    torch.manual_seed(n)
+    x = torch.rand(n, 3) * 2 - 1
+    R = 2.0
+    d, c, jac = ops.warpnet_forward(x.to(cuda), [w.to(cuda) for w in ws], [b.to(cuda) for b in bs], out_range=R)
+    assert d.shape == (n, 3) and c.shape == (n, 1) and jac.shape == (n, 4, 3)
+    got = torch.cat([d, c], 1).cpu()
+    # fp32 reference with autograd Jacobian (what the reference computes, voxurf_coarse.py:966-985)
+    xg = x.clone().requires_grad_(True)
+    y = net_fp32(xg, ws, bs) * R
+    want_jac = torch.stack([torch.autograd.grad(y[:, k].sum(), xg, retain_graph=True)[0] for k in range(4)], 1)
+    scale = float(y.detach().abs().max())
+    assert float((got - y.detach()).abs().max()) < 2e-3 * scale
+
+    def per_sample_rel(a, b):
+        return (a - b).flatten(1).norm(dim=1) / b.flatten(1).norm(dim=1).clamp_min(1e-12)
+
+    # a gate that flips because z was rounded changes that sample's Jacobian by a rank-1 term (the Jacobian of a
+    # ReLU network is discontinuous there): bounded fraction of such samples, the rest agrees to operand rounding
+    rel = per_sample_rel(jac.cpu(), want_jac)
+    assert float((rel < 5e-3).float().mean()) > 0.9 and float(rel.median()) < 2e-3, (
+        float((rel < 5e-3).float().mean()), float(rel.median()))
+    assert float((jac.cpu() - want_jac).norm() / want_jac.norm()) < 0.1
+    # emulation of the kernel's arithmetic: same gates up to accumulation order
+    ey, ejac = net_emulated(x, ws, bs)
+    assert float((got - ey * R).abs().max()) < 1e-3 * scale, float((got - ey * R).abs().max()) / scale
+    rel = per_sample_rel(jac.cpu(), ejac * R)
+    assert float((rel < 5e-3).float().mean()) > 0.9 and float(rel.median()) < 1e-3, (
+        float((rel < 5e-3).float().mean()), float(rel.median()))
+
+
+def make_scene(G, n_rays, seed):
+    from poseprobe_b200 import synthetic
+    torch.manual_seed(seed)
+    sdf = synthetic.make_sdf_grid(G, radius=0.5, noise=0.01)
+    k0 = 0.3 * torch.randn(1, 12, G, G, G)
+    net = nn.Sequential(nn.Linear(57, 128), nn.ReLU(inplace=True), nn.Sequential(nn.Linear(128, 128), nn.ReLU(inplace=True)),
+                        nn.Linear(128, 3))
+    nn.init.constant_(net[-1].bias, 0)
+    with torch.no_grad():
+        net[0].weight.mul_(2.0)
+        net[-1].weight.mul_(4.0)
+    o, d, v = synthetic.make_rays(n_rays, seed=seed + 5)
+    kw = dict(stepsize=0.5, s_val=0.05, bg=0.3, posbase_pe=5, viewbase_pe=1, barf_c2f=(0.1, 0.5), sdf_alpha=10.0,
+              sdf_beta=0.35)
+    return sdf, k0, net, o, d, v, kw
+
+
+@pytest.mark.parametrize("use_jitter", [False, True])
+def test_render_deform_vs_oracle(cuda, use_jitter):
+    from oracle import voxurf_cpu
+    from poseprobe_b200 import ops, voxurf
+    G, N, R = 32, 384, 2.0
+    sdf, k0, net, o, d, v, kw = make_scene(G, N, seed=11)
+    ws, bs = make_warp(21)
+    rw, rb = ops.rgbnet_from_sequential(net)
+    eng = voxurf.FusedVoxurf(sdf.to(cuda), k0.to(cuda), [w.detach() for w in rw], [b.detach() for b in rb], MN, MX, **kw)
+    eng.set_warp_network(ws, bs, R)
+    jitter = torch.rand(N) if use_jitter else None
+    rgb, last, cumw, depth, normal = eng.render(o.to(cuda), d.to(cuda), v.to(cuda), want_depth=True, want_normal=True,
+                                                jitter=jitter.to(cuda) if use_jitter else None)
+    b = eng._bufs
+    assert b["dcounter"].tolist()[1] == 0
+    want = voxurf_cpu.forward(sdf, k0, net, o, d, v, MN, MX, kw["stepsize"], eng.voxel_size, kw["s_val"], bg=kw["bg"],
+                              sdf_alpha=kw["sdf_alpha"], sdf_beta=kw["sdf_beta"], posbase_pe=5, viewbase_pe=1,
+                              barf_c2f=kw["barf_c2f"], progress=1.0, jitter=jitter, warp=(ws, bs, R))
+    want = {k: (t.detach() if torch.is_tensor(t) else t) for k, t in want.items()}
+    # all in-box samples went through the network, in the reference's compacted order
+    assert b["dcounter"].tolist()[0] == want["ray_id"].numel() and b["dcounter"].tolist()[2] == 4 * want["ray_id"].numel()
+    # per-sample SDF / normal of the composited samples (b["rec"]) against the oracle, ray by ray
+    m = eng.n_samples()
+    ray_cnt, ray_off = b["ray_cnt"][:N].cpu().long(), b["ray_off"][:N].cpu().long()
+    rid_ref = want["ray_id"]
+    per_ray_ref = torch.zeros(N, dtype=torch.long).index_add_(0, rid_ref, torch.ones_like(rid_ref))
+    starts_ref = torch.cumsum(per_ray_ref, 0) - per_ray_ref
+    rec = b["rec"][:m].cpu()
+    checked, grad_err = 0, []
+    for r in range(0, N, 5):
+        c = int(ray_cnt[r])
+        if c == 0:
+            continue
+        sl = slice(int(ray_off[r]), int(ray_off[r]) + c)
+        rs = slice(int(starts_ref[r]), int(starts_ref[r]) + c)
+        torch.testing.assert_close(rec[sl, 0], want["sdf"][rs], rtol=0, atol=1e-3)
+        grad_err.append((rec[sl, 1:] - want["gradient"][rs]).abs().max(-1).values)
+        checked += c
+    assert checked > 500
+    grad_err = torch.cat(grad_err)       # gate flips (see test_warpnet_forward_with_jacobian) hit a few samples
+    assert float((grad_err < 5e-3).float().mean()) > 0.95 and float(grad_err.median()) < 1e-3
+    torch.testing.assert_close(cumw.cpu(), want["cum_weights"][:, 0], rtol=0, atol=2e-2)
+    torch.testing.assert_close(last.cpu(), want["alphainv_cum"], rtol=0, atol=2e-2)
+    torch.testing.assert_close(rgb.cpu(), want["rgb_marched"], rtol=0, atol=2e-2)
+    rid, w, g = want["ray_id"], want["weights"], want["gradient"]
+    dist = kw["stepsize"] * eng.voxel_size
+    steps = want["step_id"].float() + (jitter[rid] if use_jitter else 0.0)
+    want_depth = torch.zeros(N).index_add_(0, rid, w * steps * dist)
+    want_normal = torch.zeros(N, 3).index_add_(0, rid, w[:, None] * g / (g.norm(2, -1, keepdim=True) + 1e-6))
+    torch.testing.assert_close(depth.cpu(), want_depth, rtol=0, atol=3e-2)
+    torch.testing.assert_close(normal.cpu(), want_normal, rtol=0, atol=3e-2)
+    # the deformation is not a no-op in this scene: the plain lookup renders something else
+    rgb0 = eng.render(o.to(cuda), d.to(cuda), v.to(cuda), use_deform=False,
+                      jitter=jitter.to(cuda) if use_jitter else None)[0]
+    assert float((rgb0 - rgb).abs().max()) > 0.05
+
+
+def test_voxurf_module_inference(cuda):
+    """pp.Voxurf.inference (the reference's render entry point, lib/nvs_fun.py:81-83 -> voxurf_coarse.py:1093-1215) with
+    a non-trivial warp network against the oracle's deform branch."""
+    import poseprobe_b200 as pp
+    from oracle import voxurf_cpu
+    G, N = 24, 200
+    sdf, k0, net, o, d, v, kw = make_scene(G, N, seed=31)
+    ws, bs = make_warp(41)
+    m = pp.Voxurf(MN, MX, num_voxels=G ** 3, num_voxels_base=G ** 3, rgbnet_depth=3, barf_c2f=kw["barf_c2f"],
+                  N_iters=1000).to(cuda)
+    assert "warp_network.deform_net.net.net.4.0.weight" in m.state_dict()
+    with torch.no_grad():
+        m.sdf.grid.copy_(sdf)
+        m.k0.grid.copy_(k0)
+        for dst, src in zip([q for q in m.rgbnet.modules() if isinstance(q, nn.Linear)],
+                            [q for q in net.modules() if isinstance(q, nn.Linear)]):
+            dst.weight.copy_(src.weight)
+            dst.bias.copy_(src.bias)
+        for lin, w, b in zip(m.warp_network.linears(), ws, bs):
+            lin.weight.copy_(w)
+            lin.bias.copy_(b)
+        m.sdf_alpha.fill_(kw["sdf_alpha"])
+        m.sdf_beta.fill_(kw["sdf_beta"])
+        m.s_val.fill_(kw["s_val"])
+    out = m.inference(o.to(cuda), d.to(cuda), v.to(cuda), near=0.2, far=1e9, stepsize=0.5, bg=kw["bg"])
+    R = m.warp_network.output_range
+    assert R == 2.0
+    want = voxurf_cpu.forward(sdf, k0, net, o, d, v, MN, MX, 0.5, float(m.voxel_size), kw["s_val"], bg=kw["bg"],
+                              sdf_alpha=kw["sdf_alpha"], sdf_beta=kw["sdf_beta"], posbase_pe=5, viewbase_pe=1,
+                              barf_c2f=kw["barf_c2f"], progress=1.0, warp=(ws, bs, R))
+    torch.testing.assert_close(out["rgb_marched"].cpu(), want["rgb_marched"].detach(), rtol=0, atol=2e-2)
+    torch.testing.assert_close(out["cum_weights"].cpu(), want["cum_weights"].detach(), rtol=0, atol=2e-2)
+    torch.testing.assert_close(out["alphainv_cum"].cpu(), want["alphainv_cum"].detach(), rtol=0, atol=2e-2)
+    assert out["depth"].shape == (N,) and out["normal_marched"].shape == (N, 3)
+    # the module's own network call: deformation and correction of free-standing points
+    x = (torch.rand(300, 3) * 2 - 1)
+    dfm, cor = m.warp_network(x.to(cuda))
+    y = net_fp32(x, ws, bs) * R
+    assert float((torch.cat([dfm, cor], 1).cpu() - y).abs().max()) < 2e-3 * float(y.abs().max())

@@ -76,3 +76,33 @@ def test_oracle_forward_properties():
     voxurf_cpu.mse_loss(out, torch.rand(N, 3)).backward()
     assert torch.isfinite(sdf.grad).all() and float(sdf.grad.abs().sum()) > 0
     assert torch.isfinite(k0.grad).all() and float(k0.grad.abs().sum()) > 0
+
+
+def test_deformation_network_mirror_keeps_the_reference_layout():
+    """poseprobe_b200.deform.DeformedImplicitField: state_dict keys / shapes of the reference module
+    (lib/deformation/deform_net.py + modules.py nesting, checked against the reference class when
+    tests/golden/make_golden_deform.py was written), the reference's initialisation (zero last layer), and the
+    golden fixture's warp weights load into it."""
+    import os
+    import numpy as np
+    import torch
+    from poseprobe_b200.deform import DeformedImplicitField
+    net = DeformedImplicitField(range_shape=torch.tensor([2.0, 1.5, 1.0]))
+    want = {"progress": ()}
+    shapes = [(128, 3), (128, 128), (128, 128), (128, 128), (4, 128)]
+    for i, shp in enumerate(shapes):
+        want["deform_net.net.net.%d.0.weight" % i] = shp
+        want["deform_net.net.net.%d.0.bias" % i] = (shp[0],)
+    assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == want
+    assert net.output_range == 2.0
+    lin = net.linears()
+    assert float(lin[-1].weight.abs().sum()) == 0.0 and float(lin[-1].bias.abs().sum()) == 0.0
+    assert 0.5 < float(lin[1].weight.std()) * (128 / 2) ** 0.5 < 1.5        # Kaiming normal, fan_in, ReLU gain
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "voxurf_deform.npz"))
+    sd = {"progress": torch.tensor(0.3)}
+    for i in range(5):
+        sd["deform_net.net.net.%d.0.weight" % i] = torch.from_numpy(g["ww%d" % i])
+        sd["deform_net.net.net.%d.0.bias" % i] = torch.from_numpy(g["wb%d" % i])
+    net.load_state_dict(sd)
+    ws, bs = net.parameters_for_kernel()
+    assert torch.equal(ws[4].detach(), torch.from_numpy(g["ww4"]))

@@ -397,6 +397,8 @@ def test_voxurf_module_autograd_vs_oracle(cuda):
     for name, p in net.state_dict().items():
         state["rgbnet." + name] = p
     missing, unexpected = mod.load_state_dict(state, strict=False)
+    # (this state dict carries no deformation network; a reference checkpoint does, see tests/test_deform_gpu.py)
+    missing = [k for k in missing if not k.startswith("warp_network.")]
     assert not unexpected and set(missing) <= {"xyz_min", "xyz_max", "sdf.xyz_min", "sdf.xyz_max", "k0.xyz_min",
                                                "k0.xyz_max", "sdf_alpha", "sdf_beta", "s_val"}
     with torch.no_grad():
