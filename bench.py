@@ -402,7 +402,28 @@ def fine_stage_bench(dev):
     step_bytes = 60 * RAYS + 96 * (4 + 12) * m + 32 * V * 13
     mlp_flops = 3 * 2.0 * m * (57 * 128 + 2 * 128 * 128 + 128 * 3)
     pk, _ = peaks()
-    return {"workload": "Voxurf SDF fine stage (BASELINE configs[2], one rank): 160^3 sdf + 12-ch k0 + rgbnet "
+    # render with the implicit deformation (Voxurf.inference): warp network 3-128x4-4 + Jacobian on every in-box sample
+    dims = [3, 128, 128, 128, 128, 4]
+    wws = [torch.randn(dims[i + 1], dims[i]) * (2.0 / dims[i]) ** 0.5 for i in range(5)]
+    wws[-1] = 0.005 * torch.randn(4, 128)
+    eng.set_warp_network(wws, [0.1 * torch.randn(dims[i + 1]) for i in range(5)], 2.0)
+    o, d, v, _ = batches[0]
+    for _ in range(3):
+        eng.render(o, d, v, use_deform=True)
+    e0.record()
+    for _ in range(10):
+        eng.render(o, d, v, use_deform=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_r = e0.elapsed_time(e1) / 10
+    n_in = eng._bufs["dcounter"].tolist()[0]
+    warp_flops = 4 * n_in * 2.0 * (16 * 128 + 3 * 128 * 128 + 128 * 16)
+    render_deform = {"workload": "Voxurf.inference: warp network (3-128x4-4, with input Jacobian, fp16 tcgen05) on every "
+                                 "in-box sample + warped SDF lookup + rgbnet, %d-ray chunks, forward only" % RAYS,
+                     "render_mrays_per_s": RAYS / (ms_r * 1e-3) / 1e6, "ms_per_chunk": ms_r,
+                     "inbox_samples_per_ray": n_in / RAYS, "warp_network_tflop_per_chunk": warp_flops / 1e12}
+    return {"render_deform": render_deform,
+            "workload": "Voxurf SDF fine stage (BASELINE configs[2], one rank): 160^3 sdf + 12-ch k0 + rgbnet "
                         "57-128-128-128-3 (tcgen05), 8192 rays/step, fwd+bwd+Adam",
             "train_rays_per_s": RAYS / (ms * 1e-3), "ms_per_step": ms, "composited_samples_per_ray": m / RAYS,
             "M_c_over_M": 1.0, "algorithmic_bytes_per_step": step_bytes, "mlp_algorithmic_tflop_per_step": mlp_flops / 1e12,
