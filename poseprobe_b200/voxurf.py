@@ -286,7 +286,8 @@ class FusedVoxurf:
     def n_samples(self):
         """Composited samples of the last march (host sync); raises if the sample capacity overflowed."""
         c = self._bufs["counter"].tolist()
-        if c[1]:
+        dc = self._bufs["dcounter"].tolist() if "dcounter" in self._bufs else [0, 0]
+        if c[1] or dc[1]:
             raise RuntimeError("FusedVoxurf: sample capacity exceeded (raise samples_per_ray_cap)")
         return c[0]
 

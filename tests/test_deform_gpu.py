@@ -215,3 +215,51 @@ def test_voxurf_module_inference(cuda):
     dfm, cor = m.warp_network(x.to(cuda))
     y = net_fp32(x, ws, bs) * R
     assert float((torch.cat([dfm, cor], 1).cpu() - y).abs().max()) < 2e-3 * float(y.abs().max())
+
+
+def test_render_deform_edge_cases(cuda):
+    """Non-cubic grid and box, rays that miss the box mixed in (no rows reserved for them), a ray count that is not a
+    multiple of the warps per block, and a sample capacity that is too small (flagged, nothing overrun)."""
+    from oracle import voxurf_cpu
+    from poseprobe_b200 import ops, synthetic, voxurf
+    torch.manual_seed(60)
+    X, Y, Z = 30, 22, 36
+    mn, mx = [-0.4, -0.35, -0.5], [0.45, 0.35, 0.6]
+    lx, ly, lz = [torch.linspace(a, b, n) for a, b, n in zip(mn, mx, (X, Y, Z))]
+    gx, gy, gz = torch.meshgrid(lx, ly, lz, indexing="ij")
+    sdf = ((gx * gx + gy * gy + gz * gz).sqrt() - 0.25 + 0.005 * torch.randn(X, Y, Z))[None, None].contiguous()
+    k0 = 0.3 * torch.randn(1, 12, X, Y, Z)
+    net = nn.Sequential(nn.Linear(57, 128), nn.ReLU(), nn.Linear(128, 128), nn.ReLU(), nn.Linear(128, 3))
+    with torch.no_grad():
+        net[0].weight.mul_(2.0)
+        net[-1].weight.mul_(4.0)
+    N = 203
+    o, d, v = synthetic.make_rays(N, seed=61, radius=1.5, target_half=0.3)
+    o[::9] = torch.tensor([5.0, 5.0, 5.0])           # these miss the box
+    d[::9] = torch.tensor([1.0, 0.0, 0.0])
+    v[::9] = torch.tensor([1.0, 0.0, 0.0])
+    ws, bs = make_warp(62, last_scale=0.002)
+    R = 1.1
+    rw, rb = ops.rgbnet_from_sequential(net)
+    kw = dict(stepsize=0.5, s_val=0.03, bg=0.2, posbase_pe=5, viewbase_pe=1, barf_c2f=None, sdf_alpha=10.0,
+              sdf_beta=0.35)
+    eng = voxurf.FusedVoxurf(sdf.to(cuda), k0.to(cuda), [w.detach() for w in rw], [b.detach() for b in rb], mn, mx, **kw)
+    eng.set_warp_network(ws, bs, R)
+    rgb, last, cumw = eng.render(o.to(cuda), d.to(cuda), v.to(cuda))
+    want = voxurf_cpu.forward(sdf, k0, net, o, d, v, mn, mx, 0.5, eng.voxel_size, kw["s_val"], bg=kw["bg"],
+                              sdf_alpha=10.0, sdf_beta=0.35, posbase_pe=5, viewbase_pe=1, barf_c2f=None,
+                              warp=(ws, bs, R))
+    assert eng._bufs["dcounter"].tolist()[0] == want["ray_id"].numel()
+    assert int((eng._bufs["dray_off"][:N][::9] >= 0).sum()) == len(range(0, N, 9))    # empty runs are legal, not -1
+    torch.testing.assert_close(rgb.cpu(), want["rgb_marched"].detach(), rtol=0, atol=2e-2)
+    torch.testing.assert_close(cumw.cpu(), want["cum_weights"].detach()[:, 0], rtol=0, atol=2e-2)
+    torch.testing.assert_close(rgb.cpu()[::9], torch.full((len(range(0, N, 9)), 3), kw["bg"]))
+    assert torch.equal(last.cpu()[::9], torch.ones(len(range(0, N, 9))))
+    small = voxurf.FusedVoxurf(sdf.to(cuda), k0.to(cuda), [w.detach() for w in rw], [b.detach() for b in rb], mn, mx,
+                               samples_per_ray_cap=3, **kw)
+    small.set_warp_network(ws, bs, R)
+    small.render(o.to(cuda), d.to(cuda), v.to(cuda))
+    torch.cuda.synchronize()
+    assert small._bufs["dcounter"].tolist()[1] == 1
+    with pytest.raises(RuntimeError, match="capacity"):
+        small.n_samples()
