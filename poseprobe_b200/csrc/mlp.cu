@@ -183,16 +183,23 @@ rgbnet_forward_kernel(MlpParams P, const __nv_bfloat16* __restrict__ x, int64_t 
           for (int j = 0; j < 8; ++j) bb[j] = b4[j];
           tmem_ld_wait();
           if constexpr (kJac) {
-            const float* bf = reinterpret_cast<const float*>(bb);
-            const bool is_value = (lane & 3) == 0;
+            // X = acc + bias on the value lane, acc on the tangent lanes; both become X * (z_value > 0): ReLU for the
+            // value row (z * [z > 0]), the gate for the tangents.  Packed throughout: per two accumulator columns one
+            // FFMA2, one f32x2 -> f16x2 conversion, one shuffle of the packed pair, one HSET2, one HMUL2.
+            const float2* bf2 = reinterpret_cast<const float2*>(bb);
+            const float bsel = (lane & 3) == 0 ? 1.f : 0.f;
+            const float2 bs2 = make_float2(bsel, bsel);
+            const __half2 zero2 = __floats2half2_rn(0.f, 0.f);
             uint32_t pk[16];
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              const float a0 = __uint_as_float(r[j]), a1 = __uint_as_float(r[j + 1]);
-              const float z0 = a0 + bf[j], z1 = a1 + bf[j + 1];
-              const float v0 = __shfl_sync(kFull, z0, lane & ~3), v1 = __shfl_sync(kFull, z1, lane & ~3);
-              pk[j >> 1] = pack_f16(is_value ? fmaxf(z0, 0.f) : (v0 > 0.f ? a0 : 0.f),
-                                    is_value ? fmaxf(z1, 0.f) : (v1 > 0.f ? a1 : 0.f));
+            for (int j = 0; j < 16; ++j) {
+              const float2 a = make_float2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+              const __half2 xh = __float22half2_rn(__ffma2_rn(bf2[j], bs2, a));
+              const uint32_t xu = *reinterpret_cast<const uint32_t*>(&xh);
+              const uint32_t vu = __shfl_sync(kFull, xu, lane & ~3);
+              const __half2 gate = __hgt2(*reinterpret_cast<const __half2*>(&vu), zero2);
+              const __half2 o = __hmul2(xh, gate);
+              pk[j] = *reinterpret_cast<const uint32_t*>(&o);
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j)
