@@ -106,3 +106,59 @@ def test_deformation_network_mirror_keeps_the_reference_layout():
     net.load_state_dict(sd)
     ws, bs = net.parameters_for_kernel()
     assert torch.equal(ws[4].detach(), torch.from_numpy(g["ww4"]))
+
+
+def test_deform_closed_form_matches_autograd():
+    """oracle/deform_analytic.py (the formulas the deformation kernels implement: Jacobian by tangent rows, warped
+    lookup with its cell Hessian, the four-row backward of the warp network) against autograd through
+    oracle/voxurf_cpu's deform branch, on the reference-pinned fixture's network (tests/golden/voxurf_deform.npz)."""
+    import os
+    import numpy as np
+    import torch
+    from oracle import deform_analytic as da
+    from oracle import voxurf_cpu
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "voxurf_deform.npz"))
+    torch.manual_seed(5)
+    ws = [torch.from_numpy(g["ww%d" % i]).clone().requires_grad_(True) for i in range(5)]
+    bs = [torch.from_numpy(g["wb%d" % i]).clone().requires_grad_(True) for i in range(5)]
+    R = float(g["out_range"])
+    grid = voxurf_cpu.softplus10(10.0) * (torch.sigmoid(voxurf_cpu.softplus10(0.35) * torch.from_numpy(g["sdf"])) - 0.5)
+    mn, mx = torch.tensor([-1.0, -1, -1]), torch.tensor([1.0, 1, 1])
+    M = 700
+    pts = (torch.rand(M, 3) * 1.9 - 0.95).requires_grad_(True)
+    # autograd side: the oracle's ops
+    deform, corr = voxurf_cpu.warp_mlp(pts, ws, bs, R)
+    new = deform + pts
+    ones = torch.ones(M)
+    grad_deform = torch.stack([torch.autograd.grad(new[:, k], [pts], grad_outputs=ones, create_graph=True)[0]
+                               for k in range(3)], dim=2)
+    sdf = voxurf_cpu.grid_sample_custom(new, grid, mn, mx)[:, 0] + corr.squeeze(-1)
+    sdf_deform = sdf - voxurf_cpu.grid_sample_custom(pts, grid, mn, mx)[:, 0]
+    gradient = torch.autograd.grad(sdf, [pts], grad_outputs=torch.ones_like(sdf), create_graph=True)[0]
+    a, B = torch.randn(M), torch.randn(M, 3)                       # stand-ins for the render loss's dL/dsdf, dL/dgradient
+    reg = voxurf_cpu.deform_implicit_loss({"gradient": gradient, "grad_deform": grad_deform, "sdf_correct": corr,
+                                           "sdf_deform": sdf_deform})
+    w = (1.0, 0.05, 0.07, 0.09)
+    loss = (sdf * a).sum() + (gradient * B).sum() + w[0] * reg["grad_constraint"] + w[1] * reg["grad_deform_constraint"] \
+        + w[2] * reg["sdf_correct_constraint"] + w[3] * reg["sdf_deform_constraint"]
+    want = torch.autograd.grad(loss, ws + bs + [pts])
+    # closed form
+    with torch.no_grad():
+        wd, bd, x = [t.detach() for t in ws], [t.detach() for t in bs], pts.detach()
+        y, Jt, acts = da.warp_rows_forward(x, wd, bd)
+        s2, g2, A, sd2, c2, cache = da.lookup_forward(grid, x, y, Jt, R, mn, mx)
+        torch.testing.assert_close(s2, sdf.detach(), rtol=0, atol=2e-6)
+        torch.testing.assert_close(g2, gradient.detach(), rtol=1e-5, atol=1e-5)
+        torch.testing.assert_close(A, grad_deform.detach(), rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(sd2, sdf_deform.detach(), rtol=0, atol=2e-6)
+        val, G_g, G_A, G_c, G_d = da.regulariser_grads(g2, A, c2, sd2, *w)
+        G_y, G_Jt, G_x = da.lookup_backward(cache, a, B + G_g, G_A, G_c, G_d)
+        gw, gb, dx = da.warp_rows_backward(wd, acts, G_y, G_Jt)
+
+    def rel(p, q):
+        return float((p - q).norm() / (q.norm() + 1e-12))
+
+    for i in range(5):
+        assert rel(gw[i], want[i]) < 1e-4, ("dW", i, rel(gw[i], want[i]))
+        assert rel(gb[i], want[5 + i]) < 1e-4, ("db", i, rel(gb[i], want[5 + i]))
+    assert rel(G_x + dx, want[10]) < 1e-4, rel(G_x + dx, want[10])
