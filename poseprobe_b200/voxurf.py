@@ -473,12 +473,14 @@ class _VoxurfRenderFn(torch.autograd.Function):
 
 
 class Voxurf(torch.nn.Module):
-    """Surface-stage ``Voxurf`` (lib/voxurf_coarse.py:44-1091) on the fused kernels, non-deform branch.
+    """Surface-stage ``Voxurf`` (lib/voxurf_coarse.py:44-1215) on the fused kernels: the non-deform branch with
+    autograd, the implicit-deformation branch forward only.
 
     Same parameter names as the reference (``sdf.grid`` [1,1,X,Y,Z], ``k0.grid`` [1,12,X,Y,Z], ``rgbnet.*``,
     ``sdf_alpha``, ``sdf_beta``, ``s_val``), so ``last_ckpt.tar`` state dicts load with ``strict=False``, and the same
     ``forward(rays_o, rays_d, viewdirs, global_step=None, **render_kwargs)`` returning the per-ray entries of the
-    reference's result dict (``rgb_marched``, ``alphainv_cum``, ``cum_weights``, ``s_val``).  The loss stays in the
+    reference's result dict (``rgb_marched``, ``alphainv_cum``, ``cum_weights``, ``s_val``); ``inference`` renders
+    through the deformation network (``warp_network.*``, reference keys).  The loss stays in the
     caller's Python (lib/losses.py); autograd reaches every parameter through two fused kernels per direction plus
     the tcgen05 rgbnet.  Per-sample entries of the reference's dict (``weights``, ``raw_alpha``, ``gradient`` ...) are
     not materialised."""
@@ -531,7 +533,18 @@ class Voxurf(torch.nn.Module):
             self._eng_key = key
         return self._eng, ws, bs
 
-    def forward(self, rays_o, rays_d, viewdirs, global_step=None, **render_kwargs):
+    def forward(self, rays_o, rays_d, viewdirs, use_deform=True, global_step=None, **render_kwargs):
+        """Same signature and default as the reference (lib/voxurf_coarse.py:922).  use_deform=False: the plain SDF
+        lookup, differentiable (fused kernels + autograd).  use_deform=True: the implicit-deformation lookup; its
+        render path exists (forward only, = `inference`), training through the deformation network does not yet, so
+        a call that needs gradients fails loudly instead of silently switching branch."""
+        if use_deform:
+            if torch.is_grad_enabled():
+                raise NotImplementedError(
+                    "Voxurf.forward(use_deform=True) with autograd: the backward through the deformation network is "
+                    "not implemented (DESIGN.md section 9); pass use_deform=False, or call under torch.no_grad() / "
+                    "inference() to render through the deformation")
+            return self.inference(rays_o, rays_d, viewdirs, global_step=global_step, **render_kwargs)
         eng, ws, bs = self._engine(render_kwargs)
         if global_step is not None:                      # neus_alpha_from_sdf_scatter, :485-488, and the BARF progress
             s_val = 1.0 / (global_step + self.s_ratio / self.s_start - self.step_start) * self.s_ratio
@@ -548,30 +561,26 @@ class Voxurf(torch.nn.Module):
         return {"alphainv_cum": last, "cum_weights": cumw[:, None], "rgb_marched": rgb_marched,
                 "s_val": float(self.s_val)}
 
+    def _rgbnet_params(self):
+        from .ops import rgbnet_from_sequential
+        ws, bs = rgbnet_from_sequential(self.rgbnet)
+        return [w.detach() for w in ws], [b.detach() for b in bs]
 
-def _voxurf_inference(self, rays_o, rays_d, viewdirs, global_step=None, **render_kwargs):
-    """Voxurf.inference (lib/voxurf_coarse.py:1093-1215): render with the implicit deformation - SDF and normal of
-    every in-box sample from the warped template lookup - forward only.  Returns the per-ray entries that
-    lib/nvs_fun.py:74-88 reads: rgb_marched, alphainv_cum, cum_weights, depth, disp, normal_marched."""
-    eng, _, _ = self._engine(render_kwargs)
-    ws, bs = self.warp_network.parameters_for_kernel()
-    eng.load_params(self.sdf.grid, self.k0.grid, *self._rgbnet_params(), float(self.sdf_alpha), float(self.sdf_beta))
-    eng.set_warp_network([w.detach() for w in ws], [b.detach() for b in bs], self.warp_network.output_range)
-    eng.set_schedule(s_val=float(self.s_val), progress=1.0 if global_step is None else global_step / self.N_iters)
-    rgb, last, cumw, depth, normal = eng.render(rays_o, rays_d, viewdirs, want_depth=True, want_normal=True,
-                                                use_deform=True)
-    return {"rgb_marched": rgb, "alphainv_cum": last, "cum_weights": cumw[:, None], "depth": depth,
-            "disp": 1 / depth, "normal_marched": normal, "s_val": float(self.s_val)}
-
-
-def _rgbnet_params(self):
-    from .ops import rgbnet_from_sequential
-    ws, bs = rgbnet_from_sequential(self.rgbnet)
-    return [w.detach() for w in ws], [b.detach() for b in bs]
-
-
-Voxurf.inference = torch.no_grad()(_voxurf_inference)
-Voxurf._rgbnet_params = _rgbnet_params
+    @torch.no_grad()
+    def inference(self, rays_o, rays_d, viewdirs, global_step=None, **render_kwargs):
+        """Voxurf.inference (lib/voxurf_coarse.py:1093-1215): render with the implicit deformation - SDF and normal
+        of every in-box sample from the warped template lookup - forward only.  Returns the per-ray entries that
+        lib/nvs_fun.py:74-88 reads: rgb_marched, alphainv_cum, cum_weights, depth, disp, normal_marched."""
+        eng, _, _ = self._engine(render_kwargs)
+        ws, bs = self.warp_network.parameters_for_kernel()
+        eng.load_params(self.sdf.grid, self.k0.grid, *self._rgbnet_params(), float(self.sdf_alpha),
+                        float(self.sdf_beta))
+        eng.set_warp_network([w.detach() for w in ws], [b.detach() for b in bs], self.warp_network.output_range)
+        eng.set_schedule(s_val=float(self.s_val), progress=1.0 if global_step is None else global_step / self.N_iters)
+        rgb, last, cumw, depth, normal = eng.render(rays_o, rays_d, viewdirs, want_depth=True, want_normal=True,
+                                                    use_deform=True)
+        return {"rgb_marched": rgb, "alphainv_cum": last, "cum_weights": cumw[:, None], "depth": depth,
+                "disp": 1 / depth, "normal_marched": normal, "s_val": float(self.s_val)}
 
 
 def smoke(dev):

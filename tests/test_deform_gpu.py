@@ -201,6 +201,10 @@ def test_voxurf_module_inference(cuda):
         m.sdf_beta.fill_(kw["sdf_beta"])
         m.s_val.fill_(kw["s_val"])
     out = m.inference(o.to(cuda), d.to(cuda), v.to(cuda), near=0.2, far=1e9, stepsize=0.5, bg=kw["bg"])
+    with torch.no_grad():       # forward() defaults to the deformation branch like the reference (:922)
+        out2 = m(o.to(cuda), d.to(cuda), v.to(cuda), near=0.2, far=1e9, stepsize=0.5, bg=kw["bg"])
+    # (same kernels; the colour sums are float atomics, so equal up to summation order)
+    torch.testing.assert_close(out2["rgb_marched"], out["rgb_marched"], rtol=0, atol=1e-5)
     R = m.warp_network.output_range
     assert R == 2.0
     want = voxurf_cpu.forward(sdf, k0, net, o, d, v, MN, MX, 0.5, float(m.voxel_size), kw["s_val"], bg=kw["bg"],

@@ -412,7 +412,9 @@ def test_voxurf_module_autograd_vs_oracle(cuda):
         return torch.nn.functional.mse_loss(out["rgb_marched"], tgt) \
             + 0.01 * (-(last * last.log() + (1 - last) * (1 - last).log())).mean() + 0.05 * out["cum_weights"].mean()
 
-    out = mod(o.to(cuda), d.to(cuda), v.to(cuda), global_step=None, **rk)
+    with pytest.raises(NotImplementedError, match="use_deform=False"):      # the reference's default branch needs the
+        mod(o.to(cuda), d.to(cuda), v.to(cuda), global_step=None, **rk)     # deformation backward: loud, not silent
+    out = mod(o.to(cuda), d.to(cuda), v.to(cuda), use_deform=False, global_step=None, **rk)
     loss = loss_of(out, target.to(cuda))
     loss.backward()
     # oracle with differentiable mapping parameters
