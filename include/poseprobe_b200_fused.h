@@ -203,14 +203,15 @@ PP_API int pp_voxurf_march_features(const pp_dvgo_scene* scene, const pp_voxurf_
  * pp_voxurf_deform_rows: one run of slots per ray for ALL its in-box samples (the reference's compacted ray_pts
  * order) and the warp network's input rows: rows fp16 [4 * sample_capacity, 16]; warp_ray_off [N] (first slot of
  * the ray, -1 if it did not fit); counter: 4 x int32 on the device: [0] samples, [1] overflow flag, [2] rows = 4 *
- * samples (pass &counter[2] to pp_warpnet_forward_packed as its device row count).
+ * samples (pass &counter[2] to pp_warpnet_forward_packed as its device row count); sample_pts (nullable): float4
+ * [sample_capacity] = the sample positions, kept for pp_voxurf_deform_sample_backward.
  * pp_voxurf_march_features_deform: pp_voxurf_march_features with the SDF value / normal of every sample taken from
  * the warped lookup: warp_out = the network's fp32 [rows,4] output.  The template SDF is read with the arithmetic of
  * the reference's custom sampler (weights from the unclamped floor, clamped corner indices, :545-659) and its
  * analytic gradient is chained through the warp Jacobian - the closed form of the reference's autograd.grad. */
 PP_API int pp_voxurf_deform_rows(const pp_dvgo_scene* scene, const float* rays_o, const float* rays_d,
                                  const float* jitter, int64_t n_rays, int32_t sample_capacity, void* rows,
-                                 int32_t* warp_ray_off, int32_t* counter, pp_stream_t stream);
+                                 int32_t* warp_ray_off, int32_t* counter, void* sample_pts, pp_stream_t stream);
 PP_API int pp_voxurf_march_features_deform(const pp_dvgo_scene* scene, const pp_voxurf_cfg* cfg,
                                            const void* sdf_records, const void* k0_records, const float* rays_o,
                                            const float* rays_d, const float* viewdirs, const float* jitter,
@@ -220,6 +221,34 @@ PP_API int pp_voxurf_march_features_deform(const pp_dvgo_scene* scene, const pp_
                                            int32_t* counter, float* depth, float* normal_marched,
                                            const float* warp_out, const int32_t* warp_ray_off, float out_range,
                                            pp_stream_t stream);
+
+/* ---- implicit deformation, backward pieces (training through forward(use_deform=True), :958-985) ----------------
+ * The SDF grid is frozen in this mode (voxurf_coarse.py:136-138); gradients flow to the deformation network, the
+ * feature grid, the rgbnet (and the rays).  After pp_voxurf_march_features_deform + rgbnet forward / loss / backward:
+ * pp_voxurf_backward_deform = pp_voxurf_backward with the per-sample {d loss / d sdf_final, d loss / d gradient}
+ * written to grad_val (float4 [sample_capacity], indexed like warp_out / 16; zero-fill it first: samples past early
+ * termination keep zero) instead of a scatter into the SDF records; the feature-grid scatter is unchanged.
+ * pp_voxurf_deform_sample_backward: per in-box sample, chains grad_val through the warped lookup (cell gradient and
+ * off-diagonal Hessian of the custom sampler) and the warp Jacobian, adds the regularisers of deform_implicit_loss
+ * (lib/losses.py:6-24; w_* = their weights, each term a mean over all in-box samples; reg_terms (nullable, 4 floats,
+ * accumulated): the unweighted term values) and writes grad_warp_out fp32 [4 * samples, 4] = the gradient w.r.t.
+ * pp_warpnet_forward_packed's output in the same four-row layout (the grad_out of the network's backward);
+ * grad_pts (nullable) [samples,3]: d loss / d x through x' and sdf(x).  Formulas: oracle/deform_analytic.py.
+ * NOT yet available: the backward of the warp network itself. */
+PP_API int pp_voxurf_backward_deform(const pp_dvgo_scene* scene, const pp_voxurf_cfg* cfg, const float* rays_o,
+                                     const float* rays_d, const float* viewdirs, const float* jitter,
+                                     int64_t n_rays, const void* sample_rec, const float* grad_weight,
+                                     const float* grad_feat, int32_t grad_feat_cols, const int32_t* ray_off,
+                                     const int32_t* ray_cnt, const int32_t* ray_end, const float* g_ray,
+                                     void* grad_k0_records, const float* grad_cum_weights,
+                                     const float* grad_alphainv_last, void* grad_val,
+                                     const int32_t* warp_ray_off, pp_stream_t stream);
+PP_API int pp_voxurf_deform_sample_backward(const pp_dvgo_scene* scene, const void* sdf_records,
+                                            const void* sample_pts, const float* warp_out, const void* grad_val,
+                                            const int32_t* n_samples_ptr, int64_t sample_capacity, float out_range,
+                                            float w_eikonal, float w_jacobian, float w_correction, float w_deform,
+                                            float* grad_warp_out, float* grad_pts, float* reg_terms,
+                                            pp_stream_t stream);
 
 /* rgb_marched = clamp(rgb_acc + (1 - cum_w) bg, 0, 1) (:1040-1042); photometric MSE (lib/losses.py:26-29):
  * g_ray [N,3] = d (w_rgb * mse) / d rgb_acc, loss_out[0] += w_rgb * mse, loss_out[1] += mse. */

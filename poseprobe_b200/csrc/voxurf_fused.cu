@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256)
 voxurf_deform_rows_kernel(pp_dvgo_scene sc, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                           const float* __restrict__ jitter, int64_t n_rays, int32_t cap_samples,
                           uint4* __restrict__ rows, int32_t* __restrict__ dray_off, int32_t* __restrict__ counter,
-                          unsigned int* __restrict__ queue, int cap) {
+                          unsigned int* __restrict__ queue, int cap, float4* __restrict__ pts_out) {
   const int lane = threadIdx.x & 31;
   for (;;) {
     unsigned int ticket = 0;
@@ -234,6 +234,7 @@ voxurf_deform_rows_kernel(pp_dvgo_scene sc, const float* __restrict__ rays_o, co
       dst[5] = zero;
       dst[6] = make_uint4(0u, 0x00003C00u, 0u, 0u);   // e_2
       dst[7] = zero;
+      if (pts_out) pts_out[slot] = make_float4(p[0], p[1], p[2], 0.f);
     }
   }
 }
@@ -483,6 +484,127 @@ __global__ void voxurf_ray_loss_kernel(int64_t n_rays, const float* __restrict__
   }
 }
 
+// ---- implicit deformation: per-sample backward of the warped lookup --------------------------------------------
+// One thread per in-box sample.  Inputs: the sample position, the 16 network outputs D (net(x) and d net / d x_k),
+// G = {d loss / d sdf_final, d loss / d gradient} from the reverse march (zero for samples past early termination).
+// Adds the regularisers of deform_implicit_loss (lib/losses.py:6-24: Eikonal |‖gradient‖ - 1|, ‖d x'/d x_i‖, |correction|,
+// |sdf_final - sdf(x)|, each a mean over ALL in-box samples) and writes the gradient with respect to the 16 network
+// outputs in the same four-row layout (row 0: d/d net(x), row 1+i: d/d (d net / d x_i)) - the grad_out of the warp
+// network's backward - and optionally d loss / d x through x' and the unwarped lookup (the value row's input gradient
+// of the network backward adds to it).  Formulas: oracle/deform_analytic.py (checked against autograd).
+__global__ void __launch_bounds__(256)
+voxurf_deform_sample_backward_kernel(pp_dvgo_scene sc, const float4* __restrict__ srec, const float4* __restrict__ pts,
+                                     const float* __restrict__ dout, const float4* __restrict__ g_val,
+                                     const int32_t* __restrict__ n_ptr, int64_t cap, float R, float w_eik, float w_jac,
+                                     float w_corr, float w_def, float* __restrict__ g_dout, float* __restrict__ g_pts,
+                                     float* __restrict__ reg_out) {
+  const int64_t M = min64(cap, static_cast<int64_t>(*n_ptr));
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  float t_eik = 0.f, t_jac = 0.f, t_corr = 0.f, t_def = 0.f;
+  if (i < M) {
+    const float inv_m = 1.f / static_cast<float>(M);
+    const float4 pp4 = pts[i];
+    const float p[3] = {pp4.x, pp4.y, pp4.z};
+    const float4* D = reinterpret_cast<const float4*>(dout + i * 16);
+    const float4 o = __ldg(D);
+    const float4 jr[3] = {__ldg(D + 1), __ldg(D + 2), __ldg(D + 3)};
+    const float4 G = g_val[i];
+    const float scale[3] = {static_cast<float>(sc.sx - 1) / (sc.xyz_max[0] - sc.xyz_min[0]),
+                            static_cast<float>(sc.sy - 1) / (sc.xyz_max[1] - sc.xyz_min[1]),
+                            static_cast<float>(sc.sz - 1) / (sc.xyz_max[2] - sc.xyz_min[2])};
+    // warped cell: value, world gradient, off-diagonal world Hessian
+    const Cell c = make_cell_free(sc, fma_rn(R, o.x, p[0]), fma_rn(R, o.y, p[1]), fma_rn(R, o.z, p[2]));
+    float u[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) u[q] = __ldg(&srec[corner_off(c, q)].x);
+    const float fx = c.fx, fy = c.fy, fz = c.fz, gx = c.gx(), gy = c.gy(), gz = c.gz();
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s = fma_rn(u[q], corner_w(c, q), s);
+    const float g[3] = {
+        (((u[4] - u[0]) * gz + (u[5] - u[1]) * fz) * gy + ((u[6] - u[2]) * gz + (u[7] - u[3]) * fz) * fy) * scale[0],
+        (((u[2] - u[0]) * gz + (u[3] - u[1]) * fz) * gx + ((u[6] - u[4]) * gz + (u[7] - u[5]) * fz) * fx) * scale[1],
+        (((u[1] - u[0]) * gy + (u[3] - u[2]) * fy) * gx + ((u[5] - u[4]) * gy + (u[7] - u[6]) * fy) * fx) * scale[2]};
+    const float hxy = (((u[6] - u[4]) - (u[2] - u[0])) * gz + ((u[7] - u[5]) - (u[3] - u[1])) * fz) * scale[0] * scale[1];
+    const float hxz = (((u[5] - u[4]) - (u[1] - u[0])) * gy + ((u[7] - u[6]) - (u[3] - u[2])) * fy) * scale[0] * scale[2];
+    const float hyz = (((u[3] - u[2]) - (u[1] - u[0])) * gx + ((u[7] - u[6]) - (u[5] - u[4])) * fx) * scale[1] * scale[2];
+    // unwarped lookup (sdf_deform = sdf_final - sdf(x), voxurf_coarse.py:978)
+    const Cell c0 = make_cell_free(sc, p[0], p[1], p[2]);
+    float u0[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) u0[q] = __ldg(&srec[corner_off(c0, q)].x);
+    float s0 = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s0 = fma_rn(u0[q], corner_w(c0, q), s0);
+    // A[i][k] = d x'_k / d x_i, gradient_i = sum_k A[i][k] g_k + R dc/dx_i
+    float A[3][3], grad[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      A[a][0] = R * jr[a].x + (a == 0 ? 1.f : 0.f);
+      A[a][1] = R * jr[a].y + (a == 1 ? 1.f : 0.f);
+      A[a][2] = R * jr[a].z + (a == 2 ? 1.f : 0.f);
+      grad[a] = A[a][0] * g[0] + A[a][1] * g[1] + A[a][2] * g[2] + R * jr[a].w;
+    }
+    const float corr = R * o.w;
+    const float sdf_final = s + corr;
+    const float sd = sdf_final - s0;
+    // regularisers
+    float Gg[3] = {G.y, G.z, G.w};
+    const float gn = sqrtf(grad[0] * grad[0] + grad[1] * grad[1] + grad[2] * grad[2]);
+    t_eik = fabsf(gn - 1.f) * inv_m;
+    const float sg = (gn > 1.f ? 1.f : (gn < 1.f ? -1.f : 0.f)) * w_eik * inv_m / fmaxf(gn, 1e-30f);
+    float GA[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      Gg[a] += sg * grad[a];
+      const float an = sqrtf(A[a][0] * A[a][0] + A[a][1] * A[a][1] + A[a][2] * A[a][2]);
+      t_jac += an * inv_m * (1.f / 3.f);
+      const float k = w_jac * inv_m * (1.f / 3.f) / fmaxf(an, 1e-30f);
+#pragma unroll
+      for (int b = 0; b < 3; ++b) GA[a][b] = k * A[a][b];
+    }
+    t_corr = fabsf(corr) * inv_m;
+    t_def = fabsf(sd) * inv_m;
+    const float G_corr = w_corr * inv_m * (corr > 0.f ? 1.f : (corr < 0.f ? -1.f : 0.f));
+    const float G_sd = w_def * inv_m * (sd > 0.f ? 1.f : (sd < 0.f ? -1.f : 0.f));
+    const float Gs = G.x + G_sd;
+    // h = dL/dg, G_new = dL/dx'
+    float h[3], Gn[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) h[k] = A[0][k] * Gg[0] + A[1][k] * Gg[1] + A[2][k] * Gg[2];
+    Gn[0] = Gs * g[0] + hxy * h[1] + hxz * h[2];
+    Gn[1] = Gs * g[1] + hxy * h[0] + hyz * h[2];
+    Gn[2] = Gs * g[2] + hxz * h[0] + hyz * h[1];
+    float4* out = reinterpret_cast<float4*>(g_dout + i * 16);
+    out[0] = make_float4(R * Gn[0], R * Gn[1], R * Gn[2], R * (Gs + G_corr));
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+      out[1 + a] = make_float4(R * (Gg[a] * g[0] + GA[a][0]), R * (Gg[a] * g[1] + GA[a][1]),
+                               R * (Gg[a] * g[2] + GA[a][2]), R * Gg[a]);
+    if (g_pts) {
+      const float f0x = c0.fx, f0y = c0.fy, f0z = c0.fz, g0x = c0.gx(), g0y = c0.gy(), g0z = c0.gz();
+      const float g0[3] = {
+          (((u0[4] - u0[0]) * g0z + (u0[5] - u0[1]) * f0z) * g0y + ((u0[6] - u0[2]) * g0z + (u0[7] - u0[3]) * f0z) * f0y) * scale[0],
+          (((u0[2] - u0[0]) * g0z + (u0[3] - u0[1]) * f0z) * g0x + ((u0[6] - u0[4]) * g0z + (u0[7] - u0[5]) * f0z) * f0x) * scale[1],
+          (((u0[1] - u0[0]) * g0y + (u0[3] - u0[2]) * f0y) * g0x + ((u0[5] - u0[4]) * g0y + (u0[7] - u0[6]) * f0y) * f0x) * scale[2]};
+#pragma unroll
+      for (int k = 0; k < 3; ++k) g_pts[3 * i + k] = Gn[k] - G_sd * g0[k];
+    }
+  }
+  if (reg_out) {
+    t_eik = warp_sum(t_eik);
+    t_jac = warp_sum(t_jac);
+    t_corr = warp_sum(t_corr);
+    t_def = warp_sum(t_def);
+    if ((threadIdx.x & 31) == 0 && (t_eik != 0.f || t_jac != 0.f || t_corr != 0.f || t_def != 0.f)) {
+      atomicAdd(reg_out, t_eik);
+      atomicAdd(reg_out + 1, t_jac);
+      atomicAdd(reg_out + 2, t_corr);
+      atomicAdd(reg_out + 3, t_def);
+    }
+  }
+}
+
 // ---- backward march -----------------------------------------------------------------------------------------
 // dynamic shared memory per warp: s_alpha[cap], s_slot[cap] (compacted slot of every step, -1 if none),
 // s_tin[cap/32]
@@ -516,7 +638,11 @@ voxurf_backward_kernel(pp_dvgo_scene sc, pp_voxurf_cfg cfg, const float* __restr
                        float4* __restrict__ g_srec, float4* __restrict__ g_k0rec, unsigned int* __restrict__ queue,
                        int cap, int dx_pitch, const float4* __restrict__ srec, const float4* __restrict__ k0rec,
                        float* __restrict__ grad_rays, float* __restrict__ grad_viewdirs,
-                       const float* __restrict__ g_cumw, const float* __restrict__ g_last) {
+                       const float* __restrict__ g_cumw, const float* __restrict__ g_last,
+                       float4* __restrict__ g_val, const int32_t* __restrict__ dray_off) {
+  // g_val != null (implicit deformation): the records of the forward hold {sdf_final, d sdf_final / d x} of the warped
+  // lookup; their gradients {d loss / d sdf, d loss / d gradient} go to g_val[sample] (input of the deformation
+  // backward, voxurf_deform_sample_backward_kernel) and nothing is scattered into the frozen SDF grid.
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int per_warp = 2 * cap + cap / kWarp;
@@ -630,6 +756,7 @@ voxurf_backward_kernel(pp_dvgo_scene sc, pp_voxurf_cfg cfg, const float* __restr
         ds.w = g_tc * v[2] + d3.z * inv - gg[2] * kk;
         vox_point(sc, ray, i, jit, p);
         c = make_cell(sc, p[0], p[1], p[2]);
+        if (g_val) g_val[dray_off[r] + (slot - off)] = ds;
       }
       // scatter.  Neighbouring lanes are neighbouring steps (half a voxel apart) and often sit in the same cell:
       // such pairs are merged with shuffles so that the pair issues 32 reductions instead of 64 (the kernel is
@@ -655,7 +782,7 @@ voxurf_backward_kernel(pp_dvgo_scene sc, pp_voxurf_cfg cfg, const float* __restr
         }
         if (live && !absorbed && (wq != 0.f || (absorb && wq_up != 0.f))) {
           const int64_t co = corner_off(c, q);
-          red_add_v4(g_srec + co, a[0], a[1], a[2], a[3]);
+          if (!g_val) red_add_v4(g_srec + co, a[0], a[1], a[2], a[3]);
           float4* kdst = g_k0rec + co * 3;
           red_add_v4(kdst, a[4], a[5], a[6], a[7]);
           red_add_v4(kdst + 1, a[8], a[9], a[10], a[11]);
@@ -667,7 +794,7 @@ voxurf_backward_kernel(pp_dvgo_scene sc, pp_voxurf_cfg cfg, const float* __restr
         // d loss / d point: through the SDF record interpolation, the 12 feature channels, the positional
         // encoding columns of the MLP input; d loss / d viewdirs: NeuS cosine and the view columns
         float gp[3] = {0.f, 0.f, 0.f};
-        {
+        if (!g_val) {   // (deformation: the point gradient through the SDF comes from the deformation backward)
           float4 q8[8];
           gather8(srec, c, q8);
           spatial_grad4(c, q8, ds, gp);
@@ -956,7 +1083,8 @@ extern "C" int pp_voxurf_march_features_deform(const pp_dvgo_scene* scene, const
 
 extern "C" int pp_voxurf_deform_rows(const pp_dvgo_scene* scene, const float* rays_o, const float* rays_d,
                                      const float* jitter, int64_t n_rays, int32_t sample_capacity, void* rows,
-                                     int32_t* warp_ray_off, int32_t* counter, pp_stream_t stream) {
+                                     int32_t* warp_ray_off, int32_t* counter, void* sample_pts,
+                                     pp_stream_t stream) {
   PP_REQUIRE(scene, PP_ERR_INVALID_ARG, "voxurf_deform_rows: null scene");
   PP_REQUIRE(n_rays >= 0 && sample_capacity >= 0, PP_ERR_INVALID_ARG, "voxurf_deform_rows: negative extent");
   if (n_rays == 0) return PP_OK;
@@ -970,7 +1098,7 @@ extern "C" int pp_voxurf_deform_rows(const pp_dvgo_scene* scene, const float* ra
   const int64_t blocks = min64((n_rays + 7) / 8, (int64_t)sm_count() * 8);
   voxurf_deform_rows_kernel<<<(unsigned)blocks, 256, 0, s>>>(*scene, rays_o, rays_d, jitter, n_rays, sample_capacity,
                                                              (uint4*)rows, warp_ray_off, counter, queue,
-                                                             vox_step_capacity(scene));
+                                                             vox_step_capacity(scene), (float4*)sample_pts);
   PP_CHECK_LAUNCH("voxurf_deform_rows");
   return PP_OK;
 }
@@ -987,22 +1115,25 @@ extern "C" int pp_voxurf_ray_loss(int64_t n_rays, const float* rgb_acc, const fl
   return PP_OK;
 }
 
-extern "C" int pp_voxurf_backward(const pp_dvgo_scene* scene, const pp_voxurf_cfg* cfg, const float* rays_o,
-                                  const float* rays_d, const float* viewdirs, const float* jitter, int64_t n_rays,
-                                  const void* sample_rec, const float* grad_weight, const float* grad_feat,
-                                  int32_t grad_feat_cols, const int32_t* ray_off, const int32_t* ray_cnt,
-                                  const int32_t* ray_end, const float* g_ray, void* grad_sdf_records,
-                                  void* grad_k0_records, const void* sdf_records, const void* k0_records,
-                                  float* grad_rays, float* grad_viewdirs, const float* grad_cum_weights,
-                                  const float* grad_alphainv_last, pp_stream_t stream) {
+static int launch_vox_backward(const pp_dvgo_scene* scene, const pp_voxurf_cfg* cfg, const float* rays_o,
+                               const float* rays_d, const float* viewdirs, const float* jitter, int64_t n_rays,
+                               const void* sample_rec, const float* grad_weight, const float* grad_feat,
+                               int32_t grad_feat_cols, const int32_t* ray_off, const int32_t* ray_cnt,
+                               const int32_t* ray_end, const float* g_ray, void* grad_sdf_records,
+                               void* grad_k0_records, const void* sdf_records, const void* k0_records,
+                               float* grad_rays, float* grad_viewdirs, const float* grad_cum_weights,
+                               const float* grad_alphainv_last, void* grad_val, const int32_t* warp_ray_off,
+                               pp_stream_t stream) {
   const float* grad_feat16 = grad_feat;
   const int rc = check_vox_scene(scene, cfg, "voxurf_backward");
   if (rc != PP_OK) return rc;
   PP_REQUIRE(n_rays >= 0, PP_ERR_INVALID_ARG, "voxurf_backward: n_rays < 0");
   if (n_rays == 0) return PP_OK;
   PP_REQUIRE(rays_o && rays_d && viewdirs && sample_rec && grad_weight && grad_feat16 && ray_off && ray_cnt &&
-                 ray_end && g_ray && grad_sdf_records && grad_k0_records,
+                 ray_end && g_ray && (grad_sdf_records || grad_val) && grad_k0_records,
              PP_ERR_INVALID_ARG, "voxurf_backward: null pointer");
+  PP_REQUIRE((grad_val == nullptr) == (warp_ray_off == nullptr), PP_ERR_INVALID_ARG,
+             "voxurf_backward: grad_val and warp_ray_off go together");
   const bool pose = grad_rays != nullptr;
   PP_REQUIRE(grad_feat_cols == kDxCols || grad_feat_cols == kFeatCols, PP_ERR_INVALID_ARG,
              "voxurf_backward: grad_feat_cols must be 16 or 64");
@@ -1026,8 +1157,56 @@ extern "C" int pp_voxurf_backward(const pp_dvgo_scene* scene, const pp_voxurf_cf
       *scene, *cfg, rays_o, rays_d, viewdirs, jitter, n_rays, (const float4*)sample_rec, grad_weight, grad_feat16,
       ray_off, ray_cnt, ray_end, g_ray, (float4*)grad_sdf_records, (float4*)grad_k0_records, queue, cap,
       grad_feat_cols, (const float4*)sdf_records, (const float4*)k0_records, grad_rays, grad_viewdirs,
-      grad_cum_weights, grad_alphainv_last);
+      grad_cum_weights, grad_alphainv_last, (float4*)grad_val, warp_ray_off);
   PP_CHECK_LAUNCH("voxurf_backward");
+  return PP_OK;
+}
+
+extern "C" int pp_voxurf_backward(const pp_dvgo_scene* scene, const pp_voxurf_cfg* cfg, const float* rays_o,
+                                  const float* rays_d, const float* viewdirs, const float* jitter, int64_t n_rays,
+                                  const void* sample_rec, const float* grad_weight, const float* grad_feat,
+                                  int32_t grad_feat_cols, const int32_t* ray_off, const int32_t* ray_cnt,
+                                  const int32_t* ray_end, const float* g_ray, void* grad_sdf_records,
+                                  void* grad_k0_records, const void* sdf_records, const void* k0_records,
+                                  float* grad_rays, float* grad_viewdirs, const float* grad_cum_weights,
+                                  const float* grad_alphainv_last, pp_stream_t stream) {
+  PP_REQUIRE(grad_sdf_records, PP_ERR_INVALID_ARG, "voxurf_backward: null pointer");
+  return launch_vox_backward(scene, cfg, rays_o, rays_d, viewdirs, jitter, n_rays, sample_rec, grad_weight, grad_feat,
+                             grad_feat_cols, ray_off, ray_cnt, ray_end, g_ray, grad_sdf_records, grad_k0_records,
+                             sdf_records, k0_records, grad_rays, grad_viewdirs, grad_cum_weights, grad_alphainv_last,
+                             nullptr, nullptr, stream);
+}
+
+extern "C" int pp_voxurf_backward_deform(const pp_dvgo_scene* scene, const pp_voxurf_cfg* cfg, const float* rays_o,
+                                         const float* rays_d, const float* viewdirs, const float* jitter,
+                                         int64_t n_rays, const void* sample_rec, const float* grad_weight,
+                                         const float* grad_feat, int32_t grad_feat_cols, const int32_t* ray_off,
+                                         const int32_t* ray_cnt, const int32_t* ray_end, const float* g_ray,
+                                         void* grad_k0_records, const float* grad_cum_weights,
+                                         const float* grad_alphainv_last, void* grad_val,
+                                         const int32_t* warp_ray_off, pp_stream_t stream) {
+  PP_REQUIRE(grad_val && warp_ray_off, PP_ERR_INVALID_ARG, "voxurf_backward_deform: null pointer");
+  return launch_vox_backward(scene, cfg, rays_o, rays_d, viewdirs, jitter, n_rays, sample_rec, grad_weight, grad_feat,
+                             grad_feat_cols, ray_off, ray_cnt, ray_end, g_ray, nullptr, grad_k0_records, nullptr,
+                             nullptr, nullptr, nullptr, grad_cum_weights, grad_alphainv_last, grad_val, warp_ray_off,
+                             stream);
+}
+
+extern "C" int pp_voxurf_deform_sample_backward(const pp_dvgo_scene* scene, const void* sdf_records,
+                                                const void* sample_pts, const float* warp_out, const void* grad_val,
+                                                const int32_t* n_samples_ptr, int64_t sample_capacity, float out_range,
+                                                float w_eikonal, float w_jacobian, float w_correction,
+                                                float w_deform, float* grad_warp_out, float* grad_pts,
+                                                float* reg_terms, pp_stream_t stream) {
+  PP_REQUIRE(scene, PP_ERR_INVALID_ARG, "voxurf_deform_sample_backward: null scene");
+  PP_REQUIRE(sample_capacity >= 0, PP_ERR_INVALID_ARG, "voxurf_deform_sample_backward: negative extent");
+  if (sample_capacity == 0) return PP_OK;
+  PP_REQUIRE(sdf_records && sample_pts && warp_out && grad_val && n_samples_ptr && grad_warp_out, PP_ERR_INVALID_ARG,
+             "voxurf_deform_sample_backward: null pointer");
+  voxurf_deform_sample_backward_kernel<<<ceil_div(sample_capacity, 256), 256, 0, as_stream(stream)>>>(
+      *scene, (const float4*)sdf_records, (const float4*)sample_pts, warp_out, (const float4*)grad_val, n_samples_ptr,
+      sample_capacity, out_range, w_eikonal, w_jacobian, w_correction, w_deform, grad_warp_out, grad_pts, reg_terms);
+  PP_CHECK_LAUNCH("voxurf_deform_sample_backward");
   return PP_OK;
 }
 

@@ -221,7 +221,7 @@ class FusedVoxurf:
         ws, bs = warpnet_params([w.to(self.device) for w in weights], [b.to(self.device) for b in biases])
         self.warp = (ws, bs, float(out_range))
 
-    def _march_deform(self, b, rays_o, rays_d, viewdirs, jitter, depth=None, normal=None):
+    def _march_deform(self, b, rays_o, rays_d, viewdirs, jitter, depth=None, normal=None, keep_points=False):
         n, cap = rays_o.shape[0], b["cap"]
         if "drows" not in b:
             dev = self.device
@@ -229,10 +229,12 @@ class FusedVoxurf:
             b["dout"] = torch.empty((4 * cap, 4), dtype=torch.float32, device=dev)
             b["dray_off"] = torch.empty(b["n_rays"], dtype=torch.int32, device=dev)
             b["dcounter"] = torch.zeros(4, dtype=torch.int32, device=dev)
+        if keep_points and "dpts" not in b:
+            b["dpts"] = torch.empty((cap, 4), dtype=torch.float32, device=self.device)
         ws, bs, out_range = self.warp
         check(lib.pp_voxurf_deform_rows(ctypes.byref(self.scene), ptr(rays_o), ptr(rays_d), ptr(jitter), n, cap,
-                                        ptr(b["drows"]), ptr(b["dray_off"]), ptr(b["dcounter"]), stream()),
-              "voxurf_deform_rows")
+                                        ptr(b["drows"]), ptr(b["dray_off"]), ptr(b["dcounter"]),
+                                        ptr(b["dpts"]) if keep_points else None, stream()), "voxurf_deform_rows")
         check(lib.pp_warpnet_forward_packed(ptr(b["drows"]), 4 * cap, len(ws), 128, self._arr(ws), self._arr(bs),
                                             ptr(b["dout"]), ptr(b["dcounter"][2:]), stream()), "warpnet_forward")
         check(lib.pp_voxurf_march_features_deform(
@@ -316,6 +318,55 @@ class FusedVoxurf:
                                          ptr(b["g_ray"]), ptr(self.g_srec), ptr(self.g_k0rec), ptr(self.srec),
                                          ptr(self.k0rec), ptr(b["grad_rays"]), ptr(b["grad_view"]), None, None,
                                          stream()), "voxurf_backward")
+        return b["rgb"][:n]
+
+    def backward_deform_pieces(self, rays_o, rays_d, viewdirs, target, jitter=None, reg_weights=(0.0, 0.0, 0.0, 0.0)):
+        """Training through the implicit deformation (forward(use_deform=True), voxurf_coarse.py:958-985), every stage
+        except the backward of the warp network itself: deform march -> rgbnet -> loss -> rgbnet
+        backward (rgbnet / feature-grid gradients accumulate as in `backward_only`) -> reverse march writing
+        {dL/d sdf_final, dL/d gradient} per sample -> per-sample backward of the warped lookup + the regularisers of
+        deform_implicit_loss (reg_weights = weights of grad_constraint, grad_deform_constraint, sdf_correct_constraint,
+        sdf_deform_constraint, lib/losses.py:6-24).  Leaves in the buffers: ``g_dout`` fp32 [4 * samples, 4] = the
+        gradient w.r.t. the warp network's outputs (value row + three tangent rows per sample), ``g_pts`` [samples, 3],
+        ``reg`` (the four unweighted term values)."""
+        if self.warp is None:
+            raise RuntimeError("backward_deform_pieces needs set_warp_network first")
+        for t, nme in ((rays_o, "rays_o"), (rays_d, "rays_d"), (viewdirs, "viewdirs"), (target, "target")):
+            _need_cuda(t, nme)
+        n = rays_o.shape[0]
+        b = self._buffers(n)
+        cap = b["cap"]
+        with torch.cuda.device(self.device):
+            self._march_deform(b, rays_o, rays_d, viewdirs, jitter, keep_points=True)
+            self._mlp_forward(b, n)
+            check(lib.pp_voxurf_ray_loss(n, ptr(b["acc"]), ptr(b["cum_w"]), ptr(target), self.scene.bg, self.w_rgb,
+                                         ptr(b["g_ray"]), ptr(b["rgb"]), ptr(self.loss_buf), stream()),
+                  "voxurf_ray_loss")
+            check(lib.pp_rgbnet_backward_fused(ptr(b["feat"]), cap, ptr(b["counter"]), self.d0, self.depth, 128,
+                                               self._arr(self.weights), self._arr(self.biases), ptr(b["w"]),
+                                               ptr(b["rid"]), ptr(b["g_ray"]), ptr(b["gw"]), ptr(b["dx"]),
+                                               self.dx_cols, self._arr(self.g_w), self._arr(self.g_b), stream()),
+                  "rgbnet_backward_fused")
+            if "g_val" not in b:
+                dev = self.device
+                b["g_val"] = torch.empty((cap, 4), dtype=torch.float32, device=dev)
+                b["g_dout"] = torch.empty((4 * cap, 4), dtype=torch.float32, device=dev)
+                b["g_pts"] = torch.empty((cap, 3), dtype=torch.float32, device=dev)
+                b["reg"] = torch.zeros(4, dtype=torch.float32, device=dev)
+            b["g_val"].zero_()
+            b["reg"].zero_()
+            check(lib.pp_voxurf_backward_deform(ctypes.byref(self.scene), ctypes.byref(self.cfg), ptr(rays_o),
+                                                ptr(rays_d), ptr(viewdirs), ptr(jitter), n, ptr(b["rec"]),
+                                                ptr(b["gw"]), ptr(b["dx"]), self.dx_cols, ptr(b["ray_off"]),
+                                                ptr(b["ray_cnt"]), ptr(b["ray_end"]), ptr(b["g_ray"]),
+                                                ptr(self.g_k0rec), None, None, ptr(b["g_val"]), ptr(b["dray_off"]),
+                                                stream()), "voxurf_backward_deform")
+            w = [float(x) for x in reg_weights]
+            check(lib.pp_voxurf_deform_sample_backward(ctypes.byref(self.scene), ptr(self.srec), ptr(b["dpts"]),
+                                                       ptr(b["dout"]), ptr(b["g_val"]), ptr(b["dcounter"]), cap,
+                                                       self.warp[2], w[0], w[1], w[2], w[3], ptr(b["g_dout"]),
+                                                       ptr(b["g_pts"]), ptr(b["reg"]), stream()),
+                  "voxurf_deform_sample_backward")
         return b["rgb"][:n]
 
     # ---- autograd-facing pieces (used by the Voxurf module below) ---------------------------------------------

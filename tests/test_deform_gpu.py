@@ -267,3 +267,86 @@ def test_render_deform_edge_cases(cuda):
     assert small._bufs["dcounter"].tolist()[1] == 1
     with pytest.raises(RuntimeError, match="capacity"):
         small.n_samples()
+
+
+def test_deform_backward_pieces(cuda):
+    """Training through the deformation, every stage except the warp network's own backward:
+    (a) the reverse march's per-sample {dL/d sdf_final, dL/d gradient} against autograd through the oracle's deform
+        branch (the rgbnet in between runs on bf16 operands: direction / norm);
+    (b) the per-sample backward of the warped lookup + regularisers (voxurf_deform_sample_backward_kernel) against the
+        closed form of oracle/deform_analytic.py evaluated on the kernel's OWN inputs (network outputs, positions,
+        upstream gradients): tight;
+    (c) the four regulariser terms of deform_implicit_loss."""
+    from oracle import deform_analytic as da
+    from oracle import voxurf_cpu
+    from poseprobe_b200 import ops, voxurf
+    G, N, R = 32, 256, 2.0
+    sdf, k0, net, o, d, v, kw = make_scene(G, N, seed=71)
+    target = torch.rand(N, 3)
+    ws, bs = make_warp(72)
+    rw, rb = ops.rgbnet_from_sequential(net)
+    eng = voxurf.FusedVoxurf(sdf.to(cuda), k0.to(cuda), [w.detach() for w in rw], [b.detach() for b in rb], MN, MX, **kw)
+    eng.set_warp_network(ws, bs, R)
+    wreg = (1.0, 0.05, 0.07, 0.09)
+    eng.loss_buf.zero_()
+    eng.backward_deform_pieces(o.to(cuda), d.to(cuda), v.to(cuda), target.to(cuda), reg_weights=wreg)
+    torch.cuda.synchronize()
+    b = eng._bufs
+    M = b["dcounter"].tolist()[0]
+    assert b["dcounter"].tolist()[1] == 0 and M > 5000
+    D = b["dout"][:4 * M].reshape(M, 4, 4).cpu()
+    pts = b["dpts"][:M, :3].cpu()
+    g_val = b["g_val"][:M].cpu()
+    g_dout = b["g_dout"][:4 * M].reshape(M, 4, 4).cpu()
+    g_pts = b["g_pts"][:M].cpu()
+
+    def rel(p, q):
+        return float((p - q).norm() / (q.norm() + 1e-12))
+
+    def cos(p, q):
+        return float((p * q).sum() / (p.norm() * q.norm() + 1e-30))
+
+    # ---- (b) + (c): closed form on the kernel's own inputs
+    grid = voxurf_cpu.softplus10(kw["sdf_alpha"]) * (torch.sigmoid(voxurf_cpu.softplus10(kw["sdf_beta"]) * sdf) - 0.5)
+    y, Jt = D[:, 0, :], D[:, 1:, :]              # raw network outputs (not yet multiplied by the output range)
+    sdf2, grad2, A, sd2, c2, cache = da.lookup_forward(grid, pts, y, Jt, R, MN, MX)
+    _, G_g, G_A, G_c, G_d = da.regulariser_grads(grad2, A, c2, sd2, *wreg)
+    G_y, G_Jt, G_x = da.lookup_backward(cache, g_val[:, 0], g_val[:, 1:] + G_g, G_A, G_c, G_d)
+    want_dout = torch.cat([G_y[:, None, :], G_Jt], 1)
+    assert rel(g_dout, want_dout) < 2e-3, rel(g_dout, want_dout)
+    assert rel(g_dout[:, 0], want_dout[:, 0]) < 2e-3 and rel(g_dout[:, 1:], want_dout[:, 1:]) < 2e-3
+    assert rel(g_pts, G_x) < 2e-3, rel(g_pts, G_x)
+    terms = torch.stack([(grad2.norm(dim=-1) - 1).abs().mean(), A.norm(dim=-1).mean(), c2.abs().mean(), sd2.abs().mean()])
+    torch.testing.assert_close(b["reg"].cpu(), terms, rtol=1e-3, atol=1e-6)
+
+    # ---- (a): upstream gradients against autograd through the oracle
+    want = voxurf_cpu.forward(sdf, k0, net, o, d, v, MN, MX, kw["stepsize"], eng.voxel_size, kw["s_val"], bg=kw["bg"],
+                              sdf_alpha=kw["sdf_alpha"], sdf_beta=kw["sdf_beta"], posbase_pe=5, viewbase_pe=1,
+                              barf_c2f=kw["barf_c2f"], progress=1.0, warp=(ws, bs, R))
+    loss = voxurf_cpu.mse_loss(want, target)
+    assert abs(float(eng.loss_buf[0]) - float(loss.detach())) < 3e-2 * float(loss.detach())
+    Gs_ref, Gg_ref = torch.autograd.grad(loss, [want["sdf"], want["gradient"]])
+    rid = want["ray_id"]
+    assert rid.numel() == M
+    per_ray = torch.zeros(N, dtype=torch.long).index_add_(0, rid, torch.ones_like(rid))
+    starts = torch.cumsum(per_ray, 0) - per_ray
+    doff = b["dray_off"][:N].cpu().long()
+    idx = doff[rid] + (torch.arange(M) - starts[rid])        # kernel slot of every oracle sample
+    assert int(idx.min()) >= 0 and int(idx.max()) < M and idx.unique().numel() == M
+    torch.testing.assert_close(pts[idx], want["pts"].detach(), rtol=0, atol=1e-5)
+    gk = g_val[idx]
+    assert cos(gk[:, 0], Gs_ref) > 0.99 and 0.9 < float(gk[:, 0].norm() / Gs_ref.norm()) < 1.1, (
+        cos(gk[:, 0], Gs_ref), float(gk[:, 0].norm() / Gs_ref.norm()))
+    assert cos(gk[:, 1:], Gg_ref) > 0.99 and 0.9 < float(gk[:, 1:].norm() / Gg_ref.norm()) < 1.1, (
+        cos(gk[:, 1:], Gg_ref), float(gk[:, 1:].norm() / Gg_ref.norm()))
+    # the feature-grid gradient of the deform step (k0 is sampled at the unwarped point, voxurf_coarse.py:1007)
+    k0_r = k0.clone().requires_grad_(True)
+    want2 = voxurf_cpu.forward(sdf, k0_r, net, o, d, v, MN, MX, kw["stepsize"], eng.voxel_size, kw["s_val"],
+                               bg=kw["bg"], sdf_alpha=kw["sdf_alpha"], sdf_beta=kw["sdf_beta"], posbase_pe=5,
+                               viewbase_pe=1, barf_c2f=kw["barf_c2f"], progress=1.0, warp=(ws, bs, R))
+    (g_k0_ref,) = torch.autograd.grad(voxurf_cpu.mse_loss(want2, target), [k0_r])
+    g_k0 = torch.empty((1, 12, G, G, G), device=cuda)
+    from poseprobe_b200._lib import check, lib, ptr, stream
+    with torch.cuda.device(cuda):
+        check(lib.pp_voxurf_k0_unpack(ptr(eng.g_k0rec), eng.n_voxels, ptr(g_k0), stream()), "k0_unpack")
+    assert cos(g_k0.cpu(), g_k0_ref) > 0.99
