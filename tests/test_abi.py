@@ -85,6 +85,16 @@ def test_no_cpu_fallback():
         pp.ub360_utils_cuda.cumdist_thres(torch.rand(2, 2), 0.1)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         pp.ops.segment_sum(torch.rand(4, 3), torch.zeros(4, dtype=torch.int64), 1)
+    dims = [3, 128, 128, 128, 128, 4]
+    ws = [torch.rand(dims[i + 1], dims[i]) for i in range(5)]
+    bs = [torch.rand(dims[i + 1]) for i in range(5)]
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pp.ops.warpnet_forward(torch.rand(8, 3), ws, bs)
+    with pytest.raises(RuntimeError, match="expected layers 3 -> 128"):
+        pp.ops.warpnet_params(ws[1:], bs[1:])
+    from poseprobe_b200.deform import DeformedImplicitField
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        DeformedImplicitField(range_shape=torch.ones(3))(torch.rand(8, 3))
 
 
 def test_product_does_not_import_the_oracle():
@@ -109,3 +119,14 @@ def test_c_abi_argument_validation():
     assert lib.pp_adam_upd(0, 9, None, None, None, None, None, 4, 1, 0.9, 0.99, 0.1, 1e-8, None) == -1
     assert lib.pp_sample_pts_fill(0, None, None, None, None, None, None, 0.1, 4, 2**31, None, None, None, None, None) == -3
     assert lib.pp_check_device_ptr(None) == -1
+    # deformation path: extents and null pointers are rejected before anything is launched
+    assert lib.pp_warpnet_forward_packed(None, 6, 5, 128, None, None, None, None, None) == -1      # rows % 4 != 0
+    assert b"multiple of 4" in lib.pp_last_error()
+    assert lib.pp_warpnet_forward_packed(None, 8, 5, 64, None, None, None, None, None) == -5       # width != 128
+    assert lib.pp_warpnet_forward_packed(None, 8, 6, 128, None, None, None, None, None) == -5      # depth > 5
+    assert lib.pp_warpnet_forward_packed(None, 0, 5, 128, None, None, None, None, None) == 0       # empty: no-op
+    assert lib.pp_warpnet_forward_packed(None, 8, 5, 128, None, None, None, None, None) == -1
+    assert lib.pp_warpnet_pack_points(None, 4, None, None) == -1
+    assert lib.pp_voxurf_deform_rows(None, None, None, None, 4, 4, None, None, None, None, None) == -1
+    assert lib.pp_voxurf_deform_sample_backward(None, None, None, None, None, None, 4, 1.0, 0, 0, 0, 0, None, None,
+                                                None, None) == -1
