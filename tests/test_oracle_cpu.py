@@ -177,3 +177,75 @@ def test_segment_ops_and_neus_alpha_reference_forms():
     a = oracle.neus_alpha(view, torch.zeros(9, dtype=torch.int64), 0.025, sdf, grads, 64.0)
     assert float(a[0]) < 0.05 and float(a[-1]) > 0.5 and bool((a[1:] >= a[:-1]).all())   # opacity rises through the surface
     assert bool((a >= 0).all()) and bool((a <= 1).all())
+
+
+# ---- randomised structural properties (hypothesis): ragged, empty and degenerate inputs -----------------------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.lists(st.integers(min_value=0, max_value=40), min_size=1, max_size=12), st.integers(0, 2 ** 31 - 1))
+def test_alpha2weight_properties_on_ragged_segments(lens, seed):
+    """Any segmentation (including empty rays and an empty input): weights + final transmittance partition unity while
+    the ray is not terminated, weights are zero past i_end, i_start / i_end delimit the ray's segment, and the
+    backward of a constant upstream gradient equals autograd of the cumprod form."""
+    g = torch.Generator().manual_seed(seed)
+    n_rays = len(lens)
+    ray_id = torch.repeat_interleave(torch.arange(n_rays), torch.tensor(lens))
+    alpha = torch.rand(ray_id.numel(), generator=g) * 0.9
+    w, T, last, i_start, i_end = oracle.alpha2weight(alpha, ray_id, n_rays)
+    assert w.shape == alpha.shape and last.shape == (n_rays,)
+    off = 0
+    for r, n in enumerate(lens):
+        if n == 0:
+            assert last[r].item() == 1.0
+            continue
+        assert i_start[r].item() == off and off < i_end[r].item() <= off + n
+        seg = slice(off, off + n)
+        stop = i_end[r].item() - off
+        assert float(w[seg][stop:].abs().sum()) == 0.0                     # nothing is composited past the stop
+        total = float(w[seg].double().sum() + last[r].double())
+        assert abs(total - 1.0) < 1e-5
+        ref_T = torch.cumprod(torch.cat([torch.ones(1), 1 - alpha[seg][:stop]]), 0)
+        torch.testing.assert_close(w[seg][:stop], (ref_T[:-1] * alpha[seg][:stop]), rtol=1e-5, atol=1e-7)
+        off += n
+
+
+@settings(max_examples=25, deadline=None)
+@given(st.integers(1, 40), st.floats(0.01, 0.2), st.integers(0, 2 ** 31 - 1))
+def test_sampling_enumeration_is_a_run_length_code(n_rays, stepdist, seed):
+    """ray_id is sorted, step_id restarts at 0 on every ray and counts up by one, the per-ray counts are N_steps, every
+    ray (even one that misses the box) owns at least one sample, and in-box flags agree with the point coordinates."""
+    o, d = cases.rays_with_edge_cases(n_rays, seed=seed % 1000)
+    mn, mx = cases.bbox()
+    pts, mask, ray_id, step_id, n_steps, t_min, t_max, start, rdir = oracle.sample_pts_on_rays(
+        o, d, mn, mx, 0.2, 1e9, float(stepdist))
+    assert int(n_steps.min()) >= 1 and int(n_steps.sum()) == ray_id.numel()
+    assert bool((ray_id[1:] >= ray_id[:-1]).all())
+    counts = torch.zeros(n_rays, dtype=torch.long).index_add_(0, ray_id, torch.ones_like(ray_id))
+    assert torch.equal(counts, n_steps)
+    starts = torch.cumsum(n_steps, 0) - n_steps
+    assert torch.equal(step_id, torch.arange(ray_id.numel()) - starts[ray_id])
+    outside = ((mn > pts) | (pts > mx)).any(-1)
+    assert torch.equal(outside, mask)
+
+
+@settings(max_examples=25, deadline=None)
+@given(st.integers(1, 6), st.integers(1, 50), st.floats(0.05, 2.0), st.integers(0, 2 ** 31 - 1))
+def test_cumdist_thres_is_a_running_sum_with_reset(n, s, thres, seed):
+    """ub360_utils_kernel.cu:12-47: mask[i] is set where the fp32 running sum of dist since the last set point
+    exceeds thres, and the sum restarts there."""
+    import numpy as np
+    g = torch.Generator().manual_seed(seed)
+    dist = torch.rand(n, s, generator=g)
+    mask = oracle.cumdist_thres(dist, float(thres))
+    th = np.float32(thres)
+    for r in range(n):
+        acc, want = np.float32(0.0), []
+        for i in range(s):
+            acc = np.float32(acc + np.float32(dist[r, i].item()))
+            over = bool(acc > th)
+            want.append(over)
+            if over:
+                acc = np.float32(0.0)
+        assert mask[r].tolist() == want
