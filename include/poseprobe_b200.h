@@ -160,6 +160,8 @@ PP_API int pp_total_variation_add_grad(pp_dtype dtype, const void* param, void* 
  * adam_upd_cuda  (reference: lib/cuda/adam_upd.cpp + adam_upd_kernel.cu), all in place
  * mode 0: adam_upd (:36)   mode 1: masked_adam_upd (:50, skip grad==0)
  * mode 2: adam_upd_with_perlr (:64, needs perlr)
+ * mode 3: the optimiser the reference actually RUNS - the Python Adam of lib/utils.py:176-198 (the kernels above
+ *         are never called by it): dense like mode 0, but denom = sqrt(v) / sqrt(1 - beta2^t) + eps
  * ============================================================================================= */
 PP_API int pp_adam_upd(pp_dtype dtype, int mode, void* param, const void* grad, void* exp_avg,
                 void* exp_avg_sq, const void* perlr, int64_t numel, int32_t step, float beta1,
@@ -264,6 +266,27 @@ PP_API int pp_warpnet_forward_packed(const void* x_rows, int64_t n_rows, int32_t
                                      const int32_t* n_rows_ptr, pp_stream_t stream);
 /* x fp32 [n,3] -> the four fp16 [16] rows per point that pp_warpnet_forward_packed consumes ([4n,16]). */
 PP_API int pp_warpnet_pack_points(const float* x, int64_t n_pts, void* rows, pp_stream_t stream);
+
+/* Training the deformation network: parameter gradients from gradients w.r.t. net(x) AND its input Jacobian - what
+ * the reference's double backward (torch.autograd.grad(..., create_graph=True), lib/voxurf_coarse.py:966-985, then
+ * loss.backward(), lib/recon_scene.py:649) delivers to warp_network.*.grad.  One tcgen05 pass per 128-row tile:
+ * forward recompute, layer-by-layer backward of all four rows with the value row's gates, weight / bias gradients
+ * accumulated in TMEM (bias gradients from the value rows only).  The loss's gradient w.r.t. x THROUGH the network is
+ * J^T (d loss / d value row) and is formed by the caller from the forward's Jacobian; nothing is written per row.
+ * x_rows: as pp_warpnet_forward_packed, with fp16 1.0 in column 6 of every value row (pp_voxurf_deform_rows and
+ * pp_warpnet_pack_points write it; the forward ignores the column).  grad_out: fp32 [n_rows,4], the gradient w.r.t.
+ * pp_warpnet_forward_packed's output in the same four-row layout.  depth must be 5, width 128.
+ * grad_weights / grad_biases: HOST arrays of 5 DEVICE pointers, ACCUMULATED into (+=): grad_weights[0] is [128,6]
+ * like weights[0] (the gradient of the nn.Linear weight [128,3] is the sum of its two halves), the rest nn.Linear
+ * layouts.  workspace: pp_warpnet_backward_workspace_bytes() bytes on the device.
+ * pp_warpnet_backward_stalled: 1 if a barrier wait ever ran out of its cycle budget (never expected; synchronises). */
+PP_API int64_t pp_warpnet_backward_workspace_bytes(void);
+PP_API int pp_warpnet_backward_packed(const void* x_rows, const float* grad_out, int64_t n_rows,
+                                      const int32_t* n_rows_ptr, int32_t depth, int32_t width,
+                                      const float* const* weights, const float* const* biases,
+                                      float* const* grad_weights, float* const* grad_biases, void* workspace,
+                                      pp_stream_t stream);
+PP_API int pp_warpnet_backward_stalled(void);
 
 /* rgbnet training step on tcgen05: forward recompute + backward of the whole network per 128-sample tile
  * (autograd of lib/voxurf_coarse.py:1032-1033 `torch.sigmoid(self.rgbnet(rgb_feat))`).

@@ -88,10 +88,13 @@ PP_API int pp_dvgo_train_step(const pp_dvgo_scene* scene, const pp_dvgo_loss* lo
 
 /* Masked Adam on voxel records, per element exactly masked_adam_upd (adam_upd_kernel.cu:25-40, step size
  * :72) with separate learning rates for the density channel and the three k0 channels; gradients are
- * reset to zero in the same pass (the zero_grad the reference does separately).  In place. */
+ * reset to zero in the same pass (the zero_grad the reference does separately).  In place.
+ * flags: bit 0 (1) = zero the gradients; bit 1 (2) = the reference's LIVE optimiser instead of the dormant masked
+ * kernel: dense Python Adam of lib/utils.py:176-198 - every element updated each step (zero gradients too) and
+ * eps added after the bias correction (denom = sqrt(v)/sqrt(1-beta2^t) + eps). */
 PP_API int pp_voxel_adam(void* vox, void* grad_vox, void* exp_avg, void* exp_avg_sq, int64_t n_voxels,
                          int32_t step, float beta1, float beta2, float lr_density, float lr_k0,
-                         float eps, int zero_grad, pp_stream_t stream);
+                         float eps, int flags, pp_stream_t stream);
 
 /* Same, preceded by the total-variation gradient (total_variation_add_grad, old kernel weights
  * k,j,i = wz,wy,wz; total_variation_kernel.cu:13-35) evaluated on the OLD parameters: reads vox_in,
@@ -227,14 +230,16 @@ PP_API int pp_voxurf_march_features_deform(const pp_dvgo_scene* scene, const pp_
  * feature grid, the rgbnet (and the rays).  After pp_voxurf_march_features_deform + rgbnet forward / loss / backward:
  * pp_voxurf_backward_deform = pp_voxurf_backward with the per-sample {d loss / d sdf_final, d loss / d gradient}
  * written to grad_val (float4 [sample_capacity], indexed like warp_out / 16; zero-fill it first: samples past early
- * termination keep zero) instead of a scatter into the SDF records; the feature-grid scatter is unchanged.
+ * termination keep zero) instead of a scatter into the SDF records; the feature-grid scatter is unchanged.  grad_rays /
+ * grad_viewdirs (nullable, need 64 gradient columns and the records): the colour-side pose gradient of the composited
+ * samples (features, positional encoding, NeuS cosine); pp_voxurf_deform_ray_grad adds the SDF side.
  * pp_voxurf_deform_sample_backward: per in-box sample, chains grad_val through the warped lookup (cell gradient and
  * off-diagonal Hessian of the custom sampler) and the warp Jacobian, adds the regularisers of deform_implicit_loss
  * (lib/losses.py:6-24; w_* = their weights, each term a mean over all in-box samples; reg_terms (nullable, 4 floats,
  * accumulated): the unweighted term values) and writes grad_warp_out fp32 [4 * samples, 4] = the gradient w.r.t.
  * pp_warpnet_forward_packed's output in the same four-row layout (the grad_out of the network's backward);
  * grad_pts (nullable) [samples,3]: d loss / d x through x' and sdf(x).  Formulas: oracle/deform_analytic.py.
- * NOT yet available: the backward of the warp network itself. */
+ * The network's own backward is pp_warpnet_backward_packed (poseprobe_b200.h). */
 PP_API int pp_voxurf_backward_deform(const pp_dvgo_scene* scene, const pp_voxurf_cfg* cfg, const float* rays_o,
                                      const float* rays_d, const float* viewdirs, const float* jitter,
                                      int64_t n_rays, const void* sample_rec, const float* grad_weight,
@@ -242,19 +247,55 @@ PP_API int pp_voxurf_backward_deform(const pp_dvgo_scene* scene, const pp_voxurf
                                      const int32_t* ray_cnt, const int32_t* ray_end, const float* g_ray,
                                      void* grad_k0_records, const float* grad_cum_weights,
                                      const float* grad_alphainv_last, void* grad_val,
-                                     const int32_t* warp_ray_off, pp_stream_t stream);
+                                     const int32_t* warp_ray_off, const void* sdf_records, const void* k0_records,
+                                     float* grad_rays, float* grad_viewdirs, pp_stream_t stream);
 PP_API int pp_voxurf_deform_sample_backward(const pp_dvgo_scene* scene, const void* sdf_records,
                                             const void* sample_pts, const float* warp_out, const void* grad_val,
                                             const int32_t* n_samples_ptr, int64_t sample_capacity, float out_range,
                                             float w_eikonal, float w_jacobian, float w_correction, float w_deform,
                                             float* grad_warp_out, float* grad_pts, float* reg_terms,
-                                            pp_stream_t stream);
+                                            const float* ext_grad, pp_stream_t stream);
+/* Forward half of the same per-sample computation, for callers that keep the loss in Python (lib/losses.py:6-24
+ * reads gradient, grad_deform, sdf_correct, sdf_deform of ALL in-box samples, voxurf_coarse.py:1085-1090):
+ * sample_out fp32 [samples,16] = sdf_final | gradient[3] | grad_deform[3][3] ([i][k] = d x'_k / d x_i) | sdf_correct |
+ * sdf_deform | 0.  ext_grad of pp_voxurf_deform_sample_backward (nullable) is the way back: fp32 [samples,14] =
+ * d loss / d (gradient[3] | grad_deform[9] | sdf_correct | sdf_deform), added to the built-in terms.
+ * grad_pts of pp_voxurf_deform_sample_backward is the complete d loss / d x of the sample through the deformation
+ * branch: x' and the warped lookup, the unwarped lookup of sdf_deform, and J^T (d loss / d net(x)). */
+PP_API int pp_voxurf_deform_sample_forward(const pp_dvgo_scene* scene, const void* sdf_records, const void* sample_pts,
+                                           const float* warp_out, const int32_t* n_samples_ptr,
+                                           int64_t sample_capacity, float out_range, float* sample_out,
+                                           float* reg_terms, pp_stream_t stream);
+/* d loss / d (rays_o | rays_d) [N,6] through the positions of all in-box samples: grad_pts [samples,3] chained through
+ * sample_pts_on_rays' geometry (t_min slab, normalised direction), ADDED to grad_rays (which pp_voxurf_backward_deform
+ * filled with the colour-side terms of the composited samples). */
+PP_API int pp_voxurf_deform_ray_grad(const pp_dvgo_scene* scene, const float* rays_o, const float* rays_d,
+                                     const float* jitter, int64_t n_rays, const int32_t* warp_ray_off,
+                                     const float* grad_pts, float* grad_rays, pp_stream_t stream);
 
 /* rgb_marched = clamp(rgb_acc + (1 - cum_w) bg, 0, 1) (:1040-1042); photometric MSE (lib/losses.py:26-29):
  * g_ray [N,3] = d (w_rgb * mse) / d rgb_acc, loss_out[0] += w_rgb * mse, loss_out[1] += mse. */
 PP_API int pp_voxurf_ray_loss(int64_t n_rays, const float* rgb_acc, const float* cum_w, const float* target,
                               float bg, float w_rgb, float* g_ray, float* rgb_marched, float* loss_out,
                               pp_stream_t stream);
+
+/* The reference's per-ray object losses (lib/losses.py:34-74) on the per-ray outputs, value and gradient:
+ *   img_render = sum((rgb_marched m - target m)^2) / (3 sum m)        (weight w_main;   mask null: m = 1)
+ *   weight_entropy_last on clamp(alphainv_last, 1e-6, 1-1e-6)          (weight w_entropy, 0.01 in the reference)
+ *   mask_render = BCE(clip(cum_w, 1e-3, 1-1e-3), m)                    (weight w_mask)
+ * g_acc [N,3], g_cum_w [N], g_last [N] = d (weighted sum) / d (rgb_acc, cum_weights, alphainv_last): the inputs of
+ * pp_rgbnet_backward_fused (g_ray) and pp_voxurf_backward(_deform) (grad_cum_weights, grad_alphainv_last).
+ * loss_out (nullable, 4 floats, accumulated): weighted sum, img_render, entropy, mask_render.  scratch: one device
+ * float (needed with a mask: holds sum m). */
+PP_API int pp_voxurf_object_loss(int64_t n_rays, const float* rgb_acc, const float* cum_w, const float* alphainv_last,
+                                 const float* target, const float* mask, float bg, float w_main, float w_entropy,
+                                 float w_mask, float* g_acc, float* g_cum_w, float* g_last, float* rgb_marched,
+                                 float* loss_out, float* scratch, pp_stream_t stream);
+/* Voxurf.k0_total_variation (voxurf_coarse.py:443-455 -> total_variation :1298-1313, unmasked) on the feature
+ * records: tv_out (nullable, accumulated) += sum of |forward differences| (the loss term is tv_out / (3 * 12 V));
+ * grad_k0_records (nullable) += weight * d tv / d k0. */
+PP_API int pp_voxurf_k0_tv(const pp_dvgo_scene* scene, const void* k0_records, void* grad_k0_records, float weight,
+                           float* tv_out, pp_stream_t stream);
 
 /* Reverse march: alpha2weight / NeuS / normal backward per ray and the scatter into grad_sdf_records
  * ([V] float4, same layout as the SDF records) and grad_k0_records ([V][3] float4); both are accumulated into.
@@ -277,13 +318,14 @@ PP_API int pp_voxurf_backward(const pp_dvgo_scene* scene, const pp_voxurf_cfg* c
 
 /* Dense tail of the SDF grid: folds the gradient-grid components back onto the SDF (transposed central
  * difference), applies the mapping function's chain rule and masked Adam (adam_upd_kernel.cu:35-39) in place.
- * exp_avg / exp_avg_sq null: no update (gradient only).  grad_sdf_out (nullable) receives d loss / d sdf;
+ * exp_avg / exp_avg_sq null: no update (gradient only).  dense != 0: the reference's live dense Python Adam instead
+ * (lib/utils.py:176-198, see pp_voxel_adam).  grad_sdf_out (nullable) receives d loss / d sdf;
  * grad_ab (nullable, 2 floats, accumulated) receives d loss / d (a, b).  The caller zeroes grad_sdf_records
  * afterwards and rebuilds the records. */
 PP_API int pp_voxurf_sdf_adam(const pp_dvgo_scene* scene, const pp_voxurf_cfg* cfg, float* sdf,
                               const void* grad_sdf_records, float* exp_avg, float* exp_avg_sq, int32_t step,
                               float beta1, float beta2, float lr, float eps, float* grad_sdf_out, float* grad_ab,
-                              pp_stream_t stream);
+                              int dense, pp_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -5,7 +5,7 @@ import time and turned into ctypes signatures, so a function that is declared bu
 the other way round) fails loudly here instead of silently mis-calling.
 
 There is no fallback of any kind: if the shared library is missing or a symbol cannot be resolved
-the import raises.  Build the library with `python -m poseprobe_b200.build` (or
+the import raises.  Build the library with `python poseprobe_b200/build.py` (or
 `__graft_entry__.build()`).
 """
 import ctypes
@@ -65,7 +65,7 @@ def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             "poseprobe_b200: %s is missing - the CUDA library has not been built "
-            "(run `python -m poseprobe_b200.build`). There is no CPU fallback." % LIB_PATH)
+            "(run `python poseprobe_b200/build.py`). There is no CPU fallback." % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
     protos = parse_header()
     if not protos:

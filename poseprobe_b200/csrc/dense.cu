@@ -316,13 +316,19 @@ extern "C" int pp_adam_upd(pp_dtype dtype, int mode, void* param, const void* gr
                            void* exp_avg_sq, const void* perlr, int64_t numel, int32_t step,
                            float beta1, float beta2, float lr, float eps, pp_stream_t stream) {
   PP_REQUIRE(numel >= 0, PP_ERR_INVALID_ARG, "adam_upd: numel < 0");
-  PP_REQUIRE(mode >= 0 && mode <= 2, PP_ERR_INVALID_ARG, "adam_upd: unknown mode %d", mode);
+  PP_REQUIRE(mode >= 0 && mode <= 3, PP_ERR_INVALID_ARG, "adam_upd: unknown mode %d", mode);
   if (numel == 0) return PP_OK;
   PP_REQUIRE(param && grad && exp_avg && exp_avg_sq, PP_ERR_INVALID_ARG, "adam_upd: null pointer");
   PP_REQUIRE(mode != 2 || perlr, PP_ERR_INVALID_ARG, "adam_upd: perlr is null");
   // reference host code (adam_upd_kernel.cu:72): all-float bias-corrected step size
   const float step_size =
       lr * sqrtf(1.f - powf(beta2, (float)step)) / (1.f - powf(beta1, (float)step));
+  if (mode == 3) {
+    // the reference's LIVE optimiser (lib/utils.py:176-198): denom = sqrt(v) / sqrt(bc2) + eps, step lr / bc1, i.e.
+    // m / (sqrt(v)/s + eps) = s m / (sqrt(v) + eps s) with s = sqrt(bc2): the plain kernel with eps scaled by s
+    eps *= sqrtf(1.f - powf(beta2, (float)step));
+    mode = 0;
+  }
   if (dtype == PP_F32)
     return launch_adam<float>(mode, param, grad, exp_avg, exp_avg_sq, perlr, numel, step_size,
                               beta1, beta2, eps, as_stream(stream));

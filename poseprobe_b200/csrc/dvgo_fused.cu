@@ -372,8 +372,8 @@ __global__ void voxels_unpack_kernel(const float4* __restrict__ vox, int64_t n,
 // ---- optimiser -------------------------------------------------------------------------------------
 // masked_adam_upd per element (adam_upd_kernel.cu:35-39) with the reference build's contraction
 __device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v, float step_size,
-                                          float b1, float b2, float eps) {
-  if (g == 0.f) return;
+                                          float b1, float b2, float eps, bool dense = false) {
+  if (!dense && g == 0.f) return;
   m = fma_rn(b1, m, mul_rn(1.f - b1, g));
   v = fma_rn(b2, v, mul_rn(mul_rn(1.f - b2, g), g));
   p = p - mul_rn(step_size, m) / (sqrtf(v) + eps);
@@ -385,7 +385,8 @@ __device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v,
 __global__ void __launch_bounds__(256)
 voxel_adam_kernel(float4* __restrict__ vox, float4* __restrict__ grad, float4* __restrict__ m4,
                   float4* __restrict__ v4, int64_t n, float ss_density, float ss_k0, float b1, float b2,
-                  float eps, int zero_grad) {
+                  float eps, int flags) {
+  const bool zero_grad = flags & 1, dense = flags & 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < n; i0 += 2 * stride) {
     const int64_t idx[2] = {i0, i0 + stride};
@@ -402,11 +403,11 @@ voxel_adam_kernel(float4* __restrict__ vox, float4* __restrict__ grad, float4* _
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       if (idx[u] >= n) continue;
-      if (g[u].x == 0.f && g[u].y == 0.f && g[u].z == 0.f && g[u].w == 0.f) continue;
-      adam_elem(p[u].x, g[u].x, m[u].x, v[u].x, ss_density, b1, b2, eps);
-      adam_elem(p[u].y, g[u].y, m[u].y, v[u].y, ss_k0, b1, b2, eps);
-      adam_elem(p[u].z, g[u].z, m[u].z, v[u].z, ss_k0, b1, b2, eps);
-      adam_elem(p[u].w, g[u].w, m[u].w, v[u].w, ss_k0, b1, b2, eps);
+      if (!dense && g[u].x == 0.f && g[u].y == 0.f && g[u].z == 0.f && g[u].w == 0.f) continue;
+      adam_elem(p[u].x, g[u].x, m[u].x, v[u].x, ss_density, b1, b2, eps, dense);
+      adam_elem(p[u].y, g[u].y, m[u].y, v[u].y, ss_k0, b1, b2, eps, dense);
+      adam_elem(p[u].z, g[u].z, m[u].z, v[u].z, ss_k0, b1, b2, eps, dense);
+      adam_elem(p[u].w, g[u].w, m[u].w, v[u].w, ss_k0, b1, b2, eps, dense);
       vox[idx[u]] = p[u];
       m4[idx[u]] = m[u];
       v4[idx[u]] = v[u];
@@ -663,7 +664,7 @@ static float adam_step_size(float lr, float beta1, float beta2, int step) {
 
 extern "C" int pp_voxel_adam(void* vox, void* grad_vox, void* exp_avg, void* exp_avg_sq,
                              int64_t n_voxels, int32_t step, float beta1, float beta2,
-                             float lr_density, float lr_k0, float eps, int zero_grad,
+                             float lr_density, float lr_k0, float eps, int flags,
                              pp_stream_t stream) {
   PP_REQUIRE(n_voxels >= 0, PP_ERR_INVALID_ARG, "voxel_adam: n_voxels < 0");
   if (n_voxels == 0) return PP_OK;
@@ -672,7 +673,7 @@ extern "C" int pp_voxel_adam(void* vox, void* grad_vox, void* exp_avg, void* exp
   voxel_adam_kernel<<<blocks, 256, 0, as_stream(stream)>>>(
       (float4*)vox, (float4*)grad_vox, (float4*)exp_avg, (float4*)exp_avg_sq, n_voxels,
       adam_step_size(lr_density, beta1, beta2, step), adam_step_size(lr_k0, beta1, beta2, step), beta1,
-      beta2, eps, zero_grad);
+      beta2, (flags & 2) ? eps * sqrtf(1.f - powf(beta2, (float)step)) : eps, flags);
   PP_CHECK_LAUNCH("voxel_adam");
   return PP_OK;
 }

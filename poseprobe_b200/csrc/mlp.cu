@@ -286,7 +286,7 @@ __global__ void warpnet_pack_points_kernel(const float* __restrict__ x, int64_t 
   }
   uint4* dst = rows + i * 8;
   const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-  dst[0] = make_uint4(pack_f16(hi[0], hi[1]), pack_f16(hi[2], lo[0]), pack_f16(lo[1], lo[2]), 0u);
+  dst[0] = make_uint4(pack_f16(hi[0], hi[1]), pack_f16(hi[2], lo[0]), pack_f16(lo[1], lo[2]), 0x00003C00u);   // column 6 = 1: db_0 column of the backward's dW_0 product
   dst[1] = zero;
   dst[2] = make_uint4(0x00003C00u, 0u, 0u, 0u);   // e_0 (fp16 1.0 = 0x3C00)
   dst[3] = zero;

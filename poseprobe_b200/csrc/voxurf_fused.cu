@@ -226,7 +226,7 @@ voxurf_deform_rows_kernel(pp_dvgo_scene sc, const float* __restrict__ rays_o, co
       }
       uint4* dst = rows + (int64_t)slot * 8;   // 4 rows x 2 chunks of 8 fp16
       const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-      dst[0] = make_uint4(h2(hi[0], hi[1]), h2(hi[2], lo[0]), h2(lo[1], lo[2]), 0u);
+      dst[0] = make_uint4(h2(hi[0], hi[1]), h2(hi[2], lo[0]), h2(lo[1], lo[2]), 0x00003C00u);   // column 6 = 1: db_0 column of the backward's dW_0 product
       dst[1] = zero;
       dst[2] = make_uint4(0x00003C00u, 0u, 0u, 0u);   // e_0 (fp16 1.0 = 0x3C00)
       dst[3] = zero;
@@ -497,7 +497,13 @@ voxurf_deform_sample_backward_kernel(pp_dvgo_scene sc, const float4* __restrict_
                                      const float* __restrict__ dout, const float4* __restrict__ g_val,
                                      const int32_t* __restrict__ n_ptr, int64_t cap, float R, float w_eik, float w_jac,
                                      float w_corr, float w_def, float* __restrict__ g_dout, float* __restrict__ g_pts,
-                                     float* __restrict__ reg_out) {
+                                     float* __restrict__ reg_out, const float* __restrict__ ext_grad,
+                                     float* __restrict__ sample_out) {
+  // ext_grad (nullable) [M,14]: d loss / d (gradient[3] | grad_deform[3][3] | sdf_correct | sdf_deform) of a loss that
+  // lives in the caller's autograd (lib/losses.py), added to the built-in regulariser terms.
+  // sample_out (nullable) [M,16]: sdf_final | gradient[3] | grad_deform[3][3] | sdf_correct | sdf_deform | 0 - the
+  // per-sample entries of the reference's result dict (voxurf_coarse.py:1085-1090); with g_dout == null the kernel
+  // only produces those (forward).
   const int64_t M = min64(cap, static_cast<int64_t>(*n_ptr));
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   float t_eik = 0.f, t_jac = 0.f, t_corr = 0.f, t_def = 0.f;
@@ -508,7 +514,7 @@ voxurf_deform_sample_backward_kernel(pp_dvgo_scene sc, const float4* __restrict_
     const float4* D = reinterpret_cast<const float4*>(dout + i * 16);
     const float4 o = __ldg(D);
     const float4 jr[3] = {__ldg(D + 1), __ldg(D + 2), __ldg(D + 3)};
-    const float4 G = g_val[i];
+    const float4 G = g_val ? g_val[i] : make_float4(0.f, 0.f, 0.f, 0.f);
     const float scale[3] = {static_cast<float>(sc.sx - 1) / (sc.xyz_max[0] - sc.xyz_min[0]),
                             static_cast<float>(sc.sy - 1) / (sc.xyz_max[1] - sc.xyz_min[1]),
                             static_cast<float>(sc.sz - 1) / (sc.xyz_max[2] - sc.xyz_min[2])};
@@ -548,6 +554,13 @@ voxurf_deform_sample_backward_kernel(pp_dvgo_scene sc, const float4* __restrict_
     const float corr = R * o.w;
     const float sdf_final = s + corr;
     const float sd = sdf_final - s0;
+    if (sample_out) {
+      float4* so = reinterpret_cast<float4*>(sample_out + i * 16);
+      so[0] = make_float4(sdf_final, grad[0], grad[1], grad[2]);
+      so[1] = make_float4(A[0][0], A[0][1], A[0][2], A[1][0]);
+      so[2] = make_float4(A[1][1], A[1][2], A[2][0], A[2][1]);
+      so[3] = make_float4(A[2][2], corr, sd, 0.f);
+    }
     // regularisers
     float Gg[3] = {G.y, G.z, G.w};
     const float gn = sqrtf(grad[0] * grad[0] + grad[1] * grad[1] + grad[2] * grad[2]);
@@ -565,8 +578,19 @@ voxurf_deform_sample_backward_kernel(pp_dvgo_scene sc, const float4* __restrict_
     }
     t_corr = fabsf(corr) * inv_m;
     t_def = fabsf(sd) * inv_m;
-    const float G_corr = w_corr * inv_m * (corr > 0.f ? 1.f : (corr < 0.f ? -1.f : 0.f));
-    const float G_sd = w_def * inv_m * (sd > 0.f ? 1.f : (sd < 0.f ? -1.f : 0.f));
+    float G_corr = w_corr * inv_m * (corr > 0.f ? 1.f : (corr < 0.f ? -1.f : 0.f));
+    float G_sd = w_def * inv_m * (sd > 0.f ? 1.f : (sd < 0.f ? -1.f : 0.f));
+    if (ext_grad) {
+      const float* e = ext_grad + i * 14;
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {
+        Gg[a] += e[a];
+#pragma unroll
+        for (int b = 0; b < 3; ++b) GA[a][b] += e[3 + 3 * a + b];
+      }
+      G_corr += e[12];
+      G_sd += e[13];
+    }
     const float Gs = G.x + G_sd;
     // h = dL/dg, G_new = dL/dx'
     float h[3], Gn[3];
@@ -575,12 +599,15 @@ voxurf_deform_sample_backward_kernel(pp_dvgo_scene sc, const float4* __restrict_
     Gn[0] = Gs * g[0] + hxy * h[1] + hxz * h[2];
     Gn[1] = Gs * g[1] + hxy * h[0] + hyz * h[2];
     Gn[2] = Gs * g[2] + hxz * h[0] + hyz * h[1];
-    float4* out = reinterpret_cast<float4*>(g_dout + i * 16);
-    out[0] = make_float4(R * Gn[0], R * Gn[1], R * Gn[2], R * (Gs + G_corr));
+    const float4 Gy = make_float4(R * Gn[0], R * Gn[1], R * Gn[2], R * (Gs + G_corr));
+    if (g_dout) {
+      float4* out = reinterpret_cast<float4*>(g_dout + i * 16);
+      out[0] = Gy;
 #pragma unroll
-    for (int a = 0; a < 3; ++a)
-      out[1 + a] = make_float4(R * (Gg[a] * g[0] + GA[a][0]), R * (Gg[a] * g[1] + GA[a][1]),
-                               R * (Gg[a] * g[2] + GA[a][2]), R * Gg[a]);
+      for (int a = 0; a < 3; ++a)
+        out[1 + a] = make_float4(R * (Gg[a] * g[0] + GA[a][0]), R * (Gg[a] * g[1] + GA[a][1]),
+                                 R * (Gg[a] * g[2] + GA[a][2]), R * Gg[a]);
+    }
     if (g_pts) {
       const float f0x = c0.fx, f0y = c0.fy, f0z = c0.fz, g0x = c0.gx(), g0y = c0.gy(), g0z = c0.gz();
       const float g0[3] = {
@@ -588,7 +615,8 @@ voxurf_deform_sample_backward_kernel(pp_dvgo_scene sc, const float4* __restrict_
           (((u0[2] - u0[0]) * g0z + (u0[3] - u0[1]) * f0z) * g0x + ((u0[6] - u0[4]) * g0z + (u0[7] - u0[5]) * f0z) * f0x) * scale[1],
           (((u0[1] - u0[0]) * g0y + (u0[3] - u0[2]) * f0y) * g0x + ((u0[5] - u0[4]) * g0y + (u0[7] - u0[6]) * f0y) * f0x) * scale[2]};
 #pragma unroll
-      for (int k = 0; k < 3; ++k) g_pts[3 * i + k] = Gn[k] - G_sd * g0[k];
+      for (int k = 0; k < 3; ++k)
+        g_pts[3 * i + k] = Gn[k] - G_sd * g0[k] + (jr[k].x * Gy.x + jr[k].y * Gy.y + jr[k].z * Gy.z + jr[k].w * Gy.w);
     }
   }
   if (reg_out) {
@@ -624,6 +652,86 @@ __device__ __forceinline__ void spatial_grad4(const Cell& c, const float4 (&v)[8
     gp[0] += dch[ch] * dX;
     gp[1] += dch[ch] * dY;
     gp[2] += dch[ch] * dZ;
+  }
+}
+
+// point_i = o + d*t_min + (d/|d|) * s_i; t_min is locally constant in (o, d) except through the entering slab (same
+// chain as the coarse kernel, dvgo_fused.cu).  G0 = sum_i dL/dp_i, G1 = sum_i s_i dL/dp_i -> dL/do, dL/dd
+__device__ __forceinline__ void ray_chain(const pp_dvgo_scene& sc, const Ray& ray, const float (&G0)[3],
+                                          const float (&G1)[3], float (&go)[3], float (&gd)[3]) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    go[k] = G0[k];
+    gd[k] = G0[k] * ray.t_min;
+  }
+  int axis = -1;
+  float best = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float vv = (ray.d[k] == 0.f) ? 1e-6f : ray.d[k];
+    const float a = (sc.xyz_max[k] - ray.o[k]) / vv;
+    const float b = (sc.xyz_min[k] - ray.o[k]) / vv;
+    const float m = fminf(a, b);
+    if (m > best) { best = m; axis = k; }
+  }
+  if (best == ray.t_min && ray.d[axis] != 0.f) {   // not clamped by near / far
+    const float gdot = G0[0] * ray.d[0] + G0[1] * ray.d[1] + G0[2] * ray.d[2];
+    go[axis] += gdot * (-1.f / ray.d[axis]);
+    gd[axis] += gdot * (-ray.t_min / ray.d[axis]);
+  }
+  const float inv = 1.f / ray.rnorm;
+  const float dotg = (G1[0] * ray.d[0] + G1[1] * ray.d[1] + G1[2] * ray.d[2]) * inv * inv * inv;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) gd[k] += G1[k] * inv - ray.d[k] * dotg;
+}
+
+// Implicit deformation: d loss / d (rays_o, rays_d) through the positions of ALL in-box samples of the ray (the
+// warped SDF lookup, the unwarped one of sdf_deform and the network's value row; g_pts of
+// voxurf_deform_sample_backward_kernel), ADDED to what the reverse march wrote for the composited samples.
+__global__ void __launch_bounds__(256)
+voxurf_deform_ray_grad_kernel(pp_dvgo_scene sc, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
+                              const float* __restrict__ jitter, int64_t n_rays, int cap,
+                              const int32_t* __restrict__ dray_off, const float* __restrict__ g_pts,
+                              float* __restrict__ grad_rays) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (r >= n_rays) return;
+  const int off = dray_off[r];
+  if (off < 0) return;
+  const Ray ray = setup_ray(sc, rays_o, rays_d, r);
+  const int n_steps = min(ray.n_steps, cap);
+  const float jit = jitter ? jitter[r] : 0.f;
+  float G0[3] = {0.f, 0.f, 0.f}, G1[3] = {0.f, 0.f, 0.f};
+  int run = 0;
+  for (int base = 0; base < n_steps; base += kWarp) {
+    float p[3];
+    const int i = base + lane;
+    const bool inbox = (i < n_steps) && vox_point(sc, ray, i, jit, p);
+    const unsigned m = __ballot_sync(kFull, inbox);
+    const int slot = off + run + __popc(m & ((1u << lane) - 1u));
+    run += __popc(m);
+    if (!inbox) continue;
+    const float sdist = sc.stepdist * (static_cast<float>(i) + jit);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float gp = g_pts[3 * (int64_t)slot + k];
+      G0[k] += gp;
+      G1[k] += gp * sdist;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    G0[k] = warp_sum(G0[k]);
+    G1[k] = warp_sum(G1[k]);
+  }
+  if (lane == 0) {
+    float go[3], gd[3];
+    ray_chain(sc, ray, G0, G1, go, gd);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      grad_rays[6 * r + k] += go[k];
+      grad_rays[6 * r + 3 + k] += gd[k];
+    }
   }
 }
 
@@ -848,29 +956,12 @@ voxurf_backward_kernel(pp_dvgo_scene sc, pp_voxurf_cfg cfg, const float* __restr
         GV[k] = warp_sum(GV[k]);
       }
       if (lane == 0) {
-        float go[3] = {G0[0], G0[1], G0[2]};
-        float gd[3] = {G0[0] * ray.t_min, G0[1] * ray.t_min, G0[2] * ray.t_min};
-        int axis = -1;
-        float best = -INFINITY;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const float vv = (ray.d[k] == 0.f) ? 1e-6f : ray.d[k];
-          const float a = (sc.xyz_max[k] - ray.o[k]) / vv;
-          const float b = (sc.xyz_min[k] - ray.o[k]) / vv;
-          const float m = fminf(a, b);
-          if (m > best) { best = m; axis = k; }
-        }
-        if (best == ray.t_min && ray.d[axis] != 0.f) {   // not clamped by near / far
-          const float gdot = G0[0] * ray.d[0] + G0[1] * ray.d[1] + G0[2] * ray.d[2];
-          go[axis] += gdot * (-1.f / ray.d[axis]);
-          gd[axis] += gdot * (-ray.t_min / ray.d[axis]);
-        }
-        const float inv = 1.f / ray.rnorm;
-        const float dotg = (G1[0] * ray.d[0] + G1[1] * ray.d[1] + G1[2] * ray.d[2]) * inv * inv * inv;
+        float go[3], gd[3];
+        ray_chain(sc, ray, G0, G1, go, gd);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           grad_rays[6 * r + k] = go[k];
-          grad_rays[6 * r + 3 + k] = gd[k] + G1[k] * inv - ray.d[k] * dotg;
+          grad_rays[6 * r + 3 + k] = gd[k];
           grad_viewdirs[3 * r + k] = GV[k];
         }
       }
@@ -884,7 +975,7 @@ __global__ void __launch_bounds__(256)
 sdf_fold_adam_kernel(float* __restrict__ sdf, const float4* __restrict__ g_srec, float* __restrict__ m1,
                      float* __restrict__ m2, int sx, int sy, int sz, float a, float b, float inv_2vs,
                      float step_size, float b1, float b2, float eps, float* __restrict__ grad_sdf_out,
-                     float* __restrict__ g_ab) {
+                     float* __restrict__ g_ab, bool dense) {
   const int k = blockIdx.x * 32 + threadIdx.x;
   const int j = blockIdx.y * 8 + threadIdx.y;
   float da = 0.f, db = 0.f;
@@ -911,7 +1002,7 @@ sdf_fold_adam_kernel(float* __restrict__ sdf, const float4* __restrict__ g_srec,
         gr = gs * a * b * dsg;
       }
       if (grad_sdf_out) grad_sdf_out[idx] = gr;
-      if (m1 && gr != 0.f) {   // masked_adam_upd (adam_upd_kernel.cu:35-39)
+      if (m1 && (dense || gr != 0.f)) {   // masked_adam_upd (adam_upd_kernel.cu:35-39) / dense Python Adam
         float mm = m1[idx], vv = m2[idx];
         mm = fma_rn(b1, mm, mul_rn(1.f - b1, gr));
         vv = fma_rn(b2, vv, mul_rn(mul_rn(1.f - b2, gr), gr));
@@ -1103,6 +1194,166 @@ extern "C" int pp_voxurf_deform_rows(const pp_dvgo_scene* scene, const float* ra
   return PP_OK;
 }
 
+// ---- the reference's per-ray object losses (lib/losses.py:34-74), value and gradient in one pass ---------------
+//   img_render          sum((rgb m - target m)^2) / (3 sum m)                              weight w_main
+//   weight_entropy_last -mean(p ln p + (1-p) ln(1-p)), p = clamp(alphainv_cum, 1e-6, 1-1e-6)  weight w_entropy
+//   mask_render         BCE(clip(cum_weights, 1e-3, 1-1e-3), m)                             weight w_mask
+// mask_sum: device float = sum m (voxurf_mask_sum_kernel); mask null: m = 1.
+__global__ void voxurf_mask_sum_kernel(int64_t n, const float* __restrict__ mask, float* __restrict__ out) {
+  float sum = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    sum += mask[i];
+  sum = warp_sum(sum);
+  if ((threadIdx.x & 31) == 0 && sum != 0.f) atomicAdd(out, sum);
+}
+
+__global__ void voxurf_object_loss_kernel(int64_t n_rays, const float* __restrict__ acc, const float* __restrict__ cum_w,
+                                          const float* __restrict__ last, const float* __restrict__ target,
+                                          const float* __restrict__ mask, const float* __restrict__ mask_sum, float bg,
+                                          float w_main, float w_entropy, float w_mask, float* __restrict__ g_acc,
+                                          float* __restrict__ g_cumw, float* __restrict__ g_last,
+                                          float* __restrict__ rgb_marched, float* __restrict__ loss_out) {
+  const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  float mse = 0.f, ent = 0.f, bce = 0.f;
+  if (r < n_rays) {
+    const float inv_n = 1.f / static_cast<float>(n_rays);
+    const float m = mask ? mask[r] : 1.f;
+    const float msum = mask ? *mask_sum : static_cast<float>(n_rays);
+    const float inv_m = 1.f / (3.f * msum);
+    const float cw = cum_w[r];
+    const float rest = (1.f - cw) * bg;
+    float gsum = 0.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float raw = acc[3 * r + c] + rest;
+      const float y = fminf(fmaxf(raw, 0.f), 1.f);
+      const float diff = (y - target[3 * r + c]) * m;
+      mse += diff * diff * inv_m;
+      const float g = (raw >= 0.f && raw <= 1.f) ? w_main * 2.f * diff * m * inv_m : 0.f;
+      g_acc[3 * r + c] = g;
+      gsum += g;
+      if (rgb_marched) rgb_marched[3 * r + c] = y;
+    }
+    float gc = -bg * gsum, gl = 0.f;
+    {
+      const float a = last[r];
+      const float p = fminf(fmaxf(a, 1e-6f), 1.f - 1e-6f);
+      const float lp = logf(p), lq = logf(1.f - p);
+      ent = -(p * lp + (1.f - p) * lq) * inv_n;
+      if (a >= 1e-6f && a <= 1.f - 1e-6f) gl = -w_entropy * (lp - lq) * inv_n;
+    }
+    {
+      const float c = fminf(fmaxf(cw, 1e-3f), 1.f - 1e-3f);
+      bce = -(m * logf(c) + (1.f - m) * logf(1.f - c)) * inv_n;
+      if (cw >= 1e-3f && cw <= 1.f - 1e-3f) gc += -w_mask * (m / c - (1.f - m) / (1.f - c)) * inv_n;
+    }
+    g_cumw[r] = gc;
+    g_last[r] = gl;
+  }
+  mse = warp_sum(mse);
+  ent = warp_sum(ent);
+  bce = warp_sum(bce);
+  if ((threadIdx.x & 31) == 0 && loss_out) {
+    atomicAdd(loss_out, w_main * mse + w_entropy * ent + w_mask * bce);
+    atomicAdd(loss_out + 1, mse);
+    atomicAdd(loss_out + 2, ent);
+    atomicAdd(loss_out + 3, bce);
+  }
+}
+
+// ---- k0 total variation on the feature records (Voxurf.k0_total_variation -> total_variation, voxurf_coarse.py:
+//      443-455, :1298-1313, no mask): tv = (sum |d_x| + sum |d_y| + sum |d_z|) / 3 / numel.  Every voxel forms its own
+//      gradient from its (up to) six neighbours - sign(v - v_prev) - sign(v_next - v) per axis - so nothing is atomic.
+__global__ void __launch_bounds__(256)
+k0rec_tv_kernel(const float4* __restrict__ rec, float4* __restrict__ grad, int sx, int sy, int sz, float coef,
+                float* __restrict__ tv_out) {
+  const int k = blockIdx.x * 32 + threadIdx.x;
+  const int j = blockIdx.y * 8 + threadIdx.y;
+  float tv = 0.f;
+  if (k < sz && j < sy) {
+    const int64_t ox = (int64_t)sy * sz;
+    for (int i = blockIdx.z; i < sx; i += gridDim.z) {
+      const int64_t idx = ((int64_t)i * sy + j) * sz + k;
+#pragma unroll
+      for (int grp = 0; grp < 3; ++grp) {
+        const float4 v = rec[idx * 3 + grp];
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        auto sgn = [](float d) { return d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f); };
+        auto nbr = [&](bool has, int64_t o, bool fwd) {
+          if (!has) return;
+          const float4 q = rec[(idx + o) * 3 + grp];
+          // fwd: the difference (q - v) belongs to this voxel's forward edge: d|q - v| / dv = -sign(q - v)
+          const float dx = fwd ? q.x - v.x : v.x - q.x, dy = fwd ? q.y - v.y : v.y - q.y;
+          const float dz = fwd ? q.z - v.z : v.z - q.z, dw = fwd ? q.w - v.w : v.w - q.w;
+          const float sg = fwd ? -1.f : 1.f;
+          g.x += sg * sgn(dx);
+          g.y += sg * sgn(dy);
+          g.z += sg * sgn(dz);
+          g.w += sg * sgn(dw);
+          if (fwd) tv += fabsf(dx) + fabsf(dy) + fabsf(dz) + fabsf(dw);
+        };
+        nbr(i + 1 < sx, ox, true);
+        nbr(i > 0, -ox, false);
+        nbr(j + 1 < sy, sz, true);
+        nbr(j > 0, -(int64_t)sz, false);
+        nbr(k + 1 < sz, 1, true);
+        nbr(k > 0, -1, false);
+        if (grad && (g.x != 0.f || g.y != 0.f || g.z != 0.f || g.w != 0.f)) {
+          float4 o = grad[idx * 3 + grp];
+          o.x = fma_rn(coef, g.x, o.x);
+          o.y = fma_rn(coef, g.y, o.y);
+          o.z = fma_rn(coef, g.z, o.z);
+          o.w = fma_rn(coef, g.w, o.w);
+          grad[idx * 3 + grp] = o;
+        }
+      }
+    }
+  }
+  if (tv_out) {
+    tv = warp_sum(tv);
+    if (threadIdx.x == 0 && tv != 0.f) atomicAdd(tv_out, tv);
+  }
+}
+
+extern "C" int pp_voxurf_object_loss(int64_t n_rays, const float* rgb_acc, const float* cum_w,
+                                     const float* alphainv_last, const float* target, const float* mask, float bg,
+                                     float w_main, float w_entropy, float w_mask, float* g_acc, float* g_cum_w,
+                                     float* g_last, float* rgb_marched, float* loss_out, float* scratch,
+                                     pp_stream_t stream) {
+  PP_REQUIRE(n_rays >= 0, PP_ERR_INVALID_ARG, "voxurf_object_loss: n_rays < 0");
+  if (n_rays == 0) return PP_OK;
+  PP_REQUIRE(rgb_acc && cum_w && alphainv_last && target && g_acc && g_cum_w && g_last, PP_ERR_INVALID_ARG,
+             "voxurf_object_loss: null pointer");
+  PP_REQUIRE(!mask || scratch, PP_ERR_INVALID_ARG, "voxurf_object_loss: a mask needs the 4-byte scratch word");
+  if (mask) {
+    PP_CHECK_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float), as_stream(stream)));
+    voxurf_mask_sum_kernel<<<(int)min64(ceil_div(n_rays, 256), sm_count()), 256, 0, as_stream(stream)>>>(n_rays, mask,
+                                                                                                        scratch);
+    PP_CHECK_LAUNCH("voxurf_mask_sum");
+  }
+  voxurf_object_loss_kernel<<<ceil_div(n_rays, 256), 256, 0, as_stream(stream)>>>(
+      n_rays, rgb_acc, cum_w, alphainv_last, target, mask, scratch, bg, w_main, w_entropy, w_mask, g_acc, g_cum_w,
+      g_last, rgb_marched, loss_out);
+  PP_CHECK_LAUNCH("voxurf_object_loss");
+  return PP_OK;
+}
+
+extern "C" int pp_voxurf_k0_tv(const pp_dvgo_scene* scene, const void* k0_records, void* grad_k0_records, float weight,
+                               float* tv_out, pp_stream_t stream) {
+  PP_REQUIRE(scene && k0_records, PP_ERR_INVALID_ARG, "voxurf_k0_tv: null pointer");
+  PP_REQUIRE(grad_k0_records || tv_out, PP_ERR_INVALID_ARG, "voxurf_k0_tv: nothing to produce");
+  const int64_t numel = (int64_t)scene->sx * scene->sy * scene->sz * 12;
+  const dim3 block(32, 8, 1);
+  const int tiles = ((scene->sz + 31) / 32) * ((scene->sy + 7) / 8);
+  const int zdim = (int)min64(scene->sx, (int64_t)((16 * sm_count() + tiles - 1) / tiles));
+  const dim3 grid((scene->sz + 31) / 32, (scene->sy + 7) / 8, (unsigned)(zdim < 1 ? 1 : zdim));
+  k0rec_tv_kernel<<<grid, block, 0, as_stream(stream)>>>((const float4*)k0_records, (float4*)grad_k0_records, scene->sx,
+                                                        scene->sy, scene->sz,
+                                                        weight / (3.f * static_cast<float>(numel)), tv_out);
+  PP_CHECK_LAUNCH("voxurf_k0_tv");
+  return PP_OK;
+}
+
 extern "C" int pp_voxurf_ray_loss(int64_t n_rays, const float* rgb_acc, const float* cum_w, const float* target,
                                   float bg, float w_rgb, float* g_ray, float* rgb_marched, float* loss_out,
                                   pp_stream_t stream) {
@@ -1184,12 +1435,14 @@ extern "C" int pp_voxurf_backward_deform(const pp_dvgo_scene* scene, const pp_vo
                                          const int32_t* ray_cnt, const int32_t* ray_end, const float* g_ray,
                                          void* grad_k0_records, const float* grad_cum_weights,
                                          const float* grad_alphainv_last, void* grad_val,
-                                         const int32_t* warp_ray_off, pp_stream_t stream) {
+                                         const int32_t* warp_ray_off, const void* sdf_records,
+                                         const void* k0_records, float* grad_rays, float* grad_viewdirs,
+                                         pp_stream_t stream) {
   PP_REQUIRE(grad_val && warp_ray_off, PP_ERR_INVALID_ARG, "voxurf_backward_deform: null pointer");
   return launch_vox_backward(scene, cfg, rays_o, rays_d, viewdirs, jitter, n_rays, sample_rec, grad_weight, grad_feat,
-                             grad_feat_cols, ray_off, ray_cnt, ray_end, g_ray, nullptr, grad_k0_records, nullptr,
-                             nullptr, nullptr, nullptr, grad_cum_weights, grad_alphainv_last, grad_val, warp_ray_off,
-                             stream);
+                             grad_feat_cols, ray_off, ray_cnt, ray_end, g_ray, nullptr, grad_k0_records, sdf_records,
+                             k0_records, grad_rays, grad_viewdirs, grad_cum_weights, grad_alphainv_last, grad_val,
+                             warp_ray_off, stream);
 }
 
 extern "C" int pp_voxurf_deform_sample_backward(const pp_dvgo_scene* scene, const void* sdf_records,
@@ -1197,7 +1450,7 @@ extern "C" int pp_voxurf_deform_sample_backward(const pp_dvgo_scene* scene, cons
                                                 const int32_t* n_samples_ptr, int64_t sample_capacity, float out_range,
                                                 float w_eikonal, float w_jacobian, float w_correction,
                                                 float w_deform, float* grad_warp_out, float* grad_pts,
-                                                float* reg_terms, pp_stream_t stream) {
+                                                float* reg_terms, const float* ext_grad, pp_stream_t stream) {
   PP_REQUIRE(scene, PP_ERR_INVALID_ARG, "voxurf_deform_sample_backward: null scene");
   PP_REQUIRE(sample_capacity >= 0, PP_ERR_INVALID_ARG, "voxurf_deform_sample_backward: negative extent");
   if (sample_capacity == 0) return PP_OK;
@@ -1205,15 +1458,46 @@ extern "C" int pp_voxurf_deform_sample_backward(const pp_dvgo_scene* scene, cons
              "voxurf_deform_sample_backward: null pointer");
   voxurf_deform_sample_backward_kernel<<<ceil_div(sample_capacity, 256), 256, 0, as_stream(stream)>>>(
       *scene, (const float4*)sdf_records, (const float4*)sample_pts, warp_out, (const float4*)grad_val, n_samples_ptr,
-      sample_capacity, out_range, w_eikonal, w_jacobian, w_correction, w_deform, grad_warp_out, grad_pts, reg_terms);
+      sample_capacity, out_range, w_eikonal, w_jacobian, w_correction, w_deform, grad_warp_out, grad_pts, reg_terms,
+      ext_grad, nullptr);
   PP_CHECK_LAUNCH("voxurf_deform_sample_backward");
+  return PP_OK;
+}
+
+extern "C" int pp_voxurf_deform_sample_forward(const pp_dvgo_scene* scene, const void* sdf_records,
+                                               const void* sample_pts, const float* warp_out,
+                                               const int32_t* n_samples_ptr, int64_t sample_capacity, float out_range,
+                                               float* sample_out, float* reg_terms, pp_stream_t stream) {
+  PP_REQUIRE(scene, PP_ERR_INVALID_ARG, "voxurf_deform_sample_forward: null scene");
+  PP_REQUIRE(sample_capacity >= 0, PP_ERR_INVALID_ARG, "voxurf_deform_sample_forward: negative extent");
+  if (sample_capacity == 0) return PP_OK;
+  PP_REQUIRE(sdf_records && sample_pts && warp_out && n_samples_ptr && sample_out, PP_ERR_INVALID_ARG,
+             "voxurf_deform_sample_forward: null pointer");
+  voxurf_deform_sample_backward_kernel<<<ceil_div(sample_capacity, 256), 256, 0, as_stream(stream)>>>(
+      *scene, (const float4*)sdf_records, (const float4*)sample_pts, warp_out, nullptr, n_samples_ptr, sample_capacity,
+      out_range, 0.f, 0.f, 0.f, 0.f, nullptr, nullptr, reg_terms, nullptr, sample_out);
+  PP_CHECK_LAUNCH("voxurf_deform_sample_forward");
+  return PP_OK;
+}
+
+extern "C" int pp_voxurf_deform_ray_grad(const pp_dvgo_scene* scene, const float* rays_o, const float* rays_d,
+                                         const float* jitter, int64_t n_rays, const int32_t* warp_ray_off,
+                                         const float* grad_pts, float* grad_rays, pp_stream_t stream) {
+  PP_REQUIRE(scene, PP_ERR_INVALID_ARG, "voxurf_deform_ray_grad: null scene");
+  PP_REQUIRE(n_rays >= 0, PP_ERR_INVALID_ARG, "voxurf_deform_ray_grad: negative extent");
+  if (n_rays == 0) return PP_OK;
+  PP_REQUIRE(rays_o && rays_d && warp_ray_off && grad_pts && grad_rays, PP_ERR_INVALID_ARG,
+             "voxurf_deform_ray_grad: null pointer");
+  voxurf_deform_ray_grad_kernel<<<ceil_div(n_rays * 32, 256), 256, 0, as_stream(stream)>>>(
+      *scene, rays_o, rays_d, jitter, n_rays, vox_step_capacity(scene), warp_ray_off, grad_pts, grad_rays);
+  PP_CHECK_LAUNCH("voxurf_deform_ray_grad");
   return PP_OK;
 }
 
 extern "C" int pp_voxurf_sdf_adam(const pp_dvgo_scene* scene, const pp_voxurf_cfg* cfg, float* sdf,
                                   const void* grad_sdf_records, float* exp_avg, float* exp_avg_sq, int32_t step,
                                   float beta1, float beta2, float lr, float eps, float* grad_sdf_out,
-                                  float* grad_ab, pp_stream_t stream) {
+                                  float* grad_ab, int dense, pp_stream_t stream) {
   const int rc = check_vox_scene(scene, cfg, "voxurf_sdf_adam");
   if (rc != PP_OK) return rc;
   PP_REQUIRE(sdf && grad_sdf_records, PP_ERR_INVALID_ARG, "voxurf_sdf_adam: null pointer");
@@ -1229,7 +1513,8 @@ extern "C" int pp_voxurf_sdf_adam(const pp_dvgo_scene* scene, const pp_voxurf_cf
   const dim3 grid((scene->sz + 31) / 32, (scene->sy + 7) / 8, (unsigned)(zdim < 1 ? 1 : zdim));
   sdf_fold_adam_kernel<<<grid, block, 0, as_stream(stream)>>>(
       sdf, (const float4*)grad_sdf_records, exp_avg, exp_avg_sq, scene->sx, scene->sy, scene->sz, cfg->sdf_scale_a,
-      cfg->sdf_scale_b, 0.5f / cfg->voxel_size, step_size, beta1, beta2, eps, grad_sdf_out, grad_ab);
+      cfg->sdf_scale_b, 0.5f / cfg->voxel_size, step_size, beta1, beta2,
+      dense ? eps * sqrtf(1.f - powf(beta2, (float)step)) : eps, grad_sdf_out, grad_ab, dense != 0);
   PP_CHECK_LAUNCH("voxurf_sdf_adam");
   return PP_OK;
 }

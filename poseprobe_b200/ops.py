@@ -293,6 +293,32 @@ def warpnet_forward(x, weights, biases, out_range=1.0):
     return out[:, 0, :3], out[:, 0, 3:], out[:, 1:, :].transpose(1, 2)
 
 
+def warpnet_backward(x, weights, biases, grad_rows):
+    """Parameter gradients of the deformation network from gradients w.r.t. its value AND its input Jacobian (the
+    reference's double backward through DeformedImplicitField, lib/voxurf_coarse.py:966-985), one tcgen05 pass.
+
+    x [n,3]; grad_rows [n,4,4] fp32: row 0 = d loss / d net(x) (raw outputs, before the output range), row 1+k =
+    d loss / d (d net / d x_k) -> ([dW_l], [db_l]) in the nn.Linear layouts of ``weights`` / ``biases``."""
+    import ctypes
+    if not x.is_cuda:
+        raise RuntimeError("warpnet_backward: x must be a CUDA tensor (no CPU fallback)")
+    x = x.detach().float().contiguous()
+    ws, bs = warpnet_params(weights, biases)
+    depth, n = len(ws), x.shape[0]
+    g = grad_rows.detach().float().contiguous().reshape(4 * n, 4)
+    rows = torch.empty((4 * n, 16), dtype=torch.float16, device=x.device)
+    gws = [torch.zeros_like(w) for w in ws]
+    gbs = [torch.zeros_like(b) for b in bs]
+    work = torch.empty(int(lib.pp_warpnet_backward_workspace_bytes()), dtype=torch.uint8, device=x.device)
+    arr = lambda ts: (ctypes.c_void_p * depth)(*[t.data_ptr() for t in ts])
+    with torch.cuda.device(x.device):
+        check(lib.pp_warpnet_pack_points(ptr(x), n, ptr(rows), stream()), "warpnet_pack_points")
+        check(lib.pp_warpnet_backward_packed(ptr(rows), ptr(g), 4 * n, None, depth, 128, arr(ws), arr(bs), arr(gws),
+                                             arr(gbs), ptr(work), stream()), "warpnet_backward")
+    gws[0] = gws[0][:, :3] + gws[0][:, 3:]          # the two halves of the doubled first layer
+    return gws, gbs
+
+
 class _RgbNet(torch.autograd.Function):
     """sigmoid(rgbnet(x)) with both directions on tcgen05; the backward recomputes the forward per tile."""
 

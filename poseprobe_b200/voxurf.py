@@ -79,7 +79,14 @@ class FusedVoxurf:
     def __init__(self, sdf, k0, rgbnet_weights, rgbnet_biases, xyz_min, xyz_max, stepsize=0.5, near=0.2, far=1e9,
                  bg=0.0, s_val=0.05, sdf_alpha=None, sdf_beta=None, posbase_pe=5, viewbase_pe=1, barf_c2f=None,
                  lr_sdf=0.1, lr_k0=0.1, lr_rgbnet=1e-3, betas=(0.9, 0.99), eps=1e-8, w_rgb=1.0,
-                 samples_per_ray_cap=None, pose_grad=False, voxel_size=None):
+                 samples_per_ray_cap=None, pose_grad=False, voxel_size=None, adam="reference", lr_warp=1e-3,
+                 w_entropy=0.0, w_mask=0.0, w_tv_k0=0.0, w_eikonal=0.0, w_deform=0.0):
+        """adam: "reference" = the optimiser the reference runs (dense Python Adam, lib/utils.py:176-198: every
+        element updated each step, eps after the bias correction) or "masked" = masked_adam_upd arithmetic
+        (adam_upd_kernel.cu:25-40: elements with a zero gradient are skipped, eps before the bias correction).
+        Loss weights of lib/losses.py:34-74 for `train_step`: w_rgb (weight_main), w_entropy (0.01 in the reference),
+        w_mask (weight_mask), w_tv_k0, w_eikonal (grad_constraint, 1.0) and w_deform (the dynamic weight of the three
+        deformation priors); `set_loss_weights` changes them between steps."""
         _need_cuda(sdf, "sdf")
         _need_cuda(k0, "k0")
         self.device = sdf.device
@@ -144,9 +151,17 @@ class FusedVoxurf:
         self.v_b = [torch.zeros_like(b) for b in self.biases]
         self.g_ab = torch.zeros(2, dtype=torch.float32, device=dev)
         self.hp = (betas[0], betas[1], lr_sdf, lr_k0, lr_rgbnet, eps)
+        if adam not in ("reference", "masked"):
+            raise ValueError("adam must be 'reference' or 'masked'")
+        self.adam_dense = adam == "reference"
+        self.lr_warp = lr_warp
         self.w_rgb = w_rgb
+        self.w_entropy, self.w_mask, self.w_tv_k0, self.w_eikonal, self.w_deform = (w_entropy, w_mask, w_tv_k0,
+                                                                                   w_eikonal, w_deform)
         self.step = 0
-        self.loss_buf = torch.zeros(2, dtype=torch.float32, device=dev)
+        # [0] weighted per-ray loss, [1] img_render (mse), [2] entropy, [3] mask BCE, [4] sum |k0 forward differences|
+        self.loss_buf = torch.zeros(8, dtype=torch.float32, device=dev)
+        self._scratch = torch.zeros(4, dtype=torch.float32, device=dev)
         self._cap_per_ray = samples_per_ray_cap
         self.pose_grad = bool(pose_grad)     # also emit d loss / d (rays_o, rays_d, viewdirs) (SE3 refinement)
         self.dx_cols = FEAT_COLS if self.pose_grad else DX_COLS
@@ -207,6 +222,8 @@ class FusedVoxurf:
                  "last": torch.empty(n_rays, dtype=torch.float32, device=dev),
                  "acc": torch.empty((n_rays, 3), dtype=torch.float32, device=dev),
                  "g_ray": torch.empty((n_rays, 3), dtype=torch.float32, device=dev),
+                 "g_cumw": torch.empty(n_rays, dtype=torch.float32, device=dev),
+                 "g_last": torch.empty(n_rays, dtype=torch.float32, device=dev),
                  "rgb": torch.empty((n_rays, 3), dtype=torch.float32, device=dev),
                  "counter": torch.zeros(2, dtype=torch.int32, device=dev)}
             self._bufs = b
@@ -218,8 +235,34 @@ class FusedVoxurf:
         deform_net.py:12-29; ``out_range`` = range_shape.max()).  `render` then follows Voxurf.inference
         (voxurf_coarse.py:1093-1215): SDF and normal of every sample come from the warped template lookup."""
         from .ops import warpnet_params
-        ws, bs = warpnet_params([w.to(self.device) for w in weights], [b.to(self.device) for b in biases])
+        dev = self.device
+        same = (self.warp is not None and len(self.warp_w) == len(weights) and
+                all(a.shape == b.shape for a, b in zip(self.warp_w, weights)))
+        if same:       # keep the optimiser state, refresh the values
+            for dst, src in zip(self.warp_w + self.warp_b, list(weights) + list(biases)):
+                dst.copy_(src.detach())
+        else:
+            self.warp_w = [w.detach().to(dev).float().contiguous().clone() for w in weights]      # nn.Linear layouts
+            self.warp_b = [b.detach().to(dev).float().contiguous().clone() for b in biases]
+            self.m_warp = [torch.zeros_like(t) for t in self.warp_w + self.warp_b]
+            self.v_warp = [torch.zeros_like(t) for t in self.warp_w + self.warp_b]
+        ws, bs = warpnet_params(self.warp_w, self.warp_b)        # first layer doubled: [128, 6]
         self.warp = (ws, bs, float(out_range))
+        if not same:
+            self.g_ww = [torch.zeros_like(w) for w in ws]
+            self.g_wb = [torch.zeros_like(b) for b in bs]
+            self._warp_work = torch.zeros(int(lib.pp_warpnet_backward_workspace_bytes()), dtype=torch.uint8, device=dev)
+
+    def set_loss_weights(self, **kw):
+        for k, v in kw.items():
+            if k not in ("w_rgb", "w_entropy", "w_mask", "w_tv_k0", "w_eikonal", "w_deform"):
+                raise KeyError(k)
+            setattr(self, k, float(v))
+
+    def warp_gradients(self):
+        """([dW_l], [db_l]) of the accumulated deformation-network gradients, nn.Linear layouts."""
+        g0 = self.g_ww[0][:, :3] + self.g_ww[0][:, 3:]
+        return [g0] + [g.clone() for g in self.g_ww[1:]], [g.clone() for g in self.g_wb]
 
     def _march_deform(self, b, rays_o, rays_d, viewdirs, jitter, depth=None, normal=None, keep_points=False):
         n, cap = rays_o.shape[0], b["cap"]
@@ -294,9 +337,9 @@ class FusedVoxurf:
         return c[0]
 
     # ---- training -----------------------------------------------------------------------------------------------
-    def backward_only(self, rays_o, rays_d, viewdirs, target, jitter=None):
-        """march -> MLP -> loss -> MLP backward -> reverse march.  Accumulates into the gradient buffers and
-        loss_buf ([w_rgb * mse, mse]); no parameter changes."""
+    def backward_only(self, rays_o, rays_d, viewdirs, target, jitter=None, mask=None):
+        """march -> MLP -> per-ray object losses (lib/losses.py:34-74: photometric, entropy, mask BCE) -> MLP backward
+        -> reverse march.  Accumulates into the gradient buffers and loss_buf; no parameter changes."""
         for t, nme in ((rays_o, "rays_o"), (rays_d, "rays_d"), (viewdirs, "viewdirs"), (target, "target")):
             _need_cuda(t, nme)
         n = rays_o.shape[0]
@@ -304,9 +347,7 @@ class FusedVoxurf:
         with torch.cuda.device(self.device):
             self._march(b, rays_o, rays_d, viewdirs, jitter)
             self._mlp_forward(b, n)
-            check(lib.pp_voxurf_ray_loss(n, ptr(b["acc"]), ptr(b["cum_w"]), ptr(target), self.scene.bg, self.w_rgb,
-                                         ptr(b["g_ray"]), ptr(b["rgb"]), ptr(self.loss_buf), stream()),
-                  "voxurf_ray_loss")
+            self._object_loss(b, n, target, mask)
             check(lib.pp_rgbnet_backward_fused(ptr(b["feat"]), b["cap"], ptr(b["counter"]), self.d0, self.depth, 128,
                                                self._arr(self.weights), self._arr(self.biases), ptr(b["w"]),
                                                ptr(b["rid"]), ptr(b["g_ray"]), ptr(b["gw"]), ptr(b["dx"]),
@@ -316,35 +357,56 @@ class FusedVoxurf:
                                          ptr(viewdirs), ptr(jitter), n, ptr(b["rec"]), ptr(b["gw"]), ptr(b["dx"]),
                                          self.dx_cols, ptr(b["ray_off"]), ptr(b["ray_cnt"]), ptr(b["ray_end"]),
                                          ptr(b["g_ray"]), ptr(self.g_srec), ptr(self.g_k0rec), ptr(self.srec),
-                                         ptr(self.k0rec), ptr(b["grad_rays"]), ptr(b["grad_view"]), None, None,
-                                         stream()), "voxurf_backward")
+                                         ptr(self.k0rec), ptr(b["grad_rays"]), ptr(b["grad_view"]), ptr(b["g_cumw"]),
+                                         ptr(b["g_last"]), stream()), "voxurf_backward")
         return b["rgb"][:n]
 
-    def backward_deform_pieces(self, rays_o, rays_d, viewdirs, target, jitter=None, reg_weights=(0.0, 0.0, 0.0, 0.0)):
-        """Training through the implicit deformation (forward(use_deform=True), voxurf_coarse.py:958-985), every stage
-        except the backward of the warp network itself: deform march -> rgbnet -> loss -> rgbnet
-        backward (rgbnet / feature-grid gradients accumulate as in `backward_only`) -> reverse march writing
-        {dL/d sdf_final, dL/d gradient} per sample -> per-sample backward of the warped lookup + the regularisers of
-        deform_implicit_loss (reg_weights = weights of grad_constraint, grad_deform_constraint, sdf_correct_constraint,
-        sdf_deform_constraint, lib/losses.py:6-24).  Leaves in the buffers: ``g_dout`` fp32 [4 * samples, 4] = the
-        gradient w.r.t. the warp network's outputs (value row + three tangent rows per sample), ``g_pts`` [samples, 3],
-        ``reg`` (the four unweighted term values)."""
+    def _object_loss(self, b, n, target, mask):
+        check(lib.pp_voxurf_object_loss(n, ptr(b["acc"]), ptr(b["cum_w"]), ptr(b["last"]), ptr(target), ptr(mask),
+                                        self.scene.bg, self.w_rgb, self.w_entropy, self.w_mask, ptr(b["g_ray"]),
+                                        ptr(b["g_cumw"]), ptr(b["g_last"]), ptr(b["rgb"]), ptr(self.loss_buf),
+                                        ptr(self._scratch), stream()), "voxurf_object_loss")
+
+    def forward_sums_deform(self, rays_o, rays_d, viewdirs, jitter=None, want_samples=False):
+        """Deform branch of `forward_sums`: -> (rgb_acc, cum_weights, alphainv_last); with want_samples also the
+        per-sample entries of ALL in-box samples (b["sout"] fp32 [cap,16], see pp_voxurf_deform_sample_forward)."""
         if self.warp is None:
-            raise RuntimeError("backward_deform_pieces needs set_warp_network first")
-        for t, nme in ((rays_o, "rays_o"), (rays_d, "rays_d"), (viewdirs, "viewdirs"), (target, "target")):
-            _need_cuda(t, nme)
+            raise RuntimeError("the deformation branch needs set_warp_network first")
         n = rays_o.shape[0]
         b = self._buffers(n)
-        cap = b["cap"]
         with torch.cuda.device(self.device):
             self._march_deform(b, rays_o, rays_d, viewdirs, jitter, keep_points=True)
             self._mlp_forward(b, n)
-            check(lib.pp_voxurf_ray_loss(n, ptr(b["acc"]), ptr(b["cum_w"]), ptr(target), self.scene.bg, self.w_rgb,
-                                         ptr(b["g_ray"]), ptr(b["rgb"]), ptr(self.loss_buf), stream()),
-                  "voxurf_ray_loss")
+            if want_samples:
+                if "sout" not in b:
+                    b["sout"] = torch.empty((b["cap"], 16), dtype=torch.float32, device=self.device)
+                check(lib.pp_voxurf_deform_sample_forward(ctypes.byref(self.scene), ptr(self.srec), ptr(b["dpts"]),
+                                                          ptr(b["dout"]), ptr(b["dcounter"]), b["cap"], self.warp[2],
+                                                          ptr(b["sout"]), None, stream()),
+                      "voxurf_deform_sample_forward")
+        return b["acc"][:n], b["cum_w"][:n], b["last"][:n]
+
+    def backward_deform_from_ray_grads(self, rays_o, rays_d, viewdirs, g_acc, g_cumw, g_last, jitter=None,
+                                       reg_weights=(0.0, 0.0, 0.0, 0.0), ext_grad=None):
+        """Back-propagate d loss / d (rgb_acc, cum_weights, alphainv_last) of the last `forward_sums_deform` (+ the
+        regularisers of deform_implicit_loss with `reg_weights` = weights of grad_constraint, grad_deform_constraint,
+        sdf_correct_constraint, sdf_deform_constraint, lib/losses.py:6-24; + ext_grad fp32 [cap,14], the gradient of
+        an external loss w.r.t. the per-sample entries) through the whole deformation branch
+        (voxurf_coarse.py:958-985): rgbnet backward -> reverse march writing {dL/d sdf_final, dL/d gradient} per
+        sample -> per-sample backward of the warped lookup -> tcgen05 backward of the deformation network.
+        Accumulates into the rgbnet / feature-grid / deformation-network gradient buffers; the SDF grid is frozen in
+        this mode (:136-138).  Leaves ``g_dout`` (gradient w.r.t. the network's outputs), ``g_pts`` [samples,3] and
+        ``reg`` (the four unweighted terms) in the buffers; with pose_grad the ray gradients are complete
+        (`ray_gradients`)."""
+        n = rays_o.shape[0]
+        b = self._bufs
+        cap = b["cap"]
+        g_acc = g_acc.contiguous()
+        ws, bs, out_range = self.warp
+        with torch.cuda.device(self.device):
             check(lib.pp_rgbnet_backward_fused(ptr(b["feat"]), cap, ptr(b["counter"]), self.d0, self.depth, 128,
                                                self._arr(self.weights), self._arr(self.biases), ptr(b["w"]),
-                                               ptr(b["rid"]), ptr(b["g_ray"]), ptr(b["gw"]), ptr(b["dx"]),
+                                               ptr(b["rid"]), ptr(g_acc), ptr(b["gw"]), ptr(b["dx"]),
                                                self.dx_cols, self._arr(self.g_w), self._arr(self.g_b), stream()),
                   "rgbnet_backward_fused")
             if "g_val" not in b:
@@ -358,16 +420,45 @@ class FusedVoxurf:
             check(lib.pp_voxurf_backward_deform(ctypes.byref(self.scene), ctypes.byref(self.cfg), ptr(rays_o),
                                                 ptr(rays_d), ptr(viewdirs), ptr(jitter), n, ptr(b["rec"]),
                                                 ptr(b["gw"]), ptr(b["dx"]), self.dx_cols, ptr(b["ray_off"]),
-                                                ptr(b["ray_cnt"]), ptr(b["ray_end"]), ptr(b["g_ray"]),
-                                                ptr(self.g_k0rec), None, None, ptr(b["g_val"]), ptr(b["dray_off"]),
-                                                stream()), "voxurf_backward_deform")
+                                                ptr(b["ray_cnt"]), ptr(b["ray_end"]), ptr(g_acc),
+                                                ptr(self.g_k0rec), ptr(g_cumw.contiguous()) if g_cumw is not None else None,
+                                                ptr(g_last.contiguous()) if g_last is not None else None,
+                                                ptr(b["g_val"]), ptr(b["dray_off"]), ptr(self.srec), ptr(self.k0rec),
+                                                ptr(b["grad_rays"]), ptr(b["grad_view"]), stream()),
+                  "voxurf_backward_deform")
             w = [float(x) for x in reg_weights]
             check(lib.pp_voxurf_deform_sample_backward(ctypes.byref(self.scene), ptr(self.srec), ptr(b["dpts"]),
                                                        ptr(b["dout"]), ptr(b["g_val"]), ptr(b["dcounter"]), cap,
-                                                       self.warp[2], w[0], w[1], w[2], w[3], ptr(b["g_dout"]),
-                                                       ptr(b["g_pts"]), ptr(b["reg"]), stream()),
+                                                       out_range, w[0], w[1], w[2], w[3], ptr(b["g_dout"]),
+                                                       ptr(b["g_pts"]), ptr(b["reg"]), ptr(ext_grad), stream()),
                   "voxurf_deform_sample_backward")
+            if self.pose_grad:
+                check(lib.pp_voxurf_deform_ray_grad(ctypes.byref(self.scene), ptr(rays_o), ptr(rays_d), ptr(jitter), n,
+                                                    ptr(b["dray_off"]), ptr(b["g_pts"]), ptr(b["grad_rays"]),
+                                                    stream()), "voxurf_deform_ray_grad")
+            check(lib.pp_warpnet_backward_packed(ptr(b["drows"]), ptr(b["g_dout"]), 4 * cap, ptr(b["dcounter"][2:]),
+                                                 len(ws), 128, self._arr(ws), self._arr(bs), self._arr(self.g_ww),
+                                                 self._arr(self.g_wb), ptr(self._warp_work), stream()),
+                  "warpnet_backward")
+
+    def backward_deform(self, rays_o, rays_d, viewdirs, target, jitter=None, mask=None, reg_weights=None):
+        """The reference's live train step up to the optimiser (lib/recon_scene.py:603-606, :649): forward through the
+        implicit deformation, the per-ray object losses (w_rgb / w_entropy / w_mask), the per-sample regularisers
+        (reg_weights, default (w_eikonal, w_deform, w_deform, w_deform)), full backward.  Returns rgb_marched."""
+        for t, nme in ((rays_o, "rays_o"), (rays_d, "rays_d"), (viewdirs, "viewdirs"), (target, "target")):
+            _need_cuda(t, nme)
+        if reg_weights is None:
+            reg_weights = (self.w_eikonal, self.w_deform, self.w_deform, self.w_deform)
+        n = rays_o.shape[0]
+        self.forward_sums_deform(rays_o, rays_d, viewdirs, jitter)
+        b = self._bufs
+        with torch.cuda.device(self.device):
+            self._object_loss(b, n, target, mask)
+        self.backward_deform_from_ray_grads(rays_o, rays_d, viewdirs, b["g_ray"], b["g_cumw"], b["g_last"], jitter,
+                                            reg_weights)
         return b["rgb"][:n]
+
+    backward_deform_pieces = backward_deform
 
     # ---- autograd-facing pieces (used by the Voxurf module below) ---------------------------------------------
     def load_params(self, sdf, k0, weights, biases, sdf_alpha=None, sdf_beta=None):
@@ -441,7 +532,7 @@ class FusedVoxurf:
         with torch.cuda.device(self.device):
             check(lib.pp_voxurf_sdf_adam(ctypes.byref(self.scene), ctypes.byref(self.cfg), ptr(self.sdf),
                                          ptr(self.g_srec), None, None, 1, 0.9, 0.99, 0.0, 1e-8, ptr(g_sdf),
-                                         ptr(self.g_ab), stream()), "voxurf_sdf_adam")
+                                         ptr(self.g_ab), 0, stream()), "voxurf_sdf_adam")
             g_k0 = torch.empty((1, 12) + self.world, dtype=torch.float32, device=self.device)
             check(lib.pp_voxurf_k0_unpack(ptr(self.g_k0rec), self.n_voxels, ptr(g_k0), stream()), "k0_unpack")
         gw0 = torch.zeros((128, self.d0_ref), dtype=torch.float32, device=self.device)
@@ -450,30 +541,61 @@ class FusedVoxurf:
         return g_sdf.reshape((1, 1) + self.world), g_k0, [gw0] + [g.clone() for g in self.g_w[1:]], \
             [g.clone() for g in self.g_b]
 
-    def optimizer_step(self):
+    def _k0_tv(self):
+        if self.w_tv_k0 > 0:
+            check(lib.pp_voxurf_k0_tv(ctypes.byref(self.scene), ptr(self.k0rec), ptr(self.g_k0rec), self.w_tv_k0,
+                                      ptr(self.loss_buf[4:]), stream()), "voxurf_k0_tv")
+
+    def optimizer_step(self, deform=False):
+        """Adam on everything that has a gradient.  deform=True: the live configuration of the reference (SDF grid
+        frozen, voxurf_coarse.py:136-138; feature grid, rgbnet and deformation network trained)."""
         b1, b2, lr_sdf, lr_k0, lr_net, eps = self.hp
         self.step += 1
+        dense = 1 if self.adam_dense else 0
+        mode = 3 if self.adam_dense else 0
         with torch.cuda.device(self.device):
             s = stream()
-            check(lib.pp_voxurf_sdf_adam(ctypes.byref(self.scene), ctypes.byref(self.cfg), ptr(self.sdf),
-                                         ptr(self.g_srec), ptr(self.m_sdf), ptr(self.v_sdf), self.step, b1, b2,
-                                         lr_sdf, eps, None, ptr(self.g_ab), s), "voxurf_sdf_adam")
-            self.g_srec.zero_()
-            check(lib.pp_voxurf_build_records(ctypes.byref(self.scene), ctypes.byref(self.cfg), ptr(self.sdf),
-                                              ptr(self.srec), s), "voxurf_build_records")
-            # feature records: masked Adam over 3 V float4 records, gradient reset fused
+            if not deform:
+                check(lib.pp_voxurf_sdf_adam(ctypes.byref(self.scene), ctypes.byref(self.cfg), ptr(self.sdf),
+                                             ptr(self.g_srec), ptr(self.m_sdf), ptr(self.v_sdf), self.step, b1, b2,
+                                             lr_sdf, eps, None, ptr(self.g_ab), dense, s), "voxurf_sdf_adam")
+                self.g_srec.zero_()
+                check(lib.pp_voxurf_build_records(ctypes.byref(self.scene), ctypes.byref(self.cfg), ptr(self.sdf),
+                                                  ptr(self.srec), s), "voxurf_build_records")
+            # feature records: Adam over 3 V float4 records, gradient reset fused
             check(lib.pp_voxel_adam(ptr(self.k0rec), ptr(self.g_k0rec), ptr(self.m_k0), ptr(self.v_k0),
-                                    3 * self.n_voxels, self.step, b1, b2, lr_k0, lr_k0, eps, 1, s), "voxel_adam")
+                                    3 * self.n_voxels, self.step, b1, b2, lr_k0, lr_k0, eps, 1 | (2 * dense), s),
+                  "voxel_adam")
             for p, g, m, v in zip(self.weights + self.biases, self.g_w + self.g_b, self.m_w + self.m_b,
                                   self.v_w + self.v_b):
-                check(lib.pp_adam_upd(0, 0, ptr(p), ptr(g), ptr(m), ptr(v), None, p.numel(), self.step, b1, b2,
+                check(lib.pp_adam_upd(0, mode, ptr(p), ptr(g), ptr(m), ptr(v), None, p.numel(), self.step, b1, b2,
                                       lr_net, eps, s), "adam_upd")
                 g.zero_()
+            if deform:
+                gws, gbs = self.warp_gradients()
+                for p, g, m, v in zip(self.warp_w + self.warp_b, gws + gbs, self.m_warp, self.v_warp):
+                    g = g.contiguous()
+                    check(lib.pp_adam_upd(0, mode, ptr(p), ptr(g), ptr(m), ptr(v), None, p.numel(), self.step, b1,
+                                          b2, self.lr_warp, eps, s), "adam_upd")
+                self.warp[0][0].copy_(torch.cat([self.warp_w[0], self.warp_w[0]], dim=1))
+                for dst, src in zip(self.warp[0][1:] + self.warp[1], self.warp_w[1:] + self.warp_b):
+                    if dst.data_ptr() != src.data_ptr():
+                        dst.copy_(src)
+                for g in self.g_ww + self.g_wb:
+                    g.zero_()
+            self.g_ab.zero_()
 
-    def train_step(self, rays_o, rays_d, viewdirs, target, jitter=None):
+    def train_step(self, rays_o, rays_d, viewdirs, target, jitter=None, use_deform=False, mask=None):
+        """One optimisation step; returns loss_buf ([0] weighted per-ray loss, [1] photometric MSE, [2] entropy,
+        [3] mask BCE, [4] k0 TV sum).  use_deform=True is the reference's live step (recon_scene.py:603)."""
         self.loss_buf.zero_()
-        self.backward_only(rays_o, rays_d, viewdirs, target, jitter)
-        self.optimizer_step()
+        if use_deform:
+            self.backward_deform(rays_o, rays_d, viewdirs, target, jitter, mask)
+        else:
+            self.backward_only(rays_o, rays_d, viewdirs, target, jitter, mask)
+        with torch.cuda.device(self.device):
+            self._k0_tv()
+        self.optimizer_step(deform=use_deform)
         return self.loss_buf
 
     # ---- checkpoints ----------------------------------------------------------------------------------------------

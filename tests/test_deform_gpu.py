@@ -270,7 +270,7 @@ def test_render_deform_edge_cases(cuda):
 
 
 def test_deform_backward_pieces(cuda):
-    """Training through the deformation, every stage except the warp network's own backward:
+    """Training through the deformation, stage by stage (the network's own backward: test_warpnet_backward):
     (a) the reverse march's per-sample {dL/d sdf_final, dL/d gradient} against autograd through the oracle's deform
         branch (the rgbnet in between runs on bf16 operands: direction / norm);
     (b) the per-sample backward of the warped lookup + regularisers (voxurf_deform_sample_backward_kernel) against the
@@ -312,6 +312,7 @@ def test_deform_backward_pieces(cuda):
     sdf2, grad2, A, sd2, c2, cache = da.lookup_forward(grid, pts, y, Jt, R, MN, MX)
     _, G_g, G_A, G_c, G_d = da.regulariser_grads(grad2, A, c2, sd2, *wreg)
     G_y, G_Jt, G_x = da.lookup_backward(cache, g_val[:, 0], g_val[:, 1:] + G_g, G_A, G_c, G_d)
+    G_x = G_x + torch.einsum("mik,mk->mi", Jt, G_y)      # + J^T G_y: through the network's value row
     want_dout = torch.cat([G_y[:, None, :], G_Jt], 1)
     assert rel(g_dout, want_dout) < 2e-3, rel(g_dout, want_dout)
     assert rel(g_dout[:, 0], want_dout[:, 0]) < 2e-3 and rel(g_dout[:, 1:], want_dout[:, 1:]) < 2e-3
@@ -350,3 +351,157 @@ def test_deform_backward_pieces(cuda):
     with torch.cuda.device(cuda):
         check(lib.pp_voxurf_k0_unpack(ptr(eng.g_k0rec), eng.n_voxels, ptr(g_k0), stream()), "k0_unpack")
     assert cos(g_k0.cpu(), g_k0_ref) > 0.99
+
+
+def _emulated_rows_backward(x, ws, bs, G_y, G_Jt):
+    """oracle/deform_analytic.py::warp_rows_backward on the kernel's numerics: fp16 operands (weights, activations,
+    tangents, x = x_hi + x_lo), fp32 accumulation, gates from the value row."""
+    from oracle import deform_analytic as da
+    hi = bf(x)
+    xs = hi + bf(x - hi)
+    wq = [bf(w) for w in ws]
+    h, T, acts = xs, torch.eye(3).expand(x.shape[0], 3, 3), []
+    for w, b in zip(wq[:-1], bs[:-1]):
+        z = h @ w.T + b
+        gate = (bf(z) > 0).float()
+        acts.append((h, T, gate))
+        h = bf(torch.relu(z))
+        T = bf(gate[:, None, :] * (T @ w.T))
+    acts.append((h, T, None))
+    return da.warp_rows_backward(wq, acts, G_y, G_Jt)
+
+
+@pytest.mark.parametrize("n,gscale", [(4096, 1.0), (1000, 1e-7), (33, 3e3)])
+def test_warpnet_backward(cuda, n, gscale):
+    """pp_warpnet_backward_packed (csrc/warp_bwd.cu) against the closed-form four-row backward of
+    oracle/deform_analytic.py (which tests/test_voxurf_cpu.py pins against autograd's double backward): every dW_l and
+    db_l.  Tolerances: 1e-2 relative (Frobenius) against the fp16-operand emulation (measured ~2e-3: fp16 rounding of
+    the dZ tiles), 8e-2 against plain fp32 (gate flips of samples within rounding of a ReLU kink, as in the forward
+    test).  gscale exercises the power-of-two loss scale (gradients far below / above fp16's range)."""
+    from oracle import deform_analytic as da
+    from poseprobe_b200 import ops
+    from poseprobe_b200._lib import lib
+    ws, bs = make_warp(91, last_scale=0.05)
+    torch.manual_seed(n)
+    x = torch.rand(n, 3) * 2 - 1
+    G = gscale * torch.randn(n, 4, 4) * torch.rand(n, 1, 1)
+    G[:, 1:, :] *= 0.3
+    gws, gbs = ops.warpnet_backward(x.to(cuda), [w.to(cuda) for w in ws], [b.to(cuda) for b in bs], G.to(cuda))
+    torch.cuda.synchronize()
+    assert lib.pp_warpnet_backward_stalled() == 0
+    G_y, G_Jt = G[:, 0, :], G[:, 1:, :]
+    _, _, acts = da.warp_rows_forward(x, ws, bs)
+    want_w, want_b, _ = da.warp_rows_backward(ws, acts, G_y, G_Jt)
+    emu_w, emu_b, _ = _emulated_rows_backward(x, ws, bs, G_y, G_Jt)
+
+    def rel(p, q):
+        return float((p - q).norm() / (q.norm() + 1e-30))
+
+    for l in range(5):
+        assert gws[l].shape == ws[l].shape and gbs[l].shape == bs[l].shape
+        assert rel(gws[l].cpu(), emu_w[l]) < 1e-2, ("dW", l, rel(gws[l].cpu(), emu_w[l]))
+        assert rel(gbs[l].cpu(), emu_b[l]) < 1e-2, ("db", l, rel(gbs[l].cpu(), emu_b[l]))
+        if n >= 1000:      # (with a few dozen samples one flipped gate is a visible fraction of the sum)
+            assert rel(gws[l].cpu(), want_w[l]) < 8e-2, ("dW fp32", l, rel(gws[l].cpu(), want_w[l]))
+            assert rel(gbs[l].cpu(), want_b[l]) < 8e-2, ("db fp32", l, rel(gbs[l].cpu(), want_b[l]))
+
+
+def _golden_engine(cuda, g, **extra):
+    import numpy as np
+    from poseprobe_b200 import voxurf
+    t = lambda k: torch.from_numpy(g[k])  # noqa: E731
+    sdf = t("sdf")
+    k0 = torch.from_numpy(g["k0"].astype(np.float32))
+    rw, rb = [t("w%d" % i) for i in range(3)], [t("b%d" % i) for i in range(3)]
+    ww, wb = [t("ww%d" % i) for i in range(5)], [t("wb%d" % i) for i in range(5)]
+    eng = voxurf.FusedVoxurf(sdf.to(cuda), k0.to(cuda), [w.to(cuda) for w in rw], [b.to(cuda) for b in rb], MN, MX,
+                             stepsize=0.5, s_val=float(g["s_val"]), bg=0.3, posbase_pe=5, viewbase_pe=1,
+                             barf_c2f=(0.1, 0.5), sdf_alpha=10.0, sdf_beta=0.35, voxel_size=float(g["voxel_size"]),
+                             pose_grad=True, **extra)
+    eng.set_schedule(progress=float(g["gstep"]) / float(g["N_iters"]))
+    eng.set_warp_network(ww, wb, float(g["out_range"]))
+    return eng, t
+
+
+def test_deform_training_gradients_vs_reference_golden(cuda):
+    """The reference's live train step (recon_scene.py:603: Voxurf.forward(use_deform=True) -> loss -> backward) on the
+    fused kernels against tests/golden/voxurf_deform.npz = the reference's OWN forward, deform_implicit_loss and
+    autograd double backward executed on the CPU (tests/golden/make_golden_deform.py): the loss and every gradient -
+    deformation network (tcgen05 backward, csrc/warp_bwd.cu), rgbnet, feature grid, rays.
+    Bars: cosine >= 0.999 and norm within 1 % for the feature grid, the colour network and the deformation network's
+    weights; the ray gradients (sums over ~30 samples each, a few of which sit on a gate that fp16 flips) cosine >= 0.99."""
+    import os
+    import numpy as np
+    from poseprobe_b200._lib import lib
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "voxurf_deform.npz"))
+    eng, t = _golden_engine(cuda, g)
+    o, d, v = t("rays_o").to(cuda), t("rays_d").to(cuda), t("viewdirs").to(cuda)
+    N = o.shape[0]
+    eng.loss_buf.zero_()
+    eng.backward_deform(o, d, v, t("target").to(cuda), jitter=t("jitter").to(cuda), reg_weights=(1.0, 0.05, 0.05, 0.05))
+    torch.cuda.synchronize()
+    assert lib.pp_warpnet_backward_stalled() == 0 and lib.pp_rgbnet_backward_stalled() == 0
+    b = eng._bufs
+    M = b["dcounter"].tolist()[0]
+    assert M == g["ret_weights"].shape[0] and b["dcounter"].tolist()[1] == 0
+    reg = b["reg"].cpu()
+    for i, k in enumerate(("grad_constraint", "grad_deform_constraint", "sdf_correct_constraint", "sdf_deform_constraint")):
+        assert abs(float(reg[i]) - float(g["term_" + k])) < 2e-3 * max(1.0, abs(float(g["term_" + k]))), (k, float(reg[i]))
+    loss = float(eng.loss_buf[0]) + float(reg[0]) + 0.05 * float(reg[1] + reg[2] + reg[3])
+    assert abs(loss - float(g["loss"])) < 1e-2 * float(g["loss"]), (loss, float(g["loss"]))
+
+    def cos(p, q):
+        return float((p * q).sum() / (p.norm() * q.norm() + 1e-30))
+
+    def check(name, got, want, c_min=0.999, n_tol=0.01):
+        got, want = got.detach().cpu().reshape(-1), want.reshape(-1)
+        c, r = cos(got, want), float(got.norm() / (want.norm() + 1e-30))
+        assert c >= c_min and abs(r - 1) <= n_tol, (name, c, r)
+
+    gww, gwb = eng.warp_gradients()
+    for i in range(5):
+        check("warp weight %d" % i, gww[i], t("g_ww%d" % i))
+        check("warp bias %d" % i, gwb[i], t("g_wb%d" % i), c_min=0.998, n_tol=0.02)
+    _, g_k0, g_w, g_b = eng.grid_gradients()
+    for i in range(3):
+        check("rgbnet weight %d" % i, g_w[i], t("g_w%d" % i))
+        check("rgbnet bias %d" % i, g_b[i], t("g_b%d" % i))
+    want_k0 = torch.zeros(g_k0.numel())
+    want_k0[torch.from_numpy(g["g_k0_idx"]).long()] = t("g_k0_val")
+    check("k0", g_k0, want_k0)
+    g_rays, _ = eng.ray_gradients()
+    check("rays_o", g_rays[:N, :3], t("g_rays_o"), c_min=0.99, n_tol=0.03)
+    check("rays_d", g_rays[:N, 3:], t("g_rays_d"), c_min=0.99, n_tol=0.03)
+
+
+def test_deform_train_step_reduces_the_live_loss(cuda):
+    """FusedVoxurf.train_step(use_deform=True) with the reference's full object loss (lib/losses.py:34-74: photometric
+    with mask, entropy, mask BCE, k0 TV, Eikonal over all in-box samples, the three deformation priors) and its
+    optimiser (dense Python Adam): the loss goes down, the SDF grid stays frozen, the deformation network, the feature
+    grid and the rgbnet move."""
+    import os
+    import numpy as np
+    from poseprobe_b200._lib import lib
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "voxurf_deform.npz"))
+    eng, t = _golden_engine(cuda, g, w_rgb=1.0, w_entropy=0.01, w_mask=0.1, w_tv_k0=0.01, w_eikonal=1.0, w_deform=0.05,
+                            lr_k0=0.05, lr_rgbnet=1e-3, lr_warp=1e-3)
+    o, d, v = t("rays_o").to(cuda), t("rays_d").to(cuda), t("viewdirs").to(cuda)
+    target = t("target").to(cuda)
+    mask = (torch.rand(o.shape[0], device=cuda) > 0.3).float()
+    sdf0, k0_0 = eng.sdf.clone(), eng.k0rec.clone()
+    w0 = [w.clone() for w in eng.warp_w]
+    r0 = eng.weights[1].clone()
+    losses = []
+    for _ in range(12):
+        lb = eng.train_step(o, d, v, target, use_deform=True, mask=mask)
+        reg = eng._bufs["reg"]
+        losses.append(float(lb[0]) + float(reg[0]) + 0.05 * float(reg[1] + reg[2] + reg[3]))
+    torch.cuda.synchronize()
+    assert lib.pp_warpnet_backward_stalled() == 0
+    assert all(np.isfinite(losses)) and losses[-1] < 0.9 * losses[0], losses
+    assert torch.equal(eng.sdf, sdf0)                                     # frozen (voxurf_coarse.py:136-138)
+    assert float((eng.k0rec - k0_0).abs().max()) > 0 and float((eng.weights[1] - r0).abs().max()) > 0
+    assert all(float((a - b).abs().max()) > 0 for a, b in zip(eng.warp_w, w0))
+    assert float(lb[4]) > 0                                               # the k0 TV term was evaluated
+    # the kernel-side copy of the doubled first layer follows the master weights
+    torch.testing.assert_close(eng.warp[0][0], torch.cat([eng.warp_w[0], eng.warp_w[0]], 1))
