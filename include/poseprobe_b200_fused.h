@@ -141,7 +141,12 @@ PP_API int64_t pp_voxel_shard_size(int64_t n_voxels, int32_t world);
 PP_API int pp_voxel_adam_exchange(void* const* vox_ptrs, void* const* grad_ptrs, void* exp_avg,
                                   void* exp_avg_sq, int64_t n_voxels, int32_t world, int32_t rank,
                                   int32_t step, float beta1, float beta2, float lr_density,
-                                  float lr_k0, float eps, pp_stream_t stream);
+                                  float lr_k0, float eps, const void* sync_block, pp_stream_t stream);
+/* A barrier wait that runs out of its budget (~60 s: a peer died or stalled) raises a STICKY flag in this rank's sync
+ * block instead of hanging the device; from then on the exchange kernels leave parameters and moments untouched
+ * (sync_block = this rank's block, nullable = no check; the NVLS variant reads it from sync_ptrs) and the summed
+ * payload (the global loss) is NaN.  pp_peer_sync_timed_out reads the flag (synchronises): 1 = timed out. */
+PP_API int pp_peer_sync_timed_out(const void* sync_block);
 
 /* NVSwitch (NVLS) variant of pp_voxel_adam_exchange: vox_mc / grad_mc are MULTICAST addresses bound to every
  * rank's parameter / gradient records (e.g. torch symmetric memory's multicast_ptr).  The gradient slice is
@@ -207,14 +212,17 @@ PP_API int pp_voxurf_march_features(const pp_dvgo_scene* scene, const pp_voxurf_
  * order) and the warp network's input rows: rows fp16 [4 * sample_capacity, 16]; warp_ray_off [N] (first slot of
  * the ray, -1 if it did not fit); counter: 4 x int32 on the device: [0] samples, [1] overflow flag, [2] rows = 4 *
  * samples (pass &counter[2] to pp_warpnet_forward_packed as its device row count); sample_pts (nullable): float4
- * [sample_capacity] = the sample positions, kept for pp_voxurf_deform_sample_backward.
+ * [sample_capacity] = the sample positions, kept for pp_voxurf_deform_sample_backward.  rows may be null when only
+ * the enumeration (warp_ray_off, counter, sample_pts) is wanted.  warp_ray_cnt (nullable) [N]: in-box samples per ray
+ * (runs are handed out in completion order, so the reference's ray-major sample order is offset + count per ray).
  * pp_voxurf_march_features_deform: pp_voxurf_march_features with the SDF value / normal of every sample taken from
  * the warped lookup: warp_out = the network's fp32 [rows,4] output.  The template SDF is read with the arithmetic of
  * the reference's custom sampler (weights from the unclamped floor, clamped corner indices, :545-659) and its
  * analytic gradient is chained through the warp Jacobian - the closed form of the reference's autograd.grad. */
 PP_API int pp_voxurf_deform_rows(const pp_dvgo_scene* scene, const float* rays_o, const float* rays_d,
                                  const float* jitter, int64_t n_rays, int32_t sample_capacity, void* rows,
-                                 int32_t* warp_ray_off, int32_t* counter, void* sample_pts, pp_stream_t stream);
+                                 int32_t* warp_ray_off, int32_t* counter, void* sample_pts,
+                                 int32_t* warp_ray_cnt, pp_stream_t stream);
 PP_API int pp_voxurf_march_features_deform(const pp_dvgo_scene* scene, const pp_voxurf_cfg* cfg,
                                            const void* sdf_records, const void* k0_records, const float* rays_o,
                                            const float* rays_d, const float* viewdirs, const float* jitter,
@@ -266,6 +274,20 @@ PP_API int pp_voxurf_deform_sample_forward(const pp_dvgo_scene* scene, const voi
                                            const float* warp_out, const int32_t* n_samples_ptr,
                                            int64_t sample_capacity, float out_range, float* sample_out,
                                            float* reg_terms, pp_stream_t stream);
+/* Non-deform branch, per-sample entries of ALL in-box samples (the reference's `gradient` [M,3], voxurf_coarse.py:
+ * 986-989, :1082, on which lib/losses.py:7-10 puts the live Eikonal term): sample_pts = the list
+ * pp_voxurf_deform_rows writes (rows may be null there: only the enumeration is wanted).
+ * pp_voxurf_sample_records: sample_rec_out float4 [samples] = interpolated {s', d s'/dx, d s'/dy, d s'/dz}.
+ * pp_voxurf_sample_records_backward: grad_sdf_records += scatter of grad_sample_rec (float4 [samples], nullable) plus
+ * the built-in Eikonal gradient w_eikonal * d mean|‖gradient‖ - 1|; eikonal_term (nullable, accumulated) += the
+ * unweighted term. */
+PP_API int pp_voxurf_sample_records(const pp_dvgo_scene* scene, const void* sdf_records, const void* sample_pts,
+                                    const int32_t* n_samples_ptr, int64_t sample_capacity, void* sample_rec_out,
+                                    pp_stream_t stream);
+PP_API int pp_voxurf_sample_records_backward(const pp_dvgo_scene* scene, const void* sdf_records,
+                                             const void* sample_pts, const int32_t* n_samples_ptr,
+                                             int64_t sample_capacity, const void* grad_sample_rec, float w_eikonal,
+                                             void* grad_sdf_records, float* eikonal_term, pp_stream_t stream);
 /* d loss / d (rays_o | rays_d) [N,6] through the positions of all in-box samples: grad_pts [samples,3] chained through
  * sample_pts_on_rays' geometry (t_min slab, normalised direction), ADDED to grad_rays (which pp_voxurf_backward_deform
  * filled with the colour-side terms of the composited samples). */

@@ -524,9 +524,13 @@ static int launch_march_occ(const pp_dvgo_scene* sc, const pp_dvgo_loss* ls, con
     PP_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // persistent grid: every resident warp pulls rays from a device-side queue
   static std::atomic<unsigned> next_slot{0};
-  static unsigned int* queue_base = nullptr;
-  if (!queue_base) PP_CHECK_CUDA(cudaGetSymbolAddress((void**)&queue_base, g_ray_queue));
-  unsigned int* queue = queue_base + (next_slot.fetch_add(1) % kQueueSlots);
+  // a __device__ symbol has a different address on every device: resolve it per device (like sm_count)
+  static unsigned int* queue_bases[64] = {nullptr};
+  int dev = 0;
+  PP_CHECK_CUDA(cudaGetDevice(&dev));
+  PP_REQUIRE(dev >= 0 && dev < 64, PP_ERR_UNSUPPORTED, "%s: device ordinal %d out of range", who, dev);
+  if (!queue_bases[dev]) PP_CHECK_CUDA(cudaGetSymbolAddress((void**)&queue_bases[dev], g_ray_queue));
+  unsigned int* queue = queue_bases[dev] + (next_slot.fetch_add(1) % kQueueSlots);
   PP_CHECK_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned int), s));
   int per_sm = 0;
   PP_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem));

@@ -28,6 +28,15 @@ struct SyncPtrs {
   SyncBlock* blk[kMaxWorld];
 };
 
+// Cycle budget of a barrier wait.  A rank that stays away longer (dead process, debugger) makes its peers raise the
+// STICKY timed_out flag of their sync block: from then on the exchange kernels do nothing and report NaN as the global
+// loss, and the host side (dist.py, pp_peer_sync_timed_out) raises - replicas are never updated from partial sums.
+constexpr long long kPeerWaitCycles = 120000000000LL;
+
+__device__ __forceinline__ bool peer_timed_out(const SyncPtrs& sp, int me) {
+  return *reinterpret_cast<volatile unsigned int*>(&sp.blk[me]->timed_out) != 0u;
+}
+
 // announce epoch E to every peer (optionally with a 2-float payload) and wait until every peer announced it
 // (release / acquire at system scope on flags in peer memory).  Executed by threads r < world of a warp.
 __device__ __forceinline__ void peer_announce_and_wait(const SyncPtrs& sp, int world, int me, unsigned int epoch,
@@ -49,9 +58,9 @@ __device__ __forceinline__ void peer_announce_and_wait(const SyncPtrs& sp, int w
       unsigned int v;
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(&mine->flags[r]) : "memory");
       if ((int)(v - epoch) >= 0) break;
-      if (clock64() - t0 > 20000000000LL) {   // ~10 s: a peer died; do not hang the device
-        mine->timed_out = 1;
-        break;
+      if (clock64() - t0 > kPeerWaitCycles) {   // ~60 s: a peer died; do not hang the device ...
+        mine->timed_out = 1;                     // ... and never run the exchange on half-written gradients:
+        break;                                   // every caller checks the flag (sticky) and skips its work
       }
     }
   }
@@ -77,8 +86,9 @@ template <int kWorld>
 __global__ void __launch_bounds__(kXchgThreads)
 voxel_adam_exchange_kernel(PeerPtrs pp, float4* __restrict__ m4, float4* __restrict__ v4,
                            int64_t begin, int64_t end, int rank, float ss_density, float ss_k0,
-                           float b1, float b2, float eps, int dbg) {
+                           float b1, float b2, float eps, int dbg, const unsigned int* __restrict__ timed_out) {
   constexpr int kDepth = 2;
+  if (timed_out && *reinterpret_cast<const volatile unsigned int*>(timed_out) != 0u) return;   // see kPeerWaitCycles
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t first = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -167,7 +177,9 @@ voxel_adam_exchange_mc_kernel(const float4* __restrict__ vox_local, float4* vox_
   // its first in-switch reduction (saves the separate one-warp barrier launch in front of this kernel)
   if (epoch != 0u) {
     if (threadIdx.x < 32) peer_announce_and_wait(sp, world, me, epoch, payload_in, blockIdx.x == 0);
+    __threadfence();
     __syncthreads();
+    const bool dead = peer_timed_out(sp, me);
     if (payload_sum && blockIdx.x == 0 && threadIdx.x == 0) {
       const SyncBlock* mine = sp.blk[me];
       float a = 0.f, b = 0.f;
@@ -175,9 +187,12 @@ voxel_adam_exchange_mc_kernel(const float4* __restrict__ vox_local, float4* vox_
         a += mine->payload[q][0];
         b += mine->payload[q][1];
       }
-      payload_sum[0] = a;
-      payload_sum[1] = b;
+      payload_sum[0] = dead ? __int_as_float(0x7fc00000) : a;
+      payload_sum[1] = dead ? __int_as_float(0x7fc00000) : b;
     }
+    if (dead) return;   // a peer never announced: its gradient records may be half written
+  } else if (sp.blk[me] && peer_timed_out(sp, me)) {
+    return;             // the separate barrier in front of this launch timed out
   }
   // same software pipeline as the peer-load variant: the in-switch reductions of the next records are in
   // flight (up-link: every GPU's contribution) while this record's multicast store goes out (down-link)
@@ -232,16 +247,18 @@ voxel_adam_exchange_mc_kernel(const float4* __restrict__ vox_local, float4* vox_
 __global__ void peer_sync_kernel(SyncPtrs sp, int world, int me, unsigned int epoch,
                                  const float* __restrict__ payload_in, float* __restrict__ payload_sum) {
   peer_announce_and_wait(sp, world, me, epoch, payload_in, true);
+  __threadfence();
   __syncwarp();
   if (payload_sum && threadIdx.x == 0) {
+    const bool dead = peer_timed_out(sp, me);
     const SyncBlock* mine = sp.blk[me];
     float a = 0.f, b = 0.f;
     for (int q = 0; q < world; ++q) {
       a += mine->payload[q][0];
       b += mine->payload[q][1];
     }
-    payload_sum[0] = a;
-    payload_sum[1] = b;
+    payload_sum[0] = dead ? __int_as_float(0x7fc00000) : a;
+    payload_sum[1] = dead ? __int_as_float(0x7fc00000) : b;
   }
 }
 
@@ -312,7 +329,7 @@ extern "C" int pp_voxel_adam_exchange_mc(const void* vox_local, void* vox_mc, co
   const int64_t begin = shard * rank < n_voxels ? shard * rank : n_voxels;
   const int64_t end = begin + shard < n_voxels ? begin + shard : n_voxels;
   SyncPtrs sp;
-  for (int r = 0; r < kMaxWorld; ++r) sp.blk[r] = (epoch != 0 && r < world) ? (SyncBlock*)sync_ptrs[r] : nullptr;
+  for (int r = 0; r < kMaxWorld; ++r) sp.blk[r] = (sync_ptrs && r < world) ? (SyncBlock*)sync_ptrs[r] : nullptr;
   // an empty slice still takes part in the fused barrier (one block, no records)
   if (end <= begin && epoch == 0) return PP_OK;
   const int64_t n_rec = end > begin ? end - begin : 0;
@@ -351,6 +368,16 @@ extern "C" int pp_peer_sync(void* const* sync_ptrs, int32_t world, int32_t rank,
   return PP_OK;
 }
 
+// 1 if a barrier wait of this rank ever ran out of its budget (sticky; synchronises the device), else 0
+extern "C" int pp_peer_sync_timed_out(const void* sync_block) {
+  if (!sync_block) return 0;
+  unsigned int v = 0;
+  if (cudaMemcpy(&v, &static_cast<const SyncBlock*>(sync_block)->timed_out, sizeof(v), cudaMemcpyDeviceToHost) !=
+      cudaSuccess)
+    return -1;
+  return v != 0u;
+}
+
 extern "C" int64_t pp_voxel_shard_size(int64_t n_voxels, int32_t world) {
   if (world <= 0 || n_voxels <= 0) return 0;
   const int64_t s = (n_voxels + world - 1) / world;
@@ -360,7 +387,7 @@ extern "C" int64_t pp_voxel_shard_size(int64_t n_voxels, int32_t world) {
 extern "C" int pp_voxel_adam_exchange(void* const* vox_ptrs, void* const* grad_ptrs, void* exp_avg,
                                       void* exp_avg_sq, int64_t n_voxels, int32_t world, int32_t rank,
                                       int32_t step, float beta1, float beta2, float lr_density,
-                                      float lr_k0, float eps, pp_stream_t stream) {
+                                      float lr_k0, float eps, const void* sync_block, pp_stream_t stream) {
   PP_REQUIRE(vox_ptrs && grad_ptrs && exp_avg && exp_avg_sq, PP_ERR_INVALID_ARG,
              "voxel_adam_exchange: null pointer");
   PP_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, PP_ERR_INVALID_ARG,
@@ -381,11 +408,12 @@ extern "C" int pp_voxel_adam_exchange(void* const* vox_ptrs, void* const* grad_p
   const float ssk = adam_step_size_x(lr_k0, beta1, beta2, step);
   const int blocks = exchange_blocks(end - begin);
   cudaStream_t s = as_stream(stream);
+  const unsigned int* timed_out = sync_block ? &static_cast<const SyncBlock*>(sync_block)->timed_out : nullptr;
   const char* dbg_env = getenv("PP_XCHG_FLAGS");   // timing experiments only: 1 = no peer stores, 2 = no peer loads
   const int dbg = dbg_env ? atoi(dbg_env) : 0;
 #define PP_LAUNCH_X(W)                                                                         \
   voxel_adam_exchange_kernel<W><<<blocks, kXchgThreads, 0, s>>>(pp, (float4*)exp_avg, (float4*)exp_avg_sq, \
-                                                       begin, end, rank, ssd, ssk, beta1, beta2, eps, dbg)
+                                                       begin, end, rank, ssd, ssk, beta1, beta2, eps, dbg, timed_out)
   switch (world) {
     case 1: PP_LAUNCH_X(1); break;
     case 2: PP_LAUNCH_X(2); break;

@@ -180,7 +180,8 @@ __global__ void __launch_bounds__(256)
 voxurf_deform_rows_kernel(pp_dvgo_scene sc, const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                           const float* __restrict__ jitter, int64_t n_rays, int32_t cap_samples,
                           uint4* __restrict__ rows, int32_t* __restrict__ dray_off, int32_t* __restrict__ counter,
-                          unsigned int* __restrict__ queue, int cap, float4* __restrict__ pts_out) {
+                          unsigned int* __restrict__ queue, int cap, float4* __restrict__ pts_out,
+                          int32_t* __restrict__ dray_cnt) {
   const int lane = threadIdx.x & 31;
   for (;;) {
     unsigned int ticket = 0;
@@ -206,6 +207,7 @@ voxurf_deform_rows_kernel(pp_dvgo_scene sc, const float* __restrict__ rays_o, co
         atomicAdd(counter + 2, 4 * n_in);
       }
       dray_off[r] = off;
+      if (dray_cnt) dray_cnt[r] = n_in;
     }
     off = __shfl_sync(kFull, off, 0);
     if (off < 0) continue;
@@ -218,6 +220,8 @@ voxurf_deform_rows_kernel(pp_dvgo_scene sc, const float* __restrict__ rays_o, co
       const int slot = off + run + __popc(m & ((1u << lane) - 1u));
       run += __popc(m);
       if (!inbox) continue;
+      if (pts_out) pts_out[slot] = make_float4(p[0], p[1], p[2], 0.f);
+      if (!rows) continue;
       float hi[3], lo[3];
 #pragma unroll
       for (int a = 0; a < 3; ++a) {
@@ -234,7 +238,6 @@ voxurf_deform_rows_kernel(pp_dvgo_scene sc, const float* __restrict__ rays_o, co
       dst[5] = zero;
       dst[6] = make_uint4(0u, 0x00003C00u, 0u, 0u);   // e_2
       dst[7] = zero;
-      if (pts_out) pts_out[slot] = make_float4(p[0], p[1], p[2], 0.f);
     }
   }
 }
@@ -630,6 +633,78 @@ voxurf_deform_sample_backward_kernel(pp_dvgo_scene sc, const float4* __restrict_
       atomicAdd(reg_out + 2, t_corr);
       atomicAdd(reg_out + 3, t_def);
     }
+  }
+}
+
+// ---- per-sample SDF records of ALL in-box samples (non-deform branch) -----------------------------------------
+// The reference's result dict carries `gradient` [M,3] of every in-box sample (not only the composited ones) and
+// lib/losses.py:7-10 puts the Eikonal term |‖gradient‖ - 1|.mean() on it (weight 1.0, live).  Forward: the
+// interpolated record {s', d s'} at every point of `pts` (the list pp_voxurf_deform_rows writes).  Backward: scatter of
+// a per-sample float4 gradient - or of the built-in Eikonal gradient w_eik * sign(‖g‖-1) g / ‖g‖ / M - into the
+// SDF-record gradients (128-bit reductions, one per corner).
+__global__ void __launch_bounds__(256)
+voxurf_sample_records_kernel(pp_dvgo_scene sc, const float4* __restrict__ srec, const float4* __restrict__ pts,
+                             const int32_t* __restrict__ n_ptr, int64_t cap, float4* __restrict__ out) {
+  const int64_t M = min64(cap, static_cast<int64_t>(*n_ptr));
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const float4 p = pts[i];
+  const Cell c = make_cell(sc, p.x, p.y, p.z);
+  float4 q8[8];
+  gather8(srec, c, q8);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float w = corner_w(c, q);
+    acc.x = fma_rn(w, q8[q].x, acc.x);
+    acc.y = fma_rn(w, q8[q].y, acc.y);
+    acc.z = fma_rn(w, q8[q].z, acc.z);
+    acc.w = fma_rn(w, q8[q].w, acc.w);
+  }
+  out[i] = acc;
+}
+
+__global__ void __launch_bounds__(256)
+voxurf_sample_records_backward_kernel(pp_dvgo_scene sc, const float4* __restrict__ srec, const float4* __restrict__ pts,
+                                      const int32_t* __restrict__ n_ptr, int64_t cap, const float4* __restrict__ g_in,
+                                      float w_eik, float4* __restrict__ g_srec, float* __restrict__ term_out) {
+  const int64_t M = min64(cap, static_cast<int64_t>(*n_ptr));
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  float term = 0.f;
+  if (i < M) {
+    const float4 p = pts[i];
+    const Cell c = make_cell(sc, p.x, p.y, p.z);
+    float4 g = g_in ? g_in[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (w_eik != 0.f || term_out) {
+      float4 q8[8];
+      gather8(srec, c, q8);
+      float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float w = corner_w(c, q);
+        gx = fma_rn(w, q8[q].y, gx);
+        gy = fma_rn(w, q8[q].z, gy);
+        gz = fma_rn(w, q8[q].w, gz);
+      }
+      const float inv_m = 1.f / static_cast<float>(M);
+      const float gn = sqrtf(gx * gx + gy * gy + gz * gz);
+      term = fabsf(gn - 1.f) * inv_m;
+      const float k = (gn > 1.f ? 1.f : (gn < 1.f ? -1.f : 0.f)) * w_eik * inv_m / fmaxf(gn, 1e-30f);
+      g.y += k * gx;
+      g.z += k * gy;
+      g.w += k * gz;
+    }
+    if (g.x != 0.f || g.y != 0.f || g.z != 0.f || g.w != 0.f) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float w = corner_w(c, q);
+        if (w != 0.f) red_add_v4(g_srec + corner_off(c, q), w * g.x, w * g.y, w * g.z, w * g.w);
+      }
+    }
+  }
+  if (term_out) {
+    term = warp_sum(term);
+    if ((threadIdx.x & 31) == 0 && term != 0.f) atomicAdd(term_out, term);
   }
 }
 
@@ -1046,14 +1121,17 @@ static int check_vox_scene(const pp_dvgo_scene* sc, const pp_voxurf_cfg* cfg, co
 
 static unsigned int* next_queue(cudaStream_t s, int* rc) {
   static std::atomic<unsigned> next_slot{0};
-  static unsigned int* queue_base = nullptr;
+  // a __device__ symbol has a different address on every device: resolve it per device (like sm_count)
+  static unsigned int* queue_bases[64] = {nullptr};
   *rc = PP_OK;
-  if (!queue_base && cudaGetSymbolAddress((void**)&queue_base, g_vox_queue) != cudaSuccess) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 ||
+      (!queue_bases[dev] && cudaGetSymbolAddress((void**)&queue_bases[dev], g_vox_queue) != cudaSuccess)) {
     set_error("cudaGetSymbolAddress failed");
     *rc = PP_ERR_CUDA;
     return nullptr;
   }
-  unsigned int* q = queue_base + (next_slot.fetch_add(1) % kQueueSlots);
+  unsigned int* q = queue_bases[dev] + (next_slot.fetch_add(1) % kQueueSlots);
   if (cudaMemsetAsync(q, 0, sizeof(unsigned int), s) != cudaSuccess) {
     set_error("cudaMemsetAsync failed");
     *rc = PP_ERR_CUDA;
@@ -1175,11 +1253,11 @@ extern "C" int pp_voxurf_march_features_deform(const pp_dvgo_scene* scene, const
 extern "C" int pp_voxurf_deform_rows(const pp_dvgo_scene* scene, const float* rays_o, const float* rays_d,
                                      const float* jitter, int64_t n_rays, int32_t sample_capacity, void* rows,
                                      int32_t* warp_ray_off, int32_t* counter, void* sample_pts,
-                                     pp_stream_t stream) {
+                                     int32_t* warp_ray_cnt, pp_stream_t stream) {
   PP_REQUIRE(scene, PP_ERR_INVALID_ARG, "voxurf_deform_rows: null scene");
   PP_REQUIRE(n_rays >= 0 && sample_capacity >= 0, PP_ERR_INVALID_ARG, "voxurf_deform_rows: negative extent");
   if (n_rays == 0) return PP_OK;
-  PP_REQUIRE(rays_o && rays_d && rows && warp_ray_off && counter, PP_ERR_INVALID_ARG,
+  PP_REQUIRE(rays_o && rays_d && (rows || sample_pts) && warp_ray_off && counter, PP_ERR_INVALID_ARG,
              "voxurf_deform_rows: null pointer");
   cudaStream_t s = as_stream(stream);
   int qrc;
@@ -1189,7 +1267,8 @@ extern "C" int pp_voxurf_deform_rows(const pp_dvgo_scene* scene, const float* ra
   const int64_t blocks = min64((n_rays + 7) / 8, (int64_t)sm_count() * 8);
   voxurf_deform_rows_kernel<<<(unsigned)blocks, 256, 0, s>>>(*scene, rays_o, rays_d, jitter, n_rays, sample_capacity,
                                                              (uint4*)rows, warp_ray_off, counter, queue,
-                                                             vox_step_capacity(scene), (float4*)sample_pts);
+                                                             vox_step_capacity(scene), (float4*)sample_pts,
+                                                             warp_ray_cnt);
   PP_CHECK_LAUNCH("voxurf_deform_rows");
   return PP_OK;
 }
@@ -1477,6 +1556,35 @@ extern "C" int pp_voxurf_deform_sample_forward(const pp_dvgo_scene* scene, const
       *scene, (const float4*)sdf_records, (const float4*)sample_pts, warp_out, nullptr, n_samples_ptr, sample_capacity,
       out_range, 0.f, 0.f, 0.f, 0.f, nullptr, nullptr, reg_terms, nullptr, sample_out);
   PP_CHECK_LAUNCH("voxurf_deform_sample_forward");
+  return PP_OK;
+}
+
+extern "C" int pp_voxurf_sample_records(const pp_dvgo_scene* scene, const void* sdf_records, const void* sample_pts,
+                                        const int32_t* n_samples_ptr, int64_t sample_capacity, void* sample_rec_out,
+                                        pp_stream_t stream) {
+  PP_REQUIRE(scene && sample_capacity >= 0, PP_ERR_INVALID_ARG, "voxurf_sample_records: bad argument");
+  if (sample_capacity == 0) return PP_OK;
+  PP_REQUIRE(sdf_records && sample_pts && n_samples_ptr && sample_rec_out, PP_ERR_INVALID_ARG,
+             "voxurf_sample_records: null pointer");
+  voxurf_sample_records_kernel<<<ceil_div(sample_capacity, 256), 256, 0, as_stream(stream)>>>(
+      *scene, (const float4*)sdf_records, (const float4*)sample_pts, n_samples_ptr, sample_capacity,
+      (float4*)sample_rec_out);
+  PP_CHECK_LAUNCH("voxurf_sample_records");
+  return PP_OK;
+}
+
+extern "C" int pp_voxurf_sample_records_backward(const pp_dvgo_scene* scene, const void* sdf_records,
+                                                 const void* sample_pts, const int32_t* n_samples_ptr,
+                                                 int64_t sample_capacity, const void* grad_sample_rec, float w_eikonal,
+                                                 void* grad_sdf_records, float* eikonal_term, pp_stream_t stream) {
+  PP_REQUIRE(scene && sample_capacity >= 0, PP_ERR_INVALID_ARG, "voxurf_sample_records_backward: bad argument");
+  if (sample_capacity == 0) return PP_OK;
+  PP_REQUIRE(sdf_records && sample_pts && n_samples_ptr && grad_sdf_records, PP_ERR_INVALID_ARG,
+             "voxurf_sample_records_backward: null pointer");
+  voxurf_sample_records_backward_kernel<<<ceil_div(sample_capacity, 256), 256, 0, as_stream(stream)>>>(
+      *scene, (const float4*)sdf_records, (const float4*)sample_pts, n_samples_ptr, sample_capacity,
+      (const float4*)grad_sample_rec, w_eikonal, (float4*)grad_sdf_records, eikonal_term);
+  PP_CHECK_LAUNCH("voxurf_sample_records_backward");
   return PP_OK;
 }
 

@@ -135,6 +135,18 @@ class DistributedDVGO:
         self.fused_sync = os.environ.get("PP_XCHG_FUSED_SYNC", "1") != "0"
         dev = density.device
         kw = dict(kw)
+        if self.mode in ("p2p", "nvls"):
+            # the fused exchange kernels have no total-variation stencil and exist for 1, 2, 4, 8 ranks
+            if any(kw.get(k, 0.0) for k in ("tv_density", "tv_k0")):
+                if not auto:
+                    raise RuntimeError("DistributedDVGO(mode=%r): total variation is only implemented in the "
+                                       "'nccl' mode (all-reduce + the single-GPU TV + Adam pass)" % self.mode)
+                self.mode = "nccl"
+            elif self.world not in (2, 4, 8):
+                if not auto:
+                    raise RuntimeError("DistributedDVGO(mode=%r): world size %d not supported (2, 4, 8)"
+                                       % (self.mode, self.world))
+                self.mode = "nccl"
         kw["w_rgb"] = kw.get("w_rgb", 1.0) / self.world          # global mean over all ranks' rays
         for k in ("w_entropy_last", "w_rgbper"):
             if k in kw:
@@ -237,14 +249,15 @@ class DistributedDVGO:
                                                     self.grad_mems[self.cur].multicast_ptr, ptr(eng.exp_avg),
                                                     ptr(eng.exp_avg_sq), eng.n_voxels, self.world, self.rank,
                                                     eng.step, b1, b2, lr_d, lr_k, eps,
-                                                    self.sync_ptrs if fused else None, self.epoch if fused else 0,
+                                                    self.sync_ptrs, self.epoch if fused else 0,
                                                     ptr(eng.loss_buf) if fused else None,
                                                     ptr(self.loss_global) if fused else None, s),
                       "voxel_adam_exchange_mc")
             else:
                 check(lib.pp_voxel_adam_exchange(self.vox_ptrs, self.grad_ptrs[self.cur], ptr(eng.exp_avg),
                                                  ptr(eng.exp_avg_sq), eng.n_voxels, self.world, self.rank,
-                                                 eng.step, b1, b2, lr_d, lr_k, eps, s), "voxel_adam_exchange")
+                                                 eng.step, b1, b2, lr_d, lr_k, eps, self.sync_ptrs[self.rank], s),
+                      "voxel_adam_exchange")
             if prof is not None:
                 prof[2].record()
             # barrier: all slices written, all peers done reading my gradient
@@ -264,10 +277,20 @@ class DistributedDVGO:
             prof[4].record()
         return self.loss_global
 
+    def check_health(self):
+        """Raises if a cross-rank barrier of this rank ever timed out (a peer died or stalled for ~60 s): the exchange
+        kernels stop updating from that point on and the reported loss is NaN.  Synchronises the device."""
+        if self.mode in ("p2p", "nvls"):
+            with torch.cuda.device(self.eng.device):
+                if lib.pp_peer_sync_timed_out(self.sync_ptrs[self.rank]) != 0:
+                    raise RuntimeError("DistributedDVGO: a cross-rank barrier timed out on rank %d - a peer stalled "
+                                       "or died; parameters were not updated since" % self.rank)
+
     def render(self, rays_o, rays_d, **kw):
         return self.eng.render(rays_o, rays_d, **kw)
 
     def export_grids(self):
+        self.check_health()
         return self.eng.export_grids()
 
     def close(self):

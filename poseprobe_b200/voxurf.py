@@ -264,20 +264,52 @@ class FusedVoxurf:
         g0 = self.g_ww[0][:, :3] + self.g_ww[0][:, 3:]
         return [g0] + [g.clone() for g in self.g_ww[1:]], [g.clone() for g in self.g_wb]
 
+    def _inbox_buffers(self, b, points=True):
+        dev = self.device
+        if "dray_off" not in b:
+            b["dray_off"] = torch.empty(b["n_rays"], dtype=torch.int32, device=dev)
+            b["dray_cnt"] = torch.zeros(b["n_rays"], dtype=torch.int32, device=dev)
+            b["dcounter"] = torch.zeros(4, dtype=torch.int32, device=dev)
+        if points and "dpts" not in b:
+            b["dpts"] = torch.empty((b["cap"], 4), dtype=torch.float32, device=dev)
+        if "reg" not in b:
+            b["reg"] = torch.zeros(4, dtype=torch.float32, device=dev)
+
+    def _enumerate_inbox(self, b, rays_o, rays_d, jitter):
+        """Runs of ALL in-box samples per ray (the reference's compacted ray_pts, voxurf_coarse.py:940-944) and their
+        positions, without the deformation network's rows."""
+        self._inbox_buffers(b)
+        check(lib.pp_voxurf_deform_rows(ctypes.byref(self.scene), ptr(rays_o), ptr(rays_d), ptr(jitter),
+                                        rays_o.shape[0], b["cap"], None, ptr(b["dray_off"]), ptr(b["dcounter"]),
+                                        ptr(b["dpts"]), ptr(b["dray_cnt"]), stream()), "voxurf_deform_rows")
+
+    def inbox_order(self, n):
+        """-> (idx [M], ray_id [M]): kernel slot and ray of every in-box sample in the reference's ray-major order
+        (runs are handed out in completion order on the device).  Host sync; raises on a capacity overflow."""
+        b = self._bufs
+        c = b["dcounter"].tolist()
+        if c[1]:
+            raise RuntimeError("FusedVoxurf: sample capacity exceeded (raise samples_per_ray_cap)")
+        m = c[0]
+        dev = self.device
+        cnt, off = b["dray_cnt"][:n].long(), b["dray_off"][:n].long()
+        ray_id = torch.repeat_interleave(torch.arange(n, device=dev), cnt, output_size=m)
+        starts = torch.cumsum(cnt, 0) - cnt
+        idx = off[ray_id] + (torch.arange(m, device=dev) - starts[ray_id])
+        return idx, ray_id
+
     def _march_deform(self, b, rays_o, rays_d, viewdirs, jitter, depth=None, normal=None, keep_points=False):
         n, cap = rays_o.shape[0], b["cap"]
+        self._inbox_buffers(b, keep_points)
         if "drows" not in b:
             dev = self.device
             b["drows"] = torch.empty((4 * cap, 16), dtype=torch.float16, device=dev)
             b["dout"] = torch.empty((4 * cap, 4), dtype=torch.float32, device=dev)
-            b["dray_off"] = torch.empty(b["n_rays"], dtype=torch.int32, device=dev)
-            b["dcounter"] = torch.zeros(4, dtype=torch.int32, device=dev)
-        if keep_points and "dpts" not in b:
-            b["dpts"] = torch.empty((cap, 4), dtype=torch.float32, device=self.device)
         ws, bs, out_range = self.warp
         check(lib.pp_voxurf_deform_rows(ctypes.byref(self.scene), ptr(rays_o), ptr(rays_d), ptr(jitter), n, cap,
                                         ptr(b["drows"]), ptr(b["dray_off"]), ptr(b["dcounter"]),
-                                        ptr(b["dpts"]) if keep_points else None, stream()), "voxurf_deform_rows")
+                                        ptr(b["dpts"]) if keep_points else None, ptr(b["dray_cnt"]), stream()),
+              "voxurf_deform_rows")
         check(lib.pp_warpnet_forward_packed(ptr(b["drows"]), 4 * cap, len(ws), 128, self._arr(ws), self._arr(bs),
                                             ptr(b["dout"]), ptr(b["dcounter"][2:]), stream()), "warpnet_forward")
         check(lib.pp_voxurf_march_features_deform(
@@ -359,6 +391,14 @@ class FusedVoxurf:
                                          ptr(b["g_ray"]), ptr(self.g_srec), ptr(self.g_k0rec), ptr(self.srec),
                                          ptr(self.k0rec), ptr(b["grad_rays"]), ptr(b["grad_view"]), ptr(b["g_cumw"]),
                                          ptr(b["g_last"]), stream()), "voxurf_backward")
+            if self.w_eikonal > 0:
+                # grad_constraint of lib/losses.py:7-10 on ALL in-box samples (also past the early termination)
+                self._enumerate_inbox(b, rays_o, rays_d, jitter)
+                b["reg"].zero_()
+                check(lib.pp_voxurf_sample_records_backward(ctypes.byref(self.scene), ptr(self.srec), ptr(b["dpts"]),
+                                                            ptr(b["dcounter"]), b["cap"], None, self.w_eikonal,
+                                                            ptr(self.g_srec), ptr(b["reg"]), stream()),
+                      "voxurf_sample_records_backward")
         return b["rgb"][:n]
 
     def _object_loss(self, b, n, target, mask):
@@ -367,7 +407,7 @@ class FusedVoxurf:
                                         ptr(b["g_cumw"]), ptr(b["g_last"]), ptr(b["rgb"]), ptr(self.loss_buf),
                                         ptr(self._scratch), stream()), "voxurf_object_loss")
 
-    def forward_sums_deform(self, rays_o, rays_d, viewdirs, jitter=None, want_samples=False):
+    def forward_sums_deform(self, rays_o, rays_d, viewdirs, jitter=None, want_samples=False, depth=None, normal=None):
         """Deform branch of `forward_sums`: -> (rgb_acc, cum_weights, alphainv_last); with want_samples also the
         per-sample entries of ALL in-box samples (b["sout"] fp32 [cap,16], see pp_voxurf_deform_sample_forward)."""
         if self.warp is None:
@@ -375,7 +415,7 @@ class FusedVoxurf:
         n = rays_o.shape[0]
         b = self._buffers(n)
         with torch.cuda.device(self.device):
-            self._march_deform(b, rays_o, rays_d, viewdirs, jitter, keep_points=True)
+            self._march_deform(b, rays_o, rays_d, viewdirs, jitter, depth, normal, keep_points=True)
             self._mlp_forward(b, n)
             if want_samples:
                 if "sout" not in b:
@@ -414,7 +454,6 @@ class FusedVoxurf:
                 b["g_val"] = torch.empty((cap, 4), dtype=torch.float32, device=dev)
                 b["g_dout"] = torch.empty((4 * cap, 4), dtype=torch.float32, device=dev)
                 b["g_pts"] = torch.empty((cap, 3), dtype=torch.float32, device=dev)
-                b["reg"] = torch.zeros(4, dtype=torch.float32, device=dev)
             b["g_val"].zero_()
             b["reg"].zero_()
             check(lib.pp_voxurf_backward_deform(ctypes.byref(self.scene), ctypes.byref(self.cfg), ptr(rays_o),
@@ -479,19 +518,27 @@ class FusedVoxurf:
         self._refresh_cfg()
         self.rebuild_records()
 
-    def forward_sums(self, rays_o, rays_d, viewdirs, jitter=None):
+    def forward_sums(self, rays_o, rays_d, viewdirs, jitter=None, want_samples=False, depth=None, normal=None):
         """-> (rgb_acc [N,3] = sum_i w_i rgb_i, cum_weights [N], alphainv_last [N]); state is kept for
         backward_from_ray_grads."""
         n = rays_o.shape[0]
         b = self._buffers(n)
         with torch.cuda.device(self.device):
-            self._march(b, rays_o, rays_d, viewdirs, jitter)
+            self._march(b, rays_o, rays_d, viewdirs, jitter, depth, normal)
             self._mlp_forward(b, n)
+            if want_samples:       # {sdf, gradient} of ALL in-box samples (the dict's `gradient`, :1082)
+                self._enumerate_inbox(b, rays_o, rays_d, jitter)
+                if "srec_s" not in b:
+                    b["srec_s"] = torch.empty((b["cap"], 4), dtype=torch.float32, device=self.device)
+                check(lib.pp_voxurf_sample_records(ctypes.byref(self.scene), ptr(self.srec), ptr(b["dpts"]),
+                                                   ptr(b["dcounter"]), b["cap"], ptr(b["srec_s"]), stream()),
+                      "voxurf_sample_records")
         return b["acc"][:n], b["cum_w"][:n], b["last"][:n]
 
-    def backward_from_ray_grads(self, rays_o, rays_d, viewdirs, g_acc, g_cumw, g_last, jitter=None):
+    def backward_from_ray_grads(self, rays_o, rays_d, viewdirs, g_acc, g_cumw, g_last, jitter=None, g_samples=None):
         """Back-propagate d loss / d (rgb_acc, cum_weights, alphainv_last) of the last forward_sums into the
-        gradient buffers (accumulating)."""
+        gradient buffers (accumulating).  g_samples (nullable) fp32 [cap,4]: d loss / d {sdf, gradient} of the in-box
+        samples of forward_sums(want_samples=True), kernel slot order."""
         n = rays_o.shape[0]
         b = self._bufs
         g_acc = g_acc.contiguous()
@@ -508,6 +555,11 @@ class FusedVoxurf:
                                          ptr(self.k0rec), ptr(b["grad_rays"]), ptr(b["grad_view"]),
                                          ptr(g_cumw.contiguous()), ptr(g_last.contiguous()) if g_last is not None else None,
                                          stream()), "voxurf_backward")
+            if g_samples is not None:
+                check(lib.pp_voxurf_sample_records_backward(ctypes.byref(self.scene), ptr(self.srec), ptr(b["dpts"]),
+                                                            ptr(b["dcounter"]), b["cap"], ptr(g_samples), 0.0,
+                                                            ptr(self.g_srec), None, stream()),
+                      "voxurf_sample_records_backward")
 
     def ray_gradients(self, rays_d=None):
         """d loss / d (rays_o | rays_d) [N,6] and d loss / d viewdirs [N,3] of the last backward (pose_grad=True).
@@ -618,45 +670,134 @@ class FusedVoxurf:
 
 
 class _VoxurfRenderFn(torch.autograd.Function):
-    """(sdf.grid, k0.grid, sdf_alpha, sdf_beta, rgbnet parameters) -> (rgb_acc, cum_weights, alphainv_last) with both
-    directions on the fused kernels; any loss written on those outputs trains the reference's parameters."""
+    """(sdf.grid, k0.grid, sdf_alpha, sdf_beta, rgbnet parameters, rays) -> (rgb_acc, cum_weights, alphainv_last,
+    {sdf, gradient} of every in-box sample) with both directions on the fused kernels; any loss written on those
+    outputs (lib/losses.py) trains the reference's parameters and, through the rays, the poses."""
 
     @staticmethod
     def forward(ctx, eng, rays_o, rays_d, viewdirs, jitter, depth, sdf, k0, ab, *params):
         eng.load_params(sdf, k0, params[:depth], params[depth:], float(ab[0]), float(ab[1]))
         rays_o, rays_d, viewdirs = rays_o.contiguous(), rays_d.contiguous(), viewdirs.contiguous()
-        acc, cumw, last = eng.forward_sums(rays_o, rays_d, viewdirs, jitter)
+        n = rays_o.shape[0]
+        eng.aux = {"depth": torch.empty(n, device=eng.device), "normal": torch.empty((n, 3), device=eng.device)}
+        acc, cumw, last = eng.forward_sums(rays_o, rays_d, viewdirs, jitter, want_samples=True,
+                                           depth=eng.aux["depth"], normal=eng.aux["normal"])
+        idx, ray_id = eng.inbox_order(n)
+        eng.aux.update(idx=idx, ray_id=ray_id)
         ctx.eng, ctx.depth = eng, depth
-        ctx.save_for_backward(rays_o, rays_d, viewdirs, jitter if jitter is not None else torch.empty(0), ab)
-        return acc.clone(), cumw.clone(), last.clone()
+        ctx.save_for_backward(rays_o, rays_d, viewdirs, jitter if jitter is not None else torch.empty(0), ab, idx)
+        return acc.clone(), cumw.clone(), last.clone(), eng._bufs["srec_s"][idx]
 
     @staticmethod
     @torch.autograd.function.once_differentiable
-    def backward(ctx, g_acc, g_cumw, g_last):
+    def backward(ctx, g_acc, g_cumw, g_last, g_samp):
         eng, depth = ctx.eng, ctx.depth
-        rays_o, rays_d, viewdirs, jitter, ab = ctx.saved_tensors
+        rays_o, rays_d, viewdirs, jitter, ab, idx = ctx.saved_tensors
         jitter = jitter if jitter.numel() else None
         eng.grad_flat.zero_()
         eng.g_ab.zero_()
-        eng.backward_from_ray_grads(rays_o, rays_d, viewdirs, g_acc, g_cumw, g_last, jitter)
+        g_samples = None
+        if g_samp is not None and idx.numel():
+            g_samples = torch.zeros((eng._bufs["cap"], 4), dtype=torch.float32, device=eng.device)
+            g_samples[idx] = g_samp
+        eng.backward_from_ray_grads(rays_o, rays_d, viewdirs, g_acc, g_cumw, g_last, jitter, g_samples)
         g_sdf, g_k0, g_w, g_b = eng.grid_gradients()
         # (a, b) = softplus10(sdf_alpha, sdf_beta): d softplus_beta(x) / dx = sigmoid(beta x)
         g_param_ab = eng.g_ab * torch.sigmoid(10.0 * ab)
-        return (None, None, None, None, None, None, g_sdf, g_k0, g_param_ab) + tuple(g_w) + tuple(g_b)
+        g_o = g_d = g_v = None
+        if eng.pose_grad:
+            nr = rays_o.shape[0]
+            g_rays, g_v = eng.ray_gradients()
+            g_o, g_d, g_v = g_rays[:nr, :3], g_rays[:nr, 3:], g_v[:nr]
+        return (None, g_o, g_d, g_v, None, None, g_sdf, g_k0, g_param_ab) + tuple(g_w) + tuple(g_b)
+
+
+class _VoxurfDeformFn(torch.autograd.Function):
+    """The implicit-deformation branch (voxurf_coarse.py:958-985) with autograd on both sides: (k0.grid, rgbnet and
+    warp_network parameters, rays) -> (rgb_acc, cum_weights, alphainv_last, per-sample [M,14] = gradient | grad_deform |
+    sdf_correct | sdf_deform of every in-box sample).  The backward is the reference's double backward in closed form:
+    rgbnet backward (tcgen05) -> reverse march -> warped-lookup backward (cell Hessian) -> deformation-network backward
+    (tcgen05, csrc/warp_bwd.cu).  The SDF grid is frozen in this branch (:136-138): no gradient is returned for it."""
+
+    @staticmethod
+    def forward(ctx, eng, rays_o, rays_d, viewdirs, jitter, depth, out_range, sdf, k0, ab, *params):
+        rgb, warp = params[:2 * depth], params[2 * depth:]
+        nw = len(warp) // 2
+        eng.load_params(sdf, k0, rgb[:depth], rgb[depth:], float(ab[0]), float(ab[1]))
+        eng.set_warp_network([w.detach() for w in warp[:nw]], [b.detach() for b in warp[nw:]], out_range)
+        rays_o, rays_d, viewdirs = rays_o.contiguous(), rays_d.contiguous(), viewdirs.contiguous()
+        n = rays_o.shape[0]
+        eng.aux = {"depth": torch.empty(n, device=eng.device), "normal": torch.empty((n, 3), device=eng.device)}
+        acc, cumw, last = eng.forward_sums_deform(rays_o, rays_d, viewdirs, jitter, want_samples=True,
+                                                  depth=eng.aux["depth"], normal=eng.aux["normal"])
+        idx, ray_id = eng.inbox_order(n)
+        sout = eng._bufs["sout"][idx]
+        eng.aux.update(idx=idx, ray_id=ray_id, sdf=sout[:, 0])
+        ctx.eng, ctx.depth, ctx.nw = eng, depth, nw
+        ctx.save_for_backward(rays_o, rays_d, viewdirs, jitter if jitter is not None else torch.empty(0), idx)
+        return acc.clone(), cumw.clone(), last.clone(), sout[:, 1:15].contiguous()
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_acc, g_cumw, g_last, g_samp):
+        eng, depth, nw = ctx.eng, ctx.depth, ctx.nw
+        rays_o, rays_d, viewdirs, jitter, idx = ctx.saved_tensors
+        jitter = jitter if jitter.numel() else None
+        eng.grad_flat.zero_()
+        for g in eng.g_ww + eng.g_wb:
+            g.zero_()
+        ext = None
+        if g_samp is not None and idx.numel():
+            ext = torch.zeros((eng._bufs["cap"], 14), dtype=torch.float32, device=eng.device)
+            ext[idx] = g_samp
+        eng.backward_deform_from_ray_grads(rays_o, rays_d, viewdirs, g_acc, g_cumw, g_last, jitter, ext_grad=ext)
+        _, g_k0, g_w, g_b = eng.grid_gradients()
+        g_ww, g_wb = eng.warp_gradients()
+        g_o = g_d = g_v = None
+        if eng.pose_grad:
+            nr = rays_o.shape[0]
+            g_rays, g_v = eng.ray_gradients()
+            g_o, g_d, g_v = g_rays[:nr, :3], g_rays[:nr, 3:], g_v[:nr]
+        return (None, g_o, g_d, g_v, None, None, None, None, g_k0, None) + tuple(g_w) + tuple(g_b) + tuple(g_ww) + \
+            tuple(g_wb)
+
+
+class _LazyResult(dict):
+    """The reference's result dict (voxurf_coarse.py:1069-1091).  Entries the training losses read are tensors with
+    autograd; the per-sample / diagnostic entries the trainer only logs (`weights`, `raw_alpha`, `mask`, `depth`, ...:
+    lib/recon_scene.py:725-736) are computed on first access."""
+
+    def __getitem__(self, key):
+        v = dict.__getitem__(self, key)
+        if callable(v) and not torch.is_tensor(v):
+            v = v()
+            dict.__setitem__(self, key, v)
+        return v
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def items(self):
+        return [(k, self[k]) for k in dict.keys(self)]
+
+    def values(self):
+        return [self[k] for k in dict.keys(self)]
 
 
 class Voxurf(torch.nn.Module):
-    """Surface-stage ``Voxurf`` (lib/voxurf_coarse.py:44-1215) on the fused kernels: the non-deform branch with
-    autograd, the implicit-deformation branch forward only.
+    """Surface-stage ``Voxurf`` (lib/voxurf_coarse.py:44-1215) on the fused kernels, both branches of ``forward`` with
+    autograd: the plain SDF lookup (use_deform=False) and the implicit deformation (use_deform=True, the reference's
+    default and live train step, lib/recon_scene.py:603).
 
     Same parameter names as the reference (``sdf.grid`` [1,1,X,Y,Z], ``k0.grid`` [1,12,X,Y,Z], ``rgbnet.*``,
-    ``sdf_alpha``, ``sdf_beta``, ``s_val``), so ``last_ckpt.tar`` state dicts load with ``strict=False``, and the same
-    ``forward(rays_o, rays_d, viewdirs, global_step=None, **render_kwargs)`` returning the per-ray entries of the
-    reference's result dict (``rgb_marched``, ``alphainv_cum``, ``cum_weights``, ``s_val``); ``inference`` renders
-    through the deformation network (``warp_network.*``, reference keys).  The loss stays in the
-    caller's Python (lib/losses.py); autograd reaches every parameter through two fused kernels per direction plus
-    the tcgen05 rgbnet.  Per-sample entries of the reference's dict (``weights``, ``raw_alpha``, ``gradient`` ...) are
-    not materialised."""
+    ``warp_network.*``, ``sdf_alpha``, ``sdf_beta``, ``s_val``), so ``last_ckpt.tar`` state dicts load with
+    ``strict=False``, and the same ``forward(rays_o, rays_d, viewdirs, use_deform=True, global_step=None,
+    **render_kwargs)`` returning the reference's result dict: ``rgb_marched``, ``alphainv_cum``, ``cum_weights``,
+    ``gradient`` [M,3] of every in-box sample, ``k0_tv`` and (deform) ``grad_deform``, ``sdf_correct``, ``sdf_deform``
+    carry autograd, so lib/losses.py:34-74 runs unchanged on it; ``weights``, ``raw_alpha``, ``raw_rgb``, ``mask``,
+    ``mask_outbbox``, ``depth``, ``disp``, ``normal_marched``, ``s_val`` are detached (the trainer only logs them) and
+    materialised on first access.  Rays that require grad receive the pose gradient.  ``inference`` renders through the
+    deformation network without building a graph."""
 
     def __init__(self, xyz_min, xyz_max, num_voxels=0, num_voxels_base=0, rgbnet_dim=12, rgbnet_depth=3,
                  rgbnet_width=128, posbase_pe=5, viewbase_pe=1, geo_rgb_dim=3, s_ratio=2000, s_start=0.2,
@@ -691,34 +832,34 @@ class Voxurf(torch.nn.Module):
         self.warp_network = DeformedImplicitField(range_shape=self.range_shape)                       # :84-85
         self._eng = None
 
-    def _engine(self, render_kwargs):
+    def _engine(self, render_kwargs, pose_grad=False):
         from .ops import rgbnet_from_sequential
         ws, bs = rgbnet_from_sequential(self.rgbnet)
         key = (float(render_kwargs["near"]), float(render_kwargs["far"]), float(render_kwargs["stepsize"]),
-               float(render_kwargs.get("bg", 0.0)))
+               float(render_kwargs.get("bg", 0.0)), bool(pose_grad))
         if self._eng is None or self._eng_key != key:
             self._eng = FusedVoxurf(self.sdf.grid.detach(), self.k0.grid.detach(), [w.detach() for w in ws],
                                     [b.detach() for b in bs], self.xyz_min.tolist(), self.xyz_max.tolist(),
                                     stepsize=key[2], near=key[0], far=key[1], bg=key[3], s_val=float(self.s_val),
                                     sdf_alpha=float(self.sdf_alpha), sdf_beta=float(self.sdf_beta),
                                     posbase_pe=self.posbase_pe, viewbase_pe=self.viewbase_pe, barf_c2f=self.barf_c2f,
-                                    voxel_size=float(self.voxel_size))
+                                    voxel_size=float(self.voxel_size), pose_grad=pose_grad)
             self._eng_key = key
         return self._eng, ws, bs
 
+    def k0_total_variation(self, k0_tv=1., k0_grad_tv=0.):
+        """voxurf_coarse.py:443-455 (no nonempty mask in this module)."""
+        from .ops import total_variation
+        if k0_grad_tv > 0:
+            raise NotImplementedError
+        return total_variation(self.k0.grid) if k0_tv > 0 else 0
+
     def forward(self, rays_o, rays_d, viewdirs, use_deform=True, global_step=None, **render_kwargs):
-        """Same signature and default as the reference (lib/voxurf_coarse.py:922).  use_deform=False: the plain SDF
-        lookup, differentiable (fused kernels + autograd).  use_deform=True: the implicit-deformation lookup; its
-        render path exists (forward only, = `inference`), training through the deformation network does not yet, so
-        a call that needs gradients fails loudly instead of silently switching branch."""
-        if use_deform:
-            if torch.is_grad_enabled():
-                raise NotImplementedError(
-                    "Voxurf.forward(use_deform=True) with autograd: the backward through the deformation network is "
-                    "not implemented (DESIGN.md section 9); pass use_deform=False, or call under torch.no_grad() / "
-                    "inference() to render through the deformation")
+        """Same signature, default and result dict as the reference (lib/voxurf_coarse.py:922-1091)."""
+        if not torch.is_grad_enabled() and use_deform:
             return self.inference(rays_o, rays_d, viewdirs, global_step=global_step, **render_kwargs)
-        eng, ws, bs = self._engine(render_kwargs)
+        pose = bool(rays_o.requires_grad or rays_d.requires_grad or viewdirs.requires_grad)
+        eng, ws, bs = self._engine(render_kwargs, pose_grad=pose)
         if global_step is not None:                      # neus_alpha_from_sdf_scatter, :485-488, and the BARF progress
             s_val = 1.0 / (global_step + self.s_ratio / self.s_start - self.step_start) * self.s_ratio
             self.s_val.data.fill_(s_val)
@@ -726,13 +867,93 @@ class Voxurf(torch.nn.Module):
         else:
             eng.set_schedule(progress=1.0)
         eng.s_val = float(self.s_val)
-        jitter = torch.rand(rays_o.shape[0], device=rays_o.device) if global_step is not None else None
+        eng._refresh_cfg()
+        n = rays_o.shape[0]
+        # sample_ray_ori's per-ray training jitter (:712-713); render_kwargs['jitter'] pins it (tests, replays)
+        jitter = render_kwargs.get("jitter")
+        if jitter is None and global_step is not None:
+            jitter = torch.rand(n, device=rays_o.device)
         ab = torch.cat([self.sdf_alpha, self.sdf_beta])
-        acc, cumw, last = _VoxurfRenderFn.apply(eng, rays_o, rays_d, viewdirs, jitter, len(ws), self.sdf.grid,
-                                                self.k0.grid, ab, *ws, *bs)
-        rgb_marched = (acc + (1 - cumw[:, None]) * render_kwargs.get("bg", 0.0)).clamp(0, 1)          # :1040-1042
-        return {"alphainv_cum": last, "cum_weights": cumw[:, None], "rgb_marched": rgb_marched,
-                "s_val": float(self.s_val)}
+        bg = render_kwargs.get("bg", 0.0)
+        out = _LazyResult()
+        if use_deform:
+            wws, wbs = self.warp_network.parameters_for_kernel()
+            acc, cumw, last, samp = _VoxurfDeformFn.apply(
+                eng, rays_o, rays_d, viewdirs, jitter, len(ws), self.warp_network.output_range, self.sdf.grid.detach(),
+                self.k0.grid, ab.detach(), *ws, *bs, *wws, *wbs)
+            gradient = samp[:, 0:3]
+            out.update({"sdf_deform": samp[:, 13], "grad_deform": samp[:, 3:12].reshape(-1, 3, 3),
+                        "sdf_correct": samp[:, 12:13]})
+            sdf_s = eng.aux["sdf"]
+        else:
+            acc, cumw, last, samp = _VoxurfRenderFn.apply(eng, rays_o, rays_d, viewdirs, jitter, len(ws), self.sdf.grid,
+                                                          self.k0.grid, ab, *ws, *bs)
+            gradient = samp[:, 1:4]
+            sdf_s = samp[:, 0].detach()
+        rgb_marched = (acc + (1 - cumw[:, None]) * bg).clamp(0, 1)                                     # :1040-1042
+        aux = eng.aux
+        ray_id = aux["ray_id"]
+        dist = float(render_kwargs["stepsize"]) * float(self.voxel_size)
+        memo = {}
+
+        def sample_stats():
+            # alpha / weights of ALL in-box samples from the operators (NeuS alpha, alpha2weight), detached
+            if not memo:
+                from .ops import Alphas2Weights, neus_alpha
+                with torch.no_grad():
+                    alpha = neus_alpha(viewdirs.detach().contiguous(), ray_id, dist, sdf_s.detach().contiguous(),
+                                       gradient.detach().contiguous(), 1.0 / float(self.s_val))
+                    weights, _ = Alphas2Weights.apply(alpha, ray_id, n)
+                memo.update(alpha=alpha, weights=weights)
+            return memo
+
+        def depth():
+            # train-mode definition (:1052-1058): t_min / |d| + sum_i w_i step_i (step in world units)
+            with torch.no_grad():
+                vec = torch.where(rays_d == 0, torch.full_like(rays_d, 1e-6), rays_d)
+                ra, rb = (self.xyz_max - rays_o) / vec, (self.xyz_min - rays_o) / vec
+                t_min = torch.minimum(ra, rb).amax(-1).clamp(min=render_kwargs["near"], max=render_kwargs["far"])
+                return t_min / rays_d.norm(dim=-1) + aux["depth"]
+
+        def dense_mask():
+            S = int(float((self.world_size.float() + 1).norm()) / float(render_kwargs["stepsize"])) + 1      # :700
+            cnt = eng._bufs["dray_cnt"][:n].long()
+            return (torch.arange(S, device=cnt.device)[None, :] < cnt[:, None]).flatten()
+
+        def raw_rgb():
+            # colour of EVERY in-box sample (the fused path only evaluates the composited ones): op-level path
+            from .ops import rgbnet as rgbnet_op
+            with torch.no_grad():
+                pts = eng._bufs["dpts"][aux["idx"], :3]
+                xyz = (pts - self.xyz_min) / (self.xyz_max - self.xyz_min)
+                L, Lv = self.posbase_pe, self.viewbase_pe
+                pf = torch.tensor([2.0 ** i for i in range(L)], device=pts.device)
+                vf = torch.tensor([2.0 ** i for i in range(Lv)], device=pts.device)
+                wp = torch.tensor(barf_weights(eng.progress, self.barf_c2f, L), device=pts.device)
+                wv = torch.tensor(barf_weights(eng.progress, self.barf_c2f, Lv), device=pts.device)
+                xe = (xyz.unsqueeze(-1) * pf).flatten(-2)
+                xe = torch.cat([(xe.sin().view(-1, 3, L) * wp).flatten(-2), (xe.cos().view(-1, 3, L) * wp).flatten(-2)], -1)
+                vd = viewdirs.detach()
+                ve = (vd.unsqueeze(-1) * vf).flatten(-2)
+                ve = torch.cat([(ve.sin().view(-1, 3, Lv) * wv).flatten(-2), (ve.cos().view(-1, 3, Lv) * wv).flatten(-2)], -1)
+                g = gradient.detach()
+                feat = torch.cat([self.k0(pts), xyz, xe, torch.cat([vd, ve], -1)[ray_id],
+                                  g / (g.norm(dim=-1, keepdim=True) + 1e-5)], -1)
+                return rgbnet_op(feat.contiguous(), [w.detach() for w in ws], [b.detach() for b in bs], True)
+
+        out.update({
+            "alphainv_cum": last, "cum_weights": cumw[:, None], "rgb_marched": rgb_marched, "gradient": gradient,
+            "s_val": float(self.s_val), "k0_tv": self.k0_total_variation(),
+            "weights": lambda: sample_stats()["weights"], "raw_alpha": lambda: sample_stats()["alpha"],
+            "raw_rgb": raw_rgb, "ray_id": ray_id,
+            "normal_marched": aux["normal"] if render_kwargs.get("render_grad", False) else None,
+            "depth": depth, "disp": lambda: 1 / out["depth"],
+            # `mask` = ~mask_outbbox over the DENSE [N * S] sample grid before the compaction (:937-944; the trainer
+            # logs its mean): the per-ray in-box counts are exact, the flags are packed at the start of each ray's
+            # row.  After the compaction every remaining sample is inside the box.
+            "mask": dense_mask, "mask_outbbox": lambda: torch.zeros_like(ray_id, dtype=torch.bool),
+        })
+        return out
 
     def _rgbnet_params(self):
         from .ops import rgbnet_from_sequential
@@ -744,7 +965,8 @@ class Voxurf(torch.nn.Module):
         """Voxurf.inference (lib/voxurf_coarse.py:1093-1215): render with the implicit deformation - SDF and normal
         of every in-box sample from the warped template lookup - forward only.  Returns the per-ray entries that
         lib/nvs_fun.py:74-88 reads: rgb_marched, alphainv_cum, cum_weights, depth, disp, normal_marched."""
-        eng, _, _ = self._engine(render_kwargs)
+        render_kwargs.pop("training", None)
+        eng, _, _ = self._engine(render_kwargs, pose_grad=self._eng_key[4] if self._eng is not None else False)
         ws, bs = self.warp_network.parameters_for_kernel()
         eng.load_params(self.sdf.grid, self.k0.grid, *self._rgbnet_params(), float(self.sdf_alpha),
                         float(self.sdf_beta))

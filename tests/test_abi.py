@@ -127,6 +127,22 @@ def test_c_abi_argument_validation():
     assert lib.pp_warpnet_forward_packed(None, 0, 5, 128, None, None, None, None, None) == 0       # empty: no-op
     assert lib.pp_warpnet_forward_packed(None, 8, 5, 128, None, None, None, None, None) == -1
     assert lib.pp_warpnet_pack_points(None, 4, None, None) == -1
-    assert lib.pp_voxurf_deform_rows(None, None, None, None, 4, 4, None, None, None, None, None) == -1
+    assert lib.pp_voxurf_deform_rows(None, None, None, None, 4, 4, None, None, None, None, None, None) == -1
     assert lib.pp_voxurf_deform_sample_backward(None, None, None, None, None, None, 4, 1.0, 0, 0, 0, 0, None, None,
-                                                None, None) == -1
+                                                None, None, None) == -1
+    assert lib.pp_voxurf_deform_sample_forward(None, None, None, None, None, 4, 1.0, None, None, None) == -1
+    assert lib.pp_voxurf_deform_ray_grad(None, None, None, None, 4, None, None, None, None) == -1
+    assert lib.pp_voxurf_sample_records(None, None, None, None, 4, None, None) == -1
+    assert lib.pp_voxurf_sample_records_backward(None, None, None, None, 4, None, 0.0, None, None, None) == -1
+    assert lib.pp_voxurf_object_loss(4, None, None, None, None, None, 0.0, 1.0, 0.0, 0.0, None, None, None, None, None,
+                                     None, None) == -1
+    assert lib.pp_voxurf_k0_tv(None, None, None, 1.0, None, None) == -1
+    # deformation network backward: depth 5 / width 128 only, rows in fours, null pointers rejected
+    assert lib.pp_warpnet_backward_packed(None, None, 6, None, 5, 128, None, None, None, None, None, None) == -1
+    assert lib.pp_warpnet_backward_packed(None, None, 8, None, 4, 128, None, None, None, None, None, None) == -5
+    assert lib.pp_warpnet_backward_packed(None, None, 8, None, 5, 64, None, None, None, None, None, None) == -5
+    assert lib.pp_warpnet_backward_packed(None, None, 0, None, 5, 128, None, None, None, None, None, None) == 0
+    assert lib.pp_warpnet_backward_packed(None, None, 8, None, 5, 128, None, None, None, None, None, None) == -1
+    assert lib.pp_warpnet_backward_workspace_bytes() >= 4 and lib.pp_warpnet_backward_stalled() == 0
+    assert lib.pp_peer_sync_timed_out(None) == 0
+    assert lib.pp_adam_upd(0, 4, None, None, None, None, None, 4, 1, 0.9, 0.99, 0.1, 1e-8, None) == -1   # modes 0..3

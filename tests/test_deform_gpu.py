@@ -505,3 +505,145 @@ def test_deform_train_step_reduces_the_live_loss(cuda):
     assert float(lb[4]) > 0                                               # the k0 TV term was evaluated
     # the kernel-side copy of the doubled first layer follows the master weights
     torch.testing.assert_close(eng.warp[0][0], torch.cat([eng.warp_w[0], eng.warp_w[0]], 1))
+
+
+# ---- the nn.Module against the reference's own code (golden replays) ---------------------------------------------
+def _golden_module(cuda, g, n_iters):
+    import poseprobe_b200 as pp
+    t = lambda k: torch.from_numpy(g[k])  # noqa: E731
+    G = g["sdf"].shape[-1]
+    m = pp.Voxurf(MN, MX, num_voxels=G ** 3, num_voxels_base=G ** 3, rgbnet_depth=3, barf_c2f=[0.1, 0.5],
+                  N_iters=n_iters, s_ratio=50, s_start=0.2).to(cuda)
+    with torch.no_grad():
+        m.sdf.grid.copy_(t("sdf"))
+        m.k0.grid.copy_(torch.from_numpy(g["k0"].astype("float32")))
+        lin = [q for q in m.rgbnet.modules() if isinstance(q, nn.Linear)]
+        for i, q in enumerate(lin):
+            q.weight.copy_(t("w%d" % i))
+            q.bias.copy_(t("b%d" % i))
+        m.sdf_alpha.fill_(10.0)
+        m.sdf_beta.fill_(0.35)
+    assert abs(float(m.voxel_size) - float(g["voxel_size"])) < 1e-6
+    return m, t
+
+
+@pytest.mark.parametrize("tag", ["eval", "train"])
+def test_voxurf_module_replays_the_references_forward(cuda, tag):
+    """pp.Voxurf.forward(use_deform=False) against tests/golden/voxurf_forward.npz = the reference's OWN
+    Voxurf.forward executed on the CPU (tests/golden/make_golden_voxurf.py), eval and train mode (jitter, BARF progress,
+    s_val schedule): every entry of the result dict the callers read (voxurf_coarse.py:1069-1091; lib/losses.py:39-66,
+    lib/recon_scene.py:725-736).  Per-ray outputs pass the bf16 colour network: 2e-2; geometry-only entries 2e-4."""
+    import os
+    import numpy as np
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "voxurf_forward.npz"))
+    m, t = _golden_module(cuda, g, int(g["N_iters"]))
+    o, d, v = t("rays_o").to(cuda), t("rays_d").to(cuda), t("viewdirs").to(cuda)
+    kw = dict(near=0.2, far=1e9, stepsize=0.5, bg=0.3)
+    if tag == "train":
+        out = m(o, d, v, use_deform=False, global_step=int(g["gstep"]), jitter=t("train_jitter").to(cuda), **kw)
+    else:
+        with torch.no_grad():
+            m.s_val.fill_(float(g["eval_s_val"]))
+        out = m(o, d, v, use_deform=False, **kw)
+    w = lambda k: t("%s_%s" % (tag, k))  # noqa: E731
+    assert abs(out["s_val"] - float(g[tag + "_s_val"])) < 1e-6
+    M = g[tag + "_weights"].shape[0]
+    assert out["weights"].shape == (M,) and out["gradient"].shape == (M, 3) and out["raw_rgb"].shape == (M, 3)
+    torch.testing.assert_close(out["gradient"].detach().cpu(), w("gradient"), rtol=1e-4, atol=2e-4)
+    torch.testing.assert_close(out["raw_alpha"].cpu(), w("raw_alpha"), rtol=0, atol=2e-4)
+    torch.testing.assert_close(out["weights"].cpu(), w("weights"), rtol=0, atol=2e-4)
+    torch.testing.assert_close(out["cum_weights"].detach().cpu(), w("cum_weights"), rtol=0, atol=2e-4)
+    torch.testing.assert_close(out["alphainv_cum"].detach().cpu(), w("alphainv_cum"), rtol=0, atol=2e-4)
+    torch.testing.assert_close(out["rgb_marched"].detach().cpu(), w("rgb_marched"), rtol=0, atol=2e-2)
+    torch.testing.assert_close(out["raw_rgb"].cpu(), w("raw_rgb"), rtol=0, atol=3e-2)
+    torch.testing.assert_close(out["depth"].cpu(), w("depth"), rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(out["disp"].cpu(), 1 / w("depth"), rtol=1e-3, atol=1e-4)
+    assert abs(float(out["k0_tv"]) - float(g[tag + "_k0_tv"])) < 1e-5 * max(1.0, float(g[tag + "_k0_tv"]))
+    assert out["mask"].dtype == torch.bool and int(out["mask"].sum()) == M and not bool(out["mask_outbbox"].any())
+    assert set(["alphainv_cum", "weights", "cum_weights", "rgb_marched", "normal_marched", "raw_alpha", "raw_rgb", "depth",
+                "disp", "mask", "mask_outbbox", "gradient", "s_val", "k0_tv"]) <= set(out.keys())
+
+
+def test_voxurf_module_deform_branch_trains_with_the_references_losses(cuda):
+    """pp.Voxurf.forward(use_deform=True) - the reference's default and live train step (recon_scene.py:603) - under
+    autograd with the reference's loss written in plain Python on the result dict (deform_implicit_loss +
+    photometric term, exactly the combination of tests/golden/make_golden_deform.py): the forward entries and every
+    parameter gradient against tests/golden/voxurf_deform.npz (the reference's own double backward)."""
+    import os
+    import numpy as np
+    import torch.nn.functional as F
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "voxurf_deform.npz"))
+    m, t = _golden_module(cuda, g, int(g["N_iters"]))
+    with torch.no_grad():
+        for lin, i in zip(m.warp_network.linears(), range(5)):
+            lin.weight.copy_(t("ww%d" % i))
+            lin.bias.copy_(t("wb%d" % i))
+    assert abs(m.warp_network.output_range - float(g["out_range"])) < 1e-6
+    o = t("rays_o").to(cuda).requires_grad_(True)
+    d = t("rays_d").to(cuda).requires_grad_(True)
+    v = t("viewdirs").to(cuda)
+    out = m(o, d, v, global_step=int(g["gstep"]), jitter=t("jitter").to(cuda), near=0.2, far=1e9, stepsize=0.5, bg=0.3)
+    M = g["ret_weights"].shape[0]
+    assert out["gradient"].shape == (M, 3) and out["grad_deform"].shape == (M, 3, 3)
+    assert out["sdf_correct"].shape == (M, 1) and out["sdf_deform"].shape == (M,)
+    torch.testing.assert_close(out["sdf_correct"].detach().cpu(), t("ret_sdf_correct"), rtol=0, atol=1e-4)
+    torch.testing.assert_close(out["sdf_deform"].detach().cpu(), t("ret_sdf_deform"), rtol=0, atol=2e-4)
+    err = (out["grad_deform"].detach().cpu() - t("ret_grad_deform")).flatten(1).norm(dim=1)
+    assert float((err < 5e-3).float().mean()) > 0.9 and float(err.median()) < 1e-3       # gate flips, see above
+    torch.testing.assert_close(out["rgb_marched"].detach().cpu(), t("ret_rgb_marched"), rtol=0, atol=2e-2)
+    torch.testing.assert_close(out["weights"].cpu(), t("ret_weights"), rtol=0, atol=5e-3)
+    # lib/losses.py:6-24 on the dict, as the reference's trainer combines it
+    grad_constraint = (out["gradient"].norm(dim=-1) - 1).abs().mean()
+    loss = F.mse_loss(out["rgb_marched"], t("target").to(cuda)) + grad_constraint + 0.05 * (
+        out["grad_deform"].norm(dim=-1).mean() + out["sdf_correct"].abs().mean() + out["sdf_deform"].abs().mean())
+    assert abs(float(loss) - float(g["loss"])) < 1e-2 * float(g["loss"])
+    loss.backward()
+
+    def check(name, got, want, c_min=0.999, n_tol=0.01):
+        got, want = got.detach().cpu().reshape(-1), want.reshape(-1)
+        c = float((got * want).sum() / (got.norm() * want.norm() + 1e-30))
+        r = float(got.norm() / (want.norm() + 1e-30))
+        assert c >= c_min and abs(r - 1) <= n_tol, (name, c, r)
+
+    for i, lin in enumerate(m.warp_network.linears()):
+        check("warp weight %d" % i, lin.weight.grad, t("g_ww%d" % i))
+        check("warp bias %d" % i, lin.bias.grad, t("g_wb%d" % i), c_min=0.998, n_tol=0.02)
+    for i, lin in enumerate([q for q in m.rgbnet.modules() if isinstance(q, nn.Linear)]):
+        check("rgbnet weight %d" % i, lin.weight.grad, t("g_w%d" % i))
+        check("rgbnet bias %d" % i, lin.bias.grad, t("g_b%d" % i))
+    want_k0 = torch.zeros(m.k0.grid.numel())
+    want_k0[torch.from_numpy(g["g_k0_idx"]).long()] = t("g_k0_val")
+    check("k0", m.k0.grid.grad, want_k0)
+    check("rays_o", o.grad, t("g_rays_o"), c_min=0.99, n_tol=0.03)
+    check("rays_d", d.grad, t("g_rays_d"), c_min=0.99, n_tol=0.03)
+    assert m.sdf.grid.grad is None or float(m.sdf.grid.grad.abs().max()) == 0.0       # frozen in this branch
+
+
+def test_fused_step_eikonal_term_on_all_inbox_samples(cuda):
+    """Non-deform fused step with the live Eikonal term (lib/losses.py:7-10, weight 1.0, mean over ALL in-box samples,
+    also past the early termination): SDF gradient of backward_only(w_eikonal=1) minus that of w_eikonal=0 against
+    autograd through the oracle's `gradient`."""
+    from oracle import voxurf_cpu
+    from poseprobe_b200 import ops, voxurf
+    G, N = 24, 300
+    sdf, k0, net, o, d, v, kw = make_scene(G, N, seed=81)
+    target = torch.rand(N, 3)
+    rw, rb = ops.rgbnet_from_sequential(net)
+    grads = []
+    for w_eik in (0.0, 1.0):
+        eng = voxurf.FusedVoxurf(sdf.to(cuda), k0.to(cuda), [w.detach() for w in rw], [b.detach() for b in rb], MN, MX,
+                                 w_eikonal=w_eik, **kw)
+        eng.backward_only(o.to(cuda), d.to(cuda), v.to(cuda), target.to(cuda))
+        grads.append(eng.grid_gradients()[0].cpu())
+        if w_eik:
+            term = float(eng._bufs["reg"][0])
+    sdf_r = sdf.clone().requires_grad_(True)
+    want = voxurf_cpu.forward(sdf_r, k0, net, o, d, v, MN, MX, kw["stepsize"], eng.voxel_size, kw["s_val"], bg=kw["bg"],
+                              sdf_alpha=kw["sdf_alpha"], sdf_beta=kw["sdf_beta"], posbase_pe=5, viewbase_pe=1,
+                              barf_c2f=kw["barf_c2f"], progress=1.0)
+    eik = (want["gradient"].norm(dim=-1) - 1).abs().mean()
+    (g_ref,) = torch.autograd.grad(eik, [sdf_r])
+    assert abs(term - float(eik)) < 1e-4 * max(1.0, float(eik))
+    got = grads[1] - grads[0]
+    rel = float((got - g_ref).norm() / g_ref.norm())
+    assert rel < 2e-3, rel
