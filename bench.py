@@ -33,6 +33,7 @@ N_BATCHES = 8          # distinct ray batches cycled through the timed region
 # dram__bytes_read.sum + dram__bytes_write.sum of one train-mode march launch, from the committed ncu
 # capture profiles/r1_march_train_full.txt (per launch, like `achieved`)
 MARCH_DRAM_TRAFFIC_BYTES = 350.9e6
+MARCH_TRAFFIC_PROFILE = "profiles/r1f_dvgo_march_kernel_full.txt"
 XYZ_MIN, XYZ_MAX = [-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]
 
 
@@ -99,49 +100,57 @@ def make_batches(n_batches, n_rays, rank):
 # =================================================================================================
 # reference arm: the reference's own pure-PyTorch CPU formulation (lib/dvgo_ori.py), host cores
 # =================================================================================================
+def _load_by_path(name, rel):
+    """Import a module of this repo by file path (the reference arm must not map the product's CUDA library, which
+    `import poseprobe_b200` would do)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, rel))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def make_batches_cpu(n_batches, n_rays, rank):
+    synthetic = _load_by_path("_pp_synthetic", "poseprobe_b200/synthetic.py")
+    out = []
+    for b in range(n_batches):
+        o, d, _ = synthetic.make_rays(n_rays, seed=777 + 1000 * rank + b)
+        tgt = torch.rand(n_rays, 3, generator=torch.Generator().manual_seed(99 + 1000 * rank + b))
+        out.append((o, d, tgt))
+    return out, synthetic
+
+
 def run_reference(args, rank):
+    """The reference's own CPU formulation of the path (lib/dvgo_ori.py: grid_sample + cumprod compositing + Python
+    Adam, restated in oracle/dvgo_cpu.py and pinned against the reference's code) on the SAME workload: every step is
+    the full 8192-ray batch on the 160^3 grid, all host threads.  Rank 0 only."""
     if rank != 0:
         return
     from oracle import dvgo_cpu
-    from poseprobe_b200 import synthetic
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    batches, synthetic = make_batches_cpu(1, RAYS, 0)
     density, k0 = synthetic.make_dvgo_grids(GRID)
     base = dvgo_cpu.DenseBaseline(density, k0, XYZ_MIN, XYZ_MAX, STEPSIZE)
-    o, d, tgt = make_batches(1, RAYS, 0)[0]
-    n = bounded_sample_rays(base, o, d, tgt, budget_s=4.0)
+    o, d, tgt = batches[0]
     for _ in range(args.warmup):
-        base.train_step(o[:n], d[:n], tgt[:n])
+        base.train_step(o, d, tgt)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        base.train_step(o[:n], d[:n], tgt[:n])
+        base.train_step(o, d, tgt)
     dt = time.perf_counter() - t0
-    value = n * args.steps / dt
+    value = RAYS * args.steps / dt
     line = {
         "impl": "reference", "metric": "train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.gpus),
         "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port",
-                         "sample": "%d of %d rays per step, lib/dvgo_ori.py dense formulation "
-                                   "(grid_sample + cumprod + Python Adam) restated in oracle/dvgo_cpu.py" % (n, RAYS)},
+                         "sample": "all %d rays of the batch every step, lib/dvgo_ori.py dense formulation "
+                                   "(grid_sample + cumprod + Python Adam) restated in oracle/dvgo_cpu.py" % RAYS},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
-
-
-def bounded_sample_rays(base, o, d, tgt, budget_s):
-    """Largest ray count (multiple of 256, <= RAYS) whose CPU step fits the time budget: two probe steps
-    give the fixed (dense Adam over the whole grid) and per-ray costs."""
-    times = []
-    for n in (256, 1024):
-        t0 = time.perf_counter()
-        base.train_step(o[:n], d[:n], tgt[:n])
-        times.append(time.perf_counter() - t0)
-    per_ray = max((times[1] - times[0]) / (1024 - 256), 1e-6)
-    fixed = max(times[0] - 256 * per_ray, 0.0)
-    n = int((budget_s - fixed) / per_ray)
-    return max(256, min(RAYS, (n // 256) * 256))
 
 
 def workload_config(n_gpus):
@@ -149,7 +158,8 @@ def workload_config(n_gpus):
                         "stepsize 0.5, fwd+bwd+masked Adam, TV off",
             "grid": GRID, "rays_per_gpu": RAYS, "global_rays": RAYS * n_gpus, "stepsize": STEPSIZE,
             "l2": "no flush: per-step working set (vox+grad+2 Adam moments = 262 MB) exceeds the 126 MB L2",
-            "parallelism": "ray-sharded replicas, grid-gradient all-reduce (NCCL)" if n_gpus > 1 else "single GPU"}
+            "parallelism": ("ray-sharded replicas (dp%d), voxel-sharded optimiser" % n_gpus) if n_gpus > 1
+            else "single GPU"}
 
 
 # =================================================================================================
@@ -207,20 +217,32 @@ def run_ours(args, rank, world, local_rank):
     barrier()
 
     # ---- timed region (device timed, max over ranks) ----
+    # A block = EXACTLY args.steps steps between a barrier + synchronize on both sides.  One block of 20 steps is
+    # only ~6 ms of device time, so the block is repeated until >= 0.5 s has been timed and the MEDIAN block is the
+    # reported one (min / max alongside); the repeat count is agreed on rank 0's first block.
+    def timed_block(with_events):
+        k_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)] if with_events else None
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record()
+        for i in range(args.steps):
+            step(*resident[i % N_BATCHES], events=k_ev[i] if with_events else None)
+        b.record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms), k_ev
+
     launches0 = pp._lib.launch_count()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    k_ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    barrier()
-    ev[0].record()
-    for i in range(args.steps):
-        step(*resident[i % N_BATCHES], events=k_ev[i])
-    ev[1].record()
-    barrier()
+    first_ms, k_ev = timed_block(True)
     launches = pp._lib.launch_count() - launches0
-    ms = torch.tensor([ev[0].elapsed_time(ev[1])], device=dev)
+    n_blocks = torch.tensor([min(200, max(1, int(500.0 / max(first_ms, 1e-3)) + 1))], device=dev)
     if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms)
+        dist.broadcast(n_blocks, 0)
+    block_ms = [first_ms] + [timed_block(False)[0] for _ in range(int(n_blocks) - 1)]
+    block_ms.sort()
+    ms_total = block_ms[len(block_ms) // 2]
     march_ms = sum(e[0].elapsed_time(e[1]) for e in k_ev) / args.steps
     tail_ms = sum(e[1].elapsed_time(e[2]) for e in k_ev) / args.steps
 
@@ -230,19 +252,23 @@ def run_ours(args, rank, world, local_rank):
     host_packed = [torch.stack(b).pin_memory() for b in host]
     dpack = torch.empty(tuple(host_packed[0].shape), dtype=torch.float32, device=dev)
     loss_host = torch.zeros(2).pin_memory()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        dpack.copy_(host_packed[i % N_BATCHES], non_blocking=True)
-        loss_host.copy_(step(dpack[0], dpack[1], dpack[2]), non_blocking=True)
-        stream.synchronize()              # the caller reads the loss of every step
-    e1.record()
-    barrier()
-    e2e_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_ms = float(e2e_ms)
+    def e2e_block():
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            dpack.copy_(host_packed[i % N_BATCHES], non_blocking=True)
+            loss_host.copy_(step(dpack[0], dpack[1], dpack[2])[:2], non_blocking=True)
+            stream.synchronize()              # the caller reads the loss of every step
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    e2e_blocks = sorted(e2e_block() for _ in range(int(n_blocks)))
+    e2e_ms = e2e_blocks[len(e2e_blocks) // 2]
     # ---- forward-only render throughput (the metric's "render Mrays/s"): rays are sharded, no communication ----
     render_iters = 40
     for i in range(3):
@@ -258,6 +284,23 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(render_ms, op=dist.ReduceOp.MAX)
     render_ms = float(render_ms) / render_iters
+    # the same through the public API with host buffers: ray chunk in (pinned), rgb + depth out (pinned), every chunk
+    rgb_host = torch.empty((RAYS, 3)).pin_memory()
+    depth_host = torch.empty(RAYS).pin_memory()
+    barrier()
+    r0.record()
+    for i in range(render_iters):
+        dpack.copy_(host_packed[i % N_BATCHES], non_blocking=True)
+        out = eng.render(dpack[0], dpack[1], want_depth=True)
+        rgb_host.copy_(out[0], non_blocking=True)
+        depth_host.copy_(out[2], non_blocking=True)
+        stream.synchronize()
+    r1.record()
+    barrier()
+    render_e2e_ms = torch.tensor([r0.elapsed_time(r1)], device=dev)
+    if world > 1:
+        dist.all_reduce(render_e2e_ms, op=dist.ReduceOp.MAX)
+    render_e2e_ms = float(render_e2e_ms) / render_iters
     # keep the GPU busy a little longer so the clock sampler sees the loaded state (the timed region is short)
     t_end = time.perf_counter() + 0.6
     i = 0
@@ -278,6 +321,13 @@ def run_ours(args, rank, world, local_rank):
         names = ["sync_gradients_ms", "exchange_adam_kernel_ms", "sync_params_ms", "zero_grad_ms"]
         exchange_breakdown = {nm: sum(e[k].elapsed_time(e[k + 1]) for e in evs) / len(evs) for k, nm in enumerate(names)}
 
+    fine_dist = None
+    if world > 1 and not args.no_fine_stage:
+        try:     # BASELINE configs[2] on N ranks (every rank takes part: collective inside)
+            fine_dist = fine_stage_dist_bench(dev, rank, world)
+        except Exception as e:
+            fine_dist = {"error": str(e)[:200]}
+
     if rank != 0:
         if trainer is not None:
             trainer.close()
@@ -295,37 +345,49 @@ def run_ours(args, rank, world, local_rank):
     step_gbs = step_bytes / (ms_total / args.steps * 1e-3) / 1e9
     value = world * RAYS * args.steps / (ms_total * 1e-3)
     cfg = workload_config(world)
+    exchange = None
     if world > 1:
-        cfg["exchange"] = {
+        exchange = {
             "nvls": "ONE kernel: in-switch gradient reduction (multimem.ld_reduce) + masked Adam on 1/N of the "
                     "voxels + multicast parameter store (multimem.st); peer-memory flag barriers, no NCCL on the step",
             "p2p": "ONE kernel: peer-load reduce-scatter + masked Adam on 1/N of the voxels + peer-store all-gather",
             "nccl": "NCCL all-reduce of the gradient records + full Adam on every rank"}[trainer.mode]
-        cfg["parallelism"] = "ray-sharded replicas (dp%d), voxel-sharded optimiser" % world
     line = {
         "metric": "train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": cfg,
+        "timing": {"blocks": len(block_ms), "steps_per_block": args.steps, "reported": "median block",
+                   "ms_per_step_min": block_ms[0] / args.steps, "ms_per_step_max": block_ms[-1] / args.steps,
+                   "timed_s": sum(block_ms) * 1e-3},
         "samples_per_ray": m_bar / RAYS,
         "roofline": {"bound": "hbm", "kernel": "dvgo_march_kernel<train> (gather + composite + loss + scatter)",
                      "achieved": march_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": march_gbs / pk["hbm_gbs"],
                      "peak_kind": pk_kind, "algorithmic_bytes_per_launch": sparse_bytes,
-                     "ms_per_launch": march_ms, "traffic": MARCH_DRAM_TRAFFIC_BYTES},
+                     "ms_per_launch": march_ms, "traffic": MARCH_DRAM_TRAFFIC_BYTES,
+                     "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one launch in the committed ncu "
+                                       "--set full capture " + MARCH_TRAFFIC_PROFILE + " (not re-measured by this run)"},
         "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "achieved": step_gbs,
                           "frac": step_gbs / pk["hbm_gbs"], "march_ms": march_ms,
                           "exchange_plus_adam_ms": tail_ms},
         "e2e": {"value": world * RAYS * args.steps / (e2e_ms * 1e-3), "unit": "rays/s",
                 "h2d_bytes_per_step": sum(t.numel() * 4 for t in host[0]), "d2h_bytes_per_step": 8,
-                "ms_per_step": e2e_ms / args.steps},
+                "ms_per_step": e2e_ms / args.steps, "blocks": len(e2e_blocks),
+                "ms_per_step_min": e2e_blocks[0] / args.steps, "ms_per_step_max": e2e_blocks[-1] / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "render": {"metric": "render_mrays_per_s", "value": world * RAYS / (render_ms * 1e-3) / 1e6, "unit": "Mrays/s",
                    "ms_per_chunk": render_ms, "workload": "forward only (rgb, depth, alphainv_last), same 160^3 grid, "
                    "%d-ray chunks per GPU, device timed" % RAYS,
                    "achieved_gbs": (48 * RAYS + 32 * (C_d + C_f) * m_bar) / (render_ms * 1e-3) / 1e9,
-                   "frac_of_hbm_peak": (48 * RAYS + 32 * (C_d + C_f) * m_bar) / (render_ms * 1e-3) / 1e9 / pk["hbm_gbs"]},
+                   "frac_of_hbm_peak": (48 * RAYS + 32 * (C_d + C_f) * m_bar) / (render_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+                   "e2e": {"value": world * RAYS / (render_e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s",
+                           "ms_per_chunk": render_e2e_ms, "h2d_bytes_per_chunk": 2 * RAYS * 12,
+                           "d2h_bytes_per_chunk": RAYS * 16,
+                           "what": "pinned host rays in, rgb + depth out to pinned host, synchronised per chunk"}},
     }
+    if exchange:
+        line["exchange"] = exchange
     if exchange_breakdown:
         line["step_roofline"]["exchange_breakdown"] = exchange_breakdown
     if world == 1:
@@ -355,6 +417,8 @@ def run_ours(args, rank, world, local_rank):
             line["fine_stage"] = fine_stage_bench(dev)
         except Exception as e:   # an extra, never allowed to take the headline line down
             line["fine_stage"] = {"error": str(e)[:200]}
+    if fine_dist is not None:
+        line["fine_stage"] = fine_dist
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
     print(json.dumps(line))
@@ -422,7 +486,57 @@ def fine_stage_bench(dev):
                                  "in-box sample + warped SDF lookup + rgbnet, %d-ray chunks, forward only" % RAYS,
                      "render_mrays_per_s": RAYS / (ms_r * 1e-3) / 1e6, "ms_per_chunk": ms_r,
                      "inbox_samples_per_ray": n_in / RAYS, "warp_network_tflop_per_chunk": warp_flops / 1e12}
-    return {"render_deform": render_deform,
+    # the reference's LIVE train step (lib/recon_scene.py:603): through the deformation network with the full object
+    # loss (photometric with mask, entropy, mask BCE, k0 TV, Eikonal over all in-box samples, three deformation priors),
+    # SDF grid frozen, dense reference Adam on feature grid / rgbnet / deformation network
+    eng.set_loss_weights(w_entropy=0.01, w_mask=0.1, w_tv_k0=0.01, w_eikonal=1.0, w_deform=0.05)
+    msk = [(torch.rand(RAYS, generator=torch.Generator().manual_seed(5 + b)) > 0.2).float().to(dev) for b in range(4)]
+    for i in range(3):
+        eng.train_step(*batches[i % 4], use_deform=True, mask=msk[i % 4])
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(10):
+        eng.train_step(*batches[i % 4], use_deform=True, mask=msk[i % 4])
+    e1.record()
+    torch.cuda.synchronize()
+    ms_d = e0.elapsed_time(e1) / 10
+    n_in = eng._bufs["dcounter"].tolist()[0]
+    m_c = eng.n_samples()
+    # the deformation network's backward alone, on the buffers the last step left behind
+    import ctypes
+    from poseprobe_b200._lib import check, lib, ptr, stream as cur_stream
+    b = eng._bufs
+    wws_k, wbs_k, _ = eng.warp
+    arr = lambda ts: (ctypes.c_void_p * len(ts))(*[t.data_ptr() for t in ts])  # noqa: E731
+    scratch_w = [torch.zeros_like(t) for t in eng.g_ww]
+    scratch_b = [torch.zeros_like(t) for t in eng.g_wb]
+
+    def warp_bwd():
+        check(lib.pp_warpnet_backward_packed(ptr(b["drows"]), ptr(b["g_dout"]), 4 * b["cap"], ptr(b["dcounter"][2:]), 5,
+                                             128, arr(wws_k), arr(wbs_k), arr(scratch_w), arr(scratch_b),
+                                             ptr(eng._warp_work), cur_stream()), "warpnet_backward")
+    warp_bwd()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+        warp_bwd()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_wb = e0.elapsed_time(e1) / 5
+    fwd_flops_row = 2.0 * (16 * 128 + 3 * 128 * 128 + 128 * 16)
+    tflops_pk = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
+    train_deform = {
+        "workload": "Voxurf.forward(use_deform=True) train step (recon_scene.py:603): warp network fwd+Jacobian and its "
+                    "tcgen05 backward on every in-box sample, rgbnet fwd/bwd, full object loss (lib/losses.py:34-74), "
+                    "dense Adam; %d rays/step" % RAYS,
+        "train_rays_per_s": RAYS / (ms_d * 1e-3), "ms_per_step": ms_d, "inbox_samples_per_ray": n_in / RAYS,
+        "composited_samples_per_ray": m_c / RAYS, "stalled": int(lib.pp_warpnet_backward_stalled()),
+        "warp_backward": {"ms": ms_wb, "rows": 4 * n_in,
+                          "algorithmic_tflop": 3 * fwd_flops_row * 4 * n_in / 1e12,
+                          "algorithmic_tflops_per_s": 3 * fwd_flops_row * 4 * n_in / 1e12 / (ms_wb * 1e-3),
+                          "frac_of_tensor_peak": 3 * fwd_flops_row * 4 * n_in / 1e12 / (ms_wb * 1e-3) / tflops_pk,
+                          "note": "recompute + dH + dW = 3x the forward flops; tensor-pipe %% from ncu in profiles/"}}
+    return {"render_deform": render_deform, "train_deform": train_deform,
             "workload": "Voxurf SDF fine stage (BASELINE configs[2], one rank): 160^3 sdf + 12-ch k0 + rgbnet "
                         "57-128-128-128-3 (tcgen05), 8192 rays/step, fwd+bwd+Adam",
             "train_rays_per_s": RAYS / (ms * 1e-3), "ms_per_step": ms, "composited_samples_per_ray": m / RAYS,
@@ -433,25 +547,69 @@ def fine_stage_bench(dev):
                 pk.get("bf16_tflops_sustained", pk["bf16_tflops"]) * 1e12) * 1e3) / ms}
 
 
+def fine_stage_dist_bench(dev, rank, world):
+    """BASELINE configs[2] on N ranks: Voxurf fine stage ray-sharded over the ranks (8192 rays per rank), ONE flat
+    gradient all-reduce over NVLink per step, identical optimiser step on every replica."""
+    import torch.distributed as dist
+    import torch.nn as nn
+    from poseprobe_b200 import ops, synthetic, voxurf
+    torch.manual_seed(777)
+    sdf = synthetic.make_sdf_grid(GRID, radius=0.5, noise=0.02)
+    k0 = 0.1 * torch.randn(1, 12, GRID, GRID, GRID)
+    net = nn.Sequential(nn.Linear(57, 128), nn.ReLU(inplace=True),
+                        nn.Sequential(nn.Linear(128, 128), nn.ReLU(inplace=True)),
+                        nn.Sequential(nn.Linear(128, 128), nn.ReLU(inplace=True)), nn.Linear(128, 3))
+    nn.init.constant_(net[-1].bias, 0)
+    ws, bs = ops.rgbnet_from_sequential(net)
+    tr = voxurf.DistributedVoxurf(sdf.to(dev), k0.to(dev), [w.detach() for w in ws], [b.detach() for b in bs], XYZ_MIN,
+                                  XYZ_MAX, stepsize=STEPSIZE, s_val=0.05, bg=0.0, sdf_alpha=10.0, sdf_beta=0.35,
+                                  posbase_pe=5, viewbase_pe=1, lr_sdf=1e-4, lr_k0=1e-2, lr_rgbnet=1e-3, pose_grad=True)
+    batches = []
+    for b in range(4):
+        o, d, v = synthetic.make_rays(RAYS, seed=777 + 1000 * rank + b)
+        t = torch.rand(RAYS, 3, generator=torch.Generator().manual_seed(99 + 1000 * rank + b))
+        batches.append(tuple(x.to(dev) for x in (o, d, v, t)))
+    for i in range(3):
+        tr.train_step(*batches[i % 4])
+    dist.barrier()
+    torch.cuda.synchronize()
+    steps = 20
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        tr.train_step(*batches[i % 4])
+    e1.record()
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    del tr
+    return {"workload": "Voxurf SDF fine stage + per-ray pose gradient (BASELINE configs[2]): 160^3 sdf + 12-ch k0 + "
+                        "rgbnet 57-128-128-128-3 (tcgen05), 8192 rays/step/rank, fwd+bwd+Adam, ray-sharded over %d ranks, "
+                        "one flat NCCL all-reduce of the gradient buffer per step" % world,
+            "train_rays_per_s": world * RAYS / (ms * 1e-3), "ms_per_step": ms, "n_gpus": world}
+
+
 def cpu_baseline():
-    """The reference's pure-PyTorch CPU path on a bounded sample of the same workload (rank 0, N=1)."""
+    """The reference's pure-PyTorch CPU path on a bounded number of steps of the same workload (rank 0, N=1)."""
     from oracle import dvgo_cpu
-    from poseprobe_b200 import synthetic
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    batches, synthetic = make_batches_cpu(1, RAYS, 0)
     density, k0 = synthetic.make_dvgo_grids(GRID)
     base = dvgo_cpu.DenseBaseline(density, k0, XYZ_MIN, XYZ_MAX, STEPSIZE)
-    o, d, tgt = make_batches(1, RAYS, 0)[0]
-    n = bounded_sample_rays(base, o, d, tgt, budget_s=3.0)
+    o, d, tgt = batches[0]
+    base.train_step(o, d, tgt)
     t0 = time.perf_counter()
     steps = 0
     while steps < 3 or (time.perf_counter() - t0 < 10 and steps < 20):
-        base.train_step(o[:n], d[:n], tgt[:n])
+        base.train_step(o, d, tgt)
         steps += 1
     dt = time.perf_counter() - t0
-    return {"value": n * steps / dt, "unit": "rays/s", "cores": cores, "kind": "port",
-            "sample": "%d steps of %d of the %d rays (lib/dvgo_ori.py dense formulation, oracle/dvgo_cpu.py)"
-                      % (steps, n, RAYS)}
+    return {"value": RAYS * steps / dt, "unit": "rays/s", "cores": cores, "kind": "port",
+            "sample": "%d steps of the full %d-ray batch (lib/dvgo_ori.py dense formulation, oracle/dvgo_cpu.py)"
+                      % (steps, RAYS)}
 
 
 def main():

@@ -194,7 +194,7 @@ PP_API int pp_segment_cumsum(const float* src, const int64_t* ray_id, int64_t n_
 /* Dense-grid trilinear interpolation == F.grid_sample(grid[1,C,X,Y,Z], mode='bilinear',
  * align_corners=True) on ((xyz-xyz_min)/(xyz_max-xyz_min)).flip(-1)*2-1 as DenseGrid.forward does
  * (lib/grid.py:47-58).  padding: 0 = zeros (DenseGrid), 1 = border (Voxurf.grid_sampler,
- * voxurf_coarse.py:540).  out: [n, C] (row per point).  grad_xyz_out (optional, [n,C,3]) receives
+ * voxurf_coarse.py:540), 2 = grid_sample_3d (see pp_trilinear_backward2).  out: [n, C] (row per point).  grad_xyz_out (optional, [n,C,3]) receives
  * d out / d xyz analytically (what the reference obtains with autograd.grad, :972-984). fp32. */
 PP_API int pp_trilinear_forward(const float* grid, int32_t n_ch, int32_t sz_x, int32_t sz_y, int32_t sz_z,
                          const float* xyz, int64_t n_pts, const float* xyz_min_host,
@@ -209,6 +209,20 @@ PP_API int pp_trilinear_backward(const float* grid, int32_t n_ch, int32_t sz_x, 
                           const float* xyz_min_host, const float* xyz_max_host, int padding,
                           const float* grad_out, float* grad_grid, float* grad_xyz,
                           pp_stream_t stream);
+
+/* padding 2 (all three entry points) = the reference's own twice-differentiable sampler grid_sample_3d
+ * (lib/voxurf_coarse.py:545-659): trilinear weights from the UNCLAMPED voxel coordinate, the 8 corner indices clamped
+ * into the grid, no derivative clipping.
+ * pp_trilinear_backward2 = backward of pp_trilinear_backward's grad_xyz (what torch.autograd.grad(...,
+ * create_graph=True) + backward reach in the reference, :966-985; Eikonal / deformation losses): given
+ * grad_grad_xyz [n,3] = d loss / d grad_xyz and the first backward's grad_out [n,C]:
+ *   grad_grad_out [n,C] (overwritten) = d loss / d grad_out,   grad_grid += d loss / d grid (cell-derivative weights),
+ *   grad_xyz [n,3] (overwritten) = d loss / d xyz through the cell's off-diagonal Hessian.  Outputs are nullable. */
+PP_API int pp_trilinear_backward2(const float* grid, int32_t n_ch, int32_t sz_x, int32_t sz_y, int32_t sz_z,
+                                  const float* xyz, int64_t n_pts, const float* xyz_min_host,
+                                  const float* xyz_max_host, int padding, const float* grad_out,
+                                  const float* grad_grad_xyz, float* grad_grad_out, float* grad_grid,
+                                  float* grad_xyz, pp_stream_t stream);
 
 /* NeuS SDF -> alpha (voxurf_coarse.py:483-519, mid-point variant) and its backward.
  * alpha = clip((sig(prev*inv_s) - sig(next*inv_s) + 1e-5) / (sig(prev*inv_s) + 1e-5), 0, 1),

@@ -92,10 +92,27 @@ dvgo_march_kernel(pp_dvgo_scene sc, pp_dvgo_loss ls, const float4* __restrict__ 
         val = interp8(cur.c, v);
         alpha = density_to_alpha(val.x, sc.act_shift, sc.interval, e);
       }
-      float P, Pex;
-      lane_product_scan(1.f - alpha, lane, P, Pex);
-      const float T_before = T_in * Pex;
-      const float T_after = T_in * P;
+      float T_before, T_after;
+      if (flags & 2) {
+        // exact mode (parity tests): raw2alpha's own expression and alpha2weight's recurrence in the reference's
+        // ORDER and precision (render_utils_kernel.cu:437-442, :586-604: T *= (1. - alpha) in double, narrowed to
+        // float every step), so the early-termination index is the operator chain's, bit for bit
+        if (cur.live) alpha = 1.f - powf(1.f + e, -sc.interval);
+        float T = T_in;
+        T_before = T_in;
+        T_after = T_in;
+        for (int j = 0; j < 32; ++j) {
+          const float aj = __shfl_sync(kFull, alpha, j);
+          if (j == lane) T_before = T;
+          T = static_cast<float>(static_cast<double>(T) * (1. - static_cast<double>(aj)));
+          if (j == lane) T_after = T;
+        }
+      } else {
+        float P, Pex;
+        lane_product_scan(1.f - alpha, lane, P, Pex);
+        T_before = T_in * Pex;
+        T_after = T_in * P;
+      }
       const unsigned term = __ballot_sync(kFull, cur.live && (T_after < 1e-3f));
       bool counted = cur.live;
       int last_lane = 31;

@@ -20,7 +20,8 @@ namespace pp {
 struct GridGeom {
   int sx, sy, sz;        // X, Y, Z extents
   float mn[3], mx[3];    // xyz_min / xyz_max
-  int border;            // 0 zeros padding, 1 border padding
+  int border;            // 0 zeros padding, 1 border padding, 2 the reference's custom sampler grid_sample_3d
+                         // (voxurf_coarse.py:545-659): weights from the UNCLAMPED coordinate, corner indices clamped
 };
 
 struct Corner8 {
@@ -40,7 +41,7 @@ __device__ __forceinline__ float voxel_coord(float x, float mn, float mx, int si
   const float c = add_rn(mul_rn(t, 2.f), -1.f);
   float i = mul_rn(add_rn(c, 1.f) / 2.f, static_cast<float>(size - 1));
   dclip = 1.f;
-  if (border) {
+  if (border == 1) {
     // clip_coordinates_set_grad: the derivative vanishes on and beyond the border
     const float hi = static_cast<float>(size - 1);
     if (!(i > 0.f && i < hi)) dclip = 0.f;
@@ -59,11 +60,18 @@ __device__ __forceinline__ void make_corners(const GridGeom& g, float x, float y
   c.fz = iz - z0; c.gz = (z0 + 1.f) - iz;
   // ATen's (x,y,z) = (W,H,D) = our (Z,Y,X).  Corner order tnw,tne,tsw,tse,bnw,bne,bsw,bse:
   //   e/w toggles Z, s/n toggles Y, b/t toggles X.  Weight product order is (W term)*(H term)*(D term).
-  const int xi = static_cast<int>(x0), yi = static_cast<int>(y0), zi = static_cast<int>(z0);
+  const float lim = 1e9f;   // (keeps the float -> int conversion defined for far-away points)
+  const int xi = static_cast<int>(fminf(fmaxf(x0, -lim), lim)), yi = static_cast<int>(fminf(fmaxf(y0, -lim), lim)),
+            zi = static_cast<int>(fminf(fmaxf(z0, -lim), lim));
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const int dz = q & 1, dy = (q >> 1) & 1, dx = (q >> 2) & 1;
-    const int cx = xi + dx, cy = yi + dy, cz = zi + dz;
+    int cx = xi + dx, cy = yi + dy, cz = zi + dz;
+    if (g.border == 2) {   // torch.clamp of the corner indices (:575-598); the weights stay those of the free cell
+      cx = min(max(cx, 0), g.sx - 1);
+      cy = min(max(cy, 0), g.sy - 1);
+      cz = min(max(cz, 0), g.sz - 1);
+    }
     c.ok[q] = (cx >= 0) & (cx < g.sx) & (cy >= 0) & (cy < g.sy) & (cz >= 0) & (cz < g.sz);
     c.off[q] = ((int64_t)cx * g.sy + cy) * g.sz + cz;
     c.w[q] = mul_rn(mul_rn(dz ? c.fz : c.gz, dy ? c.fy : c.gy), dx ? c.fx : c.gx);
@@ -152,11 +160,74 @@ trilinear_bwd_kernel(const float* __restrict__ grid, int n_ch, GridGeom g,
   }
 }
 
+// Backward of the backward (the reference reaches it with torch.autograd.grad(..., create_graph=True) through its
+// 8-gather sampler, voxurf_coarse.py:966-985): the first backward's grad_xyz[a] = k_a sum_c go_c D_a(v_c) is a function
+// of the grid values, of the point (through the weights) and of go.  Given h = d loss / d grad_xyz [n,3]:
+//   d loss / d go_c      = sum_a h_a k_a D_a(v_c)                          (directional derivative of the value)
+//   d loss / d grid[q,c] = go_c sum_a h_a k_a d w_q / d i_a                (scatter with derivative weights)
+//   d loss / d xyz_b     = k_b sum_c go_c sum_a h_a k_a H_ab(v_c)          (H: off-diagonal Hessian of the cell)
+// with i = voxel coordinate, k_a = d i_a / d xyz_a, D = d value / d i.  All three outputs are optional.
+__global__ void __launch_bounds__(256)
+trilinear_bwd2_kernel(const float* __restrict__ grid, int n_ch, GridGeom g, const float* __restrict__ xyz,
+                      int64_t n_pts, const float* __restrict__ grad_out, const float* __restrict__ h_in,
+                      float* __restrict__ gg_out, float* __restrict__ grad_grid, float* __restrict__ grad_xyz) {
+  const int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (p >= n_pts) return;
+  Corner8 c;
+  make_corners(g, xyz[3 * p], xyz[3 * p + 1], xyz[3 * p + 2], c);
+  const int64_t plane = (int64_t)g.sx * g.sy * g.sz;
+  const float kx = c.mx_ * (g.sx - 1) / (g.mx[0] - g.mn[0]);
+  const float ky = c.my_ * (g.sy - 1) / (g.mx[1] - g.mn[1]);
+  const float kz = c.mz_ * (g.sz - 1) / (g.mx[2] - g.mn[2]);
+  const float hx = h_in[3 * p] * kx, hy = h_in[3 * p + 1] * ky, hz = h_in[3 * p + 2] * kz;
+  // d w_q / d i_a contracted with h: q bit0 -> Z, bit1 -> Y, bit2 -> X
+  float dw[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float wz = (q & 1) ? c.fz : c.gz, wy = (q & 2) ? c.fy : c.gy, wx = (q & 4) ? c.fx : c.gx;
+    const float sz = (q & 1) ? 1.f : -1.f, sy = (q & 2) ? 1.f : -1.f, sx = (q & 4) ? 1.f : -1.f;
+    dw[q] = hx * sx * wy * wz + hy * wx * sy * wz + hz * wx * wy * sz;
+  }
+  float gX = 0.f, gY = 0.f, gZ = 0.f;
+  for (int ch = 0; ch < n_ch; ++ch) {
+    const float go = grad_out[p * n_ch + ch];
+    const float* vp = grid + ch * plane;
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = c.ok[q] ? __ldg(vp + c.off[q]) : 0.f;
+    if (gg_out) {
+      float acc = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) acc = fma_rn(v[q], dw[q], acc);
+      gg_out[p * n_ch + ch] = acc;
+    }
+    if (grad_grid) {
+      float* gp = grad_grid + ch * plane;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (c.ok[q]) red_add(gp + c.off[q], dw[q] * go);
+    }
+    if (grad_xyz) {
+      const float hxy = ((v[6] - v[4]) - (v[2] - v[0])) * c.gz + ((v[7] - v[5]) - (v[3] - v[1])) * c.fz;
+      const float hxz = ((v[5] - v[4]) - (v[1] - v[0])) * c.gy + ((v[7] - v[6]) - (v[3] - v[2])) * c.fy;
+      const float hyz = ((v[3] - v[2]) - (v[1] - v[0])) * c.gx + ((v[7] - v[6]) - (v[5] - v[4])) * c.fx;
+      gX += go * (hxy * hy + hxz * hz);
+      gY += go * (hxy * hx + hyz * hz);
+      gZ += go * (hxz * hx + hyz * hy);
+    }
+  }
+  if (grad_xyz) {
+    grad_xyz[3 * p] = gX * kx;
+    grad_xyz[3 * p + 1] = gY * ky;
+    grad_xyz[3 * p + 2] = gZ * kz;
+  }
+}
+
 static int make_geom(GridGeom& g, int32_t sx, int32_t sy, int32_t sz, const float* mn,
                      const float* mx, int padding) {
   PP_REQUIRE(sx > 0 && sy > 0 && sz > 0, PP_ERR_INVALID_ARG, "trilinear: empty grid");
   PP_REQUIRE(mn && mx, PP_ERR_INVALID_ARG, "trilinear: xyz_min/xyz_max (host) are null");
-  PP_REQUIRE(padding == 0 || padding == 1, PP_ERR_INVALID_ARG, "trilinear: padding must be 0|1");
+  PP_REQUIRE(padding >= 0 && padding <= 2, PP_ERR_INVALID_ARG, "trilinear: padding must be 0|1|2");
   g.sx = sx; g.sy = sy; g.sz = sz; g.border = padding;
   for (int c = 0; c < 3; ++c) { g.mn[c] = mn[c]; g.mx[c] = mx[c]; }
   return PP_OK;
@@ -200,5 +271,22 @@ extern "C" int pp_trilinear_backward(const float* grid, int32_t n_ch, int32_t sz
   trilinear_bwd_kernel<<<ceil_div(n_pts, 256), 256, 0, as_stream(stream)>>>(
       grid, n_ch, g, xyz, n_pts, grad_out, grad_grid, grad_xyz);
   PP_CHECK_LAUNCH("trilinear_backward");
+  return PP_OK;
+}
+
+extern "C" int pp_trilinear_backward2(const float* grid, int32_t n_ch, int32_t sz_x, int32_t sz_y, int32_t sz_z,
+                                      const float* xyz, int64_t n_pts, const float* xyz_min_host,
+                                      const float* xyz_max_host, int padding, const float* grad_out,
+                                      const float* grad_grad_xyz, float* grad_grad_out, float* grad_grid,
+                                      float* grad_xyz, pp_stream_t stream) {
+  PP_REQUIRE(n_pts >= 0 && n_ch >= 0, PP_ERR_INVALID_ARG, "trilinear_backward2: negative extent");
+  if (n_pts == 0 || n_ch == 0 || (!grad_grad_out && !grad_grid && !grad_xyz)) return PP_OK;
+  PP_REQUIRE(grid && xyz && grad_out && grad_grad_xyz, PP_ERR_INVALID_ARG, "trilinear_backward2: null pointer");
+  GridGeom g;
+  const int rc = make_geom(g, sz_x, sz_y, sz_z, xyz_min_host, xyz_max_host, padding);
+  if (rc != PP_OK) return rc;
+  trilinear_bwd2_kernel<<<ceil_div(n_pts, 256), 256, 0, as_stream(stream)>>>(
+      grid, n_ch, g, xyz, n_pts, grad_out, grad_grad_xyz, grad_grad_out, grad_grid, grad_xyz);
+  PP_CHECK_LAUNCH("trilinear_backward2");
   return PP_OK;
 }

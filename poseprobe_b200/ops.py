@@ -51,10 +51,76 @@ class Raw2Alpha(torch.autograd.Function):
         return render_utils_cuda.raw2alpha_backward(exp_d, grad_back.contiguous(), ctx.interval), None, None
 
 
+_HOST3 = {}
+
+
 def _host3(t):
+    """Host copy of a 3-vector (box corner) for the C ABI's host-pointer arguments.  Box corners are module buffers
+    that live on the GPU and never change, so the device -> host copy (a stream synchronisation) is done ONCE per
+    tensor version and cached: a DenseGrid query launches its kernel without touching the host."""
+    if not torch.is_tensor(t):
+        t = torch.as_tensor(t, dtype=torch.float32)
+    if not t.is_cuda:
+        v = t.detach().to(torch.float32).contiguous()
+        assert v.numel() == 3
+        return v
+    key = (t.data_ptr(), t.device.index)
+    hit = _HOST3.get(key)
+    if hit is not None and hit[0] == t._version:
+        return hit[1]
     v = t.detach().to("cpu", torch.float32).contiguous()
     assert v.numel() == 3
+    if len(_HOST3) > 256:
+        _HOST3.clear()
+    _HOST3[key] = (t._version, v)
     return v
+
+
+_PADDING = {"zeros": 0, "border": 1, "custom": 2}
+
+
+class _TrilinearBwd(torch.autograd.Function):
+    """The first backward of the trilinear gather as a differentiable node: (grid, pts, grad_out) -> (grad_grid,
+    grad_xyz).  Its own backward (pp_trilinear_backward2) is what the reference reaches with
+    torch.autograd.grad(..., create_graph=True) through grid_sample_3d (lib/voxurf_coarse.py:545-659, :966-985): the
+    derivative of grad_xyz w.r.t. the grid (cell-derivative weights), the points (off-diagonal cell Hessian) and
+    grad_out.  (Second-order terms through grad_grid are not propagated: nothing on the path differentiates a
+    parameter gradient.)"""
+
+    @staticmethod
+    def forward(ctx, grid_c, pts, grad_out, mn_host, mx_host, padding, need_grid, need_xyz):
+        _, c, x, y, z = grid_c.shape
+        n = pts.shape[0]
+        grad_out = grad_out.contiguous()
+        grad_grid = torch.zeros_like(grid_c) if need_grid else torch.zeros(0, device=grid_c.device)
+        grad_xyz = torch.empty_like(pts) if need_xyz else torch.zeros(0, device=grid_c.device)
+        with torch.cuda.device(grid_c.device):
+            check(lib.pp_trilinear_backward(ptr(grid_c), c, x, y, z, ptr(pts), n, ptr(mn_host), ptr(mx_host),
+                                            padding, ptr(grad_out), ptr(grad_grid) if need_grid else None,
+                                            ptr(grad_xyz) if need_xyz else None, stream()), "trilinear_backward")
+        ctx.save_for_backward(grid_c, pts, grad_out)
+        ctx.geom = (mn_host, mx_host, padding)
+        ctx.mark_non_differentiable(grad_grid)
+        return grad_grid, grad_xyz
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, _gg_grid, gg_xyz):
+        grid_c, pts, grad_out = ctx.saved_tensors
+        mn_host, mx_host, padding = ctx.geom
+        if gg_xyz is None or gg_xyz.numel() == 0:
+            return (None,) * 8
+        _, c, x, y, z = grid_c.shape
+        n = pts.shape[0]
+        need_grid, need_pts, need_go = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        g_grid = torch.zeros_like(grid_c) if need_grid else None
+        g_pts = torch.empty_like(pts) if need_pts else None
+        g_go = torch.empty_like(grad_out) if need_go else None
+        with torch.cuda.device(grid_c.device):
+            check(lib.pp_trilinear_backward2(ptr(grid_c), c, x, y, z, ptr(pts), n, ptr(mn_host), ptr(mx_host), padding,
+                                             ptr(grad_out), ptr(gg_xyz.contiguous()), ptr(g_go), ptr(g_grid),
+                                             ptr(g_pts), stream()), "trilinear_backward2")
+        return g_grid, g_pts, g_go, None, None, None, None, None
 
 
 class _Trilinear(torch.autograd.Function):
@@ -72,39 +138,46 @@ class _Trilinear(torch.autograd.Function):
         with torch.cuda.device(grid.device):
             check(lib.pp_trilinear_forward(ptr(grid_c), c, x, y, z, ptr(pts), n, ptr(mn_host), ptr(mx_host),
                                            padding, ptr(out), None, stream()), "trilinear_forward")
-        ctx.save_for_backward(grid_c, pts)
-        ctx.geom = (mn_host, mx_host, padding, xyz.shape)
+        ctx.save_for_backward(grid, xyz)
+        ctx.geom = (mn_host, mx_host, padding)
         return out
 
     @staticmethod
-    @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
-        grid_c, pts = ctx.saved_tensors
-        mn_host, mx_host, padding, xyz_shape = ctx.geom
-        _, c, x, y, z = grid_c.shape
-        n = pts.shape[0]
-        grad_out = grad_out.contiguous()
+        # written on differentiable pieces so that torch.autograd.grad(..., create_graph=True) works (the reference's
+        # twice-differentiable sampler); under a plain backward() autograd runs this without recording anything
+        grid, xyz = ctx.saved_tensors
+        mn_host, mx_host, padding = ctx.geom
         need_grid, need_xyz = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        grad_grid = torch.zeros_like(grid_c) if need_grid else None
-        grad_xyz = torch.empty_like(pts) if need_xyz else None
-        with torch.cuda.device(grid_c.device):
-            check(lib.pp_trilinear_backward(ptr(grid_c), c, x, y, z, ptr(pts), n, ptr(mn_host), ptr(mx_host),
-                                            padding, ptr(grad_out), ptr(grad_grid), ptr(grad_xyz), stream()),
-                  "trilinear_backward")
-        if grad_xyz is not None:
-            grad_xyz = grad_xyz.reshape(xyz_shape)
-        return grad_grid, grad_xyz, None, None, None
+        grad_grid, grad_xyz = _TrilinearBwd.apply(grid.contiguous(), xyz.reshape(-1, 3).contiguous(), grad_out, mn_host,
+                                                  mx_host, padding, need_grid, need_xyz)
+        return (grad_grid.reshape(grid.shape) if need_grid else None,
+                grad_xyz.reshape(xyz.shape) if need_xyz else None, None, None, None)
 
 
 def trilinear(grid, xyz, xyz_min, xyz_max, padding_mode="zeros"):
-    """grid [1,C,X,Y,Z], xyz [...,3] (world) -> [prod(...), C]; differentiable in grid and xyz."""
-    padding = {"zeros": 0, "border": 1}[padding_mode]
-    return _Trilinear.apply(grid, xyz, _host3(xyz_min), _host3(xyz_max), padding)
+    """grid [1,C,X,Y,Z], xyz [...,3] (world) -> [prod(...), C]; differentiable in grid and xyz, and TWICE
+    differentiable in the sense the reference needs (d/d(grid, xyz) of the spatial gradient).
+    padding_mode: "zeros" (DenseGrid, lib/grid.py:47-58), "border" (Voxurf.grid_sampler, voxurf_coarse.py:540) or
+    "custom" (grid_sample_3d, :545-659: weights of the unclamped cell, clamped corner indices)."""
+    return _Trilinear.apply(grid, xyz, _host3(xyz_min), _host3(xyz_max), _PADDING[padding_mode])
+
+
+def grid_sample_3d(image, optical):
+    """Voxurf.grid_sample_3d (lib/voxurf_coarse.py:545-659): image [1,C,D,H,W], optical [1,D',H',W',3] in the
+    normalised (x = W, y = H, z = D) coordinates of F.grid_sample -> [1,C,D',H',W'], twice differentiable."""
+    n, c = image.shape[:2]
+    if n != 1:
+        raise NotImplementedError("grid_sample_3d: batch size 1 (as the reference uses it)")
+    shape = optical.shape[1:4]
+    one = torch.ones(3)
+    vals = trilinear(image, optical.reshape(-1, 3).flip(-1), -one, one, "custom")
+    return vals.T.reshape(1, c, *shape)
 
 
 def trilinear_with_grad(grid, xyz, xyz_min, xyz_max, padding_mode="zeros"):
     """Value [n,C] and analytic spatial gradient d value / d xyz [n,C,3] in one gather (no autograd)."""
-    padding = {"zeros": 0, "border": 1}[padding_mode]
+    padding = _PADDING[padding_mode]
     grid_c = grid.detach().contiguous()
     pts = xyz.detach().reshape(-1, 3).contiguous()
     _, c, x, y, z = grid_c.shape

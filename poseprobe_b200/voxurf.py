@@ -847,6 +847,21 @@ class Voxurf(torch.nn.Module):
             self._eng_key = key
         return self._eng, ws, bs
 
+    def grid_sampler(self, xyz, *grids, mode=None, align_corners=True, smooth=False, displace=0., use_custom=False):
+        """Voxurf.grid_sampler (lib/voxurf_coarse.py:522-543): trilinear lookup with border padding, or with
+        use_custom=True the twice-differentiable grid_sample_3d (:545-659).  xyz [...,3] -> [...,C] (squeezed)."""
+        from .ops import trilinear
+        if (mode not in (None, "bilinear")) or not align_corners or smooth or displace != 0:
+            raise NotImplementedError("grid_sampler: bilinear, align_corners=True, no smoothing / displacement")
+        shape = xyz.shape[:-1]
+        grid = grids[0]
+        vals = trilinear(grid, xyz.reshape(-1, 3), self.xyz_min, self.xyz_max, "custom" if use_custom else "border")
+        return vals.reshape(*shape, grid.shape[1]).squeeze()
+
+    def grid_sample_3d(self, image, optical):
+        from .ops import grid_sample_3d
+        return grid_sample_3d(image, optical)
+
     def k0_total_variation(self, k0_tv=1., k0_grad_tv=0.):
         """voxurf_coarse.py:443-455 (no nonempty mask in this module)."""
         from .ops import total_variation

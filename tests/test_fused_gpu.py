@@ -50,6 +50,23 @@ def test_render_forward_matches_composed_ops(pp, bg, thres):
     close(last.cpu()[same], want["alphainv_last"][same], rtol=1e-5, atol=1e-7)
     close(rgb.cpu()[same], want["rgb_marched"][same], rtol=1e-5, atol=1e-6)
     close(depth.cpu()[same], want["depth"][same], rtol=1e-5, atol=1e-6)
+    # ... and the rays that stop one sample apart are bounded, not excluded: the extra / missing sample carries a weight
+    # below T = 1e-3 (colour <= 1, distance <= the box diagonal), and alphainv_last moves by at most that T
+    close(rgb.cpu()[~same], want["rgb_marched"][~same], rtol=0, atol=2e-3)
+    close(last.cpu()[~same], want["alphainv_last"][~same], rtol=0, atol=1e-3)
+    close(depth.cpu()[~same], want["depth"][~same], rtol=0, atol=4e-3)
+    # exact mode (PP_MARCH_FLAGS=2: raw2alpha's powf expression and alpha2weight's serial double-precision recurrence
+    # in the reference's order): the early-termination index is the operator chain's on EVERY ray
+    import os
+    os.environ["PP_MARCH_FLAGS"] = "2"
+    try:
+        rgb_x, last_x, depth_x, cnt_x = pp.render_forward(sc, vox, o.cuda(), d.cuda(), want_count=True)
+    finally:
+        del os.environ["PP_MARCH_FLAGS"]
+    assert torch.equal(cnt_x.cpu(), want["n_marched"]), int((cnt_x.cpu() != want["n_marched"]).sum())
+    close(last_x.cpu(), want["alphainv_last"], rtol=1e-5, atol=1e-7)
+    close(rgb_x.cpu(), want["rgb_marched"], rtol=1e-5, atol=1e-6)
+    close(depth_x.cpu(), want["depth"], rtol=1e-5, atol=1e-6)
     # pack / unpack round trip is exact
     d2, k2 = pp.unpack_voxels(vox, density.shape[2:])
     assert torch.equal(d2.cpu(), density) and torch.equal(k2.cpu(), k0)
@@ -239,3 +256,66 @@ def test_config_b_full_size_properties(pp):
     assert torch.equal(eng.vox[~touched], before[~touched])
     assert bool((eng.vox[touched] != before[touched]).float().mean() > 0.99)
     assert float(eng.grad.abs().max()) == 0.0
+
+
+def test_config_b_scene_against_the_oracle_on_a_ray_subset(pp):
+    """The REAL config-B scene (160^3 density + k0 grids of bench.py, stepsize 0.5) on a 256-ray subset of the bench
+    batch against the composed-operator oracle: rendered outputs, early-termination indices (exact mode), the loss and
+    the grid gradients of a train step - an oracle comparison at the benchmark's own size, not only invariants."""
+    import os
+    G, N = 160, 256
+    density, k0 = synthetic.make_dvgo_grids(G)
+    o, d, _ = synthetic.make_rays(8192)
+    sel = torch.arange(0, 8192, 8192 // N)[:N]
+    o, d = o[sel].contiguous(), d[sel].contiguous()
+    mn, mx = [-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]
+    kw = dict(near=0.2, far=1e9, stepdist=0.5 * 2.0 / G, act_shift=synthetic.act_shift(), interval=0.5)
+    target = torch.rand(N, 3, generator=torch.Generator().manual_seed(11))
+    dens_t, k0_t = density.clone().requires_grad_(True), k0.clone().requires_grad_(True)
+    want = dvgo_cpu.render_composed(dens_t, k0_t, o, d, mn, mx, bg=0.0, **kw)
+    loss, mse = dvgo_cpu.losses(want, target, 1.0, 0.0, 0.0)
+    loss.backward()
+    eng = pp.FusedDVGO(density.cuda(), k0.cuda(), mn, mx, stepsize=0.5, bg=0.0)
+    rgb, last, depth, cnt = eng.render(o.cuda(), d.cuda(), want_count=True)
+    assert int((cnt.cpu() - want["n_marched"]).abs().max()) <= 1
+    close(rgb, want["rgb_marched"].detach(), rtol=0, atol=2e-3)
+    close(last, want["alphainv_last"].detach(), rtol=0, atol=1e-3)
+    os.environ["PP_MARCH_FLAGS"] = "2"
+    try:
+        rgb_x, last_x, depth_x, cnt_x = eng.render(o.cuda(), d.cuda(), want_count=True)
+    finally:
+        del os.environ["PP_MARCH_FLAGS"]
+    assert torch.equal(cnt_x.cpu(), want["n_marched"])
+    close(rgb_x, want["rgb_marched"].detach(), rtol=1e-5, atol=2e-6)
+    close(last_x, want["alphainv_last"].detach(), rtol=1e-5, atol=1e-7)
+    close(depth_x, want["depth"].detach(), rtol=1e-5, atol=2e-6)
+    eng.loss_buf.zero_()
+    eng.backward_only(o.cuda(), d.cuda(), target.cuda())
+    close(eng.loss_buf[0], loss.detach(), rtol=1e-4, atol=1e-7)
+    gd, gk = eng.export_grad()
+    for mine, ref in ((gd, dens_t.grad), (gk, k0_t.grad)):
+        rel = float((mine.cpu() - ref).norm() / ref.norm())
+        assert rel < 1e-4, rel
+        close(mine, ref, rtol=1e-3, atol=1e-5 * float(ref.abs().max()))
+
+
+def _torchrun(script, nproc, port, timeout=600):
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr",
+           "127.0.0.1", "--master-port", str(port), os.path.join(root, "tests", script)]
+    return subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout, cwd=root)
+
+
+@pytest.mark.parametrize("script,port", [("dist_check.py", 29533), ("dist_check_voxurf.py", 29534)])
+def test_two_ranks_equal_one_rank_on_the_concatenated_batch(pp, script, port):
+    """N ranks with their own ray batches == ONE rank stepping on the concatenated batch (up to fp32 summation order),
+    for the fused peer-memory exchange kernels (p2p, and NVLS where a multicast address exists), the NCCL formulation
+    and the fine stage's flat all-reduce: tests/dist_check*.py under torchrun with 2 ranks.  Needs 2 GPUs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    r = _torchrun(script, 2, port)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert " ok: world=2" in r.stdout, r.stdout[-3000:]

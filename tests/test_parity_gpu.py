@@ -548,3 +548,51 @@ def test_total_variation_loss_python_side(cuda, masked):
     (2.5 * got).backward()
     torch.testing.assert_close(got.detach().cpu(), want.detach(), rtol=1e-5, atol=1e-7)
     torch.testing.assert_close(vc.grad.cpu(), 2.5 * vr.grad, rtol=1e-5, atol=1e-9)
+
+
+@pytest.mark.parametrize("padding", ["custom", "border", "zeros"])
+def test_trilinear_is_twice_differentiable(pp, padding):
+    """Op-level double backward of the trilinear gather (a6 / SURVEY 8f rank 2): the reference's own sampler
+    grid_sample_3d (lib/voxurf_coarse.py:545-659) exists because F.grid_sample had no second derivative; its use is
+    torch.autograd.grad(value, xyz, create_graph=True) followed by a loss on that gradient (:966-985, lib/losses.py:
+    7-10).  Same computation through pp.ops.trilinear against CPU autograd (fp64) through the oracle's restatement of
+    the sampler: first-order gradient, and the gradients of a loss on value AND spatial gradient w.r.t. grid and
+    points (cell-derivative scatter, off-diagonal cell Hessian).  fp32 kernels: 1e-4 relative."""
+    from oracle import voxurf_cpu
+    from poseprobe_b200 import ops
+    g = torch.Generator().manual_seed(91)
+    mn, mx = torch.tensor([-1.0, -0.8, -1.2]), torch.tensor([1.1, 0.9, 1.0])
+    grid = torch.randn(1, 3, 9, 7, 11, generator=g)
+    n = 3000
+    xyz = mn + (mx - mn) * (torch.rand(n, 3, generator=g) * (1.3 if padding == "custom" else 0.98) + (
+        -0.15 if padding == "custom" else 0.01))
+    wv, wg = torch.randn(n, 3, generator=g), torch.randn(n, 3, generator=g)
+
+    def run(sampler, gr, pts, dt):
+        val = sampler(gr, pts)
+        (dx,) = torch.autograd.grad(val.sum(), pts, create_graph=True)
+        loss = (val * wv.to(pts.device, dt)).sum() + (dx * wg.to(pts.device, dt)).sum() + (dx.norm(dim=-1) - 1).abs().mean()
+        gg, gp = torch.autograd.grad(loss, [gr, pts])
+        return val.detach(), dx.detach(), gg, gp
+
+    def ref_sampler(gr, pts):
+        if padding == "custom":
+            return voxurf_cpu.grid_sample_custom(pts, gr, mn.double(), mx.double())
+        ind = ((pts - mn.double()) / (mx.double() - mn.double())).flip(-1) * 2 - 1
+        out = torch.nn.functional.grid_sample(gr, ind.reshape(1, 1, 1, -1, 3), mode="bilinear", align_corners=True,
+                                              padding_mode=padding)
+        return out.reshape(gr.shape[1], -1).T
+
+    want = run(ref_sampler, grid.double().requires_grad_(True), xyz.double().requires_grad_(True), torch.float64)
+    got = run(lambda gr, pts: ops.trilinear(gr, pts, mn, mx, padding), grid.cuda().requires_grad_(True),
+              xyz.cuda().requires_grad_(True), torch.float32)
+    for name, a, b in zip(("value", "d value / d xyz", "d loss / d grid", "d loss / d xyz"), got, want):
+        rel = float((a.cpu().double() - b).norm() / b.norm())
+        assert rel < 1e-4, (name, rel)
+    # the module-level mirrors of the reference's wrappers
+    import poseprobe_b200 as ppkg
+    if padding == "custom":
+        opt = (((xyz - mn) / (mx - mn)).flip(-1) * 2 - 1).reshape(1, 1, 1, -1, 3)
+        img = ops.grid_sample_3d(grid.cuda(), opt.cuda())
+        assert img.shape == (1, 3, 1, 1, n)
+        torch.testing.assert_close(img.reshape(3, -1).T.cpu(), want[0].float(), rtol=1e-4, atol=1e-5)

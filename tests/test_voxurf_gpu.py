@@ -8,7 +8,7 @@ Tolerances, stated once:
   rounding of 1e-3 may stop one sample apart, see test_fused_gpu.py);
 * feature rows are stored as bf16: 2^-8 relative;
 * anything downstream of the rgbnet (rgb_marched, loss, every gradient) carries the MLP's bf16 operands:
-  rgb 2e-2 absolute, gradients by direction (cosine > 0.99) and norm (10 %).
+  rgb 2e-2 absolute, gradients by direction (cosine > 0.999) and norm (1 %).
 """
 import math
 
@@ -152,8 +152,8 @@ def test_gradients_vs_oracle(cuda):
         report["b%d" % i] = (_cos(g_b[i].cpu(), m.bias.grad), float(g_b[i].norm() / (m.bias.grad.norm() + 1e-30)))
     print(report)
     for k, (c, ratio) in report.items():
-        assert c > 0.99, "%s: cosine %.4f (%s)" % (k, c, report)
-        assert 0.9 < ratio < 1.1, "%s: norm ratio %.3f (%s)" % (k, ratio, report)
+        assert c > 0.999, "%s: cosine %.4f (%s)" % (k, c, report)
+        assert 0.99 < ratio < 1.01, "%s: norm ratio %.3f (%s)" % (k, ratio, report)
 
 
 def test_backward_kernel_exact_inputs(cuda):
@@ -241,7 +241,7 @@ def test_train_step_reduces_loss_and_roundtrips_state(cuda):
 def test_pose_gradient_vs_oracle(cuda):
     """d loss / d (rays_o, rays_d, viewdirs) of the fine stage (the input of the per-image SE3 reduction, SURVEY
     a21) against autograd through differentiable sample positions (sample_ray_ori's formulas).  The gradient passes
-    through the bf16 MLP input gradient: direction (cosine > 0.99) and norm (10 %) per tensor; per-ray agreement on
+    through the bf16 MLP input gradient: direction (cosine > 0.999) and norm (1 %) per tensor; per-ray agreement on
     the rays that carry 90 % of the gradient norm."""
     from oracle import voxurf_cpu
     G, N = 40, 768
@@ -261,7 +261,7 @@ def test_pose_gradient_vs_oracle(cuda):
            "viewdirs": (_cos(g_view.cpu(), vd.grad), float(g_view.norm() / vd.grad.norm()))}
     print(rep)
     for k, (c, ratio) in rep.items():
-        assert c > 0.99 and 0.9 < ratio < 1.1, (k, rep)
+        assert c > 0.999 and 0.99 < ratio < 1.01, (k, rep)
     # folded form: viewdirs = rays_d / |rays_d|
     folded = eng.ray_gradients(d.to(cuda))
     od2, dd2 = o.clone().requires_grad_(True), d.clone().requires_grad_(True)
@@ -271,7 +271,7 @@ def test_pose_gradient_vs_oracle(cuda):
                               progress=1.0, differentiable_points=True)
     voxurf_cpu.mse_loss(out2, target).backward()
     want = torch.cat([od2.grad, dd2.grad], -1)
-    assert _cos(folded.cpu(), want) > 0.99
+    assert _cos(folded.cpu(), want) > 0.999
 
 
 def test_fine_stage_se3_gradient_vs_oracle(cuda):
@@ -320,7 +320,7 @@ def test_fine_stage_se3_gradient_vs_oracle(cuda):
     c = _cos(se3.grad.cpu(), se3_r.grad)
     ratio = float(se3.grad.norm() / se3_r.grad.norm())
     print("se3 gradient: cosine %.5f, norm ratio %.4f" % (c, ratio), se3.grad.cpu(), se3_r.grad)
-    assert c > 0.99 and 0.9 < ratio < 1.1
+    assert c > 0.999 and 0.99 < ratio < 1.01
 
 
 def test_edge_cases_missing_rays_and_capacity(cuda):
@@ -412,8 +412,7 @@ def test_voxurf_module_autograd_vs_oracle(cuda):
         return torch.nn.functional.mse_loss(out["rgb_marched"], tgt) \
             + 0.01 * (-(last * last.log() + (1 - last) * (1 - last).log())).mean() + 0.05 * out["cum_weights"].mean()
 
-    with pytest.raises(NotImplementedError, match="use_deform=False"):      # the reference's default branch needs the
-        mod(o.to(cuda), d.to(cuda), v.to(cuda), global_step=None, **rk)     # deformation backward: loud, not silent
+    # (the default branch, use_deform=True, trains through the deformation network: tests/test_deform_gpu.py)
     out = mod(o.to(cuda), d.to(cuda), v.to(cuda), use_deform=False, global_step=None, **rk)
     loss = loss_of(out, target.to(cuda))
     loss.backward()
@@ -436,7 +435,7 @@ def test_voxurf_module_autograd_vs_oracle(cuda):
         rep["W%d" % i] = (_cos(a.weight.grad.cpu(), b.weight.grad), float(a.weight.grad.norm() / b.weight.grad.norm()))
     print(rep, float(mod.sdf_alpha.grad), float(al.grad), float(mod.sdf_beta.grad), float(be.grad))
     for k, (c, ratio) in rep.items():
-        assert c > 0.99 and 0.9 < ratio < 1.1, (k, rep)
+        assert c > 0.999 and 0.99 < ratio < 1.01, (k, rep)
     assert abs(float(mod.sdf_alpha.grad) - float(al.grad)) < 0.05 * abs(float(al.grad)) + 1e-7
     assert abs(float(mod.sdf_beta.grad) - float(be.grad)) < 0.05 * abs(float(be.grad)) + 1e-7
 
@@ -478,4 +477,4 @@ def test_non_cubic_grid_and_box(cuda):
     rep = {"sdf": _cos(g_sdf.cpu(), sdf_r.grad), "k0": _cos(g_k0.cpu(), k0_r.grad),
            "W0": _cos(g_w[0].cpu(), lin[0].weight.grad), "W2": _cos(g_w[2].cpu(), lin[2].weight.grad)}
     print(rep)
-    assert min(rep.values()) > 0.99, rep
+    assert min(rep.values()) > 0.999, rep
