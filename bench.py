@@ -443,7 +443,7 @@ def fine_stage_bench(dev):
     ws, bs = ops.rgbnet_from_sequential(net)
     eng = voxurf.FusedVoxurf(sdf.to(dev), k0.to(dev), [w.detach() for w in ws], [b.detach() for b in bs], XYZ_MIN,
                              XYZ_MAX, stepsize=STEPSIZE, s_val=0.05, bg=0.0, sdf_alpha=10.0, sdf_beta=0.35,
-                             posbase_pe=5, viewbase_pe=1, lr_sdf=1e-4, lr_k0=1e-2, lr_rgbnet=1e-3)
+                             posbase_pe=5, viewbase_pe=1, lr_sdf=1e-4, lr_k0=1e-2, lr_rgbnet=1e-3, lr_warp=1e-6)
     from poseprobe_b200 import synthetic as syn
     batches = []
     for b in range(4):

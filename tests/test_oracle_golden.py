@@ -301,3 +301,36 @@ def test_voxurf_deform_oracle_matches_the_references_own_forward_and_gradients()
     g_k0[torch.from_numpy(g["g_k0_idx"]).long()] = t("g_k0_val")
     assert rel(grads[16].reshape(-1), g_k0) < 2e-3
     assert rel(grads[17], t("g_rays_o")) < 5e-3 and rel(grads[18], t("g_rays_d")) < 5e-3
+
+
+def test_scene_branch_compositing_oracle_matches_the_references_own_code():
+    """oracle/bgnerf_cpu.py against tests/golden/bgnerf_composite.npz = the reference's OWN `NeRF.composite`
+    (frequency_nerf.py:283-343) and `Graph.sample_depth_from_pdf` (renderer.py:703-738) executed on the CPU
+    (tests/golden/make_golden_bgnerf.py): every output, the gradients of a loss on rgb / depth / opacity / weights
+    w.r.t. rgb_samples, density_samples and the ray, and the resampled depths (deterministic and shared-random grid)."""
+    import os
+    import numpy as np
+    import torch
+    from oracle import bgnerf_cpu
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "bgnerf_composite.npz"))
+    for tag in ("a", "b"):
+        t = lambda k: torch.from_numpy(g["%s_%s" % (tag, k)])  # noqa: E731
+        ray = t("ray").clone().requires_grad_(True)
+        rgb_s = t("rgb_samples").clone().requires_grad_(True)
+        dens = t("density_samples").clone().requires_grad_(True)
+        out = bgnerf_cpu.composite(ray, rgb_s, dens, t("depth_samples"), setbg_opaque=bool(g[tag + "_opaque"]))
+        for k in ("rgb", "rgb_var", "depth", "depth_var", "opacity", "weights", "all_cumulated"):
+            torch.testing.assert_close(out[k].detach(), t("out_" + k), rtol=1e-5, atol=1e-6, msg=lambda m, k=k: k + m)
+        loss = (out["rgb"] * t("w_rgb")).sum() + (out["depth"] * t("w_depth")).sum() + \
+            (out["opacity"] * t("w_opacity")).sum() + (out["weights"] * t("w_weights")).sum()
+        grads = torch.autograd.grad(loss, [rgb_s, dens, ray])
+        for got, k in zip(grads, ("g_rgb_samples", "g_density_samples", "g_ray")):
+            torch.testing.assert_close(got, t(k), rtol=1e-4, atol=1e-6)
+        w = t("out_weights")[..., 0]
+        N = w.shape[-1]
+        rng = [float(v) for v in g[tag + "_depth_range"]]
+        Nf = g[tag + "_fine_det"].shape[2]
+        det, _ = bgnerf_cpu.sample_depth_from_pdf(w, N, Nf, rng, torch.linspace(0, 1, Nf + 1))
+        assert torch.equal(det, t("fine_det"))
+        rnd, _ = bgnerf_cpu.sample_depth_from_pdf(w, N, Nf, rng, t("fine_grid"))
+        assert torch.equal(rnd, t("fine_rand"))

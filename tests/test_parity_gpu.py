@@ -566,6 +566,13 @@ def test_trilinear_is_twice_differentiable(pp, padding):
     n = 3000
     xyz = mn + (mx - mn) * (torch.rand(n, 3, generator=g) * (1.3 if padding == "custom" else 0.98) + (
         -0.15 if padding == "custom" else 0.01))
+    # the spatial gradient of a trilinear interpolant jumps at cell faces: drop the few points that fp32 and fp64 could
+    # place on different sides of one
+    vox = (xyz.double() - mn.double()) / (mx.double() - mn.double()) * (torch.tensor([9.0, 7.0, 11.0]).double() - 1)
+    frac = vox - vox.floor()
+    keep = ((frac > 1e-3) & (frac < 1 - 1e-3)).all(-1)
+    xyz = xyz[keep]
+    n = xyz.shape[0]
     wv, wg = torch.randn(n, 3, generator=g), torch.randn(n, 3, generator=g)
 
     def run(sampler, gr, pts, dt):
@@ -576,12 +583,9 @@ def test_trilinear_is_twice_differentiable(pp, padding):
         return val.detach(), dx.detach(), gg, gp
 
     def ref_sampler(gr, pts):
-        if padding == "custom":
-            return voxurf_cpu.grid_sample_custom(pts, gr, mn.double(), mx.double())
-        ind = ((pts - mn.double()) / (mx.double() - mn.double())).flip(-1) * 2 - 1
-        out = torch.nn.functional.grid_sample(gr, ind.reshape(1, 1, 1, -1, 3), mode="bilinear", align_corners=True,
-                                              padding_mode=padding)
-        return out.reshape(gr.shape[1], -1).T
+        # (F.grid_sample has no second derivative - the reason the reference carries its own sampler; for the zeros /
+        # border modes the points are kept strictly inside the box, where all three modes are the same function)
+        return voxurf_cpu.grid_sample_custom(pts, gr, mn.double(), mx.double())
 
     want = run(ref_sampler, grid.double().requires_grad_(True), xyz.double().requires_grad_(True), torch.float64)
     got = run(lambda gr, pts: ops.trilinear(gr, pts, mn, mx, padding), grid.cuda().requires_grad_(True),
