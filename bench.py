@@ -311,7 +311,7 @@ def run_ours(args, rank, world, local_rank):
     clocks = sampler.stop() if sampler else None
 
     exchange_breakdown = None
-    if trainer is not None and trainer.mode in ("p2p", "nvls"):
+    if trainer is not None and trainer.mode in ("p2p", "nvls", "hybrid"):
         evs = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(10)]
         for i in range(10):
             trainer.profile_events = evs[i]
@@ -327,6 +327,15 @@ def run_ours(args, rank, world, local_rank):
             fine_dist = fine_stage_dist_bench(dev, rank, world)
         except Exception as e:
             fine_dist = {"error": str(e)[:200]}
+
+    extra_configs = {}
+    if not args.no_fine_stage:
+        for key, fn in (("config_d_render_256", config_d_bench), ("config_e_dual_branch", config_e_bench)):
+            try:     # parity-case configs measured for the record; never allowed to take the headline line down
+                extra_configs[key] = fn(dev, rank, world)
+            except Exception as e:
+                extra_configs[key] = {"error": str(e)[:200]}
+                torch.cuda.empty_cache()
 
     if rank != 0:
         if trainer is not None:
@@ -350,6 +359,8 @@ def run_ours(args, rank, world, local_rank):
         exchange = {
             "nvls": "ONE kernel: in-switch gradient reduction (multimem.ld_reduce) + masked Adam on 1/N of the "
                     "voxels + multicast parameter store (multimem.st); peer-memory flag barriers, no NCCL on the step",
+            "hybrid": "ONE kernel: part of the slice through the switch (multimem.ld_reduce / multimem.st), the rest "
+                      "through peer loads / stores, concurrently; masked Adam on 1/N of the voxels",
             "p2p": "ONE kernel: peer-load reduce-scatter + masked Adam on 1/N of the voxels + peer-store all-gather",
             "nccl": "NCCL all-reduce of the gradient records + full Adam on every rank"}[trainer.mode]
     line = {
@@ -419,6 +430,7 @@ def run_ours(args, rank, world, local_rank):
             line["fine_stage"] = {"error": str(e)[:200]}
     if fine_dist is not None:
         line["fine_stage"] = fine_dist
+    line.update(extra_configs)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
     print(json.dumps(line))
@@ -589,6 +601,138 @@ def fine_stage_dist_bench(dev, rank, world):
                         "rgbnet 57-128-128-128-3 (tcgen05), 8192 rays/step/rank, fwd+bwd+Adam, ray-sharded over %d ranks, "
                         "one flat NCCL all-reduce of the gradient buffer per step" % world,
             "train_rays_per_s": world * RAYS / (ms * 1e-3), "ms_per_step": ms, "n_gpus": world}
+
+
+def _fine_net():
+    import torch.nn as nn
+    from poseprobe_b200 import ops
+    net = nn.Sequential(nn.Linear(57, 128), nn.ReLU(inplace=True),
+                        nn.Sequential(nn.Linear(128, 128), nn.ReLU(inplace=True)),
+                        nn.Sequential(nn.Linear(128, 128), nn.ReLU(inplace=True)), nn.Linear(128, 3))
+    nn.init.constant_(net[-1].bias, 0)
+    ws, bs = ops.rgbnet_from_sequential(net)
+    return [w.detach() for w in ws], [b.detach() for b in bs]
+
+
+def _sphere_sdf(G, dev, seed):
+    """distance-to-sphere SDF (r = 0.5) + 0.02 N(0,1) on [-1,1]^3, generated on the device (the 320^3 grids of
+    config E are too large to draw on the host within the bench's time budget)."""
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    lin = torch.linspace(-1, 1, G, device=dev)
+    x, y, z = torch.meshgrid(lin, lin, lin, indexing="ij")
+    sdf = (x * x + y * y + z * z).sqrt() - 0.5 + 0.02 * torch.randn(G, G, G, device=dev, generator=gen)
+    k0 = 0.1 * torch.randn(1, 12, G, G, G, device=dev, generator=gen)
+    return sdf[None, None].contiguous(), k0
+
+
+def config_d_bench(dev, rank, world):
+    """BASELINE configs[3]: full-image render throughput, 800x800 = 640 000 rays through a 256^3 SDF grid + 12-channel
+    feature grid + rgbnet (tcgen05), forward only, in 8192-ray chunks; the chunks of the image are dealt round-robin to
+    the ranks (no communication: every rank writes its own rows), time = max over ranks."""
+    import torch.distributed as dist
+    from poseprobe_b200 import synthetic, voxurf
+    G, chunk = 256, 8192
+    n_rays = 800 * 800
+    n_chunks = (n_rays + chunk - 1) // chunk
+    sdf, k0 = _sphere_sdf(G, dev, 4242)
+    ws, bs = _fine_net()
+    eng = voxurf.FusedVoxurf(sdf, k0, ws, bs, XYZ_MIN, XYZ_MAX, stepsize=STEPSIZE, s_val=0.05, bg=0.0, sdf_alpha=10.0,
+                             sdf_beta=0.35, posbase_pe=5, viewbase_pe=1)
+    del sdf, k0
+    pool = []
+    for c in range(8):
+        o, d, v = synthetic.make_rays(chunk, seed=900 + c)
+        pool.append(tuple(x.to(dev) for x in (o, d, v)))
+    mine = list(range(rank, n_chunks, world))
+    sizes = [min(chunk, n_rays - c * chunk) for c in mine]
+    out_rgb = torch.empty(chunk, 3, pin_memory=True)
+    out_depth = torch.empty(chunk, pin_memory=True)
+
+    def image(to_host):
+        for c, n in zip(mine, sizes):
+            o, d, v = pool[c % 8]
+            res = eng.render(o[:n], d[:n], v[:n], want_depth=True)
+            if to_host:
+                out_rgb[:n].copy_(res[0], non_blocking=True)
+                out_depth[:n].copy_(res[3], non_blocking=True)
+
+    def timed(to_host, reps):
+        image(to_host)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            image(to_host)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+    ms = timed(False, 3)
+    ms_host = timed(True, 3)
+    m_per_ray = eng.n_samples() / sizes[-1] if sizes else 0.0
+    del eng
+    torch.cuda.empty_cache()
+    return {"workload": "BASELINE configs[3]: 800x800 image (640 000 rays, %d chunks of 8192 dealt round-robin to %d "
+                        "rank(s)), 256^3 SDF + 12-ch k0 + rgbnet 57-128-128-128-3 (tcgen05), forward only" % (n_chunks, world),
+            "render_mrays_per_s": n_rays / (ms * 1e-3) / 1e6, "ms_per_image": ms, "n_gpus": world, "scaling": "strong",
+            "composited_samples_per_ray": m_per_ray,
+            "e2e": {"render_mrays_per_s": n_rays / (ms_host * 1e-3) / 1e6, "ms_per_image": ms_host,
+                    "what": "rgb + depth of every chunk copied to pinned host memory inside the timed region"}}
+
+
+def config_e_bench(dev, rank, world):
+    """BASELINE configs[4]: dual-branch step, object 160^3 + scene 320^3 fine-stage grids (synthetic: the reference's
+    scene branch is an MLP NeRF), 8192 rays per rank through each, fwd + bwd + Adam; ray-sharded over the
+    ranks with one flat gradient all-reduce per grid and step (N = 8: 65 536 rays per step)."""
+    import torch.distributed as dist
+    from poseprobe_b200 import synthetic, voxurf
+    ws, bs = _fine_net()
+    engines = []
+    for G, seed in ((160, 11), (320, 12)):
+        sdf, k0 = _sphere_sdf(G, dev, seed)
+        kw = dict(stepsize=STEPSIZE, s_val=0.05, bg=0.0, sdf_alpha=10.0, sdf_beta=0.35, posbase_pe=5, viewbase_pe=1,
+                  lr_sdf=1e-4, lr_k0=1e-2, lr_rgbnet=1e-3)
+        if world > 1:
+            engines.append(voxurf.DistributedVoxurf(sdf, k0, ws, bs, XYZ_MIN, XYZ_MAX, **kw))
+        else:
+            engines.append(voxurf.FusedVoxurf(sdf, k0, ws, bs, XYZ_MIN, XYZ_MAX, **kw))
+        del sdf, k0
+    batches = []
+    for b in range(4):
+        o, d, v = synthetic.make_rays(RAYS, seed=3000 + 100 * rank + b)
+        t = torch.rand(RAYS, 3, generator=torch.Generator().manual_seed(77 + 100 * rank + b))
+        batches.append(tuple(x.to(dev) for x in (o, d, v, t)))
+
+    def step(i):
+        for e in engines:
+            e.train_step(*batches[i % 4])
+    for i in range(3):
+        step(i)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    steps = 8
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    gb = torch.cuda.memory_allocated(dev) / 1e9
+    del engines
+    torch.cuda.empty_cache()
+    return {"workload": "BASELINE configs[4]: dual-branch fine-stage train step, object 160^3 + scene 320^3 grids (sdf + "
+                        "12-ch k0 + rgbnet each), %d rays/rank through each, fwd+bwd+Adam, %d rank(s)" % (RAYS, world),
+            "train_rays_per_s": world * RAYS / (ms * 1e-3), "global_rays_per_step": world * RAYS, "ms_per_step": ms,
+            "n_gpus": world, "resident_GB_per_rank": gb}
 
 
 def cpu_baseline():

@@ -161,6 +161,19 @@ PP_API int pp_voxel_adam_exchange_mc(const void* vox_local, void* vox_mc, const 
                                      uint32_t epoch, const float* payload_in, float* payload_sum_out,
                                      pp_stream_t stream);
 
+/* Hybrid of the two above in ONE launch: the first mc_fraction of the slice (rounded down to 256 records) goes
+ * through the switch (vox_mc / grad_mc), the rest through peer loads and stores (vox_ptrs / grad_ptrs, which must
+ * address the same buffers the multicast addresses are bound to).  The multimem path is held by the switch's
+ * reduction rate and the peer path by link bytes, so together they finish sooner than either alone (DESIGN.md
+ * section 7).  Rank order of the fp32 sum differs between the two halves (switch order vs 0..w-1) but is the same on
+ * every rank for a given voxel, so replicas stay bit-identical.  world in {2, 4, 8}. */
+PP_API int pp_voxel_adam_exchange_hybrid(void* const* vox_ptrs, void* const* grad_ptrs, void* vox_mc,
+                                         const void* grad_mc, void* exp_avg, void* exp_avg_sq, int64_t n_voxels,
+                                         int32_t world, int32_t rank, int32_t step, float beta1, float beta2,
+                                         float lr_density, float lr_k0, float eps, void* const* sync_ptrs,
+                                         uint32_t epoch, const float* payload_in, float* payload_sum_out,
+                                         float mc_fraction, pp_stream_t stream);
+
 /* ---- Voxurf fine stage (SDF grid + 12-channel feature grid + rgbnet), fused -------------------------------
  * Reference: Voxurf.forward, non-deform branch (lib/voxurf_coarse.py:922-1091).  A train step is
  *   pp_voxurf_march_features -> pp_rgbnet_forward_packed (compositing epilogue) -> pp_voxurf_ray_loss ->

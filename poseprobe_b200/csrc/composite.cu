@@ -4,10 +4,10 @@
 // (`for(i=i_s; i<i_e_max; ++i)`), so a warp touches 32 different rays per step: every load/store is
 // a 32-way uncoalesced access, and 8192 rays occupy 256 warps.  The recurrences themselves are strictly
 // sequential *and* their float roundings decide an integer output (the early-termination index written
-// back to i_end), so they cannot be re-associated.  The B200 design gives every ray a group of 8 lanes: they
-// load / store 8 consecutive samples as one sector, the recurrence runs in the reference's order on values
-// broadcast by shuffle (one instruction advances 4 rays), and everything that is not part of the recurrence
-// (w = T*alpha, the backward's division) is done by the lanes in parallel.
+// back to i_end), so they cannot be re-associated.  The B200 design keeps one lane per ray for the recurrence (every
+// instruction of the chain advances 32 rays) and fixes the memory side: the warp moves [32 rays x 8 samples] tiles
+// through shared memory, so every global load / store is a 32-byte sector per ray instead of a 4-byte touch of 32
+// different lines, and the next tile's loads are in flight while the chain runs.
 #include "common.cuh"
 
 namespace pp {
@@ -31,123 +31,163 @@ __global__ void segment_bounds_kernel(const int64_t* __restrict__ ray_id, int64_
 }
 
 // ---- forward -------------------------------------------------------------------------------------
-// kGroup lanes per ray, 32/kGroup rays per warp.  The recurrence T_cum *= (1. - alpha) is double arithmetic
-// narrowed to float at every step (reference :596) and its roundings decide the early-termination index, so
-// it is evaluated in the reference's order - by all lanes of the ray's group redundantly, on values broadcast
-// with width-kGroup shuffles.  The loads and stores of a kGroup-sample chunk are one 32-byte sector per ray,
-// lane j keeps the transmittance that entered sample j, nothing passes through shared memory, and one
-// instruction of the chain advances 32/kGroup rays.  8192 rays = 2048 warps, against the reference's
-// one-thread-per-ray loop that leaves 256 warps for 148 SMs and touches 32 different lines per step.
-constexpr int kGroup = 8;                     // lanes per ray
-constexpr int kRaysPerWarp = kWarp / kGroup;
-constexpr int kCompWarps = 4;                 // warps per block
-constexpr int kRaysPerBlock = kCompWarps * kRaysPerWarp;
+// The recurrence T_cum *= (1. - alpha) is double arithmetic narrowed to float at every step (reference :596) and its
+// roundings decide the early-termination index, so it runs in the reference's order: ONE lane per ray, as in the
+// reference, 32 rays per warp - every instruction of the chain (two conversions, a double multiply, a compare, all on
+// narrow pipes) advances 32 rays.  What the reference gets wrong is memory: its lanes walk 32 different rays, so every
+// load / store touches 32 lines.  Here the warp moves a [32 rays x 8 samples] tile per step: 8-lane groups read 8
+// consecutive samples of one ray (one 32-byte sector) into a shared-memory tile, each lane reads back its own ray's
+// row, runs 8 steps of the chain in registers, writes T and weight rows back, and the groups store them as sectors.
+// The loads of the next tile are in flight during the chain.  Samples past the termination get the reference's fill
+// values (T = 1, weight = 0) from the same streaming stores, so no separate fill pass over [M] is needed.
+constexpr int kTile = 8;                      // samples per ray and step
+constexpr int kGroups = kWarp / kTile;        // rays loaded / stored per instruction
+
+// row r, column c of a [32][kTile] tile; rows whose bit 2 is set swap their two 4-element halves so that the 128-bit
+// row reads of lanes r and r+4 fall into different banks
+__device__ __forceinline__ int tile_at(int r, int c) { return r * kTile + (c ^ (((r >> 2) & 1) << 2)); }
 
 template <typename scalar_t>
-__global__ void __launch_bounds__(kCompWarps* kWarp)
+__global__ void __launch_bounds__(kWarp)
 alpha2weight_fwd_kernel(const scalar_t* __restrict__ alpha, int64_t n_rays,
                         scalar_t* __restrict__ weight, scalar_t* __restrict__ T_out,
                         scalar_t* __restrict__ alphainv_last, const int64_t* __restrict__ i_start,
                         int64_t* __restrict__ i_end) {
-  const int lane = threadIdx.x & 31, sub = lane / kGroup, sl = lane % kGroup;
-  const int64_t ray = (blockIdx.x * (int64_t)kCompWarps + (threadIdx.x >> 5)) * kRaysPerWarp + sub;
+  __shared__ scalar_t s_a[kWarp * kTile], s_T[kWarp * kTile], s_w[kWarp * kTile];
+  const int lane = threadIdx.x, sub = lane / kTile, sl = lane % kTile;
+  const int64_t ray = blockIdx.x * (int64_t)kWarp + lane;
   const bool live = ray < n_rays;
-  const int64_t begin = live ? i_start[ray] : 0, end = live ? i_end[ray] : 0;
+  const int begin = live ? static_cast<int>(i_start[ray]) : 0, end = live ? static_cast<int>(i_end[ray]) : 0;
+  int pos = begin;      // (sample indices fit 32 bits: the entry point rejects n_pts > INT32_MAX)
+  int cut = -1;       // early-termination index (exclusive end), -1 while the ray is still marching
   float T_cum = 1.f;
-  int64_t cut = -1;       // early-termination index (exclusive end), -1 while the ray is still marching
-  int64_t pos = begin;
-  bool active = pos < end;
-  scalar_t a_next = (pos + sl < end) ? alpha[pos + sl] : scalar_t(0);
-  while (__any_sync(kFull, active)) {
-    const int64_t idx = pos + sl;
-    const scalar_t a = a_next;
-    if (active && pos + kGroup < end) a_next = (idx + kGroup < end) ? alpha[idx + kGroup] : scalar_t(0);
-    int done = active ? static_cast<int>(min64(kGroup, end - pos)) : 0;   // samples composited in this chunk
-    const double q = 1. - static_cast<double>(a);
-    float T_mine = 1.f;
+  // tile loads: instruction k of a step serves rays 4k + sub
+  scalar_t nxt[kTile];
+  auto issue_loads = [&](int p_mine) {
 #pragma unroll
-    for (int j = 0; j < kGroup; ++j) {
-      const double qj = __shfl_sync(kFull, q, j, kGroup);
-      if (j < done) {
-        if (sl == j) T_mine = T_cum;
-        T_cum = static_cast<float>(static_cast<double>(T_cum) * qj);
-        if (T_cum < 1e-3) {   // float widened, compared with the double literal (reference :597)
-          done = j + 1;
-          cut = pos + j + 1;
-        }
+    for (int k = 0; k < kTile; ++k) {
+      const int r = k * kGroups + sub;
+      const int p = __shfl_sync(kFull, p_mine, r), e = __shfl_sync(kFull, end, r);
+      nxt[k] = (p + sl < e) ? alpha[p + sl] : scalar_t(0);
+    }
+  };
+  issue_loads(pos);
+  while (__any_sync(kFull, pos < end)) {
+#pragma unroll
+    for (int k = 0; k < kTile; ++k) s_a[tile_at(k * kGroups + sub, sl)] = nxt[k];
+    __syncwarp();
+    scalar_t a[kTile];
+#pragma unroll
+    for (int j = 0; j < kTile; ++j) a[j] = s_a[tile_at(lane, j)];
+    issue_loads(pos + kTile);                     // next tile: in flight during the chain
+    scalar_t Tj[kTile], wj[kTile];
+#pragma unroll
+    for (int j = 0; j < kTile; ++j) {
+      const bool in = cut < 0 && pos + j < end;
+      Tj[j] = in ? static_cast<scalar_t>(T_cum) : scalar_t(1);
+      wj[j] = in ? T_cum * a[j] : scalar_t(0);
+      if (in) {
+        T_cum = static_cast<float>(static_cast<double>(T_cum) * (1. - static_cast<double>(a[j])));
+        if (T_cum < 1e-3) cut = pos + j + 1;      // float widened, compared with the double literal (reference :597)
       }
     }
-    if (active && idx < end) {
-      // samples past the termination keep the reference's fill values: T = 1, weight = 0
-      const bool in = sl < done;
-      T_out[idx] = in ? static_cast<scalar_t>(T_mine) : scalar_t(1);
-      weight[idx] = in ? T_mine * a : scalar_t(0);
-    }
-    if (active) {
-      pos += kGroup;
-      active = cut < 0 && pos < end;
-    }
-  }
-  // tails of early-terminated rays: fill values, written by the whole warp one ray at a time
 #pragma unroll
-  for (int s = 0; s < kRaysPerWarp; ++s) {
-    const int64_t from = __shfl_sync(kFull, (cut >= 0) ? pos : end, s * kGroup);
-    const int64_t to = __shfl_sync(kFull, end, s * kGroup);
-    for (int64_t i = from + lane; i < to; i += kWarp) {
-      T_out[i] = scalar_t(1);
-      weight[i] = scalar_t(0);
+    for (int j = 0; j < kTile; ++j) {
+      s_T[tile_at(lane, j)] = Tj[j];
+      s_w[tile_at(lane, j)] = wj[j];
     }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < kTile; ++k) {
+      const int r = k * kGroups + sub;
+      const int p = __shfl_sync(kFull, pos, r), e = __shfl_sync(kFull, end, r);
+      if (p + sl < e) {
+        T_out[p + sl] = s_T[tile_at(r, sl)];
+        weight[p + sl] = s_w[tile_at(r, sl)];
+      }
+    }
+    __syncwarp();
+    if (pos < end) pos += kTile;
   }
-  if (live && sl == 0) {
+  if (live) {
     if (cut >= 0) i_end[ray] = cut;  // otherwise i_end already holds i_e_max (or 0 for an empty ray)
     alphainv_last[ray] = T_cum;
   }
 }
 
 // ---- backward ------------------------------------------------------------------------------------
-// Same shape, walking each ray downwards from its (early-terminated) end: lane j of a chunk is sample
-// top-1-j.  back_cum += grad_weights*weight is an FMA in scalar_t narrowed to float (reference :674); the
-// division and the difference are not part of the recurrence and run in parallel over the lanes.
+// Same shape, walking each ray downwards from its (early-terminated) end in tiles [top - 8, top).
+// back_cum += grad_weights*weight is an FMA in scalar_t narrowed to float (reference :674); the double division and
+// the difference are not part of the recurrence but are done by the ray's own lane as well (8 per step).
 template <typename scalar_t>
-__global__ void __launch_bounds__(kCompWarps* kWarp)
+__global__ void __launch_bounds__(kWarp)
 alpha2weight_bwd_kernel(const scalar_t* __restrict__ alpha, const scalar_t* __restrict__ weight,
                         const scalar_t* __restrict__ T, const scalar_t* __restrict__ alphainv_last,
                         const int64_t* __restrict__ i_start, const int64_t* __restrict__ i_end,
                         int64_t n_rays, const scalar_t* __restrict__ grad_weights,
                         const scalar_t* __restrict__ grad_last, scalar_t* __restrict__ grad) {
-  const int lane = threadIdx.x & 31, sub = lane / kGroup, sl = lane % kGroup;
-  const int64_t ray = (blockIdx.x * (int64_t)kCompWarps + (threadIdx.x >> 5)) * kRaysPerWarp + sub;
+  __shared__ scalar_t s_in[4][kWarp * kTile], s_out[kWarp * kTile];
+  const int lane = threadIdx.x, sub = lane / kTile, sl = lane % kTile;
+  const int64_t ray = blockIdx.x * (int64_t)kWarp + lane;
   const bool live = ray < n_rays;
-  const int64_t begin = live ? i_start[ray] : 0;
-  int64_t top = live ? i_end[ray] : 0;
+  const int begin = live ? static_cast<int>(i_start[ray]) : 0;
+  int top = live ? static_cast<int>(i_end[ray]) : 0;
   // back_cum = grad_last * alphainv_last (reference :671)
   float back = live ? static_cast<float>(grad_last[ray] * alphainv_last[ray]) : 0.f;
-  while (__any_sync(kFull, top > begin)) {
-    const int64_t idx = top - 1 - sl;
-    const bool valid = idx >= begin;
-    const scalar_t gw = valid ? grad_weights[idx] : scalar_t(0);
-    const scalar_t wv = valid ? weight[idx] : scalar_t(0);
-    const scalar_t Tv = valid ? T[idx] : scalar_t(0);
-    const scalar_t av = valid ? alpha[idx] : scalar_t(0);
-    const int cnt = static_cast<int>(min64(kGroup, max64(top - begin, 0)));
-    float back_mine = 0.f;
+  const scalar_t* src[4] = {grad_weights, weight, T, alpha};
+  scalar_t nxt[4][kTile];
+  auto issue_loads = [&](int top_mine) {
 #pragma unroll
-    for (int j = 0; j < kGroup; ++j) {
-      const scalar_t gj = __shfl_sync(kFull, gw, j, kGroup);
-      const scalar_t wj = __shfl_sync(kFull, wv, j, kGroup);
-      if (j < cnt) {
-        if (sl == j) back_mine = back;
-        back = static_cast<float>(fma_rn(gj, wj, static_cast<scalar_t>(back)));
+    for (int k = 0; k < kTile; ++k) {
+      const int r = k * kGroups + sub;
+      const int t = __shfl_sync(kFull, top_mine, r), b = __shfl_sync(kFull, begin, r);
+      const int idx = t - kTile + sl;
+      const bool ok = idx >= b && idx < t;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) nxt[q][k] = ok ? src[q][idx] : scalar_t(0);
+    }
+  };
+  issue_loads(top);
+  while (__any_sync(kFull, top > begin)) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int k = 0; k < kTile; ++k) s_in[q][tile_at(k * kGroups + sub, sl)] = nxt[q][k];
+    __syncwarp();
+    scalar_t gw[kTile], wv[kTile], Tv[kTile], av[kTile];
+#pragma unroll
+    for (int j = 0; j < kTile; ++j) {
+      gw[j] = s_in[0][tile_at(lane, j)];
+      wv[j] = s_in[1][tile_at(lane, j)];
+      Tv[j] = s_in[2][tile_at(lane, j)];
+      av[j] = s_in[3][tile_at(lane, j)];
+    }
+    issue_loads(top - kTile);
+    const int base = top - kTile;           // column j of the tile is sample base + j
+#pragma unroll
+    for (int j = kTile - 1; j >= 0; --j) {
+      const bool valid = base + j >= begin && base + j < top;
+      scalar_t g = scalar_t(0);
+      if (valid) {
+        // grad = gw*T - back/(1-alpha+1e-10): product in scalar_t, quotient and difference in double
+        const scalar_t gT = mul_rn(gw[j], Tv[j]);
+        const scalar_t one_minus = scalar_t(1) - av[j];
+        const double qd = static_cast<double>(back) / (static_cast<double>(one_minus) + 1e-10);
+        g = static_cast<scalar_t>(static_cast<double>(gT) - qd);
+        back = static_cast<float>(fma_rn(gw[j], wv[j], static_cast<scalar_t>(back)));
       }
+      s_out[tile_at(lane, j)] = g;
     }
-    if (valid) {
-      // grad = gw*T - back/(1-alpha+1e-10): product in scalar_t, quotient and difference in double
-      const scalar_t gT = mul_rn(gw, Tv);
-      const scalar_t one_minus = scalar_t(1) - av;
-      const double qd = static_cast<double>(back_mine) / (static_cast<double>(one_minus) + 1e-10);
-      grad[idx] = static_cast<scalar_t>(static_cast<double>(gT) - qd);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < kTile; ++k) {
+      const int r = k * kGroups + sub;
+      const int t = __shfl_sync(kFull, top, r), b = __shfl_sync(kFull, begin, r);
+      const int idx = t - kTile + sl;
+      if (idx >= b && idx < t) grad[idx] = s_out[tile_at(r, sl)];
     }
-    top -= kGroup;
+    __syncwarp();
+    if (top > begin) top -= kTile;
   }
 }
 
@@ -357,9 +397,8 @@ extern "C" int pp_alpha2weight(pp_dtype dtype, const void* alpha, const int64_t*
   PP_REQUIRE(alpha && ray_id && weight && T, PP_ERR_INVALID_ARG, "alpha2weight: null pointer");
   segment_bounds_kernel<<<ceil_div(n_pts, 256), 256, 0, s>>>(ray_id, n_pts, n_rays, i_start, i_end);
   PP_CHECK_LAUNCH("alpha2weight(bounds)");
-  const int rays_per_block = kRaysPerBlock;
   PP_DISPATCH(dtype, {
-    alpha2weight_fwd_kernel<scalar_t><<<ceil_div(n_rays, rays_per_block), kCompWarps * kWarp, 0, s>>>(
+    alpha2weight_fwd_kernel<scalar_t><<<ceil_div(n_rays, kWarp), kWarp, 0, s>>>(
         (const scalar_t*)alpha, n_rays, (scalar_t*)weight, (scalar_t*)T, (scalar_t*)alphainv_last,
         i_start, i_end);
   });
@@ -373,6 +412,7 @@ extern "C" int pp_alpha2weight_backward(pp_dtype dtype, const void* alpha, const
                                         int64_t n_rays, int64_t n_pts, const void* grad_weights,
                                         const void* grad_last, void* grad, pp_stream_t stream) {
   PP_REQUIRE(n_pts >= 0 && n_rays >= 0, PP_ERR_INVALID_ARG, "alpha2weight_backward: negative extent");
+  PP_REQUIRE(n_pts <= INT32_MAX, PP_ERR_TOO_LARGE, "alpha2weight_backward: n_pts exceeds 32-bit index space");
   if (n_pts == 0) return PP_OK;
   PP_REQUIRE(grad, PP_ERR_INVALID_ARG, "alpha2weight_backward: grad is null");
   cudaStream_t s = as_stream(stream);
@@ -382,9 +422,8 @@ extern "C" int pp_alpha2weight_backward(pp_dtype dtype, const void* alpha, const
   if (n_rays == 0) return PP_OK;
   PP_REQUIRE(alpha && weight && T && alphainv_last && i_start && i_end && grad_weights && grad_last,
              PP_ERR_INVALID_ARG, "alpha2weight_backward: null pointer");
-  const int rays_per_block = kRaysPerBlock;
   PP_DISPATCH(dtype, {
-    alpha2weight_bwd_kernel<scalar_t><<<ceil_div(n_rays, rays_per_block), kCompWarps * kWarp, 0, s>>>(
+    alpha2weight_bwd_kernel<scalar_t><<<ceil_div(n_rays, kWarp), kWarp, 0, s>>>(
         (const scalar_t*)alpha, (const scalar_t*)weight, (const scalar_t*)T,
         (const scalar_t*)alphainv_last, i_start, i_end, n_rays, (const scalar_t*)grad_weights,
         (const scalar_t*)grad_last, (scalar_t*)grad);

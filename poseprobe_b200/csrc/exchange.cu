@@ -238,6 +238,139 @@ voxel_adam_exchange_mc_kernel(const float4* __restrict__ vox_local, float4* vox_
   }
 }
 
+// ---- hybrid: in-switch reduction AND plain peer loads / stores, side by side ------------------------------
+// Measured at 8 ranks (profiles/r1_results.md): the multimem path moves (w+1)/w of the record array per link
+// direction but is held at ~460 GB/s by the switch's reduction / multicast rate, while plain peer loads / stores
+// move 2(w-1)/w of it at ~600 GB/s - neither fills the links.  The two limits are different resources, so one
+// launch runs both: the first mc_records of the slice go through the switch (blocks [0, mc_blocks)), the rest of
+// the slice through peer loads (fixed rank order) and peer stores (the remaining blocks), concurrently.
+template <int kWorld>
+__global__ void __launch_bounds__(kXchgThreads, 2)
+voxel_adam_exchange_hybrid_kernel(PeerPtrs pp, float4* vox_mc, const float4* grad_mc, float4* __restrict__ m4,
+                                  float4* __restrict__ v4, int64_t begin, int64_t split, int64_t end, int mc_blocks,
+                                  int rank, float ss_density, float ss_k0, float b1, float b2, float eps, SyncPtrs sp,
+                                  unsigned int epoch, const float* __restrict__ payload_in,
+                                  float* __restrict__ payload_sum) {
+  if (epoch != 0u) {
+    if (threadIdx.x < 32) peer_announce_and_wait(sp, kWorld, rank, epoch, payload_in, blockIdx.x == 0);
+    __threadfence();
+    __syncthreads();
+    const bool dead = peer_timed_out(sp, rank);
+    if (payload_sum && blockIdx.x == 0 && threadIdx.x == 0) {
+      const SyncBlock* mine = sp.blk[rank];
+      float a = 0.f, b = 0.f;
+      for (int q = 0; q < kWorld; ++q) {
+        a += mine->payload[q][0];
+        b += mine->payload[q][1];
+      }
+      payload_sum[0] = dead ? __int_as_float(0x7fc00000) : a;
+      payload_sum[1] = dead ? __int_as_float(0x7fc00000) : b;
+    }
+    if (dead) return;
+  } else if (sp.blk[rank] && peer_timed_out(sp, rank)) {
+    return;
+  }
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* vox_local = pp.vox[rank];
+  if ((int)blockIdx.x < mc_blocks) {
+    // ---- switch path over [begin, split) ----
+    constexpr int kDepth = 3;
+    const int64_t stride = (int64_t)mc_blocks * blockDim.x;
+    const int64_t first = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    float4 gq[kDepth], pq[kDepth], mq[kDepth], vq[kDepth];
+#pragma unroll
+    for (int d = 0; d < kDepth; ++d) {
+      const int64_t i = first + d * stride;
+      const bool in = i < split;
+      gq[d] = in ? mc_ld_reduce_add(grad_mc + i) : zero;
+      pq[d] = in ? vox_local[i] : zero;
+      mq[d] = in ? m4[i - begin] : zero;
+      vq[d] = in ? v4[i - begin] : zero;
+    }
+    for (int64_t i = first; i < split; i += stride) {
+      const float4 g = gq[0];
+      float4 p = pq[0], m = mq[0], v = vq[0];
+#pragma unroll
+      for (int d = 0; d + 1 < kDepth; ++d) {
+        gq[d] = gq[d + 1];
+        pq[d] = pq[d + 1];
+        mq[d] = mq[d + 1];
+        vq[d] = vq[d + 1];
+      }
+      {
+        const int64_t n = i + kDepth * stride;
+        const bool in = n < split;
+        gq[kDepth - 1] = in ? mc_ld_reduce_add(grad_mc + n) : zero;
+        pq[kDepth - 1] = in ? vox_local[n] : zero;
+        mq[kDepth - 1] = in ? m4[n - begin] : zero;
+        vq[kDepth - 1] = in ? v4[n - begin] : zero;
+      }
+      if (g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f) continue;
+      adam_elem_x(p.x, g.x, m.x, v.x, ss_density, b1, b2, eps);
+      adam_elem_x(p.y, g.y, m.y, v.y, ss_k0, b1, b2, eps);
+      adam_elem_x(p.z, g.z, m.z, v.z, ss_k0, b1, b2, eps);
+      adam_elem_x(p.w, g.w, m.w, v.w, ss_k0, b1, b2, eps);
+      m4[i - begin] = m;
+      v4[i - begin] = v;
+      mc_st(vox_mc + i, p);
+    }
+  } else {
+    // ---- peer path over [split, end) ----
+    constexpr int kDepth = 2;
+    const int nb = (int)gridDim.x - mc_blocks;
+    const int64_t stride = (int64_t)nb * blockDim.x;
+    const int64_t first = split + (blockIdx.x - mc_blocks) * (int64_t)blockDim.x + threadIdx.x;
+    float4 gr[kDepth][kWorld], pq[kDepth], mq[kDepth], vq[kDepth];
+#pragma unroll
+    for (int d = 0; d < kDepth; ++d) {
+      const int64_t i = first + d * stride;
+      const bool in = i < end;
+#pragma unroll
+      for (int r = 0; r < kWorld; ++r) gr[d][r] = in ? pp.grad[r][i] : zero;
+      pq[d] = in ? vox_local[i] : zero;
+      mq[d] = in ? m4[i - begin] : zero;
+      vq[d] = in ? v4[i - begin] : zero;
+    }
+    for (int64_t i = first; i < end; i += stride) {
+      float4 g = gr[0][0];
+#pragma unroll
+      for (int r = 1; r < kWorld; ++r) {
+        g.x += gr[0][r].x;
+        g.y += gr[0][r].y;
+        g.z += gr[0][r].z;
+        g.w += gr[0][r].w;
+      }
+      float4 p = pq[0], m = mq[0], v = vq[0];
+#pragma unroll
+      for (int d = 0; d + 1 < kDepth; ++d) {
+#pragma unroll
+        for (int r = 0; r < kWorld; ++r) gr[d][r] = gr[d + 1][r];
+        pq[d] = pq[d + 1];
+        mq[d] = mq[d + 1];
+        vq[d] = vq[d + 1];
+      }
+      {
+        const int64_t n = i + kDepth * stride;
+        const bool in = n < end;
+#pragma unroll
+        for (int r = 0; r < kWorld; ++r) gr[kDepth - 1][r] = in ? pp.grad[r][n] : zero;
+        pq[kDepth - 1] = in ? vox_local[n] : zero;
+        mq[kDepth - 1] = in ? m4[n - begin] : zero;
+        vq[kDepth - 1] = in ? v4[n - begin] : zero;
+      }
+      if (g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f) continue;
+      adam_elem_x(p.x, g.x, m.x, v.x, ss_density, b1, b2, eps);
+      adam_elem_x(p.y, g.y, m.y, v.y, ss_k0, b1, b2, eps);
+      adam_elem_x(p.z, g.z, m.z, v.z, ss_k0, b1, b2, eps);
+      adam_elem_x(p.w, g.w, m.w, v.w, ss_k0, b1, b2, eps);
+      m4[i - begin] = m;
+      v4[i - begin] = v;
+#pragma unroll
+      for (int r = 0; r < kWorld; ++r) pp.vox[r][i] = p;
+    }
+  }
+}
+
 // ---- cross-rank stream barrier over peer memory -----------------------------------------------------
 // Each rank owns a small IPC-shared sync block.  Rank `me` announces epoch E by storing E into slot `me`
 // of every peer's block (release, system scope) and then waits until all slots of its own block reached E
@@ -347,6 +480,64 @@ extern "C" int pp_voxel_adam_exchange_mc(const void* vox_local, void* vox_mc, co
   else PP_LAUNCH_MC(6);
 #undef PP_LAUNCH_MC
   PP_CHECK_LAUNCH("voxel_adam_exchange_mc");
+  return PP_OK;
+}
+
+extern "C" int pp_voxel_adam_exchange_hybrid(void* const* vox_ptrs, void* const* grad_ptrs, void* vox_mc,
+                                             const void* grad_mc, void* exp_avg, void* exp_avg_sq, int64_t n_voxels,
+                                             int32_t world, int32_t rank, int32_t step, float beta1, float beta2,
+                                             float lr_density, float lr_k0, float eps, void* const* sync_ptrs,
+                                             uint32_t epoch, const float* payload_in, float* payload_sum_out,
+                                             float mc_fraction, pp_stream_t stream) {
+  PP_REQUIRE(vox_ptrs && grad_ptrs && vox_mc && grad_mc && exp_avg && exp_avg_sq, PP_ERR_INVALID_ARG,
+             "voxel_adam_exchange_hybrid: null pointer");
+  PP_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, PP_ERR_INVALID_ARG,
+             "voxel_adam_exchange_hybrid: bad world/rank %d/%d", rank, world);
+  PP_REQUIRE(epoch == 0 || sync_ptrs, PP_ERR_INVALID_ARG, "voxel_adam_exchange_hybrid: fused barrier needs sync_ptrs");
+  PP_REQUIRE(mc_fraction >= 0.f && mc_fraction <= 1.f, PP_ERR_INVALID_ARG,
+             "voxel_adam_exchange_hybrid: mc_fraction %f outside [0, 1]", (double)mc_fraction);
+  const int64_t shard = pp_voxel_shard_size(n_voxels, world);
+  const int64_t begin = shard * rank < n_voxels ? shard * rank : n_voxels;
+  const int64_t end = begin + shard < n_voxels ? begin + shard : n_voxels;
+  if (end <= begin && epoch == 0) return PP_OK;
+  const int64_t n_rec = end > begin ? end - begin : 0;
+  // the split is the same on every rank relative to its slice and falls on a 256-record (4 KB) boundary
+  int64_t n_mc = (int64_t)((double)n_rec * (double)mc_fraction) / 256 * 256;
+  if (mc_fraction >= 1.f) n_mc = n_rec;
+  const int64_t split = begin + n_mc;
+  PeerPtrs pp;
+  SyncPtrs sp;
+  for (int r = 0; r < kMaxWorld; ++r) {
+    pp.vox[r] = r < world ? (float4*)vox_ptrs[r] : nullptr;
+    pp.grad[r] = r < world ? (const float4*)grad_ptrs[r] : nullptr;
+    PP_REQUIRE(r >= world || (pp.vox[r] && pp.grad[r]), PP_ERR_INVALID_ARG,
+               "voxel_adam_exchange_hybrid: null peer pointer for rank %d", r);
+    sp.blk[r] = (sync_ptrs && r < world) ? (SyncBlock*)sync_ptrs[r] : nullptr;
+  }
+  const int total = n_rec > 0 ? exchange_blocks(n_rec) : 1;
+  int mc_blocks = n_rec > 0 ? (int)((double)total * (double)n_mc / (double)n_rec + 0.5) : 1;
+  if (n_mc > 0 && mc_blocks < 1) mc_blocks = 1;
+  if (n_mc == 0) mc_blocks = 0;
+  int p2p_blocks = total - mc_blocks;
+  if (n_rec - n_mc > 0 && p2p_blocks < 1) p2p_blocks = 1;
+  if (n_rec - n_mc == 0) p2p_blocks = 0;
+  const int blocks = mc_blocks + p2p_blocks > 0 ? mc_blocks + p2p_blocks : 1;
+  const float ssd = adam_step_size_x(lr_density, beta1, beta2, step), ssk = adam_step_size_x(lr_k0, beta1, beta2, step);
+#define PP_LAUNCH_H(W)                                                                                              \
+  voxel_adam_exchange_hybrid_kernel<W><<<blocks, kXchgThreads, 0, as_stream(stream)>>>(                             \
+      pp, (float4*)vox_mc, (const float4*)grad_mc, (float4*)exp_avg, (float4*)exp_avg_sq, begin, split, end,        \
+      n_mc > 0 ? (mc_blocks > 0 ? mc_blocks : 1) : 0, rank, ssd, ssk, beta1, beta2, eps, sp, epoch, payload_in,     \
+      payload_sum_out)
+  switch (world) {
+    case 2: PP_LAUNCH_H(2); break;
+    case 4: PP_LAUNCH_H(4); break;
+    case 8: PP_LAUNCH_H(8); break;
+    default:
+      set_error("voxel_adam_exchange_hybrid: world size %d not supported (2, 4, 8)", world);
+      return PP_ERR_UNSUPPORTED;
+  }
+#undef PP_LAUNCH_H
+  PP_CHECK_LAUNCH("voxel_adam_exchange_hybrid");
   return PP_OK;
 }
 

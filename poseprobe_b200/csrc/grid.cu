@@ -25,7 +25,7 @@ struct GridGeom {
 };
 
 struct Corner8 {
-  int64_t off[8];  // linear offsets inside one channel plane (valid only where ok)
+  int off[8];      // linear offsets inside one channel plane (valid only where ok; planes are < 2^31 elements)
   float w[8];      // trilinear weights
   bool ok[8];      // corner inside the grid
   float fx, fy, fz, gx, gy, gz;  // fractional parts along X,Y,Z and their complements
@@ -73,13 +73,14 @@ __device__ __forceinline__ void make_corners(const GridGeom& g, float x, float y
       cz = min(max(cz, 0), g.sz - 1);
     }
     c.ok[q] = (cx >= 0) & (cx < g.sx) & (cy >= 0) & (cy < g.sy) & (cz >= 0) & (cz < g.sz);
-    c.off[q] = ((int64_t)cx * g.sy + cy) * g.sz + cz;
+    c.off[q] = (cx * g.sy + cy) * g.sz + cz;
     c.w[q] = mul_rn(mul_rn(dz ? c.fz : c.gz, dy ? c.fy : c.gy), dx ? c.fx : c.gx);
   }
 }
 
+// (<= 64 registers: the kernel is gather-latency bound and wants all 2048 threads of an SM resident)
 template <bool kWithDxyz>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 trilinear_fwd_kernel(const float* __restrict__ grid, int n_ch, GridGeom g,
                      const float* __restrict__ xyz, int64_t n_pts, float* __restrict__ out,
                      float* __restrict__ dout_dxyz) {
@@ -121,7 +122,7 @@ __device__ __forceinline__ void red_add(float* addr, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 trilinear_bwd_kernel(const float* __restrict__ grid, int n_ch, GridGeom g,
                      const float* __restrict__ xyz, int64_t n_pts,
                      const float* __restrict__ grad_out, float* __restrict__ grad_grid,
@@ -228,6 +229,7 @@ static int make_geom(GridGeom& g, int32_t sx, int32_t sy, int32_t sz, const floa
   PP_REQUIRE(sx > 0 && sy > 0 && sz > 0, PP_ERR_INVALID_ARG, "trilinear: empty grid");
   PP_REQUIRE(mn && mx, PP_ERR_INVALID_ARG, "trilinear: xyz_min/xyz_max (host) are null");
   PP_REQUIRE(padding >= 0 && padding <= 2, PP_ERR_INVALID_ARG, "trilinear: padding must be 0|1|2");
+  PP_REQUIRE((int64_t)sx * sy * sz <= INT32_MAX, PP_ERR_TOO_LARGE, "trilinear: more than 2^31 voxels per channel");
   g.sx = sx; g.sy = sy; g.sz = sz; g.border = padding;
   for (int c = 0; c < 3; ++c) { g.mn[c] = mn[c]; g.mx[c] = mx[c]; }
   return PP_OK;

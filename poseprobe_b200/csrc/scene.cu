@@ -65,7 +65,11 @@ nerf_composite_fwd_kernel(const float* __restrict__ ray, const float* __restrict
       dn = s.depth;
     }
     const float incl = warp_incl_scan(sd, lane);
-    const float T = expf(-(carry + (incl - sd)));          // exclusive prefix sum (frequency_nerf.py:316)
+    // exclusive prefix sum (frequency_nerf.py:316) taken from the left neighbour, never as incl - sd: the last
+    // sample's sigma * delta carries the 1e10 interval and would absorb the prefix
+    float excl = __shfl_up_sync(kFull, incl, 1);
+    if (lane == 0) excl = 0.f;
+    const float T = expf(-(carry + excl));
     carry += __shfl_sync(kFull, incl, 31);
     if (n < N) {
       const float w = T * (1.f - ema);
@@ -156,7 +160,9 @@ nerf_composite_bwd_kernel(const float* __restrict__ ray, const float* __restrict
       cb = c_r[3 * n + 2];
     }
     const float incl = warp_incl_scan(s.sd, lane);
-    const float T = expf(-(carry_in + (incl - s.sd)));
+    float excl = __shfl_up_sync(kFull, incl, 1);
+    if (lane == 0) excl = 0.f;
+    const float T = expf(-(carry_in + excl));
     const float w = (n < N) ? T * (1.f - s.ema) : 0.f;
     const float gw = (n < N) ? gr * cr + gg * cg + gb * cb + gd * s.depth + go + (g_weights ? g_weights[r * N + n] : 0.f)
                              : 0.f;
@@ -167,7 +173,9 @@ nerf_composite_bwd_kernel(const float* __restrict__ ray, const float* __restrict
       const float dnv = __shfl_down_sync(kFull, S, o);
       if (lane + o < 32) S += dnv;
     }
-    const float after = suffix + (S - c);                   // sum over the samples strictly after n
+    float right = __shfl_down_sync(kFull, S, 1);
+    if (lane == 31) right = 0.f;
+    const float after = suffix + right;                     // sum over the samples strictly after n
     suffix += __shfl_sync(kFull, S, 0);
     if (n < N) {
       if (grad_rgb_s) {

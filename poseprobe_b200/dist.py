@@ -135,7 +135,9 @@ class DistributedDVGO:
         self.fused_sync = os.environ.get("PP_XCHG_FUSED_SYNC", "1") != "0"
         dev = density.device
         kw = dict(kw)
-        if self.mode in ("p2p", "nvls"):
+        self.mc_fraction = float(os.environ.get("PP_XCHG_MC_FRACTION", "0.7"))
+        self.symm = self.mode in ("nvls", "hybrid")       # records in torch symmetric memory (multicast address)
+        if self.mode in ("p2p", "nvls", "hybrid"):
             # the fused exchange kernels have no total-variation stencil and exist for 1, 2, 4, 8 ranks
             if any(kw.get(k, 0.0) for k in ("tv_density", "tv_k0")):
                 if not auto:
@@ -155,7 +157,7 @@ class DistributedDVGO:
         n = density.numel()
         # two gradient buffers: while step k+1 marches into one, the other (already consumed by step k's
         # exchange) is zeroed on a side stream, off the critical path
-        if self.mode == "nvls":
+        if self.symm:
             ok = True
             try:
                 self.vox_mem = SymmRecords(n, dev, group, self.world)
@@ -169,20 +171,21 @@ class DistributedDVGO:
             dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
             if not int(flag):
                 if not auto:
-                    raise RuntimeError("DistributedDVGO(mode='nvls'): no multicast address "
-                                       "(NVSwitch/NVLS or torch symmetric memory not available)")
+                    raise RuntimeError("DistributedDVGO(mode=%r): no multicast address "
+                                       "(NVSwitch/NVLS or torch symmetric memory not available)" % self.mode)
                 self.mode = "p2p"       # auto mode: fall back to peer loads / stores over NVLink
+                self.symm = False
                 self.vox_mem = self.grad_mems = None
         if self.mode == "p2p":
             self.vox_mem = SharedRecords(n, dev)
             self.grad_mems = [SharedRecords(n, dev) for _ in range(2)]
-        if self.mode in ("p2p", "nvls"):
+        if self.mode in ("p2p", "nvls", "hybrid"):
             b, e = shard_bounds(n, self.world, self.rank)
             self.eng = dvgo.FusedDVGO(density, k0, xyz_min, xyz_max, stepsize, vox_buf=self.vox_mem.tensor,
                                       grad_buf=self.grad_mems[0].tensor, moment_records=max(e - b, 1), **kw)
             self.grad_mems[1].tensor.zero_()
             n_sync = int(lib.pp_peer_sync_bytes()) // 16
-            self.sync_mem = (SymmRecords(n_sync, dev, group, self.world, zero=True) if self.mode == "nvls"
+            self.sync_mem = (SymmRecords(n_sync, dev, group, self.world, zero=True) if self.symm
                              else SharedRecords(n_sync, dev, zero=True))
             torch.cuda.synchronize(dev)
             self.vox_ptrs = self.vox_mem.exchange(group, self.world, self.rank)
@@ -212,7 +215,7 @@ class DistributedDVGO:
     def _train_step(self, rays_o, rays_d, target, events):
         eng = self.eng
         eng.loss_buf.zero_()
-        if self.mode in ("p2p", "nvls"):
+        if self.mode in ("p2p", "nvls", "hybrid"):
             eng.grad = self.grad_mems[self.cur].tensor
             torch.cuda.current_stream().wait_event(self.zeroed[self.cur])     # no-op until first recorded
         if events is not None:
@@ -238,7 +241,7 @@ class DistributedDVGO:
             # barrier: every rank finished scattering; the local [loss, mse] rides along and comes back summed.
             # NVLS mode fuses it into the exchange kernel's prologue (one launch less on the critical path).
             self.epoch += 1
-            fused = self.mode == "nvls" and self.fused_sync
+            fused = self.symm and self.fused_sync
             if not fused:
                 check(lib.pp_peer_sync(self.sync_ptrs, self.world, self.rank, self.epoch, ptr(eng.loss_buf),
                                        ptr(self.loss_global), s), "peer_sync")
@@ -253,6 +256,16 @@ class DistributedDVGO:
                                                     ptr(eng.loss_buf) if fused else None,
                                                     ptr(self.loss_global) if fused else None, s),
                       "voxel_adam_exchange_mc")
+            elif self.mode == "hybrid":
+                check(lib.pp_voxel_adam_exchange_hybrid(self.vox_ptrs, self.grad_ptrs[self.cur],
+                                                        self.vox_mem.multicast_ptr,
+                                                        self.grad_mems[self.cur].multicast_ptr, ptr(eng.exp_avg),
+                                                        ptr(eng.exp_avg_sq), eng.n_voxels, self.world, self.rank,
+                                                        eng.step, b1, b2, lr_d, lr_k, eps, self.sync_ptrs,
+                                                        self.epoch if fused else 0,
+                                                        ptr(eng.loss_buf) if fused else None,
+                                                        ptr(self.loss_global) if fused else None, self.mc_fraction, s),
+                      "voxel_adam_exchange_hybrid")
             else:
                 check(lib.pp_voxel_adam_exchange(self.vox_ptrs, self.grad_ptrs[self.cur], ptr(eng.exp_avg),
                                                  ptr(eng.exp_avg_sq), eng.n_voxels, self.world, self.rank,
@@ -280,7 +293,7 @@ class DistributedDVGO:
     def check_health(self):
         """Raises if a cross-rank barrier of this rank ever timed out (a peer died or stalled for ~60 s): the exchange
         kernels stop updating from that point on and the reported loss is NaN.  Synchronises the device."""
-        if self.mode in ("p2p", "nvls"):
+        if self.mode in ("p2p", "nvls", "hybrid"):
             with torch.cuda.device(self.eng.device):
                 if lib.pp_peer_sync_timed_out(self.sync_ptrs[self.rank]) != 0:
                     raise RuntimeError("DistributedDVGO: a cross-rank barrier timed out on rank %d - a peer stalled "
@@ -294,7 +307,7 @@ class DistributedDVGO:
         return self.eng.export_grids()
 
     def close(self):
-        if self.mode == "nvls":
+        if self.symm:
             torch.cuda.synchronize(self.eng.device)
             dist.barrier(group=self.group)
         if self.mode == "p2p":

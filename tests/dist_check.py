@@ -34,7 +34,7 @@ def main():
         t = torch.rand(N, 3, generator=torch.Generator().manual_seed(200 + r))
         batches.append((o.to(dev), d.to(dev), t.to(dev)))
     results = {}
-    modes = ("nvls", "p2p", "nccl") if ppdist.nvls_available() else ("p2p", "nccl")
+    modes = ("nvls", "hybrid", "p2p", "nccl") if ppdist.nvls_available() else ("p2p", "nccl")
     for mode in modes:
         tr = ppdist.DistributedDVGO(density.to(dev), k0.to(dev), mn, mx, 0.5, mode=mode, bg=0.5)
         losses = []

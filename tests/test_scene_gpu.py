@@ -2,7 +2,7 @@
   * tests/golden/bgnerf_composite.npz = the reference's OWN NeRF.composite / Graph.sample_depth_from_pdf run on the CPU
     (frequency_nerf.py:283-343, renderer.py:703-738; tests/golden/make_golden_bgnerf.py), and
   * oracle/bgnerf_cpu.py (itself pinned to that golden) on fresh seeded inputs, incl. ragged N (not a multiple of 32),
-    N = 1, zero densities, empty batches.
+    N = 2 (the reference indexes T[:, :, -2]: N >= 2), zero densities, empty batches.
 Tolerance: 1e-5 relative on fp32 weights / rgb / gradients (the north star's bar), written at each assert."""
 import os
 import types
@@ -22,6 +22,12 @@ def cuda():
     return torch.device("cuda:0")
 
 
+# rgb_var = sum_n w_n sum_c (rgb_nc - rgb_c) is a cancellation: it is (1 - opacity) * sum_c rgb_c up to rounding, i.e. ~0 for
+# an opaque ray, and what is left is the fp32 summation noise of N terms of size w_n (a diagnostic image in the
+# reference, training/base.py:648) - compared absolutely at the size of that noise
+_ATOL = {"rgb_var": 2e-5}
+
+
 def _opt(opaque):
     return types.SimpleNamespace(nerf=types.SimpleNamespace(setbg_opaque=opaque), mask_img=False)
 
@@ -38,7 +44,8 @@ def test_composite_replays_the_references_golden(cuda, tag):
     pred = scene.composite(_opt(bool(g[tag + "_opaque"])), ray, {"rgb_samples": rgb_s, "density_samples": dens}, depth)
     for k in ("rgb", "rgb_var", "depth", "depth_var", "opacity", "weights", "all_cumulated"):
         assert pred[k].shape == t("out_" + k).shape, k
-        torch.testing.assert_close(pred[k].detach().cpu(), t("out_" + k), rtol=1e-5, atol=2e-6, msg=lambda m, k=k: k + m)
+        torch.testing.assert_close(pred[k].detach().cpu(), t("out_" + k), rtol=1e-5, atol=_ATOL.get(k, 2e-6),
+                                   msg=lambda m, k=k: k + m)
     loss = (pred["rgb"] * t("w_rgb").to(cuda)).sum() + (pred["depth"] * t("w_depth").to(cuda)).sum() + \
         (pred["opacity"] * t("w_opacity").to(cuda)).sum() + (pred["weights"] * t("w_weights").to(cuda)).sum()
     grads = torch.autograd.grad(loss, [rgb_s, dens, ray])
@@ -69,7 +76,7 @@ def test_sample_depth_from_pdf_replays_the_references_golden(cuda, tag):
         assert float(err.max()) < (rng[1] - rng[0]) / N
 
 
-@pytest.mark.parametrize("shape", [(1, 1, 1), (2, 5, 2), (1, 33, 31), (3, 70, 97), (1, 1000, 128), (2, 300, 256)])
+@pytest.mark.parametrize("shape", [(1, 1, 2), (2, 5, 3), (1, 33, 31), (3, 70, 97), (1, 1000, 128), (2, 300, 256)])
 @pytest.mark.parametrize("opaque", [False, True])
 def test_composite_vs_oracle_ragged(cuda, shape, opaque):
     from oracle import bgnerf_cpu
@@ -95,7 +102,7 @@ def test_composite_vs_oracle_ragged(cuda, shape, opaque):
     got, gg = run(lambda a, b, c, d: scene.composite(_opt(opaque), a, {"rgb_samples": b, "density_samples": c}, d), cuda,
                   torch.float32)
     for k in ("rgb", "rgb_var", "depth", "depth_var", "opacity", "weights", "all_cumulated"):
-        torch.testing.assert_close(got[k].detach().cpu().double(), want[k].detach(), rtol=1e-5, atol=2e-6,
+        torch.testing.assert_close(got[k].detach().cpu().double(), want[k].detach(), rtol=1e-5, atol=_ATOL.get(k, 2e-6),
                                    msg=lambda m, k=k: k + m)
     for a, b, k in zip(gg, gw, ("rgb_samples", "density_samples", "ray")):
         rel = float((a.cpu().double() - b).norm() / (b.norm() + 1e-30))
