@@ -184,6 +184,17 @@ PP_API int pp_cumdist_thres(pp_dtype dtype, const void* dist, float thres, int64
 PP_API int pp_segment_sum(const float* src, const float* weight, const int64_t* ray_id, int64_t n_pts,
                    int32_t n_ch, int64_t n_rays, float* out, pp_stream_t stream);
 
+/* Dense compositing of the reference's pure-PyTorch DirectVoxGO: get_ray_marching_ray / cumprod_exclusive
+ * (lib/dvgo_ori.py:478-485).  alpha [n_rays, S] (dense samples, 0 outside the box) ->
+ * alphainv_cum [n_rays, S+1] = [1, cumprod(clamp_min(1 - alpha, 1e-10))], weights [n_rays, S] = alpha *
+ * alphainv_cum[:, :-1].  No early termination.  Backward: d loss / d alpha from d loss / d weights and
+ * d loss / d alphainv_cum (each nullable = zero), torch.cumprod's rule (sum_{i>j} G_i C_i) / p_j. */
+PP_API int pp_dense_composite_forward(const float* alpha, int64_t n_rays, int32_t n_samples, float* weights,
+                                      float* alphainv_cum, pp_stream_t stream);
+PP_API int pp_dense_composite_backward(const float* alpha, const float* alphainv_cum, int64_t n_rays,
+                                       int32_t n_samples, const float* grad_weights,
+                                       const float* grad_alphainv_cum, float* grad_alpha, pp_stream_t stream);
+
 /* Inclusive prefix sum of src within each ray segment (the north star's `segment_cumsum`, which
  * the reference names but does not ship; defined in SURVEY.md section 8 a12). fp32 only.
  * `scratch` is pp_segment_cumsum_scratch_bytes(n_pts) bytes of device memory. */

@@ -47,67 +47,121 @@ constexpr int kGroups = kWarp / kTile;        // rays loaded / stored per instru
 // row reads of lanes r and r+4 fall into different banks
 __device__ __forceinline__ int tile_at(int r, int c) { return r * kTile + (c ^ (((r >> 2) & 1) << 2)); }
 
+// Two warps per 32 rays.  Warp 0 ("chain") only runs the recurrence: per step it reads its ray's row of the input
+// tile, advances 8 samples, writes its T / weight rows - ~100 instructions, and a lone warp issues one dependent
+// instruction every ~5 cycles, so instructions on this warp ARE the kernel's duration.  Warp 1 ("memory") does all
+// the addressing: it knows every ray's [begin, end) (8 rays per lane, loaded once), loads tile i+2 from global memory
+// into registers (two steps ahead, so DRAM latency is covered), stages tile i+1 into shared memory and streams the
+// outputs of tile i-1 back as 32-byte sectors.  Tiles rotate through three shared-memory slots; one block barrier
+// per step orders the two warps.
 template <typename scalar_t>
-__global__ void __launch_bounds__(kWarp)
+__global__ void __launch_bounds__(2 * kWarp)
 alpha2weight_fwd_kernel(const scalar_t* __restrict__ alpha, int64_t n_rays,
                         scalar_t* __restrict__ weight, scalar_t* __restrict__ T_out,
                         scalar_t* __restrict__ alphainv_last, const int64_t* __restrict__ i_start,
                         int64_t* __restrict__ i_end) {
-  __shared__ scalar_t s_a[kWarp * kTile], s_T[kWarp * kTile], s_w[kWarp * kTile];
-  const int lane = threadIdx.x, sub = lane / kTile, sl = lane % kTile;
-  const int64_t ray = blockIdx.x * (int64_t)kWarp + lane;
-  const bool live = ray < n_rays;
+  __shared__ scalar_t s_a[3][kWarp * kTile], s_T[3][kWarp * kTile], s_w[3][kWarp * kTile];
+  __shared__ int s_steps;
+  const int lane = threadIdx.x & 31, sub = lane / kTile, sl = lane % kTile;
+  const bool chain = threadIdx.x < kWarp;
+  const int64_t ray0 = blockIdx.x * (int64_t)kWarp;
+  // chain warp: own ray.  (sample indices fit 32 bits: the entry point rejects n_pts > INT32_MAX)
+  const int64_t ray = ray0 + lane;
+  const bool live = chain && ray < n_rays;
   const int begin = live ? static_cast<int>(i_start[ray]) : 0, end = live ? static_cast<int>(i_end[ray]) : 0;
-  int pos = begin;      // (sample indices fit 32 bits: the entry point rejects n_pts > INT32_MAX)
-  int cut = -1;       // early-termination index (exclusive end), -1 while the ray is still marching
-  float T_cum = 1.f;
-  // tile loads: instruction k of a step serves rays 4k + sub
-  scalar_t nxt[kTile];
-  auto issue_loads = [&](int p_mine) {
+  // memory warp: instruction k of a step serves ray 4k + sub
+  int bk[kTile], ek[kTile];
+#pragma unroll
+  for (int k = 0; k < kTile; ++k) {
+    const int64_t r = ray0 + k * kGroups + sub;
+    const bool ok = !chain && r < n_rays;
+    bk[k] = ok ? static_cast<int>(i_start[r]) : 0;
+    ek[k] = ok ? static_cast<int>(i_end[r]) : 0;
+  }
+  if (chain) {
+    int steps = (end - begin + kTile - 1) / kTile;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) steps = max(steps, __shfl_xor_sync(kFull, steps, o));
+    if (lane == 0) s_steps = steps;
+  }
+  __syncthreads();
+  const int steps = s_steps;
+  scalar_t ld[2][kTile];        // memory warp: tiles in flight (tile t lives in ld[t & 1])
+  auto issue_loads = [&](int t, scalar_t (&dst)[kTile]) {
 #pragma unroll
     for (int k = 0; k < kTile; ++k) {
-      const int r = k * kGroups + sub;
-      const int p = __shfl_sync(kFull, p_mine, r), e = __shfl_sync(kFull, end, r);
-      nxt[k] = (p + sl < e) ? alpha[p + sl] : scalar_t(0);
+      const int idx = bk[k] + t * kTile + sl;
+      dst[k] = (t < steps && idx < ek[k]) ? alpha[idx] : scalar_t(0);
     }
   };
-  issue_loads(pos);
-  while (__any_sync(kFull, pos < end)) {
+  auto stage = [&](int t, const scalar_t (&src)[kTile]) {
 #pragma unroll
-    for (int k = 0; k < kTile; ++k) s_a[tile_at(k * kGroups + sub, sl)] = nxt[k];
-    __syncwarp();
-    scalar_t a[kTile];
+    for (int k = 0; k < kTile; ++k) s_a[t % 3][tile_at(k * kGroups + sub, sl)] = src[k];
+  };
+  if (!chain) {
+    issue_loads(0, ld[0]);
+    issue_loads(1, ld[1]);
+    stage(0, ld[0]);
+  }
+  __syncthreads();
+  int pos = begin, cut = -1;
+  float T_cum = 1.f;
+  for (int t = 0; t < steps; ++t) {
+    if (chain) {
+      const scalar_t* a_row = s_a[t % 3];
+      scalar_t a[kTile];
 #pragma unroll
-    for (int j = 0; j < kTile; ++j) a[j] = s_a[tile_at(lane, j)];
-    issue_loads(pos + kTile);                     // next tile: in flight during the chain
-    scalar_t Tj[kTile], wj[kTile];
+      for (int j = 0; j < kTile; ++j) a[j] = a_row[tile_at(lane, j)];
+      scalar_t Tj[kTile], wj[kTile];
 #pragma unroll
-    for (int j = 0; j < kTile; ++j) {
-      const bool in = cut < 0 && pos + j < end;
-      Tj[j] = in ? static_cast<scalar_t>(T_cum) : scalar_t(1);
-      wj[j] = in ? T_cum * a[j] : scalar_t(0);
-      if (in) {
-        T_cum = static_cast<float>(static_cast<double>(T_cum) * (1. - static_cast<double>(a[j])));
-        if (T_cum < 1e-3) cut = pos + j + 1;      // float widened, compared with the double literal (reference :597)
+      for (int j = 0; j < kTile; ++j) {
+        const bool in = cut < 0 && pos + j < end;
+        Tj[j] = in ? static_cast<scalar_t>(T_cum) : scalar_t(1);
+        wj[j] = in ? T_cum * a[j] : scalar_t(0);
+        if (in) {
+          T_cum = static_cast<float>(static_cast<double>(T_cum) * (1. - static_cast<double>(a[j])));
+          // reference :597 compares the widened float with the double literal 1e-3; 0.001f is the smallest float
+          // above it, so for a float operand `< 1e-3` and `< 0.001f` are the same predicate
+          if (T_cum < 0.001f) cut = pos + j + 1;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kTile; ++j) {
+        s_T[t % 3][tile_at(lane, j)] = Tj[j];
+        s_w[t % 3][tile_at(lane, j)] = wj[j];
+      }
+      pos += kTile;
+    } else {
+      // tile t+1 -> shared memory (its loads were issued one step ago), tile t+2 -> registers, tile t-1 -> global
+      if (((t + 1) & 1) == 0) {
+        stage(t + 1, ld[0]);
+        issue_loads(t + 2, ld[0]);
+      } else {
+        stage(t + 1, ld[1]);
+        issue_loads(t + 2, ld[1]);
+      }
+      if (t > 0) {
+#pragma unroll
+        for (int k = 0; k < kTile; ++k) {
+          const int idx = bk[k] + (t - 1) * kTile + sl;
+          if (idx < ek[k]) {
+            T_out[idx] = s_T[(t - 1) % 3][tile_at(k * kGroups + sub, sl)];
+            weight[idx] = s_w[(t - 1) % 3][tile_at(k * kGroups + sub, sl)];
+          }
+        }
       }
     }
-#pragma unroll
-    for (int j = 0; j < kTile; ++j) {
-      s_T[tile_at(lane, j)] = Tj[j];
-      s_w[tile_at(lane, j)] = wj[j];
-    }
-    __syncwarp();
+    __syncthreads();
+  }
+  if (!chain && steps > 0) {
 #pragma unroll
     for (int k = 0; k < kTile; ++k) {
-      const int r = k * kGroups + sub;
-      const int p = __shfl_sync(kFull, pos, r), e = __shfl_sync(kFull, end, r);
-      if (p + sl < e) {
-        T_out[p + sl] = s_T[tile_at(r, sl)];
-        weight[p + sl] = s_w[tile_at(r, sl)];
+      const int idx = bk[k] + (steps - 1) * kTile + sl;
+      if (idx < ek[k]) {
+        T_out[idx] = s_T[(steps - 1) % 3][tile_at(k * kGroups + sub, sl)];
+        weight[idx] = s_w[(steps - 1) % 3][tile_at(k * kGroups + sub, sl)];
       }
     }
-    __syncwarp();
-    if (pos < end) pos += kTile;
   }
   if (live) {
     if (cut >= 0) i_end[ray] = cut;  // otherwise i_end already holds i_e_max (or 0 for an empty ray)
@@ -116,78 +170,202 @@ alpha2weight_fwd_kernel(const scalar_t* __restrict__ alpha, int64_t n_rays,
 }
 
 // ---- backward ------------------------------------------------------------------------------------
-// Same shape, walking each ray downwards from its (early-terminated) end in tiles [top - 8, top).
-// back_cum += grad_weights*weight is an FMA in scalar_t narrowed to float (reference :674); the double division and
-// the difference are not part of the recurrence but are done by the ray's own lane as well (8 per step).
+// Walks each ray downwards from its (early-terminated) end in tiles [top - 8, top).  The recurrence
+// back_cum += grad_weights*weight is an FMA in scalar_t narrowed to float (reference :674) - 8 dependent FMAs per
+// step on the chain warp, which hands the value of back_cum in front of every sample to the memory warps through
+// shared memory.  Everything else - the loads of the four inputs, and grad = gw*T - back/(1-alpha+1e-10) with its
+// double-precision quotient, which is not part of the recurrence - is done by kBwdMemWarps memory warps in the
+// coalesced layout (each owns 8 / kBwdMemWarps of the step's 8 sector instructions).
+constexpr int kBwdMemWarps = 4;
+constexpr int kBwdK = kTile / kBwdMemWarps;   // sector instructions per memory warp and step
+
 template <typename scalar_t>
-__global__ void __launch_bounds__(kWarp)
+__global__ void __launch_bounds__((1 + kBwdMemWarps) * kWarp)
 alpha2weight_bwd_kernel(const scalar_t* __restrict__ alpha, const scalar_t* __restrict__ weight,
                         const scalar_t* __restrict__ T, const scalar_t* __restrict__ alphainv_last,
                         const int64_t* __restrict__ i_start, const int64_t* __restrict__ i_end,
                         int64_t n_rays, const scalar_t* __restrict__ grad_weights,
                         const scalar_t* __restrict__ grad_last, scalar_t* __restrict__ grad) {
-  __shared__ scalar_t s_in[4][kWarp * kTile], s_out[kWarp * kTile];
-  const int lane = threadIdx.x, sub = lane / kTile, sl = lane % kTile;
-  const int64_t ray = blockIdx.x * (int64_t)kWarp + lane;
-  const bool live = ray < n_rays;
+  __shared__ scalar_t s_in[3][4][kWarp * kTile];   // [slot][gw, w, T, alpha]
+  __shared__ float s_back[3][kWarp * kTile];       // back_cum in front of every sample
+  __shared__ int s_steps;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane / kTile, sl = lane % kTile;
+  const bool chain = warp == 0;
+  const int64_t ray0 = blockIdx.x * (int64_t)kWarp;
+  const int64_t ray = ray0 + lane;
+  const bool live = chain && ray < n_rays;
   const int begin = live ? static_cast<int>(i_start[ray]) : 0;
-  int top = live ? static_cast<int>(i_end[ray]) : 0;
+  const int top0 = live ? static_cast<int>(i_end[ray]) : 0;
   // back_cum = grad_last * alphainv_last (reference :671)
   float back = live ? static_cast<float>(grad_last[ray] * alphainv_last[ray]) : 0.f;
+  // memory warp w serves the sector instructions k = (w - 1) * kBwdK + q of a step: ray 4k + sub
+  int bk[kBwdK], tk[kBwdK], rk[kBwdK];
+#pragma unroll
+  for (int q = 0; q < kBwdK; ++q) {
+    rk[q] = ((warp - 1) * kBwdK + q) * kGroups + sub;
+    const int64_t r = ray0 + rk[q];
+    const bool ok = !chain && r < n_rays;
+    bk[q] = ok ? static_cast<int>(i_start[r]) : 0;
+    tk[q] = ok ? static_cast<int>(i_end[r]) : 0;
+  }
+  if (chain) {
+    int steps = (max(top0 - begin, 0) + kTile - 1) / kTile;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) steps = max(steps, __shfl_xor_sync(kFull, steps, o));
+    if (lane == 0) s_steps = steps;
+  }
+  __syncthreads();
+  const int steps = s_steps;
   const scalar_t* src[4] = {grad_weights, weight, T, alpha};
-  scalar_t nxt[4][kTile];
-  auto issue_loads = [&](int top_mine) {
+  // tile t of a ray covers samples [top - 8 (t + 1), top - 8 t); column c of the tile is sample top - 8 (t + 1) + c
+  scalar_t ld[2][4][kBwdK];
+  auto issue_loads = [&](int t, scalar_t (&dst)[4][kBwdK]) {
 #pragma unroll
-    for (int k = 0; k < kTile; ++k) {
-      const int r = k * kGroups + sub;
-      const int t = __shfl_sync(kFull, top_mine, r), b = __shfl_sync(kFull, begin, r);
-      const int idx = t - kTile + sl;
-      const bool ok = idx >= b && idx < t;
+    for (int q = 0; q < kBwdK; ++q) {
+      const int idx = tk[q] - (t + 1) * kTile + sl;
+      const bool ok = t < steps && idx >= bk[q];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) nxt[q][k] = ok ? src[q][idx] : scalar_t(0);
+      for (int f = 0; f < 4; ++f) dst[f][q] = ok ? src[f][idx] : scalar_t(0);
     }
   };
-  issue_loads(top);
-  while (__any_sync(kFull, top > begin)) {
+  auto stage = [&](int t, const scalar_t (&v)[4][kBwdK]) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
+    for (int f = 0; f < 4; ++f)
 #pragma unroll
-      for (int k = 0; k < kTile; ++k) s_in[q][tile_at(k * kGroups + sub, sl)] = nxt[q][k];
-    __syncwarp();
-    scalar_t gw[kTile], wv[kTile], Tv[kTile], av[kTile];
+      for (int q = 0; q < kBwdK; ++q) s_in[t % 3][f][tile_at(rk[q], sl)] = v[f][q];
+  };
+  auto finish = [&](int t) {     // grad of tile t from the staged inputs and the chain warp's back_cum values
 #pragma unroll
-    for (int j = 0; j < kTile; ++j) {
-      gw[j] = s_in[0][tile_at(lane, j)];
-      wv[j] = s_in[1][tile_at(lane, j)];
-      Tv[j] = s_in[2][tile_at(lane, j)];
-      av[j] = s_in[3][tile_at(lane, j)];
-    }
-    issue_loads(top - kTile);
-    const int base = top - kTile;           // column j of the tile is sample base + j
-#pragma unroll
-    for (int j = kTile - 1; j >= 0; --j) {
-      const bool valid = base + j >= begin && base + j < top;
-      scalar_t g = scalar_t(0);
-      if (valid) {
+    for (int q = 0; q < kBwdK; ++q) {
+      const int idx = tk[q] - (t + 1) * kTile + sl;
+      if (idx >= bk[q]) {
+        const int at = tile_at(rk[q], sl);
+        const scalar_t gw = s_in[t % 3][0][at], Tv = s_in[t % 3][2][at], av = s_in[t % 3][3][at];
         // grad = gw*T - back/(1-alpha+1e-10): product in scalar_t, quotient and difference in double
-        const scalar_t gT = mul_rn(gw[j], Tv[j]);
-        const scalar_t one_minus = scalar_t(1) - av[j];
-        const double qd = static_cast<double>(back) / (static_cast<double>(one_minus) + 1e-10);
-        g = static_cast<scalar_t>(static_cast<double>(gT) - qd);
-        back = static_cast<float>(fma_rn(gw[j], wv[j], static_cast<scalar_t>(back)));
+        const scalar_t gT = mul_rn(gw, Tv);
+        const scalar_t one_minus = scalar_t(1) - av;
+        const double qd = static_cast<double>(s_back[t % 3][at]) / (static_cast<double>(one_minus) + 1e-10);
+        grad[idx] = static_cast<scalar_t>(static_cast<double>(gT) - qd);
       }
-      s_out[tile_at(lane, j)] = g;
     }
-    __syncwarp();
+  };
+  if (!chain) {
+    issue_loads(0, ld[0]);
+    issue_loads(1, ld[1]);
+    stage(0, ld[0]);
+  }
+  __syncthreads();
+  int top = top0;
+  for (int t = 0; t < steps; ++t) {
+    if (chain) {
+      scalar_t gw[kTile], wv[kTile];
 #pragma unroll
-    for (int k = 0; k < kTile; ++k) {
-      const int r = k * kGroups + sub;
-      const int t = __shfl_sync(kFull, top, r), b = __shfl_sync(kFull, begin, r);
-      const int idx = t - kTile + sl;
-      if (idx >= b && idx < t) grad[idx] = s_out[tile_at(r, sl)];
+      for (int j = 0; j < kTile; ++j) {
+        gw[j] = s_in[t % 3][0][tile_at(lane, j)];
+        wv[j] = s_in[t % 3][1][tile_at(lane, j)];
+      }
+      const int base = top - kTile;
+      float bj[kTile];
+#pragma unroll
+      for (int j = kTile - 1; j >= 0; --j) {
+        bj[j] = back;
+        if (base + j >= begin && base + j < top)
+          back = static_cast<float>(fma_rn(gw[j], wv[j], static_cast<scalar_t>(back)));
+      }
+#pragma unroll
+      for (int j = 0; j < kTile; ++j) s_back[t % 3][tile_at(lane, j)] = bj[j];
+      if (top > begin) top -= kTile;
+    } else {
+      if (((t + 1) & 1) == 0) {
+        stage(t + 1, ld[0]);
+        issue_loads(t + 2, ld[0]);
+      } else {
+        stage(t + 1, ld[1]);
+        issue_loads(t + 2, ld[1]);
+      }
+      if (t > 0) finish(t - 1);
     }
-    __syncwarp();
-    if (top > begin) top -= kTile;
+    __syncthreads();
+  }
+  if (!chain && steps > 0) finish(steps - 1);
+}
+
+// ---- dense compositing: get_ray_marching_ray / cumprod_exclusive (lib/dvgo_ori.py:478-485) -------------------
+//   alphainv_cum = [1, cumprod(clamp_min(1 - alpha, 1e-10))]  [n, S+1],   weights = alpha * alphainv_cum[..., :-1]
+// over DENSE [n_rays, S] samples (out-of-box samples carry alpha = 0), with no early termination - the formulation of
+// the reference's pure-PyTorch DirectVoxGO.  One warp per ray, lanes = 32 consecutive samples: a shuffle product scan
+// per chunk, the running product carried across chunks; the backward is autograd's cumprod rule
+// d/dp_j = (sum_{i>j} G_i C_i) / p_j as a reverse pass with a suffix sum.
+constexpr int kDenseWarps = 8;
+
+__global__ void __launch_bounds__(kDenseWarps* kWarp)
+dense_composite_fwd_kernel(const float* __restrict__ alpha, int64_t n_rays, int S, float* __restrict__ weights,
+                           float* __restrict__ cum) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = blockIdx.x * (int64_t)kDenseWarps + (threadIdx.x >> 5);
+  if (r >= n_rays) return;
+  const float* a_r = alpha + r * S;
+  float* w_r = weights + r * S;
+  float* c_r = cum + r * (int64_t)(S + 1);
+  float carry = 1.f;
+  if (lane == 0) c_r[0] = 1.f;
+  for (int base = 0; base < S; base += 32) {
+    const int i = base + lane;
+    const float a = i < S ? a_r[i] : 0.f;
+    float incl = i < S ? fmaxf(1.f - a, 1e-10f) : 1.f;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float up = __shfl_up_sync(kFull, incl, o);
+      if (lane >= o) incl *= up;
+    }
+    float excl = __shfl_up_sync(kFull, incl, 1);
+    if (lane == 0) excl = 1.f;
+    if (i < S) {
+      w_r[i] = a * (carry * excl);
+      c_r[i + 1] = carry * incl;
+    }
+    carry *= __shfl_sync(kFull, incl, 31);
+  }
+}
+
+__global__ void __launch_bounds__(kDenseWarps* kWarp)
+dense_composite_bwd_kernel(const float* __restrict__ alpha, const float* __restrict__ cum, int64_t n_rays, int S,
+                           const float* __restrict__ g_w, const float* __restrict__ g_cum,
+                           float* __restrict__ g_alpha) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = blockIdx.x * (int64_t)kDenseWarps + (threadIdx.x >> 5);
+  if (r >= n_rays) return;
+  const float* a_r = alpha + r * S;
+  const float* c_r = cum + r * (int64_t)(S + 1);
+  const float* gw_r = g_w ? g_w + r * S : nullptr;
+  const float* gc_r = g_cum ? g_cum + r * (int64_t)(S + 1) : nullptr;
+  float* ga_r = g_alpha + r * S;
+  // suffix = sum_{i > j} G_i C_i with G_i = g_cum[i] + g_w[i] alpha_i (i < S); starts with the entry i = S
+  float suffix = gc_r ? gc_r[S] * c_r[S] : 0.f;
+  const int last_base = ((S - 1) / 32) * 32;
+  for (int base = last_base; base >= 0; base -= 32) {
+    const int j = base + lane;
+    const bool in = j < S;
+    const float a = in ? a_r[j] : 0.f;
+    const float C = in ? c_r[j] : 0.f;
+    const float gw = (in && gw_r) ? gw_r[j] : 0.f;
+    const float term = in ? ((gc_r ? gc_r[j] : 0.f) + gw * a) * C : 0.f;   // G_j C_j
+    float sfx = term;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const float dn = __shfl_down_sync(kFull, sfx, o);
+      if (lane + o < 32) sfx += dn;
+    }
+    float right = __shfl_down_sync(kFull, sfx, 1);
+    if (lane == 31) right = 0.f;
+    const float after = suffix + right;              // sum over i > j
+    suffix += __shfl_sync(kFull, sfx, 0);
+    if (in) {
+      const float q = 1.f - a;
+      const float p = fmaxf(q, 1e-10f);
+      const float dp = (q >= 1e-10f) ? -(after / p) : 0.f;   // clamp_min passes the gradient where it does not clamp
+      ga_r[j] = gw * C + dp;
+    }
   }
 }
 
@@ -398,7 +576,7 @@ extern "C" int pp_alpha2weight(pp_dtype dtype, const void* alpha, const int64_t*
   segment_bounds_kernel<<<ceil_div(n_pts, 256), 256, 0, s>>>(ray_id, n_pts, n_rays, i_start, i_end);
   PP_CHECK_LAUNCH("alpha2weight(bounds)");
   PP_DISPATCH(dtype, {
-    alpha2weight_fwd_kernel<scalar_t><<<ceil_div(n_rays, kWarp), kWarp, 0, s>>>(
+    alpha2weight_fwd_kernel<scalar_t><<<ceil_div(n_rays, kWarp), 2 * kWarp, 0, s>>>(
         (const scalar_t*)alpha, n_rays, (scalar_t*)weight, (scalar_t*)T, (scalar_t*)alphainv_last,
         i_start, i_end);
   });
@@ -423,12 +601,36 @@ extern "C" int pp_alpha2weight_backward(pp_dtype dtype, const void* alpha, const
   PP_REQUIRE(alpha && weight && T && alphainv_last && i_start && i_end && grad_weights && grad_last,
              PP_ERR_INVALID_ARG, "alpha2weight_backward: null pointer");
   PP_DISPATCH(dtype, {
-    alpha2weight_bwd_kernel<scalar_t><<<ceil_div(n_rays, kWarp), kWarp, 0, s>>>(
+    alpha2weight_bwd_kernel<scalar_t><<<ceil_div(n_rays, kWarp), (1 + kBwdMemWarps) * kWarp, 0, s>>>(
         (const scalar_t*)alpha, (const scalar_t*)weight, (const scalar_t*)T,
         (const scalar_t*)alphainv_last, i_start, i_end, n_rays, (const scalar_t*)grad_weights,
         (const scalar_t*)grad_last, (scalar_t*)grad);
   });
   PP_CHECK_LAUNCH("alpha2weight_backward");
+  return PP_OK;
+}
+
+extern "C" int pp_dense_composite_forward(const float* alpha, int64_t n_rays, int32_t n_samples, float* weights,
+                                          float* alphainv_cum, pp_stream_t stream) {
+  PP_REQUIRE(n_rays >= 0 && n_samples >= 0, PP_ERR_INVALID_ARG, "dense_composite_forward: negative extent");
+  if (n_rays == 0) return PP_OK;
+  PP_REQUIRE(alphainv_cum && (n_samples == 0 || (alpha && weights)), PP_ERR_INVALID_ARG,
+             "dense_composite_forward: null pointer");
+  dense_composite_fwd_kernel<<<ceil_div(n_rays, kDenseWarps), kDenseWarps * kWarp, 0, as_stream(stream)>>>(
+      alpha, n_rays, n_samples, weights, alphainv_cum);
+  PP_CHECK_LAUNCH("dense_composite_forward");
+  return PP_OK;
+}
+
+extern "C" int pp_dense_composite_backward(const float* alpha, const float* alphainv_cum, int64_t n_rays,
+                                           int32_t n_samples, const float* grad_weights,
+                                           const float* grad_alphainv_cum, float* grad_alpha, pp_stream_t stream) {
+  PP_REQUIRE(n_rays >= 0 && n_samples >= 0, PP_ERR_INVALID_ARG, "dense_composite_backward: negative extent");
+  if (n_rays == 0 || n_samples == 0) return PP_OK;
+  PP_REQUIRE(alpha && alphainv_cum && grad_alpha, PP_ERR_INVALID_ARG, "dense_composite_backward: null pointer");
+  dense_composite_bwd_kernel<<<ceil_div(n_rays, kDenseWarps), kDenseWarps * kWarp, 0, as_stream(stream)>>>(
+      alpha, alphainv_cum, n_rays, n_samples, grad_weights, grad_alphainv_cum, grad_alpha);
+  PP_CHECK_LAUNCH("dense_composite_backward");
   return PP_OK;
 }
 

@@ -12,8 +12,10 @@ Mirrors the coarse-stage ``DirectVoxGO`` of the reference (lib/dvgo_ori.py:14-43
 import ctypes
 import math
 
+import numpy as np
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from ._lib import check, lib, ptr, stream
 
@@ -142,30 +144,121 @@ class _RenderFn(torch.autograd.Function):
         return g_density, g_k0, g_o, g_d, None
 
 
-class DirectVoxGO(nn.Module):
-    """Coarse-stage DirectVoxGO (lib/dvgo_ori.py:14-131) on the fused kernels.
+class MaskCache(nn.Module):
+    """`MaskCache` of the reference (lib/dvgo_ori.py:436-475): the coarse stage's max-pooled density as a free-space
+    oracle; built from a checkpoint path as in the reference, or directly from tensors (`from_state`)."""
 
-    Supported configuration: ``rgbnet_dim=0`` (colour voxel grid), post-activation density,
-    no mask cache -- the configuration BASELINE.json's config B names.
-    """
-
-    def __init__(self, xyz_min, xyz_max, num_voxels=0, num_voxels_base=0, alpha_init=None,
-                 fast_color_thres=0, rgbnet_dim=0, **kwargs):
+    def __init__(self, path=None, mask_cache_thres=1e-3, ks=3, state=None):
         super().__init__()
-        if rgbnet_dim > 0:
-            raise NotImplementedError("rgbnet (fine stage) is served by the op-level API, not the fused module")
+        st = torch.load(path) if state is None else state
+        self.mask_cache_thres = mask_cache_thres
+        kw = st['MaskCache_kwargs']
+        self.register_buffer('xyz_min', torch.FloatTensor(kw['xyz_min']))
+        self.register_buffer('xyz_max', torch.FloatTensor(kw['xyz_max']))
+        self.register_buffer('density', F.max_pool3d(st['model_state_dict']['density'], kernel_size=ks,
+                                                     padding=ks // 2, stride=1))
+        self.act_shift = kw['act_shift']
+        self.voxel_size_ratio = kw['voxel_size_ratio']
+        self.nearest = kw.get('nearest', False)
+        self.pre_act_density = kw.get('pre_act_density', False)
+        self.in_act_density = kw.get('in_act_density', False)
+        if self.nearest or self.pre_act_density:
+            raise NotImplementedError("MaskCache: nearest / pre_act_density lookups are not served (INTEGRATION.md)")
+
+    @torch.no_grad()
+    def forward(self, xyz):
+        from . import ops
+        shape = xyz.shape[:-1]
+        grid = F.softplus(self.density + self.act_shift) if self.in_act_density else self.density
+        d = ops.trilinear(grid, xyz.reshape(-1, 3), self.xyz_min, self.xyz_max)[:, 0]
+        if self.in_act_density:
+            alpha = 1 - torch.exp(-d * self.voxel_size_ratio)
+        else:
+            alpha = 1 - torch.exp(-F.softplus(d + self.act_shift) * self.voxel_size_ratio)
+        return (alpha >= self.mask_cache_thres).reshape(shape)
+
+
+class DirectVoxGO(nn.Module):
+    """`DirectVoxGO` of the reference (lib/dvgo_ori.py:14-435): same constructor arguments, parameter names
+    (`density`, `k0`, `rgbnet.*`; checkpoints interchange) and `forward(rays_o, rays_d, viewdirs, global_step,
+    **render_kwargs)` returning the reference's NINE result entries with the reference's semantics - dense [N, S]
+    sampling, no early termination, sigmoid(0) colour under `fast_color_thres`, depth along |o - p| plus the
+    `alphainv_last * far` term, jitter under training.  The gathers (pp_trilinear_*), the activation (pp_raw2alpha) and
+    the compositing (pp_dense_composite_*) are this library's kernels; the per-ray elementwise glue is torch.
+
+    `forward_fused` is the B200-first path for the coarse configuration (`rgbnet_dim=0`, post-activation density, no
+    mask cache): ONE kernel forward, ONE backward, compacted samples with the reference CUDA sampler's early
+    termination (what `FusedDVGO` trains with); it returns the per-ray entries only.
+
+    Not served (raise NotImplementedError): `nearest=True`, `rgbnet_full_implicit=True`."""
+
+    def __init__(self, xyz_min, xyz_max, num_voxels=0, num_voxels_base=0, alpha_init=None, nearest=False,
+                 pre_act_density=False, in_act_density=False, mask_cache_path=None, mask_cache_thres=1e-3,
+                 fast_color_thres=0, rgbnet_dim=0, rgbnet_direct=False, rgbnet_full_implicit=False, rgbnet_depth=3,
+                 rgbnet_width=128, posbase_pe=5, viewbase_pe=4, **kwargs):
+        super().__init__()
+        if nearest or rgbnet_full_implicit:
+            raise NotImplementedError("DirectVoxGO: nearest / rgbnet_full_implicit are not served (INTEGRATION.md)")
         self.register_buffer('xyz_min', torch.Tensor(xyz_min))
         self.register_buffer('xyz_max', torch.Tensor(xyz_max))
         self.fast_color_thres = fast_color_thres
+        self.nearest = nearest
+        self.pre_act_density = pre_act_density
+        self.in_act_density = in_act_density
         self.num_voxels_base = num_voxels_base
         self.voxel_size_base = ((self.xyz_max - self.xyz_min).prod() / self.num_voxels_base).pow(1 / 3)
         self.alpha_init = alpha_init
         self.act_shift = math.log(1 / (1 - alpha_init) - 1)
         self._set_grid_resolution(num_voxels)
         self.density = nn.Parameter(torch.zeros([1, 1, *self.world_size]))
-        self.k0_dim = 3
-        self.k0 = nn.Parameter(torch.zeros([1, self.k0_dim, *self.world_size]))
-        self.rgbnet = None
+        self.rgbnet_kwargs = {'rgbnet_dim': rgbnet_dim, 'rgbnet_direct': rgbnet_direct,
+                              'rgbnet_full_implicit': rgbnet_full_implicit, 'rgbnet_depth': rgbnet_depth,
+                              'rgbnet_width': rgbnet_width, 'posbase_pe': posbase_pe, 'viewbase_pe': viewbase_pe}
+        self.rgbnet_full_implicit = rgbnet_full_implicit
+        if rgbnet_dim <= 0:
+            self.k0_dim = 3
+            self.k0 = nn.Parameter(torch.zeros([1, self.k0_dim, *self.world_size]))
+            self.rgbnet = None
+        else:
+            # feature voxel grid + shallow MLP (lib/dvgo_ori.py:62-90)
+            self.k0_dim = rgbnet_dim
+            self.k0 = nn.Parameter(torch.zeros([1, self.k0_dim, *self.world_size]))
+            self.rgbnet_direct = rgbnet_direct
+            self.register_buffer('posfreq', torch.FloatTensor([(2 ** i) for i in range(posbase_pe)]))
+            self.register_buffer('viewfreq', torch.FloatTensor([(2 ** i) for i in range(viewbase_pe)]))
+            dim0 = (3 + 3 * posbase_pe * 2) + (3 + 3 * viewbase_pe * 2)
+            dim0 += self.k0_dim if rgbnet_direct else self.k0_dim - 3
+            self.rgbnet = nn.Sequential(
+                nn.Linear(dim0, rgbnet_width), nn.ReLU(inplace=True),
+                *[nn.Sequential(nn.Linear(rgbnet_width, rgbnet_width), nn.ReLU(inplace=True))
+                  for _ in range(rgbnet_depth - 2)],
+                nn.Linear(rgbnet_width, 3))
+            nn.init.constant_(self.rgbnet[-1].bias, 0)
+        self.mask_cache_path = mask_cache_path
+        self.mask_cache_thres = mask_cache_thres
+        self.mask_cache = None
+        self.nonempty_mask = None
+        if mask_cache_path is not None and mask_cache_path:
+            self.set_mask_cache(MaskCache(path=mask_cache_path, mask_cache_thres=mask_cache_thres))
+
+    def set_mask_cache(self, mask_cache):
+        """attach a MaskCache (the reference builds it from `mask_cache_path` in the constructor)"""
+        self.mask_cache = mask_cache.to(self.xyz_min.device)
+        self._set_nonempty_mask()
+
+    def _grid_xyz(self):
+        return torch.stack(torch.meshgrid(
+            torch.linspace(float(self.xyz_min[0]), float(self.xyz_max[0]), self.density.shape[2]),
+            torch.linspace(float(self.xyz_min[1]), float(self.xyz_max[1]), self.density.shape[3]),
+            torch.linspace(float(self.xyz_min[2]), float(self.xyz_max[2]), self.density.shape[4]),
+            indexing="ij"), -1).to(self.density.device)
+
+    @torch.no_grad()
+    def _set_nonempty_mask(self):
+        # lib/dvgo_ori.py:154-167
+        nonempty_mask = self.mask_cache(self._grid_xyz())[None, None].contiguous()
+        self.nonempty_mask = nonempty_mask
+        self.density[~self.nonempty_mask] = -100
 
     def _set_grid_resolution(self, num_voxels):
         # lib/dvgo_ori.py:115-125
@@ -174,13 +267,130 @@ class DirectVoxGO(nn.Module):
         self.world_size = ((self.xyz_max - self.xyz_min) / self.voxel_size).long()
         self.voxel_size_ratio = self.voxel_size / self.voxel_size_base
 
+    def get_kwargs(self):
+        return {'xyz_min': self.xyz_min.cpu().numpy(), 'xyz_max': self.xyz_max.cpu().numpy(),
+                'num_voxels': self.num_voxels, 'num_voxels_base': self.num_voxels_base, 'alpha_init': self.alpha_init,
+                'nearest': self.nearest, 'pre_act_density': self.pre_act_density,
+                'in_act_density': self.in_act_density, 'mask_cache_path': self.mask_cache_path,
+                'mask_cache_thres': self.mask_cache_thres, 'fast_color_thres': self.fast_color_thres,
+                **self.rgbnet_kwargs}
+
+    def get_MaskCache_kwargs(self):
+        return {'xyz_min': self.xyz_min.cpu().numpy(), 'xyz_max': self.xyz_max.cpu().numpy(),
+                'act_shift': self.act_shift, 'voxel_size_ratio': self.voxel_size_ratio, 'nearest': self.nearest,
+                'pre_act_density': self.pre_act_density, 'in_act_density': self.in_act_density}
+
+    def activate_density(self, density, interval=None):
+        """1 - exp(-softplus(density + act_shift) * interval) (lib/dvgo_ori.py:242-244) = raw2alpha's expression:
+        on a flat [M] tensor this is the pp_raw2alpha kernel (with its backward), on a grid plain torch."""
+        from . import ops
+        interval = interval if interval is not None else self.voxel_size_ratio
+        if density.dim() == 1 and density.is_cuda:
+            return ops.Raw2Alpha.apply(density, self.act_shift, float(interval))
+        return 1 - torch.exp(-F.softplus(density + self.act_shift) * interval)
+
+    def grid_sampler(self, xyz, *grids, mode=None, align_corners=True):
+        """lib/dvgo_ori.py:246-261 on the trilinear gather kernel (zero padding, align_corners=True)."""
+        from . import ops
+        if mode not in (None, 'bilinear') or not align_corners:
+            raise NotImplementedError("DirectVoxGO.grid_sampler: bilinear / align_corners=True only")
+        shape = xyz.shape[:-1]
+        ret_lst = [ops.trilinear(grid, xyz.reshape(-1, 3), self.xyz_min, self.xyz_max).reshape(
+            *shape, grid.shape[1]).squeeze() for grid in grids]
+        return ret_lst[0] if len(ret_lst) == 1 else ret_lst
+
+    def density_total_variation(self):
+        from . import ops
+        return ops.total_variation(self.activate_density(self.density, 1), self.nonempty_mask)
+
+    def k0_total_variation(self):
+        from . import ops
+        v = self.k0 if self.rgbnet is not None else torch.sigmoid(self.k0)
+        return ops.total_variation(v, self.nonempty_mask)
+
+    def sample_ray(self, rays_o, rays_d, near, far, stepsize, is_train=False, jitter=None, **render_kwargs):
+        """lib/dvgo_ori.py:263-287: dense [N, S] query points and the out-of-box mask.  `jitter` ([N,1], optional)
+        replaces the reference's torch.rand_like draw under training so a test can fix it."""
+        N_samples = int(np.linalg.norm(np.array(self.density.shape[2:]) + 1) / stepsize) + 1
+        vec = torch.where(rays_d == 0, torch.full_like(rays_d, 1e-6), rays_d)
+        rate_a = (self.xyz_max - rays_o) / vec
+        rate_b = (self.xyz_min - rays_o) / vec
+        t_min = torch.minimum(rate_a, rate_b).amax(-1).clamp(min=near, max=far)
+        t_max = torch.maximum(rate_a, rate_b).amin(-1).clamp(min=near, max=far)
+        mask_outbbox = (t_max <= t_min)
+        rng = torch.arange(N_samples, device=rays_o.device)[None].float()
+        if is_train:
+            rng = rng.repeat(rays_d.shape[-2], 1)
+            rng = rng + (torch.rand_like(rng[:, [0]]) if jitter is None else jitter.to(rng))
+        step = stepsize * self.voxel_size * rng
+        interpx = (t_min[..., None] + step / rays_d.norm(dim=-1, keepdim=True))
+        rays_pts = rays_o[..., None, :] + rays_d[..., None, :] * interpx[..., None]
+        mask_outbbox = mask_outbbox[..., None] | ((self.xyz_min > rays_pts) | (rays_pts > self.xyz_max)).any(dim=-1)
+        return rays_pts, mask_outbbox
+
+    def forward(self, rays_o, rays_d, viewdirs, global_step=None, **render_kwargs):
+        """Volume rendering, lib/dvgo_ori.py:289-379."""
+        from . import ops
+        rays_pts, mask_outbbox = self.sample_ray(rays_o=rays_o, rays_d=rays_d, is_train=global_step is not None,
+                                                 **render_kwargs)
+        interval = render_kwargs['stepsize'] * self.voxel_size_ratio
+        if self.mask_cache is not None:
+            mask_outbbox[~mask_outbbox] |= (~self.mask_cache(rays_pts[~mask_outbbox]))
+        inbox = ~mask_outbbox
+        pts_in = rays_pts[inbox]
+        if self.pre_act_density:
+            a_in = ops.trilinear(self.activate_density(self.density, interval), pts_in, self.xyz_min, self.xyz_max)[:, 0]
+        elif self.in_act_density:
+            d_in = ops.trilinear(F.softplus(self.density + self.act_shift), pts_in, self.xyz_min, self.xyz_max)[:, 0]
+            a_in = 1 - torch.exp(-d_in * interval)
+        else:
+            d_in = ops.trilinear(self.density, pts_in, self.xyz_min, self.xyz_max)[:, 0]
+            a_in = ops.Raw2Alpha.apply(d_in.contiguous(), self.act_shift, float(interval))
+        alpha = torch.zeros_like(rays_pts[..., 0]).masked_scatter(inbox, a_in)
+        weights, alphainv_cum = ops.get_ray_marching_ray(alpha)
+        mask = (weights > self.fast_color_thres)
+        k0 = torch.zeros(*weights.shape, self.k0_dim, device=weights.device, dtype=weights.dtype)
+        pts_m = rays_pts[mask]
+        k0_m = ops.trilinear(self.k0, pts_m, self.xyz_min, self.xyz_max)
+        if self.rgbnet is None:
+            k0 = k0.masked_scatter(mask[..., None], k0_m)
+            rgb = torch.sigmoid(k0)
+        else:
+            if self.rgbnet_direct:
+                k0_view = k0_m
+            else:
+                k0_view, k0_diffuse = k0_m[:, 3:], k0_m[:, :3]
+            viewdirs_emb = (viewdirs.unsqueeze(-1) * self.viewfreq).flatten(-2)
+            viewdirs_emb = torch.cat([viewdirs, viewdirs_emb.sin(), viewdirs_emb.cos()], -1)
+            rays_xyz = (pts_m - self.xyz_min) / (self.xyz_max - self.xyz_min)
+            xyz_emb = (rays_xyz.unsqueeze(-1) * self.posfreq).flatten(-2)
+            xyz_emb = torch.cat([rays_xyz, xyz_emb.sin(), xyz_emb.cos()], -1)
+            ray_of = torch.arange(weights.shape[0], device=weights.device)[:, None].expand_as(mask)[mask]
+            rgb_feat = torch.cat([k0_view, xyz_emb, viewdirs_emb[ray_of]], -1)
+            logit_m = self.rgbnet(rgb_feat)
+            if not self.rgbnet_direct:
+                logit_m = logit_m + k0_diffuse
+            rgb_logit = torch.zeros(*weights.shape, 3, device=weights.device, dtype=weights.dtype)
+            rgb = torch.sigmoid(rgb_logit.masked_scatter(mask[..., None], logit_m))
+        rgb_marched = (weights[..., None] * rgb).sum(-2) + alphainv_cum[..., [-1]] * render_kwargs['bg']
+        rgb_marched = rgb_marched.clamp(0, 1)
+        depth = (rays_o[..., None, :] - rays_pts).norm(dim=-1)
+        depth = (weights * depth).sum(-1) + alphainv_cum[..., -1] * render_kwargs['far']
+        disp = 1 / depth
+        return {'alphainv_cum': alphainv_cum, 'weights': weights, 'rgb_marched': rgb_marched, 'raw_alpha': alpha,
+                'raw_rgb': rgb, 'depth': depth, 'disp': disp, 'mask': mask, 'mask_outbbox': mask_outbbox}
+
     def scene(self, near, far, stepsize, bg):
         return make_scene(self.world_size.tolist(), self.xyz_min.tolist(), self.xyz_max.tolist(), near, far,
                           stepsize * float(self.voxel_size), self.act_shift,
                           stepsize * float(self.voxel_size_ratio), bg, self.fast_color_thres)
 
-    def forward(self, rays_o, rays_d, viewdirs=None, global_step=None, **render_kwargs):
-        """Volume rendering; keys of the reference's result dict that exist per ray are returned."""
+    def forward_fused(self, rays_o, rays_d, viewdirs=None, global_step=None, **render_kwargs):
+        """The coarse configuration on the fused march kernels (one launch forward, one backward): compacted in-box
+        samples with the reference CUDA sampler's early termination (T < 1e-3), per-ray entries only; `depth` here is
+        the distance from the box entry point (sum w * step), not the reference's |o - p| + alphainv_last * far."""
+        if self.rgbnet is not None or self.mask_cache is not None or self.pre_act_density or self.in_act_density:
+            raise NotImplementedError("forward_fused serves rgbnet_dim=0, post-activation density, no mask cache")
         sc = self.scene(render_kwargs['near'], render_kwargs['far'], render_kwargs['stepsize'],
                         float(render_kwargs.get('bg', 0.0)))
         rgb, last, depth = _RenderFn.apply(self.density, self.k0, rays_o, rays_d, sc)

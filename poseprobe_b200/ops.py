@@ -227,6 +227,44 @@ def segment_cumsum(src, ray_id):
     return out
 
 
+class _DenseComposite(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, alpha):
+        a2 = alpha.reshape(-1, alpha.shape[-1]).contiguous()
+        n, S = a2.shape
+        weights = torch.empty_like(a2)
+        cum = torch.empty((n, S + 1), dtype=torch.float32, device=a2.device)
+        with torch.cuda.device(a2.device):
+            check(lib.pp_dense_composite_forward(ptr(a2), n, S, ptr(weights), ptr(cum), stream()),
+                  "dense_composite_forward")
+        ctx.save_for_backward(a2, cum)
+        ctx.shape = alpha.shape
+        return weights.reshape(alpha.shape), cum.reshape(alpha.shape[:-1] + (S + 1,))
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_w, g_cum):
+        a2, cum = ctx.saved_tensors
+        n, S = a2.shape
+        g_alpha = torch.empty_like(a2)
+        gw = g_w.reshape(n, S).contiguous() if g_w is not None else None
+        gc = g_cum.reshape(n, S + 1).contiguous() if g_cum is not None else None
+        with torch.cuda.device(a2.device):
+            check(lib.pp_dense_composite_backward(ptr(a2), ptr(cum), n, S, ptr(gw), ptr(gc), ptr(g_alpha), stream()),
+                  "dense_composite_backward")
+        return g_alpha.reshape(ctx.shape)
+
+
+def get_ray_marching_ray(alpha):
+    """`get_ray_marching_ray(alpha)` of the reference's pure-PyTorch DirectVoxGO (lib/dvgo_ori.py:478-485): dense
+    alpha [..., S] -> (weights [..., S], alphainv_cum [..., S+1]); differentiable (torch.cumprod's rule)."""
+    if not alpha.is_cuda:
+        raise RuntimeError("get_ray_marching_ray: alpha must be a CUDA tensor (no CPU fallback)")
+    if alpha.dtype != torch.float32:
+        raise RuntimeError('"get_ray_marching_ray" not implemented for %s' % str(alpha.dtype))
+    return _DenseComposite.apply(alpha)
+
+
 class _NeusAlpha(torch.autograd.Function):
     @staticmethod
     def forward(ctx, sdf, gradient, viewdirs, ray_id, dist, inv_s):

@@ -206,10 +206,12 @@ def test_module_drop_in(pp):
         m.density.normal_()
         m.k0.normal_()
     o, d, v = synthetic.make_rays(100)
-    out = m(o.cuda(), d.cuda(), v.cuda(), global_step=1, near=0.2, far=1e9, stepsize=0.5, bg=1.0)
-    assert set(out) >= {"rgb_marched", "alphainv_cum", "depth", "disp"}
-    torch.nn.functional.mse_loss(out["rgb_marched"], torch.rand(100, 3, device="cuda")).backward()
-    assert float(m.density.grad.abs().sum()) > 0 and float(m.k0.grad.abs().sum()) > 0
+    for fwd in (m.forward, m.forward_fused):
+        m.zero_grad()
+        out = fwd(o.cuda(), d.cuda(), v.cuda(), global_step=1, near=0.2, far=1e9, stepsize=0.5, bg=1.0)
+        assert set(out) >= {"rgb_marched", "alphainv_cum", "depth", "disp"}
+        torch.nn.functional.mse_loss(out["rgb_marched"], torch.rand(100, 3, device="cuda")).backward()
+        assert float(m.density.grad.abs().sum()) > 0 and float(m.k0.grad.abs().sum()) > 0
 
 
 def test_config_b_full_size_properties(pp):
