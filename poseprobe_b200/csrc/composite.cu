@@ -50,30 +50,34 @@ __device__ __forceinline__ int tile_at(int r, int c) { return r * kTile + (c ^ (
 // Two warps per 32 rays.  Warp 0 ("chain") only runs the recurrence: per step it reads its ray's row of the input
 // tile, advances 8 samples, writes its T / weight rows - ~100 instructions, and a lone warp issues one dependent
 // instruction every ~5 cycles, so instructions on this warp ARE the kernel's duration.  Warp 1 ("memory") does all
-// the addressing: it knows every ray's [begin, end) (8 rays per lane, loaded once), loads tile i+2 from global memory
-// into registers (two steps ahead, so DRAM latency is covered), stages tile i+1 into shared memory and streams the
+// the addressing: it knows every ray's [begin, end) (8 rays per lane, loaded once), loads tile i+3 from global memory
+// into registers (two steps before it is staged, so DRAM latency is covered), stages tile i+1 into shared memory and streams the
 // outputs of tile i-1 back as 32-byte sectors.  Tiles rotate through three shared-memory slots; one block barrier
 // per step orders the two warps.
+constexpr int kFwdMemWarps = 4;
+constexpr int kFwdK = kTile / kFwdMemWarps;   // sector instructions per memory warp and step
+
 template <typename scalar_t>
-__global__ void __launch_bounds__(2 * kWarp)
+__global__ void __launch_bounds__((1 + kFwdMemWarps) * kWarp)
 alpha2weight_fwd_kernel(const scalar_t* __restrict__ alpha, int64_t n_rays,
                         scalar_t* __restrict__ weight, scalar_t* __restrict__ T_out,
                         scalar_t* __restrict__ alphainv_last, const int64_t* __restrict__ i_start,
                         int64_t* __restrict__ i_end) {
   __shared__ scalar_t s_a[3][kWarp * kTile], s_T[3][kWarp * kTile], s_w[3][kWarp * kTile];
   __shared__ int s_steps;
-  const int lane = threadIdx.x & 31, sub = lane / kTile, sl = lane % kTile;
-  const bool chain = threadIdx.x < kWarp;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane / kTile, sl = lane % kTile;
+  const bool chain = warp == 0;
   const int64_t ray0 = blockIdx.x * (int64_t)kWarp;
   // chain warp: own ray.  (sample indices fit 32 bits: the entry point rejects n_pts > INT32_MAX)
   const int64_t ray = ray0 + lane;
   const bool live = chain && ray < n_rays;
   const int begin = live ? static_cast<int>(i_start[ray]) : 0, end = live ? static_cast<int>(i_end[ray]) : 0;
-  // memory warp: instruction k of a step serves ray 4k + sub
-  int bk[kTile], ek[kTile];
+  // memory warp w serves the sector instructions k = (w - 1) * kFwdK + q of a step: ray 4k + sub
+  int bk[kFwdK], ek[kFwdK], rk[kFwdK];
 #pragma unroll
-  for (int k = 0; k < kTile; ++k) {
-    const int64_t r = ray0 + k * kGroups + sub;
+  for (int k = 0; k < kFwdK; ++k) {
+    rk[k] = ((warp - 1) * kFwdK + k) * kGroups + sub;
+    const int64_t r = ray0 + rk[k];
     const bool ok = !chain && r < n_rays;
     bk[k] = ok ? static_cast<int>(i_start[r]) : 0;
     ek[k] = ok ? static_cast<int>(i_end[r]) : 0;
@@ -86,22 +90,23 @@ alpha2weight_fwd_kernel(const scalar_t* __restrict__ alpha, int64_t n_rays,
   }
   __syncthreads();
   const int steps = s_steps;
-  scalar_t ld[2][kTile];        // memory warp: tiles in flight (tile t lives in ld[t & 1])
-  auto issue_loads = [&](int t, scalar_t (&dst)[kTile]) {
+  scalar_t ld[2][kFwdK];        // memory warp: tiles in flight (tile t lives in ld[t & 1])
+  auto issue_loads = [&](int t, scalar_t (&dst)[kFwdK]) {
 #pragma unroll
-    for (int k = 0; k < kTile; ++k) {
+    for (int k = 0; k < kFwdK; ++k) {
       const int idx = bk[k] + t * kTile + sl;
-      dst[k] = (t < steps && idx < ek[k]) ? alpha[idx] : scalar_t(0);
+      dst[k] = (t < steps && idx < ek[k]) ? __ldcg(alpha + idx) : scalar_t(0);
     }
   };
-  auto stage = [&](int t, const scalar_t (&src)[kTile]) {
+  auto stage = [&](int t, const scalar_t (&src)[kFwdK]) {
 #pragma unroll
-    for (int k = 0; k < kTile; ++k) s_a[t % 3][tile_at(k * kGroups + sub, sl)] = src[k];
+    for (int k = 0; k < kFwdK; ++k) s_a[t % 3][tile_at(rk[k], sl)] = src[k];
   };
   if (!chain) {
     issue_loads(0, ld[0]);
     issue_loads(1, ld[1]);
     stage(0, ld[0]);
+    issue_loads(2, ld[0]);      // from here on: tile t lives in ld[t & 1] until it is staged
   }
   __syncthreads();
   int pos = begin, cut = -1;
@@ -132,34 +137,29 @@ alpha2weight_fwd_kernel(const scalar_t* __restrict__ alpha, int64_t n_rays,
       }
       pos += kTile;
     } else {
-      // tile t+1 -> shared memory (its loads were issued one step ago), tile t+2 -> registers, tile t-1 -> global
-      if (((t + 1) & 1) == 0) {
-        stage(t + 1, ld[0]);
-        issue_loads(t + 2, ld[0]);
-      } else {
-        stage(t + 1, ld[1]);
-        issue_loads(t + 2, ld[1]);
-      }
+      // tile t+1 -> shared memory (its loads were issued two steps ago), tile t+3 -> registers, tile t-1 -> global
+      if (((t + 1) & 1) == 0) stage(t + 1, ld[0]); else stage(t + 1, ld[1]);
       if (t > 0) {
 #pragma unroll
-        for (int k = 0; k < kTile; ++k) {
+        for (int k = 0; k < kFwdK; ++k) {
           const int idx = bk[k] + (t - 1) * kTile + sl;
           if (idx < ek[k]) {
-            T_out[idx] = s_T[(t - 1) % 3][tile_at(k * kGroups + sub, sl)];
-            weight[idx] = s_w[(t - 1) % 3][tile_at(k * kGroups + sub, sl)];
+            T_out[idx] = s_T[(t - 1) % 3][tile_at(rk[k], sl)];
+            weight[idx] = s_w[(t - 1) % 3][tile_at(rk[k], sl)];
           }
         }
       }
+      if (((t + 1) & 1) == 0) issue_loads(t + 3, ld[0]); else issue_loads(t + 3, ld[1]);
     }
     __syncthreads();
   }
   if (!chain && steps > 0) {
 #pragma unroll
-    for (int k = 0; k < kTile; ++k) {
+    for (int k = 0; k < kFwdK; ++k) {
       const int idx = bk[k] + (steps - 1) * kTile + sl;
       if (idx < ek[k]) {
-        T_out[idx] = s_T[(steps - 1) % 3][tile_at(k * kGroups + sub, sl)];
-        weight[idx] = s_w[(steps - 1) % 3][tile_at(k * kGroups + sub, sl)];
+        T_out[idx] = s_T[(steps - 1) % 3][tile_at(rk[k], sl)];
+        weight[idx] = s_w[(steps - 1) % 3][tile_at(rk[k], sl)];
       }
     }
   }
@@ -176,7 +176,7 @@ alpha2weight_fwd_kernel(const scalar_t* __restrict__ alpha, int64_t n_rays,
 // shared memory.  Everything else - the loads of the four inputs, and grad = gw*T - back/(1-alpha+1e-10) with its
 // double-precision quotient, which is not part of the recurrence - is done by kBwdMemWarps memory warps in the
 // coalesced layout (each owns 8 / kBwdMemWarps of the step's 8 sector instructions).
-constexpr int kBwdMemWarps = 4;
+constexpr int kBwdMemWarps = 8;
 constexpr int kBwdK = kTile / kBwdMemWarps;   // sector instructions per memory warp and step
 
 template <typename scalar_t>
@@ -225,7 +225,7 @@ alpha2weight_bwd_kernel(const scalar_t* __restrict__ alpha, const scalar_t* __re
       const int idx = tk[q] - (t + 1) * kTile + sl;
       const bool ok = t < steps && idx >= bk[q];
 #pragma unroll
-      for (int f = 0; f < 4; ++f) dst[f][q] = ok ? src[f][idx] : scalar_t(0);
+      for (int f = 0; f < 4; ++f) dst[f][q] = ok ? __ldcg(src[f] + idx) : scalar_t(0);
     }
   };
   auto stage = [&](int t, const scalar_t (&v)[4][kBwdK]) {
@@ -253,6 +253,7 @@ alpha2weight_bwd_kernel(const scalar_t* __restrict__ alpha, const scalar_t* __re
     issue_loads(0, ld[0]);
     issue_loads(1, ld[1]);
     stage(0, ld[0]);
+    issue_loads(2, ld[0]);      // from here on: tile t lives in ld[t & 1] until it is staged
   }
   __syncthreads();
   int top = top0;
@@ -278,10 +279,10 @@ alpha2weight_bwd_kernel(const scalar_t* __restrict__ alpha, const scalar_t* __re
     } else {
       if (((t + 1) & 1) == 0) {
         stage(t + 1, ld[0]);
-        issue_loads(t + 2, ld[0]);
+        issue_loads(t + 3, ld[0]);
       } else {
         stage(t + 1, ld[1]);
-        issue_loads(t + 2, ld[1]);
+        issue_loads(t + 3, ld[1]);
       }
       if (t > 0) finish(t - 1);
     }
@@ -576,7 +577,7 @@ extern "C" int pp_alpha2weight(pp_dtype dtype, const void* alpha, const int64_t*
   segment_bounds_kernel<<<ceil_div(n_pts, 256), 256, 0, s>>>(ray_id, n_pts, n_rays, i_start, i_end);
   PP_CHECK_LAUNCH("alpha2weight(bounds)");
   PP_DISPATCH(dtype, {
-    alpha2weight_fwd_kernel<scalar_t><<<ceil_div(n_rays, kWarp), 2 * kWarp, 0, s>>>(
+    alpha2weight_fwd_kernel<scalar_t><<<ceil_div(n_rays, kWarp), (1 + kFwdMemWarps) * kWarp, 0, s>>>(
         (const scalar_t*)alpha, n_rays, (scalar_t*)weight, (scalar_t*)T, (scalar_t*)alphainv_last,
         i_start, i_end);
   });

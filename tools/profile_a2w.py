@@ -26,21 +26,29 @@ gw, gl = torch.randn(M, device=dev), torch.randn(N, device=dev)
 flush = torch.empty(64 * 1024 * 1024, device=dev)
 
 
-def timed(fn, n=10):
-    fn()
-    torch.cuda.synchronize()
-    tot = 0.0
-    for _ in range(n):
-        flush.fill_(1.0)
+def timed(fn, n=20):
+    """device time of fn() alone: CUDA graphs of [L2 flush; fn] and [L2 flush] replayed back to back, difference of
+    the two (no host launch gaps, cold L2, clocks under load)"""
+    def graph_ms(body):
+        body()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            body()
+        g.replay()
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        # a long kernel in front hides the host-side launch overhead of the op behind it
-        flush.fill_(2.0)
         e0.record()
-        fn()
+        for _ in range(n):
+            g.replay()
         e1.record()
         torch.cuda.synchronize()
-        tot += e0.elapsed_time(e1)
-    return tot / n * 1e3
+        return e0.elapsed_time(e1) / n
+
+    def both():
+        flush.fill_(1.0)
+        fn()
+    return (graph_ms(both) - graph_ms(lambda: flush.fill_(1.0))) * 1e3
 
 
 w, T, last, i_s, i_e = ru.alpha2weight(alpha, ray_id, N)
@@ -49,4 +57,7 @@ print("alpha2weight fwd (bounds + march): %.1f us" % timed(lambda: ru.alpha2weig
 print("alpha2weight bwd:                  %.1f us" % timed(
     lambda: ru.alpha2weight_backward(alpha, w, T, last, i_s, i_e, N, gw, gl)))
 print("raw2alpha fwd:                     %.1f us" % timed(lambda: ru.raw2alpha(dens, synthetic.act_shift(), 0.5)))
-print("trilinear fwd C=1:                 %.1f us" % timed(lambda: ops.trilinear(density.to(dev), pts, mn, mx)))
+dens_grid = density.to(dev)
+print("trilinear fwd C=1:                 %.1f us" % timed(lambda: ops.trilinear(dens_grid, pts, mn, mx)))
+rgb = torch.rand(M, 3, device=dev)
+print("segment_sum [M,3]:                 %.1f us" % timed(lambda: ops.segment_sum(rgb, ray_id, N)))
