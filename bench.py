@@ -596,10 +596,16 @@ def fine_stage_dist_bench(dev, rank, world):
     ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms)
+    mode = tr.mode
+    tr.close()
     del tr
     return {"workload": "Voxurf SDF fine stage + per-ray pose gradient (BASELINE configs[2]): 160^3 sdf + 12-ch k0 + "
-                        "rgbnet 57-128-128-128-3 (tcgen05), 8192 rays/step/rank, fwd+bwd+Adam, ray-sharded over %d ranks, "
-                        "one flat NCCL all-reduce of the gradient buffer per step" % world,
+                        "rgbnet 57-128-128-128-3 (tcgen05), 8192 rays/step/rank, fwd+bwd+Adam, ray-sharded over %d ranks; "
+                        "exchange: %s" % (world, {
+                            "nvls": "feature records through ONE in-switch reduce-scatter + sharded Adam + multicast "
+                                    "kernel, SDF / rgbnet gradients summed in place through the switch, flag barriers "
+                                    "in peer memory (no NCCL on the step)",
+                            "nccl": "one flat NCCL all-reduce of the gradient buffer, full Adam on every rank"}[mode]),
             "train_rays_per_s": world * RAYS / (ms * 1e-3), "ms_per_step": ms, "n_gpus": world}
 
 
@@ -751,9 +757,24 @@ def cpu_baseline():
         base.train_step(o, d, tgt)
         steps += 1
     dt = time.perf_counter() - t0
-    return {"value": RAYS * steps / dt, "unit": "rays/s", "cores": cores, "kind": "port",
-            "sample": "%d steps of the full %d-ray batch (lib/dvgo_ori.py dense formulation, oracle/dvgo_cpu.py)"
-                      % (steps, RAYS)}
+    out = {"value": RAYS * steps / dt, "unit": "rays/s", "cores": cores, "kind": "port",
+           "sample": "%d steps of the full %d-ray batch (lib/dvgo_ori.py dense formulation, oracle/dvgo_cpu.py)"
+                     % (steps, RAYS)}
+    # BASELINE configs[0] (the reference's own CPU-runnable case): 64^3 grid, 4096-ray step, same formulation
+    density, k0 = synthetic.make_dvgo_grids(64)
+    o, d, _ = synthetic.make_rays(4096)
+    tgt = torch.rand(4096, 3, generator=torch.Generator().manual_seed(99))
+    base = dvgo_cpu.DenseBaseline(density, k0, XYZ_MIN, XYZ_MAX, STEPSIZE)
+    base.train_step(o, d, tgt)
+    t0 = time.perf_counter()
+    steps = 0
+    while steps < 3 or (time.perf_counter() - t0 < 4 and steps < 20):
+        base.train_step(o, d, tgt)
+        steps += 1
+    dt = time.perf_counter() - t0
+    out["config_a"] = {"workload": "BASELINE configs[0]: 64^3 density+k0(3) grid, 4096-ray fwd+bwd+Adam step, CPU",
+                       "value": 4096 * steps / dt, "unit": "rays/s", "ms_per_step": dt / steps * 1e3, "steps": steps}
+    return out
 
 
 def main():

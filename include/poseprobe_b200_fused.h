@@ -161,6 +161,21 @@ PP_API int pp_voxel_adam_exchange_mc(const void* vox_local, void* vox_mc, const 
                                      uint32_t epoch, const float* payload_in, float* payload_sum_out,
                                      pp_stream_t stream);
 
+/* The same exchange for any array of float4 records with ONE learning rate (the fine stage's 12-channel feature
+ * records = 3 records per voxel): reduce-scatter in the switch + Adam on this rank's slice (moments for the slice
+ * only) + multicast store.  dense != 0: the reference's live dense Python Adam (lib/utils.py:176-198, see
+ * pp_voxel_adam flags bit 1) instead of masked_adam_upd. */
+PP_API int pp_records_adam_exchange_mc(const void* rec_local, void* rec_mc, const void* grad_mc, void* exp_avg,
+                                       void* exp_avg_sq, int64_t n_records, int32_t world, int32_t rank,
+                                       int32_t step, float beta1, float beta2, float lr, float eps, int dense,
+                                       void* const* sync_ptrs, uint32_t epoch, const float* payload_in,
+                                       float* payload_sum_out, pp_stream_t stream);
+/* In-place sum all-reduce of n_records float4 records at a multicast address (multimem.ld_reduce + multimem.st on
+ * this rank's slice).  The caller brackets it with the cross-rank barriers (all contributions written before; all
+ * slices written after).  sync_ptrs (nullable): skip when this rank's barrier timed out. */
+PP_API int pp_allreduce_mc(void* buf_mc, int64_t n_records, int32_t world, int32_t rank, void* const* sync_ptrs,
+                           pp_stream_t stream);
+
 /* Hybrid of the two above in ONE launch: the first mc_fraction of the slice (rounded down to 256 records) goes
  * through the switch (vox_mc / grad_mc), the rest through peer loads and stores (vox_ptrs / grad_ptrs, which must
  * address the same buffers the multicast addresses are bound to).  The multimem path is held by the switch's

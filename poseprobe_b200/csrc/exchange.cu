@@ -67,8 +67,8 @@ __device__ __forceinline__ void peer_announce_and_wait(const SyncPtrs& sp, int w
 }
 
 __device__ __forceinline__ void adam_elem_x(float& p, float g, float& m, float& v, float step_size,
-                                            float b1, float b2, float eps) {
-  if (g == 0.f) return;   // masked_adam_upd (adam_upd_kernel.cu:35)
+                                            float b1, float b2, float eps, bool dense = false) {
+  if (!dense && g == 0.f) return;   // masked_adam_upd (adam_upd_kernel.cu:35); dense: lib/utils.py:176-198
   m = fma_rn(b1, m, mul_rn(1.f - b1, g));
   v = fma_rn(b2, v, mul_rn(mul_rn(1.f - b2, g), g));
   p = p - mul_rn(step_size, m) / (sqrtf(v) + eps);
@@ -172,7 +172,7 @@ voxel_adam_exchange_mc_kernel(const float4* __restrict__ vox_local, float4* vox_
                               float4* __restrict__ m4, float4* __restrict__ v4, int64_t begin, int64_t end,
                               float ss_density, float ss_k0, float b1, float b2, float eps, SyncPtrs sp, int world,
                               int me, unsigned int epoch, const float* __restrict__ payload_in,
-                              float* __restrict__ payload_sum) {
+                              float* __restrict__ payload_sum, int dense) {
   // optional fused "all gradients complete" barrier: block 0 announces, every block waits for all peers before
   // its first in-switch reduction (saves the separate one-warp barrier launch in front of this kernel)
   if (epoch != 0u) {
@@ -227,14 +227,34 @@ voxel_adam_exchange_mc_kernel(const float4* __restrict__ vox_local, float4* vox_
       mq[kDepth - 1] = in ? m4[n - begin] : zero;
       vq[kDepth - 1] = in ? v4[n - begin] : zero;
     }
-    if (g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f) continue;
-    adam_elem_x(p.x, g.x, m.x, v.x, ss_density, b1, b2, eps);
-    adam_elem_x(p.y, g.y, m.y, v.y, ss_k0, b1, b2, eps);
-    adam_elem_x(p.z, g.z, m.z, v.z, ss_k0, b1, b2, eps);
-    adam_elem_x(p.w, g.w, m.w, v.w, ss_k0, b1, b2, eps);
+    if (!dense && g.x == 0.f && g.y == 0.f && g.z == 0.f && g.w == 0.f) continue;
+    adam_elem_x(p.x, g.x, m.x, v.x, ss_density, b1, b2, eps, dense);
+    adam_elem_x(p.y, g.y, m.y, v.y, ss_k0, b1, b2, eps, dense);
+    adam_elem_x(p.z, g.z, m.z, v.z, ss_k0, b1, b2, eps, dense);
+    adam_elem_x(p.w, g.w, m.w, v.w, ss_k0, b1, b2, eps, dense);
     m4[i - begin] = m;
     v4[i - begin] = v;
     mc_st(vox_mc + i, p);
+  }
+}
+
+// In-place sum all-reduce of float4 records through the switch: every rank reduces its slice of the multicast
+// address (multimem.ld_reduce) and writes the sum back to every replica (multimem.st) - the same (w+1)/w traffic per
+// direction as the exchange kernel, no optimiser.  Used for the small or stencil-coupled gradients of the fine stage
+// (SDF gradient records, rgbnet gradients), which every rank then applies identically.
+__global__ void __launch_bounds__(kXchgThreads)
+allreduce_mc_kernel(float4* buf_mc, int64_t begin, int64_t end, SyncPtrs sp, int me) {
+  if (sp.blk[me] && peer_timed_out(sp, me)) return;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  constexpr int kDepth = 4;
+  for (int64_t i0 = begin + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < end; i0 += kDepth * stride) {
+    float4 v[kDepth];
+#pragma unroll
+    for (int d = 0; d < kDepth; ++d)
+      if (i0 + d * stride < end) v[d] = mc_ld_reduce_add(buf_mc + i0 + d * stride);
+#pragma unroll
+    for (int d = 0; d < kDepth; ++d)
+      if (i0 + d * stride < end) mc_st(buf_mc + i0 + d * stride, v[d]);
   }
 }
 
@@ -447,12 +467,11 @@ extern "C" int pp_shared_free(void* ptr) {
   return PP_OK;
 }
 
-extern "C" int pp_voxel_adam_exchange_mc(const void* vox_local, void* vox_mc, const void* grad_mc,
-                                         void* exp_avg, void* exp_avg_sq, int64_t n_voxels,
-                                         int32_t world, int32_t rank, int32_t step, float beta1,
-                                         float beta2, float lr_density, float lr_k0, float eps,
-                                         void* const* sync_ptrs, uint32_t epoch, const float* payload_in,
-                                         float* payload_sum_out, pp_stream_t stream) {
+static int exchange_mc_impl(const void* vox_local, void* vox_mc, const void* grad_mc, void* exp_avg,
+                            void* exp_avg_sq, int64_t n_voxels, int32_t world, int32_t rank, int32_t step,
+                            float beta1, float beta2, float lr_density, float lr_k0, float eps,
+                            void* const* sync_ptrs, uint32_t epoch, const float* payload_in,
+                            float* payload_sum_out, int dense, pp_stream_t stream) {
   PP_REQUIRE(vox_local && vox_mc && grad_mc && exp_avg && exp_avg_sq, PP_ERR_INVALID_ARG,
              "voxel_adam_exchange_mc: null pointer");
   PP_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, PP_ERR_INVALID_ARG,
@@ -473,13 +492,50 @@ extern "C" int pp_voxel_adam_exchange_mc(const void* vox_local, void* vox_mc, co
 #define PP_LAUNCH_MC(D)                                                                                          \
   voxel_adam_exchange_mc_kernel<D><<<blocks, kXchgThreads, 0, as_stream(stream)>>>(                              \
       (const float4*)vox_local, (float4*)vox_mc, (const float4*)grad_mc, (float4*)exp_avg, (float4*)exp_avg_sq, \
-      begin, end, ssd, ssk, beta1, beta2, eps, sp, world, rank, epoch, payload_in, payload_sum_out)
+      begin, end, ssd, ssk, beta1, beta2, dense ? eps * sqrtf(1.f - powf(beta2, (float)step)) : eps, sp, world,     \
+      rank, epoch, payload_in, payload_sum_out, dense)
   if (depth <= 2) PP_LAUNCH_MC(2);
   else if (depth == 3) PP_LAUNCH_MC(3);
   else if (depth == 4) PP_LAUNCH_MC(4);
   else PP_LAUNCH_MC(6);
 #undef PP_LAUNCH_MC
   PP_CHECK_LAUNCH("voxel_adam_exchange_mc");
+  return PP_OK;
+}
+
+extern "C" int pp_voxel_adam_exchange_mc(const void* vox_local, void* vox_mc, const void* grad_mc,
+                                         void* exp_avg, void* exp_avg_sq, int64_t n_voxels,
+                                         int32_t world, int32_t rank, int32_t step, float beta1,
+                                         float beta2, float lr_density, float lr_k0, float eps,
+                                         void* const* sync_ptrs, uint32_t epoch, const float* payload_in,
+                                         float* payload_sum_out, pp_stream_t stream) {
+  return exchange_mc_impl(vox_local, vox_mc, grad_mc, exp_avg, exp_avg_sq, n_voxels, world, rank, step, beta1, beta2,
+                          lr_density, lr_k0, eps, sync_ptrs, epoch, payload_in, payload_sum_out, 0, stream);
+}
+
+extern "C" int pp_records_adam_exchange_mc(const void* rec_local, void* rec_mc, const void* grad_mc, void* exp_avg,
+                                           void* exp_avg_sq, int64_t n_records, int32_t world, int32_t rank,
+                                           int32_t step, float beta1, float beta2, float lr, float eps, int dense,
+                                           void* const* sync_ptrs, uint32_t epoch, const float* payload_in,
+                                           float* payload_sum_out, pp_stream_t stream) {
+  return exchange_mc_impl(rec_local, rec_mc, grad_mc, exp_avg, exp_avg_sq, n_records, world, rank, step, beta1, beta2,
+                          lr, lr, eps, sync_ptrs, epoch, payload_in, payload_sum_out, dense ? 1 : 0, stream);
+}
+
+extern "C" int pp_allreduce_mc(void* buf_mc, int64_t n_records, int32_t world, int32_t rank,
+                               void* const* sync_ptrs, pp_stream_t stream) {
+  PP_REQUIRE(buf_mc && n_records >= 0, PP_ERR_INVALID_ARG, "allreduce_mc: bad argument");
+  PP_REQUIRE(world >= 1 && world <= kMaxWorld && rank >= 0 && rank < world, PP_ERR_INVALID_ARG,
+             "allreduce_mc: bad world/rank %d/%d", rank, world);
+  const int64_t shard = pp_voxel_shard_size(n_records, world);
+  const int64_t begin = shard * rank < n_records ? shard * rank : n_records;
+  const int64_t end = begin + shard < n_records ? begin + shard : n_records;
+  if (end <= begin) return PP_OK;
+  SyncPtrs sp;
+  for (int r = 0; r < kMaxWorld; ++r) sp.blk[r] = (sync_ptrs && r < world) ? (SyncBlock*)sync_ptrs[r] : nullptr;
+  allreduce_mc_kernel<<<exchange_blocks(end - begin), kXchgThreads, 0, as_stream(stream)>>>((float4*)buf_mc, begin,
+                                                                                             end, sp, rank);
+  PP_CHECK_LAUNCH("allreduce_mc");
   return PP_OK;
 }
 

@@ -80,7 +80,8 @@ class FusedVoxurf:
                  bg=0.0, s_val=0.05, sdf_alpha=None, sdf_beta=None, posbase_pe=5, viewbase_pe=1, barf_c2f=None,
                  lr_sdf=0.1, lr_k0=0.1, lr_rgbnet=1e-3, betas=(0.9, 0.99), eps=1e-8, w_rgb=1.0,
                  samples_per_ray_cap=None, pose_grad=False, voxel_size=None, adam="reference", lr_warp=1e-3,
-                 w_entropy=0.0, w_mask=0.0, w_tv_k0=0.0, w_eikonal=0.0, w_deform=0.0):
+                 w_entropy=0.0, w_mask=0.0, w_tv_k0=0.0, w_eikonal=0.0, w_deform=0.0, k0rec_buf=None,
+                 grad_flat_buf=None, k0_moment_records=None):
         """adam: "reference" = the optimiser the reference runs (dense Python Adam, lib/utils.py:176-198: every
         element updated each step, eps after the bias correction) or "masked" = masked_adam_upd arithmetic
         (adam_upd_kernel.cu:25-40: elements with a zero gradient are skipped, eps before the bias correction).
@@ -119,7 +120,10 @@ class FusedVoxurf:
         dev = self.device
         # parameters in the kernels' layouts
         self.sdf = sdf.detach().clone().reshape(-1).contiguous()
-        self.k0rec = torch.empty((self.n_voxels, 12), dtype=torch.float32, device=dev)
+        # (k0rec_buf / grad_flat_buf: caller-owned, e.g. peer-mapped, memory for the feature records and the flat
+        # gradient buffer; k0_moment_records: Adam moments for a slice of the feature records only - DistributedVoxurf)
+        self.k0rec = (torch.empty((self.n_voxels, 12), dtype=torch.float32, device=dev) if k0rec_buf is None
+                      else k0rec_buf.view(-1)[:12 * self.n_voxels].view(self.n_voxels, 12))
         with torch.cuda.device(dev):
             check(lib.pp_voxurf_k0_pack(ptr(k0.contiguous()), self.n_voxels, ptr(self.k0rec), stream()), "k0_pack")
         idx = torch.tensor([max(p, 0) for p in self.perm], device=dev)
@@ -132,7 +136,12 @@ class FusedVoxurf:
         # gradients: ONE flat buffer (SDF-record gradients | feature-record gradients | rgbnet gradients), so a
         # multi-GPU step reduces everything with a single all-reduce (DistributedVoxurf)
         n_net = sum(w.numel() for w in self.weights) + sum(b.numel() for b in self.biases)
-        self.grad_flat = torch.zeros(16 * self.n_voxels + n_net, dtype=torch.float32, device=dev)
+        if grad_flat_buf is None:
+            self.grad_flat = torch.zeros(16 * self.n_voxels + n_net, dtype=torch.float32, device=dev)
+        else:
+            self.grad_flat = grad_flat_buf.view(-1)[:16 * self.n_voxels + n_net]
+            self.grad_flat.zero_()
+        self.n_net = n_net
         self.g_srec = self.grad_flat[:4 * self.n_voxels].view(self.n_voxels, 4)
         self.g_k0rec = self.grad_flat[4 * self.n_voxels:16 * self.n_voxels].view(self.n_voxels, 12)
         self.g_w, self.g_b = [], []
@@ -144,7 +153,11 @@ class FusedVoxurf:
             self.g_b.append(self.grad_flat[off:off + bb.numel()].view_as(bb))
             off += bb.numel()
         self.m_sdf, self.v_sdf = torch.zeros_like(self.sdf), torch.zeros_like(self.sdf)
-        self.m_k0, self.v_k0 = torch.zeros_like(self.k0rec), torch.zeros_like(self.k0rec)
+        if k0_moment_records is None:
+            self.m_k0, self.v_k0 = torch.zeros_like(self.k0rec), torch.zeros_like(self.k0rec)
+        else:
+            self.m_k0 = torch.zeros((int(k0_moment_records), 4), dtype=torch.float32, device=dev)
+            self.v_k0 = torch.zeros_like(self.m_k0)
         self.m_w = [torch.zeros_like(w) for w in self.weights]
         self.v_w = [torch.zeros_like(w) for w in self.weights]
         self.m_b = [torch.zeros_like(b) for b in self.biases]
@@ -598,9 +611,10 @@ class FusedVoxurf:
             check(lib.pp_voxurf_k0_tv(ctypes.byref(self.scene), ptr(self.k0rec), ptr(self.g_k0rec), self.w_tv_k0,
                                       ptr(self.loss_buf[4:]), stream()), "voxurf_k0_tv")
 
-    def optimizer_step(self, deform=False):
+    def optimizer_step(self, deform=False, skip_k0=False):
         """Adam on everything that has a gradient.  deform=True: the live configuration of the reference (SDF grid
-        frozen, voxurf_coarse.py:136-138; feature grid, rgbnet and deformation network trained)."""
+        frozen, voxurf_coarse.py:136-138; feature grid, rgbnet and deformation network trained).  skip_k0: the feature
+        records were already updated (by the multi-GPU exchange kernel, which owns their Adam moments)."""
         b1, b2, lr_sdf, lr_k0, lr_net, eps = self.hp
         self.step += 1
         dense = 1 if self.adam_dense else 0
@@ -615,9 +629,10 @@ class FusedVoxurf:
                 check(lib.pp_voxurf_build_records(ctypes.byref(self.scene), ctypes.byref(self.cfg), ptr(self.sdf),
                                                   ptr(self.srec), s), "voxurf_build_records")
             # feature records: Adam over 3 V float4 records, gradient reset fused
-            check(lib.pp_voxel_adam(ptr(self.k0rec), ptr(self.g_k0rec), ptr(self.m_k0), ptr(self.v_k0),
-                                    3 * self.n_voxels, self.step, b1, b2, lr_k0, lr_k0, eps, 1 | (2 * dense), s),
-                  "voxel_adam")
+            if not skip_k0:
+                check(lib.pp_voxel_adam(ptr(self.k0rec), ptr(self.g_k0rec), ptr(self.m_k0), ptr(self.v_k0),
+                                        3 * self.n_voxels, self.step, b1, b2, lr_k0, lr_k0, eps, 1 | (2 * dense), s),
+                      "voxel_adam")
             for p, g, m, v in zip(self.weights + self.biases, self.g_w + self.g_b, self.m_w + self.m_b,
                                   self.v_w + self.v_b):
                 check(lib.pp_adam_upd(0, mode, ptr(p), ptr(g), ptr(m), ptr(v), None, p.numel(), self.step, b1, b2,
@@ -1015,28 +1030,116 @@ def smoke(dev):
 
 
 class DistributedVoxurf:
-    """FusedVoxurf replicated over the ranks of a process group: every rank marches its own ray batch, the flat
-    gradient buffer (SDF-record, feature-record and rgbnet gradients) is summed with ONE NCCL all-reduce over
-    NVLink, and every rank applies the same optimiser step.  The loss is the global mean over all ranks' rays,
-    so N ranks with batches b_0..b_{N-1} equal one rank stepping on their concatenation (up to fp32 summation
-    order)."""
+    """FusedVoxurf replicated over the ranks of a process group: every rank marches its own ray batch; the loss is
+    the global mean over all ranks' rays, so N ranks with batches b_0..b_{N-1} equal one rank stepping on their
+    concatenation (up to fp32 summation order).
 
-    def __init__(self, *args, group=None, **kw):
+    mode="nvls" (default when the system offers a multicast address): the feature records - 3/4 of the gradient
+    bytes and of the optimiser work - go through ONE kernel per rank that reduces the gradient slice in the NVSwitch
+    (multimem.ld_reduce), applies Adam to 1/world of the records (moments exist for the slice only) and multicasts
+    the result into every replica (pp_records_adam_exchange_mc); the SDF gradient records (coupled by the
+    finite-difference fold, so every rank needs all of them) and the rgbnet gradients are summed in place by the same
+    switch path without an optimiser (pp_allreduce_mc) and applied identically on every rank.  The cross-rank
+    barriers are flag words in peer memory (the first is fused into the exchange kernel and carries the global loss):
+    no NCCL call on the step.
+    mode="nccl": the flat gradient buffer (SDF-record, feature-record and rgbnet gradients) is summed with ONE NCCL
+    all-reduce and every rank applies the full optimiser step (the comparison baseline)."""
+
+    def __init__(self, sdf, k0, rgbnet_weights, rgbnet_biases, *args, group=None, mode="auto", **kw):
         import torch.distributed as dist
+        from . import dist as ppdist
         self.dist = dist
         self.group = group
         self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
         kw = dict(kw)
         kw["w_rgb"] = kw.get("w_rgb", 1.0) / self.world
-        self.eng = FusedVoxurf(*args, **kw)
+        auto = mode == "auto"
+        if auto:
+            mode = "nvls" if (self.world in (2, 4, 8) and ppdist.nvls_available() and not kw.get("w_tv_k0")) else "nccl"
+        if mode not in ("nvls", "nccl"):
+            raise ValueError("DistributedVoxurf: mode must be 'auto', 'nvls' or 'nccl'")
+        if self.world == 1:
+            mode = "nccl"
+        dev = sdf.device
+        if mode == "nvls":
+            if kw.get("w_tv_k0"):
+                raise RuntimeError("DistributedVoxurf(mode='nvls'): the k0 total-variation term needs mode='nccl'")
+            V = sdf.numel()
+            n_net = sum(w.numel() for w in rgbnet_weights) + sum(b.numel() for b in rgbnet_biases)
+            n_grad_rec = (16 * V + n_net + 3) // 4
+            ok, err = True, None
+            try:
+                self.k0_mem = ppdist.SymmRecords(3 * V, dev, group, self.world)
+                self.grad_mem = ppdist.SymmRecords(n_grad_rec, dev, group, self.world, zero=True)
+                n_sync = int(lib.pp_peer_sync_bytes()) // 16
+                self.sync_mem = ppdist.SymmRecords(n_sync, dev, group, self.world, zero=True)
+                ok = bool(self.k0_mem.multicast_ptr and self.grad_mem.multicast_ptr)
+            except Exception as e:      # no symmetric memory / multicast on this system
+                ok, err = False, e
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if not int(flag):
+                if not auto:
+                    raise RuntimeError("DistributedVoxurf(mode='nvls'): no multicast address (%s)" % (err,))
+                mode = "nccl"
+        self.mode = mode
+        if mode == "nvls":
+            b, e = ppdist.shard_bounds(3 * V, self.world, self.rank)
+            self.eng = FusedVoxurf(sdf, k0, rgbnet_weights, rgbnet_biases, *args, k0rec_buf=self.k0_mem.tensor,
+                                   grad_flat_buf=self.grad_mem.tensor, k0_moment_records=max(e - b, 1), **kw)
+            self.sync_ptrs = self.sync_mem.table
+            self.epoch = 0
+            self.loss_global = torch.zeros(2, dtype=torch.float32, device=dev)
+            self.n_net_rec = (n_net + 3) // 4
+            torch.cuda.synchronize(dev)
+            dist.barrier(group=group)
+        else:
+            self.eng = FusedVoxurf(sdf, k0, rgbnet_weights, rgbnet_biases, *args, **kw)
 
     def train_step(self, rays_o, rays_d, viewdirs, target, jitter=None):
         eng = self.eng
         eng.loss_buf.zero_()
         eng.backward_only(rays_o, rays_d, viewdirs, target, jitter)
-        if self.world > 1:
-            self.dist.all_reduce(eng.grad_flat, group=self.group)
-            self.dist.all_reduce(eng.loss_buf, group=self.group)
-        eng.optimizer_step()
-        eng.loss_buf[1] /= self.world          # [global w_rgb-weighted loss, global mean-squared error]
-        return eng.loss_buf
+        if self.mode == "nccl":
+            if self.world > 1:
+                self.dist.all_reduce(eng.grad_flat, group=self.group)
+                self.dist.all_reduce(eng.loss_buf, group=self.group)
+            eng.optimizer_step()
+            eng.loss_buf[1] /= self.world          # [global w_rgb-weighted loss, global mean-squared error]
+            return eng.loss_buf
+        b1, b2, _, lr_k0, _, eps = eng.hp
+        V = eng.n_voxels
+        g_mc = self.grad_mem.multicast_ptr
+        with torch.cuda.device(eng.device):
+            s = stream()
+            self.epoch += 1
+            # feature records: in-switch reduce-scatter + Adam on this rank's slice + multicast store; the prologue is
+            # the "all gradients complete" barrier and sums the ranks' [loss, mse]
+            check(lib.pp_records_adam_exchange_mc(ptr(eng.k0rec), self.k0_mem.multicast_ptr, g_mc + 16 * V,
+                                                  ptr(eng.m_k0), ptr(eng.v_k0), 3 * V, self.world, self.rank,
+                                                  eng.step + 1, b1, b2, lr_k0, eps, 1 if eng.adam_dense else 0,
+                                                  self.sync_ptrs, self.epoch, ptr(eng.loss_buf), ptr(self.loss_global),
+                                                  s), "records_adam_exchange_mc")
+            # SDF gradient records and rgbnet gradients: summed in place, applied identically by every rank below
+            check(lib.pp_allreduce_mc(g_mc, V, self.world, self.rank, self.sync_ptrs, s), "allreduce_mc")
+            check(lib.pp_allreduce_mc(g_mc + 64 * V, self.n_net_rec, self.world, self.rank, self.sync_ptrs, s),
+                  "allreduce_mc")
+            self.epoch += 1
+            check(lib.pp_peer_sync(self.sync_ptrs, self.world, self.rank, self.epoch, None, None, s), "peer_sync")
+        eng.optimizer_step(skip_k0=True)
+        eng.g_k0rec.zero_()
+        self.loss_global[1] /= self.world
+        return self.loss_global
+
+    def check_health(self):
+        """Raises if a cross-rank barrier of this rank ever timed out (see DistributedDVGO.check_health)."""
+        if self.mode == "nvls":
+            with torch.cuda.device(self.eng.device):
+                if lib.pp_peer_sync_timed_out(self.sync_ptrs[self.rank]) != 0:
+                    raise RuntimeError("DistributedVoxurf: a cross-rank barrier timed out on rank %d" % self.rank)
+
+    def close(self):
+        if self.mode == "nvls":
+            torch.cuda.synchronize(self.eng.device)
+            self.dist.barrier(group=self.group)

@@ -39,17 +39,25 @@ def main():
         batches.append(tuple(x.to(dev) for x in (o, d, v, t)))
     mk = lambda cls, **extra: cls(sdf.to(dev), k0.to(dev), [w.detach() for w in ws], [b.detach() for b in bs], mn, mx,
                                   **kw, **extra)
-    tr = mk(voxurf.DistributedVoxurf)
-    losses = []
-    for _ in range(K):
-        losses.append(float(tr.train_step(*batches[rank])[0]))
-    st = tr.eng.export_state()
-    # identical replicas
-    for key in ("sdf.grid", "k0.grid", "rgbnet.0.weight"):
-        mine = st[key].contiguous()
-        ref = mine.clone()
-        dist.broadcast(ref, 0)
-        assert torch.equal(mine, ref), "rank %d: %s differs from rank 0" % (rank, key)
+    from poseprobe_b200 import dist as ppdist
+    modes = ("nvls", "nccl") if ppdist.nvls_available() and world in (2, 4, 8) else ("nccl",)
+    results = {}
+    for mode in modes:
+        tr = mk(voxurf.DistributedVoxurf, mode=mode)
+        assert tr.mode == mode
+        losses = []
+        for _ in range(K):
+            losses.append(float(tr.train_step(*batches[rank])[0]))
+        st = tr.eng.export_state()
+        # identical replicas
+        for key in ("sdf.grid", "k0.grid", "rgbnet.0.weight"):
+            mine = st[key].contiguous()
+            ref = mine.clone()
+            dist.broadcast(ref, 0)
+            assert torch.equal(mine, ref), "%s, rank %d: %s differs from rank 0" % (mode, rank, key)
+        tr.check_health()
+        tr.close()
+        results[mode] = (st, losses)
     # one engine on the concatenated batch
     single = mk(voxurf.FusedVoxurf)
     cat = tuple(torch.cat([b[i] for b in batches]) for i in range(4))
@@ -58,16 +66,19 @@ def main():
         l1.append(float(single.train_step(*cat)[0]))
     s1 = single.export_state()
     if rank == 0:
-        for key in ("sdf.grid", "k0.grid", "rgbnet.0.weight", "rgbnet.3.weight"):
-            a, b = st[key], s1[key]
-            diff = (a - b).abs()
-            frac = float((diff > 1e-3).float().mean())
-            print("%s: %.6f of the elements differ by > 1e-3, max |diff| %.3e (|param| max %.3e)"
-                  % (key, frac, float(diff.max()), float(b.abs().max())))
-            # Adam turns a sign flip of a noise-level gradient into a full lr-sized step: allow a few stragglers
-            assert frac < 1e-3, key
-        print("dist_check_voxurf ok: world=%d losses %s vs single %s" % (world, ["%.6f" % x for x in losses],
-                                                                          ["%.6f" % x for x in l1]))
+        for mode, (st, losses) in results.items():
+            for key in ("sdf.grid", "k0.grid", "rgbnet.0.weight", "rgbnet.3.weight"):
+                a, b = st[key], s1[key]
+                diff = (a - b).abs()
+                frac = float((diff > 1e-3).float().mean())
+                print("%s %s: %.6f of the elements differ by > 1e-3, max |diff| %.3e (|param| max %.3e)"
+                      % (mode, key, frac, float(diff.max()), float(b.abs().max())))
+                # Adam turns a sign flip of a noise-level gradient into a full lr-sized step: allow a few stragglers
+                assert frac < 1e-3, (mode, key)
+            for a, b in zip(losses, l1):
+                assert abs(a - b) < 1e-4 * abs(b) + 1e-7, (mode, losses, l1)
+            print("dist_check_voxurf ok: %s world=%d losses %s vs single %s" % (mode, world, ["%.6f" % x for x in losses],
+                                                                             ["%.6f" % x for x in l1]))
     dist.destroy_process_group()
 
 
