@@ -1066,7 +1066,9 @@ class DistributedVoxurf:
             if kw.get("w_tv_k0"):
                 raise RuntimeError("DistributedVoxurf(mode='nvls'): the k0 total-variation term needs mode='nccl'")
             V = sdf.numel()
-            n_net = sum(w.numel() for w in rgbnet_weights) + sum(b.numel() for b in rgbnet_biases)
+            # (the engine holds the first layer permuted and zero-padded to FEAT_COLS input columns)
+            n_net = (rgbnet_weights[0].shape[0] * FEAT_COLS + sum(w.numel() for w in rgbnet_weights[1:]) +
+                     sum(b.numel() for b in rgbnet_biases))
             n_grad_rec = (16 * V + n_net + 3) // 4
             ok, err = True, None
             try:
@@ -1091,6 +1093,7 @@ class DistributedVoxurf:
             self.sync_ptrs = self.sync_mem.table
             self.epoch = 0
             self.loss_global = torch.zeros(2, dtype=torch.float32, device=dev)
+            assert self.eng.n_net == n_net
             self.n_net_rec = (n_net + 3) // 4
             torch.cuda.synchronize(dev)
             dist.barrier(group=group)

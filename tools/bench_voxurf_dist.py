@@ -32,7 +32,7 @@ def main():
     ws, bs = ops.rgbnet_from_sequential(net)
     kw = dict(stepsize=0.5, s_val=0.05, bg=0.0, sdf_alpha=10.0, sdf_beta=0.35, lr_sdf=1e-4, lr_k0=1e-2, lr_rgbnet=1e-3)
     args = (sdf.to(dev), k0.to(dev), [w.detach() for w in ws], [b.detach() for b in bs], [-1.0, -1, -1], [1.0, 1, 1])
-    tr = voxurf.DistributedVoxurf(*args, **kw) if world > 1 else None
+    tr = voxurf.DistributedVoxurf(*args, mode=os.environ.get('PP_VOXURF_DIST_MODE', 'auto'), **kw) if world > 1 else None
     eng = tr.eng if tr else voxurf.FusedVoxurf(*args, **kw)
     batches = []
     for b in range(4):
@@ -58,7 +58,7 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     # the all-reduce alone (device time)
     ar_ms = 0.0
-    if world > 1:
+    if world > 1 and tr.mode == "nccl":
         a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         dist.all_reduce(eng.grad_flat)
         torch.cuda.synchronize()
@@ -71,10 +71,11 @@ def main():
     if rank == 0:
         print(json.dumps({"workload": "Voxurf SDF fine stage (BASELINE configs[2]): 160^3 sdf + 12-ch k0 + rgbnet (tcgen05), "
                                       "8192 rays/step/GPU, fwd+bwd+Adam, ray-sharded dp%d, one flat gradient all-reduce" % world,
-                          "n_gpus": world, "train_rays_per_s": world * N / (float(ms) * 1e-3), "ms_per_step": float(ms),
+                          "mode": tr.mode if tr else "single", "n_gpus": world, "train_rays_per_s": world * N / (float(ms) * 1e-3), "ms_per_step": float(ms),
                           "allreduce_ms": ar_ms, "allreduce_bytes": eng.grad_flat.numel() * 4,
                           "samples_per_ray": eng.n_samples() / N}))
     if world > 1:
+        tr.close()
         dist.destroy_process_group()
 
 
