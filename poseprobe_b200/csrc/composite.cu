@@ -47,15 +47,28 @@ constexpr int kGroups = kWarp / kTile;        // rays loaded / stored per instru
 // row reads of lanes r and r+4 fall into different banks
 __device__ __forceinline__ int tile_at(int r, int c) { return r * kTile + (c ^ (((r >> 2) & 1) << 2)); }
 
-// Two warps per 32 rays.  Warp 0 ("chain") only runs the recurrence: per step it reads its ray's row of the input
-// tile, advances 8 samples, writes its T / weight rows - ~100 instructions, and a lone warp issues one dependent
-// instruction every ~5 cycles, so instructions on this warp ARE the kernel's duration.  Warp 1 ("memory") does all
-// the addressing: it knows every ray's [begin, end) (8 rays per lane, loaded once), loads tile i+3 from global memory
-// into registers (two steps before it is staged, so DRAM latency is covered), stages tile i+1 into shared memory and streams the
-// outputs of tile i-1 back as 32-byte sectors.  Tiles rotate through three shared-memory slots; one block barrier
-// per step orders the two warps.
+// 1 + kFwdMemWarps warps per 32 rays.  Warp 0 ("chain") only runs the recurrence: per step it reads its ray's row of
+// the input tile, advances 8 samples, writes its T / weight rows - ~100 instructions, and a lone warp issues one
+// dependent instruction every ~5 cycles, so instructions on this warp ARE the kernel's duration.  The memory warps do
+// all the addressing (each owns 8 / kFwdMemWarps of a step's 8 sector instructions): they know their rays'
+// [begin, end), copy tile t+3 from global memory STRAIGHT into shared memory with cp.async (zero-filled outside the
+// ray; it is needed two steps later, so DRAM latency is covered - register-staged loads were serialised by the compiler's
+// scoreboard waits, profiles/r2_results.md) and stream the outputs of tile t-1 back as 32-byte sectors.  Input tiles
+// rotate through five shared-memory slots, output tiles through three; one block barrier per step orders the warps.
 constexpr int kFwdMemWarps = 4;
 constexpr int kFwdK = kTile / kFwdMemWarps;   // sector instructions per memory warp and step
+constexpr int kInSlots = 5;
+
+template <int kBytes>
+__device__ __forceinline__ void cp_async_elem(void* dst_smem, const void* src, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst_smem));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(d), "l"(src), "n"(kBytes),
+               "r"(valid ? (uint32_t)kBytes : 0u)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
 
 template <typename scalar_t>
 __global__ void __launch_bounds__((1 + kFwdMemWarps) * kWarp)
@@ -63,7 +76,8 @@ alpha2weight_fwd_kernel(const scalar_t* __restrict__ alpha, int64_t n_rays,
                         scalar_t* __restrict__ weight, scalar_t* __restrict__ T_out,
                         scalar_t* __restrict__ alphainv_last, const int64_t* __restrict__ i_start,
                         int64_t* __restrict__ i_end) {
-  __shared__ scalar_t s_a[3][kWarp * kTile], s_T[3][kWarp * kTile], s_w[3][kWarp * kTile];
+  __shared__ __align__(16) scalar_t s_a[kInSlots][kWarp * kTile];
+  __shared__ __align__(16) scalar_t s_T[3][kWarp * kTile], s_w[3][kWarp * kTile];
   __shared__ int s_steps;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane / kTile, sl = lane % kTile;
   const bool chain = warp == 0;
@@ -90,30 +104,37 @@ alpha2weight_fwd_kernel(const scalar_t* __restrict__ alpha, int64_t n_rays,
   }
   __syncthreads();
   const int steps = s_steps;
-  scalar_t ld[2][kFwdK];        // memory warp: tiles in flight (tile t lives in ld[t & 1])
-  auto issue_loads = [&](int t, scalar_t (&dst)[kFwdK]) {
+  auto fetch = [&](int t) {      // tile t: global -> shared, asynchronously; one commit group per tile
 #pragma unroll
     for (int k = 0; k < kFwdK; ++k) {
       const int idx = bk[k] + t * kTile + sl;
-      dst[k] = (t < steps && idx < ek[k]) ? __ldcg(alpha + idx) : scalar_t(0);
+      const bool ok = t < steps && idx < ek[k];
+      cp_async_elem<sizeof(scalar_t)>(&s_a[t % kInSlots][tile_at(rk[k], sl)], alpha + (ok ? idx : 0), ok);
+    }
+    cp_async_commit();
+  };
+  auto flush = [&](int t) {      // outputs of tile t: shared -> global
+#pragma unroll
+    for (int k = 0; k < kFwdK; ++k) {
+      const int idx = bk[k] + t * kTile + sl;
+      if (idx < ek[k]) {
+        T_out[idx] = s_T[t % 3][tile_at(rk[k], sl)];
+        weight[idx] = s_w[t % 3][tile_at(rk[k], sl)];
+      }
     }
   };
-  auto stage = [&](int t, const scalar_t (&src)[kFwdK]) {
-#pragma unroll
-    for (int k = 0; k < kFwdK; ++k) s_a[t % 3][tile_at(rk[k], sl)] = src[k];
-  };
   if (!chain) {
-    issue_loads(0, ld[0]);
-    issue_loads(1, ld[1]);
-    stage(0, ld[0]);
-    issue_loads(2, ld[0]);      // from here on: tile t lives in ld[t & 1] until it is staged
+    fetch(0);
+    fetch(1);
+    fetch(2);
+    cp_async_wait<2>();          // tile 0 has landed
   }
   __syncthreads();
   int pos = begin, cut = -1;
   float T_cum = 1.f;
   for (int t = 0; t < steps; ++t) {
     if (chain) {
-      const scalar_t* a_row = s_a[t % 3];
+      const scalar_t* a_row = s_a[t % kInSlots];
       scalar_t a[kTile];
 #pragma unroll
       for (int j = 0; j < kTile; ++j) a[j] = a_row[tile_at(lane, j)];
@@ -137,32 +158,13 @@ alpha2weight_fwd_kernel(const scalar_t* __restrict__ alpha, int64_t n_rays,
       }
       pos += kTile;
     } else {
-      // tile t+1 -> shared memory (its loads were issued two steps ago), tile t+3 -> registers, tile t-1 -> global
-      if (((t + 1) & 1) == 0) stage(t + 1, ld[0]); else stage(t + 1, ld[1]);
-      if (t > 0) {
-#pragma unroll
-        for (int k = 0; k < kFwdK; ++k) {
-          const int idx = bk[k] + (t - 1) * kTile + sl;
-          if (idx < ek[k]) {
-            T_out[idx] = s_T[(t - 1) % 3][tile_at(rk[k], sl)];
-            weight[idx] = s_w[(t - 1) % 3][tile_at(rk[k], sl)];
-          }
-        }
-      }
-      if (((t + 1) & 1) == 0) issue_loads(t + 3, ld[0]); else issue_loads(t + 3, ld[1]);
+      fetch(t + 3);              // slot (t + 3) % 5: last read by the chain warp in step t - 2
+      if (t > 0) flush(t - 1);
+      cp_async_wait<2>();        // tile t + 1 has landed (tiles t + 2, t + 3 may still be in flight)
     }
     __syncthreads();
   }
-  if (!chain && steps > 0) {
-#pragma unroll
-    for (int k = 0; k < kFwdK; ++k) {
-      const int idx = bk[k] + (steps - 1) * kTile + sl;
-      if (idx < ek[k]) {
-        T_out[idx] = s_T[(steps - 1) % 3][tile_at(rk[k], sl)];
-        weight[idx] = s_w[(steps - 1) % 3][tile_at(rk[k], sl)];
-      }
-    }
-  }
+  if (!chain && steps > 0) flush(steps - 1);
   if (live) {
     if (cut >= 0) i_end[ray] = cut;  // otherwise i_end already holds i_e_max (or 0 for an empty ray)
     alphainv_last[ray] = T_cum;
@@ -173,9 +175,9 @@ alpha2weight_fwd_kernel(const scalar_t* __restrict__ alpha, int64_t n_rays,
 // Walks each ray downwards from its (early-terminated) end in tiles [top - 8, top).  The recurrence
 // back_cum += grad_weights*weight is an FMA in scalar_t narrowed to float (reference :674) - 8 dependent FMAs per
 // step on the chain warp, which hands the value of back_cum in front of every sample to the memory warps through
-// shared memory.  Everything else - the loads of the four inputs, and grad = gw*T - back/(1-alpha+1e-10) with its
-// double-precision quotient, which is not part of the recurrence - is done by kBwdMemWarps memory warps in the
-// coalesced layout (each owns 8 / kBwdMemWarps of the step's 8 sector instructions).
+// shared memory.  Everything else - the cp.async copies of the four inputs, and grad = gw*T - back/(1-alpha+1e-10)
+// with its double-precision quotient, which is not part of the recurrence - is done by kBwdMemWarps memory warps in
+// the coalesced layout (each owns 8 / kBwdMemWarps of the step's 8 sector instructions).
 constexpr int kBwdMemWarps = 8;
 constexpr int kBwdK = kTile / kBwdMemWarps;   // sector instructions per memory warp and step
 
@@ -186,8 +188,8 @@ alpha2weight_bwd_kernel(const scalar_t* __restrict__ alpha, const scalar_t* __re
                         const int64_t* __restrict__ i_start, const int64_t* __restrict__ i_end,
                         int64_t n_rays, const scalar_t* __restrict__ grad_weights,
                         const scalar_t* __restrict__ grad_last, scalar_t* __restrict__ grad) {
-  __shared__ scalar_t s_in[3][4][kWarp * kTile];   // [slot][gw, w, T, alpha]
-  __shared__ float s_back[3][kWarp * kTile];       // back_cum in front of every sample
+  __shared__ __align__(16) scalar_t s_in[kInSlots][4][kWarp * kTile];   // [slot][gw, w, T, alpha]
+  __shared__ __align__(16) float s_back[3][kWarp * kTile];              // back_cum in front of every sample
   __shared__ int s_steps;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane / kTile, sl = lane % kTile;
   const bool chain = warp == 0;
@@ -218,21 +220,16 @@ alpha2weight_bwd_kernel(const scalar_t* __restrict__ alpha, const scalar_t* __re
   const int steps = s_steps;
   const scalar_t* src[4] = {grad_weights, weight, T, alpha};
   // tile t of a ray covers samples [top - 8 (t + 1), top - 8 t); column c of the tile is sample top - 8 (t + 1) + c
-  scalar_t ld[2][4][kBwdK];
-  auto issue_loads = [&](int t, scalar_t (&dst)[4][kBwdK]) {
+  auto fetch = [&](int t) {
 #pragma unroll
     for (int q = 0; q < kBwdK; ++q) {
       const int idx = tk[q] - (t + 1) * kTile + sl;
       const bool ok = t < steps && idx >= bk[q];
 #pragma unroll
-      for (int f = 0; f < 4; ++f) dst[f][q] = ok ? __ldcg(src[f] + idx) : scalar_t(0);
+      for (int f = 0; f < 4; ++f)
+        cp_async_elem<sizeof(scalar_t)>(&s_in[t % kInSlots][f][tile_at(rk[q], sl)], src[f] + (ok ? idx : 0), ok);
     }
-  };
-  auto stage = [&](int t, const scalar_t (&v)[4][kBwdK]) {
-#pragma unroll
-    for (int f = 0; f < 4; ++f)
-#pragma unroll
-      for (int q = 0; q < kBwdK; ++q) s_in[t % 3][f][tile_at(rk[q], sl)] = v[f][q];
+    cp_async_commit();
   };
   auto finish = [&](int t) {     // grad of tile t from the staged inputs and the chain warp's back_cum values
 #pragma unroll
@@ -240,7 +237,7 @@ alpha2weight_bwd_kernel(const scalar_t* __restrict__ alpha, const scalar_t* __re
       const int idx = tk[q] - (t + 1) * kTile + sl;
       if (idx >= bk[q]) {
         const int at = tile_at(rk[q], sl);
-        const scalar_t gw = s_in[t % 3][0][at], Tv = s_in[t % 3][2][at], av = s_in[t % 3][3][at];
+        const scalar_t gw = s_in[t % kInSlots][0][at], Tv = s_in[t % kInSlots][2][at], av = s_in[t % kInSlots][3][at];
         // grad = gw*T - back/(1-alpha+1e-10): product in scalar_t, quotient and difference in double
         const scalar_t gT = mul_rn(gw, Tv);
         const scalar_t one_minus = scalar_t(1) - av;
@@ -250,10 +247,10 @@ alpha2weight_bwd_kernel(const scalar_t* __restrict__ alpha, const scalar_t* __re
     }
   };
   if (!chain) {
-    issue_loads(0, ld[0]);
-    issue_loads(1, ld[1]);
-    stage(0, ld[0]);
-    issue_loads(2, ld[0]);      // from here on: tile t lives in ld[t & 1] until it is staged
+    fetch(0);
+    fetch(1);
+    fetch(2);
+    cp_async_wait<2>();
   }
   __syncthreads();
   int top = top0;
@@ -262,8 +259,8 @@ alpha2weight_bwd_kernel(const scalar_t* __restrict__ alpha, const scalar_t* __re
       scalar_t gw[kTile], wv[kTile];
 #pragma unroll
       for (int j = 0; j < kTile; ++j) {
-        gw[j] = s_in[t % 3][0][tile_at(lane, j)];
-        wv[j] = s_in[t % 3][1][tile_at(lane, j)];
+        gw[j] = s_in[t % kInSlots][0][tile_at(lane, j)];
+        wv[j] = s_in[t % kInSlots][1][tile_at(lane, j)];
       }
       const int base = top - kTile;
       float bj[kTile];
@@ -277,14 +274,9 @@ alpha2weight_bwd_kernel(const scalar_t* __restrict__ alpha, const scalar_t* __re
       for (int j = 0; j < kTile; ++j) s_back[t % 3][tile_at(lane, j)] = bj[j];
       if (top > begin) top -= kTile;
     } else {
-      if (((t + 1) & 1) == 0) {
-        stage(t + 1, ld[0]);
-        issue_loads(t + 3, ld[0]);
-      } else {
-        stage(t + 1, ld[1]);
-        issue_loads(t + 3, ld[1]);
-      }
+      fetch(t + 3);              // slot (t + 3) % 5: the chain warp reads slot t % 5, finish(t - 1) slot (t - 1) % 5
       if (t > 0) finish(t - 1);
+      cp_async_wait<2>();
     }
     __syncthreads();
   }
