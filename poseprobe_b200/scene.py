@@ -104,7 +104,8 @@ def sample_depth_from_pdf(weights, n_samples_coarse, n_samples_fine, depth_range
     assert N == n_samples_coarse
     dev = weights.device
     if grid is None:
-        grid = torch.linspace(0, 1, n_samples_fine + 1) if det else torch.rand(n_samples_fine + 1)
+        # renderer.py:717-721: linspace on the model's device, the random grid drawn on the CPU and moved over
+        grid = torch.linspace(0, 1, n_samples_fine + 1, device=dev) if det else torch.rand(n_samples_fine + 1)
     grid = grid.to(dev, torch.float32)
     unif = (0.5 * (grid[:-1] + grid[1:])).contiguous()
     out = torch.empty(B, R, n_samples_fine, 1, device=dev, dtype=torch.float32)
