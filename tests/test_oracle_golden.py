@@ -334,3 +334,20 @@ def test_scene_branch_compositing_oracle_matches_the_references_own_code():
         assert torch.equal(det, t("fine_det"))
         rnd, _ = bgnerf_cpu.sample_depth_from_pdf(w, N, Nf, rng, t("fine_grid"))
         assert torch.equal(rnd, t("fine_rand"))
+
+
+def test_dense_compositing_oracle_matches_the_references_own_dvgo_forward():
+    """oracle.get_ray_marching_ray (lib/dvgo_ori.py:478-485) against tests/golden/dvgo_module.npz = the reference's own
+    `DirectVoxGO.forward` (make_golden_dvgo_module.py): weights and alphainv_cum recomputed from the stored raw_alpha,
+    for both stored configurations (the GPU tier replays the whole module against the same file)."""
+    import os
+    import numpy as np
+    import torch
+    from oracle import oracle
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "dvgo_module.npz"))
+    for tag in ("a", "b"):
+        alpha = torch.from_numpy(g[tag + "_out_raw_alpha"])
+        w, c = oracle.get_ray_marching_ray(alpha)
+        torch.testing.assert_close(w, torch.from_numpy(g[tag + "_out_weights"]), rtol=1e-6, atol=1e-8)
+        torch.testing.assert_close(c, torch.from_numpy(g[tag + "_out_alphainv_cum"]), rtol=1e-6, atol=1e-8)
+        assert torch.equal(w > 1e-4, torch.from_numpy(g[tag + "_out_mask"]))
