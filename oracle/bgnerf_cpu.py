@@ -39,7 +39,7 @@ def sample_depth_from_pdf(weights, n_samples_coarse, n_samples_fine, depth_range
     cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], dim=-1)
     unif = (0.5 * (grid[:-1] + grid[1:])).repeat(*cdf.shape[:-1], 1)
     idx = torch.searchsorted(cdf, unif, right=True)
-    depth_bin = torch.linspace(depth_min, depth_max, n_samples_coarse + 1).repeat(*cdf.shape[:-1], 1)
+    depth_bin = torch.linspace(depth_min, depth_max, n_samples_coarse + 1, device=weights.device).repeat(*cdf.shape[:-1], 1)
     lo, hi = (idx - 1).clamp(min=0), idx.clamp(max=n_samples_coarse)
     depth_low, depth_high = depth_bin.gather(2, lo), depth_bin.gather(2, hi)
     cdf_low, cdf_high = cdf.gather(2, lo), cdf.gather(2, hi)

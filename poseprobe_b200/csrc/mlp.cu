@@ -80,7 +80,10 @@ rgbnet_forward_kernel(MlpParams P, const __nv_bfloat16* __restrict__ x, int64_t 
   float* sBias = reinterpret_cast<float*>(smem + off);
   off += L * kMlpWidth * 4;
   uint64_t* sBar = reinterpret_cast<uint64_t*>(smem + off);
-  uint32_t* sTmem = reinterpret_cast<uint32_t*>(smem + off + 16);
+  // (behind ALL kPipes mbarriers: at + 16 it shared its bytes with the third pipeline's barrier, and the deallocation
+  // at the end read whatever state that barrier was in - cudaErrorTensorMemoryLeak once per few thousand launches)
+  uint32_t* sTmem = reinterpret_cast<uint32_t*>(smem + off + 8 * kPipes);
+  static_assert(8 * kPipes + 4 <= 64, "the host reserves 64 bytes for the barriers and the TMEM base");
 
   // ---- prologue (whole CTA): weights -> bf16 canonical layout, biases, TMEM, mbarriers ----
   for (int l = 0; l < L; ++l) {
@@ -126,7 +129,8 @@ rgbnet_forward_kernel(MlpParams P, const __nv_bfloat16* __restrict__ x, int64_t 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *sTmem + g * kMlpWidth;   // this pipeline's accumulator: 128 columns, logits in the first 16
+  const uint32_t tmem_base = *sTmem;
+  const uint32_t tmem = tmem_base + g * kMlpWidth;   // this pipeline's accumulator: 128 columns, logits in the first 16
   const uint32_t bar = smem_u32(sBar + g);
   uint32_t phase = 0;
   const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
@@ -269,8 +273,10 @@ rgbnet_forward_kernel(MlpParams P, const __nv_bfloat16* __restrict__ x, int64_t 
 
   tc_fence_before();
   __syncthreads();
-  if (tid < 32)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*sTmem), "r"(512) : "memory");
+  if (tid < 32) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
 }
 
 // rows of pp_warpnet_forward_packed for free-standing points: x fp32 [n,3] -> fp16 [4n,16]

@@ -554,8 +554,10 @@ rgbnet_backward2_kernel(MlpBwdParams P, const __nv_bfloat16* __restrict__ x, con
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0)
+  if (warp == 0) {
+    tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  }
 }
 
 // fp32 [n,d0] rows -> bf16 [n,k0p] rows (zero padded): one thread per 8 output columns

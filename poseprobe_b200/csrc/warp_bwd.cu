@@ -514,8 +514,10 @@ warpnet_backward_kernel(WarpBwdParams P, const __half* __restrict__ x, const flo
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0)
+  if (warp == 0) {
+    tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  }
 }
 
 }  // namespace pp

@@ -234,6 +234,11 @@ class DirectVoxGO(nn.Module):
                   for _ in range(rgbnet_depth - 2)],
                 nn.Linear(rgbnet_width, 3))
             nn.init.constant_(self.rgbnet[-1].bias, 0)
+        # rgbnet_tensor_cores=True (kwarg, default False): run the colour head on the tcgen05 MLP kernels (width 128,
+        # depth 3 or 4) - bf16 operands, so ~1e-2 from the fp32 nn.Sequential the parity tests compare at 1e-5
+        self.rgbnet_tensor_cores = bool(kwargs.get('rgbnet_tensor_cores', False))
+        if self.rgbnet_tensor_cores and (rgbnet_dim <= 0 or rgbnet_width != 128 or rgbnet_depth not in (3, 4)):
+            raise NotImplementedError("rgbnet_tensor_cores: rgbnet_dim > 0, rgbnet_width=128, rgbnet_depth 3 or 4")
         self.mask_cache_path = mask_cache_path
         self.mask_cache_thres = mask_cache_thres
         self.mask_cache = None
@@ -367,7 +372,12 @@ class DirectVoxGO(nn.Module):
             xyz_emb = torch.cat([rays_xyz, xyz_emb.sin(), xyz_emb.cos()], -1)
             ray_of = torch.arange(weights.shape[0], device=weights.device)[:, None].expand_as(mask)[mask]
             rgb_feat = torch.cat([k0_view, xyz_emb, viewdirs_emb[ray_of]], -1)
-            logit_m = self.rgbnet(rgb_feat)
+            if self.rgbnet_tensor_cores:
+                # tcgen05 colour MLP (bf16 operands, fp32 accumulation; forward + fused backward, csrc/mlp*.cu)
+                ws, bs = ops.rgbnet_from_sequential(self.rgbnet)
+                logit_m = ops.rgbnet(rgb_feat.contiguous(), ws, bs, sigmoid=False)
+            else:
+                logit_m = self.rgbnet(rgb_feat)
             if not self.rgbnet_direct:
                 logit_m = logit_m + k0_diffuse
             rgb_logit = torch.zeros(*weights.shape, 3, device=weights.device, dtype=weights.dtype)

@@ -84,6 +84,19 @@ def test_fine_rgbnet_mask_cache_replays_the_reference(cuda):
     # (the rgbnet of this non-live module is nn.Sequential: cuBLAS fp32 / TF32-off, so 1e-4 on its gradients)
     _check("b", g, m, ret, params, cuda, grad_rel=1e-4)
     assert isinstance(pp.DirectVoxGO, type)
+    # the same module with its colour head on the tcgen05 MLP kernels: bf16 operands -> 2e-2 on colours, and the
+    # gradients still point the same way
+    ret = m(t("rays_o"), t("rays_d"), t("viewdirs"), global_step=None, **RK)        # (fresh graph)
+    m.rgbnet_tensor_cores = True
+    ret_tc = m(t("rays_o"), t("rays_d"), t("viewdirs"), global_step=None, **RK)
+    torch.testing.assert_close(ret_tc["rgb_marched"], ret["rgb_marched"], rtol=0, atol=2e-2)
+    assert torch.equal(ret_tc["weights"], ret["weights"])
+    tgt = torch.rand_like(ret["rgb_marched"])
+    g_tc = torch.autograd.grad(((ret_tc["rgb_marched"] - tgt) ** 2).mean(), [m.k0, m.rgbnet[0].weight])
+    g_32 = torch.autograd.grad(((ret["rgb_marched"] - tgt) ** 2).mean(), [m.k0, m.rgbnet[0].weight])
+    for a, b in zip(g_tc, g_32):
+        cos = float((a * b).sum() / (a.norm() * b.norm() + 1e-30))
+        assert cos > 0.99, cos
 
 
 @pytest.mark.parametrize("shape", [(1, 1), (3, 2), (7, 31), (5, 33), (64, 226), (257, 558)])
