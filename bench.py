@@ -335,7 +335,10 @@ def run_ours(args, rank, world, local_rank):
                 extra_configs[key] = fn(dev, rank, world)
             except Exception as e:
                 extra_configs[key] = {"error": str(e)[:200]}
-                torch.cuda.empty_cache()
+                try:
+                    torch.cuda.empty_cache()
+                except Exception:
+                    pass
 
     if rank != 0:
         if trainer is not None:
@@ -432,12 +435,18 @@ def run_ours(args, rank, world, local_rank):
         line["fine_stage"] = fine_dist
     line.update(extra_configs)
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline()
-    print(json.dumps(line))
-    if trainer is not None:
-        trainer.close()
-    if world > 1:
-        dist.destroy_process_group()
+        try:
+            line["cpu_baseline"] = cpu_baseline()
+        except Exception as e:
+            line["cpu_baseline"] = {"error": str(e)[:200]}
+    print(json.dumps(line), flush=True)
+    try:
+        if trainer is not None:
+            trainer.close()
+        if world > 1:
+            dist.destroy_process_group()
+    except Exception as e:      # the line is out: a teardown problem must not turn the run into a failure
+        print("bench.py: teardown: %s" % str(e)[:200], file=sys.stderr)
 
 
 def fine_stage_bench(dev):
