@@ -31,9 +31,9 @@ RAYS = 8192
 STEPSIZE = 0.5
 N_BATCHES = 8          # distinct ray batches cycled through the timed region
 # dram__bytes_read.sum + dram__bytes_write.sum of one train-mode march launch, from the committed ncu
-# capture profiles/r1_march_train_full.txt (per launch, like `achieved`)
-MARCH_DRAM_TRAFFIC_BYTES = 350.9e6
-MARCH_TRAFFIC_PROFILE = "profiles/r1f_dvgo_march_kernel_full.txt"
+# capture of this round (per launch, like `achieved`; round 1 measured the same 350.8-350.9 MB)
+MARCH_DRAM_TRAFFIC_BYTES = 350.8e6
+MARCH_TRAFFIC_PROFILE = "profiles/r2_dvgo_march_kernel_full.txt"
 XYZ_MIN, XYZ_MAX = [-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]
 
 
