@@ -5,7 +5,7 @@
  * HBM: sample_pts_on_rays -> DenseGrid(density) -> raw2alpha -> alpha2weight -> DenseGrid(k0) ->
  * sigmoid -> segment_coo sums -> loss -> autograd of all of it -> (masked) Adam
  * (lib/dvgo_ori.py:289-379 for the dense pure-PyTorch form, lib/voxurf_coarse.py:661-695 and
- * :1094-1222 for the CUDA-sampler form, lib/cuda/*.cu for the kernels).  The entry points below
+ * :1094-1222 for the CUDA-sampler form, the .cu files under lib/cuda for the kernels).  The entry points below
  * compute the same quantities with ONE kernel per direction: a warp marches a ray, gathers 16-byte
  * voxel records, composites with a warp scan, and (backward) scatters with 128-bit reductions.  No
  * per-sample tensor ever reaches HBM.
