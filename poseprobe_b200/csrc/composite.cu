@@ -40,15 +40,18 @@ __global__ void segment_bounds_kernel(const int64_t* __restrict__ ray_id, int64_
 // row, runs 8 steps of the chain in registers, writes T and weight rows back, and the groups store them as sectors.
 // The loads of the next tile are in flight during the chain.  Samples past the termination get the reference's fill
 // values (T = 1, weight = 0) from the same streaming stores, so no separate fill pass over [M] is needed.
-constexpr int kTile = 8;                      // samples per ray and step
-constexpr int kGroups = kWarp / kTile;        // rays loaded / stored per instruction
-
-// row r, column c of a [32][kTile] tile; rows whose bit 2 is set swap their two 4-element halves so that the 128-bit
-// row reads of lanes r and r+4 fall into different banks
-__device__ __forceinline__ int tile_at(int r, int c) { return r * kTile + (c ^ (((r >> 2) & 1) << 2)); }
+// Tile geometry: kT samples per ray and step (16 for fp32, 8 for fp64), kWarp / kT rays per sector instruction.
+// row r, column c of a [32][kT] tile.  A lane reads its whole row with 128-bit loads, 8 lanes per bank cycle; rows that
+// would meet in the same banks (32 / kT rows apart) get their 4-element groups XOR-permuted by the row's index within
+// that cycle, so the row reads and the column-wise staging stores are both conflict free.
+template <int kT>
+__device__ __forceinline__ int tile_at(int r, int c) {
+  constexpr int kRowsPerCycle = 32 / kT, kQuads = kT / 4;
+  return r * kT + (c ^ (((r / kRowsPerCycle) % kQuads) << 2));
+}
 
 // 1 + kFwdMemWarps warps per 32 rays.  Warp 0 ("chain") only runs the recurrence: per step it reads its ray's row of
-// the input tile, advances 8 samples, writes its T / weight rows - ~100 instructions, and a lone warp issues one
+// the input tile, advances kT samples, writes its T / weight rows - ~100 instructions, and a lone warp issues one
 // dependent instruction every ~5 cycles, so instructions on this warp ARE the kernel's duration.  The memory warps do
 // all the addressing (each owns 8 / kFwdMemWarps of a step's 8 sector instructions): they know their rays'
 // [begin, end), copy tile t+3 from global memory STRAIGHT into shared memory with cp.async (zero-filled outside the
@@ -56,7 +59,6 @@ __device__ __forceinline__ int tile_at(int r, int c) { return r * kTile + (c ^ (
 // scoreboard waits, profiles/r2_results.md) and stream the outputs of tile t-1 back as 32-byte sectors.  Input tiles
 // rotate through five shared-memory slots, output tiles through three; one block barrier per step orders the warps.
 constexpr int kFwdMemWarps = 4;
-constexpr int kFwdK = kTile / kFwdMemWarps;   // sector instructions per memory warp and step
 constexpr int kInSlots = 5;
 
 template <int kBytes>
@@ -70,16 +72,18 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int kPending>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
 
-template <typename scalar_t>
+template <typename scalar_t, int kT>
 __global__ void __launch_bounds__((1 + kFwdMemWarps) * kWarp)
 alpha2weight_fwd_kernel(const scalar_t* __restrict__ alpha, int64_t n_rays,
                         scalar_t* __restrict__ weight, scalar_t* __restrict__ T_out,
                         scalar_t* __restrict__ alphainv_last, const int64_t* __restrict__ i_start,
                         int64_t* __restrict__ i_end) {
-  __shared__ __align__(16) scalar_t s_a[kInSlots][kWarp * kTile];
-  __shared__ __align__(16) scalar_t s_T[3][kWarp * kTile], s_w[3][kWarp * kTile];
+  constexpr int kGroups = kWarp / kT;            // rays per sector instruction
+  constexpr int kFwdK = kT / kFwdMemWarps;       // sector instructions per memory warp and step
+  __shared__ __align__(16) scalar_t s_a[kInSlots][kWarp * kT];
+  __shared__ __align__(16) scalar_t s_T[3][kWarp * kT], s_w[3][kWarp * kT];
   __shared__ int s_steps;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane / kTile, sl = lane % kTile;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane / kT, sl = lane % kT;
   const bool chain = warp == 0;
   const int64_t ray0 = blockIdx.x * (int64_t)kWarp;
   // chain warp: own ray.  (sample indices fit 32 bits: the entry point rejects n_pts > INT32_MAX)
@@ -97,7 +101,7 @@ alpha2weight_fwd_kernel(const scalar_t* __restrict__ alpha, int64_t n_rays,
     ek[k] = ok ? static_cast<int>(i_end[r]) : 0;
   }
   if (chain) {
-    int steps = (end - begin + kTile - 1) / kTile;
+    int steps = (end - begin + kT - 1) / kT;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) steps = max(steps, __shfl_xor_sync(kFull, steps, o));
     if (lane == 0) s_steps = steps;
@@ -107,19 +111,19 @@ alpha2weight_fwd_kernel(const scalar_t* __restrict__ alpha, int64_t n_rays,
   auto fetch = [&](int t) {      // tile t: global -> shared, asynchronously; one commit group per tile
 #pragma unroll
     for (int k = 0; k < kFwdK; ++k) {
-      const int idx = bk[k] + t * kTile + sl;
+      const int idx = bk[k] + t * kT + sl;
       const bool ok = t < steps && idx < ek[k];
-      cp_async_elem<sizeof(scalar_t)>(&s_a[t % kInSlots][tile_at(rk[k], sl)], alpha + (ok ? idx : 0), ok);
+      cp_async_elem<sizeof(scalar_t)>(&s_a[t % kInSlots][tile_at<kT>(rk[k], sl)], alpha + (ok ? idx : 0), ok);
     }
     cp_async_commit();
   };
   auto flush = [&](int t) {      // outputs of tile t: shared -> global
 #pragma unroll
     for (int k = 0; k < kFwdK; ++k) {
-      const int idx = bk[k] + t * kTile + sl;
+      const int idx = bk[k] + t * kT + sl;
       if (idx < ek[k]) {
-        T_out[idx] = s_T[t % 3][tile_at(rk[k], sl)];
-        weight[idx] = s_w[t % 3][tile_at(rk[k], sl)];
+        T_out[idx] = s_T[t % 3][tile_at<kT>(rk[k], sl)];
+        weight[idx] = s_w[t % 3][tile_at<kT>(rk[k], sl)];
       }
     }
   };
@@ -135,12 +139,12 @@ alpha2weight_fwd_kernel(const scalar_t* __restrict__ alpha, int64_t n_rays,
   for (int t = 0; t < steps; ++t) {
     if (chain) {
       const scalar_t* a_row = s_a[t % kInSlots];
-      scalar_t a[kTile];
+      scalar_t a[kT];
 #pragma unroll
-      for (int j = 0; j < kTile; ++j) a[j] = a_row[tile_at(lane, j)];
-      scalar_t Tj[kTile], wj[kTile];
+      for (int j = 0; j < kT; ++j) a[j] = a_row[tile_at<kT>(lane, j)];
+      scalar_t Tj[kT], wj[kT];
 #pragma unroll
-      for (int j = 0; j < kTile; ++j) {
+      for (int j = 0; j < kT; ++j) {
         const bool in = cut < 0 && pos + j < end;
         Tj[j] = in ? static_cast<scalar_t>(T_cum) : scalar_t(1);
         wj[j] = in ? T_cum * a[j] : scalar_t(0);
@@ -152,11 +156,11 @@ alpha2weight_fwd_kernel(const scalar_t* __restrict__ alpha, int64_t n_rays,
         }
       }
 #pragma unroll
-      for (int j = 0; j < kTile; ++j) {
-        s_T[t % 3][tile_at(lane, j)] = Tj[j];
-        s_w[t % 3][tile_at(lane, j)] = wj[j];
+      for (int j = 0; j < kT; ++j) {
+        s_T[t % 3][tile_at<kT>(lane, j)] = Tj[j];
+        s_w[t % 3][tile_at<kT>(lane, j)] = wj[j];
       }
-      pos += kTile;
+      pos += kT;
     } else {
       fetch(t + 3);              // slot (t + 3) % 5: last read by the chain warp in step t - 2
       if (t > 0) flush(t - 1);
@@ -179,19 +183,20 @@ alpha2weight_fwd_kernel(const scalar_t* __restrict__ alpha, int64_t n_rays,
 // with its double-precision quotient, which is not part of the recurrence - is done by kBwdMemWarps memory warps in
 // the coalesced layout (each owns 8 / kBwdMemWarps of the step's 8 sector instructions).
 constexpr int kBwdMemWarps = 8;
-constexpr int kBwdK = kTile / kBwdMemWarps;   // sector instructions per memory warp and step
 
-template <typename scalar_t>
+template <typename scalar_t, int kT>
 __global__ void __launch_bounds__((1 + kBwdMemWarps) * kWarp)
 alpha2weight_bwd_kernel(const scalar_t* __restrict__ alpha, const scalar_t* __restrict__ weight,
                         const scalar_t* __restrict__ T, const scalar_t* __restrict__ alphainv_last,
                         const int64_t* __restrict__ i_start, const int64_t* __restrict__ i_end,
                         int64_t n_rays, const scalar_t* __restrict__ grad_weights,
                         const scalar_t* __restrict__ grad_last, scalar_t* __restrict__ grad) {
-  __shared__ __align__(16) scalar_t s_in[kInSlots][4][kWarp * kTile];   // [slot][gw, w, T, alpha]
-  __shared__ __align__(16) float s_back[3][kWarp * kTile];              // back_cum in front of every sample
+  constexpr int kGroups = kWarp / kT;
+  constexpr int kBwdK = kT / kBwdMemWarps;       // sector instructions per memory warp and step
+  __shared__ __align__(16) scalar_t s_in[kInSlots][4][kWarp * kT];   // [slot][gw, w, T, alpha]
+  __shared__ __align__(16) float s_back[3][kWarp * kT];              // back_cum in front of every sample
   __shared__ int s_steps;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane / kTile, sl = lane % kTile;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane / kT, sl = lane % kT;
   const bool chain = warp == 0;
   const int64_t ray0 = blockIdx.x * (int64_t)kWarp;
   const int64_t ray = ray0 + lane;
@@ -211,7 +216,7 @@ alpha2weight_bwd_kernel(const scalar_t* __restrict__ alpha, const scalar_t* __re
     tk[q] = ok ? static_cast<int>(i_end[r]) : 0;
   }
   if (chain) {
-    int steps = (max(top0 - begin, 0) + kTile - 1) / kTile;
+    int steps = (max(top0 - begin, 0) + kT - 1) / kT;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) steps = max(steps, __shfl_xor_sync(kFull, steps, o));
     if (lane == 0) s_steps = steps;
@@ -223,20 +228,20 @@ alpha2weight_bwd_kernel(const scalar_t* __restrict__ alpha, const scalar_t* __re
   auto fetch = [&](int t) {
 #pragma unroll
     for (int q = 0; q < kBwdK; ++q) {
-      const int idx = tk[q] - (t + 1) * kTile + sl;
+      const int idx = tk[q] - (t + 1) * kT + sl;
       const bool ok = t < steps && idx >= bk[q];
 #pragma unroll
       for (int f = 0; f < 4; ++f)
-        cp_async_elem<sizeof(scalar_t)>(&s_in[t % kInSlots][f][tile_at(rk[q], sl)], src[f] + (ok ? idx : 0), ok);
+        cp_async_elem<sizeof(scalar_t)>(&s_in[t % kInSlots][f][tile_at<kT>(rk[q], sl)], src[f] + (ok ? idx : 0), ok);
     }
     cp_async_commit();
   };
   auto finish = [&](int t) {     // grad of tile t from the staged inputs and the chain warp's back_cum values
 #pragma unroll
     for (int q = 0; q < kBwdK; ++q) {
-      const int idx = tk[q] - (t + 1) * kTile + sl;
+      const int idx = tk[q] - (t + 1) * kT + sl;
       if (idx >= bk[q]) {
-        const int at = tile_at(rk[q], sl);
+        const int at = tile_at<kT>(rk[q], sl);
         const scalar_t gw = s_in[t % kInSlots][0][at], Tv = s_in[t % kInSlots][2][at], av = s_in[t % kInSlots][3][at];
         // grad = gw*T - back/(1-alpha+1e-10): product in scalar_t, quotient and difference in double
         const scalar_t gT = mul_rn(gw, Tv);
@@ -256,23 +261,23 @@ alpha2weight_bwd_kernel(const scalar_t* __restrict__ alpha, const scalar_t* __re
   int top = top0;
   for (int t = 0; t < steps; ++t) {
     if (chain) {
-      scalar_t gw[kTile], wv[kTile];
+      scalar_t gw[kT], wv[kT];
 #pragma unroll
-      for (int j = 0; j < kTile; ++j) {
-        gw[j] = s_in[t % kInSlots][0][tile_at(lane, j)];
-        wv[j] = s_in[t % kInSlots][1][tile_at(lane, j)];
+      for (int j = 0; j < kT; ++j) {
+        gw[j] = s_in[t % kInSlots][0][tile_at<kT>(lane, j)];
+        wv[j] = s_in[t % kInSlots][1][tile_at<kT>(lane, j)];
       }
-      const int base = top - kTile;
-      float bj[kTile];
+      const int base = top - kT;
+      float bj[kT];
 #pragma unroll
-      for (int j = kTile - 1; j >= 0; --j) {
+      for (int j = kT - 1; j >= 0; --j) {
         bj[j] = back;
         if (base + j >= begin && base + j < top)
           back = static_cast<float>(fma_rn(gw[j], wv[j], static_cast<scalar_t>(back)));
       }
 #pragma unroll
-      for (int j = 0; j < kTile; ++j) s_back[t % 3][tile_at(lane, j)] = bj[j];
-      if (top > begin) top -= kTile;
+      for (int j = 0; j < kT; ++j) s_back[t % 3][tile_at<kT>(lane, j)] = bj[j];
+      if (top > begin) top -= kT;
     } else {
       fetch(t + 3);              // slot (t + 3) % 5: the chain warp reads slot t % 5, finish(t - 1) slot (t - 1) % 5
       if (t > 0) finish(t - 1);
@@ -569,7 +574,8 @@ extern "C" int pp_alpha2weight(pp_dtype dtype, const void* alpha, const int64_t*
   segment_bounds_kernel<<<ceil_div(n_pts, 256), 256, 0, s>>>(ray_id, n_pts, n_rays, i_start, i_end);
   PP_CHECK_LAUNCH("alpha2weight(bounds)");
   PP_DISPATCH(dtype, {
-    alpha2weight_fwd_kernel<scalar_t><<<ceil_div(n_rays, kWarp), (1 + kFwdMemWarps) * kWarp, 0, s>>>(
+    constexpr int kT = sizeof(scalar_t) == 4 ? 16 : 8;
+    alpha2weight_fwd_kernel<scalar_t, kT><<<ceil_div(n_rays, kWarp), (1 + kFwdMemWarps) * kWarp, 0, s>>>(
         (const scalar_t*)alpha, n_rays, (scalar_t*)weight, (scalar_t*)T, (scalar_t*)alphainv_last,
         i_start, i_end);
   });
@@ -594,7 +600,8 @@ extern "C" int pp_alpha2weight_backward(pp_dtype dtype, const void* alpha, const
   PP_REQUIRE(alpha && weight && T && alphainv_last && i_start && i_end && grad_weights && grad_last,
              PP_ERR_INVALID_ARG, "alpha2weight_backward: null pointer");
   PP_DISPATCH(dtype, {
-    alpha2weight_bwd_kernel<scalar_t><<<ceil_div(n_rays, kWarp), (1 + kBwdMemWarps) * kWarp, 0, s>>>(
+    constexpr int kT = sizeof(scalar_t) == 4 ? 16 : 8;
+    alpha2weight_bwd_kernel<scalar_t, kT><<<ceil_div(n_rays, kWarp), (1 + kBwdMemWarps) * kWarp, 0, s>>>(
         (const scalar_t*)alpha, (const scalar_t*)weight, (const scalar_t*)T,
         (const scalar_t*)alphainv_last, i_start, i_end, n_rays, (const scalar_t*)grad_weights,
         (const scalar_t*)grad_last, (scalar_t*)grad);
