@@ -50,6 +50,41 @@ __device__ __forceinline__ int tile_at(int r, int c) {
   return r * kT + (c ^ (((r / kRowsPerCycle) % kQuads) << 2));
 }
 
+// a lane's whole row of a tile (its ray's kT samples): 128-bit shared-memory accesses, four elements at a time - the
+// XOR permutation of tile_at moves whole 4-element groups, so group q of the row sits at group q ^ swz
+template <typename T, int kT>
+__device__ __forceinline__ void load_row(const T* tile, int r, T (&v)[kT]) {
+  if constexpr (sizeof(T) == 4) {
+    constexpr int kRowsPerCycle = 32 / kT, kQuads = kT / 4;
+    const int swz = (r / kRowsPerCycle) % kQuads;
+    const float4* row = reinterpret_cast<const float4*>(tile + r * kT);
+#pragma unroll
+    for (int q = 0; q < kQuads; ++q) {
+      const float4 x = row[q ^ swz];
+      v[4 * q] = x.x;
+      v[4 * q + 1] = x.y;
+      v[4 * q + 2] = x.z;
+      v[4 * q + 3] = x.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < kT; ++j) v[j] = tile[tile_at<kT>(r, j)];
+  }
+}
+template <typename T, int kT>
+__device__ __forceinline__ void store_row(T* tile, int r, const T (&v)[kT]) {
+  if constexpr (sizeof(T) == 4) {
+    constexpr int kRowsPerCycle = 32 / kT, kQuads = kT / 4;
+    const int swz = (r / kRowsPerCycle) % kQuads;
+    float4* row = reinterpret_cast<float4*>(tile + r * kT);
+#pragma unroll
+    for (int q = 0; q < kQuads; ++q) row[q ^ swz] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < kT; ++j) tile[tile_at<kT>(r, j)] = v[j];
+  }
+}
+
 // 1 + kFwdMemWarps warps per 32 rays.  Warp 0 ("chain") only runs the recurrence: per step it reads its ray's row of
 // the input tile, advances kT samples, writes its T / weight rows - ~100 instructions, and a lone warp issues one
 // dependent instruction every ~5 cycles, so instructions on this warp ARE the kernel's duration.  The memory warps do
@@ -138,28 +173,44 @@ alpha2weight_fwd_kernel(const scalar_t* __restrict__ alpha, int64_t n_rays,
   float T_cum = 1.f;
   for (int t = 0; t < steps; ++t) {
     if (chain) {
-      const scalar_t* a_row = s_a[t % kInSlots];
       scalar_t a[kT];
+      load_row<scalar_t, kT>(s_a[t % kInSlots], lane, a);
+      // The chain itself carries no predicate: samples beyond the ray's end were staged as alpha = 0, which leaves T
+      // unchanged exactly (T * 1.0 in double, narrowed back), and the termination test is taken off the dependent path
+      // - all kT transmittances are produced first, the first one below 1e-3 is located afterwards.  What the chain
+      // computes past the termination is discarded (the reference stops multiplying there).
+      float Tarr[kT + 1];
+      Tarr[0] = T_cum;
 #pragma unroll
-      for (int j = 0; j < kT; ++j) a[j] = a_row[tile_at<kT>(lane, j)];
+      for (int j = 0; j < kT; ++j)
+        Tarr[j + 1] = static_cast<float>(static_cast<double>(Tarr[j]) * (1. - static_cast<double>(a[j])));
+      // reference :597 compares the widened float with the double literal 1e-3; 0.001f is the smallest float above
+      // it, so for a float operand `< 1e-3` and `< 0.001f` are the same predicate
+      int stop = kT;                 // index of the sample after which the ray terminates (kT: not in this tile)
+#pragma unroll
+      for (int j = kT - 1; j >= 0; --j)
+        if (Tarr[j + 1] < 0.001f && pos + j < end) stop = j;
+      const bool alive = cut < 0;
       scalar_t Tj[kT], wj[kT];
 #pragma unroll
       for (int j = 0; j < kT; ++j) {
-        const bool in = cut < 0 && pos + j < end;
-        Tj[j] = in ? static_cast<scalar_t>(T_cum) : scalar_t(1);
-        wj[j] = in ? T_cum * a[j] : scalar_t(0);
-        if (in) {
-          T_cum = static_cast<float>(static_cast<double>(T_cum) * (1. - static_cast<double>(a[j])));
-          // reference :597 compares the widened float with the double literal 1e-3; 0.001f is the smallest float
-          // above it, so for a float operand `< 1e-3` and `< 0.001f` are the same predicate
-          if (T_cum < 0.001f) cut = pos + j + 1;
+        const bool in = alive && j <= stop && pos + j < end;
+        Tj[j] = in ? static_cast<scalar_t>(Tarr[j]) : scalar_t(1);
+        wj[j] = in ? Tarr[j] * a[j] : scalar_t(0);
+      }
+      if (alive) {
+        if (stop < kT) {
+          cut = pos + stop + 1;
+          T_cum = Tarr[kT];
+#pragma unroll
+          for (int j = 0; j < kT; ++j)
+            if (j == stop) T_cum = Tarr[j + 1];
+        } else {
+          T_cum = Tarr[kT];
         }
       }
-#pragma unroll
-      for (int j = 0; j < kT; ++j) {
-        s_T[t % 3][tile_at<kT>(lane, j)] = Tj[j];
-        s_w[t % 3][tile_at<kT>(lane, j)] = wj[j];
-      }
+      store_row<scalar_t, kT>(s_T[t % 3], lane, Tj);
+      store_row<scalar_t, kT>(s_w[t % 3], lane, wj);
       pos += kT;
     } else {
       fetch(t + 3);              // slot (t + 3) % 5: last read by the chain warp in step t - 2
@@ -262,11 +313,8 @@ alpha2weight_bwd_kernel(const scalar_t* __restrict__ alpha, const scalar_t* __re
   for (int t = 0; t < steps; ++t) {
     if (chain) {
       scalar_t gw[kT], wv[kT];
-#pragma unroll
-      for (int j = 0; j < kT; ++j) {
-        gw[j] = s_in[t % kInSlots][0][tile_at<kT>(lane, j)];
-        wv[j] = s_in[t % kInSlots][1][tile_at<kT>(lane, j)];
-      }
+      load_row<scalar_t, kT>(s_in[t % kInSlots][0], lane, gw);
+      load_row<scalar_t, kT>(s_in[t % kInSlots][1], lane, wv);
       const int base = top - kT;
       float bj[kT];
 #pragma unroll
@@ -275,8 +323,7 @@ alpha2weight_bwd_kernel(const scalar_t* __restrict__ alpha, const scalar_t* __re
         if (base + j >= begin && base + j < top)
           back = static_cast<float>(fma_rn(gw[j], wv[j], static_cast<scalar_t>(back)));
       }
-#pragma unroll
-      for (int j = 0; j < kT; ++j) s_back[t % 3][tile_at<kT>(lane, j)] = bj[j];
+      store_row<float, kT>(s_back[t % 3], lane, bj);
       if (top > begin) top -= kT;
     } else {
       fetch(t + 3);              // slot (t + 3) % 5: the chain warp reads slot t % 5, finish(t - 1) slot (t - 1) % 5
