@@ -58,3 +58,35 @@ try:
 except Exception as e:
     print("mlp-only stress FAILED after %d launches: %s" % (it, str(e)[:120]))
     sys.exit(1)
+
+# ---- train loops: rgbnet forward + fused backward, then the deformation network forward / backward ----
+if os.environ.get("TRAIN"):
+    del eng
+    torch.cuda.empty_cache()
+    sdf, k0 = bench._sphere_sdf(160, dev, 7)
+    eng = voxurf.FusedVoxurf(sdf, k0, ws, bs, bench.XYZ_MIN, bench.XYZ_MAX, stepsize=0.5, s_val=0.05, bg=0.0,
+                             sdf_alpha=10.0, sdf_beta=0.35, lr_sdf=1e-4, lr_k0=1e-2, lr_rgbnet=1e-3, lr_warp=1e-6,
+                             w_eikonal=0.1, w_deform=0.1)
+    dims = [3, 128, 128, 128, 128, 4]
+    wws = [torch.randn(dims[i + 1], dims[i]) * (2.0 / dims[i]) ** 0.5 for i in range(5)]
+    wws[-1] = 0.005 * torch.randn(4, 128)
+    wbs = [0.1 * torch.randn(dims[i + 1]) for i in range(5)]
+    eng.set_warp_network(wws, wbs, 2.0)
+    tgt = torch.rand(8192, 3, device=dev)
+    for use_deform in (False, True):
+        t0 = time.time()
+        it = 0
+        try:
+            while time.time() - t0 < budget / 2:
+                o, d, v = pool[it % 8]
+                loss = eng.train_step(o, d, v, tgt, use_deform=use_deform)
+                it += 1
+                if it % 10 == 0:
+                    torch.cuda.synchronize()
+            torch.cuda.synchronize()
+            assert torch.isfinite(loss).all()
+            print("train stress ok (use_deform=%s): %d steps in %.1f s, loss %.5f" % (use_deform, it, time.time() - t0,
+                                                                                     float(loss[0])))
+        except Exception as e:
+            print("train stress FAILED (use_deform=%s) at step %d: %s" % (use_deform, it, str(e)[:160]))
+            sys.exit(1)
