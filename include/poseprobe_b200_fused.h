@@ -404,6 +404,10 @@ PP_API int pp_nerf_composite_backward(const float* ray, const float* rgb_samples
 PP_API int pp_nerf_sample_depth_from_pdf(const float* weights, int64_t n_rays, int32_t n_samples_coarse,
                                          const float* unif, int32_t n_samples_fine, float depth_min,
                                          float depth_max, float* depth_samples_fine, pp_stream_t stream);
+/* torch.cat([depth_samples, depth_samples_fine], dim=2).sort(dim=2).values (renderer.py:612-614): per ray the n_a
+ * coarse and n_b resampled depths merged in ascending order -> out [n, n_a + n_b].  n_a + n_b <= 1024. */
+PP_API int pp_nerf_sort_depth(const float* depth_a, int32_t n_a, const float* depth_b, int32_t n_b, int64_t n_rays,
+                              float* out, pp_stream_t stream);
 
 #ifdef __cplusplus
 }

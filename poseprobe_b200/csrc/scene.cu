@@ -252,6 +252,41 @@ nerf_sample_pdf_kernel(const float* __restrict__ weights, int64_t n_rays, int N,
   }
 }
 
+
+// cat([depth_samples, depth_samples_fine], dim=2).sort(dim=2).values (renderer.py:612-614): the union of the coarse and
+// the resampled depths of a ray in ascending order.  One warp per ray: the na + nb values (<= 1024) are padded with +inf
+// to a power of two in shared memory and sorted with a bitonic network (compare-exchange pairs strided over the lanes).
+__global__ void __launch_bounds__(256)
+nerf_sort_depth_kernel(const float* __restrict__ a, int na, const float* __restrict__ b, int nb, int64_t n_rays,
+                       int n_pad, float* __restrict__ out) {
+  extern __shared__ float s_sort_all[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* v = s_sort_all + (size_t)warp * n_pad;
+  const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (r >= n_rays) return;
+  const int n = na + nb;
+  for (int i = lane; i < n_pad; i += 32)
+    v[i] = i < na ? a[r * na + i] : (i < n ? b[r * nb + (i - na)] : __int_as_float(0x7f800000));
+  __syncwarp();
+  for (int k = 2; k <= n_pad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = lane; t < (n_pad >> 1); t += 32) {
+        // t-th compare-exchange of this stage: partner indices i < l = i ^ j
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+        const int l = i | j;
+        const bool up = (i & k) == 0;
+        const float x = v[i], y = v[l];
+        if ((x > y) == up) {
+          v[i] = y;
+          v[l] = x;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  for (int i = lane; i < n; i += 32) out[r * n + i] = v[i];
+}
+
 }  // namespace pp
 
 using namespace pp;
@@ -302,5 +337,20 @@ extern "C" int pp_nerf_sample_depth_from_pdf(const float* weights, int64_t n_ray
   nerf_sample_pdf_kernel<<<ceil_div(n_rays * 32, 256), 256, smem, as_stream(stream)>>>(
       weights, n_rays, n_samples_coarse, unif, n_samples_fine, depth_min, depth_max, depth_samples_fine);
   PP_CHECK_LAUNCH("nerf_sample_depth_from_pdf");
+  return PP_OK;
+}
+
+extern "C" int pp_nerf_sort_depth(const float* depth_a, int32_t n_a, const float* depth_b, int32_t n_b, int64_t n_rays,
+                                  float* out, pp_stream_t stream) {
+  PP_REQUIRE(n_rays >= 0 && n_a >= 0 && n_b >= 0, PP_ERR_INVALID_ARG, "nerf_sort_depth: negative extent");
+  PP_REQUIRE(n_a + n_b <= 1024, PP_ERR_UNSUPPORTED, "nerf_sort_depth: at most 1024 samples per ray");
+  if (n_rays == 0 || n_a + n_b == 0) return PP_OK;
+  PP_REQUIRE((depth_a || n_a == 0) && (depth_b || n_b == 0) && out, PP_ERR_INVALID_ARG, "nerf_sort_depth: null pointer");
+  int n_pad = 2;
+  while (n_pad < n_a + n_b) n_pad <<= 1;
+  const size_t smem = (size_t)8 * n_pad * sizeof(float);
+  nerf_sort_depth_kernel<<<ceil_div(n_rays * 32, 256), 256, smem, as_stream(stream)>>>(depth_a, n_a, depth_b, n_b,
+                                                                                         n_rays, n_pad, out);
+  PP_CHECK_LAUNCH("nerf_sort_depth");
   return PP_OK;
 }

@@ -114,3 +114,19 @@ def sample_depth_from_pdf(weights, n_samples_coarse, n_samples_fine, depth_range
                                                 float(depth_range[0]), float(depth_range[1]), ptr(out), stream()),
               "nerf_sample_depth_from_pdf")
     return out
+
+
+@torch.no_grad()
+def merge_depth_samples(depth_samples, depth_samples_fine):
+    """`torch.cat([depth_samples, depth_samples_fine], dim=2).sort(dim=2).values` (renderer.py:612-614): the coarse and
+    the resampled depths of every ray, [B,R,N,1] and [B,R,Nf,1] -> [B,R,N+Nf,1] ascending, in one kernel."""
+    _need_cuda(depth_samples, "depth_samples")
+    _need_cuda(depth_samples_fine, "depth_samples_fine")
+    B, R, N = depth_samples.shape[:3]
+    Nf = depth_samples_fine.shape[2]
+    a = depth_samples.reshape(B * R, N).contiguous()
+    b = depth_samples_fine.reshape(B * R, Nf).contiguous()
+    out = torch.empty(B, R, N + Nf, 1, device=a.device, dtype=torch.float32)
+    with torch.cuda.device(a.device):
+        check(lib.pp_nerf_sort_depth(ptr(a), N, ptr(b), Nf, B * R, ptr(out), stream()), "nerf_sort_depth")
+    return out

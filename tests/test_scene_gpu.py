@@ -143,3 +143,18 @@ def test_composite_full_size_properties(cuda):
     fine = scene.sample_depth_from_pdf(w, N, 128, [0.5, 6.0], det=True)
     assert float(fine.min()) >= 0.5 - 1e-5 and float(fine.max()) <= 6.0 + 1e-5
     assert bool((fine[:, :, 1:, 0] >= fine[:, :, :-1, 0] - 1e-6).all())
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1, 1), (2, 7, 64, 48), (1, 100, 128, 128), (1, 33, 500, 524), (3, 5, 17, 0)])
+def test_merge_depth_samples_is_cat_sort(cuda, shape):
+    """pp_nerf_sort_depth == torch.cat(...).sort(dim=2).values (renderer.py:612-614): exact (a sort moves values)."""
+    from poseprobe_b200 import scene
+    B, R, N, Nf = shape
+    gen = torch.Generator().manual_seed(N * 7 + Nf)
+    a = torch.rand(B, R, N, 1, generator=gen) * 5
+    b = torch.rand(B, R, Nf, 1, generator=gen) * 5
+    if Nf > 3:
+        b[..., :3, :] = a[..., :3, :]                      # ties
+    want = torch.cat([a, b], dim=2).sort(dim=2).values
+    got = scene.merge_depth_samples(a.to(cuda), b.to(cuda)).cpu()
+    assert got.shape == want.shape and torch.equal(got, want)
