@@ -272,6 +272,56 @@ class DirectVoxGO(nn.Module):
         self.world_size = ((self.xyz_max - self.xyz_min) / self.voxel_size).long()
         self.voxel_size_ratio = self.voxel_size / self.voxel_size_base
 
+    @torch.no_grad()
+    def maskout_near_cam_vox(self, cam_o, near):
+        # lib/dvgo_ori.py:169-181
+        self_grid_xyz = self._grid_xyz()
+        nearest_dist = torch.stack([(self_grid_xyz.unsqueeze(-2) - co).pow(2).sum(-1).sqrt().amin(-1)
+                                    for co in cam_o.split(100)]).amin(0)
+        self.density[nearest_dist[None, None] <= near] = -100
+
+    @torch.no_grad()
+    def scale_volume_grid(self, num_voxels):
+        # lib/dvgo_ori.py:183-199 (progressive grid scaling: trilinear resampling of both grids)
+        self._set_grid_resolution(num_voxels)
+        size = tuple(self.world_size.tolist())
+        self.density = nn.Parameter(F.interpolate(self.density.data, size=size, mode='trilinear', align_corners=True))
+        if self.k0_dim > 0:
+            self.k0 = nn.Parameter(F.interpolate(self.k0.data, size=size, mode='trilinear', align_corners=True))
+        else:
+            self.k0 = nn.Parameter(torch.zeros([1, self.k0_dim, *size], device=self.density.device))
+        if self.mask_cache is not None:
+            self._set_nonempty_mask()
+
+    def voxel_count_views(self, rays_o_tr, rays_d_tr, imsz, near, far, stepsize, downrate=1, irregular_shape=False):
+        """lib/dvgo_ori.py:201-233: how many training views see each voxel - the gradient of sum(grid_sampler(pts, ones))
+        w.r.t. `ones` counts the samples that touch a voxel; here that is the trilinear scatter kernel."""
+        from . import ops
+        N_samples = int(np.linalg.norm(np.array(self.density.shape[2:]) + 1) / stepsize) + 1
+        dev = self.density.device
+        rng = torch.arange(N_samples, device=dev)[None].float()
+        count = torch.zeros_like(self.density.detach())
+        for rays_o_, rays_d_ in zip(rays_o_tr.split(imsz), rays_d_tr.split(imsz)):
+            ones = torch.ones_like(self.density).requires_grad_()
+            if irregular_shape:
+                rays_o_ = rays_o_.split(10000)
+                rays_d_ = rays_d_.split(10000)
+            else:
+                rays_o_ = rays_o_[::downrate, ::downrate].to(dev).flatten(0, -2).split(10000)
+                rays_d_ = rays_d_[::downrate, ::downrate].to(dev).flatten(0, -2).split(10000)
+            for rays_o, rays_d in zip(rays_o_, rays_d_):
+                vec = torch.where(rays_d == 0, torch.full_like(rays_d, 1e-6), rays_d)
+                rate_a = (self.xyz_max - rays_o) / vec
+                rate_b = (self.xyz_min - rays_o) / vec
+                t_min = torch.minimum(rate_a, rate_b).amax(-1).clamp(min=near, max=far)
+                step = stepsize * self.voxel_size * rng
+                interpx = (t_min[..., None] + step / rays_d.norm(dim=-1, keepdim=True))
+                rays_pts = rays_o[..., None, :] + rays_d[..., None, :] * interpx[..., None]
+                ops.trilinear(ones, rays_pts.reshape(-1, 3), self.xyz_min, self.xyz_max).sum().backward()
+            with torch.no_grad():
+                count += (ones.grad > 1)
+        return count
+
     def get_kwargs(self):
         return {'xyz_min': self.xyz_min.cpu().numpy(), 'xyz_max': self.xyz_max.cpu().numpy(),
                 'num_voxels': self.num_voxels, 'num_voxels_base': self.num_voxels_base, 'alpha_init': self.alpha_init,

@@ -126,3 +126,40 @@ def test_get_ray_marching_ray_vs_oracle(cuda, shape):
     rel = float((ga.cpu().double()[ok] - ga64[ok]).norm() / (ga64[ok].norm() + 1e-30))
     assert rel < 1e-5, rel
     assert bool(torch.isfinite(ga).all())
+
+
+def test_voxel_count_views_and_scale_volume_grid(cuda):
+    """`voxel_count_views` (lib/dvgo_ori.py:201-233) through the trilinear scatter kernel == the same count through
+    F.grid_sample's autograd; `scale_volume_grid` resamples both grids and keeps the module renderable."""
+    import poseprobe_b200 as pp
+    import torch.nn.functional as F
+    from poseprobe_b200 import synthetic
+    m = pp.DirectVoxGO(xyz_min=[-1, -1, -1], xyz_max=[1, 1, 1], num_voxels=16 ** 3, num_voxels_base=16 ** 3,
+                       alpha_init=1e-2).to(cuda)
+    H = W = 12
+    o, d, _ = synthetic.make_rays(2 * H * W, seed=3)
+    rays_o, rays_d = o.reshape(2 * H, W, 3).to(cuda), d.reshape(2 * H, W, 3).to(cuda)
+    got = m.voxel_count_views(rays_o, rays_d, imsz=[H, H], near=0.2, far=6.0, stepsize=0.5)
+    # the reference formulation with ATen's sampler
+    N_samples = int(np.linalg.norm(np.array(m.density.shape[2:]) + 1) / 0.5) + 1
+    rng = torch.arange(N_samples, device=cuda)[None].float()
+    want = torch.zeros_like(m.density.detach())
+    for ro, rd in zip(rays_o.split([H, H]), rays_d.split([H, H])):
+        ones = torch.ones_like(m.density).requires_grad_()
+        ro, rd = ro.flatten(0, -2), rd.flatten(0, -2)
+        vec = torch.where(rd == 0, torch.full_like(rd, 1e-6), rd)
+        t_min = torch.minimum((m.xyz_max - ro) / vec, (m.xyz_min - ro) / vec).amax(-1).clamp(min=0.2, max=6.0)
+        pts = ro[..., None, :] + rd[..., None, :] * (t_min[..., None] + 0.5 * m.voxel_size * rng / rd.norm(dim=-1, keepdim=True))[..., None]
+        ind = ((pts.reshape(1, 1, 1, -1, 3) - m.xyz_min) / (m.xyz_max - m.xyz_min)).flip((-1,)) * 2 - 1
+        F.grid_sample(ones, ind, mode="bilinear", align_corners=True).sum().backward()
+        want += (ones.grad > 1)
+    # a voxel whose accumulated weight is within rounding of 1 may be counted differently (atomic order): allow a few
+    assert float((got != want).float().mean()) < 2e-3 and float(got.sum()) > 0
+    with torch.no_grad():
+        m.density.normal_()
+        m.k0.normal_()
+    m.scale_volume_grid(24 ** 3)
+    assert tuple(m.density.shape) == (1, 1, 24, 24, 24) and tuple(m.k0.shape) == (1, 3, 24, 24, 24)
+    ro, rd = rays_o.flatten(0, -2), rays_d.flatten(0, -2)
+    out = m(ro, rd, rd, global_step=None, near=0.2, far=6.0, stepsize=0.5, bg=0.0)
+    assert out["rgb_marched"].shape == (2 * H * W, 3) and bool(torch.isfinite(out["rgb_marched"]).all())
