@@ -1008,6 +1008,49 @@ class Voxurf(torch.nn.Module):
                 "disp": 1 / depth, "normal_marched": normal, "s_val": float(self.s_val)}
 
 
+    @torch.no_grad()
+    def _query_surface(self, rays_o, rays_d, global_step, keep_dim, return_depth, use_deform, render_kwargs):
+        """Depth-only march of `query_sdf_point_wocuda_render` (lib/voxurf_coarse.py:839-920): NeuS alpha +
+        alpha2weight along every ray, n_step = sum_i w_i step_i, depth = t_min + n_step / |d|, surface point
+        rays_o + rays_d * depth, valid where n_step > 0.  One march launch (plus the deformation network when
+        use_deform), no colour network.  Forward only: the reference lets the projection loss of
+        lib/recon_scene.py:622-637 reach the model through this depth; here the points are detached."""
+        render_kwargs = dict(render_kwargs)
+        render_kwargs.pop("training", None)
+        jitter = render_kwargs.pop("jitter", None)
+        eng, _, _ = self._engine(render_kwargs, pose_grad=self._eng_key[4] if self._eng is not None else False)
+        eng.load_params(self.sdf.grid, self.k0.grid, *self._rgbnet_params(), float(self.sdf_alpha), float(self.sdf_beta))
+        if use_deform:
+            ws, bs = self.warp_network.parameters_for_kernel()
+            eng.set_warp_network([w.detach() for w in ws], [b.detach() for b in bs], self.warp_network.output_range)
+        if global_step is not None:          # neus_alpha_from_sdf_scatter(is_train=True): the s_val schedule (:485-488)
+            self.s_val.data.fill_(1.0 / (global_step + self.s_ratio / self.s_start - self.step_start) * self.s_ratio)
+        eng.set_schedule(s_val=float(self.s_val), progress=1.0 if global_step is None else global_step / self.N_iters)
+        rays_o, rays_d = rays_o.detach().contiguous(), rays_d.detach().contiguous()
+        n = rays_o.shape[0]
+        if jitter is None and global_step is not None:
+            jitter = torch.rand(n, device=rays_o.device)                                     # sample_ray_ori, :712-713
+        viewdirs = (rays_d / rays_d.norm(dim=-1, keepdim=True)).contiguous()
+        b = eng._buffers(n)
+        n_step = torch.empty(n, dtype=torch.float32, device=eng.device)
+        with torch.cuda.device(eng.device):
+            (eng._march_deform if use_deform else eng._march)(b, rays_o, rays_d, viewdirs, jitter, n_step, None)
+        vec = torch.where(rays_d == 0, torch.full_like(rays_d, 1e-6), rays_d)
+        ra, rb = (self.xyz_max - rays_o) / vec, (self.xyz_min - rays_o) / vec
+        t_min = torch.minimum(ra, rb).amax(-1).clamp(min=render_kwargs["near"], max=render_kwargs["far"])
+        depth = t_min[..., None] + n_step[..., None] / rays_d.norm(dim=-1, keepdim=True)
+        mask = n_step > 0.
+        if keep_dim:
+            return rays_o + rays_d * depth, mask, depth
+        pts_sdf0 = rays_o[mask] + rays_d[mask] * depth[mask]
+        return (pts_sdf0, depth[mask]) if return_depth else pts_sdf0
+
+    def query_sdf_point_wocuda_render(self, rays_o, rays_d, global_step=None, keep_dim=False, return_depth=False,
+                                      use_deform=True, **render_kwargs):
+        """lib/voxurf_coarse.py:839-920 (the second, small render of every train step: lib/recon_scene.py:622-637)."""
+        return self._query_surface(rays_o, rays_d, global_step, keep_dim, return_depth, use_deform, render_kwargs)
+
+
 def smoke(dev):
     """Tiny fused fine-stage train step (used by __graft_entry__.smoke): runs the march, both tcgen05 rgbnet
     kernels, the reverse march and the optimiser tail once."""

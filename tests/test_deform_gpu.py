@@ -562,6 +562,20 @@ def test_voxurf_module_replays_the_references_forward(cuda, tag):
     assert out["mask"].dtype == torch.bool and int(out["mask"].sum()) == M and not bool(out["mask_outbbox"].any())
     assert set(["alphainv_cum", "weights", "cum_weights", "rgb_marched", "normal_marched", "raw_alpha", "raw_rgb", "depth",
                 "disp", "mask", "mask_outbbox", "gradient", "s_val", "k0_tv"]) <= set(out.keys())
+    if tag == "eval":
+        # query_sdf_point_wocuda_render (voxurf_coarse.py:839-920, the depth-only render of lib/recon_scene.py:622-637):
+        # depth = t_min + sum_i w_i step_i / |d| - for the unit directions of the golden rays the forward's own depth
+        pts, valid, depth = m.query_sdf_point_wocuda_render(o, d, global_step=None, keep_dim=True, use_deform=False, **kw)
+        torch.testing.assert_close(depth[:, 0].cpu(), w("depth"), rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(pts, o + d * depth, rtol=0, atol=1e-6)
+        assert valid.dtype == torch.bool and valid.shape == (o.shape[0],) and int(valid.sum()) > 0
+        # the surface point does not depend on the length of the direction vector (depth scales with 1 / |d|)
+        pts2, valid2, depth2 = m.query_sdf_point_wocuda_render(o, 2.0 * d, global_step=None, keep_dim=True,
+                                                               use_deform=False, **kw)
+        torch.testing.assert_close(pts2[valid], pts[valid], rtol=0, atol=2e-4)
+        assert torch.equal(valid, valid2)
+        only = m.query_sdf_point_wocuda_render(o, d, global_step=None, use_deform=False, **kw)
+        assert only.shape == (int(valid.sum()), 3)
 
 
 def test_voxurf_module_deform_branch_trains_with_the_references_losses(cuda):
