@@ -17,6 +17,9 @@
 //     applies the sigmoid and writes [M,3].
 // Activations never touch HBM: traffic is d0*4 B in and 12 B out per sample.
 #include <stdlib.h>
+#include <string.h>
+
+#include <cuda.h>   // CUtensorMap (type and enums only: the encoder is fetched through cudaGetDriverEntryPoint)
 
 #include "mlp_common.cuh"
 
@@ -56,11 +59,14 @@ __device__ __forceinline__ void group_sync(int g) {
 // Operands are fp16 here (11 significant bits, same MMA rate as bf16): a gate that flips because z_l was rounded
 // changes the Jacobian of that sample by a whole rank-1 term, and the flip rate scales with the operand rounding;
 // the values of this small network (|h| < ~1e2) are far inside the fp16 range.
-template <int kPipes, bool kJac>
+// kTma: the input tiles arrive by TMA (cp.async.bulk.tensor, one elected thread, completion on an mbarrier) in the
+// chunked layout of desc_kmajor_chunked instead of 16-byte cp.async from every thread.
+template <int kPipes, bool kJac, bool kTma>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 rgbnet_forward_kernel(MlpParams P, const __nv_bfloat16* __restrict__ x, int64_t M, int apply_sigmoid,
                       float* __restrict__ out, const float* __restrict__ wgt, const int32_t* __restrict__ ray_id,
-                      float* __restrict__ rgb_marched, const int32_t* __restrict__ n_ptr) {
+                      float* __restrict__ rgb_marched, const int32_t* __restrict__ n_ptr,
+                      const __grid_constant__ CUtensorMap x_map) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if (n_ptr) M = min64(M, static_cast<int64_t>(*n_ptr));   // row count produced on the device (compacted samples)
   constexpr int kPipeThreads = kFwdThreads / kPipes;       // 256 or 128
@@ -83,7 +89,8 @@ rgbnet_forward_kernel(MlpParams P, const __nv_bfloat16* __restrict__ x, int64_t 
   // (behind ALL kPipes mbarriers: at + 16 it shared its bytes with the third pipeline's barrier, and the deallocation
   // at the end read whatever state that barrier was in - cudaErrorTensorMemoryLeak once per few thousand launches)
   uint32_t* sTmem = reinterpret_cast<uint32_t*>(smem + off + 8 * kPipes);
-  static_assert(8 * kPipes + 4 <= 64, "the host reserves 64 bytes for the barriers and the TMEM base");
+  uint64_t* sBarX = reinterpret_cast<uint64_t*>(smem + off + 64);      // kPipes "input tile has landed" barriers (TMA)
+  static_assert(8 * kPipes + 4 <= 64 && 64 + 8 * kPipes <= 128, "the host reserves 128 bytes for barriers + TMEM base");
 
   // ---- prologue (whole CTA): weights -> bf16 canonical layout, biases, TMEM, mbarriers ----
   for (int l = 0; l < L; ++l) {
@@ -122,7 +129,10 @@ rgbnet_forward_kernel(MlpParams P, const __nv_bfloat16* __restrict__ x, int64_t 
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
-    for (int q = 0; q < kPipes; ++q) mbar_init(smem_u32(sBar + q), 1);
+    for (int q = 0; q < kPipes; ++q) {
+      mbar_init(smem_u32(sBar + q), 1);
+      mbar_init(smem_u32(sBarX + q), 1);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   fence_async_smem();
@@ -131,8 +141,8 @@ rgbnet_forward_kernel(MlpParams P, const __nv_bfloat16* __restrict__ x, int64_t 
   tc_fence_after();
   const uint32_t tmem_base = *sTmem;
   const uint32_t tmem = tmem_base + g * kMlpWidth;   // this pipeline's accumulator: 128 columns, logits in the first 16
-  const uint32_t bar = smem_u32(sBar + g);
-  uint32_t phase = 0;
+  const uint32_t bar = smem_u32(sBar + g), bar_x = smem_u32(sBarX + g);
+  uint32_t phase = 0, phase_x = 0;
   const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
   const uint32_t idesc_h = kJac ? umma_idesc_f16(kFwdTile, kMlpWidth) : umma_idesc_bf16(kFwdTile, kMlpWidth);
   const uint32_t idesc_o = kJac ? umma_idesc_f16(kFwdTile, kMlpOutPad) : umma_idesc_bf16(kFwdTile, kMlpOutPad);
@@ -142,13 +152,21 @@ rgbnet_forward_kernel(MlpParams P, const __nv_bfloat16* __restrict__ x, int64_t 
   const int64_t tile_stride = (int64_t)gridDim.x * kPipes;
   auto stage = [&](int64_t tile) {   // request a tile of packed rows straight into the A buffer (UMMA layout)
     const uint32_t base = smem_u32(sA);
-    for (int id = gt; id < kFwdTile * chunks_per_row; id += kPipeThreads) {
-      const int r = id / chunks_per_row, c8 = id - r * chunks_per_row;
-      const int64_t grow = tile * kFwdTile + r;
-      const bool ok = grow < M;
-      const uint32_t dst = base + canon_off(r, c8 * 8, k0p);
-      const void* src = x + (ok ? grow : 0) * k0p + c8 * 8;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u) : "memory");
+    if constexpr (kTma) {
+      if (gt == 0) {
+        mbar_expect_tx(bar_x, static_cast<uint32_t>(kFwdTile * k0p * 2));
+        for (int c8 = 0; c8 < chunks_per_row; ++c8)
+          tma_load_2d(base + c8 * 2048, &x_map, c8 * 8, static_cast<int>(tile * kFwdTile), bar_x);
+      }
+    } else {
+      for (int id = gt; id < kFwdTile * chunks_per_row; id += kPipeThreads) {
+        const int r = id / chunks_per_row, c8 = id - r * chunks_per_row;
+        const int64_t grow = tile * kFwdTile + r;
+        const bool ok = grow < M;
+        const uint32_t dst = base + canon_off(r, c8 * 8, k0p);
+        const void* src = x + (ok ? grow : 0) * k0p + c8 * 8;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16u : 0u) : "memory");
+      }
     }
   };
   int64_t tile = (int64_t)blockIdx.x * kPipes + g;
@@ -156,8 +174,13 @@ rgbnet_forward_kernel(MlpParams P, const __nv_bfloat16* __restrict__ x, int64_t 
   for (; tile < n_tiles; tile += tile_stride) {
     const int64_t grow = tile * kFwdTile + row;
     const bool valid = grow < M;
-    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-    fence_async_smem();
+    if constexpr (kTma) {
+      mbar_wait_or_trap(bar_x, phase_x);     // the tile's bytes have landed (rows past the buffer's end: zeros;
+      phase_x ^= 1;                          // rows between M and the buffer's end: stale, their outputs are dropped)
+    } else {
+      asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+      fence_async_smem();
+    }
     group_sync<kPipeThreads>(g);
 
     for (int l = 0; l < L; ++l) {
@@ -168,7 +191,8 @@ rgbnet_forward_kernel(MlpParams P, const __nv_bfloat16* __restrict__ x, int64_t 
         tc_fence_after();
         const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sW[l]);
         for (int k = 0; k < (K >> 4); ++k)
-          umma_bf16(d_tmem, desc_kmajor(a0, K, k), desc_kmajor(b0, K, k), last ? idesc_o : idesc_h, k > 0);
+          umma_bf16(d_tmem, (kTma && l == 0) ? desc_kmajor_chunked(a0, k) : desc_kmajor(a0, K, k),
+                    desc_kmajor(b0, K, k), last ? idesc_o : idesc_h, k > 0);
         umma_commit(bar);
       }
       mbar_wait(bar, phase);
@@ -306,6 +330,38 @@ __global__ void warpnet_pack_points_kernel(const float* __restrict__ x, int64_t 
 
 using namespace pp;
 
+// cuTensorMapEncodeTiled, fetched through the runtime (the library links cudart only).  nullptr: not available.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+// [n_rows, k0p] bf16 rows as a 2-D tensor, box = {8 columns, 128 rows} (see desc_kmajor_chunked)
+static bool make_rows_map(CUtensorMap* map, const void* rows, int64_t n_rows, int k0p) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enc || (reinterpret_cast<uintptr_t>(rows) & 15)) return false;
+  const cuuint64_t gdim[2] = {(cuuint64_t)k0p, (cuuint64_t)n_rows};
+  const cuuint64_t gstr[1] = {(cuuint64_t)k0p * 2};
+  const cuuint32_t box[2] = {8, (cuuint32_t)kFwdTile};
+  const cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(rows), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 extern "C" int pp_warpnet_pack_points(const float* x, int64_t n_pts, void* rows, pp_stream_t stream) {
   PP_REQUIRE(n_pts >= 0, PP_ERR_INVALID_ARG, "warpnet_pack_points: n_pts < 0");
   if (n_pts == 0) return PP_OK;
@@ -346,7 +402,7 @@ extern "C" int pp_rgbnet_forward_packed(const void* x_packed, int64_t n_pts, int
       smem += (size_t)rows * K * 2;
     }
   }
-  smem += (size_t)depth * kMlpWidth * 4 + 64;
+  smem += (size_t)depth * kMlpWidth * 4 + 128;
   const size_t tile_bytes = (size_t)kFwdTile * kMlpWidth * 2;
   const char* pe = getenv("PP_MLP_PIPES");
   int pipes = (smem + 4 * tile_bytes <= 227 * 1024) ? 4 : 2;
@@ -355,15 +411,25 @@ extern "C" int pp_rgbnet_forward_packed(const void* x_packed, int64_t n_pts, int
   PP_REQUIRE(smem <= 227 * 1024, PP_ERR_UNSUPPORTED, "rgbnet_forward: %zu B of shared memory needed", smem);
   const int64_t n_tiles = (n_pts + kFwdTile - 1) / kFwdTile;
   const int blocks = (int)min64((n_tiles + pipes - 1) / pipes, sm_count());
+  // input tiles by TMA when a tensor map can be built (PP_MLP_TMA=0 keeps the cp.async staging)
+  CUtensorMap x_map;
+  memset(&x_map, 0, sizeof(x_map));
+  const char* te = getenv("PP_MLP_TMA");
+  const bool tma = !(te && atoi(te) == 0) && make_rows_map(&x_map, x_packed, n_pts, P.k0p);
+#define PP_LAUNCH_FWD(PIPES, TMA)                                                                                   \
+  do {                                                                                                              \
+    PP_CHECK_CUDA(cudaFuncSetAttribute(rgbnet_forward_kernel<PIPES, false, TMA>,                                    \
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
+    rgbnet_forward_kernel<PIPES, false, TMA><<<blocks, kFwdThreads, smem, as_stream(stream)>>>(                     \
+        P, (const __nv_bfloat16*)x_packed, n_pts, apply_sigmoid, out, sample_weight, ray_id, rgb_marched, n_ptr,    \
+        x_map);                                                                                                     \
+  } while (0)
   if (pipes == 4) {
-    PP_CHECK_CUDA(cudaFuncSetAttribute(rgbnet_forward_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rgbnet_forward_kernel<4, false><<<blocks, kFwdThreads, smem, as_stream(stream)>>>(
-        P, (const __nv_bfloat16*)x_packed, n_pts, apply_sigmoid, out, sample_weight, ray_id, rgb_marched, n_ptr);
+    if (tma) PP_LAUNCH_FWD(4, true); else PP_LAUNCH_FWD(4, false);
   } else {
-    PP_CHECK_CUDA(cudaFuncSetAttribute(rgbnet_forward_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    rgbnet_forward_kernel<2, false><<<blocks, kFwdThreads, smem, as_stream(stream)>>>(
-        P, (const __nv_bfloat16*)x_packed, n_pts, apply_sigmoid, out, sample_weight, ray_id, rgb_marched, n_ptr);
+    if (tma) PP_LAUNCH_FWD(2, true); else PP_LAUNCH_FWD(2, false);
   }
+#undef PP_LAUNCH_FWD
   PP_CHECK_LAUNCH("rgbnet_forward");
   return PP_OK;
 }
@@ -397,16 +463,18 @@ extern "C" int pp_warpnet_forward_packed(const void* x_rows, int64_t n_rows, int
       smem += (size_t)rows * K * 2;
     }
   }
-  smem += (size_t)depth * kMlpWidth * 4 + 64;
+  smem += (size_t)depth * kMlpWidth * 4 + 128;
   const size_t tile_bytes = (size_t)kFwdTile * kMlpWidth * 2;
   smem += 2 * tile_bytes;
   PP_REQUIRE(smem <= 227 * 1024, PP_ERR_UNSUPPORTED, "warpnet_forward: %zu B of shared memory needed", smem);
   const int64_t n_tiles = (n_rows + kFwdTile - 1) / kFwdTile;
   const int blocks = (int)min64((n_tiles + 1) / 2, sm_count());
-  PP_CHECK_CUDA(cudaFuncSetAttribute(rgbnet_forward_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  CUtensorMap no_map;
+  memset(&no_map, 0, sizeof(no_map));
+  PP_CHECK_CUDA(cudaFuncSetAttribute(rgbnet_forward_kernel<2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)smem));
-  rgbnet_forward_kernel<2, true><<<blocks, kFwdThreads, smem, as_stream(stream)>>>(
-      P, (const __nv_bfloat16*)x_rows, n_rows, 0, out, nullptr, nullptr, nullptr, n_rows_ptr);
+  rgbnet_forward_kernel<2, true, false><<<blocks, kFwdThreads, smem, as_stream(stream)>>>(
+      P, (const __nv_bfloat16*)x_rows, n_rows, 0, out, nullptr, nullptr, nullptr, n_rows_ptr, no_map);
   PP_CHECK_LAUNCH("warpnet_forward");
   return PP_OK;
 }

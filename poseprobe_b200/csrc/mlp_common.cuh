@@ -150,6 +150,44 @@ __device__ __forceinline__ uint32_t umma_idesc_bf16_major(int M, int N, int a_mn
   return umma_idesc_bf16(M, N) | (static_cast<uint32_t>(a_mn) << 15) | (static_cast<uint32_t>(b_mn) << 16);
 }
 
+// ---- TMA (cp.async.bulk.tensor) pieces for the input tiles of the forward kernel ---------------------------
+// A [rows x k0p] bf16 tile arrives as k0p / 8 two-dimensional boxes of {8 columns (16 B), 128 rows}: TMA writes a box
+// row after row, 16 B each, which stacks the tile's 8 x 8 core matrices of one column chunk contiguously (128 B per
+// core matrix, 2 KB per chunk).  Element (r, c) therefore sits at (c / 8) * 2048 + (r / 8) * 128 + (r % 8) * 16 +
+// (c % 8) * 2: still a no-swizzle K-major operand, with LBO = 2048 B between the two column chunks of a K = 16 slice and
+// SBO = 128 B between row groups.
+__device__ __forceinline__ uint64_t desc_kmajor_chunked(uint32_t base, int slice) {
+  return umma_desc(base + slice * 2 * 2048, 2048, 128);
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar_smem, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void* tensor_map, int c0, int c1,
+                                            uint32_t bar_smem) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst_smem), "l"(tensor_map), "r"(c0), "r"(c1), "r"(bar_smem)
+      : "memory");
+}
+// mbarrier wait with a cycle budget: a transfer that never completes (a bad tensor map) traps instead of hanging
+__device__ __forceinline__ void mbar_wait_or_trap(uint32_t bar_smem, uint32_t parity) {
+  const long long t0 = clock64();
+  for (int spin = 0;; ++spin) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar_smem), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((spin & 255) == 255 && clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,"
