@@ -249,3 +249,58 @@ def test_cumdist_thres_is_a_running_sum_with_reset(n, s, thres, seed):
             if over:
                 acc = np.float32(0.0)
         assert mask[r].tolist() == want
+
+
+def test_scene_oracle_structural_properties():
+    """oracle/bgnerf_cpu.py (NeRF.composite / sample_depth_from_pdf restated): weights are a sub-probability whose sum
+    is the opacity; with positive densities the 1e10 last interval makes every ray opaque; the exclusive transmittance
+    is non-increasing; resampled depths stay inside the range, are sorted for a sorted grid, and concentrate where the
+    weights are."""
+    import torch
+    from oracle import bgnerf_cpu
+    g = torch.Generator().manual_seed(3)
+    B, R, N = 2, 17, 40
+    ray = torch.randn(B, R, 3, generator=g)
+    edges = torch.linspace(0.5, 4.0, N + 1)
+    depth = (edges[:-1] + (edges[1:] - edges[:-1]) * torch.rand(B, R, N, generator=g))[..., None]
+    rgb = torch.rand(B, R, N, 3, generator=g)
+    dens = torch.rand(B, R, N, generator=g) * 2 + 1e-3
+    out = bgnerf_cpu.composite(ray, rgb, dens, depth)
+    w = out["weights"][..., 0]
+    assert float(w.min()) >= 0
+    torch.testing.assert_close(w.sum(-1, keepdim=True), out["opacity"])
+    torch.testing.assert_close(out["opacity"], torch.ones_like(out["opacity"]), rtol=0, atol=1e-5)
+    assert float(out["rgb"].min()) >= 0 and float(out["rgb"].max()) <= 1 + 1e-5
+    assert float(out["depth"].min()) >= 0.5 - 1e-5
+    # zero density everywhere except the last sample: the whole weight sits on the last sample
+    d0 = torch.zeros(B, R, N)
+    d0[..., -1] = 1.0
+    o0 = bgnerf_cpu.composite(ray, rgb, d0, depth)
+    torch.testing.assert_close(o0["weights"][..., -1, 0], torch.ones(B, R))
+    torch.testing.assert_close(o0["rgb"], rgb[:, :, -1])
+    # resampling: a single peaked bin attracts all fine samples into that bin's depth interval
+    peak = torch.zeros(1, 1, N)
+    peak[..., 7] = 1.0
+    fine, idx = bgnerf_cpu.sample_depth_from_pdf(peak, N, 16, [0.5, 4.0], torch.linspace(0, 1, 17))
+    lo, hi = 0.5 + 3.5 * 7 / N, 0.5 + 3.5 * 8 / N
+    assert float(fine.min()) >= lo - 1e-5 and float(fine.max()) <= hi + 1e-5
+    assert bool((fine[0, 0, 1:, 0] >= fine[0, 0, :-1, 0]).all())
+    fine2, _ = bgnerf_cpu.sample_depth_from_pdf(w, N, 32, [0.5, 4.0], torch.linspace(0, 1, 33))
+    assert float(fine2.min()) >= 0.5 - 1e-5 and float(fine2.max()) <= 4.0 + 1e-5
+
+
+def test_dense_compositing_oracle_properties():
+    """oracle.get_ray_marching_ray (lib/dvgo_ori.py:478-485): weights + final transmittance partition unity, the
+    clamp keeps a fully opaque sample from zeroing the tail exactly (1e-10), alpha = 0 samples get zero weight."""
+    import torch
+    from oracle import oracle
+    g = torch.Generator().manual_seed(4)
+    a = torch.rand(9, 33, generator=g) ** 2
+    a[:, 5] = 0.0
+    w, c = oracle.get_ray_marching_ray(a)
+    assert c.shape == (9, 34) and bool((c[:, 0] == 1).all())
+    torch.testing.assert_close(w.sum(-1) + c[:, -1], torch.ones(9), rtol=0, atol=1e-5)
+    assert bool((w[:, 5] == 0).all()) and bool((c[:, 1:] <= c[:, :-1] + 1e-7).all())
+    a[:, 10] = 1.0
+    w, c = oracle.get_ray_marching_ray(a)
+    assert float(c[:, 11:].max()) <= 1.0001e-10 and float(c[:, 11].min()) > 0
