@@ -33,13 +33,14 @@ __global__ void segment_bounds_kernel(const int64_t* __restrict__ ray_id, int64_
 // ---- forward -------------------------------------------------------------------------------------
 // The recurrence T_cum *= (1. - alpha) is double arithmetic narrowed to float at every step (reference :596) and its
 // roundings decide the early-termination index, so it runs in the reference's order: ONE lane per ray, as in the
-// reference, 32 rays per warp - every instruction of the chain (two conversions, a double multiply, a compare, all on
-// narrow pipes) advances 32 rays.  What the reference gets wrong is memory: its lanes walk 32 different rays, so every
-// load / store touches 32 lines.  Here the warp moves a [32 rays x 8 samples] tile per step: 8-lane groups read 8
-// consecutive samples of one ray (one 32-byte sector) into a shared-memory tile, each lane reads back its own ray's
-// row, runs 8 steps of the chain in registers, writes T and weight rows back, and the groups store them as sectors.
-// The loads of the next tile are in flight during the chain.  Samples past the termination get the reference's fill
-// values (T = 1, weight = 0) from the same streaming stores, so no separate fill pass over [M] is needed.
+// reference, 32 rays per warp - every instruction of the chain (two conversions and a double multiply, 44 cycles per
+// sample) advances 32 rays.  What the reference gets wrong is memory: its lanes walk 32 different rays, so every load /
+// store touches 32 lines.  Here a block moves a [32 rays x kT samples] tile per step through shared memory: groups
+// of kT lanes copy kT consecutive samples of one ray (64 bytes for fp32), the ray's own lane reads its row back with
+// 128-bit loads, runs kT steps of the chain in registers and writes its T / weight rows, which leave as 64-byte runs
+// again.  Samples past the termination get the reference's fill values (T = 1, weight = 0) from the same streaming
+// stores, so no separate fill pass over [M] is needed.  The kernels below split this between one chain warp and
+// several memory warps.
 // Tile geometry: kT samples per ray and step (16 for fp32, 8 for fp64), kWarp / kT rays per sector instruction.
 // row r, column c of a [32][kT] tile.  A lane reads its whole row with 128-bit loads, 8 lanes per bank cycle; rows that
 // would meet in the same banks (32 / kT rows apart) get their 4-element groups XOR-permuted by the row's index within
