@@ -464,7 +464,11 @@ class FusedDVGO:
                  alpha_init=1e-2, near=0.2, far=1e9, bg=0.0, fast_color_thres=0.0,
                  lr_density=0.1, lr_k0=0.1, betas=(0.9, 0.99), eps=1e-8,
                  w_rgb=1.0, w_entropy_last=0.0, w_rgbper=0.0, tv_density=0.0, tv_k0=0.0, tv_dense=False,
-                 pose_grad=False, vox_buf=None, grad_buf=None, moment_records=None, mse_scale=1.0):
+                 pose_grad=False, vox_buf=None, grad_buf=None, moment_records=None, mse_scale=1.0, adam="masked"):
+        """adam: "masked" = masked_adam_upd arithmetic (adam_upd_kernel.cu:25-40, the operator the north star names:
+        voxels with a zero gradient are skipped, eps before the bias correction) or "reference" = the optimiser the
+        reference actually runs (dense Python Adam, lib/utils.py:176-198: every voxel updated each step, eps after the
+        bias correction)."""
         self.world_size = tuple(int(v) for v in density.shape[2:])
         if voxel_size is None:
             voxel_size = float((xyz_max[0] - xyz_min[0]) / self.world_size[0])
@@ -481,6 +485,11 @@ class FusedDVGO:
         n_mom = self.vox.shape[0] if moment_records is None else int(moment_records)
         self.exp_avg = torch.zeros((n_mom, 4), dtype=torch.float32, device=self.vox.device)
         self.exp_avg_sq = torch.zeros_like(self.exp_avg)
+        if adam not in ("masked", "reference"):
+            raise ValueError("adam must be 'masked' or 'reference'")
+        if adam == "reference" and (tv_density or tv_k0):
+            raise NotImplementedError("FusedDVGO(adam='reference'): the fused TV + Adam pass is masked_adam_upd only")
+        self.adam_dense = adam == "reference"
         self.tv = (float(tv_density), float(tv_k0), bool(tv_dense))
         self.vox_next = torch.empty_like(self.vox) if (tv_density or tv_k0) else None
         self.hp = (float(betas[0]), float(betas[1]), float(lr_density), float(lr_k0), float(eps))
@@ -522,8 +531,8 @@ class FusedDVGO:
                 self.vox, self.vox_next = self.vox_next, self.vox
             else:
                 check(lib.pp_voxel_adam(ptr(self.vox), ptr(self.grad), ptr(self.exp_avg), ptr(self.exp_avg_sq),
-                                        self.n_voxels, self.step, b1, b2, lr_d, lr_k, eps, 1, stream()),
-                      "voxel_adam")
+                                        self.n_voxels, self.step, b1, b2, lr_d, lr_k, eps,
+                                        1 | (2 if self.adam_dense else 0), stream()), "voxel_adam")
 
     def train_step(self, rays_o, rays_d, target, rgb_out=None, grad_rays=None):
         """One optimisation step on a ray batch.  Returns the device tensor [loss, mse] (no sync)."""

@@ -321,3 +321,35 @@ def test_two_ranks_equal_one_rank_on_the_concatenated_batch(pp, script, port):
     r = _torchrun(script, 2, port)
     assert r.returncode == 0, r.stdout[-3000:]
     assert " ok: world=2" in r.stdout, r.stdout[-3000:]
+
+
+def test_fused_dvgo_reference_adam_mode(pp):
+    """FusedDVGO(adam="reference"): the optimiser the reference runs (dense Python Adam, lib/utils.py:176-198) - every
+    voxel moves each step (zero-gradient ones through their momentum), eps after the bias correction - against
+    oracle.python_adam_step on the engine's own gradients, two steps."""
+    G, N = 20, 256
+    density, k0 = synthetic.make_dvgo_grids(G)
+    o, d, _ = synthetic.make_rays(N, seed=5)
+    tgt = torch.rand(N, 3, generator=torch.Generator().manual_seed(6))
+    mn, mx = [-1.0, -1, -1], [1.0, 1, 1]
+    eng = pp.FusedDVGO(density.cuda(), k0.cuda(), mn, mx, stepsize=0.5, adam="reference", lr_density=0.1, lr_k0=0.05)
+    pd, pk = density.clone(), k0.clone()
+    st = [torch.zeros_like(pd), torch.zeros_like(pd), torch.zeros_like(pk), torch.zeros_like(pk)]
+    for step in (1, 2):
+        if step == 2:                     # other rays: some voxels of step 1 get no gradient now
+            o, d, _ = synthetic.make_rays(N // 4, seed=7)
+            tgt = tgt[:N // 4]
+        eng.loss_buf.zero_()
+        eng.backward_only(o.cuda(), d.cuda(), tgt.cuda())
+        gd, gk = (t.cpu() for t in eng.export_grad())
+        eng.optimizer_step()
+        oracle.python_adam_step(pd, gd, st[0], st[1], step, 0.9, 0.99, 0.1, 1e-8)
+        oracle.python_adam_step(pk, gk, st[2], st[3], step, 0.9, 0.99, 0.05, 1e-8)
+        nd, nk = eng.export_grids()
+        close(nd.cpu(), pd, rtol=1e-5, atol=1e-6)
+        close(nk.cpu(), pk, rtol=1e-5, atol=1e-6)
+    # a voxel no ray touched in step 2 still moved (momentum): the masked kernel would have left it alone
+    untouched = (gd == 0) & (st[0] != 0)
+    assert bool(untouched.any())
+    with pytest.raises(NotImplementedError):
+        pp.FusedDVGO(density.cuda(), k0.cuda(), mn, mx, stepsize=0.5, adam="reference", tv_density=0.1)
