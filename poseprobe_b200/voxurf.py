@@ -1,8 +1,10 @@
 """Host side of the fused Voxurf fine-stage train / render path (C ABI: include/poseprobe_b200_fused.h).
 
-Mirrors the surface stage of the reference (``Voxurf.forward``, lib/voxurf_coarse.py:922-1091, non-deform
-branch): ``sdf.grid`` [1,1,X,Y,Z] with the per-step mapping function and the finite-difference gradient grid,
-``k0.grid`` [1,12,X,Y,Z], ``rgbnet`` (57 -> 128 x (depth-1) -> 3), NeuS alpha, alpha compositing, photometric MSE.
+Mirrors the surface stage of the reference (``Voxurf.forward``, lib/voxurf_coarse.py:922-1091, both branches):
+``sdf.grid`` [1,1,X,Y,Z] with the per-step mapping function and the finite-difference gradient grid, ``k0.grid``
+[1,12,X,Y,Z], ``rgbnet`` (57 -> 128 x (depth-1) -> 3), NeuS alpha, alpha compositing, the object losses of
+lib/losses.py:34-74, and - use_deform=True, the reference's live configuration - the implicit deformation network
+with its input Jacobian (forward and the tcgen05 backward of the double backward).
 Parameter layouts interchange with the reference's checkpoints (``import_state`` / ``export_state`` use the keys
 ``sdf.grid``, ``k0.grid``, ``rgbnet.*`` of lib/recon_scene.py:779-791).
 
@@ -10,8 +12,9 @@ Parameter layouts interchange with the reference's checkpoints (``import_state``
 loss, MLP forward-recompute+backward (tcgen05), reverse march + scatter, SDF fold + Adam, SDF record rebuild,
 feature-record Adam, rgbnet Adam, gradient clears.  With ``pose_grad=True`` the reverse march also emits
 d loss / d (rays_o, rays_d, viewdirs) for the SE3 refinement (``ray_gradients`` -> ``camera.rays_from_pixels``'
-backward = the fused per-image reduction).  The deformation network (use_implict_deform) is not part of this path
-(SURVEY.md 8f rank 3).
+backward = the fused per-image reduction).  ``FusedVoxurf.train_step(use_deform=True)`` is the live step through the
+deformation network; ``Voxurf`` is the nn.Module face with the reference's parameter names and
+result dict; ``DistributedVoxurf`` shards rays over the GPUs of a node.
 """
 import ctypes
 import math
