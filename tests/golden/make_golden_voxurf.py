@@ -153,6 +153,14 @@ def main():
                voxel_size=np.float64(float(m.voxel_size)), N_iters=N_iters, gstep=gstep)
     for i, p in enumerate([q for q in m.rgbnet.modules() if isinstance(q, nn.Linear)]):
         out["w%d" % i], out["b%d" % i] = p.weight.detach().numpy(), p.bias.detach().numpy()
+    # query_sdf_point_wocuda_render (:839-920, the depth-only render of lib/recon_scene.py:622-637) on the template SDF,
+    # with NON-unit directions (depth = t_min + n_step / |d|); deterministic (global_step=None), placed last so that the
+    # random stream of everything above is unchanged
+    with torch.no_grad():
+        q_pts, q_mask, q_depth = m.query_sdf_point_wocuda_render(rays_o, 1.7 * rays_d, global_step=None, keep_dim=True,
+                                                                 use_deform=False, **render_kwargs)
+    out.update(query_pts=q_pts.numpy(), query_mask=q_mask.numpy(), query_depth=q_depth.numpy(),
+               query_s_val=np.float64(float(m.s_val)), query_dir_scale=np.float64(1.7))
     path = os.path.join(ROOT, "tests", "golden", "voxurf_forward.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes;", {k: v.shape for k, v in out.items() if hasattr(v, "shape") and v.ndim})

@@ -576,6 +576,14 @@ def test_voxurf_module_replays_the_references_forward(cuda, tag):
         assert torch.equal(valid, valid2)
         only = m.query_sdf_point_wocuda_render(o, d, global_step=None, use_deform=False, **kw)
         assert only.shape == (int(valid.sum()), 3)
+        # ... and against the reference's OWN method on non-unit directions (golden query_*: make_golden_voxurf.py)
+        with torch.no_grad():
+            m.s_val.fill_(float(g["query_s_val"]))
+        qp, qm, qd = m.query_sdf_point_wocuda_render(o, float(g["query_dir_scale"]) * d, global_step=None,
+                                                     keep_dim=True, use_deform=False, **kw)
+        assert torch.equal(qm.cpu(), t("query_mask"))
+        torch.testing.assert_close(qd.cpu(), t("query_depth"), rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(qp.cpu(), t("query_pts"), rtol=0, atol=3e-4)
 
 
 def test_voxurf_module_deform_branch_trains_with_the_references_losses(cuda):
