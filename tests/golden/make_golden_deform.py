@@ -107,6 +107,12 @@ def main():
     nz = np.flatnonzero(g_k0)
     out["g_k0_idx"], out["g_k0_val"] = nz.astype(np.int32), g_k0.reshape(-1)[nz]
     out["g_rays_o"], out["g_rays_d"] = grads[base + 1].numpy(), grads[base + 2].numpy()
+    # the depth-only render through the deformation (query_sdf_point_wocuda_render, :839-920, use_deform=True: what
+    # lib/recon_scene.py:622-637 calls every step), eval mode, non-unit directions; last, so nothing above changes
+    q_pts, q_mask, q_depth = m.query_sdf_point_wocuda_render(rays_o, 1.3 * rays_d, global_step=None,
+                                                             keep_dim=True, use_deform=True, **render_kwargs)
+    out.update(query_pts=q_pts.detach().numpy(), query_mask=q_mask.numpy(), query_depth=q_depth.detach().numpy(),
+               query_s_val=np.float64(float(m.s_val)), query_dir_scale=np.float64(1.3))
     path = os.path.join(ROOT, "tests", "golden", "voxurf_deform.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes; loss", float(loss), {k: float(v) for k, v in terms.items()})
