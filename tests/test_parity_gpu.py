@@ -600,3 +600,28 @@ def test_trilinear_is_twice_differentiable(pp, padding):
         img = ops.grid_sample_3d(grid.cuda(), opt.cuda())
         assert img.shape == (1, 3, 1, 1, n)
         torch.testing.assert_close(img.reshape(3, -1).T.cpu(), want[0].float(), rtol=1e-4, atol=1e-5)
+
+
+def test_alpha2weight_termination_at_tile_boundaries(pp):
+    """Early termination exactly before / at / after the 16-sample tile boundaries of the chain kernel, rays shorter
+    than, equal to and one longer than a tile, empty rays, a ray count that is not a multiple of 32, and a ray of 2500
+    samples: forward and backward bit-exact against the C oracle (render_utils_kernel.cu:577-707)."""
+    ru = pp.render_utils_cuda
+    # (alpha, length): 0.65^n crosses 1e-3 at n = 17, 0.649 at 16, 0.8031 at 32, 0.8085 at 33, 0.35 at 15/16 ...
+    spec = [(0.35, 40), (0.351, 16), (0.351, 17), (0.1969, 64), (0.1915, 33), (0.1915, 32), (0.5, 1), (0.0, 0),
+            (0.9, 15), (1.0, 20), (1e-4, 2500), (0.3508, 31), (0.0, 16), (0.02, 47)] * 3 + [(0.2, 5)]
+    n_rays = len(spec) + 2                      # two trailing rays without samples
+    alpha = torch.cat([torch.full((n,), a) for a, n in spec])
+    g = torch.Generator().manual_seed(0)
+    alpha = (alpha * (1 + 1e-3 * torch.randn(alpha.numel(), generator=g))).clamp(0, 1)
+    ray_id = torch.cat([torch.full((n,), r, dtype=torch.int64) for r, (_, n) in enumerate(spec)])
+    got = ru.alpha2weight(alpha.cuda(), ray_id.cuda(), n_rays)
+    want = oracle.alpha2weight(alpha, ray_id, n_rays)
+    for a_, b_ in zip(got, want):
+        exact(a_, b_)
+    cut = (want[4] - want[3])                   # composited samples per ray
+    assert int(cut[0]) in (16, 17) and int(cut[10]) == 2500 and int(cut[7]) == 0 and int(cut[-1]) == 0
+    gw = torch.randn(alpha.numel(), generator=g)
+    gl = torch.randn(n_rays, generator=g)
+    grad = ru.alpha2weight_backward(alpha.cuda(), *got, n_rays, gw.cuda(), gl.cuda())
+    exact(grad, oracle.alpha2weight_backward(alpha, *want, n_rays, gw, gl))
