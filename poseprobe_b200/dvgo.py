@@ -150,7 +150,9 @@ class MaskCache(nn.Module):
 
     def __init__(self, path=None, mask_cache_thres=1e-3, ks=3, state=None):
         super().__init__()
-        st = torch.load(path) if state is None else state
+        # (reference checkpoints carry numpy arrays in MaskCache_kwargs: the pre-2.6 torch.load default, as the
+        # reference calls it, lib/dvgo_ori.py:439)
+        st = torch.load(path, map_location="cpu", weights_only=False) if state is None else state
         self.mask_cache_thres = mask_cache_thres
         kw = st['MaskCache_kwargs']
         self.register_buffer('xyz_min', torch.FloatTensor(kw['xyz_min']))
