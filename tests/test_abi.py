@@ -146,3 +146,22 @@ def test_c_abi_argument_validation():
     assert lib.pp_warpnet_backward_workspace_bytes() >= 4 and lib.pp_warpnet_backward_stalled() == 0
     assert lib.pp_peer_sync_timed_out(None) == 0
     assert lib.pp_adam_upd(0, 4, None, None, None, None, None, 4, 1, 0.9, 0.99, 0.1, 1e-8, None) == -1   # modes 0..3
+
+
+def test_maskcache_loads_a_reference_style_checkpoint(tmp_path):
+    """dvgo.MaskCache(path=...) reads checkpoints as the reference writes them (numpy arrays in MaskCache_kwargs,
+    lib/dvgo_ori.py:143-152, :436-451); construction is host logic only."""
+    import numpy as np
+    import torch
+    from poseprobe_b200 import dvgo
+    ck = {"MaskCache_kwargs": {"xyz_min": np.array([-1., -1, -1], dtype=np.float32),
+                               "xyz_max": np.array([1., 1, 1], dtype=np.float32), "act_shift": -4.6,
+                               "voxel_size_ratio": 1.0, "nearest": False, "pre_act_density": False,
+                               "in_act_density": False},
+          "model_state_dict": {"density": torch.randn(1, 1, 8, 8, 8)}}
+    path = str(tmp_path / "coarse_last.tar")
+    torch.save(ck, path)
+    m = dvgo.MaskCache(path=path, mask_cache_thres=1e-3)
+    assert tuple(m.density.shape) == (1, 1, 8, 8, 8) and m.xyz_max.tolist() == [1.0, 1.0, 1.0]
+    pooled = torch.nn.functional.max_pool3d(ck["model_state_dict"]["density"], kernel_size=3, padding=1, stride=1)
+    assert torch.equal(m.density, pooled)
