@@ -83,7 +83,8 @@ class DenseGrid(nn.Module):
 def _occupancy_from_checkpoint(path, thres):
     """Coarse-stage checkpoint -> (bool [X,Y,Z], xyz_min, xyz_max): density dilated by a 3^3 max-pool, turned
     into alpha with the checkpoint's act_shift / voxel_size_ratio, thresholded (lib/grid.py:215-222)."""
-    ckpt = torch.load(path)
+    # (the reference's checkpoints hold numpy arrays in model_kwargs: load them the way the reference does, :215)
+    ckpt = torch.load(path, map_location="cpu", weights_only=False)
     state, kwargs = ckpt['model_state_dict'], ckpt['model_kwargs']
     dilated = F.max_pool3d(state['density.grid'], kernel_size=3, stride=1, padding=1)
     alpha = 1 - torch.exp(-F.softplus(dilated + state['act_shift']) * kwargs['voxel_size_ratio'])
