@@ -106,6 +106,25 @@ PP_API int pp_voxel_tv_adam(const pp_dvgo_scene* scene, const void* vox_in, void
                             float beta2, float lr_density, float lr_k0, float eps, float tv_density,
                             float tv_k0, int dense_mode, pp_stream_t stream);
 
+/* ---- the whole step as ONE CUDA-graph launch ---------------------------------------------------------
+ * A trainer that reads the loss of every step (lib/recon_scene.py:655-700 does: psnr, logging) pays the launch
+ * latency of every stream operation of the step.  pp_dvgo_step_graph_create captures
+ *     rays_host (pinned, [3,N,3] = origins | directions | target colours)  ->  rays_dev      (H2D copy)
+ *     loss_dev[0..1] = 0, pp_dvgo_train_step, pp_voxel_adam(adam_flags)                      (the step)
+ *     loss_dev -> loss_host (pinned, 2 floats: loss, photometric MSE)                        (D2H copy)
+ * once; pp_dvgo_step_graph_launch replays it as one launch on `stream` after patching the two things that change
+ * per step: the pinned buffer the rays come from (null = same as last time) and Adam's step sizes for optimiser
+ * step `step` (1-based; same host arithmetic as pp_voxel_adam, so replay and eager calls give the same update).
+ * The caller synchronises the stream (or an event) before reading loss_host.  All device pointers must stay valid
+ * and fixed for the life of the graph; TV and the pose gradient are not part of it (use the eager calls). */
+PP_API int pp_dvgo_step_graph_create(const pp_dvgo_scene* scene, const pp_dvgo_loss* loss, void* vox,
+                                     void* grad_vox, void* exp_avg, void* exp_avg_sq, const float* rays_host,
+                                     float* rays_dev, int64_t n_rays, float* loss_dev, float* loss_host,
+                                     void* workspace, int64_t workspace_bytes, float beta1, float beta2,
+                                     float lr_density, float lr_k0, float eps, int adam_flags, void** graph_out);
+PP_API int pp_dvgo_step_graph_launch(void* graph, const float* rays_host, int32_t step, pp_stream_t stream);
+PP_API int pp_dvgo_step_graph_destroy(void* graph);
+
 /* ---- multi-GPU: ray-sharded replicas, voxel-sharded optimiser --------------------------------------
  * The reference is single-GPU; rays are independent, so each rank marches its own batch
  * into its own gradient records and the only exchange per step is the voxel gradient / parameter

@@ -23,7 +23,7 @@ def sources():
 
 def _digest():
     h = hashlib.sha256()
-    files = sorted(os.listdir(CSRC)) + ["../../include/poseprobe_b200.h"]
+    files = sorted(os.listdir(CSRC)) + ["../../include/poseprobe_b200.h", "../../include/poseprobe_b200_fused.h"]
     for f in files:
         p = os.path.join(CSRC, f)
         if os.path.isfile(p):

@@ -515,6 +515,17 @@ static int tune_env(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
+// a __device__ symbol has a different address on every device: resolved per device (like sm_count)
+static int ray_queue_base(unsigned int** out, const char* who) {
+  static unsigned int* queue_bases[64] = {nullptr};
+  int dev = 0;
+  PP_CHECK_CUDA(cudaGetDevice(&dev));
+  PP_REQUIRE(dev >= 0 && dev < 64, PP_ERR_UNSUPPORTED, "%s: device ordinal %d out of range", who, dev);
+  if (!queue_bases[dev]) PP_CHECK_CUDA(cudaGetSymbolAddress((void**)&queue_bases[dev], g_ray_queue));
+  *out = queue_bases[dev];
+  return PP_OK;
+}
+
 template <int kMode, bool kPoseGrad, int kMinBlocks>
 static int launch_march_occ(const pp_dvgo_scene* sc, const pp_dvgo_loss* ls, const void* vox,
                         const float* rays_o, const float* rays_d, int64_t n_rays, const float* target,
@@ -541,13 +552,10 @@ static int launch_march_occ(const pp_dvgo_scene* sc, const pp_dvgo_loss* ls, con
     PP_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // persistent grid: every resident warp pulls rays from a device-side queue
   static std::atomic<unsigned> next_slot{0};
-  // a __device__ symbol has a different address on every device: resolve it per device (like sm_count)
-  static unsigned int* queue_bases[64] = {nullptr};
-  int dev = 0;
-  PP_CHECK_CUDA(cudaGetDevice(&dev));
-  PP_REQUIRE(dev >= 0 && dev < 64, PP_ERR_UNSUPPORTED, "%s: device ordinal %d out of range", who, dev);
-  if (!queue_bases[dev]) PP_CHECK_CUDA(cudaGetSymbolAddress((void**)&queue_bases[dev], g_ray_queue));
-  unsigned int* queue = queue_bases[dev] + (next_slot.fetch_add(1) % kQueueSlots);
+  unsigned int* queue_base = nullptr;
+  const int qrc = ray_queue_base(&queue_base, who);
+  if (qrc != PP_OK) return qrc;
+  unsigned int* queue = queue_base + (next_slot.fetch_add(1) % kQueueSlots);
   PP_CHECK_CUDA(cudaMemsetAsync(queue, 0, sizeof(unsigned int), s));
   int per_sm = 0;
   PP_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, warps * 32, smem));
@@ -715,5 +723,198 @@ extern "C" int pp_voxel_tv_adam(const pp_dvgo_scene* scene, const void* vox_in, 
       scene->sx, scene->sy, scene->sz, adam_step_size(lr_density, beta1, beta2, step),
       adam_step_size(lr_k0, beta1, beta2, step), beta1, beta2, eps, tv_density / 6, tv_k0 / 6, dense_mode);
   PP_CHECK_LAUNCH("voxel_tv_adam");
+  return PP_OK;
+}
+
+// ---- one training step as one CUDA-graph launch ----------------------------------------------------------
+// The step of the coarse stage is five stream operations (ray batch host -> device, loss reset, ray-queue reset,
+// march, Adam) plus the loss read-back; issued one by one from the host they cost ~30 us of launch latency against a
+// 0.27 ms step whenever the caller reads the loss of every step (as the reference's trainer does).  Captured once
+// and replayed, the step is ONE launch; what changes from step to step - the pinned host buffer the rays come from
+// and Adam's bias-corrected step sizes (host-computed in float exactly as adam_upd_kernel.cu:72, so the graph
+// replay and the eager path give the same bits) - is patched into the instantiated graph before each launch.
+namespace pp {
+
+struct AdamArgs {
+  float4 *vox, *grad, *m4, *v4;
+  int64_t n;
+  float ss_density, ss_k0, b1, b2, eps;
+  int flags;
+};
+
+struct StepGraph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  cudaGraphNode_t h2d_node = nullptr, adam_node = nullptr;
+  cudaKernelNodeParams adam_params{};
+  AdamArgs adam{};
+  void* adam_argv[11];
+  float* rays_dev = nullptr;
+  const float* rays_host = nullptr;
+  size_t ray_bytes = 0;
+  float lr_density = 0.f, lr_k0 = 0.f, eps = 0.f;
+  int device = 0;
+  int kernels = 0;
+};
+
+static void step_graph_free(StepGraph* g) {
+  if (!g) return;
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  if (g->graph) cudaGraphDestroy(g->graph);
+  delete g;
+}
+
+}  // namespace pp
+
+extern "C" int pp_dvgo_step_graph_create(const pp_dvgo_scene* scene, const pp_dvgo_loss* loss, void* vox,
+                                         void* grad_vox, void* exp_avg, void* exp_avg_sq,
+                                         const float* rays_host, float* rays_dev, int64_t n_rays,
+                                         float* loss_dev, float* loss_host, void* workspace,
+                                         int64_t workspace_bytes, float beta1, float beta2, float lr_density,
+                                         float lr_k0, float eps, int adam_flags, void** graph_out) {
+  const int rc = check_scene(scene, "dvgo_step_graph_create");
+  if (rc != PP_OK) return rc;
+  PP_REQUIRE(graph_out, PP_ERR_INVALID_ARG, "dvgo_step_graph_create: graph_out is null");
+  *graph_out = nullptr;
+  PP_REQUIRE(n_rays > 0, PP_ERR_INVALID_ARG, "dvgo_step_graph_create: n_rays must be positive");
+  PP_REQUIRE(vox && grad_vox && exp_avg && exp_avg_sq && rays_host && rays_dev && loss_dev && loss_host,
+             PP_ERR_INVALID_ARG, "dvgo_step_graph_create: null pointer");
+  cudaPointerAttributes attr;
+  PP_CHECK_CUDA(cudaPointerGetAttributes(&attr, rays_host));
+  PP_REQUIRE(attr.type == cudaMemoryTypeHost, PP_ERR_INVALID_ARG,
+             "dvgo_step_graph_create: rays_host must be pinned host memory");
+  PP_CHECK_CUDA(cudaPointerGetAttributes(&attr, loss_host));
+  PP_REQUIRE(attr.type == cudaMemoryTypeHost, PP_ERR_INVALID_ARG,
+             "dvgo_step_graph_create: loss_host must be pinned host memory");
+  const int64_t n_voxels = (int64_t)scene->sx * scene->sy * scene->sz;
+  // everything with process-wide lazy state is touched before the capture starts
+  unsigned int* qb = nullptr;
+  const int qrc = ray_queue_base(&qb, "dvgo_step_graph_create");
+  if (qrc != PP_OK) return qrc;
+  (void)sm_count();
+
+  StepGraph* g = new StepGraph();
+  PP_CHECK_CUDA(cudaGetDevice(&g->device));
+  g->rays_dev = rays_dev;
+  g->rays_host = rays_host;
+  g->ray_bytes = (size_t)n_rays * 9 * sizeof(float);
+  g->lr_density = lr_density;
+  g->lr_k0 = lr_k0;
+  g->eps = eps;
+  cudaStream_t cap = nullptr;
+  cudaError_t e = cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    step_graph_free(g);
+    set_error("dvgo_step_graph_create: stream: %s", cudaGetErrorString(e));
+    return PP_ERR_CUDA;
+  }
+  const uint64_t launches0 = pp_launch_count();
+  int step_rc = PP_OK;
+  e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed);
+  if (e == cudaSuccess) {
+    e = cudaMemcpyAsync(rays_dev, rays_host, g->ray_bytes, cudaMemcpyHostToDevice, cap);
+    if (e == cudaSuccess) e = cudaMemsetAsync(loss_dev, 0, 2 * sizeof(float), cap);
+    if (e == cudaSuccess) {
+      step_rc = pp_dvgo_train_step(scene, loss, vox, rays_dev, rays_dev + 3 * n_rays, rays_dev + 6 * n_rays, n_rays,
+                                   grad_vox, nullptr, loss_dev, nullptr, workspace, workspace_bytes,
+                                   (pp_stream_t)cap);
+      if (step_rc == PP_OK)
+        step_rc = pp_voxel_adam(vox, grad_vox, exp_avg, exp_avg_sq, n_voxels, 1, beta1, beta2, lr_density, lr_k0, eps,
+                                adam_flags, (pp_stream_t)cap);
+    }
+    if (e == cudaSuccess && step_rc == PP_OK)
+      e = cudaMemcpyAsync(loss_host, loss_dev, 2 * sizeof(float), cudaMemcpyDeviceToHost, cap);
+    const cudaError_t e_end = cudaStreamEndCapture(cap, &g->graph);
+    if (e == cudaSuccess) e = e_end;
+  }
+  g->kernels = (int)(pp_launch_count() - launches0);
+  count_launch(-g->kernels);   // recorded, not launched: replays are counted in pp_dvgo_step_graph_launch
+  cudaStreamDestroy(cap);
+  if (step_rc != PP_OK) {
+    step_graph_free(g);
+    return step_rc;
+  }
+  if (e != cudaSuccess || !g->graph) {
+    step_graph_free(g);
+    set_error("dvgo_step_graph_create: capture failed: %s", cudaGetErrorString(e));
+    return PP_ERR_CUDA;
+  }
+  // locate the two nodes that are patched per launch
+  size_t n_nodes = 0;
+  cudaGraphNode_t nodes[32];
+  e = cudaGraphGetNodes(g->graph, nullptr, &n_nodes);
+  if (e == cudaSuccess && n_nodes <= 32) e = cudaGraphGetNodes(g->graph, nodes, &n_nodes);
+  if (e != cudaSuccess || n_nodes > 32) {
+    step_graph_free(g);
+    set_error("dvgo_step_graph_create: unexpected graph (%zu nodes): %s", n_nodes, cudaGetErrorString(e));
+    return PP_ERR_CUDA;
+  }
+  for (size_t i = 0; i < n_nodes; ++i) {
+    cudaGraphNodeType type;
+    if (cudaGraphNodeGetType(nodes[i], &type) != cudaSuccess) continue;
+    if (type == cudaGraphNodeTypeMemcpy) {
+      cudaMemcpy3DParms mp;
+      if (cudaGraphMemcpyNodeGetParams(nodes[i], &mp) == cudaSuccess && mp.dstPtr.ptr == (void*)rays_dev)
+        g->h2d_node = nodes[i];
+    } else if (type == cudaGraphNodeTypeKernel) {
+      cudaKernelNodeParams kp;
+      // the Adam pass is the kernel whose first two arguments are the parameter and gradient record arrays (the
+      // march takes the scene struct first)
+      if (cudaGraphKernelNodeGetParams(nodes[i], &kp) == cudaSuccess && kp.kernelParams &&
+          (kp.func == (void*)voxel_adam_kernel ||
+           (*(void**)kp.kernelParams[0] == vox && *(void**)kp.kernelParams[1] == grad_vox))) {
+        g->adam_node = nodes[i];
+        g->adam_params = kp;
+      }
+    }
+  }
+  if (!g->h2d_node || !g->adam_node) {
+    step_graph_free(g);
+    set_error("dvgo_step_graph_create: could not locate the %s node among %zu captured nodes",
+              g->h2d_node ? "Adam kernel" : "ray copy", n_nodes);
+    return PP_ERR_CUDA;
+  }
+  g->adam = AdamArgs{(float4*)vox, (float4*)grad_vox, (float4*)exp_avg, (float4*)exp_avg_sq, n_voxels,
+                     0.f, 0.f, beta1, beta2, eps, adam_flags};
+  void* argv[11] = {&g->adam.vox, &g->adam.grad, &g->adam.m4, &g->adam.v4, &g->adam.n, &g->adam.ss_density,
+                    &g->adam.ss_k0, &g->adam.b1, &g->adam.b2, &g->adam.eps, &g->adam.flags};
+  for (int i = 0; i < 11; ++i) g->adam_argv[i] = argv[i];
+  g->adam_params.kernelParams = g->adam_argv;
+  g->adam_params.extra = nullptr;
+  e = cudaGraphInstantiate(&g->exec, g->graph, 0);
+  if (e != cudaSuccess) {
+    step_graph_free(g);
+    set_error("dvgo_step_graph_create: instantiate failed: %s", cudaGetErrorString(e));
+    return PP_ERR_CUDA;
+  }
+  *graph_out = g;
+  return PP_OK;
+}
+
+extern "C" int pp_dvgo_step_graph_launch(void* graph, const float* rays_host, int32_t step, pp_stream_t stream) {
+  StepGraph* g = static_cast<StepGraph*>(graph);
+  PP_REQUIRE(g && g->exec, PP_ERR_INVALID_ARG, "dvgo_step_graph_launch: null graph");
+  PP_REQUIRE(step >= 1, PP_ERR_INVALID_ARG, "dvgo_step_graph_launch: step counts from 1");
+  int dev = 0;
+  PP_CHECK_CUDA(cudaGetDevice(&dev));
+  PP_REQUIRE(dev == g->device, PP_ERR_INVALID_ARG, "dvgo_step_graph_launch: graph belongs to device %d, current is %d",
+             g->device, dev);
+  if (rays_host && rays_host != g->rays_host) {
+    PP_CHECK_CUDA(cudaGraphExecMemcpyNodeSetParams1D(g->exec, g->h2d_node, g->rays_dev, rays_host, g->ray_bytes,
+                                                     cudaMemcpyHostToDevice));
+    g->rays_host = rays_host;
+  }
+  // the same host arithmetic as pp_voxel_adam
+  g->adam.ss_density = adam_step_size(g->lr_density, g->adam.b1, g->adam.b2, step);
+  g->adam.ss_k0 = adam_step_size(g->lr_k0, g->adam.b1, g->adam.b2, step);
+  g->adam.eps = (g->adam.flags & 2) ? g->eps * sqrtf(1.f - powf(g->adam.b2, (float)step)) : g->eps;
+  PP_CHECK_CUDA(cudaGraphExecKernelNodeSetParams(g->exec, g->adam_node, &g->adam_params));
+  PP_CHECK_CUDA(cudaGraphLaunch(g->exec, as_stream(stream)));
+  count_launch(g->kernels);
+  return PP_OK;
+}
+
+extern "C" int pp_dvgo_step_graph_destroy(void* graph) {
+  step_graph_free(static_cast<StepGraph*>(graph));
   return PP_OK;
 }

@@ -353,3 +353,104 @@ def test_fused_dvgo_reference_adam_mode(pp):
     assert bool(untouched.any())
     with pytest.raises(NotImplementedError):
         pp.FusedDVGO(density.cuda(), k0.cuda(), mn, mx, stepsize=0.5, adam="reference", tv_density=0.1)
+
+
+@pytest.mark.parametrize("adam", ["masked", "reference"])
+def test_train_step_host_graph_equals_eager_steps(pp, adam):
+    """FusedDVGO.train_step_host (pinned rays in, step, pinned loss out as ONE CUDA-graph launch, pp_dvgo_step_graph_*)
+    against the same steps issued eagerly on a second engine: same losses, same parameters after four steps fed from
+    DIFFERENT pinned buffers (the ray-copy node is re-pointed per launch, Adam's bias-corrected step sizes are patched
+    per step).  Gradient sums are unordered fp32 atomics in both engines, so equality is to rounding, not to the bit."""
+    G, N = 24, 512
+    density, k0 = synthetic.make_dvgo_grids(G)
+    mn, mx = [-1.0, -1, -1], [1.0, 1, 1]
+    kw = dict(stepsize=0.5, adam=adam, lr_density=0.1, lr_k0=0.05)
+    a = pp.FusedDVGO(density.cuda(), k0.cuda(), mn, mx, **kw)
+    b = pp.FusedDVGO(density.cuda(), k0.cuda(), mn, mx, **kw)
+    loss_host = torch.zeros(2).pin_memory()
+    before = pp.lib.pp_launch_count()
+    for step in range(4):
+        o, d, _ = synthetic.make_rays(N, seed=20 + step)
+        tgt = torch.rand(N, 3, generator=torch.Generator().manual_seed(30 + step))
+        packed = torch.stack([o, d, tgt]).pin_memory()          # a fresh pinned buffer every step
+        a.train_step_host(packed, loss_host)
+        torch.cuda.current_stream().synchronize()
+        want = b.train_step(o.cuda(), d.cuda(), tgt.cuda()).cpu()
+        close(loss_host, want, rtol=1e-5, atol=1e-7)
+        assert float(loss_host[0]) > 0
+    assert a.step == b.step == 4 and len(a._step_graphs) == 1
+    # replays are counted like eager launches (2 kernels per step on either engine)
+    assert pp.lib.pp_launch_count() - before == 4 * 2 + 4 * 2
+    for got, ref in zip(a.export_grids(), b.export_grids()):
+        diff = (got - ref).abs().flatten()
+        assert float(diff.quantile(0.999)) <= 1e-6, float(diff.quantile(0.999))
+        assert float(diff.max()) <= 2 * 0.1 * 4       # a gradient within rounding of zero may flip one Adam step
+    # the second batch size gets its own graph; unpinned input is rejected, nothing falls back to pageable copies
+    o, d, _ = synthetic.make_rays(64, seed=40)
+    small = torch.stack([o, d, torch.rand(64, 3)]).pin_memory()
+    a.train_step_host(small, loss_host)
+    torch.cuda.current_stream().synchronize()
+    assert len(a._step_graphs) == 2 and torch.isfinite(loss_host).all()
+    with pytest.raises(RuntimeError, match="pinned"):
+        a.train_step_host(torch.stack([o, d, torch.rand(64, 3)]), loss_host)
+    with pytest.raises(RuntimeError, match=r"\[3, N, 3\]"):
+        a.train_step_host(torch.zeros(2, 64, 3).pin_memory(), loss_host)
+
+
+def test_train_step_host_with_tv_runs_the_eager_sequence(pp):
+    """TV on: the step is not graph-captured (the TV + Adam pass ping-pongs the parameter buffers); train_step_host
+    issues copy-in, train_step, copy-out on the stream and gives train_step's numbers."""
+    G, N = 20, 256
+    density, k0 = synthetic.make_dvgo_grids(G)
+    mn, mx = [-1.0, -1, -1], [1.0, 1, 1]
+    a = pp.FusedDVGO(density.cuda(), k0.cuda(), mn, mx, stepsize=0.5, tv_density=0.1, tv_k0=0.1)
+    b = pp.FusedDVGO(density.cuda(), k0.cuda(), mn, mx, stepsize=0.5, tv_density=0.1, tv_k0=0.1)
+    o, d, _ = synthetic.make_rays(N, seed=3)
+    tgt = torch.rand(N, 3, generator=torch.Generator().manual_seed(4))
+    loss_host = torch.zeros(2).pin_memory()
+    a.train_step_host(torch.stack([o, d, tgt]).pin_memory(), loss_host)
+    torch.cuda.current_stream().synchronize()
+    close(loss_host, b.train_step(o.cuda(), d.cuda(), tgt.cuda()).cpu(), rtol=1e-5, atol=1e-7)
+    assert len(a._step_graphs) == 0
+    for got, ref in zip(a.export_grids(), b.export_grids()):
+        assert float((got - ref).abs().flatten().quantile(0.999)) <= 1e-6
+
+
+def test_host_pipeline_overlapped_steps_equal_eager_steps(pp):
+    """FusedDVGO.host_pipeline: the copy of batch k+1 is queued on the copy stream while step k runs, the host reads
+    the loss of step k while step k+1 runs.  Six steps with one batch of look-ahead must give the eager engine's losses
+    in order and its parameters; the slot discipline (depth steps in flight at most, result() before reuse) is
+    enforced."""
+    G, N = 24, 512
+    density, k0 = synthetic.make_dvgo_grids(G)
+    mn, mx = [-1.0, -1, -1], [1.0, 1, 1]
+    kw = dict(stepsize=0.5, lr_density=0.1, lr_k0=0.05)
+    a = pp.FusedDVGO(density.cuda(), k0.cuda(), mn, mx, **kw)
+    b = pp.FusedDVGO(density.cuda(), k0.cuda(), mn, mx, **kw)
+    batches = []
+    for step in range(6):
+        o, d, _ = synthetic.make_rays(N, seed=50 + step)
+        batches.append(torch.stack([o, d, torch.rand(N, 3, generator=torch.Generator().manual_seed(60 + step))]))
+    pinned = [t.pin_memory() for t in batches]
+    pipe = a.host_pipeline(N, depth=2)
+    with pytest.raises(RuntimeError, match="nothing in flight"):
+        pipe.result()
+    got = []
+    pipe.submit(pinned[0])
+    for k in range(6):
+        if k + 1 < 6:
+            pipe.submit(pinned[k + 1])
+        got.append(pipe.result())
+    assert not pipe.pending and a.step == 6
+    for k, blk in enumerate(batches):
+        want = b.train_step(blk[0].cuda(), blk[1].cuda(), blk[2].cuda()).cpu()
+        assert got[k][0] == pytest.approx(float(want[0]), rel=1e-5) and got[k][1] == pytest.approx(float(want[1]), rel=1e-5)
+    for x, y in zip(a.export_grids(), b.export_grids()):
+        assert float((x - y).abs().flatten().quantile(0.999)) <= 1e-6
+    pipe.submit(pinned[0])
+    pipe.submit(pinned[1])
+    with pytest.raises(RuntimeError, match="in flight"):
+        pipe.submit(pinned[2])
+    assert len(pipe.drain()) == 2
+    with pytest.raises(RuntimeError, match="pinned"):
+        pipe.submit(batches[0])
