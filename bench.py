@@ -331,6 +331,25 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(render_e2e_ms, op=dist.ReduceOp.MAX)
     render_e2e_ms = float(render_e2e_ms) / render_iters
+    # the same work as ONE call on host buffers (FusedDVGO.render_host): the chunks' copies in / out run on copy streams
+    # under the neighbouring chunks' kernels, one synchronisation at the end of the image
+    img_rays = torch.cat([hp[:2] for hp in host_packed] * (render_iters // N_BATCHES), dim=1).contiguous().pin_memory()
+    n_img = img_rays.shape[1]
+    img_rgb = torch.empty((n_img, 3)).pin_memory()
+    img_depth = torch.empty(n_img).pin_memory()
+    eng.render_host(img_rays, img_rgb, img_depth, chunk=RAYS)
+    host_ms = []
+    for _ in range(5):
+        barrier()
+        r0.record()
+        eng.render_host(img_rays, img_rgb, img_depth, chunk=RAYS)
+        r1.record()
+        barrier()
+        t = torch.tensor([r0.elapsed_time(r1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        host_ms.append(float(t))
+    render_host_ms = sorted(host_ms)[len(host_ms) // 2] / (n_img / RAYS)
     # keep the GPU busy a little longer so the clock sampler sees the loaded state (the timed region is short)
     t_end = time.perf_counter() + 0.6
     i = 0
@@ -433,10 +452,14 @@ def run_ours(args, rank, world, local_rank):
                    "frac_note": "ALGORITHMIC bytes (B_render = 48 N + 32 C M, every corner gather counted, no cache reuse) "
                                 "over the measured HBM copy peak: neighbouring samples of a ray share corners in L1 / L2, "
                                 "so the DRAM traffic is ~3x smaller and this ratio can exceed 1",
-                   "e2e": {"value": world * RAYS / (render_e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s",
-                           "ms_per_chunk": render_e2e_ms, "h2d_bytes_per_chunk": 2 * RAYS * 12,
+                   "e2e": {"value": world * RAYS / (render_host_ms * 1e-3) / 1e6, "unit": "Mrays/s",
+                           "ms_per_chunk": render_host_ms, "h2d_bytes_per_chunk": 2 * RAYS * 12,
                            "d2h_bytes_per_chunk": RAYS * 16,
-                           "what": "pinned host rays in, rgb + depth out to pinned host, synchronised per chunk"}},
+                           "what": "FusedDVGO.render_host: %d pinned host rays in, rgb + depth out to pinned host in one "
+                                   "call; chunk copies on copy streams under the neighbouring chunks' kernels, one "
+                                   "synchronisation per image" % n_img,
+                           "synchronised_per_chunk": {"value": world * RAYS / (render_e2e_ms * 1e-3) / 1e6,
+                                                      "ms_per_chunk": render_e2e_ms}}},
     }
     if exchange:
         line["exchange"] = exchange

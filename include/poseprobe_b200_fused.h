@@ -125,6 +125,17 @@ PP_API int pp_dvgo_step_graph_create(const pp_dvgo_scene* scene, const pp_dvgo_l
 PP_API int pp_dvgo_step_graph_launch(void* graph, const float* rays_host, int32_t step, pp_stream_t stream);
 PP_API int pp_dvgo_step_graph_destroy(void* graph);
 
+/* Forward render of rays that live in HOST memory, results into host memory, in ONE call: rays_host is pinned
+ * [2,N,3] (rays_o | rays_d), rgb_host pinned [N,3], depth_host / last_host (alphainv_last) pinned [N] or null.  The
+ * rays are marched `chunk` at a time on `stream`; chunk c+1's host->device copy and chunk c-1's device->host copy run
+ * on the library's two copy streams under chunk c's kernel (double-buffered device staging, event-ordered).  Returns
+ * once everything has landed in the host buffers.  This is lib/nvs_fun.py:60-90's chunked full-image loop
+ * (rays.split(8192) -> model(...) -> .cpu()) with the copies and the host round trips taken off the critical path.
+ * One call at a time per device (the staging blocks belong to the device, not to the call). */
+PP_API int pp_dvgo_render_host(const pp_dvgo_scene* scene, const void* vox, const float* rays_host, int64_t n_rays,
+                               int64_t chunk, float* rgb_host, float* depth_host, float* last_host,
+                               pp_stream_t stream);
+
 /* ---- multi-GPU: ray-sharded replicas, voxel-sharded optimiser --------------------------------------
  * The reference is single-GPU; rays are independent, so each rank marches its own batch
  * into its own gradient records and the only exchange per step is the voxel gradient / parameter

@@ -918,3 +918,108 @@ extern "C" int pp_dvgo_step_graph_destroy(void* graph) {
   step_graph_free(static_cast<StepGraph*>(graph));
   return PP_OK;
 }
+
+// ---- rendering rays that live in host memory ---------------------------------------------------------------
+// An image is marched in chunks; issued in line, every chunk pays its PCIe copies (24 B in, 12..20 B out per ray)
+// and a host round trip on top of a ~49 us kernel (8192 rays, config B).  Here chunk c+1's copy-in and chunk c-1's
+// copy-out run on two copy streams under chunk c's kernel (double-buffered staging blocks, event-ordered), and the
+// whole image is issued by this one call - ~8 driver calls per chunk from C instead of ~25 from an interpreter, which
+// is what keeps the issue rate above the kernel rate.
+namespace pp {
+
+struct RenderHostCtx {
+  cudaStream_t in = nullptr, out = nullptr;
+  cudaEvent_t copied[2] = {nullptr, nullptr}, marched[2] = {nullptr, nullptr}, landed[2] = {nullptr, nullptr};
+  float* rays[2] = {nullptr, nullptr};   // [2, chunk, 3]
+  float* outs[2] = {nullptr, nullptr};   // rgb [chunk,3] | depth [chunk] | last [chunk]
+  int64_t chunk = 0;
+};
+
+static int render_host_ctx(RenderHostCtx** out, int64_t chunk) {
+  static RenderHostCtx ctxs[64];
+  int dev = 0;
+  PP_CHECK_CUDA(cudaGetDevice(&dev));
+  PP_REQUIRE(dev >= 0 && dev < 64, PP_ERR_UNSUPPORTED, "dvgo_render_host: device ordinal %d out of range", dev);
+  RenderHostCtx& c = ctxs[dev];
+  if (!c.in) {
+    PP_CHECK_CUDA(cudaStreamCreateWithFlags(&c.in, cudaStreamNonBlocking));
+    PP_CHECK_CUDA(cudaStreamCreateWithFlags(&c.out, cudaStreamNonBlocking));
+    for (int j = 0; j < 2; ++j) {
+      PP_CHECK_CUDA(cudaEventCreateWithFlags(&c.copied[j], cudaEventDisableTiming));
+      PP_CHECK_CUDA(cudaEventCreateWithFlags(&c.marched[j], cudaEventDisableTiming));
+      PP_CHECK_CUDA(cudaEventCreateWithFlags(&c.landed[j], cudaEventDisableTiming));
+    }
+  }
+  if (c.chunk < chunk) {
+    // every earlier call ended with a synchronisation of the copy-out stream, so the old blocks are idle
+    for (int j = 0; j < 2; ++j) {
+      if (c.rays[j]) cudaFree(c.rays[j]);
+      if (c.outs[j]) cudaFree(c.outs[j]);
+      c.rays[j] = c.outs[j] = nullptr;
+    }
+    c.chunk = 0;
+    for (int j = 0; j < 2; ++j) {
+      PP_CHECK_CUDA(cudaMalloc((void**)&c.rays[j], (size_t)chunk * 6 * sizeof(float)));
+      PP_CHECK_CUDA(cudaMalloc((void**)&c.outs[j], (size_t)chunk * 5 * sizeof(float)));
+    }
+    c.chunk = chunk;
+  }
+  *out = &c;
+  return PP_OK;
+}
+
+}  // namespace pp
+
+extern "C" int pp_dvgo_render_host(const pp_dvgo_scene* scene, const void* vox, const float* rays_host,
+                                   int64_t n_rays, int64_t chunk, float* rgb_host, float* depth_host,
+                                   float* last_host, pp_stream_t stream) {
+  const int rc = check_scene(scene, "dvgo_render_host");
+  if (rc != PP_OK) return rc;
+  PP_REQUIRE(n_rays >= 0, PP_ERR_INVALID_ARG, "dvgo_render_host: n_rays < 0");
+  if (n_rays == 0) return PP_OK;
+  PP_REQUIRE(chunk > 0, PP_ERR_INVALID_ARG, "dvgo_render_host: chunk must be positive");
+  PP_REQUIRE(vox && rays_host && rgb_host, PP_ERR_INVALID_ARG, "dvgo_render_host: null pointer");
+  const void* host_ptrs[4] = {rays_host, rgb_host, depth_host, last_host};
+  for (int i = 0; i < 4; ++i) {
+    if (!host_ptrs[i]) continue;
+    cudaPointerAttributes attr;
+    PP_CHECK_CUDA(cudaPointerGetAttributes(&attr, host_ptrs[i]));
+    PP_REQUIRE(attr.type == cudaMemoryTypeHost, PP_ERR_INVALID_ARG,
+               "dvgo_render_host: host buffer %d is not pinned host memory (no pageable staging here)", i);
+  }
+  if (chunk > n_rays) chunk = n_rays;
+  RenderHostCtx* cx = nullptr;
+  const int crc = render_host_ctx(&cx, chunk);
+  if (crc != PP_OK) return crc;
+  cudaStream_t s = as_stream(stream);
+  int64_t c = 0;
+  for (int64_t c0 = 0; c0 < n_rays; c0 += chunk, ++c) {
+    const int j = (int)(c & 1);
+    const int64_t m = min64(chunk, n_rays - c0);
+    float* o_dev = cx->rays[j];
+    float* d_dev = cx->rays[j] + 3 * cx->chunk;
+    float* rgb_dev = cx->outs[j];
+    float* depth_dev = cx->outs[j] + 3 * cx->chunk;
+    float* last_dev = cx->outs[j] + 4 * cx->chunk;
+    PP_CHECK_CUDA(cudaStreamWaitEvent(cx->in, cx->marched[j], 0));   // the kernel that last read this block
+    PP_CHECK_CUDA(cudaMemcpyAsync(o_dev, rays_host + 3 * c0, (size_t)m * 12, cudaMemcpyHostToDevice, cx->in));
+    PP_CHECK_CUDA(cudaMemcpyAsync(d_dev, rays_host + 3 * (n_rays + c0), (size_t)m * 12, cudaMemcpyHostToDevice, cx->in));
+    PP_CHECK_CUDA(cudaEventRecord(cx->copied[j], cx->in));
+    PP_CHECK_CUDA(cudaStreamWaitEvent(s, cx->copied[j], 0));
+    PP_CHECK_CUDA(cudaStreamWaitEvent(s, cx->landed[j], 0));         // the copy-out that last read these outputs
+    const int mrc = launch_march<kModeForward, false>(scene, nullptr, vox, o_dev, d_dev, m, nullptr, nullptr, nullptr,
+                                                      nullptr, rgb_dev, last_dev, depth_host ? depth_dev : nullptr,
+                                                      nullptr, nullptr, nullptr, nullptr, 0, s, "dvgo_render_host");
+    if (mrc != PP_OK) return mrc;
+    PP_CHECK_CUDA(cudaEventRecord(cx->marched[j], s));
+    PP_CHECK_CUDA(cudaStreamWaitEvent(cx->out, cx->marched[j], 0));
+    PP_CHECK_CUDA(cudaMemcpyAsync(rgb_host + 3 * c0, rgb_dev, (size_t)m * 12, cudaMemcpyDeviceToHost, cx->out));
+    if (depth_host)
+      PP_CHECK_CUDA(cudaMemcpyAsync(depth_host + c0, depth_dev, (size_t)m * 4, cudaMemcpyDeviceToHost, cx->out));
+    if (last_host)
+      PP_CHECK_CUDA(cudaMemcpyAsync(last_host + c0, last_dev, (size_t)m * 4, cudaMemcpyDeviceToHost, cx->out));
+    PP_CHECK_CUDA(cudaEventRecord(cx->landed[j], cx->out));
+  }
+  PP_CHECK_CUDA(cudaStreamSynchronize(cx->out));
+  return PP_OK;
+}

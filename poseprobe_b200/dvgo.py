@@ -545,6 +545,30 @@ class FusedDVGO:
         self.optimizer_step()
         return self.loss_buf
 
+    def render_host(self, rays_host, rgb_host, depth_host=None, last_host=None, chunk=8192):
+        """Render rays that live in HOST memory into host buffers: `rays_host` pinned float32 [2, N, 3] (rays_o,
+        rays_d), `rgb_host` pinned [N, 3], optional `depth_host` / `last_host` (alphainv_last) pinned [N].  One call
+        of pp_dvgo_render_host: the rays are marched in chunks, chunk c+1's host -> device copy and chunk c-1's
+        device -> host copy run on copy streams under chunk c's kernel, so a full image costs the kernels plus one
+        chunk's copies, not their sum.  Returns after everything has landed in the host buffers."""
+        if rays_host.dim() != 3:
+            raise RuntimeError("render_host: rays_host must have shape [2, N, 3]")
+        n = int(rays_host.shape[1])
+        for t, nme, shape in ((rays_host, "rays_host", (2, n, 3)), (rgb_host, "rgb_host", (n, 3)),
+                              (depth_host, "depth_host", (n,)), (last_host, "last_host", (n,))):
+            if t is None:
+                continue
+            if t.dtype != torch.float32 or tuple(t.shape) != shape or not t.is_contiguous() or t.is_cuda or \
+                    (n > 0 and not t.is_pinned()):
+                raise RuntimeError("render_host: %s must be a pinned contiguous float32 host tensor of shape %s"
+                                   % (nme, list(shape)))
+        if n == 0:
+            return
+        with torch.cuda.device(self.device):
+            check(lib.pp_dvgo_render_host(ctypes.byref(self.scene), ptr(self.vox), ptr(rays_host), n, int(chunk),
+                                          ptr(rgb_host), ptr(depth_host), ptr(last_host), stream()),
+                  "dvgo_render_host")
+
     def host_pipeline(self, n_rays, depth=2):
         """-> HostPipeline: host-fed steps with the PCIe copies overlapped with the step in flight."""
         return HostPipeline(self, n_rays, depth)

@@ -454,3 +454,30 @@ def test_host_pipeline_overlapped_steps_equal_eager_steps(pp):
     assert len(pipe.drain()) == 2
     with pytest.raises(RuntimeError, match="pinned"):
         pipe.submit(batches[0])
+
+
+def test_render_host_chunk_pipeline_equals_device_render(pp):
+    """FusedDVGO.render_host (pinned rays in, pinned rgb / depth / alphainv_last out, chunk copies on copy streams under
+    the neighbouring chunks' kernels) against one device-resident render of the same rays: bit-equal (the forward march
+    has no atomics), for a ray count that is not a multiple of the chunk, repeated calls on the same streams, a
+    larger chunk afterwards, and no rays at all."""
+    G, N = 24, 1000
+    density, k0 = synthetic.make_dvgo_grids(G)
+    eng = pp.FusedDVGO(density.cuda() * 3 + 2, k0.cuda(), [-1.0, -1, -1], [1.0, 1, 1], stepsize=0.5)
+    o, d, _ = synthetic.make_rays(N, seed=9)
+    rgb, last, depth, _ = eng.render(o.cuda(), d.cuda(), want_depth=True)
+    rays_host = torch.stack([o, d]).pin_memory()
+    for chunk in (256, 256, 4096):
+        rgb_h = torch.full((N, 3), -1.0).pin_memory()
+        depth_h = torch.full((N,), -1.0).pin_memory()
+        last_h = torch.full((N,), -1.0).pin_memory()
+        eng.render_host(rays_host, rgb_h, depth_h, last_h, chunk=chunk)
+        assert torch.equal(rgb_h, rgb.cpu()) and torch.equal(depth_h, depth.cpu()) and torch.equal(last_h, last.cpu())
+    rgb_only = torch.full((N, 3), -1.0).pin_memory()
+    eng.render_host(rays_host, rgb_only, chunk=300)
+    assert torch.equal(rgb_only, rgb.cpu())
+    eng.render_host(torch.zeros(2, 0, 3).pin_memory(), torch.zeros(0, 3).pin_memory())
+    with pytest.raises(RuntimeError, match="pinned"):
+        eng.render_host(torch.stack([o, d]), rgb_only)
+    with pytest.raises(RuntimeError, match="shape"):
+        eng.render_host(rays_host, torch.zeros(N - 1, 3).pin_memory())
