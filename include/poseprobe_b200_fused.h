@@ -107,8 +107,12 @@ PP_API int pp_voxel_tv_adam(const pp_dvgo_scene* scene, const void* vox_in, void
                             float tv_k0, int dense_mode, pp_stream_t stream);
 
 /* ---- the whole step as ONE CUDA-graph launch ---------------------------------------------------------
- * A trainer that reads the loss of every step (lib/recon_scene.py:655-700 does: psnr, logging) pays the launch
- * latency of every stream operation of the step.  pp_dvgo_step_graph_create captures
+ * A trainer that reads the loss of every step (lib/recon_scene.py:607 does: `mse2psnr(...).item()`) issues six stream
+ * operations per 0.27 ms step; a host that is slow to issue them (an interpreter busy with the rest of the trainer)
+ * leaves the GPU waiting.  Captured once, the step is ONE launch.  Measured on an otherwise idle host (B200, config B,
+ * profiles/r2_results.md section 8): 0.301 ms per step against 0.300 ms for the eager sequence - there the ~30 us
+ * between steps is the PCIe copy plus the host round trip, which the look-ahead form (HostPipeline in dvgo.py:
+ * next batch copied on a copy stream under the step in flight) hides: 0.275 ms.  pp_dvgo_step_graph_create captures
  *     rays_host (pinned, [3,N,3] = origins | directions | target colours)  ->  rays_dev      (H2D copy)
  *     loss_dev[0..1] = 0, pp_dvgo_train_step, pp_voxel_adam(adam_flags)                      (the step)
  *     loss_dev -> loss_host (pinned, 2 floats: loss, photometric MSE)                        (D2H copy)
@@ -129,8 +133,9 @@ PP_API int pp_dvgo_step_graph_destroy(void* graph);
  * [2,N,3] (rays_o | rays_d), rgb_host pinned [N,3], depth_host / last_host (alphainv_last) pinned [N] or null.  The
  * rays are marched `chunk` at a time on `stream`; chunk c+1's host->device copy and chunk c-1's device->host copy run
  * on the library's two copy streams under chunk c's kernel (double-buffered device staging, event-ordered).  Returns
- * once everything has landed in the host buffers.  This is lib/nvs_fun.py:60-90's chunked full-image loop
- * (rays.split(8192) -> model(...) -> .cpu()) with the copies and the host round trips taken off the critical path.
+ * once everything has landed in the host buffers.  This is lib/nvs_fun.py:83-91's chunked full-image loop
+ * (rays.split(4096) -> model.inference(...) -> torch.cat -> .cpu()) with the copies and the host round trips taken off
+ * the critical path.
  * One call at a time per device (the staging blocks belong to the device, not to the call). */
 PP_API int pp_dvgo_render_host(const pp_dvgo_scene* scene, const void* vox, const float* rays_host, int64_t n_rays,
                                int64_t chunk, float* rgb_host, float* depth_host, float* last_host,

@@ -728,9 +728,11 @@ extern "C" int pp_voxel_tv_adam(const pp_dvgo_scene* scene, const void* vox_in, 
 
 // ---- one training step as one CUDA-graph launch ----------------------------------------------------------
 // The step of the coarse stage is five stream operations (ray batch host -> device, loss reset, ray-queue reset,
-// march, Adam) plus the loss read-back; issued one by one from the host they cost ~30 us of launch latency against a
-// 0.27 ms step whenever the caller reads the loss of every step (as the reference's trainer does).  Captured once
-// and replayed, the step is ONE launch; what changes from step to step - the pinned host buffer the rays come from
+// march, Adam) plus the loss read-back, issued one by one from the host whenever the caller reads the loss of every
+// step (as the reference's trainer does).  Captured once and replayed, the step is ONE launch - for hosts that are
+// slow to issue (measured on an idle host: no gain, 0.301 vs 0.300 ms; the gap to the device-resident 0.269 ms is
+// the PCIe copy and the host round trip, which dvgo.py's HostPipeline hides instead).  What changes from step to
+// step - the pinned host buffer the rays come from
 // and Adam's bias-corrected step sizes (host-computed in float exactly as adam_upd_kernel.cu:72, so the graph
 // replay and the eager path give the same bits) - is patched into the instantiated graph before each launch.
 namespace pp {

@@ -577,9 +577,11 @@ class FusedDVGO:
         """One optimisation step fed from HOST memory: `rays_host` is a pinned float32 [3, N, 3] block (rays_o,
         rays_d, target colours), `loss_host` a pinned float32 [2] that receives (loss, photometric MSE) - valid once
         the current stream has been synchronised.  The copy in, the step and the copy out are ONE CUDA-graph launch
-        (pp_dvgo_step_graph_*): a trainer that reads the loss of every step, as lib/recon_scene.py:655-700 does,
-        otherwise pays the launch latency of six stream operations per 0.27 ms step.  Same arithmetic as
-        train_step.  With TV or the pose gradient switched on the step is issued eagerly instead."""
+        (pp_dvgo_step_graph_*) for a trainer that reads the loss of every step, as lib/recon_scene.py:607 does
+        (`.item()`), from a host that is slow to issue the six stream operations of the step.  On an idle host it
+        measures the same as the eager sequence (0.301 vs 0.300 ms at config B); the form that removes the copy and
+        the host round trip from the critical path is host_pipeline() (0.275 ms).  Same arithmetic as train_step.
+        With TV or the pose gradient switched on the step is issued eagerly instead."""
         if not (rays_host.is_pinned() and loss_host.is_pinned()):
             raise RuntimeError("train_step_host: rays_host and loss_host must be pinned host tensors")
         if rays_host.dtype != torch.float32 or rays_host.dim() != 3 or rays_host.shape[0] != 3 or \
