@@ -148,6 +148,39 @@ def test_c_abi_argument_validation():
     assert lib.pp_adam_upd(0, 4, None, None, None, None, None, 4, 1, 0.9, 0.99, 0.1, 1e-8, None) == -1   # modes 0..3
 
 
+def test_host_fed_entry_points_validate_before_touching_the_device():
+    """pp_dvgo_render_host / pp_dvgo_step_graph_*: extents, null pointers and the scene are checked before any CUDA
+    call; empty work is a no-op; a null graph is rejected, destroying one is harmless."""
+    import ctypes
+    from poseprobe_b200 import _lib, dvgo
+    lib = _lib.lib
+    sc = dvgo.make_scene((8, 8, 8), [-1.0, -1, -1], [1.0, 1, 1], 0.2, 1e9, 0.125, -4.6, 0.5, 0.0, 0.0)
+    bad = dvgo.make_scene((8, 8, 8), [-1.0, -1, -1], [1.0, -1, 1], 0.2, 1e9, 0.125, -4.6, 0.5, 0.0, 0.0)
+    ref = ctypes.byref
+    assert lib.pp_dvgo_render_host(ref(sc), None, None, 0, 8192, None, None, None, None) == 0          # no rays: no-op
+    assert lib.pp_dvgo_render_host(ref(sc), None, None, -1, 8192, None, None, None, None) == -1
+    assert lib.pp_dvgo_render_host(ref(sc), None, None, 16, 0, None, None, None, None) == -1
+    assert b"chunk" in lib.pp_last_error()
+    assert lib.pp_dvgo_render_host(ref(sc), None, None, 16, 8, None, None, None, None) == -1
+    assert b"null pointer" in lib.pp_last_error()
+    assert lib.pp_dvgo_render_host(ref(bad), None, None, 16, 8, None, None, None, None) == -1
+    assert b"bounding box" in lib.pp_last_error()
+    assert lib.pp_dvgo_render_host(None, None, None, 16, 8, None, None, None, None) == -1
+    out = ctypes.c_void_p()
+    args = (None, None, None, None, None, None)
+    assert lib.pp_dvgo_step_graph_create(ref(sc), None, *args, 16, None, None, None, 0, 0.9, 0.99, 0.1, 0.1, 1e-8, 1,
+                                         None) == -1
+    assert b"graph_out" in lib.pp_last_error()
+    assert lib.pp_dvgo_step_graph_create(ref(sc), None, *args, 0, None, None, None, 0, 0.9, 0.99, 0.1, 0.1, 1e-8, 1,
+                                         ref(out)) == -1
+    assert b"n_rays" in lib.pp_last_error()
+    assert lib.pp_dvgo_step_graph_create(ref(sc), None, *args, 16, None, None, None, 0, 0.9, 0.99, 0.1, 0.1, 1e-8, 1,
+                                         ref(out)) == -1
+    assert b"null pointer" in lib.pp_last_error() and out.value is None
+    assert lib.pp_dvgo_step_graph_launch(None, None, 1, None) == -1
+    assert lib.pp_dvgo_step_graph_destroy(None) == 0
+
+
 def test_maskcache_loads_a_reference_style_checkpoint(tmp_path):
     """dvgo.MaskCache(path=...) reads checkpoints as the reference writes them (numpy arrays in MaskCache_kwargs,
     lib/dvgo_ori.py:143-152, :436-451); construction is host logic only."""
