@@ -1,8 +1,10 @@
 """A/B timing of the coarse march's tuning switches at BASELINE configs[1] (160^3, 8192 rays) in ONE process.
 
-The C library reads PP_MARCH_WIDE / PP_MARCH_FLAGS / PP_MARCH_OCC with getenv at every launch, so the variants are
-alternated block by block on the same grids and rays (same clocks, same L2 state): per variant the median of the
-block times of the march kernel alone (fwd + loss + bwd in one launch) and of the whole step (march + masked Adam).
+The C library reads PP_MARCH_FLAGS / PP_MARCH_OCC (and, with profiles/r2_march_wide_stash_experiment.patch applied,
+PP_MARCH_WIDE) with getenv at every launch, so the variants are alternated block by block on the same grids and rays
+(same clocks, same L2 state): per variant the median of the block times of the march kernel alone (fwd + loss + bwd
+in one launch) and of the whole step (march + masked Adam).  Without the patch the PP_MARCH_WIDE rows repeat the
+shipped kernel.  profiles/r2_ab_march.md is this tool's output with the patch applied.
 Usage: python tools/ab_march.py [blocks] ; prints one markdown table.
 """
 import os
